@@ -1,0 +1,158 @@
+/* sfmgpu.h — C ABI of libsfmgpu.so: the B200 (sm_100a) front end of the SfM pipeline.
+ *
+ * Drop-in boundary for the data-parallel front end of RoozbehSanaei/Structure-from-Motion-3D-Reconstruction
+ * (reference citations are relative to cpp/src/templering_sfm.cpp unless a header is named):
+ *   build_pyr :224-232, shi_tomasi :237-302, KLTTracker :323-466, sampson_err/find_E_ransac scoring loop
+ *   :629-638 / :664-677, two-view front end :1836-1857.
+ * The reference has no FFI: its hot functions are file-static.  These entry points are what a binding
+ * for that path would call; the C++ source-compatible shim that re-creates the reference's own names on
+ * top of them is host/sfmgpu_shim.hpp.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns 0 on success or a negative sfmgpu_status;
+ *     sfmgpu_last_error(ctx) gives the message.  No exceptions cross the boundary.
+ *   - the caller owns host buffers; the library owns device memory and pinned staging.
+ *   - one context = one CUDA device + one stream; calls on a context are stream-ordered; functions that
+ *     take host output pointers return after the results are in those buffers.
+ *   - there is no CPU fallback anywhere: without a usable B200 every call fails with SFMGPU_E_CUDA.
+ *   - images are 8-bit, row-major, stride = w on the host side (GrayImage, cpp/include/pgm_io.hpp:10-15);
+ *     points are (x, y) double pairs (Vec2, cpp/include/linalg.hpp:15-17); 3x3 matrices are 9 doubles
+ *     row-major (Mat33, linalg.hpp:25-35).
+ */
+#ifndef SFMGPU_H_
+#define SFMGPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFMGPU_VERSION 100
+
+typedef enum sfmgpu_status {
+  SFMGPU_OK = 0,
+  SFMGPU_E_ARG = -1,      /* invalid argument */
+  SFMGPU_E_CUDA = -2,     /* CUDA runtime / driver failure (including "no device") */
+  SFMGPU_E_CAPACITY = -3, /* a caller- or batch-sized buffer was too small; nothing was truncated silently */
+  SFMGPU_E_STATE = -4     /* call sequence error (e.g. pyramid not built) */
+} sfmgpu_status;
+
+typedef struct sfmgpu_ctx sfmgpu_ctx;
+typedef struct sfmgpu_frames sfmgpu_frames;   /* F frames of one size + their pyramids, resident in HBM */
+typedef struct sfmgpu_pairs sfmgpu_pairs;     /* device-resident results of a batch of frame pairs */
+typedef struct sfmgpu_tracker sfmgpu_tracker; /* stateful KLTTracker twin */
+
+/* LKConfig, :307-316 (same field meaning and defaults). */
+typedef struct sfmgpu_lkcfg {
+  int max_tracks;    /* 2200 */
+  int min_tracks;    /* 900  */
+  double quality;    /* 0.01 */
+  int min_distance;  /* 8    */
+  int pyr_levels;    /* 3    */
+  int win_radius;    /* 5    */
+  int iters;         /* 10   */
+  double fb_thresh;  /* 1.0  */
+} sfmgpu_lkcfg;
+
+void sfmgpu_lkcfg_default(sfmgpu_lkcfg* cfg);
+
+/* ---- context ------------------------------------------------------------------------------------ */
+int sfmgpu_version(void);
+int sfmgpu_create(int device, sfmgpu_ctx** out);
+void sfmgpu_destroy(sfmgpu_ctx* ctx);
+const char* sfmgpu_last_error(sfmgpu_ctx* ctx);
+int sfmgpu_sync(sfmgpu_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+long long sfmgpu_launch_count(sfmgpu_ctx* ctx);
+/* CUDA-event timer on the context's stream: start, ..., stop -> elapsed milliseconds. */
+int sfmgpu_timer_start(sfmgpu_ctx* ctx);
+int sfmgpu_timer_stop(sfmgpu_ctx* ctx, float* ms);
+/* Write `bytes` of device memory (L2 flush between timed iterations). */
+int sfmgpu_flush_l2(sfmgpu_ctx* ctx, size_t bytes);
+/* Pinned host memory for callers that want asynchronous uploads. */
+int sfmgpu_host_alloc(sfmgpu_ctx* ctx, size_t bytes, void** out);
+int sfmgpu_host_free(sfmgpu_ctx* ctx, void* p);
+
+/* ---- frames + pyramid: GrayImage / Pyramid / build_pyr / downsample2 (:200-232) ------------------ */
+/* Storage for `nframes` images of w x h with `levels` pyramid levels (level 0 = the image itself). */
+int sfmgpu_frames_create(sfmgpu_ctx* ctx, int w, int h, int nframes, int levels, sfmgpu_frames** out);
+void sfmgpu_frames_destroy(sfmgpu_ctx* ctx, sfmgpu_frames* f);
+/* Host -> level 0 of frames [first, first+count); host_pix = count images, each w*h bytes, stride w. */
+int sfmgpu_frames_upload(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first, int count, const uint8_t* host_pix);
+/* Same from device memory (row pitch in bytes). */
+int sfmgpu_frames_upload_device(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first, int count, const uint8_t* dev_pix,
+                                size_t pitch);
+/* Integer synthetic generator (sfmgpu/synth.py twin): frame first+k gets time index t0+k of sequence seed. */
+int sfmgpu_frames_synth(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first, int count, uint32_t seed, int t0);
+/* build_pyr for frames [first, first+count): fills levels 1..levels-1 (one fused launch per 2 levels). */
+int sfmgpu_pyramid_build(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first, int count);
+/* Level geometry and download (parity checks): out = w_l*h_l bytes, stride w_l. */
+int sfmgpu_frames_level_size(const sfmgpu_frames* f, int level, int* w, int* h);
+int sfmgpu_frames_download(sfmgpu_ctx* ctx, sfmgpu_frames* f, int frame, int level, uint8_t* host_out);
+
+/* ---- corners: shi_tomasi (:237-302) ---------------------------------------------------------------- */
+/* Raster-ordered candidate list {s >= max*quality} of one frame (:274-285): pixel (x,y) and exact score.
+ * Returns SFMGPU_E_CAPACITY (with *n_out = required size) when cap is too small. */
+int sfmgpu_corner_candidates(sfmgpu_ctx* ctx, sfmgpu_frames* f, int frame, double quality, int32_t* xy,
+                             double* score, int cap, int* n_out, double* max_score);
+/* Full shi_tomasi: corners in acceptance order, integer-valued doubles; xy_out holds max_corners pairs. */
+int sfmgpu_corners(sfmgpu_ctx* ctx, sfmgpu_frames* f, int frame, int max_corners, double quality, int min_dist,
+                   double* xy_out, int* n_out);
+/* The libstdc++ std::sort permutation (:286) of n keys sorted descending, computed on the device:
+ * perm[i] = original index of the element that std::sort leaves at position i. */
+int sfmgpu_sort_perm_desc(sfmgpu_ctx* ctx, const double* keys, int n, int32_t* perm);
+
+/* ---- KLT: track_one / lk_step / sample_bilinear (:183-198, :396-460) ------------------------------- */
+/* Forward track frame a -> b and backward b -> a for n points (what :356-361 and :1846-1848 do per
+ * track).  p1 = forward result, p0_back = backward result; n_iters (optional) = LK iterations executed. */
+int sfmgpu_klt_track(sfmgpu_ctx* ctx, sfmgpu_frames* f, int frame_a, int frame_b, const double* p0_xy, int n,
+                     int win_radius, int iters, double* p1_xy, double* p0_back_xy, int32_t* n_iters);
+
+/* ---- stateless two-view front end over a batch of pairs (:1836-1857) -------------------------------- */
+/* For every pair (first_frame+k, first_frame+k+1), k < npairs: pyramids must be built; detect up to
+ * cfg->max_tracks corners on the first frame, track fwd/bwd, keep iff !(fb >= fb_thresh).
+ * Results stay on the device in `out` (create once, reuse). */
+int sfmgpu_pairs_create(sfmgpu_ctx* ctx, int max_pairs, int max_corners, sfmgpu_pairs** out);
+void sfmgpu_pairs_destroy(sfmgpu_ctx* ctx, sfmgpu_pairs* p);
+int sfmgpu_pair_frontend(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int npairs, const sfmgpu_lkcfg* cfg,
+                         sfmgpu_pairs* out);
+/* Totals over the last batch: corners detected (= tracks attempted), survivors, LK iterations. */
+int sfmgpu_pairs_totals(sfmgpu_ctx* ctx, sfmgpu_pairs* p, long long* n_corners, long long* n_kept,
+                        long long* n_lk_iters);
+/* One pair's results: survivors in corner order.  li/lj = (x,y) in first/second frame, cap pairs each. */
+int sfmgpu_pairs_download(sfmgpu_ctx* ctx, sfmgpu_pairs* p, int pair, double* li_xy, double* lj_xy, int cap,
+                          int* n_kept, int* n_corners);
+
+/* ---- stateful tracker: KLTTracker (:323-391) ---------------------------------------------------------- */
+int sfmgpu_tracker_create(sfmgpu_ctx* ctx, const sfmgpu_lkcfg* cfg, sfmgpu_tracker** out);
+void sfmgpu_tracker_destroy(sfmgpu_ctx* ctx, sfmgpu_tracker* t);
+/* reset(gray) :327-332 */
+int sfmgpu_tracker_reset(sfmgpu_ctx* ctx, sfmgpu_tracker* t, const uint8_t* host_pix, int w, int h);
+/* step(gray) :340-391.  Survivors (prev, cur, id) in track order; *n_out = 0 on the first frame. */
+int sfmgpu_tracker_step(sfmgpu_ctx* ctx, sfmgpu_tracker* t, const uint8_t* host_pix, int w, int h,
+                        double* prev_xy, double* cur_xy, int32_t* ids, int cap, int* n_out);
+/* Same with the frame already resident (frame index into `f`, pyramid built): no H2D in the step. */
+int sfmgpu_tracker_step_frames(sfmgpu_ctx* ctx, sfmgpu_tracker* t, sfmgpu_frames* f, int frame, double* prev_xy,
+                               double* cur_xy, int32_t* ids, int cap, int* n_out);
+/* tracks() :393 */
+int sfmgpu_tracker_tracks(sfmgpu_ctx* ctx, sfmgpu_tracker* t, double* xy, int32_t* ids, int cap, int* n_out);
+/* Sum of track-list sizes entering step() so far, and LK iterations executed. */
+int sfmgpu_tracker_totals(sfmgpu_ctx* ctx, sfmgpu_tracker* t, long long* n_track_steps, long long* n_lk_iters);
+
+/* ---- RANSAC scoring: sampson_err + the loop at :667-676 ------------------------------------------------- */
+/* xi/xj: n normalised correspondences; E: H hypotheses, 9 doubles each.  counts[h] = #{i : e_i < thr};
+ * best_h = lowest h with the largest count (-1 when every count is 0); best_inl = its inlier indices
+ * ascending (n ints of room), best_n their number.  counts may be NULL. */
+int sfmgpu_ransac_score(sfmgpu_ctx* ctx, const double* xi_xy, const double* xj_xy, int n, const double* E, int H,
+                        double thr, int32_t* counts, int* best_h, int32_t* best_inl, int* best_n);
+/* Device-resident variant for throughput runs: upload once, score many times. */
+int sfmgpu_ransac_upload(sfmgpu_ctx* ctx, const double* xi_xy, const double* xj_xy, int n, const double* E, int H);
+int sfmgpu_ransac_score_resident(sfmgpu_ctx* ctx, double thr, int* best_h, int* best_n);
+int sfmgpu_ransac_download(sfmgpu_ctx* ctx, int32_t* counts, int32_t* best_inl, int cap_inl);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFMGPU_H_ */

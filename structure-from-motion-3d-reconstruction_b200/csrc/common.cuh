@@ -1,0 +1,122 @@
+// common.cuh — internal definitions shared by the sm_100a kernels of libsfmgpu.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/sfmgpu.h"
+
+#define SFM_MAXL 8        // pyramid levels supported by the by-value views
+#define SFM_NSM_FALLBACK 148
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+// By-value view of a frame batch handed to kernels: level l of frame f starts at base[l] + f*fstride[l].
+struct PyrView {
+  const uint8_t* base[SFM_MAXL];
+  int w[SFM_MAXL], h[SFM_MAXL], pitch[SFM_MAXL];
+  size_t fstride[SFM_MAXL];
+  int levels;
+};
+
+struct sfmgpu_frames {
+  int w = 0, h = 0, n = 0, levels = 0;
+  int lw[SFM_MAXL], lh[SFM_MAXL], pitch[SFM_MAXL];
+  size_t fstride[SFM_MAXL];
+  uint8_t* lvl[SFM_MAXL];
+  PyrView view() const {
+    PyrView v;
+    for (int l = 0; l < SFM_MAXL; l++) {
+      v.base[l] = l < levels ? lvl[l] : nullptr;
+      v.w[l] = l < levels ? lw[l] : 0;
+      v.h[l] = l < levels ? lh[l] : 0;
+      v.pitch[l] = l < levels ? pitch[l] : 0;
+      v.fstride[l] = l < levels ? fstride[l] : 0;
+    }
+    v.levels = levels;
+    return v;
+  }
+};
+
+struct sfmgpu_ctx {
+  int device = 0;
+  int n_sm = SFM_NSM_FALLBACK;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  long long launches = 0;
+  // scratch, grown on demand (never shrunk)
+  DevBuf flush;
+  DevBuf klt_in, klt_p1, klt_pb, klt_nit, klt_keep;
+  DevBuf cs_work;    // corner-score work area for single-frame calls
+  DevBuf sel_work;   // corner-select work area
+  DevBuf misc;       // small scalars
+  DevBuf rs_xi, rs_xj, rs_E, rs_counts, rs_inl, rs_best;
+  int rs_n = 0, rs_H = 0;
+  void* pinned = nullptr;  // staging for small D2H results
+  size_t pinned_cap = 0;
+};
+
+int sfm_fail(sfmgpu_ctx* ctx, int code, const char* fmt, ...);
+int sfm_reserve(sfmgpu_ctx* ctx, DevBuf& b, size_t bytes);
+int sfm_pinned(sfmgpu_ctx* ctx, size_t bytes);
+
+#define SFM_CUDA(ctx, expr)                                                                          \
+  do {                                                                                               \
+    cudaError_t e__ = (expr);                                                                        \
+    if (e__ != cudaSuccess)                                                                          \
+      return sfm_fail(ctx, SFMGPU_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),   \
+                      __FILE__, __LINE__);                                                           \
+  } while (0)
+
+#define SFM_TRY(expr)        \
+  do {                       \
+    int r__ = (expr);        \
+    if (r__ != 0) return r__; \
+  } while (0)
+
+// Launch a kernel on the context stream, count it, and surface launch errors.
+#define SFM_LAUNCH(ctx, kernel, grid, block, smem, ...)                                  \
+  do {                                                                                   \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                     \
+    (ctx)->launches++;                                                                   \
+    SFM_CUDA(ctx, cudaGetLastError());                                                   \
+  } while (0)
+
+static inline int sfm_align16(int v) { return v <= 0 ? 16 : ((v + 15) / 16) * 16; }
+static inline unsigned sfm_cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+
+// ---- internal cross-file entry points (device-pointer level) --------------------------------------------
+// klt.cu
+struct KltLaunch {
+  PyrView pv;
+  const double2* p0;     // [npairs*cap] (or [n] when npairs == 1)
+  const int* counts;     // per-pair valid count, or nullptr (all cap valid)
+  int npairs, cap;
+  int fa0, fa_step, fb0, fb_step;  // frame indices of image A / B for pair k: fa0 + k*fa_step ...
+  int radius, iters;
+  double fb_thresh;
+  double2* p1;           // forward result
+  double2* pb;           // backward result
+  int* nit;              // optional
+  uint8_t* keep;         // optional: !(fb >= fb_thresh)
+};
+int sfm_klt_launch(sfmgpu_ctx* ctx, const KltLaunch& k);
+
+// corner_score.cu / corner_select.cu
+struct CornerWork;  // opaque per-batch work area
+size_t sfm_corner_work_bytes(int w, int h, int nframes, int cand_cap);
+size_t sfm_corner_work_bytes_md(int w, int h, int nframes, int cand_cap, int min_dist);
+// Detect corners for frames [first, first+count): out_xy [count][max_corners] (double2, integer valued),
+// out_n[count].  cand_cap = per-frame candidate capacity (overflow -> E_CAPACITY, reported via status word).
+int sfm_corners_batch(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first, int count, int max_corners, double quality,
+                      int min_dist, int cand_cap, void* work, size_t work_bytes, double2* out_xy, int* out_n);
+int sfm_candidates_single(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int frame, double quality, int32_t* xy,
+                          double* score, int cap, int* n_out, double* max_score);
+int sfm_sort_perm(sfmgpu_ctx* ctx, const double* keys, int n, int32_t* perm);

@@ -1,0 +1,499 @@
+// corner_select.cu — exact std::sort permutation + greedy min-distance selection, one thread block per frame.
+//
+// Replaces (reference cpp/src/templering_sfm.cpp) shi_tomasi :286-301: std::sort of the candidates by score
+// descending (unstable: libstdc++ introsort decides the order of ties), then the sequential greedy loop that
+// accepts a candidate iff no already accepted corner lies at squared distance < min_dist^2, capped at
+// max_corners (tested after the push, so at least one corner comes back whenever a candidate exists).
+//
+// Sort: the introsort segment tree is walked LEFT-FIRST and LAZILY (sort_emul.h facts 1-4): only as much of
+// the array is sorted as the selection consumes.  Segments larger than SMALL are partitioned by the whole
+// block (two ordered compactions of the misfits + pairwise swaps); smaller ones are handed to warps, up to 32
+// at a time, each warp finishing its segment completely (warp partitions, then one leaf per lane with the
+// stable insertion sort).  Depth-limit exhaustion takes the sequential heap-sort restatement.
+//
+// Selection: greedy acceptance only ever depends on higher-priority candidates, so a chunk of the sorted
+// prefix is decided in parallel: (1) kill candidates within min_dist of corners accepted in earlier chunks
+// (lookup in a min_dist-cell grid holding <= 2 corners per cell), (2) resolve conflicts inside the chunk by
+// rounds (a candidate is accepted once every closer, higher-priority survivor is decided), (3) append the
+// accepted ones in priority order.  Coordinates are integers: the arithmetic is exact.
+#include "common.cuh"
+#include "corner_work.cuh"
+#include "sort_emul.h"
+
+int sfm_corner_candidates_batch(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first, int count, double quality,
+                                const CornerWorkView& wv);
+
+namespace {
+
+constexpr int SEL_THREADS = 1024;
+constexpr int SEL_WARPS = SEL_THREADS / 32;
+constexpr int SMALL = 2048;       // segments up to this size are sorted by one warp
+constexpr int CHUNK = 1024;       // candidates decided per selection round
+constexpr int BSTACK = 96;        // block stack entries (depth limit is 2*lg(n) <= 64)
+constexpr int WSTACK = 64;        // per-warp stack entries
+constexpr unsigned EMPTY = 0xFFFFFFFFu;
+
+struct Seg {
+  int f, l, d;
+};
+
+struct SelSmem {
+  Seg bstack[BSTACK];
+  Seg wstack[SEL_WARPS][WSTACK];
+  int2 leaf[SEL_WARPS][32];
+  Seg task[SEL_WARPS];
+  int wcntL[SEL_WARPS], wcntR[SEL_WARPS], wpreL[SEL_WARPS], wpreR[SEL_WARPS];
+  int totL, totR;
+  int bsp, ntask, sorted_upto, consumed, accepted, flag;
+  int red[SEL_WARPS];
+  // selection chunk
+  unsigned short ax[CHUNK], ay[CHUNK];
+  unsigned char st[CHUNK];
+};
+
+enum { ST_UNDEC = 0, ST_ACC = 1, ST_DEAD = 2 };
+
+// ---- warp-level partition of [f, l) (l - f > 16); returns cut (identical in all lanes) --------------------
+__device__ int warp_partition(sfm_key_t* key, uint32_t* idx, int f, int l, uint32_t* lpos, uint32_t* rpos, int lane) {
+  if (lane == 0) sfm_median_to_first(key, idx, f, l);
+  __syncwarp();
+  const sfm_key_t p = key[f];
+  const int mR = l - f - 1;
+  int nl = 0, nr = 0;
+  for (int t0 = 0; t0 < mR; t0 += 32) {
+    const int t = t0 + lane;
+    const bool v = t < mR;
+    const bool isL = v && !(key[f + 1 + t] > p);
+    const bool isR = v && !(p > key[l - 1 - t]);
+    const unsigned bl = __ballot_sync(0xffffffffu, isL), br = __ballot_sync(0xffffffffu, isR);
+    const unsigned lt = (1u << lane) - 1u;
+    if (isL) lpos[f + nl + __popc(bl & lt)] = (uint32_t)(f + 1 + t);
+    if (isR) rpos[f + nr + __popc(br & lt)] = (uint32_t)(l - 1 - t);
+    nl += __popc(bl);
+    nr += __popc(br);
+  }
+  __syncwarp();
+  const int lim = nl < nr ? nl : nr;
+  int m = 0;
+  for (int k0 = 0; k0 < lim; k0 += 32) {
+    const int k = k0 + lane;
+    const bool ok = k < lim && lpos[f + k] < rpos[f + k];
+    const unsigned b = __ballot_sync(0xffffffffu, ok);
+    m += __popc(b);
+    if (b != 0xffffffffu) break;  // the predicate is a prefix (monotone), uniform exit
+  }
+  for (int k = lane; k < m; k += 32) sfm_swap_elem(key, idx, (int)lpos[f + k], (int)rpos[f + k]);
+  uint32_t cut = EMPTY;
+  if (m < nl) cut = lpos[f + m];
+  if (m > 0) {
+    const uint32_t r = rpos[f + m - 1];
+    cut = r < cut ? r : cut;
+  }
+  __syncwarp();
+  return (int)cut;
+}
+
+// ---- one warp sorts [f, l) completely ------------------------------------------------------------------------
+__device__ void warp_sort_segment(SelSmem& sm, sfm_key_t* key, uint32_t* idx, uint32_t* lpos, uint32_t* rpos, Seg s0,
+                                  int warp, int lane) {
+  Seg* stk = sm.wstack[warp];
+  int2* leaf = sm.leaf[warp];
+  int sp = 0, nleaf = 0;
+  if (lane == 0) stk[0] = s0;
+  sp = 1;
+  __syncwarp();
+  while (sp > 0) {
+    const Seg s = stk[sp - 1];
+    sp--;
+    __syncwarp();
+    if (s.l - s.f <= SFM_SORT_THRESHOLD) {
+      if (lane == 0) leaf[nleaf] = make_int2(s.f, s.l);
+      nleaf++;
+      if (nleaf == 32) {
+        __syncwarp();
+        sfm_leaf_sort(key, idx, leaf[lane].x, leaf[lane].y);
+        nleaf = 0;
+        __syncwarp();
+      }
+      continue;
+    }
+    if (s.d == 0 || sp + 2 > WSTACK) {
+      // depth limit reached (libstdc++: __partial_sort); also the guard for a full stack, which cannot
+      // happen while WSTACK >= depth limit.
+      if (lane == 0) sfm_heap_sort(key, idx, s.f, s.l);
+      __syncwarp();
+      continue;
+    }
+    const int cut = warp_partition(key, idx, s.f, s.l, lpos, rpos, lane);
+    if (lane == 0) {
+      stk[sp] = Seg{cut, s.l, s.d - 1};
+      stk[sp + 1] = Seg{s.f, cut, s.d - 1};
+    }
+    sp += 2;
+    __syncwarp();
+  }
+  __syncwarp();
+  if (lane < nleaf) sfm_leaf_sort(key, idx, leaf[lane].x, leaf[lane].y);
+  __syncwarp();
+}
+
+// ---- block-level partition of [f, l); returns cut (identical in all threads) ------------------------------------
+__device__ int block_partition(SelSmem& sm, sfm_key_t* key, uint32_t* idx, int f, int l, uint32_t* lpos, uint32_t* rpos) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) sfm_median_to_first(key, idx, f, l);
+  __syncthreads();
+  const sfm_key_t p = key[f];
+  const int mR = l - f - 1;
+  int nl = 0, nr = 0;
+  for (int t0 = 0; t0 < mR; t0 += SEL_THREADS) {
+    const int t = t0 + tid;
+    const bool v = t < mR;
+    const bool isL = v && !(key[f + 1 + t] > p);
+    const bool isR = v && !(p > key[l - 1 - t]);
+    const unsigned bl = __ballot_sync(0xffffffffu, isL), br = __ballot_sync(0xffffffffu, isR);
+    if (lane == 0) {
+      sm.wcntL[warp] = __popc(bl);
+      sm.wcntR[warp] = __popc(br);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      int a = sm.wcntL[lane], b = sm.wcntR[lane];
+      int ia = a, ib = b;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int ua = __shfl_up_sync(0xffffffffu, ia, o), ub = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o) {
+          ia += ua;
+          ib += ub;
+        }
+      }
+      sm.wpreL[lane] = ia - a;
+      sm.wpreR[lane] = ib - b;
+      if (lane == 31) {
+        sm.totL = ia;
+        sm.totR = ib;
+      }
+    }
+    __syncthreads();
+    const unsigned lt = (1u << lane) - 1u;
+    if (isL) lpos[f + nl + sm.wpreL[warp] + __popc(bl & lt)] = (uint32_t)(f + 1 + t);
+    if (isR) rpos[f + nr + sm.wpreR[warp] + __popc(br & lt)] = (uint32_t)(l - 1 - t);
+    nl += sm.totL;
+    nr += sm.totR;
+    __syncthreads();
+  }
+  const int lim = nl < nr ? nl : nr;
+  int cnt = 0;
+  for (int k = tid; k < lim; k += SEL_THREADS) cnt += (lpos[f + k] < rpos[f + k]) ? 1 : 0;
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if (lane == 0) sm.red[warp] = cnt;
+  __syncthreads();
+  int m = 0;
+#pragma unroll
+  for (int k = 0; k < SEL_WARPS; k++) m += sm.red[k];
+  for (int k = tid; k < m; k += SEL_THREADS) sfm_swap_elem(key, idx, (int)lpos[f + k], (int)rpos[f + k]);
+  uint32_t cut = EMPTY;
+  if (m < nl) cut = lpos[f + m];
+  if (m > 0) {
+    const uint32_t r = rpos[f + m - 1];
+    cut = r < cut ? r : cut;
+  }
+  __syncthreads();
+  return (int)cut;
+}
+
+// Extend the sorted prefix: pops the block stack until at least `want` sorted-but-unconsumed elements exist
+// or the stack is empty.  Uniform control flow across the block.
+__device__ void produce_sorted(SelSmem& sm, sfm_key_t* key, uint32_t* idx, uint32_t* lpos, uint32_t* rpos, int want) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  while (true) {
+    __syncthreads();
+    if (sm.bsp == 0 || sm.sorted_upto - sm.consumed >= want) break;
+    const Seg top = sm.bstack[sm.bsp - 1];
+    __syncthreads();
+    if (top.l - top.f > SMALL) {
+      if (top.d == 0 || sm.bsp + 1 > BSTACK) {
+        if (tid == 0) {
+          sfm_heap_sort(key, idx, top.f, top.l);
+          sm.bsp--;
+          sm.sorted_upto = top.l;
+        }
+        continue;
+      }
+      const int cut = block_partition(sm, key, idx, top.f, top.l, lpos, rpos);
+      if (tid == 0) {
+        sm.bstack[sm.bsp - 1] = Seg{cut, top.l, top.d - 1};
+        sm.bstack[sm.bsp] = Seg{top.f, cut, top.d - 1};
+        sm.bsp++;
+      }
+      continue;
+    }
+    // gather consecutive small segments (left to right) for the warps
+    if (tid == 0) {
+      int nt = 0;
+      while (nt < SEL_WARPS && sm.bsp > 0 && sm.bstack[sm.bsp - 1].l - sm.bstack[sm.bsp - 1].f <= SMALL) {
+        sm.task[nt++] = sm.bstack[sm.bsp - 1];
+        sm.bsp--;
+      }
+      sm.ntask = nt;
+    }
+    __syncthreads();
+    const int nt = sm.ntask;
+    if (warp < nt) warp_sort_segment(sm, key, idx, lpos, rpos, sm.task[warp], warp, lane);
+    __syncthreads();
+    if (tid == 0) sm.sorted_upto = sm.task[nt - 1].l;
+  }
+}
+
+// mode 0: full shi_tomasi selection; mode 1: sort only (sfmgpu_sort_perm_desc).
+__global__ void __launch_bounds__(SEL_THREADS) select_kernel(CornerWorkView wv, int w, int max_corners, int min_dist, int mode,
+                                                            double2* __restrict__ out_xy, int* __restrict__ out_n) {
+  extern __shared__ __align__(16) unsigned char sel_raw[];
+  SelSmem& sm = *reinterpret_cast<SelSmem*>(sel_raw);
+  const int fr = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t cb = (size_t)fr * wv.cand_cap;
+  sfm_key_t* key = wv.key + cb;
+  uint32_t* idx = wv.idx + cb;
+  uint32_t* lpos = wv.lpos + cb;
+  uint32_t* rpos = wv.rpos + cb;
+  const unsigned ntot = wv.ntotal[fr];
+  if (ntot > (unsigned)wv.cand_cap) {  // capacity exceeded: report, never truncate silently
+    if (tid == 0) {
+      wv.status[fr] = 1;
+      if (out_n) out_n[fr] = -1;
+    }
+    return;
+  }
+  const int n = (int)ntot;
+  const int cap_out = max_corners < 1 ? 1 : max_corners;  // the cap is tested after the push (:298-299)
+  if (tid == 0) {
+    wv.status[fr] = 0;
+    sm.bsp = 0;
+    if (n > 0) sm.bstack[sm.bsp++] = Seg{0, n, 2 * sfm_lg2((unsigned)n)};
+    sm.sorted_upto = 0;
+    sm.consumed = 0;
+    sm.accepted = 0;
+  }
+  __syncthreads();
+  if (mode == 1) {
+    produce_sorted(sm, key, idx, lpos, rpos, 0x7fffffff);
+    return;
+  }
+  unsigned* grid = wv.grid + (size_t)fr * wv.grid_per_frame;
+  double2* out = out_xy + (size_t)fr * cap_out;
+  const int d = min_dist, d2 = min_dist * min_dist;
+  const bool suppress = wv.cell > 0;
+
+  while (true) {
+    produce_sorted(sm, key, idx, lpos, rpos, CHUNK);
+    const int consumed = sm.consumed, upto = sm.sorted_upto, acc0 = sm.accepted;
+    if (consumed >= upto || acc0 >= cap_out) break;
+    const int cnt = min(CHUNK, upto - consumed);
+    __syncthreads();
+    // (1) candidates of this chunk vs corners accepted in earlier chunks
+    int x = 0, y = 0;
+    bool alive = false;
+    if (tid < cnt) {
+      const unsigned pix = idx[consumed + tid];
+      y = (int)(pix / (unsigned)w);
+      x = (int)(pix - (unsigned)y * (unsigned)w);
+      alive = true;
+      if (suppress) {
+        const int cx = x / d, cy = y / d;
+        for (int gy = max(cy - 1, 0); gy <= min(cy + 1, wv.gh - 1) && alive; gy++)
+          for (int gx = max(cx - 1, 0); gx <= min(cx + 1, wv.gw - 1) && alive; gx++) {
+            const unsigned* cell = grid + ((size_t)gy * wv.gw + gx) * 2;
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+              const unsigned v = __ldcg(cell + s);
+              if (v != EMPTY) {
+                const int dx = (int)(v & 0xFFFFu) - x, dy = (int)(v >> 16) - y;
+                if (dx * dx + dy * dy < d2) alive = false;
+              }
+            }
+          }
+      }
+    }
+    // ordered compaction of the survivors into ax/ay (block scan of `alive`)
+    const unsigned bal = __ballot_sync(0xffffffffu, alive);
+    if (lane == 0) sm.wcntL[warp] = __popc(bal);
+    __syncthreads();
+    if (warp == 0) {
+      const int a = sm.wcntL[lane];
+      int ia = a;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int ua = __shfl_up_sync(0xffffffffu, ia, o);
+        if (lane >= o) ia += ua;
+      }
+      sm.wpreL[lane] = ia - a;
+      if (lane == 31) sm.totL = ia;
+    }
+    __syncthreads();
+    const int na = sm.totL;
+    if (alive) {
+      const int k = sm.wpreL[warp] + __popc(bal & ((1u << lane) - 1u));
+      sm.ax[k] = (unsigned short)x;
+      sm.ay[k] = (unsigned short)y;
+      sm.st[k] = ST_UNDEC;
+    }
+    __syncthreads();
+    // (2) conflicts inside the chunk, by rounds
+    if (suppress) {
+      while (true) {
+        int ns = ST_DEAD + 1;  // "no change"
+        if (tid < na && sm.st[tid] == ST_UNDEC) {
+          const int mx = sm.ax[tid], my = sm.ay[tid];
+          bool dead = false, blocked = false;
+          for (int j = 0; j < tid; j++) {
+            const int sj = sm.st[j];
+            if (sj == ST_DEAD) continue;
+            const int dx = (int)sm.ax[j] - mx, dy = (int)sm.ay[j] - my;
+            if (dx * dx + dy * dy < d2) {
+              if (sj == ST_ACC) {
+                dead = true;
+                break;
+              }
+              blocked = true;
+            }
+          }
+          ns = dead ? ST_DEAD : (blocked ? ST_UNDEC : ST_ACC);
+        }
+        __syncthreads();
+        if (tid == 0) sm.flag = 0;
+        if (ns <= ST_DEAD) sm.st[tid] = (unsigned char)ns;
+        __syncthreads();
+        if (ns == ST_UNDEC) sm.flag = 1;
+        __syncthreads();
+        if (!sm.flag) break;
+        __syncthreads();
+      }
+    } else {
+      if (tid < na) sm.st[tid] = ST_ACC;
+      __syncthreads();
+    }
+    // (3) append accepted survivors in priority order, stop at the cap
+    const bool acc = tid < na && sm.st[tid] == ST_ACC;
+    const unsigned bac = __ballot_sync(0xffffffffu, acc);
+    if (lane == 0) sm.wcntR[warp] = __popc(bac);
+    __syncthreads();
+    if (warp == 0) {
+      const int a = sm.wcntR[lane];
+      int ia = a;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int ua = __shfl_up_sync(0xffffffffu, ia, o);
+        if (lane >= o) ia += ua;
+      }
+      sm.wpreR[lane] = ia - a;
+      if (lane == 31) sm.totR = ia;
+    }
+    __syncthreads();
+    if (acc) {
+      const int k = acc0 + sm.wpreR[warp] + __popc(bac & ((1u << lane) - 1u));
+      if (k < cap_out) {
+        const int px = sm.ax[tid], py = sm.ay[tid];
+        out[k] = make_double2((double)px, (double)py);
+        if (suppress) {
+          unsigned* cell = grid + ((size_t)(py / d) * wv.gw + (px / d)) * 2;
+          const unsigned v = ((unsigned)py << 16) | (unsigned)px;
+          if (atomicCAS(cell, EMPTY, v) != EMPTY) atomicCAS(cell + 1, EMPTY, v);
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      sm.accepted = min(cap_out, acc0 + sm.totR);
+      sm.consumed = consumed + cnt;
+    }
+    __threadfence_block();
+    __syncthreads();
+  }
+  if (tid == 0 && out_n) out_n[fr] = sm.accepted;
+}
+
+int select_smem_config(sfmgpu_ctx* ctx) {
+  static bool done = false;
+  if (!done) {
+    SFM_CUDA(ctx, cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelSmem)));
+    done = true;
+  }
+  return 0;
+}
+
+}  // namespace
+
+// Detect corners for frames [first, first+count): out_xy [count][max(1,max_corners)], out_n[count] (device).
+int sfm_corners_batch(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first, int count, int max_corners, double quality,
+                      int min_dist, int cand_cap, void* work, size_t work_bytes, double2* out_xy, int* out_n) {
+  if (f->w > 65535 || f->h > 65535) return sfm_fail(ctx, SFMGPU_E_ARG, "corners: image larger than 65535 px");
+  if (min_dist < 0) min_dist = -min_dist;  // the reference compares against (double)min_dist*min_dist (:295)
+  if (min_dist > 30000) return sfm_fail(ctx, SFMGPU_E_ARG, "corners: min_dist too large");
+  CornerWorkView wv;
+  const size_t need = corner_work_carve(wv, work, f->w, f->h, count, cand_cap, min_dist);
+  if (need > work_bytes) return sfm_fail(ctx, SFMGPU_E_ARG, "corners: work area too small (%zu < %zu)", work_bytes, need);
+  SFM_TRY(select_smem_config(ctx));
+  SFM_TRY(sfm_corner_candidates_batch(ctx, f, first, count, quality, wv));
+  if (wv.grid_per_frame)
+    SFM_CUDA(ctx, cudaMemsetAsync(wv.grid, 0xFF, sizeof(unsigned) * wv.grid_per_frame * count, ctx->stream));
+  SFM_LAUNCH(ctx, select_kernel, count, SEL_THREADS, sizeof(SelSmem), wv, f->w, max_corners, min_dist, 0, out_xy, out_n);
+  return 0;
+}
+
+size_t sfm_corner_work_bytes_md(int w, int h, int nframes, int cand_cap, int min_dist) {
+  CornerWorkView v;
+  return corner_work_carve(v, nullptr, w, h, nframes, cand_cap, min_dist);
+}
+
+extern "C" int sfmgpu_corners(sfmgpu_ctx* ctx, sfmgpu_frames* f, int frame, int max_corners, double quality, int min_dist,
+                              double* xy_out, int* n_out) {
+  if (!ctx || !f || !xy_out || !n_out) return SFMGPU_E_ARG;
+  if (frame < 0 || frame >= f->n) return sfm_fail(ctx, SFMGPU_E_ARG, "corners: bad frame index");
+  const int cap_out = max_corners < 1 ? 1 : max_corners;
+  const int cand_cap = f->w * f->h;  // worst case (flat image: every pixel is a candidate)
+  const size_t wb = sfm_corner_work_bytes_md(f->w, f->h, 1, cand_cap, min_dist < 0 ? -min_dist : min_dist);
+  SFM_TRY(sfm_reserve(ctx, ctx->cs_work, wb));
+  SFM_TRY(sfm_reserve(ctx, ctx->sel_work, (size_t)cap_out * sizeof(double2) + 256));
+  double2* d_xy = (double2*)ctx->sel_work.p;
+  int* d_n = (int*)((char*)ctx->sel_work.p + (size_t)cap_out * sizeof(double2));
+  SFM_TRY(sfm_corners_batch(ctx, f, frame, 1, max_corners, quality, min_dist, cand_cap, ctx->cs_work.p, ctx->cs_work.cap, d_xy,
+                            d_n));
+  int n = 0;
+  SFM_CUDA(ctx, cudaMemcpyAsync(&n, d_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n < 0) return sfm_fail(ctx, SFMGPU_E_CAPACITY, "corners: candidate capacity exceeded");
+  *n_out = n;
+  if (n > 0) {
+    SFM_CUDA(ctx, cudaMemcpyAsync(xy_out, d_xy, (size_t)n * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return 0;
+}
+
+// Device std::sort permutation of arbitrary non-negative keys (test / parity entry point).
+int sfm_sort_perm(sfmgpu_ctx* ctx, const double* keys, int n, int32_t* perm) {
+  if (n < 0) return sfm_fail(ctx, SFMGPU_E_ARG, "sort_perm: negative n");
+  if (n == 0) return 0;
+  for (int i = 0; i < n; i++)
+    if (!(keys[i] >= 0.0)) return sfm_fail(ctx, SFMGPU_E_ARG, "sort_perm: keys must be non-negative, non-NaN (scores are)");
+  CornerWorkView wv;
+  const size_t wb = corner_work_carve(wv, nullptr, 32, 1, 1, n, 0);
+  SFM_TRY(sfm_reserve(ctx, ctx->cs_work, wb));
+  corner_work_carve(wv, ctx->cs_work.p, 32, 1, 1, n, 0);
+  SFM_TRY(select_smem_config(ctx));
+  std::vector<unsigned> iota(n);
+  for (int i = 0; i < n; i++) iota[i] = (unsigned)i;
+  const unsigned un = (unsigned)n;
+  SFM_CUDA(ctx, cudaMemcpyAsync(wv.key, keys, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  SFM_CUDA(ctx, cudaMemcpyAsync(wv.idx, iota.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  SFM_CUDA(ctx, cudaMemcpyAsync(wv.ntotal, &un, 4, cudaMemcpyHostToDevice, ctx->stream));
+  SFM_LAUNCH(ctx, select_kernel, 1, SEL_THREADS, sizeof(SelSmem), wv, 32, 0, 0, 1, (double2*)nullptr, (int*)nullptr);
+  SFM_CUDA(ctx, cudaMemcpyAsync(perm, wv.idx, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int sfmgpu_sort_perm_desc(sfmgpu_ctx* ctx, const double* keys, int n, int32_t* perm) {
+  if (!ctx || (n > 0 && (!keys || !perm))) return SFMGPU_E_ARG;
+  return sfm_sort_perm(ctx, keys, n, perm);
+}

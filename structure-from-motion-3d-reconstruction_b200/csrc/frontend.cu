@@ -1,0 +1,530 @@
+// frontend.cu — the two callers of the kernels that the reference has:
+//   * the stateless two-view front end (cpp/src/templering_sfm.cpp:1836-1857), batched over frame pairs;
+//   * the stateful KLTTracker (:323-391): reset / step / tracks, with the replenish rule (:374-389).
+// Everything stays on the device between stages; only survivors / counts are copied back when the caller asks.
+#include "common.cuh"
+
+// ---- small kernels -----------------------------------------------------------------------------------------------
+namespace {
+
+// Ordered compaction of the survivors of one pair / one tracker step: block = one pair.
+// keep == nullptr keeps everything.  Outputs (any may be null): a/b = p0/p1 of survivors, ids_out, n_out.
+__global__ void __launch_bounds__(1024) compact_kernel(const double2* __restrict__ p0, const double2* __restrict__ p1,
+                                                      const uint8_t* __restrict__ keep, const int* __restrict__ ids,
+                                                      const int* __restrict__ counts, int cap, double2* __restrict__ oa,
+                                                      double2* __restrict__ ob, int* __restrict__ oid,
+                                                      int* __restrict__ n_out) {
+  __shared__ int wcnt[32], wpre[32];
+  __shared__ int base, total;
+  const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int n = counts ? counts[pair] : cap;
+  n = n < 0 ? 0 : (n > cap ? cap : n);
+  const size_t off = (size_t)pair * cap;
+  if (tid == 0) base = 0;
+  __syncthreads();
+  for (int s = 0; s < n; s += 1024) {
+    const int i = s + tid;
+    const bool k = i < n && (keep ? keep[off + i] != 0 : true);
+    const unsigned m = __ballot_sync(0xffffffffu, k);
+    if (lane == 0) wcnt[warp] = __popc(m);
+    __syncthreads();
+    if (warp == 0) {
+      const int a = wcnt[lane];
+      int ia = a;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, ia, o);
+        if (lane >= o) ia += u;
+      }
+      wpre[lane] = ia - a;
+      if (lane == 31) total = ia;
+    }
+    __syncthreads();
+    if (k) {
+      const int r = base + wpre[warp] + __popc(m & ((1u << lane) - 1u));
+      if (oa) oa[off + r] = p0[off + i];
+      if (ob) ob[off + r] = p1[off + i];
+      if (oid) oid[off + r] = ids[off + i];
+    }
+    __syncthreads();
+    if (tid == 0) base += total;
+    __syncthreads();
+  }
+  if (tid == 0 && n_out) n_out[pair] = base;
+}
+
+// totals[0] += sum max(ncorn,0); totals[1] += sum nkept; totals[2] += sum nit; totals[3] += #frames with ncorn < 0
+__global__ void __launch_bounds__(256) totals_kernel(const int* __restrict__ ncorn, const int* __restrict__ nkept,
+                                                    const int* __restrict__ nit, int npairs, int cap,
+                                                    unsigned long long* __restrict__ totals) {
+  unsigned long long c = 0, k = 0, it = 0, bad = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)npairs * cap;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int pair = (int)(i / cap), slot = (int)(i - (long long)pair * cap);
+    const int n = ncorn[pair];
+    if (slot == 0) {
+      if (n < 0) bad++;
+      c += n > 0 ? n : 0;
+      k += nkept[pair];
+    }
+    if (slot < n) it += nit[i];
+  }
+  c = __reduce_add_sync(0xffffffffu, (unsigned)c);  // per-warp partials fit 32 bits
+  k = __reduce_add_sync(0xffffffffu, (unsigned)k);
+  bad = __reduce_add_sync(0xffffffffu, (unsigned)bad);
+  // nit can exceed 32 bits per warp only for absurd sizes; reduce in two halves to be safe
+  unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(it & 0xFFFFu));
+  unsigned hi = __reduce_add_sync(0xffffffffu, (unsigned)(it >> 16));
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&totals[0], c);
+    atomicAdd(&totals[1], k);
+    atomicAdd(&totals[2], (unsigned long long)lo + ((unsigned long long)hi << 16));
+    atomicAdd(&totals[3], bad);
+  }
+}
+
+// Replenish filter (:378-388): new corner i survives iff no LIVE track lies at squared distance < d^2
+// (FP64, no contraction: this file is built with -fmad=false).  Corners are pairwise >= d apart already,
+// so tracks appended earlier in the same loop can never reject a later corner; the test is independent per corner.
+__global__ void __launch_bounds__(256) replenish_filter_kernel(const double2* __restrict__ fresh, const int* __restrict__ n_fresh,
+                                                              const double2* __restrict__ tracks, int n_tracks, double d2,
+                                                              uint8_t* __restrict__ ok) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nf = *n_fresh;
+  if (i >= nf) return;
+  const double2 p = fresh[i];
+  bool good = true;
+  for (int j = 0; j < n_tracks; j++) {
+    const double2 t = tracks[j];
+    const double dx = t.x - p.x, dy = t.y - p.y;
+    if (dx * dx + dy * dy < d2) {
+      good = false;
+      break;
+    }
+  }
+  ok[i] = good ? 1 : 0;
+}
+
+// Append up to `room` surviving fresh corners to the track list with consecutive ids (one block).
+__global__ void __launch_bounds__(1024) replenish_append_kernel(const double2* __restrict__ fresh, const int* __restrict__ n_fresh,
+                                                               const uint8_t* __restrict__ ok, double2* __restrict__ tracks,
+                                                               int* __restrict__ ids, int n_tracks, int room, int next_id,
+                                                               int* __restrict__ n_added) {
+  __shared__ int wcnt[32], wpre[32];
+  __shared__ int base, total;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nf = *n_fresh;
+  if (tid == 0) base = 0;
+  __syncthreads();
+  for (int s = 0; s < nf; s += 1024) {
+    const int i = s + tid;
+    const bool k = i < nf && ok[i];
+    const unsigned m = __ballot_sync(0xffffffffu, k);
+    if (lane == 0) wcnt[warp] = __popc(m);
+    __syncthreads();
+    if (warp == 0) {
+      const int a = wcnt[lane];
+      int ia = a;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, ia, o);
+        if (lane >= o) ia += u;
+      }
+      wpre[lane] = ia - a;
+      if (lane == 31) total = ia;
+    }
+    __syncthreads();
+    if (k) {
+      const int r = base + wpre[warp] + __popc(m & ((1u << lane) - 1u));
+      if (r < room) {
+        tracks[n_tracks + r] = fresh[i];
+        ids[n_tracks + r] = next_id + r;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) base += total;
+    __syncthreads();
+    if (base >= room) break;
+  }
+  if (tid == 0) *n_added = base < room ? base : room;
+}
+
+// out[0] += sum v[0..n)
+__global__ void __launch_bounds__(256) sum_int_kernel(const int* __restrict__ v, int n, unsigned long long* __restrict__ out) {
+  unsigned s = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += (unsigned)v[i];
+  s = __reduce_add_sync(0xffffffffu, s);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, (unsigned long long)s);
+}
+
+__global__ void iota_ids_kernel(int* ids, const int* n, int next_id) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < *n) ids[i] = next_id + i;
+}
+
+int default_cand_cap(int w, int h) {
+  long long px = (long long)w * h;
+  long long cap = px / 6;
+  if (cap < 65536) cap = 65536;
+  if (cap > px) cap = px;
+  return (int)cap;
+}
+
+}  // namespace
+
+// ---- batched pair front end -------------------------------------------------------------------------------------------
+struct sfmgpu_pairs {
+  int max_pairs = 0, cap = 0;
+  double2 *xy0 = nullptr, *p1 = nullptr, *pb = nullptr, *li = nullptr, *lj = nullptr;
+  int *ncorn = nullptr, *nkept = nullptr, *nit = nullptr;
+  uint8_t* keep = nullptr;
+  unsigned long long* totals = nullptr;
+  DevBuf work;
+  int last_npairs = 0;
+};
+
+extern "C" {
+
+int sfmgpu_pairs_create(sfmgpu_ctx* ctx, int max_pairs, int max_corners, sfmgpu_pairs** out) {
+  if (!ctx || !out || max_pairs <= 0) return sfm_fail(ctx, SFMGPU_E_ARG, "pairs_create: bad arguments");
+  sfmgpu_pairs* p = new sfmgpu_pairs();
+  p->max_pairs = max_pairs;
+  p->cap = max_corners < 1 ? 1 : max_corners;
+  const size_t n = (size_t)max_pairs * p->cap;
+  cudaError_t e = cudaSuccess;
+  auto al = [&](void** q, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(q, bytes + 256);
+  };
+  al((void**)&p->xy0, n * 16);
+  al((void**)&p->p1, n * 16);
+  al((void**)&p->pb, n * 16);
+  al((void**)&p->li, n * 16);
+  al((void**)&p->lj, n * 16);
+  al((void**)&p->nit, n * 4);
+  al((void**)&p->keep, n);
+  al((void**)&p->ncorn, (size_t)max_pairs * 4);
+  al((void**)&p->nkept, (size_t)max_pairs * 4);
+  al((void**)&p->totals, 64);
+  if (e != cudaSuccess) {
+    sfmgpu_pairs_destroy(ctx, p);
+    return sfm_fail(ctx, SFMGPU_E_CUDA, "pairs_create: cudaMalloc failed: %s", cudaGetErrorString(e));
+  }
+  *out = p;
+  return 0;
+}
+
+void sfmgpu_pairs_destroy(sfmgpu_ctx* ctx, sfmgpu_pairs* p) {
+  if (!p) return;
+  if (ctx) cudaStreamSynchronize(ctx->stream);
+  void* ptrs[] = {p->xy0, p->p1, p->pb, p->li, p->lj, p->nit, p->keep, p->ncorn, p->nkept, p->totals, p->work.p};
+  for (void* q : ptrs)
+    if (q) cudaFree(q);
+  delete p;
+}
+
+int sfmgpu_pair_frontend(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int npairs, const sfmgpu_lkcfg* cfg,
+                         sfmgpu_pairs* out) {
+  if (!ctx || !f || !cfg || !out) return SFMGPU_E_ARG;
+  if (npairs < 0 || npairs > out->max_pairs || first_frame < 0 || first_frame + npairs + (npairs > 0 ? 1 : 0) > f->n)
+    return sfm_fail(ctx, SFMGPU_E_ARG, "pair_frontend: pair range [%d,%d) does not fit (frames %d, max_pairs %d)", first_frame,
+                    first_frame + npairs, f->n, out->max_pairs);
+  const int cap_out = cfg->max_tracks < 1 ? 1 : cfg->max_tracks;
+  if (cap_out != out->cap) return sfm_fail(ctx, SFMGPU_E_ARG, "pair_frontend: cfg->max_tracks != pairs capacity");
+  if (cfg->pyr_levels != f->levels) return sfm_fail(ctx, SFMGPU_E_ARG, "pair_frontend: cfg->pyr_levels != frames levels");
+  out->last_npairs = npairs;
+  SFM_CUDA(ctx, cudaMemsetAsync(out->totals, 0, 64, ctx->stream));
+  if (npairs == 0) return 0;
+  // corners, in chunks of frames that bound the work area
+  const int cand_cap = default_cand_cap(f->w, f->h);
+  const int md = cfg->min_distance < 0 ? -cfg->min_distance : cfg->min_distance;
+  int chunk = npairs < 256 ? npairs : 256;
+  const size_t wb = sfm_corner_work_bytes_md(f->w, f->h, chunk, cand_cap, md);
+  SFM_TRY(sfm_reserve(ctx, out->work, wb));
+  for (int c0 = 0; c0 < npairs; c0 += chunk) {
+    const int cnt = npairs - c0 < chunk ? npairs - c0 : chunk;
+    SFM_TRY(sfm_corners_batch(ctx, f, first_frame + c0, cnt, cfg->max_tracks, cfg->quality, cfg->min_distance, cand_cap,
+                              out->work.p, out->work.cap, out->xy0 + (size_t)c0 * out->cap, out->ncorn + c0));
+  }
+  KltLaunch k;
+  k.pv = f->view();
+  k.p0 = out->xy0;
+  k.counts = out->ncorn;
+  k.npairs = npairs;
+  k.cap = out->cap;
+  k.fa0 = first_frame;
+  k.fa_step = 1;
+  k.fb0 = first_frame + 1;
+  k.fb_step = 1;
+  k.radius = cfg->win_radius;
+  k.iters = cfg->iters;
+  k.fb_thresh = cfg->fb_thresh;
+  k.p1 = out->p1;
+  k.pb = out->pb;
+  k.nit = out->nit;
+  k.keep = out->keep;
+  SFM_TRY(sfm_klt_launch(ctx, k));
+  SFM_LAUNCH(ctx, compact_kernel, npairs, 1024, 0, out->xy0, out->p1, out->keep, (const int*)nullptr, out->ncorn, out->cap, out->li,
+             out->lj, (int*)nullptr, out->nkept);
+  SFM_LAUNCH(ctx, totals_kernel, 256, 256, 0, out->ncorn, out->nkept, out->nit, npairs, out->cap, out->totals);
+  return 0;
+}
+
+int sfmgpu_pairs_totals(sfmgpu_ctx* ctx, sfmgpu_pairs* p, long long* n_corners, long long* n_kept, long long* n_lk_iters) {
+  if (!ctx || !p) return SFMGPU_E_ARG;
+  unsigned long long t[4];
+  SFM_CUDA(ctx, cudaMemcpyAsync(t, p->totals, sizeof t, cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n_corners) *n_corners = (long long)t[0];
+  if (n_kept) *n_kept = (long long)t[1];
+  if (n_lk_iters) *n_lk_iters = (long long)t[2];
+  if (t[3])
+    return sfm_fail(ctx, SFMGPU_E_CAPACITY, "pair_frontend: %llu frame(s) exceeded the candidate capacity", t[3]);
+  return 0;
+}
+
+int sfmgpu_pairs_download(sfmgpu_ctx* ctx, sfmgpu_pairs* p, int pair, double* li_xy, double* lj_xy, int cap, int* n_kept,
+                          int* n_corners) {
+  if (!ctx || !p || pair < 0 || pair >= p->last_npairs) return sfm_fail(ctx, SFMGPU_E_ARG, "pairs_download: bad pair index");
+  int nk = 0, nc = 0;
+  SFM_CUDA(ctx, cudaMemcpyAsync(&nk, p->nkept + pair, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(ctx, cudaMemcpyAsync(&nc, p->ncorn + pair, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (nc < 0) return sfm_fail(ctx, SFMGPU_E_CAPACITY, "pairs_download: pair %d exceeded the candidate capacity", pair);
+  if (n_kept) *n_kept = nk;
+  if (n_corners) *n_corners = nc;
+  if (nk > cap) return sfm_fail(ctx, SFMGPU_E_CAPACITY, "pairs_download: %d survivors, room for %d", nk, cap);
+  if (nk > 0) {
+    if (li_xy) SFM_CUDA(ctx, cudaMemcpyAsync(li_xy, p->li + (size_t)pair * p->cap, (size_t)nk * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (lj_xy) SFM_CUDA(ctx, cudaMemcpyAsync(lj_xy, p->lj + (size_t)pair * p->cap, (size_t)nk * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return 0;
+}
+
+}  // extern "C"
+
+// ---- stateful tracker -------------------------------------------------------------------------------------------------
+struct sfmgpu_tracker {
+  sfmgpu_lkcfg cfg;
+  sfmgpu_frames* own = nullptr;     // 2-slot ping-pong used by the host-image entry points
+  sfmgpu_frames* prev_frames = nullptr;
+  int prev_index = -1;
+  int n = 0;                        // live tracks (host copy)
+  int next_id = 0;
+  int cap = 0;
+  double2 *trk = nullptr, *p1 = nullptr, *pb = nullptr, *oa = nullptr, *ob = nullptr, *fresh = nullptr;
+  int *ids = nullptr, *oid = nullptr, *nit = nullptr, *scal = nullptr;  // scal: [0] n_out, [1] n_fresh, [2] n_added
+  uint8_t *keep = nullptr, *ok = nullptr;
+  int fresh_cap = 0;
+  long long track_steps = 0;
+  unsigned long long* tot = nullptr;
+};
+
+namespace {
+
+int tracker_detect(sfmgpu_ctx* ctx, sfmgpu_tracker* t, sfmgpu_frames* f, int frame, int max_corners, double2* out, int* d_n) {
+  const int cand_cap = f->w * f->h;  // single frame: always room for the worst case
+  const int md = t->cfg.min_distance < 0 ? -t->cfg.min_distance : t->cfg.min_distance;
+  const size_t wb = sfm_corner_work_bytes_md(f->w, f->h, 1, cand_cap, md);
+  SFM_TRY(sfm_reserve(ctx, ctx->cs_work, wb));
+  return sfm_corners_batch(ctx, f, frame, 1, max_corners, t->cfg.quality, t->cfg.min_distance, cand_cap, ctx->cs_work.p,
+                           ctx->cs_work.cap, out, d_n);
+}
+
+int tracker_reset_on(sfmgpu_ctx* ctx, sfmgpu_tracker* t, sfmgpu_frames* f, int frame) {
+  // reset(gray) :327-332: prev_ = gray; tracks_ = shi_tomasi(...) with ids next_id_++
+  SFM_TRY(tracker_detect(ctx, t, f, frame, t->cfg.max_tracks, t->trk, t->scal + 1));
+  int n = 0;
+  SFM_CUDA(ctx, cudaMemcpyAsync(&n, t->scal + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n < 0) return sfm_fail(ctx, SFMGPU_E_CAPACITY, "tracker: candidate capacity exceeded");
+  if (n > 0) SFM_LAUNCH(ctx, iota_ids_kernel, sfm_cdiv(n, 256), 256, 0, t->ids, (const int*)(t->scal + 1), t->next_id);
+  t->n = n;
+  t->next_id += n;
+  t->prev_frames = f;
+  t->prev_index = frame;
+  return 0;
+}
+
+int tracker_step_on(sfmgpu_ctx* ctx, sfmgpu_tracker* t, sfmgpu_frames* f, int frame, double* prev_xy, double* cur_xy,
+                    int32_t* ids, int cap, int* n_out) {
+  if (n_out) *n_out = 0;
+  if (t->prev_index < 0 || t->n == 0) return tracker_reset_on(ctx, t, f, frame);  // :341-344
+  if (t->prev_frames != f) return sfm_fail(ctx, SFMGPU_E_STATE, "tracker: previous frame lives in another frame batch");
+  KltLaunch k;
+  k.pv = f->view();
+  k.p0 = t->trk;
+  k.counts = nullptr;
+  k.npairs = 1;
+  k.cap = t->n;
+  k.fa0 = t->prev_index;
+  k.fa_step = 0;
+  k.fb0 = frame;
+  k.fb_step = 0;
+  k.radius = t->cfg.win_radius;
+  k.iters = t->cfg.iters;
+  k.fb_thresh = t->cfg.fb_thresh;
+  k.p1 = t->p1;
+  k.pb = t->pb;
+  k.nit = t->nit;
+  k.keep = t->keep;
+  SFM_TRY(sfm_klt_launch(ctx, k));
+  t->track_steps += t->n;
+  SFM_LAUNCH(ctx, sum_int_kernel, 8, 256, 0, (const int*)t->nit, t->n, t->tot + 2);
+  // survivors in track order: (p0, p1, id); tracks_ = kept (:364-371)
+  SFM_LAUNCH(ctx, compact_kernel, 1, 1024, 0, t->trk, t->p1, t->keep, t->ids, (const int*)nullptr, t->n, t->oa, t->ob, t->oid,
+             t->scal);
+  int nk = 0;
+  SFM_CUDA(ctx, cudaMemcpyAsync(&nk, t->scal, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (nk > cap && (prev_xy || cur_xy || ids))
+    return sfm_fail(ctx, SFMGPU_E_CAPACITY, "tracker_step: %d survivors, room for %d", nk, cap);
+  if (nk > 0) {
+    if (prev_xy) SFM_CUDA(ctx, cudaMemcpyAsync(prev_xy, t->oa, (size_t)nk * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cur_xy) SFM_CUDA(ctx, cudaMemcpyAsync(cur_xy, t->ob, (size_t)nk * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ids) SFM_CUDA(ctx, cudaMemcpyAsync(ids, t->oid, (size_t)nk * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(ctx, cudaMemcpyAsync(t->trk, t->ob, (size_t)nk * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+    SFM_CUDA(ctx, cudaMemcpyAsync(t->ids, t->oid, (size_t)nk * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  t->n = nk;
+  t->prev_frames = f;
+  t->prev_index = frame;
+  if (n_out) *n_out = nk;
+  // replenish (:374-389)
+  if (t->n < t->cfg.min_tracks) {
+    const int need = t->cfg.max_tracks - t->n;
+    long long want = (long long)need * 3;
+    if (want > t->fresh_cap) want = t->fresh_cap;  // fresh_cap = 3*max_tracks >= need*3
+    SFM_TRY(tracker_detect(ctx, t, f, frame, (int)want, t->fresh, t->scal + 1));
+    int nf = 0;
+    SFM_CUDA(ctx, cudaMemcpyAsync(&nf, t->scal + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (nf < 0) return sfm_fail(ctx, SFMGPU_E_CAPACITY, "tracker: candidate capacity exceeded");
+    if (nf > 0) {
+      const double d2 = (double)t->cfg.min_distance * t->cfg.min_distance;
+      SFM_LAUNCH(ctx, replenish_filter_kernel, sfm_cdiv(nf, 256), 256, 0, t->fresh, (const int*)(t->scal + 1), t->trk, t->n, d2,
+                 t->ok);
+      // the reference appends first and tests the cap afterwards (:386-387): at least one corner is added
+      int room = t->cfg.max_tracks - t->n;
+      if (room < 1) room = 1;
+      SFM_LAUNCH(ctx, replenish_append_kernel, 1, 1024, 0, t->fresh, (const int*)(t->scal + 1), t->ok, t->trk, t->ids, t->n, room,
+                 t->next_id, t->scal + 2);
+      int na = 0;
+      SFM_CUDA(ctx, cudaMemcpyAsync(&na, t->scal + 2, 4, cudaMemcpyDeviceToHost, ctx->stream));
+      SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      t->n += na;
+      t->next_id += na;
+    }
+  }
+  return 0;
+}
+
+int tracker_own_frames(sfmgpu_ctx* ctx, sfmgpu_tracker* t, int w, int h) {
+  if (t->own && (t->own->w != w || t->own->h != h))
+    return sfm_fail(ctx, SFMGPU_E_ARG, "tracker: image size changed from %dx%d to %dx%d (not supported)", t->own->w, t->own->h, w,
+                    h);
+  if (!t->own) SFM_TRY(sfmgpu_frames_create(ctx, w, h, 2, t->cfg.pyr_levels, &t->own));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sfmgpu_tracker_create(sfmgpu_ctx* ctx, const sfmgpu_lkcfg* cfg, sfmgpu_tracker** out) {
+  if (!ctx || !cfg || !out) return SFMGPU_E_ARG;
+  if (cfg->pyr_levels < 1 || cfg->pyr_levels > SFM_MAXL || cfg->max_tracks > (1 << 24))
+    return sfm_fail(ctx, SFMGPU_E_ARG, "tracker_create: bad configuration");
+  sfmgpu_tracker* t = new sfmgpu_tracker();
+  t->cfg = *cfg;
+  // the track list can hold max(max_tracks, 1) entries after reset, plus one overshoot entry from replenish
+  t->cap = (cfg->max_tracks < 1 ? 1 : cfg->max_tracks) + 1;
+  t->fresh_cap = 3 * (cfg->max_tracks < 1 ? 1 : cfg->max_tracks);
+  cudaError_t e = cudaSuccess;
+  auto al = [&](void** q, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(q, bytes + 256);
+  };
+  const size_t n = (size_t)t->cap;
+  al((void**)&t->trk, n * 16);
+  al((void**)&t->p1, n * 16);
+  al((void**)&t->pb, n * 16);
+  al((void**)&t->oa, n * 16);
+  al((void**)&t->ob, n * 16);
+  al((void**)&t->ids, n * 4);
+  al((void**)&t->oid, n * 4);
+  al((void**)&t->nit, n * 4);
+  al((void**)&t->keep, n);
+  al((void**)&t->fresh, (size_t)t->fresh_cap * 16);
+  al((void**)&t->ok, (size_t)t->fresh_cap);
+  al((void**)&t->scal, 64);
+  al((void**)&t->tot, 64);
+  if (e == cudaSuccess) e = cudaMemsetAsync(t->tot, 0, 64, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(t->scal, 0, 64, ctx->stream);
+  if (e != cudaSuccess) {
+    sfmgpu_tracker_destroy(ctx, t);
+    return sfm_fail(ctx, SFMGPU_E_CUDA, "tracker_create: CUDA allocation failed: %s", cudaGetErrorString(e));
+  }
+  *out = t;
+  return 0;
+}
+
+void sfmgpu_tracker_destroy(sfmgpu_ctx* ctx, sfmgpu_tracker* t) {
+  if (!t) return;
+  if (ctx) cudaStreamSynchronize(ctx->stream);
+  void* ptrs[] = {t->trk, t->p1, t->pb, t->oa, t->ob, t->ids, t->oid, t->nit, t->keep, t->fresh, t->ok, t->scal, t->tot};
+  for (void* q : ptrs)
+    if (q) cudaFree(q);
+  if (t->own) sfmgpu_frames_destroy(ctx, t->own);
+  delete t;
+}
+
+int sfmgpu_tracker_reset(sfmgpu_ctx* ctx, sfmgpu_tracker* t, const uint8_t* host_pix, int w, int h) {
+  if (!ctx || !t || !host_pix) return SFMGPU_E_ARG;
+  SFM_TRY(tracker_own_frames(ctx, t, w, h));
+  const int slot = (t->prev_frames == t->own && t->prev_index == 0) ? 1 : 0;
+  SFM_TRY(sfmgpu_frames_upload(ctx, t->own, slot, 1, host_pix));
+  SFM_TRY(sfmgpu_pyramid_build(ctx, t->own, slot, 1));
+  return tracker_reset_on(ctx, t, t->own, slot);
+}
+
+int sfmgpu_tracker_step(sfmgpu_ctx* ctx, sfmgpu_tracker* t, const uint8_t* host_pix, int w, int h, double* prev_xy,
+                        double* cur_xy, int32_t* ids, int cap, int* n_out) {
+  if (!ctx || !t || !host_pix) return SFMGPU_E_ARG;
+  SFM_TRY(tracker_own_frames(ctx, t, w, h));
+  const int slot = (t->prev_frames == t->own && t->prev_index == 0) ? 1 : 0;
+  SFM_TRY(sfmgpu_frames_upload(ctx, t->own, slot, 1, host_pix));
+  SFM_TRY(sfmgpu_pyramid_build(ctx, t->own, slot, 1));
+  return tracker_step_on(ctx, t, t->own, slot, prev_xy, cur_xy, ids, cap, n_out);
+}
+
+int sfmgpu_tracker_step_frames(sfmgpu_ctx* ctx, sfmgpu_tracker* t, sfmgpu_frames* f, int frame, double* prev_xy,
+                               double* cur_xy, int32_t* ids, int cap, int* n_out) {
+  if (!ctx || !t || !f) return SFMGPU_E_ARG;
+  if (frame < 0 || frame >= f->n) return sfm_fail(ctx, SFMGPU_E_ARG, "tracker_step_frames: bad frame index");
+  if (f->levels != t->cfg.pyr_levels) return sfm_fail(ctx, SFMGPU_E_ARG, "tracker_step_frames: pyramid levels differ from cfg");
+  return tracker_step_on(ctx, t, f, frame, prev_xy, cur_xy, ids, cap, n_out);
+}
+
+int sfmgpu_tracker_tracks(sfmgpu_ctx* ctx, sfmgpu_tracker* t, double* xy, int32_t* ids, int cap, int* n_out) {
+  if (!ctx || !t) return SFMGPU_E_ARG;
+  if (n_out) *n_out = t->n;
+  if (t->n > cap) return sfm_fail(ctx, SFMGPU_E_CAPACITY, "tracker_tracks: %d tracks, room for %d", t->n, cap);
+  if (t->n > 0) {
+    if (xy) SFM_CUDA(ctx, cudaMemcpyAsync(xy, t->trk, (size_t)t->n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ids) SFM_CUDA(ctx, cudaMemcpyAsync(ids, t->ids, (size_t)t->n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return 0;
+}
+
+int sfmgpu_tracker_totals(sfmgpu_ctx* ctx, sfmgpu_tracker* t, long long* n_track_steps, long long* n_lk_iters) {
+  if (!ctx || !t) return SFMGPU_E_ARG;
+  unsigned long long tt[4];
+  SFM_CUDA(ctx, cudaMemcpyAsync(tt, t->tot, sizeof tt, cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n_track_steps) *n_track_steps = t->track_steps;
+  if (n_lk_iters) *n_lk_iters = (long long)tt[2];
+  return 0;
+}
+
+}  // extern "C"

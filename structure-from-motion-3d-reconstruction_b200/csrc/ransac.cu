@@ -1,0 +1,246 @@
+// ransac.cu — essential-matrix hypothesis scoring: Sampson error + exact inlier counts, winner and its mask.
+//
+// Replaces (reference cpp/src/templering_sfm.cpp): sampson_err :629-638 and the scoring loop of
+// find_E_ransac :667-676 (inlier iff e < thr; winner = FIRST hypothesis with the strictly largest count;
+// its inlier indices ascending).  Hypotheses are produced by the caller (the reference's own seeded sampling
+// :657-665 + eight_point_E) so "same seeded hypotheses" holds by construction.
+//
+// Exactness: every count is bit-exact.  The Sampson numerator/denominator are evaluated in FP64 in the
+// reference's operation order (this file is compiled with -fmad=false).  The reference's test
+// fl(n2/den) < thr is decided without the division whenever n2 is outside a 2^-50 relative band around
+// thr*den (proof in DESIGN.md §RANSAC); inside the band the literal division is executed.
+//
+// Mapping: a thread owns PTS correspondences in registers; a block walks a chunk of hypotheses whose nine
+// coefficients are staged in shared memory; per-hypothesis block counts are reduced with ballots + shared
+// atomics and added to counts[h] with one global atomic per (block, hypothesis).  Operand traffic is
+// negligible (~4000 flop/B at 64k x 10k): the bound is the FP64 CUDA-core pipe, tensor cores are not used
+// (no dense contraction).
+#include "common.cuh"
+
+namespace {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_PTS = 2;        // points per thread
+constexpr int RS_HCHUNK = 64;    // hypotheses staged per block iteration
+
+// Reference-order Sampson pieces; returns n2 = num*num and den.
+__device__ __forceinline__ void sampson_parts(const double* __restrict__ E, double x, double y, double xp, double yp, double& n2,
+                                              double& den) {
+  const double ex = (E[0] * x + E[1] * y) + E[2];  // E*[x y 1]; the *1.0 of the reference is exact
+  const double ey = (E[3] * x + E[4] * y) + E[5];
+  const double ez = (E[6] * x + E[7] * y) + E[8];
+  const double tx = (E[0] * xp + E[3] * yp) + E[6];  // E^T*[xp yp 1], z row unused
+  const double ty = (E[1] * xp + E[4] * yp) + E[7];
+  const double num = (xp * ex + yp * ey) + ez;
+  den = (((ex * ex + ey * ey) + tx * tx) + ty * ty) + 1e-12;
+  n2 = num * num;
+}
+
+__device__ __forceinline__ bool is_inlier(double n2, double den, double thr, double thr_lo, double thr_hi) {
+  if (n2 < thr_lo * den) return true;    // n2/den < thr(1-2^-51)  =>  fl(n2/den) < thr
+  if (n2 > thr_hi * den) return false;   // n2/den > thr(1+2^-51)  =>  fl(n2/den) >= thr
+  return (n2 / den) < thr;               // inside the band: the reference's literal test
+}
+
+__global__ void __launch_bounds__(RS_THREADS) ransac_count_kernel(const double2* __restrict__ xi, const double2* __restrict__ xj,
+                                                                 int n, const double* __restrict__ E, int H, int h_per_block,
+                                                                 double thr, double thr_lo, double thr_hi,
+                                                                 int* __restrict__ counts) {
+  __shared__ double sE[RS_HCHUNK * 9];
+  __shared__ int sC[RS_HCHUNK];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int p0 = (blockIdx.x * RS_THREADS + tid) * RS_PTS;
+  double x[RS_PTS], y[RS_PTS], xp[RS_PTS], yp[RS_PTS];
+  bool valid[RS_PTS];
+#pragma unroll
+  for (int k = 0; k < RS_PTS; k++) {
+    valid[k] = p0 + k < n;
+    const double2 a = valid[k] ? xi[p0 + k] : make_double2(0, 0);
+    const double2 b = valid[k] ? xj[p0 + k] : make_double2(0, 0);
+    x[k] = a.x;
+    y[k] = a.y;
+    xp[k] = b.x;
+    yp[k] = b.y;
+  }
+  const int h_begin = blockIdx.y * h_per_block;
+  const int h_end = min(H, h_begin + h_per_block);
+  for (int hc = h_begin; hc < h_end; hc += RS_HCHUNK) {
+    const int nh = min(RS_HCHUNK, h_end - hc);
+    __syncthreads();
+    for (int i = tid; i < nh * 9; i += RS_THREADS) sE[i] = E[(size_t)hc * 9 + i];
+    if (tid < RS_HCHUNK) sC[tid] = 0;
+    __syncthreads();
+    for (int h = 0; h < nh; h++) {
+      const double* e = sE + h * 9;
+      int c = 0;
+#pragma unroll
+      for (int k = 0; k < RS_PTS; k++) {
+        double n2, den;
+        sampson_parts(e, x[k], y[k], xp[k], yp[k], n2, den);
+        c += (valid[k] && is_inlier(n2, den, thr, thr_lo, thr_hi)) ? 1 : 0;
+      }
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (lane == 0 && c) atomicAdd(&sC[h], c);
+    }
+    __syncthreads();
+    if (tid < nh && sC[tid]) atomicAdd(&counts[hc + tid], sC[tid]);
+  }
+}
+
+// Winner: largest count, lowest index on ties; -1 when every count is 0 (best_inl starts empty, :673).
+__global__ void __launch_bounds__(1024) ransac_argmax_kernel(const int* __restrict__ counts, int H, int* __restrict__ best) {
+  __shared__ unsigned long long sbest[32];
+  // key = count << 32 | (0xFFFFFFFF - h): max key = max count then min h
+  unsigned long long key = 0;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    const unsigned long long k = ((unsigned long long)(unsigned)counts[h] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)h);
+    key = k > key ? k : key;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+    key = other > key ? other : key;
+  }
+  if ((threadIdx.x & 31) == 0) sbest[threadIdx.x >> 5] = key;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    key = threadIdx.x < (blockDim.x >> 5) ? sbest[threadIdx.x] : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+      key = other > key ? other : key;
+    }
+    if (threadIdx.x == 0) {
+      const int cnt = (int)(key >> 32);
+      best[0] = cnt > 0 ? (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull)) : -1;
+      best[1] = cnt;
+    }
+  }
+}
+
+// Inlier indices of the winner, ascending (:669-672), by one block with an ordered ballot compaction.
+__global__ void __launch_bounds__(1024) ransac_mask_kernel(const double2* __restrict__ xi, const double2* __restrict__ xj, int n,
+                                                          const double* __restrict__ E, const int* __restrict__ best, double thr,
+                                                          int* __restrict__ inl) {
+  __shared__ int swarp[32];
+  __shared__ int sbase;
+  const int bh = best[0];
+  if (bh < 0) return;
+  const double* e = E + (size_t)bh * 9;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) sbase = 0;
+  __syncthreads();
+  for (int start = 0; start < n; start += blockDim.x) {
+    const int i = start + tid;
+    bool in = false;
+    if (i < n) {
+      double n2, den;
+      const double2 a = xi[i], b = xj[i];
+      sampson_parts(e, a.x, a.y, b.x, b.y, n2, den);
+      in = (n2 / den) < thr;  // literal
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, in);
+    if (lane == 0) swarp[warp] = __popc(m);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int wq = 0; wq < (int)(blockDim.x >> 5); wq++) {
+      const int c = swarp[wq];
+      before += wq < warp ? c : 0;
+      total += c;
+    }
+    const int base = sbase;
+    if (in) inl[base + before + __popc(m & ((1u << lane) - 1u))] = i;
+    __syncthreads();
+    if (tid == 0) sbase = base + total;
+    __syncthreads();
+  }
+}
+
+int score_resident(sfmgpu_ctx* ctx, double thr) {
+  const int n = ctx->rs_n, H = ctx->rs_H;
+  SFM_CUDA(ctx, cudaMemsetAsync(ctx->rs_counts.p, 0, (size_t)(H > 0 ? H : 1) * sizeof(int), ctx->stream));
+  int* best = (int*)ctx->rs_best.p;
+  if (H > 0 && n > 0) {
+    const unsigned gx = sfm_cdiv(n, RS_THREADS * RS_PTS);
+    // enough blocks to fill the machine several times over, whole chunks of hypotheses per block
+    long long want_y = ((long long)ctx->n_sm * 8 + gx - 1) / gx;
+    long long hpb = (H + want_y - 1) / want_y;
+    hpb = ((hpb + RS_HCHUNK - 1) / RS_HCHUNK) * RS_HCHUNK;
+    const unsigned gy = sfm_cdiv(H, hpb);
+    // thr_lo / thr_hi bracket thr by 2^-50 relative (see is_inlier)
+    const double eps = 8.8817841970012523e-16;  // 2^-50
+    SFM_LAUNCH(ctx, ransac_count_kernel, dim3(gx, gy), RS_THREADS, 0, (const double2*)ctx->rs_xi.p, (const double2*)ctx->rs_xj.p,
+               n, (const double*)ctx->rs_E.p, H, (int)hpb, thr, thr * (1.0 - eps), thr * (1.0 + eps), (int*)ctx->rs_counts.p);
+  }
+  SFM_LAUNCH(ctx, ransac_argmax_kernel, 1, 1024, 0, (const int*)ctx->rs_counts.p, H, best);
+  if (H > 0 && n > 0)
+    SFM_LAUNCH(ctx, ransac_mask_kernel, 1, 1024, 0, (const double2*)ctx->rs_xi.p, (const double2*)ctx->rs_xj.p, n,
+               (const double*)ctx->rs_E.p, (const int*)best, thr, (int*)ctx->rs_inl.p);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sfmgpu_ransac_upload(sfmgpu_ctx* ctx, const double* xi_xy, const double* xj_xy, int n, const double* E, int H) {
+  if (!ctx || n < 0 || H < 0) return sfm_fail(ctx, SFMGPU_E_ARG, "ransac_upload: bad sizes");
+  if ((n > 0 && (!xi_xy || !xj_xy)) || (H > 0 && !E)) return sfm_fail(ctx, SFMGPU_E_ARG, "ransac_upload: null pointer");
+  SFM_TRY(sfm_reserve(ctx, ctx->rs_xi, (size_t)(n + 1) * 16));
+  SFM_TRY(sfm_reserve(ctx, ctx->rs_xj, (size_t)(n + 1) * 16));
+  SFM_TRY(sfm_reserve(ctx, ctx->rs_E, (size_t)(H + 1) * 72));
+  SFM_TRY(sfm_reserve(ctx, ctx->rs_counts, (size_t)(H + 1) * 4));
+  SFM_TRY(sfm_reserve(ctx, ctx->rs_inl, (size_t)(n + 1) * 4));
+  SFM_TRY(sfm_reserve(ctx, ctx->rs_best, 16));
+  if (n > 0) {
+    SFM_CUDA(ctx, cudaMemcpyAsync(ctx->rs_xi.p, xi_xy, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    SFM_CUDA(ctx, cudaMemcpyAsync(ctx->rs_xj.p, xj_xy, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (H > 0) SFM_CUDA(ctx, cudaMemcpyAsync(ctx->rs_E.p, E, (size_t)H * 72, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->rs_n = n;
+  ctx->rs_H = H;
+  return 0;
+}
+
+int sfmgpu_ransac_score_resident(sfmgpu_ctx* ctx, double thr, int* best_h, int* best_n) {
+  if (!ctx) return SFMGPU_E_ARG;
+  if (!ctx->rs_best.p) return sfm_fail(ctx, SFMGPU_E_STATE, "ransac_score_resident: nothing uploaded");
+  SFM_TRY(score_resident(ctx, thr));
+  if (best_h || best_n) {
+    int hb[2];
+    SFM_CUDA(ctx, cudaMemcpyAsync(hb, ctx->rs_best.p, sizeof hb, cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (best_h) *best_h = hb[0];
+    if (best_n) *best_n = hb[1];
+  }
+  return 0;
+}
+
+int sfmgpu_ransac_download(sfmgpu_ctx* ctx, int32_t* counts, int32_t* best_inl, int cap_inl) {
+  if (!ctx) return SFMGPU_E_ARG;
+  if (!ctx->rs_best.p) return sfm_fail(ctx, SFMGPU_E_STATE, "ransac_download: nothing scored");
+  int hb[2];
+  SFM_CUDA(ctx, cudaMemcpyAsync(hb, ctx->rs_best.p, sizeof hb, cudaMemcpyDeviceToHost, ctx->stream));
+  if (counts && ctx->rs_H > 0)
+    SFM_CUDA(ctx, cudaMemcpyAsync(counts, ctx->rs_counts.p, (size_t)ctx->rs_H * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (best_inl && hb[0] >= 0) {
+    if (cap_inl < hb[1]) return sfm_fail(ctx, SFMGPU_E_CAPACITY, "ransac_download: %d inliers, room for %d", hb[1], cap_inl);
+    SFM_CUDA(ctx, cudaMemcpyAsync(best_inl, ctx->rs_inl.p, (size_t)hb[1] * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return 0;
+}
+
+int sfmgpu_ransac_score(sfmgpu_ctx* ctx, const double* xi_xy, const double* xj_xy, int n, const double* E, int H, double thr,
+                        int32_t* counts, int* best_h, int32_t* best_inl, int* best_n) {
+  if (!ctx) return SFMGPU_E_ARG;
+  SFM_TRY(sfmgpu_ransac_upload(ctx, xi_xy, xj_xy, n, E, H));
+  int bh = -1, bn = 0;
+  SFM_TRY(sfmgpu_ransac_score_resident(ctx, thr, &bh, &bn));
+  if (best_h) *best_h = bh;
+  if (best_n) *best_n = bn;
+  return sfmgpu_ransac_download(ctx, counts, best_inl, n);
+}
+
+}  // extern "C"

@@ -1,0 +1,386 @@
+"""ctypes binding of libsfmgpu.so (C ABI in include/sfmgpu.h) — plumbing for tests/, bench.py and the scheduler.
+
+The product is the CUDA library; this module only marshals numpy arrays through the C ABI.  There is no CPU
+fallback: if the library is missing or no B200 is visible, construction raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, "libsfmgpu.so")
+
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_vp = C.c_void_p
+_i = C.c_int
+_d = C.c_double
+_ll = C.c_longlong
+
+# every symbol include/sfmgpu.h declares (tests/test_abi.py checks the library exports exactly these)
+SYMBOLS = [
+    "sfmgpu_lkcfg_default", "sfmgpu_version", "sfmgpu_create", "sfmgpu_destroy", "sfmgpu_last_error", "sfmgpu_sync",
+    "sfmgpu_launch_count", "sfmgpu_timer_start", "sfmgpu_timer_stop", "sfmgpu_flush_l2", "sfmgpu_host_alloc",
+    "sfmgpu_host_free", "sfmgpu_frames_create", "sfmgpu_frames_destroy", "sfmgpu_frames_upload",
+    "sfmgpu_frames_upload_device", "sfmgpu_frames_synth", "sfmgpu_pyramid_build", "sfmgpu_frames_level_size",
+    "sfmgpu_frames_download", "sfmgpu_corner_candidates", "sfmgpu_corners", "sfmgpu_sort_perm_desc",
+    "sfmgpu_klt_track", "sfmgpu_pairs_create", "sfmgpu_pairs_destroy", "sfmgpu_pair_frontend", "sfmgpu_pairs_totals",
+    "sfmgpu_pairs_download", "sfmgpu_tracker_create", "sfmgpu_tracker_destroy", "sfmgpu_tracker_reset",
+    "sfmgpu_tracker_step", "sfmgpu_tracker_step_frames", "sfmgpu_tracker_tracks", "sfmgpu_tracker_totals",
+    "sfmgpu_ransac_score", "sfmgpu_ransac_upload", "sfmgpu_ransac_score_resident", "sfmgpu_ransac_download",
+]
+
+
+class LKCfg(C.Structure):
+    """sfmgpu_lkcfg == LKConfig (cpp/src/templering_sfm.cpp:307-316)."""
+    _fields_ = [("max_tracks", _i), ("min_tracks", _i), ("quality", _d), ("min_distance", _i), ("pyr_levels", _i),
+                ("win_radius", _i), ("iters", _i), ("fb_thresh", _d)]
+
+
+def lkcfg(**kw):
+    c = LKCfg(2200, 900, 0.01, 8, 3, 5, 10, 1.0)
+    for k, v in kw.items():
+        if not hasattr(c, k):
+            raise AttributeError(k)
+        setattr(c, k, v)
+    return c
+
+
+class SfmGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"sfmgpu error {code}: {msg}")
+        self.code = code
+
+
+def build_library(force=False):
+    """Compile libsfmgpu.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    args = ["make", "-C", _PKG, "-s", "-j8"] + (["-B"] if force else [])
+    subprocess.run(args, check=True)
+    return LIB_PATH
+
+
+def load_library():
+    if not os.path.exists(LIB_PATH):
+        raise SfmGpuError(-2, f"{LIB_PATH} is missing: build it with __graft_entry__.build() — there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    S = {
+        "sfmgpu_lkcfg_default": (None, [C.POINTER(LKCfg)]),
+        "sfmgpu_version": (_i, []),
+        "sfmgpu_create": (_i, [_i, C.POINTER(_vp)]),
+        "sfmgpu_destroy": (None, [_vp]),
+        "sfmgpu_last_error": (C.c_char_p, [_vp]),
+        "sfmgpu_sync": (_i, [_vp]),
+        "sfmgpu_launch_count": (_ll, [_vp]),
+        "sfmgpu_timer_start": (_i, [_vp]),
+        "sfmgpu_timer_stop": (_i, [_vp, C.POINTER(C.c_float)]),
+        "sfmgpu_flush_l2": (_i, [_vp, C.c_size_t]),
+        "sfmgpu_host_alloc": (_i, [_vp, C.c_size_t, C.POINTER(_vp)]),
+        "sfmgpu_host_free": (_i, [_vp, _vp]),
+        "sfmgpu_frames_create": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_vp)]),
+        "sfmgpu_frames_destroy": (None, [_vp, _vp]),
+        "sfmgpu_frames_upload": (_i, [_vp, _vp, _i, _i, _vp]),
+        "sfmgpu_frames_upload_device": (_i, [_vp, _vp, _i, _i, _vp, C.c_size_t]),
+        "sfmgpu_frames_synth": (_i, [_vp, _vp, _i, _i, C.c_uint32, _i]),
+        "sfmgpu_pyramid_build": (_i, [_vp, _vp, _i, _i]),
+        "sfmgpu_frames_level_size": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i)]),
+        "sfmgpu_frames_download": (_i, [_vp, _vp, _i, _i, _u8p]),
+        "sfmgpu_corner_candidates": (_i, [_vp, _vp, _i, _d, _i32p, _f64p, _i, C.POINTER(_i), C.POINTER(_d)]),
+        "sfmgpu_corners": (_i, [_vp, _vp, _i, _i, _d, _i, _f64p, C.POINTER(_i)]),
+        "sfmgpu_sort_perm_desc": (_i, [_vp, _f64p, _i, _i32p]),
+        "sfmgpu_klt_track": (_i, [_vp, _vp, _i, _i, _f64p, _i, _i, _i, _f64p, _f64p, _vp]),
+        "sfmgpu_pairs_create": (_i, [_vp, _i, _i, C.POINTER(_vp)]),
+        "sfmgpu_pairs_destroy": (None, [_vp, _vp]),
+        "sfmgpu_pair_frontend": (_i, [_vp, _vp, _i, _i, C.POINTER(LKCfg), _vp]),
+        "sfmgpu_pairs_totals": (_i, [_vp, _vp, C.POINTER(_ll), C.POINTER(_ll), C.POINTER(_ll)]),
+        "sfmgpu_pairs_download": (_i, [_vp, _vp, _i, _f64p, _f64p, _i, C.POINTER(_i), C.POINTER(_i)]),
+        "sfmgpu_tracker_create": (_i, [_vp, C.POINTER(LKCfg), C.POINTER(_vp)]),
+        "sfmgpu_tracker_destroy": (None, [_vp, _vp]),
+        "sfmgpu_tracker_reset": (_i, [_vp, _vp, _u8p, _i, _i]),
+        "sfmgpu_tracker_step": (_i, [_vp, _vp, _u8p, _i, _i, _vp, _vp, _vp, _i, C.POINTER(_i)]),
+        "sfmgpu_tracker_step_frames": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, C.POINTER(_i)]),
+        "sfmgpu_tracker_tracks": (_i, [_vp, _vp, _f64p, _i32p, _i, C.POINTER(_i)]),
+        "sfmgpu_tracker_totals": (_i, [_vp, _vp, C.POINTER(_ll), C.POINTER(_ll)]),
+        "sfmgpu_ransac_score": (_i, [_vp, _f64p, _f64p, _i, _f64p, _i, _d, _vp, C.POINTER(_i), _vp, C.POINTER(_i)]),
+        "sfmgpu_ransac_upload": (_i, [_vp, _f64p, _f64p, _i, _f64p, _i]),
+        "sfmgpu_ransac_score_resident": (_i, [_vp, _d, C.POINTER(_i), C.POINTER(_i)]),
+        "sfmgpu_ransac_download": (_i, [_vp, _vp, _vp, _i]),
+    }
+    for name, (res, args) in S.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+class Context:
+    """One CUDA device + stream (sfmgpu_ctx)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = _vp()
+        rc = self.lib.sfmgpu_create(device, C.byref(h))
+        if rc != 0:
+            raise SfmGpuError(rc, "sfmgpu_create failed: no usable CUDA device (this library has no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SfmGpuError(rc, self.lib.sfmgpu_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sfmgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self._ck(self.lib.sfmgpu_sync(self.h))
+
+    def launches(self):
+        return int(self.lib.sfmgpu_launch_count(self.h))
+
+    def timer_start(self):
+        self._ck(self.lib.sfmgpu_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        self._ck(self.lib.sfmgpu_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def flush_l2(self, nbytes=256 << 20):
+        self._ck(self.lib.sfmgpu_flush_l2(self.h, nbytes))
+
+    def pinned_empty(self, shape, dtype=np.uint8):
+        """numpy array backed by page-locked host memory (freed with the context)."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = _vp()
+        self._ck(self.lib.sfmgpu_host_alloc(self.h, max(n, 1), C.byref(p)))
+        buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    # ---- frames / pyramid ----------------------------------------------------------------------
+    def frames(self, w, h, nframes, levels=3):
+        return Frames(self, w, h, nframes, levels)
+
+    # ---- RANSAC scoring -------------------------------------------------------------------------
+    def ransac_score(self, xi, xj, E, thr, want_counts=True):
+        xi = np.ascontiguousarray(xi, np.float64).reshape(-1, 2)
+        xj = np.ascontiguousarray(xj, np.float64).reshape(-1, 2)
+        E = np.ascontiguousarray(E, np.float64).reshape(-1, 9)
+        n, H = len(xi), len(E)
+        counts = np.zeros(max(H, 1), np.int32) if want_counts else None
+        inl = np.zeros(max(n, 1), np.int32)
+        bh, bn = _i(-1), _i(0)
+        z2, z9 = np.zeros((1, 2)), np.zeros((1, 9))
+        self._ck(self.lib.sfmgpu_ransac_score(self.h, xi if n else z2, xj if n else z2, n, E if H else z9, H, thr,
+                                              _ptr(counts), C.byref(bh), _ptr(inl), C.byref(bn)))
+        return (counts[:H] if want_counts else None), bh.value, inl[:bn.value].copy()
+
+    def ransac_upload(self, xi, xj, E):
+        xi = np.ascontiguousarray(xi, np.float64).reshape(-1, 2)
+        xj = np.ascontiguousarray(xj, np.float64).reshape(-1, 2)
+        E = np.ascontiguousarray(E, np.float64).reshape(-1, 9)
+        self._ck(self.lib.sfmgpu_ransac_upload(self.h, xi, xj, len(xi), E, len(E)))
+
+    def ransac_score_resident(self, thr, fetch=True):
+        bh, bn = _i(-1), _i(0)
+        if fetch:
+            self._ck(self.lib.sfmgpu_ransac_score_resident(self.h, thr, C.byref(bh), C.byref(bn)))
+            return bh.value, bn.value
+        self._ck(self.lib.sfmgpu_ransac_score_resident(self.h, thr, None, None))
+        return None
+
+    def sort_perm_desc(self, keys):
+        keys = np.ascontiguousarray(keys, np.float64)
+        perm = np.zeros(max(len(keys), 1), np.int32)
+        self._ck(self.lib.sfmgpu_sort_perm_desc(self.h, keys if len(keys) else np.zeros(1), len(keys), perm))
+        return perm[:len(keys)]
+
+    def pairs(self, max_pairs, max_corners):
+        return Pairs(self, max_pairs, max_corners)
+
+    def tracker(self, cfg=None, **kw):
+        return Tracker(self, cfg if cfg is not None else lkcfg(**kw))
+
+
+class Frames:
+    """sfmgpu_frames: F images of one size with their pyramids, resident in HBM."""
+
+    def __init__(self, ctx, w, h, nframes, levels):
+        self.ctx, self.w, self.h, self.n, self.levels = ctx, w, h, nframes, levels
+        p = _vp()
+        ctx._ck(ctx.lib.sfmgpu_frames_create(ctx.h, w, h, nframes, levels, C.byref(p)))
+        self.h_ = p
+
+    def close(self):
+        if getattr(self, "h_", None) and self.ctx.h:
+            self.ctx.lib.sfmgpu_frames_destroy(self.ctx.h, self.h_)
+        self.h_ = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, first, imgs):
+        imgs = np.ascontiguousarray(imgs, np.uint8)
+        if imgs.ndim == 2:
+            imgs = imgs[None]
+        assert imgs.shape[1:] == (self.h, self.w), (imgs.shape, self.h, self.w)
+        self.ctx._ck(self.ctx.lib.sfmgpu_frames_upload(self.ctx.h, self.h_, first, len(imgs), imgs.ctypes.data_as(_vp)))
+        self._keep = imgs  # keep the host buffer alive until the stream has consumed it
+
+    def upload_ptr(self, first, count, host_ptr):
+        self.ctx._ck(self.ctx.lib.sfmgpu_frames_upload(self.ctx.h, self.h_, first, count, host_ptr))
+
+    def synth(self, first, count, seed, t0):
+        self.ctx._ck(self.ctx.lib.sfmgpu_frames_synth(self.ctx.h, self.h_, first, count, seed & 0xFFFFFFFF, t0))
+
+    def build_pyramid(self, first=0, count=None):
+        self.ctx._ck(self.ctx.lib.sfmgpu_pyramid_build(self.ctx.h, self.h_, first, self.n - first if count is None else count))
+
+    def level_size(self, level):
+        w, h = _i(0), _i(0)
+        self.ctx._ck(self.ctx.lib.sfmgpu_frames_level_size(self.h_, level, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def download(self, frame, level=0):
+        w, h = self.level_size(level)
+        out = np.zeros((h, w), np.uint8) if w * h else np.zeros((h, w), np.uint8)
+        if w * h:
+            self.ctx._ck(self.ctx.lib.sfmgpu_frames_download(self.ctx.h, self.h_, frame, level, out))
+        return out
+
+    def candidates(self, frame, quality=0.01):
+        cap = self.w * self.h
+        xy = np.zeros((cap, 2), np.int32)
+        s = np.zeros(cap, np.float64)
+        n, mx = _i(0), _d(0)
+        self.ctx._ck(self.ctx.lib.sfmgpu_corner_candidates(self.ctx.h, self.h_, frame, quality, xy, s, cap, C.byref(n),
+                                                           C.byref(mx)))
+        return xy[:n.value].copy(), s[:n.value].copy(), mx.value
+
+    def corners(self, frame, max_corners, quality=0.01, min_dist=8):
+        xy = np.zeros((max(1, max_corners), 2), np.float64)
+        n = _i(0)
+        self.ctx._ck(self.ctx.lib.sfmgpu_corners(self.ctx.h, self.h_, frame, max_corners, quality, min_dist, xy, C.byref(n)))
+        return xy[:n.value].copy()
+
+    def klt_track(self, frame_a, frame_b, p0, radius=5, iters=10, count=False):
+        p0 = np.ascontiguousarray(p0, np.float64).reshape(-1, 2)
+        n = len(p0)
+        p1, pb = np.zeros((max(n, 1), 2)), np.zeros((max(n, 1), 2))
+        nit = np.zeros(max(n, 1), np.int32)
+        self.ctx._ck(self.ctx.lib.sfmgpu_klt_track(self.ctx.h, self.h_, frame_a, frame_b, p0 if n else np.zeros((1, 2)), n,
+                                                   radius, iters, p1, pb, _ptr(nit)))
+        return (p1[:n], pb[:n], nit[:n]) if count else (p1[:n], pb[:n])
+
+
+class Pairs:
+    """sfmgpu_pairs: device-resident results of a batch of frame pairs."""
+
+    def __init__(self, ctx, max_pairs, max_corners):
+        self.ctx, self.max_pairs, self.cap = ctx, max_pairs, max(1, max_corners)
+        p = _vp()
+        ctx._ck(ctx.lib.sfmgpu_pairs_create(ctx.h, max_pairs, max_corners, C.byref(p)))
+        self.h_ = p
+
+    def close(self):
+        if getattr(self, "h_", None) and self.ctx.h:
+            self.ctx.lib.sfmgpu_pairs_destroy(self.ctx.h, self.h_)
+        self.h_ = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, frames, first_frame, npairs, cfg):
+        self.ctx._ck(self.ctx.lib.sfmgpu_pair_frontend(self.ctx.h, frames.h_, first_frame, npairs, C.byref(cfg), self.h_))
+
+    def totals(self):
+        a, b, c = _ll(0), _ll(0), _ll(0)
+        self.ctx._ck(self.ctx.lib.sfmgpu_pairs_totals(self.ctx.h, self.h_, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def download(self, pair):
+        li, lj = np.zeros((self.cap, 2)), np.zeros((self.cap, 2))
+        nk, nc = _i(0), _i(0)
+        self.ctx._ck(self.ctx.lib.sfmgpu_pairs_download(self.ctx.h, self.h_, pair, li, lj, self.cap, C.byref(nk), C.byref(nc)))
+        return li[:nk.value].copy(), lj[:nk.value].copy(), nc.value
+
+
+class Tracker:
+    """sfmgpu_tracker: KLTTracker twin (reset / step / tracks)."""
+
+    def __init__(self, ctx, cfg):
+        self.ctx, self.cfg = ctx, cfg
+        p = _vp()
+        ctx._ck(ctx.lib.sfmgpu_tracker_create(ctx.h, C.byref(cfg), C.byref(p)))
+        self.h_ = p
+        self.cap = max(1, cfg.max_tracks) + 1
+
+    def close(self):
+        if getattr(self, "h_", None) and self.ctx.h:
+            self.ctx.lib.sfmgpu_tracker_destroy(self.ctx.h, self.h_)
+        self.h_ = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        self.ctx._ck(self.ctx.lib.sfmgpu_tracker_reset(self.ctx.h, self.h_, img, img.shape[1], img.shape[0]))
+
+    def _outs(self, fetch):
+        if not fetch:
+            return None, None, None
+        return np.zeros((self.cap, 2)), np.zeros((self.cap, 2)), np.zeros(self.cap, np.int32)
+
+    def step(self, img, fetch=True):
+        img = np.ascontiguousarray(img, np.uint8)
+        prev, cur, ids = self._outs(fetch)
+        n = _i(0)
+        self.ctx._ck(self.ctx.lib.sfmgpu_tracker_step(self.ctx.h, self.h_, img, img.shape[1], img.shape[0], _ptr(prev),
+                                                      _ptr(cur), _ptr(ids), self.cap, C.byref(n)))
+        if not fetch:
+            return n.value
+        return prev[:n.value].copy(), cur[:n.value].copy(), ids[:n.value].copy()
+
+    def step_frames(self, frames, frame, fetch=True):
+        prev, cur, ids = self._outs(fetch)
+        n = _i(0)
+        self.ctx._ck(self.ctx.lib.sfmgpu_tracker_step_frames(self.ctx.h, self.h_, frames.h_, frame, _ptr(prev), _ptr(cur),
+                                                             _ptr(ids), self.cap, C.byref(n)))
+        if not fetch:
+            return n.value
+        return prev[:n.value].copy(), cur[:n.value].copy(), ids[:n.value].copy()
+
+    def tracks(self):
+        xy, ids = np.zeros((self.cap, 2)), np.zeros(self.cap, np.int32)
+        n = _i(0)
+        self.ctx._ck(self.ctx.lib.sfmgpu_tracker_tracks(self.ctx.h, self.h_, xy, ids, self.cap, C.byref(n)))
+        return xy[:n.value].copy(), ids[:n.value].copy()
+
+    def totals(self):
+        a, b = _ll(0), _ll(0)
+        self.ctx._ck(self.ctx.lib.sfmgpu_tracker_totals(self.ctx.h, self.h_, C.byref(a), C.byref(b)))
+        return a.value, b.value

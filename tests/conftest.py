@@ -1,0 +1,66 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "structure-from-motion-3d-reconstruction_b200"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def port():
+    import oracle
+    return oracle.port()
+
+
+@pytest.fixture(scope="session")
+def ref():
+    import oracle
+    r = oracle.ref()
+    if r is None:
+        pytest.skip("compiled reference (oracle/_ref/libsfmref.so) not available on this machine")
+    return r
+
+
+@pytest.fixture(scope="session")
+def checker():
+    """The strongest CPU checker available: the compiled reference if present, else the port."""
+    import oracle
+    return oracle.best()[0]
+
+
+@pytest.fixture(scope="session")
+def ctx():
+    import sfmgpu
+    c = sfmgpu.Context(0)  # raises when the library or the GPU is missing: no CPU fallback
+    yield c
+    c.close()
+
+
+TEMPLE_K = np.array([1520.4, 0, 302.32, 0, 1525.9, 246.87, 0, 0, 1.0]).reshape(3, 3)
+
+
+def two_view_scene(n, seed=777, outlier_frac=0.3, sigma=0.3):
+    """synthetic two-view correspondences in pixels (numpy PCG64, deterministic)."""
+    rng = np.random.default_rng(seed)
+    X = np.stack([rng.uniform(-0.5, 0.5, n), rng.uniform(-0.4, 0.4, n), rng.uniform(1.5, 2.5, n)], 1)
+    w = np.array([0.02, -0.15, 0.01])
+    th = np.linalg.norm(w)
+    k = w / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    R = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+    t = np.array([0.2, 0.01, 0.03])
+    X2 = X @ R.T + t
+    pi = (X / X[:, 2:3]) @ TEMPLE_K.T
+    pj = (X2 / X2[:, 2:3]) @ TEMPLE_K.T
+    pi, pj = pi[:, :2] + rng.normal(0, sigma, (n, 2)), pj[:, :2] + rng.normal(0, sigma, (n, 2))
+    out = rng.random(n) < outlier_frac
+    pj[out] = np.stack([rng.uniform(0, 640, out.sum()), rng.uniform(0, 480, out.sum())], 1)
+    return np.ascontiguousarray(pi), np.ascontiguousarray(pj)

@@ -1,0 +1,258 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU checker (compiled reference when
+oracle/_ref is present, else the port) and against the committed golden vectors.
+
+Bars (BASELINE.json north_star): pyramid bytes, corner candidates, corners, NMS survivors, std::sort permutation,
+inlier counts / winner / mask: BIT-EXACT.  KLT positions: within 1e-3 px (KLT_TOL); measured deviation is ~1e-11.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import TEMPLE_K, two_view_scene
+from sfmgpu import synth
+import sfmgpu
+
+pytestmark = pytest.mark.gpu
+KLT_TOL = 1e-3  # px, the tolerance north_star states
+W, H, SEED = 320, 240, 20261018
+
+
+def _images():
+    rng = np.random.default_rng(3)
+    return {
+        "kat": synth.kat_image(320, 200),
+        "synth": synth.frame(11, 0, 320, 240),
+        "ties": (synth.frame(12, 0, 200, 160) >> 4 << 4),
+        "noise_odd": rng.integers(0, 256, (97, 131), dtype=np.uint8),
+        "flat": np.full((24, 40), 77, np.uint8),
+        "tiny": rng.integers(0, 256, (4, 9), dtype=np.uint8),
+        "one_bright": np.pad(np.full((1, 1), 255, np.uint8), 20),
+        "wide": synth.frame(13, 5, 700, 90),
+    }
+
+
+def _frames(ctx, imgs, levels=3):
+    imgs = [np.ascontiguousarray(i) for i in imgs]
+    f = ctx.frames(imgs[0].shape[1], imgs[0].shape[0], len(imgs), levels)
+    f.upload(0, np.stack(imgs))
+    f.build_pyramid()
+    return f
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "frontend_golden.npz"))
+
+
+# ---- synthetic generator ----------------------------------------------------------------------------------
+def test_device_generator_matches_numpy(ctx):
+    for (w, h) in [(320, 240), (333, 77)]:
+        f = ctx.frames(w, h, 4, 1)
+        f.synth(0, 4, 77, 62)  # covers the triangle-wave turn at t = 64
+        for k in range(4):
+            assert np.array_equal(f.download(k, 0), synth.frame(77, 62 + k, w, h))
+
+
+# ---- pyramid -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(_images()))
+@pytest.mark.parametrize("levels", [1, 2, 3, 4, 5])
+def test_pyramid(ctx, checker, name, levels):
+    img = _images()[name]
+    f = _frames(ctx, [img, img[::-1].copy()], levels)
+    for k, im in enumerate([img, img[::-1].copy()]):
+        want = checker.build_pyr(im, levels)
+        for l in range(levels):
+            got = f.download(k, l)
+            assert got.shape == want[l].shape and np.array_equal(got, want[l]), (name, k, l)
+
+
+def test_pyramid_golden(ctx, g):
+    f = _frames(ctx, [synth.frame(SEED, 0, W, H)])
+    assert np.array_equal(f.download(0, 1), g["pyr_l1"]) and np.array_equal(f.download(0, 2), g["pyr_l2"])
+
+
+# ---- corners -----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(_images()))
+def test_candidates_bit_exact(ctx, port, name):
+    img = _images()[name]
+    f = _frames(ctx, [img], 1)
+    for q in (0.01, 0.3, 0.0, 1.0):
+        xy, s, mx = f.candidates(0, q)
+        wxy, ws, wmx = port.candidates(img, q)
+        assert mx == wmx, (name, q)
+        assert np.array_equal(xy, wxy) and np.array_equal(s.view(np.uint64), ws.view(np.uint64)), (name, q)
+
+
+@pytest.mark.parametrize("n,distinct", [(0, 1), (1, 1), (16, 2), (17, 2), (33, 1), (1000, 3), (2049, 5), (5000, 40), (70000, 200),
+                                        (70000, 10**6), (300000, 1000)])
+def test_device_std_sort_permutation(ctx, port, n, distinct):
+    rng = np.random.default_rng(n + distinct)
+    for variant in range(3):
+        keys = rng.integers(0, distinct, n).astype(np.float64)
+        if variant == 1:
+            keys = np.sort(keys)[::-1].copy()
+        if variant == 2:
+            keys = np.sort(keys).copy()
+        assert np.array_equal(ctx.sort_perm_desc(keys), port.sort_perm_desc(keys)), (n, distinct, variant)
+
+
+@pytest.mark.parametrize("name", list(_images()))
+@pytest.mark.parametrize("mc,q,d", [(2200, 0.01, 8), (50, 0.2, 3), (0, 0.01, 8), (300, 0.0, 1), (100, 0.01, 0), (4000, 0.001, 2),
+                                    (500, 0.01, 25)])
+def test_corners_bit_exact(ctx, checker, name, mc, q, d):
+    img = _images()[name]
+    f = _frames(ctx, [img], 1)
+    got, want = f.corners(0, mc, q, d), checker.shi_tomasi(img, mc, q, d)
+    assert got.shape == want.shape and np.array_equal(got, want), (name, mc, q, d, len(got), len(want))
+
+
+def test_corners_golden(ctx, g):
+    f0 = synth.frame(SEED, 0, W, H)
+    f = _frames(ctx, [f0, f0 >> 4 << 4, synth.kat_image(W, H)], 1)
+    assert np.array_equal(f.corners(0, 400), g["corners"])
+    assert np.array_equal(f.corners(1, 400), g["corners_ties"])
+    assert np.array_equal(f.corners(2, 600), g["corners_kat"])
+
+
+def test_corners_larger_image(ctx, checker):
+    img = synth.frame(5, 9, 1280, 720)
+    f = _frames(ctx, [img], 1)
+    assert np.array_equal(f.corners(0, 3000), checker.shi_tomasi(img, 3000))
+
+
+# ---- KLT ---------------------------------------------------------------------------------------------------------
+def _klt_close(a, b):
+    return np.array_equal(np.isnan(a), np.isnan(b)) and np.nanmax(np.abs(a - b), initial=0.0) <= KLT_TOL
+
+
+@pytest.mark.parametrize("lv,r,it", [(3, 5, 10), (1, 3, 4), (4, 2, 7), (2, 7, 3), (3, 10, 2)])
+def test_klt_positions(ctx, checker, lv, r, it):
+    rng = np.random.default_rng(5)
+    f0, f1 = synth.frame(21, 0, 320, 240), synth.frame(21, 3, 320, 240)
+    pts = np.concatenate([checker.shi_tomasi(f0, 150), rng.uniform(-8, 330, (80, 2)) * [1, 0.75],
+                          [[0.0, 0.0], [318.0, 238.0], [319.5, 100.25], [127.99999999999999, 64.0], [1e12, 5.0],
+                           [np.nan, 3.0], [-1e300, 1e300]]])
+    f = _frames(ctx, [f0, f1], lv)
+    p1, pb, nit = f.klt_track(0, 1, pts, r, it, count=True)
+    w1, wb = checker.klt_track(f0, f1, pts, lv, r, it)
+    assert _klt_close(p1, w1) and _klt_close(pb, wb)
+    dev = max(np.nanmax(np.abs(p1[:230] - w1[:230])), np.nanmax(np.abs(pb[:230] - wb[:230])))
+    print(f"klt max deviation {dev:.3e} px")
+    assert dev < 1e-6  # far inside the budget; a regression here means the arithmetic changed
+
+
+def test_klt_noise_images(ctx, checker):
+    rng = np.random.default_rng(8)
+    n0, n1 = rng.integers(0, 256, (200, 300), dtype=np.uint8), rng.integers(0, 256, (200, 300), dtype=np.uint8)
+    pts = rng.uniform(0, 300, (300, 2)) * [1, 0.66]
+    f = _frames(ctx, [n0, n1], 3)
+    p1, pb = f.klt_track(0, 1, pts)
+    w1, wb = checker.klt_track(n0, n1, pts)
+    assert _klt_close(p1, w1) and _klt_close(pb, wb)
+
+
+def test_klt_golden(ctx, g):
+    f = _frames(ctx, [synth.frame(SEED, 0, W, H), synth.frame(SEED, 1, W, H)])
+    p1, pb = f.klt_track(0, 1, g["corners"].astype(np.float64)[:200])
+    assert _klt_close(p1, g["klt_p1"]) and _klt_close(pb, g["klt_pb"])
+
+
+def test_klt_iteration_count(ctx, port):
+    f0, f1 = synth.frame(21, 0, 320, 240), synth.frame(21, 1, 320, 240)
+    pts = port.shi_tomasi(f0, 100)
+    f = _frames(ctx, [f0, f1])
+    _, _, nit = f.klt_track(0, 1, pts, count=True)
+    _, _, want = port.klt_track(f0, f1, pts, count=True)
+    assert np.array_equal(nit, want)
+
+
+# ---- stateful tracker ---------------------------------------------------------------------------------------------
+def test_tracker_sequence(ctx, checker):
+    kw = dict(max_tracks=150, min_tracks=120, quality=0.01, min_distance=8, levels=3, radius=5, iters=10, fb=1.0)
+    want = checker.tracker(**kw)
+    got = ctx.tracker(max_tracks=150, min_tracks=120)
+    for t in [0, 1, 2, 40, 41, 42]:
+        img = synth.frame(SEED, t, W, H)
+        wp, wc, wi = want.step(img)
+        gp, gc, gi = got.step(img)
+        assert np.array_equal(gi, wi), t
+        assert _klt_close(gp, wp) and _klt_close(gc, wc), t
+        wxy, wid = want.tracks()
+        gxy, gid = got.tracks()
+        assert np.array_equal(gid, wid) and _klt_close(gxy, wxy), t
+
+
+def test_tracker_resident_frames_equals_host_fed(ctx):
+    imgs = [synth.frame(SEED, t, W, H) for t in range(4)]
+    f = _frames(ctx, imgs)
+    a, b = ctx.tracker(max_tracks=150, min_tracks=120), ctx.tracker(max_tracks=150, min_tracks=120)
+    for k, img in enumerate(imgs):
+        ra, rb = a.step(img), b.step_frames(f, k)
+        for x, y in zip(ra, rb):
+            assert np.array_equal(x, y)
+
+
+# ---- RANSAC scoring ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,H", [(300, 40), (2200, 250), (10000, 64), (9, 3), (513, 129)])
+def test_ransac_counts_bit_exact(ctx, checker, port, n, H):
+    pi, pj = two_view_scene(n, seed=n + H)
+    xi, xj = port.norm_points(TEMPLE_K, pi), port.norm_points(TEMPLE_K, pj)
+    E, _ = checker.ransac_hypotheses(xi, xj, H)
+    for thr in (1e-3, 2e-3, 1e-6, 0.0, 1e3):
+        counts, bh, inl = ctx.ransac_score(xi, xj, E, thr)
+        wc, wb, wi = checker.ransac_score(xi, xj, E, thr)
+        assert np.array_equal(counts, wc) and bh == wb and np.array_equal(inl, wi), (n, H, thr)
+
+
+def test_ransac_threshold_band_takes_the_literal_division(ctx, port):
+    # thresholds placed exactly ON computed errors: the division-free screen must hand over to the exact test
+    pi, pj = two_view_scene(400, seed=4)
+    xi, xj = port.norm_points(TEMPLE_K, pi), port.norm_points(TEMPLE_K, pj)
+    E, _ = port.ransac_hypotheses(xi, xj, 8)
+    for h in range(8):
+        e = np.array([port.sampson(E[h], xi[i], xj[i]) for i in range(0, 400, 37)])
+        for thr in e:
+            for t in (thr, np.nextafter(thr, 0), np.nextafter(thr, 1)):
+                counts, bh, inl = ctx.ransac_score(xi, xj, E, float(t))
+                wc, wb, wi = port.ransac_score(xi, xj, E, float(t))
+                assert np.array_equal(counts, wc) and bh == wb and np.array_equal(inl, wi)
+
+
+def test_ransac_golden(ctx, g):
+    counts, bh, inl = ctx.ransac_score(g["rs_xi"], g["rs_xj"], g["rs_E"], 1e-3)
+    assert np.array_equal(counts, g["rs_counts"]) and bh == g["rs_best"][0] and np.array_equal(inl, g["rs_inl"])
+
+
+def test_ransac_degenerate(ctx):
+    counts, bh, inl = ctx.ransac_score(np.zeros((0, 2)), np.zeros((0, 2)), np.zeros((3, 9)), 1e-3)
+    assert counts.tolist() == [0, 0, 0] and bh == -1 and len(inl) == 0
+
+
+# ---- batched two-view front end ----------------------------------------------------------------------------------------
+def test_pair_frontend_batch(ctx, checker, g):
+    imgs = [synth.frame(SEED, t, W, H) for t in range(6)]
+    f = _frames(ctx, imgs)
+    cfg = sfmgpu.lkcfg(max_tracks=300)
+    pairs = ctx.pairs(5, 300)
+    pairs.run(f, 0, 5, cfg)
+    nc_tot, nk_tot, nit_tot = pairs.totals()
+    cs = ks = 0
+    for p in range(5):
+        li, lj, nc = pairs.download(p)
+        wl, wj, wnc = checker.pair_frontend(imgs[p], imgs[p + 1], 300)
+        assert nc == wnc and np.array_equal(li, wl) and _klt_close(lj, wj), p
+        cs, ks = cs + nc, ks + len(li)
+    assert (nc_tot, nk_tot) == (cs, ks) and nit_tot > 0
+    li, lj, nc = pairs.download(2)
+    assert nc == g["pair_nc"][0] and np.array_equal(li, g["pair_li"]) and _klt_close(lj, g["pair_lj"])
+
+
+def test_errors_are_loud(ctx):
+    f = ctx.frames(64, 48, 2, 3)
+    with pytest.raises(sfmgpu.SfmGpuError):
+        f.klt_track(0, 5, np.zeros((1, 2)))
+    with pytest.raises(sfmgpu.SfmGpuError):
+        f.klt_track(0, 1, np.zeros((1, 2)), radius=50)
+    with pytest.raises(sfmgpu.SfmGpuError):
+        ctx.frames(0, 48, 2, 3)
