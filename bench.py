@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py — the front-end hot path on synthetic sequences, one JSON line on stdout.
+
+Workload at N GPUs (BASELINE.json configs[1], "C2"): every rank owns ONE synthetic 1080p 1,000-frame sequence
+(seed 20261018 + rank, integer generator of sfmgpu/synth.py) and runs the stateless two-view front end
+(cpp/src/templering_sfm.cpp:1836-1857) on all 999 frame pairs: 3-level pyramid for every frame, Shi-Tomasi +
+exact std::sort + greedy NMS (2000 corners/frame), forward+backward pyramidal LK with the fb test.  One "step" =
+one pass over the whole sequence.  Sequences are independent, so ranks shard with no data-path collective
+(weak scaling, SURVEY.md §8e mode 2); tracks and counts are gathered to rank 0 with NCCL at the end of a step.
+
+metric  : KLT feature-tracks/s (1 feature-track = fwd + bwd track_one + fb test of one corner);
+          the RANSAC half of BASELINE.json's metric (hyp x pts / s, config C4) is reported under "ransac".
+value   : inputs resident in HBM, CUDA events on the library's stream, max over ranks.
+e2e     : same step through the C ABI with HOST (pinned) frames: H2D of the sequence and D2H of all tracks inside
+          the timed region.
+--impl reference : the reference's own CPU front end (oracle/_ref = the unmodified TU compiled where it lies,
+          else the oracle port) on all host cores, bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "structure-from-motion-3d-reconstruction_b200"))
+
+W, H, NFRAMES, MAX_CORNERS, LEVELS = 1920, 1080, 1000, 2000, 3
+SEED0 = 20261018
+METRIC = "KLT feature-tracks/sec (+ RANSAC hyp*pts/sec under 'ransac')"
+UNIT = "feature-tracks/s"
+B_KLT = 2092.0      # algorithmic bytes per feature-track
+F_KLT_IT = 5045.0   # algorithmic FP64 flop per LK iteration
+F_RS = 35.0         # flop per hyp x pt
+RS_N, RS_H = 10000, 65536
+
+
+def workload_cfg(n_gpus, nframes):
+    return {
+        "workload": f"C2: synthetic 1080p {nframes}-frame sequence per GPU, pair-mode front end "
+                    f"(pyramid L=3 + Shi-Tomasi/NMS {MAX_CORNERS} corners/frame + fwd/bwd KLT r=5 iters=10 + fb<1.0)",
+        "frames_per_gpu": nframes, "pairs_per_gpu": nframes - 1, "width": W, "height": H, "max_corners": MAX_CORNERS,
+        "pyr_levels": LEVELS, "sharding": f"sequence-per-rank x{n_gpus} (no data-path collective; NCCL gather of results)",
+        "l2_policy": "inputs (2.07 GB of frames per GPU) exceed the 126 MB L2; no explicit flush needed",
+        "ransac_workload": f"C4: {RS_H} hypotheses x {RS_N} correspondences, thr 1e-3",
+    }
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.p, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json (of measured)"
+        except Exception:
+            pass
+    return 6650.0, "B200_PROFILING.md fallback (of fallback)"
+
+
+def synthetic_hypotheses(H, seed=5):
+    """Essential matrices [t]x R around the C4 scene's true motion (scoring cost does not depend on the values)."""
+    rng = np.random.default_rng(seed)
+    w = np.array([0.02, -0.15, 0.01]) + rng.normal(0, 0.05, (H, 3))
+    t = np.array([0.2, 0.01, 0.03]) + rng.normal(0, 0.05, (H, 3))
+    th = np.linalg.norm(w, axis=1, keepdims=True)
+    k = w / th
+    Kx = np.zeros((H, 3, 3))
+    Kx[:, 0, 1], Kx[:, 0, 2], Kx[:, 1, 0], Kx[:, 1, 2], Kx[:, 2, 0], Kx[:, 2, 1] = -k[:, 2], k[:, 1], k[:, 2], -k[:, 0], -k[:, 1], k[:, 0]
+    R = np.eye(3) + np.sin(th)[:, :, None] * Kx + (1 - np.cos(th))[:, :, None] * (Kx @ Kx)
+    t = t / np.linalg.norm(t, axis=1, keepdims=True)
+    Tx = np.zeros((H, 3, 3))
+    Tx[:, 0, 1], Tx[:, 0, 2], Tx[:, 1, 0], Tx[:, 1, 2], Tx[:, 2, 0], Tx[:, 2, 1] = -t[:, 2], t[:, 1], t[:, 2], -t[:, 0], -t[:, 1], t[:, 0]
+    return np.ascontiguousarray((Tx @ R).reshape(H, 9))
+
+
+def c4_points(n):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import TEMPLE_K, two_view_scene
+    pi, pj = two_view_scene(n)
+    Kinv = np.linalg.inv(TEMPLE_K)
+    def norm(p):
+        hp = np.concatenate([p, np.ones((len(p), 1))], 1) @ Kinv.T
+        return np.ascontiguousarray(hp[:, :2] / hp[:, 2:3])
+    return norm(pi), norm(pj)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """The reference's CPU front end on all host cores (rank 0 only), bounded sample of C2."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    chk, kind = oracle.best()
+    gen = oracle.port()
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, 64))
+    nfr = threads + 1  # one pair per thread and step
+    frames = gen.synth_frames(SEED0, 0, nfr, W, H, threads=threads)
+    times, tracks = [], 0
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        tracks, kept = chk.pair_frontend_mt(frames, MAX_CORNERS, threads)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times)) if times else float("nan")
+    val = tracks / (ms * 1e-3) if times else 0.0
+    # RANSAC scoring half, same threads
+    xi, xj = c4_points(RS_N)
+    Hs = 64 * threads
+    E = synthetic_hypotheses(Hs)
+    t0 = time.perf_counter()
+    chk.ransac_score_mt(xi, xj, E, 1e-3, threads)
+    rs = Hs * RS_N / (time.perf_counter() - t0)
+    sample = f"{threads} pairs of the C2 sequence per step (one per host thread), {tracks} feature-tracks; RANSAC {Hs} x {RS_N}"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_cfg(args.gpus, NFRAMES),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+                         "ransac_hyp_pts_per_s": rs},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=NFRAMES, help="frames per GPU (default: the C2 sequence length)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import sfmgpu
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = sfmgpu.Context(local)  # raises without the CUDA library / device: there is no CPU fallback
+    nfr, npairs = args.frames, args.frames - 1
+    cfg = sfmgpu.lkcfg(max_tracks=MAX_CORNERS, pyr_levels=LEVELS)
+    frames = ctx.frames(W, H, nfr, LEVELS)
+    pairs = ctx.pairs(npairs, MAX_CORNERS)
+    frames.synth(0, nfr, SEED0 + rank, 0)  # this rank's sequence, generated in HBM
+    ctx.sync()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.sync()
+
+    def step_resident():
+        frames.build_pyramid(0, nfr)
+        pairs.run(frames, 0, npairs, cfg)
+
+    # ---- value: inputs resident in HBM ---------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_resident()
+    ctx.sync()
+    tot = pairs.totals()  # raises if a frame overflowed the candidate capacity
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launches()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step_resident()
+    ms_total = ctx.timer_stop()
+    launches = ctx.launches() - l0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    n_tracks, n_kept, n_it = pairs.totals()
+
+    # ---- per-stage times (separate, untimed-for-value pass) + FP64 peak ---------------------------------------------
+    ctx.profile(True)
+    ctx.timer_start()
+    frames.build_pyramid(0, nfr)
+    pyr_ms = ctx.timer_stop()
+    pairs.run(frames, 0, npairs, cfg)
+    st = ctx.stage_times()
+    ctx.profile(False)
+    fp64_peak = ctx.fp64_peak()
+
+    # ---- e2e: host (pinned) frames in, all tracks out, copies inside the timed region --------------------------------
+    host = ctx.pinned_empty((nfr, H, W), np.uint8)
+    for k in range(0, nfr, 50):  # fill the pinned buffer with this rank's sequence (device generator == numpy twin)
+        for j in range(k, min(k + 50, nfr)):
+            host[j] = frames.download(j, 0)
+    li = ctx.pinned_empty((npairs, MAX_CORNERS, 2), np.float64)
+    lj = ctx.pinned_empty((npairs, MAX_CORNERS, 2), np.float64)
+    nk = ctx.pinned_empty((npairs,), np.int32)
+    nc = ctx.pinned_empty((npairs,), np.int32)
+    h2d = host.nbytes
+    d2h = li.nbytes + lj.nbytes + nk.nbytes + nc.nbytes
+
+    def step_e2e():
+        frames.upload_ptr(0, nfr, host.ctypes.data)
+        frames.build_pyramid(0, nfr)
+        pairs.run(frames, 0, npairs, cfg)
+        pairs.download_all(li, lj, nk, nc)
+
+    e2e_steps = max(1, min(args.steps, 3))
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    ctx.timer_start()
+    for _ in range(e2e_steps):
+        step_e2e()
+    e2e_ms_dev = ctx.timer_stop()
+    e2e_wall = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e2e_ms_dev, e2e_wall) / e2e_steps
+    assert int(nc.sum()) == n_tracks and int(nk.sum()) == n_kept, "e2e results differ from the resident run"
+
+    # ---- RANSAC half of the metric (C4), rank-local ---------------------------------------------------------------------
+    xi, xj = c4_points(RS_N)
+    E = synthetic_hypotheses(RS_H)
+    ctx.ransac_upload(xi, xj, E)
+    for _ in range(3):
+        ctx.ransac_score_resident(1e-3, fetch=False)
+    ctx.sync()
+    ctx.timer_start()
+    RS_REP = 10
+    for _ in range(RS_REP):
+        ctx.ransac_score_resident(1e-3, fetch=False)
+    rs_ms = ctx.timer_stop() / RS_REP
+    t0 = time.perf_counter()
+    counts, bh, inl = ctx.ransac_score(xi, xj, E, 1e-3)
+    rs_e2e_ms = (time.perf_counter() - t0) * 1e3
+
+    # ---- reduce over ranks: max time, summed work; gather per-pair counts to rank 0 with NCCL --------------------------------
+    ms_step = ms_total / args.steps
+    vals = torch.tensor([ms_step, e2e_ms, rs_ms, pyr_ms, st["klt"], st["corner_score"], st["corner_select"]], device="cuda",
+                        dtype=torch.float64)
+    work = torch.tensor([n_tracks, n_kept, n_it], device="cuda", dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+        mine = torch.from_numpy(np.stack([nc, nk]).astype(np.int32)).cuda()
+        gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, gathered, dst=0)  # the scheduler's result gather (tracks/inlier sets would ride the same call)
+    ms_step, e2e_ms, rs_ms, pyr_ms, klt_ms, cs_ms, sel_ms = [float(v) for v in vals.tolist()]
+    tracks_all, kept_all, it_all = [int(v) for v in work.tolist()]
+
+    if rank == 0:
+        hbm_peak, peak_src = measured_peaks()
+        value = tracks_all / (ms_step * 1e-3)
+        e2e_val = tracks_all / (e2e_ms * 1e-3)
+        per_rank_tracks = tracks_all / world
+        klt_bytes = B_KLT * per_rank_tracks
+        achieved = klt_bytes / (klt_ms * 1e-3) / 1e9
+        pyr_bytes = nfr * W * H * sum(0.25 ** l for l in range(LEVELS))
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_cfg(world, nfr),
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
+                    "ms_per_step": e2e_ms, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "klt_kernel<5,true>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "note": "KLT is bound by the FP64 CUDA-core pipe, not HBM (SURVEY.md §8d): see roofline_fp64"},
+            "roofline_fp64": {"kernel": "klt_kernel<5,true>", "achieved_tflops": F_KLT_IT * (it_all / world) / (klt_ms * 1e-3) / 1e12,
+                              "peak_tflops": fp64_peak, "peak_source": "in-run DFMA micro-benchmark (sfmgpu_fp64_peak)",
+                              "frac": F_KLT_IT * (it_all / world) / (klt_ms * 1e-3) / 1e12 / fp64_peak,
+                              "flop_per_lk_iteration": F_KLT_IT, "lk_iterations": it_all // world},
+            "stages_ms": {"pyramid": pyr_ms, "corner_score": cs_ms, "corner_select": sel_ms, "klt": klt_ms, "compact": st["compact"]},
+            "stage_rooflines": {
+                "pyramid": {"bound": "hbm", "achieved": pyr_bytes / (pyr_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": pyr_bytes / (pyr_ms * 1e-3) / 1e9 / hbm_peak},
+                "corner_score": {"bound": "hbm", "achieved": npairs * W * H / (cs_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": npairs * W * H / (cs_ms * 1e-3) / 1e9 / hbm_peak, "mpx_per_s": npairs * W * H / (cs_ms * 1e-3) / 1e6},
+            },
+            "kept_fraction": kept_all / max(tracks_all, 1),
+            "ransac": {"value": RS_H * RS_N / (rs_ms * 1e-3), "unit": "hyp*pts/s", "ms": rs_ms, "hypotheses": RS_H, "points": RS_N,
+                       "e2e_value": RS_H * RS_N / (rs_e2e_ms * 1e-3), "best_h": int(bh), "best_inliers": int(len(inl)),
+                       "fp64_frac": F_RS * RS_H * RS_N / (rs_ms * 1e-3) / 1e12 / fp64_peak,
+                       "hypotheses_source": "synthetic [t]x R around the C4 motion (scoring cost is value-independent)"},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(host)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(host_frames):
+    """The reference's CPU path on this box's host cores, bounded sample of the same frames (reported, not the target)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    chk, kind = oracle.best()
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, 64))
+    sample = np.ascontiguousarray(host_frames[:threads + 1])
+    t0 = time.perf_counter()
+    tracks, kept = chk.pair_frontend_mt(sample, MAX_CORNERS, threads)
+    dt = time.perf_counter() - t0
+    xi, xj = c4_points(RS_N)
+    Hs = 64 * threads
+    E = synthetic_hypotheses(Hs)
+    t1 = time.perf_counter()
+    chk.ransac_score_mt(xi, xj, E, 1e-3, threads)
+    rs = Hs * RS_N / (time.perf_counter() - t1)
+    return {"value": tracks / dt, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"first {threads} pairs of the same sequence, one per host thread ({tracks} feature-tracks in {dt:.2f} s wall)",
+            "ransac_hyp_pts_per_s": rs}
+
+
+if __name__ == "__main__":
+    main()

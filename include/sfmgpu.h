@@ -71,6 +71,13 @@ int sfmgpu_timer_start(sfmgpu_ctx* ctx);
 int sfmgpu_timer_stop(sfmgpu_ctx* ctx, float* ms);
 /* Write `bytes` of device memory (L2 flush between timed iterations). */
 int sfmgpu_flush_l2(sfmgpu_ctx* ctx, size_t bytes);
+/* Per-stage device times of pair_frontend calls: enable, run, then read the accumulated milliseconds
+ * ms[0] corner score (max, candidates, scan, order), ms[1] corner select (sort + NMS), ms[2] KLT, ms[3] compaction.
+ * Reading synchronises the stream and resets the accumulators. */
+int sfmgpu_profile(sfmgpu_ctx* ctx, int enable);
+int sfmgpu_stage_times(sfmgpu_ctx* ctx, float* ms4);
+/* Measured non-tensor FP64 throughput of this GPU (DFMA micro-benchmark, ~10 ms): the KLT / RANSAC roofline. */
+int sfmgpu_fp64_peak(sfmgpu_ctx* ctx, double* tflops);
 /* Pinned host memory for callers that want asynchronous uploads. */
 int sfmgpu_host_alloc(sfmgpu_ctx* ctx, size_t bytes, void** out);
 int sfmgpu_host_free(sfmgpu_ctx* ctx, void* p);
@@ -124,6 +131,13 @@ int sfmgpu_pairs_totals(sfmgpu_ctx* ctx, sfmgpu_pairs* p, long long* n_corners, 
 /* One pair's results: survivors in corner order.  li/lj = (x,y) in first/second frame, cap pairs each. */
 int sfmgpu_pairs_download(sfmgpu_ctx* ctx, sfmgpu_pairs* p, int pair, double* li_xy, double* lj_xy, int cap,
                           int* n_kept, int* n_corners);
+
+/* All pairs of the last batch at once: li/lj are [npairs][max_corners] (x,y) pairs, n_kept/n_corners [npairs].
+ * Any pointer may be NULL.  Use pinned buffers (sfmgpu_host_alloc) for full-speed copies. */
+int sfmgpu_pairs_download_all(sfmgpu_ctx* ctx, sfmgpu_pairs* p, double* li_xy, double* lj_xy, int32_t* n_kept,
+                              int32_t* n_corners);
+/* Device addresses of the same arrays (for NCCL gathers by the scheduler); valid until pairs_destroy. */
+int sfmgpu_pairs_device_ptrs(sfmgpu_pairs* p, void** li_xy, void** lj_xy, void** n_kept, void** n_corners);
 
 /* ---- stateful tracker: KLTTracker (:323-391) ---------------------------------------------------------- */
 int sfmgpu_tracker_create(sfmgpu_ctx* ctx, const sfmgpu_lkcfg* cfg, sfmgpu_tracker** out);

@@ -65,6 +65,7 @@ class CpuFrontEnd:
                 "candidates": (i, [_u8p, i, i, d, i, _i32p, _f64p, i, C.POINTER(d)]),
                 "sort_perm_desc": (i, [_f64p, i, _i32p]),
                 "klt_track_count": (i, [_u8p, _u8p, i, i, i, i, i, _f64p, i, _f64p, _f64p, _i32p]),
+                "synth_frames": (i, [C.c_uint32, i, i, i, i, _u8p, i]),
             })
         for name, (res, args) in S.items():
             fn = self._f(name)
@@ -108,6 +109,11 @@ class CpuFrontEnd:
         mx = C.c_double(0)
         n = self._f("candidates")(np.ascontiguousarray(img), w, h, quality, int(sorted_), xy, s, cap, C.byref(mx))
         return xy[:n].copy(), s[:n].copy(), mx.value
+
+    def synth_frames(self, seed, t0, nframes, w, h, threads=8):
+        out = np.zeros((nframes, h, w), np.uint8)
+        self._f("synth_frames")(seed & 0xFFFFFFFF, t0, nframes, w, h, out.reshape(-1), threads)
+        return out
 
     def sort_perm_desc(self, keys):
         keys = np.ascontiguousarray(keys, np.float64)

@@ -782,5 +782,45 @@ int orc_ransac_score_mt(const double* xi, const double* xj, int n, const double*
   return 0;
 }
 
+// Integer synthetic generator, twin of sfmgpu/synth.py (inputs for the CPU arms without touching GPU code).
+static inline uint32_t h32(uint32_t a) {
+  a ^= a >> 16; a *= 0x7FEB352Du; a ^= a >> 15; a *= 0x846CA68Bu; a ^= a >> 16;
+  return a;
+}
+static inline uint32_t lat(uint32_t s, uint32_t ix, uint32_t iy) { return h32(ix + h32(iy + s)) >> 24; }
+static inline uint32_t vnoise(uint32_t s, uint32_t X, uint32_t Y, int lc) {
+  const uint32_t ix = X >> (lc + 8), iy = Y >> (lc + 8), fx = (X >> lc) & 255u, fy = (Y >> lc) & 255u;
+  const uint32_t top = lat(s, ix, iy) * (256u - fx) + lat(s, ix + 1, iy) * fx;
+  const uint32_t bot = lat(s, ix, iy + 1) * (256u - fx) + lat(s, ix + 1, iy + 1) * fx;
+  return (top * (256u - fy) + bot * fy) >> 16;
+}
+static inline uint32_t blk(uint32_t s, uint32_t i, uint32_t j) { return (lat(s, i, j) & 3u) == 0u ? 255u : 0u; }
+
+int orc_synth_frames(uint32_t seed, int t0, int nframes, int w, int h, uint8_t* out, int threads) {
+  std::vector<std::thread> pool;
+  for (int th = 0; th < threads; th++)
+    pool.emplace_back([=]() {
+      const uint32_t s0 = h32(seed * 4u), s1 = h32(seed * 4u + 1u), s2 = h32(seed * 4u + 2u);
+      for (int k = th; k < nframes; k += threads) {
+        const int t = t0 + k, m = ((t % 128) + 128) % 128, tri = m < 64 ? m : 128 - m;
+        uint8_t* dst = out + (size_t)k * w * h;
+        for (int y = 0; y < h; y++) {
+          const uint32_t Y = (uint32_t)y * 256u + (uint32_t)((1 << 20) - 8 * tri);
+          for (int x = 0; x < w; x++) {
+            const uint32_t X = (uint32_t)x * 256u + (uint32_t)((1 << 20) + 16 * tri);
+            const uint32_t ix = X >> 13, iy = Y >> 13, fx = X & 8191u, fy = Y & 8191u;
+            const uint32_t w1x = fx > 8192u - 256u ? fx - (8192u - 256u) : 0u, w0x = 256u - w1x;
+            const uint32_t w1y = fy > 8192u - 256u ? fy - (8192u - 256u) : 0u, w0y = 256u - w1y;
+            const uint32_t B = (blk(s0, ix, iy) * w0x * w0y + blk(s0, ix + 1, iy) * w1x * w0y +
+                                blk(s0, ix, iy + 1) * w0x * w1y + blk(s0, ix + 1, iy + 1) * w1x * w1y) >> 16;
+            dst[(size_t)y * w + x] = (uint8_t)((4u * B + 3u * vnoise(s1, X, Y, 4) + vnoise(s2, X, Y, 2)) >> 3);
+          }
+        }
+      }
+    });
+  for (auto& t : pool) t.join();
+  return 0;
+}
+
 const char* orc_kind() { return "port"; }
 }

@@ -59,6 +59,10 @@ struct sfmgpu_ctx {
   DevBuf misc;       // small scalars
   DevBuf rs_xi, rs_xj, rs_E, rs_counts, rs_inl, rs_best;
   int rs_n = 0, rs_H = 0;
+  bool profile = false;
+  struct StageEv { int stage; cudaEvent_t a, b; };
+  std::vector<StageEv> stage_evs;
+  float stage_ms[4] = {0, 0, 0, 0};
   void* pinned = nullptr;  // staging for small D2H results
   size_t pinned_cap = 0;
 };
@@ -88,6 +92,24 @@ int sfm_pinned(sfmgpu_ctx* ctx, size_t bytes);
     (ctx)->launches++;                                                                   \
     SFM_CUDA(ctx, cudaGetLastError());                                                   \
   } while (0)
+
+// Stage timing (only when ctx->profile): records a CUDA event pair around a stage on the context stream.
+struct StageTimer {
+  sfmgpu_ctx* ctx;
+  int idx = -1;
+  StageTimer(sfmgpu_ctx* c, int stage) : ctx(c) {
+    if (!c->profile) return;
+    sfmgpu_ctx::StageEv e;
+    e.stage = stage;
+    if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return;
+    cudaEventRecord(e.a, c->stream);
+    c->stage_evs.push_back(e);
+    idx = (int)c->stage_evs.size() - 1;
+  }
+  ~StageTimer() {
+    if (idx >= 0) cudaEventRecord(ctx->stage_evs[idx].b, ctx->stream);
+  }
+};
 
 static inline int sfm_align16(int v) { return v <= 0 ? 16 : ((v + 15) / 16) * 16; }
 static inline unsigned sfm_cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }

@@ -433,7 +433,11 @@ int sfm_corners_batch(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first, int co
   const size_t need = corner_work_carve(wv, work, f->w, f->h, count, cand_cap, min_dist);
   if (need > work_bytes) return sfm_fail(ctx, SFMGPU_E_ARG, "corners: work area too small (%zu < %zu)", work_bytes, need);
   SFM_TRY(select_smem_config(ctx));
-  SFM_TRY(sfm_corner_candidates_batch(ctx, f, first, count, quality, wv));
+  {
+    StageTimer st(ctx, 0);
+    SFM_TRY(sfm_corner_candidates_batch(ctx, f, first, count, quality, wv));
+  }
+  StageTimer st(ctx, 1);
   if (wv.grid_per_frame)
     SFM_CUDA(ctx, cudaMemsetAsync(wv.grid, 0xFF, sizeof(unsigned) * wv.grid_per_frame * count, ctx->stream));
   SFM_LAUNCH(ctx, select_kernel, count, SEL_THREADS, sizeof(SelSmem), wv, f->w, max_corners, min_dist, 0, out_xy, out_n);

@@ -262,7 +262,11 @@ int sfmgpu_pair_frontend(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int
   k.pb = out->pb;
   k.nit = out->nit;
   k.keep = out->keep;
-  SFM_TRY(sfm_klt_launch(ctx, k));
+  {
+    StageTimer st(ctx, 2);
+    SFM_TRY(sfm_klt_launch(ctx, k));
+  }
+  StageTimer st(ctx, 3);
   SFM_LAUNCH(ctx, compact_kernel, npairs, 1024, 0, out->xy0, out->p1, out->keep, (const int*)nullptr, out->ncorn, out->cap, out->li,
              out->lj, (int*)nullptr, out->nkept);
   SFM_LAUNCH(ctx, totals_kernel, 256, 256, 0, out->ncorn, out->nkept, out->nit, npairs, out->cap, out->totals);
@@ -279,6 +283,28 @@ int sfmgpu_pairs_totals(sfmgpu_ctx* ctx, sfmgpu_pairs* p, long long* n_corners, 
   if (n_lk_iters) *n_lk_iters = (long long)t[2];
   if (t[3])
     return sfm_fail(ctx, SFMGPU_E_CAPACITY, "pair_frontend: %llu frame(s) exceeded the candidate capacity", t[3]);
+  return 0;
+}
+
+int sfmgpu_pairs_download_all(sfmgpu_ctx* ctx, sfmgpu_pairs* p, double* li_xy, double* lj_xy, int32_t* n_kept,
+                              int32_t* n_corners) {
+  if (!ctx || !p) return SFMGPU_E_ARG;
+  const size_t np_ = (size_t)p->last_npairs;
+  if (np_ == 0) return 0;
+  if (li_xy) SFM_CUDA(ctx, cudaMemcpyAsync(li_xy, p->li, np_ * p->cap * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  if (lj_xy) SFM_CUDA(ctx, cudaMemcpyAsync(lj_xy, p->lj, np_ * p->cap * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  if (n_kept) SFM_CUDA(ctx, cudaMemcpyAsync(n_kept, p->nkept, np_ * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (n_corners) SFM_CUDA(ctx, cudaMemcpyAsync(n_corners, p->ncorn, np_ * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int sfmgpu_pairs_device_ptrs(sfmgpu_pairs* p, void** li_xy, void** lj_xy, void** n_kept, void** n_corners) {
+  if (!p) return SFMGPU_E_ARG;
+  if (li_xy) *li_xy = p->li;
+  if (lj_xy) *lj_xy = p->lj;
+  if (n_kept) *n_kept = p->nkept;
+  if (n_corners) *n_corners = p->ncorn;
   return 0;
 }
 

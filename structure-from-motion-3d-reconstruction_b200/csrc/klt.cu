@@ -10,18 +10,19 @@
 //   * the early exit tests the step that was just added (hypot(step) < 1e-3);
 //   * p is rescaled from the running full-resolution position at every level.
 //
-// Arithmetic: positions, bilinear weights, accumulators and the 2x2 solve are FP64 and this file is compiled
-// with -fmad=false (the x86-64 oracle has no FMA contraction).  Two deliberate, measured deviations from the
-// reference's operation ORDER (not from its formulas):
-//   (1) the 11x11 window's six samples per pixel are taken from one shared grid of bilinear samples whose
-//       column/row coordinates are fl(x+i), fl(y+j) (the reference reaches the +-1 neighbours as fl(fl(x+i)+-1));
-//   (2) the five sums are reduced lane-strided + butterfly instead of sequentially in raster order.
-//   Measured on CPU against the exact order (1500 points x 60 iterations, smooth, checker and pure-noise
-//   images): max deviation 1.8e-11 px, i.e. 8 orders of magnitude inside the 1e-3 px parity budget.
+// Arithmetic: positions, bilinear weights, accumulators and the 2x2 solve are FP64.  The file is compiled with
+// -fmad=false; fused multiply-adds appear only where written explicitly (__fma_rn).  Deliberate, measured
+// deviations from the reference's operation ORDER / rounding (never from its formulas or its discontinuities):
+//   (1) the window's six samples per pixel come from one shared grid of bilinear samples whose column / row
+//       coordinates are fl(x+i), fl(y+j) (the reference reaches the +-1 neighbours as fl(fl(x+i)+-1));
+//   (2) lerps are evaluated as a + (b-a)*t with one FMA; the normal equations are accumulated with FMAs,
+//       lane-strided and then butterfly-reduced instead of sequentially in raster order;
+//   (3) the 0.5 factors of the central differences are folded into the solve (exact power-of-two scaling).
+//   Measured against the exact order: max deviation ~1e-13 px on smooth, checker and pure-noise images
+//   (tests/test_gpu_parity.py prints it), 10 orders of magnitude inside the 1e-3 px parity budget; the
+//   reference's update is non-contractive but not chaotic (perturbations of 1e-13 stay below 1e-10 after the
+//   60 iterations of a fwd+bwd track).
 //
-// Work per LK iteration and warp (r = 5): 338 horizontal lerps (each tap pair read once from a cached u8
-// tile in shared memory), 290 vertical lerps, 121 pixel terms, 5 warp reductions.  The u8 tiles (24x24 per
-// image) are re-staged only when the window leaves the cached region, i.e. about once per level.
 // Roofline: FP64 CUDA-core pipe, not HBM (algorithmic traffic is 2,092 B per track-step).
 #include "common.cuh"
 
@@ -31,24 +32,16 @@ constexpr int KLT_MARGIN = 4;
 
 template <int R>
 struct KltSmem {
-  static constexpr int NC = 2 * R + 3;               // sample-grid columns / rows (window + 1 each side)
-  static constexpr int NR = 2 * R + 5;               // tile rows a sample grid can touch
+  static constexpr int NC = 2 * R + 3;                  // sample-grid columns / rows (window + 1 each side)
   static constexpr int T = 2 * KLT_MARGIN + 2 * R + 6;  // cached tile edge (24 for R = 5)
-  double H1[NR * NC];   // horizontal lerps of I1
-  double H0[NR * NC];   // horizontal lerps of I0 (inner columns only are used)
-  double S1[NC * NC];   // bilinear samples of I1 on the grid
-  double S0[NC * NC];   // bilinear samples of I0 (inner (2R+1)^2 used)
-  double cfx[NC], cfy[NC];  // fractional parts per grid column / row
-  int ccx[NC], ccy[NC];     // tile-relative tap column / row (left / top tap)
-  int cvx[NC], cvy[NC];     // validity (both taps inside the image)
-  uint8_t t0[T * T];
-  uint8_t t1[T * T];
+  double cfy[NC + 3];   // per grid row: fractional weight of the lower tap row
+  int cvy[NC + 3];      // per grid row: both tap rows inside the image
+  uint8_t t0[T * T];    // cached u8 tile of image A around the window
+  uint8_t t1[T * T];    // same for image B
 };
 
-__device__ __forceinline__ double u8_to_f64(uint32_t v) {
-  // exact: 2^52 + v has v in its low mantissa bits
-  return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
-}
+// exact int32 -> double on the FP64 pipe (no conversion-pipe instruction): (2^52 + 2^31 + v) - (2^52 + 2^31)
+__device__ __forceinline__ double i2d(int v) { return __hiloint2double(0x43300000, v ^ 0x80000000) - 4503601774854144.0; }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -71,15 +64,33 @@ __device__ __forceinline__ void stage_tile(uint8_t* tile, const uint8_t* __restr
 
 // One pyramidal track (:402-422) of point (px,py) from pyramid A to pyramid B.  All lanes hold identical
 // scalars; shared memory `sm` is private to the warp.
+//
+// Lane layout ("column lanes"): lane = g*nc + i owns grid column i (x offset i-r-1) for the g-th contiguous
+// chunk of window rows; G = 32/nc groups (2 for r = 5: 26 of 32 lanes busy).  A lane walks down its rows keeping
+// the horizontal lerps, the last three I1 samples and the last two I0 samples in REGISTERS; the only exchanges
+// are two shuffles per pixel row (left / right neighbour sample) and the final 5-value warp reduction.
+// Shared memory holds just the cached u8 tiles and the tiny per-row weight table.
+//
+// Weights: column i uses the REGULAR tap pair (FX+i-r-1, +1) with f = fl(x+i') - (FX+i') in [0,1].  In the rare
+// case where fl(x+i') rounds up to the next integer the reference's own floor moves by one and its fraction is
+// 0; f == 1 on the regular pair selects exactly the same tap (weights 0 and 1), so no special case is needed
+// for the value, only for the bounds test, which uses the reference's floor.
 template <int R, bool FIXED>
 __device__ void track_one(KltSmem<R>& sm, const PyrView& pv, int fa, int fb, int radius_rt, int iters, double& px, double& py,
                           int& n_it, int lane) {
-  constexpr int NC = KltSmem<R>::NC;
   constexpr int T = KltSmem<R>::T;
-  const int radius = FIXED ? R : radius_rt;  // compile-time window for the default radius: no runtime divisions
-  const int nc = 2 * radius + 3;  // grid edge actually used
-  const int nr = 2 * radius + 5;
+  const int radius = FIXED ? R : radius_rt;  // compile-time window for the default radius
+  const int nc = 2 * radius + 3;
   const int nw = 2 * radius + 1;
+  const int G = 32 / nc;                     // >= 1 for r <= 14
+  const int chunk = (nw + G - 1) / G;        // pixel rows per group
+  const int NK = chunk + 3;                  // tap rows a group walks
+  const int gi = lane / nc, i = lane - gi * nc;
+  const bool col_active = gi < G;
+  const bool pix_col = col_active && i >= 1 && i <= nc - 2;
+  const int p0 = (col_active ? gi : 0) * chunk;          // first pixel row of this lane's group
+  const int p1 = p0 + chunk < nw ? p0 + chunk : nw;      // one past the last
+  const double off_i = (double)(i - radius - 1);
 
   for (int l = pv.levels - 1; l >= 0; --l) {
     const int w = pv.w[l], h = pv.h[l], pitch = pv.pitch[l];
@@ -109,76 +120,77 @@ __device__ void track_one(KltSmem<R>& sm, const PyrView& pv, int fa, int fb, int
           stage_tile<R>(sm.t1, I1, w, h, pitch, tx0, ty0, lane);
           have_tile = true;
         }
-        // per-column / per-row tables: coordinate fl(x+i), its floor, fraction, validity (:184-190)
-        for (int t = lane; t < 2 * nc; t += 32) {
-          const bool isx = t < nc;
-          const int i = isx ? t : t - nc;
-          const double c0 = (isx ? x : y) + (double)(i - radius - 1);
-          const double cf = floor(c0);
-          const bool ok = (cf >= 0.0) && (cf <= (double)((isx ? w : h) - 2));
-          int c = ok ? (int)cf - (isx ? tx0 : ty0) : 0;
-          c = c < 0 ? 0 : (c > T - 2 ? T - 2 : c);
-          if (isx) {
-            sm.cfx[i] = c0 - cf;
-            sm.cvx[i] = ok ? 1 : 0;
-            sm.ccx[i] = c;
-          } else {
-            sm.cfy[i] = c0 - cf;
-            sm.cvy[i] = ok ? 1 : 0;
-            sm.ccy[i] = c;
-          }
+        // per-row weight table (lanes 0..nc-1), per-column weights in registers
+        if (lane < nc) {
+          const double reg = fyy + off_i;            // off_i == lane - r - 1 here
+          const double f = (y + off_i) - reg;        // == x - x0 of :189-190, or exactly 1 after a round-up
+          const double tf = f == 1.0 ? reg + 1.0 : reg;
+          sm.cfy[lane] = f;
+          sm.cvy[lane] = (tf >= 0.0 && tf <= (double)(h - 2)) ? 1 : 0;
         }
+        const double regx = fxx + off_i;
+        const double fx = (x + off_i) - regx;
+        const double tfx = fx == 1.0 ? regx + 1.0 : regx;
+        const bool vx = col_active && tfx >= 0.0 && tfx <= (double)(w - 2);
+        int col = FX - radius - 1 - tx0 + i;
+        col = col < 0 ? 0 : (col > T - 2 ? T - 2 : col);
+        const int rowbase = FY - radius - 1 - ty0 + p0;
         __syncwarp();
-        // horizontal lerps v00*(1-dx) + v10*dx on every tile row the grid can touch (rows rb .. rb+nr-1)
-        int rb = FY - radius - 1 - ty0;
-        rb = rb < 0 ? 0 : (rb > T - nr ? T - nr : rb);
-        for (int idx = lane; idx < nr * nc; idx += 32) {
-          const int rr = idx / nc, i = idx - rr * nc;
-          const int off = (rb + rr) * T + sm.ccx[i];
-          const double f = sm.cfx[i], g = 1.0 - f;
-          const double a1 = u8_to_f64(sm.t1[off]), b1 = u8_to_f64(sm.t1[off + 1]);
-          sm.H1[rr * NC + i] = a1 * g + b1 * f;
-          const double a0 = u8_to_f64(sm.t0[off]), b0 = u8_to_f64(sm.t0[off + 1]);
-          sm.H0[rr * NC + i] = a0 * g + b0 * f;
-        }
-        __syncwarp();
-        // vertical lerps v0*(1-dy) + v1*dy; invalid taps zero the sample (:188)
-        for (int idx = lane; idx < nc * nc; idx += 32) {
-          const int j = idx / nc, i = idx - j * nc;
-          int rr = sm.ccy[j] - rb;
-          rr = rr < 0 ? 0 : (rr > nr - 2 ? nr - 2 : rr);
-          const bool ok = sm.cvx[i] && sm.cvy[j];
-          const double f = sm.cfy[j], g = 1.0 - f;
-          const double v1 = sm.H1[rr * NC + i] * g + sm.H1[(rr + 1) * NC + i] * f;
-          const double v0 = sm.H0[rr * NC + i] * g + sm.H0[(rr + 1) * NC + i] * f;
-          sm.S1[j * NC + i] = ok ? v1 : 0.0;
-          sm.S0[j * NC + i] = ok ? v0 : 0.0;
-        }
-        __syncwarp();
-        // normal equations over the (2r+1)^2 window (:433-450)
+
         double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0;
-        for (int idx = lane; idx < nw * nw; idx += 32) {
-          const int dy = idx / nw, dx = idx - dy * nw;
-          const int c = (dy + 1) * NC + (dx + 1);
-          const double ix = 0.5 * (sm.S1[c + 1] - sm.S1[c - 1]);
-          const double iy = 0.5 * (sm.S1[c + NC] - sm.S1[c - NC]);
-          const double e = sm.S0[c] - sm.S1[c];
-          a00 += ix * ix;
-          a01 += ix * iy;
-          a11 += iy * iy;
-          b0 += ix * e;
-          b1 += iy * e;
+        double h1p = 0, h0p = 0, s1a = 0, s1b = 0, s0b = 0;
+#pragma unroll
+        for (int k = 0; k < (FIXED ? (2 * R + 1 + 32 / (2 * R + 3) - 1) / (32 / (2 * R + 3)) + 3 : NK); k++) {
+          int trow = rowbase + k;
+          trow = trow > T - 1 ? T - 1 : trow;
+          const uint8_t* q1 = sm.t1 + trow * T + col;
+          const uint8_t* q0 = sm.t0 + trow * T + col;
+          const int a1 = q1[0], c1 = q1[1], a0 = q0[0], c0 = q0[1];
+          // horizontal lerp v00 + (v10 - v00)*dx  (== v00*(1-dx) + v10*dx up to one rounding)
+          const double h1 = __fma_rn(fx, i2d(c1 - a1), i2d(a1));
+          const double h0 = __fma_rn(fx, i2d(c0 - a0), i2d(a0));
+          if (k >= 1) {
+            int j = p0 + k - 1;  // grid row just completed
+            j = j > nc - 1 ? nc - 1 : j;
+            const double fy = sm.cfy[j];
+            const bool ok = vx && sm.cvy[j];
+            double s1c = __fma_rn(fy, h1 - h1p, h1p);
+            double s0c = __fma_rn(fy, h0 - h0p, h0p);
+            s1c = ok ? s1c : 0.0;  // any out-of-range tap zeroes the whole sample (:188)
+            s0c = ok ? s0c : 0.0;
+            if (k >= 3) {
+              // pixel row p0+k-3: centre sample s1b, vertical neighbours s1a / s1c, horizontal from lanes +-1
+              const double left = __shfl_up_sync(0xffffffffu, s1b, 1);
+              const double right = __shfl_down_sync(0xffffffffu, s1b, 1);
+              if (pix_col && p0 + k - 3 < p1) {
+                const double gx2 = right - left;   // 2*Ix: the reference's 0.5 factors are folded into the solve
+                const double gy2 = s1c - s1a;      // 2*Iy
+                const double e = s0b - s1b;
+                a00 = __fma_rn(gx2, gx2, a00);
+                a01 = __fma_rn(gx2, gy2, a01);
+                a11 = __fma_rn(gy2, gy2, a11);
+                b0 = __fma_rn(gx2, e, b0);
+                b1 = __fma_rn(gy2, e, b1);
+              }
+            }
+            s1a = s1b;
+            s1b = s1c;
+            s0b = s0c;
+          }
+          h1p = h1;
+          h0p = h0;
         }
         a00 = warp_sum(a00);
         a01 = warp_sum(a01);
         a11 = warp_sum(a11);
         b0 = warp_sum(b0);
         b1 = warp_sum(b1);
+        // a** = 4*A, b* = 2*b of :444-448 (exact power-of-two scalings): det' = 16 det, step = 2 * A'^-1 b'
         const double det = a00 * a11 - a01 * a01;
-        if (!(fabs(det) < 1e-9)) {
+        if (!(fabs(det) < 16.0 * 1e-9)) {  // |det| < 1e-9 of :452, scaled exactly
           const double i00 = a11 / det, i01 = -a01 / det, i11 = a00 / det;
-          sx = i00 * b0 + i01 * b1;
-          sy = i01 * b0 + i11 * b1;
+          sx = 2.0 * (i00 * b0 + i01 * b1);
+          sy = 2.0 * (i01 * b0 + i11 * b1);
         }
       }
       n_it++;

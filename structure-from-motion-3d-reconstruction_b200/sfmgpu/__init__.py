@@ -23,12 +23,12 @@ _ll = C.c_longlong
 # every symbol include/sfmgpu.h declares (tests/test_abi.py checks the library exports exactly these)
 SYMBOLS = [
     "sfmgpu_lkcfg_default", "sfmgpu_version", "sfmgpu_create", "sfmgpu_destroy", "sfmgpu_last_error", "sfmgpu_sync",
-    "sfmgpu_launch_count", "sfmgpu_timer_start", "sfmgpu_timer_stop", "sfmgpu_flush_l2", "sfmgpu_host_alloc",
+    "sfmgpu_launch_count", "sfmgpu_timer_start", "sfmgpu_timer_stop", "sfmgpu_flush_l2", "sfmgpu_profile", "sfmgpu_stage_times", "sfmgpu_fp64_peak", "sfmgpu_host_alloc",
     "sfmgpu_host_free", "sfmgpu_frames_create", "sfmgpu_frames_destroy", "sfmgpu_frames_upload",
     "sfmgpu_frames_upload_device", "sfmgpu_frames_synth", "sfmgpu_pyramid_build", "sfmgpu_frames_level_size",
     "sfmgpu_frames_download", "sfmgpu_corner_candidates", "sfmgpu_corners", "sfmgpu_sort_perm_desc",
     "sfmgpu_klt_track", "sfmgpu_pairs_create", "sfmgpu_pairs_destroy", "sfmgpu_pair_frontend", "sfmgpu_pairs_totals",
-    "sfmgpu_pairs_download", "sfmgpu_tracker_create", "sfmgpu_tracker_destroy", "sfmgpu_tracker_reset",
+    "sfmgpu_pairs_download", "sfmgpu_pairs_download_all", "sfmgpu_pairs_device_ptrs", "sfmgpu_tracker_create", "sfmgpu_tracker_destroy", "sfmgpu_tracker_reset",
     "sfmgpu_tracker_step", "sfmgpu_tracker_step_frames", "sfmgpu_tracker_tracks", "sfmgpu_tracker_totals",
     "sfmgpu_ransac_score", "sfmgpu_ransac_upload", "sfmgpu_ransac_score_resident", "sfmgpu_ransac_download",
 ]
@@ -77,6 +77,9 @@ def load_library():
         "sfmgpu_timer_start": (_i, [_vp]),
         "sfmgpu_timer_stop": (_i, [_vp, C.POINTER(C.c_float)]),
         "sfmgpu_flush_l2": (_i, [_vp, C.c_size_t]),
+        "sfmgpu_profile": (_i, [_vp, _i]),
+        "sfmgpu_stage_times": (_i, [_vp, C.POINTER(C.c_float)]),
+        "sfmgpu_fp64_peak": (_i, [_vp, C.POINTER(_d)]),
         "sfmgpu_host_alloc": (_i, [_vp, C.c_size_t, C.POINTER(_vp)]),
         "sfmgpu_host_free": (_i, [_vp, _vp]),
         "sfmgpu_frames_create": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_vp)]),
@@ -96,6 +99,8 @@ def load_library():
         "sfmgpu_pair_frontend": (_i, [_vp, _vp, _i, _i, C.POINTER(LKCfg), _vp]),
         "sfmgpu_pairs_totals": (_i, [_vp, _vp, C.POINTER(_ll), C.POINTER(_ll), C.POINTER(_ll)]),
         "sfmgpu_pairs_download": (_i, [_vp, _vp, _i, _f64p, _f64p, _i, C.POINTER(_i), C.POINTER(_i)]),
+        "sfmgpu_pairs_download_all": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+        "sfmgpu_pairs_device_ptrs": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
         "sfmgpu_tracker_create": (_i, [_vp, C.POINTER(LKCfg), C.POINTER(_vp)]),
         "sfmgpu_tracker_destroy": (None, [_vp, _vp]),
         "sfmgpu_tracker_reset": (_i, [_vp, _vp, _u8p, _i, _i]),
@@ -162,6 +167,19 @@ class Context:
 
     def flush_l2(self, nbytes=256 << 20):
         self._ck(self.lib.sfmgpu_flush_l2(self.h, nbytes))
+
+    def profile(self, on=True):
+        self._ck(self.lib.sfmgpu_profile(self.h, int(on)))
+
+    def stage_times(self):
+        ms = (C.c_float * 4)()
+        self._ck(self.lib.sfmgpu_stage_times(self.h, ms))
+        return dict(corner_score=ms[0], corner_select=ms[1], klt=ms[2], compact=ms[3])
+
+    def fp64_peak(self):
+        t = _d(0)
+        self._ck(self.lib.sfmgpu_fp64_peak(self.h, C.byref(t)))
+        return t.value
 
     def pinned_empty(self, shape, dtype=np.uint8):
         """numpy array backed by page-locked host memory (freed with the context)."""
@@ -317,6 +335,15 @@ class Pairs:
         a, b, c = _ll(0), _ll(0), _ll(0)
         self.ctx._ck(self.ctx.lib.sfmgpu_pairs_totals(self.ctx.h, self.h_, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+    def download_all(self, li, lj, nkept, ncorn):
+        """Bulk D2H of the last batch into caller (ideally pinned) arrays; any may be None."""
+        self.ctx._ck(self.ctx.lib.sfmgpu_pairs_download_all(self.ctx.h, self.h_, _ptr(li), _ptr(lj), _ptr(nkept), _ptr(ncorn)))
+
+    def device_ptrs(self):
+        a, b, c, d = _vp(), _vp(), _vp(), _vp()
+        self.ctx._ck(self.ctx.lib.sfmgpu_pairs_device_ptrs(self.h_, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return a.value, b.value, c.value, d.value
 
     def download(self, pair):
         li, lj = np.zeros((self.cap, 2)), np.zeros((self.cap, 2))
