@@ -32,6 +32,7 @@ for r in rows:
     if hd is None or len(r) < len(hd): continue
     try: sm = float(r[ci]); ba = float(r[bi]); ie = float(r[ii])
     except ValueError: continue
+    if not r[li].strip(): continue  # SASS rows repeat their CUDA line's counts
     k = (r[li], r[si].strip())
     agg[k][0] += sm; agg[k][1] += ba; agg[k][2] += ie
 tot = sum(v[0] for v in agg.values()) or 1
@@ -39,6 +40,10 @@ totb = sum(v[1] for v in agg.values())
 print(f"--- samples total {tot:.0f}, of which barrier stalls {totb:.0f}; top lines by non-barrier samples, then by barrier")
 for (ln, txt), (sm, ba, ie) in sorted(agg.items(), key=lambda x: -(x[1][0] - x[1][1]))[:top]:
     print(f"{100*(sm-ba)/tot:5.1f}% nb {100*ba/tot:5.1f}% bar inst={ie:12.0f} L{ln:>4s} {txt[:120]}")
+toti = sum(v[2] for v in agg.values()) or 1
+print(f"--- top lines by warp instructions executed (total {toti:.3g})")
+for (ln, txt), (sm, ba, ie) in sorted(agg.items(), key=lambda x: -x[1][2])[:top]:
+    print(f"{100*ie/toti:5.1f}% inst  {100*sm/tot:5.1f}% samp L{ln:>4s} {txt[:110]}")
 print("--- top lines by barrier-stall samples")
 for (ln, txt), (sm, ba, ie) in sorted(agg.items(), key=lambda x: -x[1][1])[:8]:
     print(f"{100*ba/tot:5.1f}% bar L{ln:>4s} {txt[:120]}")

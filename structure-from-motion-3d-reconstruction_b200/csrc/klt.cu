@@ -32,33 +32,105 @@ constexpr int KLT_MARGIN = 4;
 
 template <int R>
 struct KltSmem {
-  static constexpr int NC = 2 * R + 3;                  // sample-grid columns / rows (window + 1 each side)
-  static constexpr int T = 2 * KLT_MARGIN + 2 * R + 6;  // cached tile edge (24 for R = 5)
-  double cfy[NC + 3];   // per grid row: fractional weight of the lower tap row
-  int cvy[NC + 3];      // per grid row: both tap rows inside the image
-  uint8_t t0[T * T];    // cached u8 tile of image A around the window
-  uint8_t t1[T * T];    // same for image B
+  static constexpr int NC = 2 * R + 3;                         // sample-grid columns / rows (window + 1 each side)
+  static constexpr int TH = 2 * KLT_MARGIN + 2 * R + 6;        // cached tile rows (24 for R = 5)
+  static constexpr int TW = ((2 * R + 17 + 3) / 4) * 4;        // cached tile row bytes, origin 4-aligned (28 for R = 5)
+  static constexpr int WPR = TW / 4;
+  double cfy[NC + 3];      // per grid row: fractional weight of the lower tap row
+  int cvy[NC + 3];         // per grid row: both tap rows inside the image
+  uint32_t t0[TH * WPR];   // cached u8 tile of image A around the window (rows of TW bytes)
+  uint32_t t1[TH * WPR];   // same for image B
 };
 
-// exact int32 -> double on the FP64 pipe (no conversion-pipe instruction): (2^52 + 2^31 + v) - (2^52 + 2^31)
-__device__ __forceinline__ double i2d(int v) { return __hiloint2double(0x43300000, v ^ 0x80000000) - 4503601774854144.0; }
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, o);
-  return v;  // identical in every lane (a+b == b+a bitwise)
+// Sum five per-lane partials over the warp by recursive halving (8 exchanges instead of 25), then broadcast.
+__device__ __forceinline__ void reduce5(double& a00, double& a01, double& a11, double& b0, double& b1, int lane) {
+  const unsigned FULL = 0xffffffffu;
+  const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4;
+  // xor 16: lower half keeps (a00,a01,a11), upper half keeps (b0,b1)
+  const double x0 = __shfl_xor_sync(FULL, up16 ? a00 : b0, 16);
+  const double x1 = __shfl_xor_sync(FULL, up16 ? a01 : b1, 16);
+  const double x2 = __shfl_xor_sync(FULL, up16 ? a11 : 0.0, 16);
+  double u0 = (up16 ? b0 : a00) + x0, u1 = (up16 ? b1 : a01) + x1, u2 = up16 ? 0.0 : a11 + x2;
+  // xor 8: bit3 == 0 keeps (u0,u1), bit3 == 1 keeps u2
+  const double y0 = __shfl_xor_sync(FULL, up8 ? u0 : u2, 8);
+  const double y1 = __shfl_xor_sync(FULL, up8 ? u1 : 0.0, 8);
+  double v0 = up8 ? u2 + y0 : u0 + y0, v1 = up8 ? 0.0 : u1 + y1;
+  // xor 4: bit2 == 0 keeps v0, bit2 == 1 keeps v1
+  const double z0 = __shfl_xor_sync(FULL, up4 ? v0 : v1, 4);
+  double z = (up4 ? v1 : v0) + z0;
+  z = z + __shfl_xor_sync(FULL, z, 2);
+  z = z + __shfl_xor_sync(FULL, z, 1);
+  a00 = __shfl_sync(FULL, z, 0);
+  a01 = __shfl_sync(FULL, z, 4);
+  a11 = __shfl_sync(FULL, z, 8);
+  b0 = __shfl_sync(FULL, z, 16);
+  b1 = __shfl_sync(FULL, z, 20);
 }
 
+// Stage TH rows of TW bytes starting at (tx0 [multiple of 4], ty0) with aligned 32-bit loads.  Coordinates are
+// clamped to the allocation; bytes outside the image are garbage that only ever feeds samples the bounds test zeroes.
 template <int R>
-__device__ __forceinline__ void stage_tile(uint8_t* tile, const uint8_t* __restrict__ img, int w, int h, int pitch, int tx0,
-                                           int ty0, int lane) {
-  constexpr int T = KltSmem<R>::T;
-  for (int idx = lane; idx < T * T; idx += 32) {
-    const int r = idx / T, c = idx - r * T;
-    int gx = tx0 + c, gy = ty0 + r;
-    gx = gx < 0 ? 0 : (gx > w - 1 ? w - 1 : gx);
+__device__ __forceinline__ void stage_tile(uint32_t* tile, const uint8_t* __restrict__ img, int h, int pitch, int tx0, int ty0,
+                                           int lane) {
+  constexpr int TH = KltSmem<R>::TH, WPR = KltSmem<R>::WPR;
+  const int wmax = (pitch >> 2) - 1, wx0 = tx0 >> 2;
+#pragma unroll 2
+  for (int idx = lane; idx < TH * WPR; idx += 32) {
+    const int r = idx / WPR, c = idx - r * WPR;
+    int gw = wx0 + c, gy = ty0 + r;
+    gw = gw < 0 ? 0 : (gw > wmax ? wmax : gw);
     gy = gy < 0 ? 0 : (gy > h - 1 ? h - 1 : gy);
-    tile[idx] = __ldg(img + (size_t)gy * pitch + gx);
+    tile[idx] = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)gy * pitch) + gw);
+  }
+}
+
+// The window walk of one LK iteration for this lane (see track_one).  INTERIOR: every tap is inside the image, so
+// the per-sample bounds logic (:188) is compiled out.
+template <int R, bool FIXED, bool INTERIOR>
+__device__ __forceinline__ void walk_rows(const KltSmem<R>& sm, int NK, int nc, int rowbase, int col, int p0, int p1, bool pix_col,
+                                          bool vx, double fx, double& a00, double& a01, double& a11, double& b0, double& b1) {
+  constexpr int TW = KltSmem<R>::TW;
+  const uint8_t* q1 = reinterpret_cast<const uint8_t*>(sm.t1) + rowbase * TW + col;
+  const uint8_t* q0 = reinterpret_cast<const uint8_t*>(sm.t0) + rowbase * TW + col;
+  double h1p = 0, h0p = 0, s1a = 0, s1b = 0, s0b = 0;
+#pragma unroll
+  for (int k = 0; k < (FIXED ? (2 * R + 1 + 32 / (2 * R + 3) - 1) / (32 / (2 * R + 3)) + 3 : NK); k++) {
+    const int a1 = q1[k * TW], c1 = q1[k * TW + 1], a0 = q0[k * TW], c0 = q0[k * TW + 1];
+    // horizontal lerp v00 + (v10 - v00)*dx  (== v00*(1-dx) + v10*dx up to one rounding)
+    const double h1 = __fma_rn(fx, (double)(c1 - a1), (double)a1);
+    const double h0 = __fma_rn(fx, (double)(c0 - a0), (double)a0);
+    if (k >= 1) {
+      int j = p0 + k - 1;  // grid row just completed
+      j = j > nc - 1 ? nc - 1 : j;
+      const double fy = sm.cfy[j];
+      double s1c = __fma_rn(fy, h1 - h1p, h1p);
+      double s0c = __fma_rn(fy, h0 - h0p, h0p);
+      if (!INTERIOR) {
+        const bool ok = vx && sm.cvy[j];
+        s1c = ok ? s1c : 0.0;  // any out-of-range tap zeroes the whole sample (:188)
+        s0c = ok ? s0c : 0.0;
+      }
+      if (k >= 3) {
+        // pixel row p0+k-3: centre sample s1b, vertical neighbours s1a / s1c, horizontal from lanes +-1
+        const double left = __shfl_up_sync(0xffffffffu, s1b, 1);
+        const double right = __shfl_down_sync(0xffffffffu, s1b, 1);
+        if (pix_col && p0 + k - 3 < p1) {
+          const double gx2 = right - left;  // 2*Ix: the reference's 0.5 factors are folded into the solve
+          const double gy2 = s1c - s1a;     // 2*Iy
+          const double e = s0b - s1b;
+          a00 = __fma_rn(gx2, gx2, a00);
+          a01 = __fma_rn(gx2, gy2, a01);
+          a11 = __fma_rn(gy2, gy2, a11);
+          b0 = __fma_rn(gx2, e, b0);
+          b1 = __fma_rn(gy2, e, b1);
+        }
+      }
+      s1a = s1b;
+      s1b = s1c;
+      s0b = s0c;
+    }
+    h1p = h1;
+    h0p = h0;
   }
 }
 
@@ -78,7 +150,7 @@ __device__ __forceinline__ void stage_tile(uint8_t* tile, const uint8_t* __restr
 template <int R, bool FIXED>
 __device__ void track_one(KltSmem<R>& sm, const PyrView& pv, int fa, int fb, int radius_rt, int iters, double& px, double& py,
                           int& n_it, int lane) {
-  constexpr int T = KltSmem<R>::T;
+  constexpr int TH = KltSmem<R>::TH, TW = KltSmem<R>::TW;
   const int radius = FIXED ? R : radius_rt;  // compile-time window for the default radius
   const int nc = 2 * radius + 3;
   const int nw = 2 * radius + 1;
@@ -111,92 +183,53 @@ __device__ void track_one(KltSmem<R>& sm, const PyrView& pv, int fa, int fb, int
       if (finite_ok && w >= 2 && h >= 2) {
         const int FX = (int)fxx, FY = (int)fyy;
         // cached tile must cover columns [FX-r-1, FX+r+3] and rows [FY-r-1, FY+r+3]
-        if (!have_tile || FX - radius - 1 < tx0 || FX + radius + 3 > tx0 + T - 1 || FY - radius - 1 < ty0 ||
-            FY + radius + 3 > ty0 + T - 1) {
-          tx0 = FX - radius - 1 - KLT_MARGIN;
+        if (!have_tile || FX - radius - 1 < tx0 || FX + radius + 3 > tx0 + TW - 1 || FY - radius - 1 < ty0 ||
+            FY + radius + 3 > ty0 + TH - 1) {
+          tx0 = (FX - radius - 1 - KLT_MARGIN) & ~3;
           ty0 = FY - radius - 1 - KLT_MARGIN;
           __syncwarp();
-          stage_tile<R>(sm.t0, I0, w, h, pitch, tx0, ty0, lane);
-          stage_tile<R>(sm.t1, I1, w, h, pitch, tx0, ty0, lane);
+          stage_tile<R>(sm.t0, I0, h, pitch, tx0, ty0, lane);
+          stage_tile<R>(sm.t1, I1, h, pitch, tx0, ty0, lane);
           have_tile = true;
         }
+        const bool interior = FX - radius - 1 >= 0 && FX + radius + 3 <= w - 1 && FY - radius - 1 >= 0 && FY + radius + 3 <= h - 1;
         // per-row weight table (lanes 0..nc-1), per-column weights in registers
         if (lane < nc) {
           const double reg = fyy + off_i;            // off_i == lane - r - 1 here
           const double f = (y + off_i) - reg;        // == x - x0 of :189-190, or exactly 1 after a round-up
-          const double tf = f == 1.0 ? reg + 1.0 : reg;
           sm.cfy[lane] = f;
-          sm.cvy[lane] = (tf >= 0.0 && tf <= (double)(h - 2)) ? 1 : 0;
+          if (!interior) {
+            const double tf = f == 1.0 ? reg + 1.0 : reg;
+            sm.cvy[lane] = (tf >= 0.0 && tf <= (double)(h - 2)) ? 1 : 0;
+          }
         }
         const double regx = fxx + off_i;
         const double fx = (x + off_i) - regx;
-        const double tfx = fx == 1.0 ? regx + 1.0 : regx;
-        const bool vx = col_active && tfx >= 0.0 && tfx <= (double)(w - 2);
-        int col = FX - radius - 1 - tx0 + i;
-        col = col < 0 ? 0 : (col > T - 2 ? T - 2 : col);
+        const int col = FX - radius - 1 - tx0 + i;
         const int rowbase = FY - radius - 1 - ty0 + p0;
         __syncwarp();
 
         double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0;
-        double h1p = 0, h0p = 0, s1a = 0, s1b = 0, s0b = 0;
-#pragma unroll
-        for (int k = 0; k < (FIXED ? (2 * R + 1 + 32 / (2 * R + 3) - 1) / (32 / (2 * R + 3)) + 3 : NK); k++) {
-          int trow = rowbase + k;
-          trow = trow > T - 1 ? T - 1 : trow;
-          const uint8_t* q1 = sm.t1 + trow * T + col;
-          const uint8_t* q0 = sm.t0 + trow * T + col;
-          const int a1 = q1[0], c1 = q1[1], a0 = q0[0], c0 = q0[1];
-          // horizontal lerp v00 + (v10 - v00)*dx  (== v00*(1-dx) + v10*dx up to one rounding)
-          const double h1 = __fma_rn(fx, i2d(c1 - a1), i2d(a1));
-          const double h0 = __fma_rn(fx, i2d(c0 - a0), i2d(a0));
-          if (k >= 1) {
-            int j = p0 + k - 1;  // grid row just completed
-            j = j > nc - 1 ? nc - 1 : j;
-            const double fy = sm.cfy[j];
-            const bool ok = vx && sm.cvy[j];
-            double s1c = __fma_rn(fy, h1 - h1p, h1p);
-            double s0c = __fma_rn(fy, h0 - h0p, h0p);
-            s1c = ok ? s1c : 0.0;  // any out-of-range tap zeroes the whole sample (:188)
-            s0c = ok ? s0c : 0.0;
-            if (k >= 3) {
-              // pixel row p0+k-3: centre sample s1b, vertical neighbours s1a / s1c, horizontal from lanes +-1
-              const double left = __shfl_up_sync(0xffffffffu, s1b, 1);
-              const double right = __shfl_down_sync(0xffffffffu, s1b, 1);
-              if (pix_col && p0 + k - 3 < p1) {
-                const double gx2 = right - left;   // 2*Ix: the reference's 0.5 factors are folded into the solve
-                const double gy2 = s1c - s1a;      // 2*Iy
-                const double e = s0b - s1b;
-                a00 = __fma_rn(gx2, gx2, a00);
-                a01 = __fma_rn(gx2, gy2, a01);
-                a11 = __fma_rn(gy2, gy2, a11);
-                b0 = __fma_rn(gx2, e, b0);
-                b1 = __fma_rn(gy2, e, b1);
-              }
-            }
-            s1a = s1b;
-            s1b = s1c;
-            s0b = s0c;
-          }
-          h1p = h1;
-          h0p = h0;
+        if (interior) {
+          walk_rows<R, FIXED, true>(sm, NK, nc, rowbase, col, p0, p1, pix_col, true, fx, a00, a01, a11, b0, b1);
+        } else {
+          const double tfx = fx == 1.0 ? regx + 1.0 : regx;
+          const bool vx = col_active && tfx >= 0.0 && tfx <= (double)(w - 2);
+          walk_rows<R, FIXED, false>(sm, NK, nc, rowbase, col, p0, p1, pix_col, vx, fx, a00, a01, a11, b0, b1);
         }
-        a00 = warp_sum(a00);
-        a01 = warp_sum(a01);
-        a11 = warp_sum(a11);
-        b0 = warp_sum(b0);
-        b1 = warp_sum(b1);
+        reduce5(a00, a01, a11, b0, b1, lane);
         // a** = 4*A, b* = 2*b of :444-448 (exact power-of-two scalings): det' = 16 det, step = 2 * A'^-1 b'
         const double det = a00 * a11 - a01 * a01;
         if (!(fabs(det) < 16.0 * 1e-9)) {  // |det| < 1e-9 of :452, scaled exactly
-          const double i00 = a11 / det, i01 = -a01 / det, i11 = a00 / det;
-          sx = 2.0 * (i00 * b0 + i01 * b1);
-          sy = 2.0 * (i01 * b0 + i11 * b1);
+          const double rd = 2.0 / det;
+          sx = (a11 * b0 - a01 * b1) * rd;
+          sy = (a00 * b1 - a01 * b0) * rd;
         }
       }
       n_it++;
       dlx += sx;
       dly += sy;
-      if (hypot(sx, sy) < 1e-3) break;
+      if (sx * sx + sy * sy < 1e-6) break;  // hypot(step) < 1e-3 (:416)
     }
     const double up = (double)(1 << l);
     px = (plx + dlx) * up;
@@ -205,7 +238,7 @@ __device__ void track_one(KltSmem<R>& sm, const PyrView& pv, int fa, int fb, int
 }
 
 template <int R, bool FIXED>
-__global__ void __launch_bounds__(128) klt_kernel(KltLaunch k) {
+__global__ void __launch_bounds__(128, (R <= 5 ? 6 : 3)) klt_kernel(KltLaunch k) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   KltSmem<R>& sm = reinterpret_cast<KltSmem<R>*>(smem_raw)[warp];
