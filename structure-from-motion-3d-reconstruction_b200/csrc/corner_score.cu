@@ -52,7 +52,7 @@ __device__ __forceinline__ bool may_reach(int a, int b, int c, int theta_i) {
 template <int MODE>
 __global__ void __launch_bounds__(256) score_tile_kernel(const uint8_t* __restrict__ img, int w, int h, int pitch, size_t fstride,
                                                         int frame0, CornerWorkView wv, double quality) {
-  __shared__ uint8_t taps[TAP_H * TAP_S];
+  __shared__ __align__(16) uint8_t taps[TAP_H * TAP_S];
   __shared__ int hxx[HS_ROWS * HS_S], hxy[HS_ROWS * HS_S], hyy[HS_ROWS * HS_S];
   __shared__ double wmax[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -60,20 +60,39 @@ __global__ void __launch_bounds__(256) score_tile_kernel(const uint8_t* __restri
   const uint8_t* im = img + (size_t)(frame0 + fr) * fstride;
   const int X0 = blockIdx.x * TW, Y0 = blockIdx.y * TH;
 
-  // phase 0: taps of image(X0-3 .., Y0-3 ..) with clamped coordinates (= the reference's clamped gradient taps)
-  for (int idx = tid; idx < TAP_H * TAP_W; idx += 256) {
-    const int ty = idx / TAP_W, tx = idx - ty * TAP_W;
-    int gx = X0 - 3 + tx, gy = Y0 - 3 + ty;
-    gx = gx < 0 ? 0 : (gx > w - 1 ? w - 1 : gx);
-    gy = gy < 0 ? 0 : (gy > h - 1 ? h - 1 : gy);
-    taps[ty * TAP_S + tx] = __ldg(im + (size_t)gy * pitch + gx);
+  // phase 0: taps of image(X0-3 .., Y0-3 ..) with clamped coordinates (= the reference's clamped gradient taps).
+  // Shared rows start at image column X0-4 (4-aligned), so tap tx lives at byte tx+1.  Tiles whose halo lies
+  // inside the image are staged with aligned 32-bit loads (all loads issued before the stores); border tiles
+  // take the byte path, which implements the clamp.
+  if (X0 >= 4 && X0 + 68 <= w && Y0 >= 3 && Y0 + TAP_H - 3 <= h) {
+    constexpr int WPT = (TAP_H * 18 + 255) / 256;
+    uint32_t v[WPT];
+    const uint8_t* src = im + (size_t)(Y0 - 3) * pitch + (X0 - 4);
+#pragma unroll
+    for (int k = 0; k < WPT; k++) {
+      const int idx = tid + 256 * k, r = idx / 18, c = idx - r * 18;
+      if (idx < TAP_H * 18) v[k] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)r * pitch) + c);
+    }
+#pragma unroll
+    for (int k = 0; k < WPT; k++) {
+      const int idx = tid + 256 * k, r = idx / 18, c = idx - r * 18;
+      if (idx < TAP_H * 18) reinterpret_cast<uint32_t*>(taps)[r * (TAP_S / 4) + c] = v[k];
+    }
+  } else {
+    for (int idx = tid; idx < TAP_H * TAP_W; idx += 256) {
+      const int ty = idx / TAP_W, tx = idx - ty * TAP_W;
+      int gx = X0 - 3 + tx, gy = Y0 - 3 + ty;
+      gx = gx < 0 ? 0 : (gx > w - 1 ? w - 1 : gx);
+      gy = gy < 0 ? 0 : (gy > h - 1 ? h - 1 : gy);
+      taps[ty * TAP_S + tx + 1] = __ldg(im + (size_t)gy * pitch + gx);
+    }
   }
   __syncthreads();
 
   // phase 1: horizontal 5-sums of the gradient products.  warp = column group (8 outputs), lane = row.
   {
     const int r = lane, cb = warp * 8;
-    const uint8_t* tm = taps + r * TAP_S + cb;
+    const uint8_t* tm = taps + r * TAP_S + cb + 1;
     const uint8_t* tc = tm + TAP_S;
     const uint8_t* tp = tc + TAP_S;
     int pxx[12], pxy[12], pyy[12];

@@ -25,12 +25,16 @@ int sfm_corner_candidates_batch(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int fir
 
 namespace {
 
-constexpr int SEL_THREADS = 1024;
+constexpr int SEL_THREADS = 256;          // small blocks: several frames resident per SM hide the serial latencies
 constexpr int SEL_WARPS = SEL_THREADS / 32;
-constexpr int SMALL = 2048;       // segments up to this size are sorted by one warp
-constexpr int CHUNK = 1024;       // candidates decided per selection round
-constexpr int BSTACK = 96;        // block stack entries (depth limit is 2*lg(n) <= 64)
-constexpr int WSTACK = 64;        // per-warp stack entries
+constexpr int EPT = 4;                    // elements per thread / lane and pass
+constexpr int SMALL = 2048;               // segments up to this size are sorted by one warp
+constexpr int WINDOW = 8192;              // the sorted prefix is extended in windows of about this many elements
+constexpr int CHUNK = SEL_THREADS * EPT;  // candidates examined per selection round
+constexpr int ALIVE_CAP = SEL_THREADS;    // survivors resolved per selection round
+constexpr int BSTACK = 640;               // block stack entries (<= depth limit + WINDOW/17 in the worst case)
+constexpr int MAXT = 256;                 // small segments sorted per window at most
+constexpr int WSTACK = 64;                // per-warp stack entries (>= 2*lg(n))
 constexpr unsigned EMPTY = 0xFFFFFFFFu;
 
 struct Seg {
@@ -41,36 +45,90 @@ struct SelSmem {
   Seg bstack[BSTACK];
   Seg wstack[SEL_WARPS][WSTACK];
   int2 leaf[SEL_WARPS][32];
-  Seg task[SEL_WARPS];
-  int wcntL[SEL_WARPS], wcntR[SEL_WARPS], wpreL[SEL_WARPS], wpreR[SEL_WARPS];
-  int totL, totR;
-  int bsp, ntask, sorted_upto, consumed, accepted, flag;
+  int wcnt[SEL_WARPS], wpre[SEL_WARPS];
+  int tot;
+  int bsp, big_at, ntask, next_task, sorted_upto, consumed, accepted, flag, cut, error;
   int red[SEL_WARPS];
   // selection chunk
-  unsigned short ax[CHUNK], ay[CHUNK];
-  unsigned char st[CHUNK];
+  unsigned short ax[ALIVE_CAP], ay[ALIVE_CAP];
+  unsigned char st[ALIVE_CAP];
 };
 
 enum { ST_UNDEC = 0, ST_ACC = 1, ST_DEAD = 2 };
 
+// Leaf (<= 16 elements): stable insertion sort done in registers/local memory instead of on L2-resident data.
+__device__ __forceinline__ void leaf_sort_local(sfm_key_t* key, uint32_t* idx, int f, int l) {
+  sfm_key_t k[SFM_SORT_THRESHOLD];
+  uint32_t v[SFM_SORT_THRESHOLD];
+  const int n = l - f;
+#pragma unroll
+  for (int i = 0; i < SFM_SORT_THRESHOLD; i++)
+    if (i < n) {
+      k[i] = key[f + i];
+      v[i] = idx[f + i];
+    }
+  for (int i = 1; i < n; i++) {
+    const sfm_key_t vk = k[i];
+    const uint32_t vi = v[i];
+    int j = i;
+    while (j > 0 && vk > k[j - 1]) {
+      k[j] = k[j - 1];
+      v[j] = v[j - 1];
+      j--;
+    }
+    k[j] = vk;
+    v[j] = vi;
+  }
+#pragma unroll
+  for (int i = 0; i < SFM_SORT_THRESHOLD; i++)
+    if (i < n) {
+      key[f + i] = k[i];
+      idx[f + i] = v[i];
+    }
+}
+
 // ---- warp-level partition of [f, l) (l - f > 16); returns cut (identical in all lanes) --------------------
+// Each lane owns EPT consecutive positions per pass (from the left for the "left misfit" scan, from the right
+// for the "right misfit" scan), so ranks are lane-prefix + in-lane order: two ordered compactions.
 __device__ int warp_partition(sfm_key_t* key, uint32_t* idx, int f, int l, uint32_t* lpos, uint32_t* rpos, int lane) {
   if (lane == 0) sfm_median_to_first(key, idx, f, l);
   __syncwarp();
   const sfm_key_t p = key[f];
   const int mR = l - f - 1;
   int nl = 0, nr = 0;
-  for (int t0 = 0; t0 < mR; t0 += 32) {
-    const int t = t0 + lane;
-    const bool v = t < mR;
-    const bool isL = v && !(key[f + 1 + t] > p);
-    const bool isR = v && !(p > key[l - 1 - t]);
-    const unsigned bl = __ballot_sync(0xffffffffu, isL), br = __ballot_sync(0xffffffffu, isR);
-    const unsigned lt = (1u << lane) - 1u;
-    if (isL) lpos[f + nl + __popc(bl & lt)] = (uint32_t)(f + 1 + t);
-    if (isR) rpos[f + nr + __popc(br & lt)] = (uint32_t)(l - 1 - t);
-    nl += __popc(bl);
-    nr += __popc(br);
+  for (int t0 = 0; t0 < mR; t0 += 32 * EPT) {
+    const int tb = t0 + lane * EPT;
+    sfm_key_t kl[EPT], kr[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; e++) {
+      const bool v = tb + e < mR;
+      kl[e] = v ? key[f + 1 + tb + e] : 0;
+      kr[e] = v ? key[l - 1 - tb - e] : 0;
+    }
+    unsigned ml = 0, mr = 0;
+#pragma unroll
+    for (int e = 0; e < EPT; e++) {
+      const bool v = tb + e < mR;
+      if (v && !(kl[e] > p)) ml |= 1u << e;
+      if (v && !(p > kr[e])) mr |= 1u << e;
+    }
+    const int c = __popc(ml) | (__popc(mr) << 16);
+    int inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += u;
+    }
+    const int tot = __shfl_sync(0xffffffffu, inc, 31);
+    const int exc = inc - c;
+    int ol = f + nl + (exc & 0xFFFF), orr = f + nr + (exc >> 16);
+#pragma unroll
+    for (int e = 0; e < EPT; e++) {
+      if (ml & (1u << e)) lpos[ol++] = (uint32_t)(f + 1 + tb + e);
+      if (mr & (1u << e)) rpos[orr++] = (uint32_t)(l - 1 - tb - e);
+    }
+    nl += tot & 0xFFFF;
+    nr += tot >> 16;
   }
   __syncwarp();
   const int lim = nl < nr ? nl : nr;
@@ -111,15 +169,14 @@ __device__ void warp_sort_segment(SelSmem& sm, sfm_key_t* key, uint32_t* idx, ui
       nleaf++;
       if (nleaf == 32) {
         __syncwarp();
-        sfm_leaf_sort(key, idx, leaf[lane].x, leaf[lane].y);
+        leaf_sort_local(key, idx, leaf[lane].x, leaf[lane].y);
         nleaf = 0;
         __syncwarp();
       }
       continue;
     }
     if (s.d == 0 || sp + 2 > WSTACK) {
-      // depth limit reached (libstdc++: __partial_sort); also the guard for a full stack, which cannot
-      // happen while WSTACK >= depth limit.
+      // depth limit reached (libstdc++: __partial_sort); the stack guard cannot trigger while WSTACK >= 2*lg(n)
       if (lane == 0) sfm_heap_sort(key, idx, s.f, s.l);
       __syncwarp();
       continue;
@@ -133,8 +190,35 @@ __device__ void warp_sort_segment(SelSmem& sm, sfm_key_t* key, uint32_t* idx, ui
     __syncwarp();
   }
   __syncwarp();
-  if (lane < nleaf) sfm_leaf_sort(key, idx, leaf[lane].x, leaf[lane].y);
+  if (lane < nleaf) leaf_sort_local(key, idx, leaf[lane].x, leaf[lane].y);
   __syncwarp();
+}
+
+// Block-wide exclusive scan of a packed pair of 16-bit counts (value < 2^16 in total per field).
+__device__ __forceinline__ int block_scan_packed(SelSmem& sm, int c, int& total) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int inc = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) sm.wcnt[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const int a = lane < SEL_WARPS ? sm.wcnt[lane] : 0;
+    int ia = a;
+#pragma unroll
+    for (int o = 1; o < SEL_WARPS; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, ia, o);
+      if (lane >= o) ia += u;
+    }
+    if (lane < SEL_WARPS) sm.wpre[lane] = ia - a;
+    if (lane == SEL_WARPS - 1) sm.tot = ia;
+  }
+  __syncthreads();
+  total = sm.tot;
+  return inc - c + sm.wpre[warp];
 }
 
 // ---- block-level partition of [f, l); returns cut (identical in all threads) ------------------------------------
@@ -145,42 +229,33 @@ __device__ int block_partition(SelSmem& sm, sfm_key_t* key, uint32_t* idx, int f
   const sfm_key_t p = key[f];
   const int mR = l - f - 1;
   int nl = 0, nr = 0;
-  for (int t0 = 0; t0 < mR; t0 += SEL_THREADS) {
-    const int t = t0 + tid;
-    const bool v = t < mR;
-    const bool isL = v && !(key[f + 1 + t] > p);
-    const bool isR = v && !(p > key[l - 1 - t]);
-    const unsigned bl = __ballot_sync(0xffffffffu, isL), br = __ballot_sync(0xffffffffu, isR);
-    if (lane == 0) {
-      sm.wcntL[warp] = __popc(bl);
-      sm.wcntR[warp] = __popc(br);
-    }
-    __syncthreads();
-    if (warp == 0) {
-      int a = sm.wcntL[lane], b = sm.wcntR[lane];
-      int ia = a, ib = b;
+  for (int t0 = 0; t0 < mR; t0 += SEL_THREADS * EPT) {
+    const int tb = t0 + tid * EPT;
+    sfm_key_t kl[EPT], kr[EPT];
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int ua = __shfl_up_sync(0xffffffffu, ia, o), ub = __shfl_up_sync(0xffffffffu, ib, o);
-        if (lane >= o) {
-          ia += ua;
-          ib += ub;
-        }
-      }
-      sm.wpreL[lane] = ia - a;
-      sm.wpreR[lane] = ib - b;
-      if (lane == 31) {
-        sm.totL = ia;
-        sm.totR = ib;
-      }
+    for (int e = 0; e < EPT; e++) {
+      const bool v = tb + e < mR;
+      kl[e] = v ? key[f + 1 + tb + e] : 0;
+      kr[e] = v ? key[l - 1 - tb - e] : 0;
     }
-    __syncthreads();
-    const unsigned lt = (1u << lane) - 1u;
-    if (isL) lpos[f + nl + sm.wpreL[warp] + __popc(bl & lt)] = (uint32_t)(f + 1 + t);
-    if (isR) rpos[f + nr + sm.wpreR[warp] + __popc(br & lt)] = (uint32_t)(l - 1 - t);
-    nl += sm.totL;
-    nr += sm.totR;
-    __syncthreads();
+    unsigned ml = 0, mr = 0;
+#pragma unroll
+    for (int e = 0; e < EPT; e++) {
+      const bool v = tb + e < mR;
+      if (v && !(kl[e] > p)) ml |= 1u << e;
+      if (v && !(p > kr[e])) mr |= 1u << e;
+    }
+    int tot;
+    const int exc = block_scan_packed(sm, __popc(ml) | (__popc(mr) << 16), tot);
+    int ol = f + nl + (exc & 0xFFFF), orr = f + nr + (exc >> 16);
+#pragma unroll
+    for (int e = 0; e < EPT; e++) {
+      if (ml & (1u << e)) lpos[ol++] = (uint32_t)(f + 1 + tb + e);
+      if (mr & (1u << e)) rpos[orr++] = (uint32_t)(l - 1 - tb - e);
+    }
+    nl += tot & 0xFFFF;
+    nr += tot >> 16;
+    __syncthreads();  // sm.tot / wpre are reused by the next pass
   }
   const int lim = nl < nr ? nl : nr;
   int cnt = 0;
@@ -202,52 +277,82 @@ __device__ int block_partition(SelSmem& sm, sfm_key_t* key, uint32_t* idx, int f
   return (int)cut;
 }
 
-// Extend the sorted prefix: pops the block stack until at least `want` sorted-but-unconsumed elements exist
-// or the stack is empty.  Uniform control flow across the block.
+// Extend the sorted prefix until at least `want` sorted-but-unconsumed elements exist or everything is sorted.
+// The block stack holds the pending introsort segments left to right (top = leftmost).  Within a window past
+// the sorted prefix every segment larger than SMALL is first split by the whole block; the small segments of
+// the window are then sorted concurrently, one warp each (dynamic assignment).
 __device__ void produce_sorted(SelSmem& sm, sfm_key_t* key, uint32_t* idx, uint32_t* lpos, uint32_t* rpos, int want) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   while (true) {
     __syncthreads();
     if (sm.bsp == 0 || sm.sorted_upto - sm.consumed >= want) break;
-    const Seg top = sm.bstack[sm.bsp - 1];
+    if (tid == 0) {
+      // scan the window from the top of the stack: first unsorted big segment, or the number of small ones
+      const long long target = (long long)sm.sorted_upto + WINDOW;
+      int e = sm.bsp - 1, nt = 0, big = -1;
+      while (e >= 0 && sm.bstack[e].f < target && nt < MAXT) {
+        if (sm.bstack[e].l - sm.bstack[e].f > SMALL && sm.bstack[e].d >= 0) {
+          big = e;
+          break;
+        }
+        nt++;
+        e--;
+      }
+      sm.big_at = big;
+      sm.ntask = nt;
+      sm.next_task = 0;
+    }
     __syncthreads();
-    if (top.l - top.f > SMALL) {
-      if (top.d == 0 || sm.bsp + 1 > BSTACK) {
+    const int big = sm.big_at;
+    if (big >= 0) {
+      const Seg s = sm.bstack[big];
+      __syncthreads();
+      if (sm.bsp + 1 > BSTACK) {
+        // Unreachable: at most 2*lg(n) pending right siblings + MAXT small segments are ever stacked.  Never
+        // degrade silently: flag the frame and stop.
+        if (tid == 0) sm.error = 1;
+        __syncthreads();
+        return;
+      }
+      if (s.d == 0) {
+        // depth limit reached (libstdc++: __partial_sort): sequential heap sort, then the segment only waits
+        // to be retired (d = -1 marks "sorted")
         if (tid == 0) {
-          sfm_heap_sort(key, idx, top.f, top.l);
-          sm.bsp--;
-          sm.sorted_upto = top.l;
+          sfm_heap_sort(key, idx, s.f, s.l);
+          sm.bstack[big].d = -1;
         }
         continue;
       }
-      const int cut = block_partition(sm, key, idx, top.f, top.l, lpos, rpos);
+      const int cut = block_partition(sm, key, idx, s.f, s.l, lpos, rpos);
       if (tid == 0) {
-        sm.bstack[sm.bsp - 1] = Seg{cut, top.l, top.d - 1};
-        sm.bstack[sm.bsp] = Seg{top.f, cut, top.d - 1};
+        for (int e = sm.bsp; e > big + 1; e--) sm.bstack[e] = sm.bstack[e - 1];  // make room above `big`
+        sm.bstack[big] = Seg{cut, s.l, s.d - 1};
+        sm.bstack[big + 1] = Seg{s.f, cut, s.d - 1};
         sm.bsp++;
       }
       continue;
     }
-    // gather consecutive small segments (left to right) for the warps
-    if (tid == 0) {
-      int nt = 0;
-      while (nt < SEL_WARPS && sm.bsp > 0 && sm.bstack[sm.bsp - 1].l - sm.bstack[sm.bsp - 1].f <= SMALL) {
-        sm.task[nt++] = sm.bstack[sm.bsp - 1];
-        sm.bsp--;
-      }
-      sm.ntask = nt;
+    // every segment of the window is small: sort them concurrently, one warp per segment
+    const int nt = sm.ntask, top = sm.bsp - 1;
+    while (true) {
+      int t = 0;
+      if (lane == 0) t = atomicAdd(&sm.next_task, 1);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t >= nt) break;
+      const Seg s = sm.bstack[top - t];
+      if (s.d >= 0) warp_sort_segment(sm, key, idx, lpos, rpos, s, warp, lane);
     }
     __syncthreads();
-    const int nt = sm.ntask;
-    if (warp < nt) warp_sort_segment(sm, key, idx, lpos, rpos, sm.task[warp], warp, lane);
-    __syncthreads();
-    if (tid == 0) sm.sorted_upto = sm.task[nt - 1].l;
+    if (tid == 0) {
+      sm.sorted_upto = sm.bstack[top - (nt - 1)].l;
+      sm.bsp -= nt;
+    }
   }
 }
 
 // mode 0: full shi_tomasi selection; mode 1: sort only (sfmgpu_sort_perm_desc).
-__global__ void __launch_bounds__(SEL_THREADS) select_kernel(CornerWorkView wv, int w, int max_corners, int min_dist, int mode,
-                                                            double2* __restrict__ out_xy, int* __restrict__ out_n) {
+__global__ void __launch_bounds__(SEL_THREADS, 4) select_kernel(CornerWorkView wv, int w, int max_corners, int min_dist, int mode,
+                                                               double2* __restrict__ out_xy, int* __restrict__ out_n) {
   extern __shared__ __align__(16) unsigned char sel_raw[];
   SelSmem& sm = *reinterpret_cast<SelSmem*>(sel_raw);
   const int fr = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -273,71 +378,87 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(CornerWorkView wv, 
     sm.sorted_upto = 0;
     sm.consumed = 0;
     sm.accepted = 0;
+    sm.error = 0;
   }
   __syncthreads();
   if (mode == 1) {
     produce_sorted(sm, key, idx, lpos, rpos, 0x7fffffff);
+    if (tid == 0 && sm.error) wv.status[fr] = 2;
     return;
   }
-  unsigned* grid = wv.grid + (size_t)fr * wv.grid_per_frame;
+  const uint2* grid = reinterpret_cast<const uint2*>(wv.grid + (size_t)fr * wv.grid_per_frame);
+  unsigned* gridw = wv.grid + (size_t)fr * wv.grid_per_frame;
   double2* out = out_xy + (size_t)fr * cap_out;
   const int d = min_dist, d2 = min_dist * min_dist;
   const bool suppress = wv.cell > 0;
 
   while (true) {
     produce_sorted(sm, key, idx, lpos, rpos, CHUNK);
+    if (sm.error) {
+      if (tid == 0) {
+        wv.status[fr] = 2;
+        if (out_n) out_n[fr] = -1;
+      }
+      return;
+    }
     const int consumed = sm.consumed, upto = sm.sorted_upto, acc0 = sm.accepted;
     if (consumed >= upto || acc0 >= cap_out) break;
     const int cnt = min(CHUNK, upto - consumed);
     __syncthreads();
-    // (1) candidates of this chunk vs corners accepted in earlier chunks
-    int x = 0, y = 0;
-    bool alive = false;
-    if (tid < cnt) {
-      const unsigned pix = idx[consumed + tid];
-      y = (int)(pix / (unsigned)w);
-      x = (int)(pix - (unsigned)y * (unsigned)w);
-      alive = true;
-      if (suppress) {
-        const int cx = x / d, cy = y / d;
-        for (int gy = max(cy - 1, 0); gy <= min(cy + 1, wv.gh - 1) && alive; gy++)
-          for (int gx = max(cx - 1, 0); gx <= min(cx + 1, wv.gw - 1) && alive; gx++) {
-            const unsigned* cell = grid + ((size_t)gy * wv.gw + gx) * 2;
+    // (1) candidates of this chunk vs corners accepted in earlier chunks; EPT consecutive candidates per thread
+    int cx_[EPT], cy_[EPT];
+    unsigned am = 0;
 #pragma unroll
-            for (int s = 0; s < 2; s++) {
-              const unsigned v = __ldcg(cell + s);
-              if (v != EMPTY) {
-                const int dx = (int)(v & 0xFFFFu) - x, dy = (int)(v >> 16) - y;
+    for (int e = 0; e < EPT; e++) {
+      const int t = tid * EPT + e;
+      cx_[e] = cy_[e] = 0;
+      if (t < cnt) {
+        const unsigned pix = idx[consumed + t];
+        const int y = (int)(pix / (unsigned)w), x = (int)(pix - (unsigned)y * (unsigned)w);
+        cx_[e] = x;
+        cy_[e] = y;
+        bool alive = true;
+        if (suppress) {
+          const int gx0 = max(x / d - 1, 0), gx1 = min(x / d + 1, wv.gw - 1);
+          const int gy0 = max(y / d - 1, 0), gy1 = min(y / d + 1, wv.gh - 1);
+          for (int gy = gy0; gy <= gy1; gy++)
+            for (int gx = gx0; gx <= gx1; gx++) {
+              const uint2 v = __ldcg(grid + (size_t)gy * wv.gw + gx);
+              if (v.x != EMPTY) {
+                const int dx = (int)(v.x & 0xFFFFu) - x, dy = (int)(v.x >> 16) - y;
+                if (dx * dx + dy * dy < d2) alive = false;
+              }
+              if (v.y != EMPTY) {
+                const int dx = (int)(v.y & 0xFFFFu) - x, dy = (int)(v.y >> 16) - y;
                 if (dx * dx + dy * dy < d2) alive = false;
               }
             }
-          }
+        }
+        if (alive) am |= 1u << e;
       }
     }
-    // ordered compaction of the survivors into ax/ay (block scan of `alive`)
-    const unsigned bal = __ballot_sync(0xffffffffu, alive);
-    if (lane == 0) sm.wcntL[warp] = __popc(bal);
+    // ordered compaction of the survivors; at most ALIVE_CAP are resolved now, the chunk is cut after the last one
+    int na;
+    const int exc = block_scan_packed(sm, __popc(am), na);
+    if (tid == 0) sm.cut = cnt;
     __syncthreads();
-    if (warp == 0) {
-      const int a = sm.wcntL[lane];
-      int ia = a;
+    {
+      int r = exc;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int ua = __shfl_up_sync(0xffffffffu, ia, o);
-        if (lane >= o) ia += ua;
-      }
-      sm.wpreL[lane] = ia - a;
-      if (lane == 31) sm.totL = ia;
+      for (int e = 0; e < EPT; e++)
+        if (am & (1u << e)) {
+          if (r < ALIVE_CAP) {
+            sm.ax[r] = (unsigned short)cx_[e];
+            sm.ay[r] = (unsigned short)cy_[e];
+            sm.st[r] = ST_UNDEC;
+          }
+          if (r == ALIVE_CAP) sm.cut = tid * EPT + e;  // first candidate that does not fit: it starts the next chunk
+          r++;
+        }
     }
+    na = na < ALIVE_CAP ? na : ALIVE_CAP;
     __syncthreads();
-    const int na = sm.totL;
-    if (alive) {
-      const int k = sm.wpreL[warp] + __popc(bal & ((1u << lane) - 1u));
-      sm.ax[k] = (unsigned short)x;
-      sm.ay[k] = (unsigned short)y;
-      sm.st[k] = ST_UNDEC;
-    }
-    __syncthreads();
+    const int used = sm.cut;
     // (2) conflicts inside the chunk, by rounds
     if (suppress) {
       while (true) {
@@ -374,28 +495,15 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(CornerWorkView wv, 
     }
     // (3) append accepted survivors in priority order, stop at the cap
     const bool acc = tid < na && sm.st[tid] == ST_ACC;
-    const unsigned bac = __ballot_sync(0xffffffffu, acc);
-    if (lane == 0) sm.wcntR[warp] = __popc(bac);
-    __syncthreads();
-    if (warp == 0) {
-      const int a = sm.wcntR[lane];
-      int ia = a;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int ua = __shfl_up_sync(0xffffffffu, ia, o);
-        if (lane >= o) ia += ua;
-      }
-      sm.wpreR[lane] = ia - a;
-      if (lane == 31) sm.totR = ia;
-    }
-    __syncthreads();
+    int nacc;
+    const int rank = block_scan_packed(sm, acc ? 1 : 0, nacc);
     if (acc) {
-      const int k = acc0 + sm.wpreR[warp] + __popc(bac & ((1u << lane) - 1u));
+      const int k = acc0 + rank;
       if (k < cap_out) {
         const int px = sm.ax[tid], py = sm.ay[tid];
         out[k] = make_double2((double)px, (double)py);
         if (suppress) {
-          unsigned* cell = grid + ((size_t)(py / d) * wv.gw + (px / d)) * 2;
+          unsigned* cell = gridw + ((size_t)(py / d) * wv.gw + (px / d)) * 2;
           const unsigned v = ((unsigned)py << 16) | (unsigned)px;
           if (atomicCAS(cell, EMPTY, v) != EMPTY) atomicCAS(cell + 1, EMPTY, v);
         }
@@ -403,10 +511,9 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(CornerWorkView wv, 
     }
     __syncthreads();
     if (tid == 0) {
-      sm.accepted = min(cap_out, acc0 + sm.totR);
-      sm.consumed = consumed + cnt;
+      sm.accepted = min(cap_out, acc0 + nacc);
+      sm.consumed = consumed + used;
     }
-    __threadfence_block();
     __syncthreads();
   }
   if (tid == 0 && out_n) out_n[fr] = sm.accepted;

@@ -237,7 +237,7 @@ int sfmgpu_pair_frontend(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int
   // corners, in chunks of frames that bound the work area
   const int cand_cap = default_cand_cap(f->w, f->h);
   const int md = cfg->min_distance < 0 ? -cfg->min_distance : cfg->min_distance;
-  int chunk = npairs < 256 ? npairs : 256;
+  int chunk = npairs < 1024 ? npairs : 1024;  // frames per corner launch: >= 4 blocks per SM keeps the select kernel busy
   const size_t wb = sfm_corner_work_bytes_md(f->w, f->h, chunk, cand_cap, md);
   SFM_TRY(sfm_reserve(ctx, out->work, wb));
   for (int c0 = 0; c0 < npairs; c0 += chunk) {
