@@ -176,11 +176,33 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Route everything libraries print on fd 1 (e.g. NCCL's version banner) to stderr; the JSON line alone goes to
+    the real stdout through emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -266,11 +288,43 @@ def main():
     h2d = host.nbytes
     d2h = li.nbytes + lj.nbytes + nk.nbytes + nc.nbytes
 
+    if world > 1:
+        # multi-GPU: every rank's tracks go to rank 0 over NCCL (padded gather of the device-resident results),
+        # rank 0 then reads everything back to pinned host memory
+        v_li, v_lj, v_nk, v_nc = pairs.torch_views(npairs)
+        if rank == 0:
+            g_li = [torch.empty_like(v_li) for _ in range(world)]
+            g_lj = [torch.empty_like(v_lj) for _ in range(world)]
+            g_nk = [torch.empty_like(v_nk) for _ in range(world)]
+            g_nc = [torch.empty_like(v_nc) for _ in range(world)]
+            h_li = torch.empty((world,) + tuple(v_li.shape), dtype=v_li.dtype, pin_memory=True)
+            h_lj = torch.empty((world,) + tuple(v_lj.shape), dtype=v_lj.dtype, pin_memory=True)
+            h_nk = torch.empty((world, npairs), dtype=torch.int32, pin_memory=True)
+            h_nc = torch.empty((world, npairs), dtype=torch.int32, pin_memory=True)
+            d2h = h_li.numel() * 8 + h_lj.numel() * 8 + h_nk.numel() * 4 + h_nc.numel() * 4
+        else:
+            g_li = g_lj = g_nk = g_nc = None
+            d2h = 0
+
     def step_e2e():
         frames.upload_ptr(0, nfr, host.ctypes.data)
         frames.build_pyramid(0, nfr)
         pairs.run(frames, 0, npairs, cfg)
-        pairs.download_all(li, lj, nk, nc)
+        if world == 1:
+            pairs.download_all(li, lj, nk, nc)
+            return
+        ctx.sync()  # results are written on the library's stream; NCCL runs on torch's
+        dist.gather(v_nk, g_nk, dst=0)
+        dist.gather(v_nc, g_nc, dst=0)
+        dist.gather(v_li, g_li, dst=0)
+        dist.gather(v_lj, g_lj, dst=0)
+        if rank == 0:
+            for r in range(world):
+                h_li[r].copy_(g_li[r], non_blocking=True)
+                h_lj[r].copy_(g_lj[r], non_blocking=True)
+                h_nk[r].copy_(g_nk[r], non_blocking=True)
+                h_nc[r].copy_(g_nc[r], non_blocking=True)
+        torch.cuda.synchronize()
 
     e2e_steps = max(1, min(args.steps, 3))
     step_e2e()
@@ -282,7 +336,10 @@ def main():
     e2e_ms_dev = ctx.timer_stop()
     e2e_wall = (time.perf_counter() - t0) * 1e3
     e2e_ms = max(e2e_ms_dev, e2e_wall) / e2e_steps
-    assert int(nc.sum()) == n_tracks and int(nk.sum()) == n_kept, "e2e results differ from the resident run"
+    if world == 1:
+        assert int(nc.sum()) == n_tracks and int(nk.sum()) == n_kept, "e2e results differ from the resident run"
+    elif rank == 0:
+        assert int(h_nc[0].sum()) == n_tracks and int(h_nk[0].sum()) == n_kept, "gathered results differ from the resident run"
 
     # ---- RANSAC half of the metric (C4), rank-local ---------------------------------------------------------------------
     xi, xj = c4_points(RS_N)
@@ -308,9 +365,9 @@ def main():
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(work, op=dist.ReduceOp.SUM)
-        mine = torch.from_numpy(np.stack([nc, nk]).astype(np.int32)).cuda()
-        gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
-        dist.gather(mine, gathered, dst=0)  # the scheduler's result gather (tracks/inlier sets would ride the same call)
+        d2h_t = torch.tensor([d2h], device="cuda", dtype=torch.int64)
+        dist.all_reduce(d2h_t, op=dist.ReduceOp.SUM)
+        d2h = int(d2h_t.item())
     ms_step, e2e_ms, rs_ms, pyr_ms, klt_ms, cs_ms, sel_ms = [float(v) for v in vals.tolist()]
     tracks_all, kept_all, it_all = [int(v) for v in work.tolist()]
 
@@ -326,7 +383,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_cfg(world, nfr),
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * (world if world == 1 else 1),
+                    "gather": "none (1 GPU)" if world == 1 else f"NCCL gather of tracks + counts to rank 0, {world} ranks",
                     "ms_per_step": e2e_ms, "steps": e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -352,7 +410,7 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(host)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

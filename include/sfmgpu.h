@@ -113,7 +113,8 @@ int sfmgpu_sort_perm_desc(sfmgpu_ctx* ctx, const double* keys, int n, int32_t* p
 
 /* ---- KLT: track_one / lk_step / sample_bilinear (:183-198, :396-460) ------------------------------- */
 /* Forward track frame a -> b and backward b -> a for n points (what :356-361 and :1846-1848 do per
- * track).  p1 = forward result, p0_back = backward result; n_iters (optional) = LK iterations executed. */
+ * track).  p1 = forward result, p0_back = backward result (NULL: forward only, i.e. one track_one_public call
+ * per point); n_iters (optional) = LK iterations executed. */
 int sfmgpu_klt_track(sfmgpu_ctx* ctx, sfmgpu_frames* f, int frame_a, int frame_b, const double* p0_xy, int n,
                      int win_radius, int iters, double* p1_xy, double* p0_back_xy, int32_t* n_iters);
 

@@ -253,10 +253,10 @@ __global__ void __launch_bounds__(128, (R <= 5 ? 6 : 3)) klt_kernel(KltLaunch k)
   track_one<R, FIXED>(sm, k.pv, fa, fb, k.radius, k.iters, x, y, n_it, lane);
   const double x1 = x, y1 = y;
   __syncwarp();
-  track_one<R, FIXED>(sm, k.pv, fb, fa, k.radius, k.iters, x, y, n_it, lane);
+  if (k.pb) track_one<R, FIXED>(sm, k.pv, fb, fa, k.radius, k.iters, x, y, n_it, lane);  // pb == null: forward only
   if (lane == 0) {
     k.p1[g] = make_double2(x1, y1);
-    k.pb[g] = make_double2(x, y);
+    if (k.pb) k.pb[g] = make_double2(x, y);
     if (k.nit) k.nit[g] = n_it;
     if (k.keep) {
       const double fbd = hypot(x - p0.x, y - p0.y);
@@ -299,7 +299,7 @@ extern "C" int sfmgpu_klt_track(sfmgpu_ctx* ctx, sfmgpu_frames* f, int frame_a, 
   if (frame_a < 0 || frame_a >= f->n || frame_b < 0 || frame_b >= f->n || n < 0)
     return sfm_fail(ctx, SFMGPU_E_ARG, "klt_track: bad frame index or count");
   if (n == 0) return 0;
-  if (!p0_xy || !p1_xy || !p0_back_xy) return sfm_fail(ctx, SFMGPU_E_ARG, "klt_track: null pointer");
+  if (!p0_xy || !p1_xy) return sfm_fail(ctx, SFMGPU_E_ARG, "klt_track: null pointer");
   const size_t pb = (size_t)n * sizeof(double2);
   SFM_TRY(sfm_reserve(ctx, ctx->klt_in, pb));
   SFM_TRY(sfm_reserve(ctx, ctx->klt_p1, pb));
@@ -320,12 +320,12 @@ extern "C" int sfmgpu_klt_track(sfmgpu_ctx* ctx, sfmgpu_frames* f, int frame_a, 
   k.iters = iters;
   k.fb_thresh = 0.0;
   k.p1 = (double2*)ctx->klt_p1.p;
-  k.pb = (double2*)ctx->klt_pb.p;
+  k.pb = p0_back_xy ? (double2*)ctx->klt_pb.p : nullptr;  // forward only when the caller does not want the way back
   k.nit = (int*)ctx->klt_nit.p;
   k.keep = nullptr;
   SFM_TRY(sfm_klt_launch(ctx, k));
   SFM_CUDA(ctx, cudaMemcpyAsync(p1_xy, ctx->klt_p1.p, pb, cudaMemcpyDeviceToHost, ctx->stream));
-  SFM_CUDA(ctx, cudaMemcpyAsync(p0_back_xy, ctx->klt_pb.p, pb, cudaMemcpyDeviceToHost, ctx->stream));
+  if (p0_back_xy) SFM_CUDA(ctx, cudaMemcpyAsync(p0_back_xy, ctx->klt_pb.p, pb, cudaMemcpyDeviceToHost, ctx->stream));
   if (n_iters)
     SFM_CUDA(ctx, cudaMemcpyAsync(n_iters, ctx->klt_nit.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -1,0 +1,320 @@
+// sfmgpu_shim.hpp — C++ source-compatible drop-in for the reference's front-end entry points, on top of the C ABI
+// (include/sfmgpu.h).  Same names, parameter lists, return types, ordering guarantees and error behaviour as
+// cpp/src/templering_sfm.cpp:
+//     Pyramid build_pyr(const GrayImage&, int levels)                                   :220-232
+//     std::vector<Vec2> shi_tomasi(const GrayImage&, int max_corners, double q, int d)  :237-302
+//     struct LKConfig / struct Track / class KLTTracker {reset, step, tracks,
+//                                                        track_one_public}             :307-466
+//     struct RelPose; std::optional<RelPose> find_E_ransac(K, pi, pj, iters, thr, mi)   :640-761
+// plus one batched extra, track_pairs(), for callers that loop over track_one_public (:1845-1849).
+//
+// Two ways to use it:
+//   * inside the reference TU: include it after the reference's own headers (its sfm::GrayImage / Vec2 / Vec3 /
+//     Mat33 are used as they are) in place of the reference's definitions of the functions above;
+//   * stand-alone: define SFMGPU_SHIM_STANDALONE first and the minimal PODs below are provided.
+//
+// Errors: CUDA / library failures throw std::runtime_error (the reference's main catches std::exception at
+// :1913); two-view failure is std::nullopt; step() on the first frame returns empty vectors.  There is no CPU
+// fallback: without libsfmgpu.so and a GPU every call throws.
+// Threading: like the reference, single-threaded; one process-wide context (device SFMGPU_DEVICE, default 0).
+#pragma once
+#include <array>
+#include <cstdint>
+#include <cstdlib>
+#include <memory>
+#include <optional>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/sfmgpu.h"
+#include "two_view_host.hpp"
+
+#ifdef SFMGPU_SHIM_STANDALONE
+// Layout-compatible stand-ins for cpp/include/pgm_io.hpp:10-15 and cpp/include/linalg.hpp:15-35.
+namespace sfm {
+struct GrayImage {
+  int w = 0, h = 0;
+  std::vector<std::uint8_t> pix;
+  std::uint8_t at(int x, int y) const { return pix[(size_t)y * w + x]; }
+};
+struct Vec2 {
+  double x{}, y{};
+};
+struct Vec3 {
+  double x{}, y{}, z{};
+};
+struct Mat33 {
+  std::array<double, 9> a{};
+  double& operator()(int r, int c) { return a[3 * r + c]; }
+  double operator()(int r, int c) const { return a[3 * r + c]; }
+};
+}  // namespace sfm
+using sfm::GrayImage;
+using sfm::Mat33;
+using sfm::Vec2;
+using sfm::Vec3;
+#endif
+
+namespace sfmgpu_shim {
+
+inline void check(sfmgpu_ctx* ctx, int rc, const char* what) {
+  if (rc != 0) throw std::runtime_error(std::string("sfmgpu: ") + what + ": " + sfmgpu_last_error(ctx));
+}
+
+// Process-wide context.
+inline sfmgpu_ctx* context() {
+  static sfmgpu_ctx* ctx = [] {
+    sfmgpu_ctx* c = nullptr;
+    const char* dev = std::getenv("SFMGPU_DEVICE");
+    if (sfmgpu_create(dev ? std::atoi(dev) : 0, &c) != 0)
+      throw std::runtime_error("sfmgpu: no usable CUDA device (the GPU front end has no CPU fallback)");
+    return c;
+  }();
+  return ctx;
+}
+
+// Device twin of one Pyramid: a slot in a small pool of equally sized frames, so that two pyramids of the same
+// size (the only case the reference ever tracks between) live in one batch.
+struct Pool {
+  sfmgpu_frames* frames = nullptr;
+  int w = 0, h = 0, levels = 0;
+  std::vector<char> used;
+  ~Pool() {
+    if (frames) sfmgpu_frames_destroy(context(), frames);
+  }
+};
+struct DevicePyr {
+  std::shared_ptr<Pool> pool;
+  int slot = -1;
+  ~DevicePyr() {
+    if (pool && slot >= 0) pool->used[slot] = 0;
+  }
+};
+inline std::shared_ptr<DevicePyr> acquire_slot(int w, int h, int levels) {
+  static std::vector<std::shared_ptr<Pool>> pools;
+  constexpr int SLOTS = 8;
+  for (auto& p : pools)
+    if (p->w == w && p->h == h && p->levels == levels)
+      for (int s = 0; s < SLOTS; s++)
+        if (!p->used[s]) {
+          p->used[s] = 1;
+          auto d = std::make_shared<DevicePyr>();
+          d->pool = p;
+          d->slot = s;
+          return d;
+        }
+  auto p = std::make_shared<Pool>();
+  p->w = w;
+  p->h = h;
+  p->levels = levels;
+  p->used.assign(SLOTS, 0);
+  check(context(), sfmgpu_frames_create(context(), w, h, SLOTS, levels, &p->frames), "frames_create");
+  pools.push_back(p);
+  p->used[0] = 1;
+  auto d = std::make_shared<DevicePyr>();
+  d->pool = p;
+  d->slot = 0;
+  return d;
+}
+
+}  // namespace sfmgpu_shim
+
+// ---- Pyramid / build_pyr (:220-232) -----------------------------------------------------------------------------
+struct Pyramid {
+  std::vector<GrayImage> lvl;                    // host copies, exactly what the reference exposes
+  std::shared_ptr<sfmgpu_shim::DevicePyr> dev;   // the same pyramid resident on the GPU
+};
+
+static Pyramid build_pyr(const GrayImage& im, int levels) {
+  using namespace sfmgpu_shim;
+  if (levels < 1 || levels > 8 || im.w <= 0 || im.h <= 0) throw std::runtime_error("sfmgpu: build_pyr: unsupported image / levels");
+  sfmgpu_ctx* ctx = context();
+  Pyramid p;
+  p.dev = acquire_slot(im.w, im.h, levels);
+  sfmgpu_frames* f = p.dev->pool->frames;
+  check(ctx, sfmgpu_frames_upload(ctx, f, p.dev->slot, 1, im.pix.data()), "frames_upload");
+  check(ctx, sfmgpu_pyramid_build(ctx, f, p.dev->slot, 1), "pyramid_build");
+  p.lvl.reserve((size_t)levels);
+  p.lvl.push_back(im);  // level 0 is a copy of the input (:227)
+  for (int l = 1; l < levels; l++) {
+    GrayImage g;
+    sfmgpu_frames_level_size(f, l, &g.w, &g.h);
+    g.pix.resize((size_t)g.w * g.h);
+    check(ctx, sfmgpu_frames_download(ctx, f, p.dev->slot, l, g.pix.data()), "frames_download");
+    p.lvl.push_back(std::move(g));
+  }
+  return p;
+}
+
+// ---- shi_tomasi (:237-302) ------------------------------------------------------------------------------------------
+static std::vector<Vec2> shi_tomasi(const GrayImage& im, int max_corners, double quality, int min_dist) {
+  using namespace sfmgpu_shim;
+  sfmgpu_ctx* ctx = context();
+  auto slot = acquire_slot(im.w, im.h, 1);
+  sfmgpu_frames* f = slot->pool->frames;
+  check(ctx, sfmgpu_frames_upload(ctx, f, slot->slot, 1, im.pix.data()), "frames_upload");
+  std::vector<double> xy(2 * (size_t)(max_corners < 1 ? 1 : max_corners));
+  int n = 0;
+  check(ctx, sfmgpu_corners(ctx, f, slot->slot, max_corners, quality, min_dist, xy.data(), &n), "corners");
+  std::vector<Vec2> out((size_t)n);
+  for (int i = 0; i < n; i++) out[i] = Vec2{xy[2 * i], xy[2 * i + 1]};
+  return out;
+}
+
+// ---- KLT (:307-466) -----------------------------------------------------------------------------------------------
+struct LKConfig {
+  int max_tracks = 2200;
+  int min_tracks = 900;
+  double quality = 0.01;
+  int min_distance = 8;
+  int pyr_levels = 3;
+  int win_radius = 5;
+  int iters = 10;
+  double fb_thresh = 1.0;
+};
+
+struct Track {
+  int id;
+  Vec2 p;
+};
+
+// Batched form of the loop at :1845-1849: forward a->b and backward b->a for all points in one launch.
+static void track_pairs(const Pyramid& a, const Pyramid& b, const std::vector<Vec2>& p0, int win_radius, int iters,
+                        std::vector<Vec2>& p1, std::vector<Vec2>* p0_back) {
+  using namespace sfmgpu_shim;
+  if (!a.dev || !b.dev || a.dev->pool != b.dev->pool)
+    throw std::runtime_error("sfmgpu: track: pyramids must come from build_pyr and have the same size / levels");
+  sfmgpu_ctx* ctx = context();
+  const int n = (int)p0.size();
+  p1.resize(p0.size());
+  if (p0_back) p0_back->resize(p0.size());
+  if (n == 0) return;
+  static_assert(sizeof(Vec2) == 2 * sizeof(double), "Vec2 must be two packed doubles");
+  check(ctx,
+        sfmgpu_klt_track(ctx, a.dev->pool->frames, a.dev->slot, b.dev->slot, reinterpret_cast<const double*>(p0.data()), n,
+                         win_radius, iters, reinterpret_cast<double*>(p1.data()),
+                         p0_back ? reinterpret_cast<double*>(p0_back->data()) : nullptr, nullptr),
+        "klt_track");
+}
+
+class KLTTracker {
+ public:
+  explicit KLTTracker(LKConfig cfg) : cfg_(cfg) {
+    sfmgpu_lkcfg c;
+    c.max_tracks = cfg.max_tracks;
+    c.min_tracks = cfg.min_tracks;
+    c.quality = cfg.quality;
+    c.min_distance = cfg.min_distance;
+    c.pyr_levels = cfg.pyr_levels;
+    c.win_radius = cfg.win_radius;
+    c.iters = cfg.iters;
+    c.fb_thresh = cfg.fb_thresh;
+    sfmgpu_tracker* t = nullptr;
+    sfmgpu_shim::check(sfmgpu_shim::context(), sfmgpu_tracker_create(sfmgpu_shim::context(), &c, &t), "tracker_create");
+    trk_ = std::shared_ptr<sfmgpu_tracker>(t, [](sfmgpu_tracker* p) { sfmgpu_tracker_destroy(sfmgpu_shim::context(), p); });
+    cap_ = (cfg.max_tracks < 1 ? 1 : cfg.max_tracks) + 1;
+  }
+
+  void reset(const GrayImage& gray) {
+    auto* ctx = sfmgpu_shim::context();
+    sfmgpu_shim::check(ctx, sfmgpu_tracker_reset(ctx, trk_.get(), gray.pix.data(), gray.w, gray.h), "tracker_reset");
+    fetch_tracks();
+  }
+
+  struct StepOut {
+    std::vector<Vec2> prev_pts;
+    std::vector<Vec2> cur_pts;
+    std::vector<int> ids;
+  };
+
+  StepOut step(const GrayImage& gray) {
+    auto* ctx = sfmgpu_shim::context();
+    StepOut out;
+    out.prev_pts.resize((size_t)cap_);
+    out.cur_pts.resize((size_t)cap_);
+    out.ids.resize((size_t)cap_);
+    int n = 0;
+    sfmgpu_shim::check(ctx,
+                       sfmgpu_tracker_step(ctx, trk_.get(), gray.pix.data(), gray.w, gray.h,
+                                           reinterpret_cast<double*>(out.prev_pts.data()),
+                                           reinterpret_cast<double*>(out.cur_pts.data()), out.ids.data(), cap_, &n),
+                       "tracker_step");
+    out.prev_pts.resize((size_t)n);
+    out.cur_pts.resize((size_t)n);
+    out.ids.resize((size_t)n);
+    fetch_tracks();
+    return out;
+  }
+
+  const std::vector<Track>& tracks() const { return tracks_; }
+
+  // Single-direction, single-point track (:396-398).  One launch per call: prefer track_pairs() in loops.
+  Vec2 track_one_public(const Pyramid& a, const Pyramid& b, Vec2 p0) const {
+    std::vector<Vec2> in{p0}, out;
+    track_pairs(a, b, in, cfg_.win_radius, cfg_.iters, out, nullptr);
+    return out[0];
+  }
+
+ private:
+  void fetch_tracks() {
+    auto* ctx = sfmgpu_shim::context();
+    std::vector<double> xy(2 * (size_t)cap_);
+    std::vector<int> ids((size_t)cap_);
+    int n = 0;
+    sfmgpu_shim::check(ctx, sfmgpu_tracker_tracks(ctx, trk_.get(), xy.data(), ids.data(), cap_, &n), "tracker_tracks");
+    tracks_.resize((size_t)n);
+    for (int i = 0; i < n; i++) tracks_[i] = Track{ids[i], Vec2{xy[2 * i], xy[2 * i + 1]}};
+  }
+  LKConfig cfg_;
+  std::shared_ptr<sfmgpu_tracker> trk_;
+  std::vector<Track> tracks_;
+  int cap_ = 0;
+};
+
+// ---- find_E_ransac (:640-761) --------------------------------------------------------------------------------------
+struct RelPose {
+  Mat33 R_ji;
+  Vec3 t_ji;
+  std::vector<int> inliers;
+};
+
+static std::optional<RelPose> find_E_ransac(const Mat33& K, const std::vector<Vec2>& pi, const std::vector<Vec2>& pj, int iters = 2000,
+                                            double thr = 1e-4, int min_inliers = 80) {
+  using namespace sfmgpu_shim;
+  if (pi.size() < 8) return std::nullopt;  // before any RNG use (:648)
+  const int n = (int)pi.size();
+  double Ki[9];
+  if (!sfmgpu_host::invert_K(K.a.data(), Ki)) throw std::runtime_error("Singular K");
+  std::vector<double> xi(2 * (size_t)n), xj(2 * (size_t)n);
+  for (int i = 0; i < n; i++) {
+    sfmgpu_host::norm_point(Ki, pi[i].x, pi[i].y, &xi[2 * i]);
+    sfmgpu_host::norm_point(Ki, pj[i].x, pj[i].y, &xj[2 * i]);
+  }
+  // the reference's seeded sampling (:657-665), one continuing stream, re-seeded on every call
+  std::mt19937 rng(12345);
+  std::uniform_int_distribution<int> uni(0, n - 1);
+  const int H = iters > 0 ? iters : 0;
+  std::vector<double> E(9 * (size_t)H);
+  int idx8[8];
+  for (int it = 0; it < H; it++) {
+    for (int k = 0; k < 8; k++) idx8[k] = uni(rng);
+    sfmgpu_host::eight_point_E(xi.data(), xj.data(), idx8, &E[9 * (size_t)it]);
+  }
+  // scoring loop (:667-676) on the GPU: exact counts, first hypothesis with the strictly largest count
+  sfmgpu_ctx* ctx = context();
+  std::vector<int> inl((size_t)n);
+  int best_h = -1, best_n = 0;
+  check(ctx, sfmgpu_ransac_score(ctx, xi.data(), xj.data(), n, E.data(), H, thr, nullptr, &best_h, inl.data(), &best_n), "ransac_score");
+  if (best_n < min_inliers) return std::nullopt;
+  RelPose rp;
+  double R[9], t[3];
+  // best_h < 0 means "no hypothesis won": the reference then decomposes the zero matrix
+  const double zeroE[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  sfmgpu_host::recover_pose(best_h >= 0 ? &E[9 * (size_t)best_h] : zeroE, xi.data(), xj.data(), inl.data(), best_n, R, t);
+  for (int k = 0; k < 9; k++) rp.R_ji.a[k] = R[k];
+  rp.t_ji = Vec3{t[0], t[1], t[2]};
+  rp.inliers.assign(inl.begin(), inl.begin() + best_n);
+  return rp;
+}

@@ -345,6 +345,22 @@ class Pairs:
         self.ctx._ck(self.ctx.lib.sfmgpu_pairs_device_ptrs(self.h_, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
         return a.value, b.value, c.value, d.value
 
+    def torch_views(self, npairs):
+        """Zero-copy torch views (li, lj [npairs, cap, 2] float64; n_kept, n_corners [npairs] int32) of the device results,
+        for NCCL gathers by the scheduler.  Synchronise the context before handing them to another stream."""
+        import torch
+
+        class _View:
+            def __init__(self, ptr, shape, typestr):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+
+        li, lj, nk, nc = self.device_ptrs()
+        dev = f"cuda:{self.ctx.device}"
+        return (torch.as_tensor(_View(li, (npairs, self.cap, 2), "<f8"), device=dev),
+                torch.as_tensor(_View(lj, (npairs, self.cap, 2), "<f8"), device=dev),
+                torch.as_tensor(_View(nk, (npairs,), "<i4"), device=dev),
+                torch.as_tensor(_View(nc, (npairs,), "<i4"), device=dev))
+
     def download(self, pair):
         li, lj = np.zeros((self.cap, 2)), np.zeros((self.cap, 2))
         nk, nc = _i(0), _i(0)

@@ -1,0 +1,71 @@
+"""Multi-GPU frame-pair / sequence scheduler: one process per GPU, torch.distributed for the plumbing.
+
+The front end shards with NO data-path collective:
+  * pair mode     — the stateless two-view unit (cpp/src/templering_sfm.cpp:1836-1857): pairs (t, t+1) are independent;
+                    rank g owns a contiguous block of pairs plus one halo frame;
+  * sequence mode — whole sequences per rank (a KLTTracker chain cannot be split across frames, :370-371).
+The only communication is the gather of results (tracks, survivor counts, inlier sets) to rank 0: an all_gather of
+per-rank sizes followed by one padded gather (NCCL has no gatherv).  Works on NCCL (GPU tensors) and gloo (CPU tests).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items, world, rank):
+    """Contiguous block [start, end) of n_items for `rank`; sizes differ by at most one, lower ranks get the extra."""
+    base, extra = divmod(n_items, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def pair_shard(n_frames, world, rank):
+    """Pairs [p0, p1) of a sequence of n_frames and the frames [p0, p1] (inclusive halo) the rank must hold."""
+    p0, p1 = shard_range(max(n_frames - 1, 0), world, rank)
+    return p0, p1, (p0, p1 + 1 if p1 > p0 else p0)
+
+
+def sequence_shard(n_sequences, world, rank):
+    return shard_range(n_sequences, world, rank)
+
+
+def _dev(t):
+    return t.device
+
+
+def gather_rows(local, dst=0):
+    """Gather 2-D tensors with different numbers of rows to `dst`.  Returns the list of per-rank tensors on dst,
+    None elsewhere.  One all_gather of row counts + one padded gather."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=_dev(local))
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(s.item()) for s in sizes]
+    cap = max(max(sizes), 1)
+    pad = torch.zeros((cap,) + tuple(local.shape[1:]), dtype=local.dtype, device=_dev(local))
+    pad[: local.shape[0]] = local
+    out = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, out, dst=dst)
+    if rank != dst:
+        return None
+    return [o[:s] for o, s in zip(out, sizes)]
+
+
+def gather_pair_results(n_kept, li, lj, dst=0):
+    """Per-rank results of a block of pairs -> rank `dst`.
+    n_kept: int32 [P]; li, lj: float64 [P, cap, 2] (first n_kept[p] rows of pair p are valid).
+    Returns (n_kept_all [sum P], li_list, lj_list) on dst with pairs in global order, None elsewhere."""
+    dev = _dev(n_kept)
+    flat_i = torch.cat([li[p, : int(n_kept[p])] for p in range(li.shape[0])]) if li.shape[0] else torch.zeros((0, 2), dtype=li.dtype, device=dev)
+    flat_j = torch.cat([lj[p, : int(n_kept[p])] for p in range(lj.shape[0])]) if lj.shape[0] else torch.zeros((0, 2), dtype=lj.dtype, device=dev)
+    counts = gather_rows(n_kept.reshape(-1, 1).to(torch.int64), dst)
+    gi = gather_rows(flat_i, dst)
+    gj = gather_rows(flat_j, dst)
+    if dist.get_rank() != dst:
+        return None
+    counts = torch.cat(counts).reshape(-1)
+    fi, fj = torch.cat(gi), torch.cat(gj)
+    offs = np.concatenate([[0], np.cumsum(counts.cpu().numpy())])
+    li_list = [fi[offs[k]:offs[k + 1]] for k in range(len(counts))]
+    lj_list = [fj[offs[k]:offs[k + 1]] for k in range(len(counts))]
+    return counts, li_list, lj_list
