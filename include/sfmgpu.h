@@ -117,6 +117,10 @@ int sfmgpu_sort_perm_desc(sfmgpu_ctx* ctx, const double* keys, int n, int32_t* p
  * per point); n_iters (optional) = LK iterations executed. */
 int sfmgpu_klt_track(sfmgpu_ctx* ctx, sfmgpu_frames* f, int frame_a, int frame_b, const double* p0_xy, int n,
                      int win_radius, int iters, double* p1_xy, double* p0_back_xy, int32_t* n_iters);
+/* Kernel selection for every KLT launch of this context (tests and profiling; results agree within the parity
+ * budget either way): 0 = automatic (lane-per-feature kernel for batches of >= 6000 features with win_radius 5,
+ * warp-per-feature otherwise), 1 = warp-per-feature only, 2 = lane-per-feature whenever win_radius is 5. */
+int sfmgpu_klt_set_mode(sfmgpu_ctx* ctx, int mode);
 
 /* ---- stateless two-view front end over a batch of pairs (:1836-1857) -------------------------------- */
 /* For every pair (first_frame+k, first_frame+k+1), k < npairs: pyramids must be built; detect up to

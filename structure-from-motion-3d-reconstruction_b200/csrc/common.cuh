@@ -53,7 +53,8 @@ struct sfmgpu_ctx {
   long long launches = 0;
   // scratch, grown on demand (never shrunk)
   DevBuf flush;
-  DevBuf klt_in, klt_p1, klt_pb, klt_nit, klt_keep;
+  DevBuf klt_in, klt_p1, klt_pb, klt_nit, klt_keep, klt_defer;
+  int klt_mode = 0;  // 0 auto, 1 warp-per-feature, 2 lane-per-feature (tests / profiling)
   DevBuf cs_work;    // corner-score work area for single-frame calls
   DevBuf sel_work;   // corner-select work area
   DevBuf misc;       // small scalars

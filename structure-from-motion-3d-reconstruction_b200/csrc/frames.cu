@@ -86,7 +86,7 @@ void sfmgpu_destroy(sfmgpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->flush,  &ctx->klt_in, &ctx->klt_p1, &ctx->klt_pb,    &ctx->klt_nit, &ctx->klt_keep, &ctx->cs_work,
+  DevBuf* bufs[] = {&ctx->flush,  &ctx->klt_in, &ctx->klt_p1, &ctx->klt_pb,    &ctx->klt_nit, &ctx->klt_keep, &ctx->klt_defer, &ctx->cs_work,
                     &ctx->sel_work, &ctx->misc,   &ctx->rs_xi,  &ctx->rs_xj,     &ctx->rs_E,    &ctx->rs_counts, &ctx->rs_inl,
                     &ctx->rs_best};
   for (DevBuf* b : bufs)

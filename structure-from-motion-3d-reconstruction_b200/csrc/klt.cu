@@ -237,36 +237,42 @@ __device__ void track_one(KltSmem<R>& sm, const PyrView& pv, int fa, int fb, int
   }
 }
 
+// list == nullptr: one warp per slot of the launch (grid covers them all).  list != nullptr: the warps of a
+// fixed-size grid walk the deferred-feature list written by klt_lane_kernel (count read from device memory).
 template <int R, bool FIXED>
-__global__ void __launch_bounds__(128, (R <= 5 ? 6 : 3)) klt_kernel(KltLaunch k) {
+__global__ void __launch_bounds__(128, (R <= 5 ? 6 : 3)) klt_kernel(KltLaunch k, const int* __restrict__ list,
+                                                                    const int* __restrict__ list_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   KltSmem<R>& sm = reinterpret_cast<KltSmem<R>*>(smem_raw)[warp];
-  const long long g = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-  if (g >= (long long)k.npairs * k.cap) return;
-  const int pair = (int)(g / k.cap), slot = (int)(g - (long long)pair * k.cap);
-  if (k.counts && slot >= k.counts[pair]) return;
-  const int fa = k.fa0 + pair * k.fa_step, fb = k.fb0 + pair * k.fb_step;
-  const double2 p0 = k.p0[g];
-  int n_it = 0;
-  double x = p0.x, y = p0.y;
-  track_one<R, FIXED>(sm, k.pv, fa, fb, k.radius, k.iters, x, y, n_it, lane);
-  const double x1 = x, y1 = y;
-  __syncwarp();
-  if (k.pb) track_one<R, FIXED>(sm, k.pv, fb, fa, k.radius, k.iters, x, y, n_it, lane);  // pb == null: forward only
-  if (lane == 0) {
-    k.p1[g] = make_double2(x1, y1);
-    if (k.pb) k.pb[g] = make_double2(x, y);
-    if (k.nit) k.nit[g] = n_it;
-    if (k.keep) {
-      const double fbd = hypot(x - p0.x, y - p0.y);
-      k.keep[g] = (fbd >= k.fb_thresh) ? 0 : 1;  // NaN is kept (:362)
+  const long long nwork = list ? (long long)*list_count : (long long)k.npairs * k.cap;
+  for (long long idx = (long long)blockIdx.x * (blockDim.x >> 5) + warp; idx < nwork; idx += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const long long g = list ? (long long)list[idx] : idx;
+    const int pair = (int)(g / k.cap), slot = (int)(g - (long long)pair * k.cap);
+    if (k.counts && slot >= k.counts[pair]) continue;
+    const int fa = k.fa0 + pair * k.fa_step, fb = k.fb0 + pair * k.fb_step;
+    const double2 p0 = k.p0[g];
+    int n_it = 0;
+    double x = p0.x, y = p0.y;
+    __syncwarp();
+    track_one<R, FIXED>(sm, k.pv, fa, fb, k.radius, k.iters, x, y, n_it, lane);
+    const double x1 = x, y1 = y;
+    __syncwarp();
+    if (k.pb) track_one<R, FIXED>(sm, k.pv, fb, fa, k.radius, k.iters, x, y, n_it, lane);  // pb == null: forward only
+    if (lane == 0) {
+      k.p1[g] = make_double2(x1, y1);
+      if (k.pb) k.pb[g] = make_double2(x, y);
+      if (k.nit) k.nit[g] = n_it;
+      if (k.keep) {
+        const double fbd = hypot(x - p0.x, y - p0.y);
+        k.keep[g] = (fbd >= k.fb_thresh) ? 0 : 1;  // NaN is kept (:362)
+      }
     }
   }
 }
 
 template <int R, bool FIXED>
-int launch_r(sfmgpu_ctx* ctx, const KltLaunch& k) {
+int launch_r(sfmgpu_ctx* ctx, const KltLaunch& k, const int* list, const int* list_count) {
   const int warps_per_block = 4;
   const size_t smem = sizeof(KltSmem<R>) * warps_per_block;
   static bool configured = false;
@@ -276,21 +282,52 @@ int launch_r(sfmgpu_ctx* ctx, const KltLaunch& k) {
   }
   const long long total = (long long)k.npairs * k.cap;
   if (total == 0) return 0;
-  const unsigned grid = sfm_cdiv(total, warps_per_block);
-  SFM_LAUNCH(ctx, (klt_kernel<R, FIXED>), grid, warps_per_block * 32, smem, k);
+  unsigned grid = sfm_cdiv(total, warps_per_block);
+  if (list) {
+    const unsigned cap = (unsigned)ctx->n_sm * 24;  // deferred features are a few % of the batch: a resident grid walks the list
+    grid = grid < cap ? grid : cap;
+  }
+  SFM_LAUNCH(ctx, (klt_kernel<R, FIXED>), grid, warps_per_block * 32, smem, k, list, list_count);
   return 0;
 }
 
 }  // namespace
 
+// klt_lane.cu
+int sfm_klt_lane_launch(sfmgpu_ctx* ctx, const KltLaunch& k, int* defer_count, int* defer_list);
+
+// Batches of at least this many feature slots go to the lane-per-feature kernel (32 features per warp need many
+// features to fill 148 SMs); smaller ones (a single tracker step) keep one warp per feature.
+static const long long KLT_LANE_MIN = 6000;
+
 int sfm_klt_launch(sfmgpu_ctx* ctx, const KltLaunch& k) {
   if (k.radius < 1 || k.radius > 10)
     return sfm_fail(ctx, SFMGPU_E_ARG, "klt: win_radius %d outside the supported range [1,10]", k.radius);
   if (k.iters < 0) return sfm_fail(ctx, SFMGPU_E_ARG, "klt: negative iteration count");
-  if (k.radius == 5) return launch_r<5, true>(ctx, k);
-  if (k.radius < 5) return launch_r<5, false>(ctx, k);
-  if (k.radius == 10) return launch_r<10, true>(ctx, k);
-  return launch_r<10, false>(ctx, k);
+  const long long total = (long long)k.npairs * k.cap;
+  const int* list = nullptr;
+  const int* list_count = nullptr;
+  const int mode = ctx->klt_mode;  // 0 auto, 1 warp-per-feature only, 2 lane-per-feature (+ deferred) always
+  if (k.radius == 5 && total < (1ll << 31) && (mode == 2 || (mode == 0 && total >= KLT_LANE_MIN))) {
+    SFM_TRY(sfm_reserve(ctx, ctx->klt_defer, (size_t)(total + 1) * sizeof(int)));
+    int* dcount = (int*)ctx->klt_defer.p;
+    int* dlist = dcount + 1;
+    SFM_CUDA(ctx, cudaMemsetAsync(dcount, 0, sizeof(int), ctx->stream));
+    SFM_TRY(sfm_klt_lane_launch(ctx, k, dcount, dlist));
+    list = dlist;
+    list_count = dcount;
+  }
+  if (k.radius == 5) return launch_r<5, true>(ctx, k, list, list_count);
+  if (k.radius < 5) return launch_r<5, false>(ctx, k, list, list_count);
+  if (k.radius == 10) return launch_r<10, true>(ctx, k, list, list_count);
+  return launch_r<10, false>(ctx, k, list, list_count);
+}
+
+extern "C" int sfmgpu_klt_set_mode(sfmgpu_ctx* ctx, int mode) {
+  if (!ctx) return SFMGPU_E_ARG;
+  if (mode < 0 || mode > 2) return sfm_fail(ctx, SFMGPU_E_ARG, "klt_set_mode: mode %d not in {0,1,2}", mode);
+  ctx->klt_mode = mode;
+  return 0;
 }
 
 extern "C" int sfmgpu_klt_track(sfmgpu_ctx* ctx, sfmgpu_frames* f, int frame_a, int frame_b, const double* p0_xy, int n,

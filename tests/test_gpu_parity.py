@@ -123,7 +123,11 @@ def test_corners_larger_image(ctx, checker):
 
 # ---- KLT ---------------------------------------------------------------------------------------------------------
 def _klt_close(a, b):
-    return np.array_equal(np.isnan(a), np.isnan(b)) and np.nanmax(np.abs(a - b), initial=0.0) <= KLT_TOL
+    ok = np.array_equal(np.isnan(a), np.isnan(b)) and np.nanmax(np.abs(a - b), initial=0.0) <= KLT_TOL
+    if not ok and a.shape == b.shape:
+        bad = np.flatnonzero((np.isnan(a) != np.isnan(b)).any(1) | (np.nan_to_num(np.abs(a - b), nan=0.0) > KLT_TOL).any(1))
+        print(f"KLT mismatch at {len(bad)} of {len(a)} points, first: " + "; ".join(f"#{i} got {a[i]} want {b[i]}" for i in bad[:6]))
+    return ok
 
 
 @pytest.mark.parametrize("lv,r,it", [(3, 5, 10), (1, 3, 4), (4, 2, 7), (2, 7, 3), (3, 10, 2)])
@@ -165,6 +169,53 @@ def test_klt_iteration_count(ctx, port):
     _, _, nit = f.klt_track(0, 1, pts, count=True)
     _, _, want = port.klt_track(f0, f1, pts, count=True)
     assert np.array_equal(nit, want)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_klt_kernel_modes(ctx, checker, port, mode):
+    """Both KLT kernels (warp-per-feature, lane-per-feature + deferred border features) against the checker on
+    the same points, including border, out-of-image and non-finite ones; iteration counts must be identical."""
+    rng = np.random.default_rng(15)
+    f0, f1 = synth.frame(21, 0, 320, 240), synth.frame(21, 3, 320, 240)
+    pts = np.concatenate([checker.shi_tomasi(f0, 400), rng.uniform(-8, 330, (200, 2)) * [1, 0.75],
+                          [[0.0, 0.0], [318.0, 238.0], [319.5, 100.25], [127.99999999999999, 64.0], [1e12, 5.0],
+                           [np.nan, 3.0], [-1e300, 1e300], [160.0, 120.0], [7.0, 7.0], [28.0, 28.0], [27.999, 120.0]]])
+    f = _frames(ctx, [f0, f1], 3)
+    ctx.klt_set_mode(mode)
+    try:
+        p1, pb, nit = f.klt_track(0, 1, pts, count=True)
+        q1, _ = f.klt_track(0, 1, pts[:77])  # ragged tail of a warp
+    finally:
+        ctx.klt_set_mode(0)
+    w1, wb = checker.klt_track(f0, f1, pts)
+    _, _, wn = port.klt_track(f0, f1, pts, count=True)
+    assert _klt_close(p1, w1) and _klt_close(pb, wb) and _klt_close(q1, w1[:77])
+    assert np.array_equal(nit, wn)
+    dev = max(np.nanmax(np.abs(p1[:600] - w1[:600])), np.nanmax(np.abs(pb[:600] - wb[:600])))
+    print(f"klt mode {mode} max deviation {dev:.3e} px")
+    assert dev < 1e-6
+
+
+def test_klt_large_batch_takes_the_lane_kernel(ctx, checker):
+    """>= 6000 features in one launch: automatic selection of the lane-per-feature kernel (1280x720, 7000 corners)."""
+    f0, f1 = synth.frame(31, 0, 1280, 720), synth.frame(31, 2, 1280, 720)
+    f = _frames(ctx, [f0, f1], 3)
+    rng = np.random.default_rng(16)
+    pts = np.concatenate([f.corners(0, 7000), rng.uniform(0, 1280, (6500, 2)) * [1, 0.5625]])
+    n0 = ctx.launches()
+    p1, pb = f.klt_track(0, 1, pts)
+    assert ctx.launches() - n0 == 2  # lane kernel + deferred pass
+    sel = np.r_[0:1500, len(pts) - 1500:len(pts)]
+    w1, wb = checker.klt_track(f0, f1, pts[sel])
+    assert _klt_close(p1[sel], w1) and _klt_close(pb[sel], wb)
+    ctx.klt_set_mode(1)
+    try:
+        r1, rb = f.klt_track(0, 1, pts)
+    finally:
+        ctx.klt_set_mode(0)
+    dev = max(np.abs(p1 - r1).max(), np.abs(pb - rb).max())
+    print(f"lane vs warp kernel max difference {dev:.3e} px over {len(pts)} features")
+    assert dev < 1e-6
 
 
 # ---- stateful tracker ---------------------------------------------------------------------------------------------
