@@ -294,7 +294,7 @@ int launch_r(sfmgpu_ctx* ctx, const KltLaunch& k, const int* list, const int* li
 }  // namespace
 
 // klt_lane.cu
-int sfm_klt_lane_launch(sfmgpu_ctx* ctx, const KltLaunch& k, int* defer_count, int* defer_list);
+int sfm_klt_lane_launch(sfmgpu_ctx* ctx, const KltLaunch& k, int* defer_count, int* defer_list, int variant);
 
 // Batches of at least this many feature slots go to the lane-per-feature kernel (32 features per warp need many
 // features to fill 148 SMs); smaller ones (a single tracker step) keep one warp per feature.
@@ -307,13 +307,13 @@ int sfm_klt_launch(sfmgpu_ctx* ctx, const KltLaunch& k) {
   const long long total = (long long)k.npairs * k.cap;
   const int* list = nullptr;
   const int* list_count = nullptr;
-  const int mode = ctx->klt_mode;  // 0 auto, 1 warp-per-feature only, 2 lane-per-feature (+ deferred) always
-  if (k.radius == 5 && total < (1ll << 31) && (mode == 2 || (mode == 0 && total >= KLT_LANE_MIN))) {
+  const int mode = ctx->klt_mode;  // 0 auto, 1 warp-per-feature only, 2 lane-per-feature (+ deferred) always, 10+v tuning variant v
+  if (k.radius == 5 && total < (1ll << 31) && (mode >= 2 || (mode == 0 && total >= KLT_LANE_MIN))) {
     SFM_TRY(sfm_reserve(ctx, ctx->klt_defer, (size_t)(total + 1) * sizeof(int)));
     int* dcount = (int*)ctx->klt_defer.p;
     int* dlist = dcount + 1;
     SFM_CUDA(ctx, cudaMemsetAsync(dcount, 0, sizeof(int), ctx->stream));
-    SFM_TRY(sfm_klt_lane_launch(ctx, k, dcount, dlist));
+    SFM_TRY(sfm_klt_lane_launch(ctx, k, dcount, dlist, mode >= 10 ? mode - 10 : 0));
     list = dlist;
     list_count = dcount;
   }
@@ -325,7 +325,8 @@ int sfm_klt_launch(sfmgpu_ctx* ctx, const KltLaunch& k) {
 
 extern "C" int sfmgpu_klt_set_mode(sfmgpu_ctx* ctx, int mode) {
   if (!ctx) return SFMGPU_E_ARG;
-  if (mode < 0 || mode > 2) return sfm_fail(ctx, SFMGPU_E_ARG, "klt_set_mode: mode %d not in {0,1,2}", mode);
+  if (mode < 0 || (mode > 2 && (mode < 10 || mode > 19)))
+    return sfm_fail(ctx, SFMGPU_E_ARG, "klt_set_mode: mode %d not in {0,1,2} (10..19: tuning variants)", mode);
   ctx->klt_mode = mode;
   return 0;
 }

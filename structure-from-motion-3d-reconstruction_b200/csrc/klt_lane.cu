@@ -34,7 +34,7 @@ constexpr int LIMG = LN * 16;                // bytes of one staged image tile
 constexpr int LSTRIDE = 2 * LIMG + 16;       // bytes per lane: 116 words, == 20 (mod 32) -> LDS.128 conflict free
 constexpr int LWARPS = 1;                    // warps per block (no block-level cooperation)
 
-__device__ __forceinline__ double off_byte(uint32_t w, int k, uint32_t) {
+__device__ __forceinline__ double byte_f64(uint32_t w, int k) {
   // PRMT extracts the byte, the conversion pipe (I2F.F64, overlaps with FP64 issue) widens it.  Inline PTX keeps
   // the compiler from rewriting (double)c - (double)a as a second conversion of the integer difference.
   const uint32_t b = __byte_perm(w, 0, 0x4440 | k);
@@ -44,103 +44,132 @@ __device__ __forceinline__ double off_byte(uint32_t w, int k, uint32_t) {
 }
 
 // 14 consecutive tap bytes of one tile row as doubles
-__device__ __forceinline__ void row_bytes(const uint4 q, uint32_t c4096, double (&v)[LN]) {
-  v[0] = off_byte(q.x, 0, c4096);
-  v[1] = off_byte(q.x, 1, c4096);
-  v[2] = off_byte(q.x, 2, c4096);
-  v[3] = off_byte(q.x, 3, c4096);
-  v[4] = off_byte(q.y, 0, c4096);
-  v[5] = off_byte(q.y, 1, c4096);
-  v[6] = off_byte(q.y, 2, c4096);
-  v[7] = off_byte(q.y, 3, c4096);
-  v[8] = off_byte(q.z, 0, c4096);
-  v[9] = off_byte(q.z, 1, c4096);
-  v[10] = off_byte(q.z, 2, c4096);
-  v[11] = off_byte(q.z, 3, c4096);
-  v[12] = off_byte(q.w, 0, c4096);
-  v[13] = off_byte(q.w, 1, c4096);
+__device__ __forceinline__ void row_bytes(const uint4 q, double (&v)[LN]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < LN; i++) v[i] = byte_f64(w[i >> 2], i & 3);
+}
+
+// Horizontal lerps a + (b - a) * fx of one tile row (grid columns I0..I1-1 use taps i, i+1)
+template <int I0, int I1>
+__device__ __forceinline__ void hlerp_row(const unsigned char* rowp, double fx, double (&h)[LNC]) {
+  double px[LN];
+  row_bytes(*reinterpret_cast<const uint4*>(rowp), px);
+#pragma unroll
+  for (int i = I0; i < I1; i++) h[i] = __fma_rn(fx, px[i + 1] - px[i], px[i]);
+}
+
+// One tap row of the main window walk, straight-line.  v = tap row (3..13, warp-uniform, runtime).  Computes the
+// horizontal lerps of I1 row v, completes grid row v-1 of I1 into `snew`, and accumulates pixel row g = v-2 from
+// sold = S1[g-1], smid = S1[g], snew = S1[g+1] and S0[g] (I0 tap rows g = h0p and g+1 = tap row v-1).
+// ACC: accumulator sets (2 = even / odd columns: shorter dependent DFMA chains).
+template <int ACC>
+__device__ __forceinline__ void walk_row(const unsigned char* tile, int v, double fx, double fy, double (&h1p)[LNC], double (&h0p)[LNC],
+                                         const double (&sold)[LNC], const double (&smid)[LNC], double (&snew)[LNC],
+                                         double (&acc)[ACC][5]) {
+  double px[LN];
+  row_bytes(*reinterpret_cast<const uint4*>(tile + v * 16), px);
+#pragma unroll
+  for (int i = 0; i < LNC; i++) {
+    const double h = __fma_rn(fx, px[i + 1] - px[i], px[i]);
+    snew[i] = __fma_rn(fy, h - h1p[i], h1p[i]);  // grid row v-1 of I1
+    h1p[i] = h;
+  }
+  row_bytes(*reinterpret_cast<const uint4*>(tile + LIMG + (v - 1) * 16), px);
+#pragma unroll
+  for (int i = 1; i <= LNC - 2; i++) {
+    const double h = __fma_rn(fx, px[i + 1] - px[i], px[i]);
+    const double s0 = __fma_rn(fy, h - h0p[i], h0p[i]);
+    h0p[i] = h;
+    const double gx2 = smid[i + 1] - smid[i - 1];  // 2*Ix (:439)
+    const double gy2 = snew[i] - sold[i];          // 2*Iy (:440)
+    const double e = s0 - smid[i];                 // I0 - I1 at the same location (:441-442)
+    double(&a)[5] = acc[i % ACC];
+    a[0] = __fma_rn(gx2, gx2, a[0]);
+    a[1] = __fma_rn(gx2, gy2, a[1]);
+    a[2] = __fma_rn(gy2, gy2, a[2]);
+    a[3] = __fma_rn(gx2, e, a[3]);
+    a[4] = __fma_rn(gy2, e, a[4]);
+  }
 }
 
 // The five sums of lk_step (:431-448) for one interior window.  tile: this lane's staged taps (image B = I1 first,
 // then image A = I0).  Returns 4*A and 2*b like klt.cu (the 0.5 factors are folded into the solve).
-__device__ __forceinline__ void window_sums(const unsigned char* tile, double fx, double fy, uint32_t c4096, double& a00,
-                                            double& a01, double& a11, double& b0, double& b1) {
-  const uint4* t1 = reinterpret_cast<const uint4*>(tile);
-  const uint4* t0 = reinterpret_cast<const uint4*>(tile + LIMG);
-  double h1p[LNC], sa[LNC], sb[LNC], sc[LNC];
-  double h0p[LNC];
-  a00 = a01 = a11 = b0 = b1 = 0.0;
+//
+// Tap rows 0..2 only feed lerps (no pixel row is complete yet) and are peeled.  Rows 3..13 are a ROLLED loop over
+// groups of three rows (the three S1 row buffers rotate by argument order), so the hot code is ~16 KB and stays in
+// the 32 KB instruction cache.  Fully unrolled, the 14 rows are 53 KB and the kernel stalls on instruction fetch
+// (measured: 'no_instruction' was the top stall reason).  The 15th row of the last group does not exist and is skipped.
+template <int ACC>
+__device__ __forceinline__ void window_sums(const unsigned char* tile, double fx, double fy, double& a00, double& a01, double& a11,
+                                            double& b0, double& b1) {
+  double h1p[LNC], h0p[LNC], s0[LNC], s1[LNC], s2[LNC], t[LNC];
+  double acc[ACC][5];
 #pragma unroll
-  for (int v = 0; v < LN; v++) {
-    double px[LN];
-    double h1n[LNC];
-    row_bytes(t1[v], c4096, px);
+  for (int j = 0; j < ACC; j++)
 #pragma unroll
-    for (int i = 0; i < LNC; i++) h1n[i] = __fma_rn(fx, px[i + 1] - px[i], px[i]);
-    if (v >= 1) {
+    for (int q = 0; q < 5; q++) acc[j][q] = 0.0;
+  hlerp_row<0, LNC>(tile, fx, h1p);  // I1 tap row 0
+  hlerp_row<0, LNC>(tile + 16, fx, t);  // I1 tap row 1 -> grid row 0
 #pragma unroll
-      for (int i = 0; i < LNC; i++) {
-        sa[i] = sb[i];
-        sb[i] = sc[i];
-        sc[i] = __fma_rn(fy, h1n[i] - h1p[i], h1p[i]);  // grid row v-1 of I1
-      }
-    }
+  for (int i = 0; i < LNC; i++) {
+    s0[i] = __fma_rn(fy, t[i] - h1p[i], h1p[i]);
+    h1p[i] = t[i];
+  }
+  hlerp_row<0, LNC>(tile + 32, fx, t);  // I1 tap row 2 -> grid row 1
 #pragma unroll
-    for (int i = 0; i < LNC; i++) h1p[i] = h1n[i];
-    if (v >= 2) {
-      // I0 tap row v-1 (grid rows 1..11 need tap rows 1..12)
-      double h0n[LNC];
-      row_bytes(t0[v - 1], c4096, px);
+  for (int i = 0; i < LNC; i++) {
+    s1[i] = __fma_rn(fy, t[i] - h1p[i], h1p[i]);
+    h1p[i] = t[i];
+  }
+  hlerp_row<1, LNC - 1>(tile + LIMG + 16, fx, h0p);  // I0 tap row 1
+  // step v writes grid row v-1 into buffer (v-1) % 3 and reads grid rows v-3, v-2 from the other two
+#pragma unroll 1
+  for (int v = 3; v < LN; v += 3) {
+    walk_row<ACC>(tile, v, fx, fy, h1p, h0p, s0, s1, s2, acc);      // writes s2
+    walk_row<ACC>(tile, v + 1, fx, fy, h1p, h0p, s1, s2, s0, acc);  // writes s0
+    if (v + 2 < LN) walk_row<ACC>(tile, v + 2, fx, fy, h1p, h0p, s2, s0, s1, acc);  // writes s1
+  }
+  a00 = acc[0][0]; a01 = acc[0][1]; a11 = acc[0][2]; b0 = acc[0][3]; b1 = acc[0][4];
 #pragma unroll
-      for (int i = 1; i <= LNC - 2; i++) h0n[i] = __fma_rn(fx, px[i + 1] - px[i], px[i]);
-      if (v >= 3) {
-        // pixel row g = v-2: sa = S1[g-1], sb = S1[g], sc = S1[g+1]; S0[g] from tap rows g (h0p) and g+1 (h0n)
-#pragma unroll
-        for (int i = 1; i <= LNC - 2; i++) {
-          const double s0 = __fma_rn(fy, h0n[i] - h0p[i], h0p[i]);
-          const double gx2 = sb[i + 1] - sb[i - 1];  // 2*Ix (:439)
-          const double gy2 = sc[i] - sa[i];          // 2*Iy (:440)
-          const double e = s0 - sb[i];               // I0 - I1 at the same location (:441-442)
-          a00 = __fma_rn(gx2, gx2, a00);
-          a01 = __fma_rn(gx2, gy2, a01);
-          a11 = __fma_rn(gy2, gy2, a11);
-          b0 = __fma_rn(gx2, e, b0);
-          b1 = __fma_rn(gy2, e, b1);
-        }
-      }
-#pragma unroll
-      for (int i = 1; i <= LNC - 2; i++) h0p[i] = h0n[i];
-    }
+  for (int j = 1; j < ACC; j++) {
+    a00 += acc[j][0]; a01 += acc[j][1]; a11 += acc[j][2]; b0 += acc[j][3]; b1 += acc[j][4];
   }
 }
 
-// Cooperative staging of ONE feature's tiles: lanes 0..27 each fetch one 14-byte row segment (image = t / 14, row =
-// t % 14) starting at byte column x0 with two aligned 16-byte loads, realign, and store one 16-byte smem row.
-__device__ __forceinline__ void stage_feature(unsigned char* tile_s, const uint8_t* __restrict__ imgA, const uint8_t* __restrict__ imgB,
-                                              int pitch, int x0, int y0, int lane) {
-  if (lane < 2 * LN) {
-    const int img = lane >= LN ? 1 : 0, row = lane - img * LN;
-    const uint8_t* rowp = (img ? imgA : imgB) + (size_t)(y0 + row) * pitch;  // tile order: I1 (= image B) first
-    const int xa = x0 & ~15, o = x0 & 15;
-    uint32_t W[8];
-    const uint4 lo = __ldg(reinterpret_cast<const uint4*>(rowp + xa));
-    W[0] = lo.x; W[1] = lo.y; W[2] = lo.z; W[3] = lo.w;
-    uint4 hi = make_uint4(0, 0, 0, 0);
-    if (o > 2) hi = __ldg(reinterpret_cast<const uint4*>(rowp + xa + 16));  // needed bytes reach the next chunk
-    W[4] = hi.x; W[5] = hi.y; W[6] = hi.z; W[7] = hi.w;
-    const int q = o >> 2, sh = (o & 3) * 8;
-    if (q & 2) { W[0] = W[2]; W[1] = W[3]; W[2] = W[4]; W[3] = W[5]; W[4] = W[6]; W[5] = W[7]; }
-    if (q & 1) { W[0] = W[1]; W[1] = W[2]; W[2] = W[3]; W[3] = W[4]; W[4] = W[5]; }
-    uint4 out;
-    out.x = __funnelshift_r(W[0], W[1], sh);
-    out.y = __funnelshift_r(W[1], W[2], sh);
-    out.z = __funnelshift_r(W[2], W[3], sh);
-    out.w = __funnelshift_r(W[3], W[4], sh);
-    *reinterpret_cast<uint4*>(tile_s + img * LIMG + row * 16) = out;
-  }
+// Cooperative staging of one feature's tiles, split in two halves so that the loads of several features are in
+// flight together: lanes 0..27 each fetch one 14-byte row segment (image = t / 14, row = t % 14) starting at byte
+// column x0 with two aligned 16-byte loads (stage_load), then realign and store one 16-byte smem row (stage_store).
+struct StageRegs {
+  uint4 lo, hi;
+};
+
+__device__ __forceinline__ void stage_load(StageRegs& r, const uint8_t* __restrict__ imgA, const uint8_t* __restrict__ imgB, int pitch,
+                                           int x0, int y0, int lane) {
+  const int img = lane >= LN ? 1 : 0, row = lane - img * LN;
+  const uint8_t* rowp = (img ? imgA : imgB) + (size_t)(y0 + row) * pitch;  // tile order: I1 (= image B) first
+  const int xa = x0 & ~15, o = x0 & 15;
+  r.lo = __ldg(reinterpret_cast<const uint4*>(rowp + xa));
+  r.hi = make_uint4(0, 0, 0, 0);
+  if (o > 2) r.hi = __ldg(reinterpret_cast<const uint4*>(rowp + xa + 16));  // needed bytes reach the next chunk
 }
 
-__global__ void __launch_bounds__(32 * LWARPS) klt_lane_kernel(KltLaunch k, int* __restrict__ defer_count, int* __restrict__ defer_list) {
+__device__ __forceinline__ void stage_store(const StageRegs& r, unsigned char* tile_s, int x0, int lane) {
+  const int img = lane >= LN ? 1 : 0, row = lane - img * LN;
+  const int o = x0 & 15, q = o >> 2, sh = (o & 3) * 8;
+  uint32_t W[8] = {r.lo.x, r.lo.y, r.lo.z, r.lo.w, r.hi.x, r.hi.y, r.hi.z, r.hi.w};
+  if (q & 2) { W[0] = W[2]; W[1] = W[3]; W[2] = W[4]; W[3] = W[5]; W[4] = W[6]; W[5] = W[7]; }
+  if (q & 1) { W[0] = W[1]; W[1] = W[2]; W[2] = W[3]; W[3] = W[4]; W[4] = W[5]; }
+  uint4 out;
+  out.x = __funnelshift_r(W[0], W[1], sh);
+  out.y = __funnelshift_r(W[1], W[2], sh);
+  out.z = __funnelshift_r(W[2], W[3], sh);
+  out.w = __funnelshift_r(W[3], W[4], sh);
+  *reinterpret_cast<uint4*>(tile_s + img * LIMG + row * 16) = out;
+}
+
+template <int ACC, int MINB, int LSTAGE>
+__global__ void __launch_bounds__(32 * LWARPS, MINB) klt_lane_kernel(KltLaunch k, int* __restrict__ defer_count, int* __restrict__ defer_list) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const unsigned FULL = 0xffffffffu;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -151,8 +180,6 @@ __global__ void __launch_bounds__(32 * LWARPS) klt_lane_kernel(KltLaunch k, int*
   const int pair = g < total ? (int)(g / k.cap) : 0;
   const int slot = (int)(g - (long long)pair * k.cap);
   const bool valid = g < total && (!k.counts || slot < k.counts[pair]);
-  uint32_t c4096 = 0x40B00000u;
-  asm volatile("" : "+r"(c4096));  // keep it in a register (PRMT takes register operands)
 
   double2 p0 = make_double2(0.0, 0.0);
   if (valid) p0 = k.p0[g];
@@ -160,10 +187,8 @@ __global__ void __launch_bounds__(32 * LWARPS) klt_lane_kernel(KltLaunch k, int*
   int n_it = 0;
   bool alive = valid;
   const int ndir = k.pb ? 2 : 1;
-  const int frA = k.fa0 + pair * k.fa_step, frB = k.fb0 + pair * k.fb_step;
 
   for (int dir = 0; dir < ndir; dir++) {
-    const int fa = dir ? frB : frA, fb = dir ? frA : frB;  // track from image fa to image fb
     for (int l = k.pv.levels - 1; l >= 0; --l) {
       const int w = k.pv.w[l], h = k.pv.h[l], pitch = k.pv.pitch[l];
       const uint8_t* lbase = k.pv.base[l];
@@ -195,12 +220,24 @@ __global__ void __launch_bounds__(32 * LWARPS) klt_lane_kernel(KltLaunch k, int*
         if (need) {
           __syncwarp();
           while (need) {
-            const int s = __ffs(need) - 1;
-            need &= need - 1;
-            const int sFX = __shfl_sync(FULL, FX, s), sFY = __shfl_sync(FULL, FY, s);
-            const int sfa = __shfl_sync(FULL, fa, s), sfb = __shfl_sync(FULL, fb, s);
-            stage_feature(wtile + s * LSTRIDE, lbase + (size_t)sfa * fstride, lbase + (size_t)sfb * fstride, pitch, sFX - LR - 1,
-                          sFY - LR - 1, lane);
+            // up to LSTAGE features per round: all their loads are issued before the first realign / store
+            int ss[LSTAGE], sx0[LSTAGE];
+            StageRegs sr[LSTAGE];
+#pragma unroll
+            for (int j = 0; j < LSTAGE; j++) {
+              ss[j] = need ? __ffs(need) - 1 : -1;
+              need &= need - 1;
+              const int src = ss[j] < 0 ? 0 : ss[j];
+              const int sFX = __shfl_sync(FULL, FX, src), sFY = __shfl_sync(FULL, FY, src), spair = __shfl_sync(FULL, pair, src);
+              const int sA = k.fa0 + spair * k.fa_step, sB = k.fb0 + spair * k.fb_step;
+              sx0[j] = sFX - LR - 1;
+              if (ss[j] >= 0 && lane < 2 * LN)
+                stage_load(sr[j], lbase + (size_t)(dir ? sB : sA) * fstride, lbase + (size_t)(dir ? sA : sB) * fstride, pitch, sx0[j],
+                           sFY - LR - 1, lane);
+            }
+#pragma unroll
+            for (int j = 0; j < LSTAGE; j++)
+              if (ss[j] >= 0 && lane < 2 * LN) stage_store(sr[j], wtile + ss[j] * LSTRIDE, sx0[j], lane);
           }
           __syncwarp();
         }
@@ -208,7 +245,7 @@ __global__ void __launch_bounds__(32 * LWARPS) klt_lane_kernel(KltLaunch k, int*
           tFX = FX;
           tFY = FY;
           double a00, a01, a11, b0, b1;
-          window_sums(tile, x - fxx, y - fyy, c4096, a00, a01, a11, b0, b1);
+          window_sums<ACC>(tile, x - fxx, y - fyy, a00, a01, a11, b0, b1);
           double sx = 0.0, sy = 0.0;
           const double det = a00 * a11 - a01 * a01;
           if (!(fabs(det) < 16.0 * 1e-9)) {  // |det| < 1e-9 of :452 on the 16x scaled determinant
@@ -252,18 +289,29 @@ __global__ void __launch_bounds__(32 * LWARPS) klt_lane_kernel(KltLaunch k, int*
 
 }  // namespace
 
-// Runs the lane kernel over all slots; features it cannot handle are appended to defer_list (device), count in
-// *defer_count (device, must be zeroed by the caller on the same stream).
-int sfm_klt_lane_launch(sfmgpu_ctx* ctx, const KltLaunch& k, int* defer_count, int* defer_list) {
+template <int ACC, int MINB, int LSTAGE>
+static int lane_launch(sfmgpu_ctx* ctx, const KltLaunch& k, int* defer_count, int* defer_list) {
   const size_t smem = (size_t)LWARPS * 32 * LSTRIDE;
   static bool configured = false;
   if (!configured) {
-    SFM_CUDA(ctx, cudaFuncSetAttribute(klt_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SFM_CUDA(ctx, cudaFuncSetAttribute(klt_lane_kernel<ACC, MINB, LSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   const long long total = (long long)k.npairs * k.cap;
   if (total == 0) return 0;
   const unsigned grid = sfm_cdiv(total, 32 * LWARPS);
-  SFM_LAUNCH(ctx, klt_lane_kernel, grid, 32 * LWARPS, smem, k, defer_count, defer_list);
+  SFM_LAUNCH(ctx, (klt_lane_kernel<ACC, MINB, LSTAGE>), grid, 32 * LWARPS, smem, k, defer_count, defer_list);
   return 0;
+}
+
+// Runs the lane kernel over all slots; features it cannot handle are appended to defer_list (device), count in
+// *defer_count (device, must be zeroed by the caller on the same stream).  variant: tuning builds (A/B runs).
+int sfm_klt_lane_launch(sfmgpu_ctx* ctx, const KltLaunch& k, int* defer_count, int* defer_list, int variant) {
+  // Measured on B200, C2 shape (scripts/klt_ab.py, KLT stage incl. the deferred pass, 238k tracks): <1,12,4> 4.43 ms
+  // (168 registers, spills), <1,8,4> 3.57 ms, <2,8,4> 3.66 ms, <2,8,8> 3.97 ms: the schedule wants registers, not warps.
+  switch (variant) {
+    case 1: return lane_launch<1, 12, 4>(ctx, k, defer_count, defer_list);
+    case 2: return lane_launch<2, 8, 4>(ctx, k, defer_count, defer_list);
+    default: return lane_launch<1, 8, 4>(ctx, k, defer_count, defer_list);
+  }
 }
