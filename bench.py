@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=NFRAMES, help="frames per GPU (default: the C2 sequence length)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk", type=int, default=0, help="frames per chunk of the streaming e2e call (0: a quarter of the sequence)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -307,12 +308,13 @@ def main():
             d2h = 0
 
     def step_e2e():
+        if world == 1:
+            # the library's streaming call: H2D of chunk c+1 || pyramid + corners + KLT of chunk c || D2H of chunk c-1
+            pairs.run_host(frames, host, cfg, li, lj, nk, nc, chunk=args.chunk)
+            return
         frames.upload_ptr(0, nfr, host.ctypes.data)
         frames.build_pyramid(0, nfr)
         pairs.run(frames, 0, npairs, cfg)
-        if world == 1:
-            pairs.download_all(li, lj, nk, nc)
-            return
         ctx.sync()  # results are written on the library's stream; NCCL runs on torch's
         dist.gather(v_nk, g_nk, dst=0)
         dist.gather(v_nc, g_nc, dst=0)
@@ -388,10 +390,10 @@ def main():
                     "ms_per_step": e2e_ms, "steps": e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "klt_kernel<5,true>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "klt_lane_kernel (+ klt_kernel<5,true> on deferred border features)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                          "note": "KLT is bound by the FP64 CUDA-core pipe, not HBM (SURVEY.md §8d): see roofline_fp64"},
-            "roofline_fp64": {"kernel": "klt_kernel<5,true>", "achieved_tflops": F_KLT_IT * (it_all / world) / (klt_ms * 1e-3) / 1e12,
+            "roofline_fp64": {"kernel": "klt_lane_kernel (+ klt_kernel<5,true> on deferred border features)", "achieved_tflops": F_KLT_IT * (it_all / world) / (klt_ms * 1e-3) / 1e12,
                               "peak_tflops": fp64_peak, "peak_source": "in-run DFMA micro-benchmark (sfmgpu_fp64_peak)",
                               "frac": F_KLT_IT * (it_all / world) / (klt_ms * 1e-3) / 1e12 / fp64_peak,
                               "flop_per_lk_iteration": F_KLT_IT, "lk_iterations": it_all // world},

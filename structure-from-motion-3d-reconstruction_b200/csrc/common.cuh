@@ -48,6 +48,8 @@ struct sfmgpu_ctx {
   int device = 0;
   int n_sm = SFM_NSM_FALLBACK;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr, back_stream = nullptr;  // H2D / D2H legs of the streaming front end
+  std::vector<cudaEvent_t> pipe_evs;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
   long long launches = 0;

@@ -92,6 +92,9 @@ void sfmgpu_destroy(sfmgpu_ctx* ctx) {
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (cudaEvent_t e : ctx->pipe_evs) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->back_stream) cudaStreamDestroy(ctx->back_stream);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);

@@ -222,17 +222,10 @@ void sfmgpu_pairs_destroy(sfmgpu_ctx* ctx, sfmgpu_pairs* p) {
   delete p;
 }
 
-int sfmgpu_pair_frontend(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int npairs, const sfmgpu_lkcfg* cfg,
-                         sfmgpu_pairs* out) {
-  if (!ctx || !f || !cfg || !out) return SFMGPU_E_ARG;
-  if (npairs < 0 || npairs > out->max_pairs || first_frame < 0 || first_frame + npairs + (npairs > 0 ? 1 : 0) > f->n)
-    return sfm_fail(ctx, SFMGPU_E_ARG, "pair_frontend: pair range [%d,%d) does not fit (frames %d, max_pairs %d)", first_frame,
-                    first_frame + npairs, f->n, out->max_pairs);
-  const int cap_out = cfg->max_tracks < 1 ? 1 : cfg->max_tracks;
-  if (cap_out != out->cap) return sfm_fail(ctx, SFMGPU_E_ARG, "pair_frontend: cfg->max_tracks != pairs capacity");
-  if (cfg->pyr_levels != f->levels) return sfm_fail(ctx, SFMGPU_E_ARG, "pair_frontend: cfg->pyr_levels != frames levels");
-  out->last_npairs = npairs;
-  SFM_CUDA(ctx, cudaMemsetAsync(out->totals, 0, 64, ctx->stream));
+// Pairs (first_frame + k, first_frame + k + 1), k < npairs, written to slots [pair_off, pair_off + npairs) of `out`
+// on the context stream; totals are accumulated (the caller zeroes them).
+static int pair_range(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int pair_off, int npairs, const sfmgpu_lkcfg* cfg,
+                      sfmgpu_pairs* out) {
   if (npairs == 0) return 0;
   // corners, in chunks of frames that bound the work area
   const int cand_cap = default_cand_cap(f->w, f->h);
@@ -240,15 +233,16 @@ int sfmgpu_pair_frontend(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int
   int chunk = npairs < 1024 ? npairs : 1024;  // frames per corner launch: >= 4 blocks per SM keeps the select kernel busy
   const size_t wb = sfm_corner_work_bytes_md(f->w, f->h, chunk, cand_cap, md);
   SFM_TRY(sfm_reserve(ctx, out->work, wb));
+  const size_t so = (size_t)pair_off * out->cap;
   for (int c0 = 0; c0 < npairs; c0 += chunk) {
     const int cnt = npairs - c0 < chunk ? npairs - c0 : chunk;
     SFM_TRY(sfm_corners_batch(ctx, f, first_frame + c0, cnt, cfg->max_tracks, cfg->quality, cfg->min_distance, cand_cap,
-                              out->work.p, out->work.cap, out->xy0 + (size_t)c0 * out->cap, out->ncorn + c0));
+                              out->work.p, out->work.cap, out->xy0 + so + (size_t)c0 * out->cap, out->ncorn + pair_off + c0));
   }
   KltLaunch k;
   k.pv = f->view();
-  k.p0 = out->xy0;
-  k.counts = out->ncorn;
+  k.p0 = out->xy0 + so;
+  k.counts = out->ncorn + pair_off;
   k.npairs = npairs;
   k.cap = out->cap;
   k.fa0 = first_frame;
@@ -258,18 +252,95 @@ int sfmgpu_pair_frontend(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int
   k.radius = cfg->win_radius;
   k.iters = cfg->iters;
   k.fb_thresh = cfg->fb_thresh;
-  k.p1 = out->p1;
-  k.pb = out->pb;
-  k.nit = out->nit;
-  k.keep = out->keep;
+  k.p1 = out->p1 + so;
+  k.pb = out->pb + so;
+  k.nit = out->nit + so;
+  k.keep = out->keep + so;
   {
     StageTimer st(ctx, 2);
     SFM_TRY(sfm_klt_launch(ctx, k));
   }
   StageTimer st(ctx, 3);
-  SFM_LAUNCH(ctx, compact_kernel, npairs, 1024, 0, out->xy0, out->p1, out->keep, (const int*)nullptr, out->ncorn, out->cap, out->li,
-             out->lj, (int*)nullptr, out->nkept);
-  SFM_LAUNCH(ctx, totals_kernel, 256, 256, 0, out->ncorn, out->nkept, out->nit, npairs, out->cap, out->totals);
+  SFM_LAUNCH(ctx, compact_kernel, npairs, 1024, 0, out->xy0 + so, out->p1 + so, out->keep + so, (const int*)nullptr,
+             out->ncorn + pair_off, out->cap, out->li + so, out->lj + so, (int*)nullptr, out->nkept + pair_off);
+  SFM_LAUNCH(ctx, totals_kernel, 256, 256, 0, out->ncorn + pair_off, out->nkept + pair_off, out->nit + so, npairs, out->cap,
+             out->totals);
+  return 0;
+}
+
+static int pair_args_ok(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int npairs, const sfmgpu_lkcfg* cfg, sfmgpu_pairs* out) {
+  if (npairs < 0 || npairs > out->max_pairs || first_frame < 0 || first_frame + npairs + (npairs > 0 ? 1 : 0) > f->n)
+    return sfm_fail(ctx, SFMGPU_E_ARG, "pair_frontend: pair range [%d,%d) does not fit (frames %d, max_pairs %d)", first_frame,
+                    first_frame + npairs, f->n, out->max_pairs);
+  const int cap_out = cfg->max_tracks < 1 ? 1 : cfg->max_tracks;
+  if (cap_out != out->cap) return sfm_fail(ctx, SFMGPU_E_ARG, "pair_frontend: cfg->max_tracks != pairs capacity");
+  if (cfg->pyr_levels != f->levels) return sfm_fail(ctx, SFMGPU_E_ARG, "pair_frontend: cfg->pyr_levels != frames levels");
+  return 0;
+}
+
+int sfmgpu_pair_frontend(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int npairs, const sfmgpu_lkcfg* cfg,
+                         sfmgpu_pairs* out) {
+  if (!ctx || !f || !cfg || !out) return SFMGPU_E_ARG;
+  SFM_TRY(pair_args_ok(ctx, f, first_frame, npairs, cfg, out));
+  out->last_npairs = npairs;
+  SFM_CUDA(ctx, cudaMemsetAsync(out->totals, 0, 64, ctx->stream));
+  return pair_range(ctx, f, first_frame, 0, npairs, cfg, out);
+}
+
+// Streaming variant for frames that live in HOST memory: frames [0, nframes) of `f` are filled from host_pix in
+// chunks on a copy stream while the compute stream builds pyramids and runs the pair front end on the chunks that
+// have arrived; each chunk's results go back on a third stream.  One synchronisation at the end.
+int sfmgpu_pair_frontend_host(sfmgpu_ctx* ctx, sfmgpu_frames* f, const uint8_t* host_pix, int nframes, const sfmgpu_lkcfg* cfg,
+                              sfmgpu_pairs* out, int chunk_frames, double* li_xy, double* lj_xy, int32_t* n_kept,
+                              int32_t* n_corners) {
+  if (!ctx || !f || !cfg || !out || !host_pix) return SFMGPU_E_ARG;
+  if (nframes < 0 || nframes > f->n) return sfm_fail(ctx, SFMGPU_E_ARG, "pair_frontend_host: %d frames do not fit (%d)", nframes, f->n);
+  const int npairs = nframes > 0 ? nframes - 1 : 0;
+  SFM_TRY(pair_args_ok(ctx, f, 0, npairs, cfg, out));
+  out->last_npairs = npairs;
+  SFM_CUDA(ctx, cudaMemsetAsync(out->totals, 0, 64, ctx->stream));
+  if (nframes == 0) return 0;
+  if (!ctx->copy_stream) {
+    SFM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    SFM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->back_stream, cudaStreamNonBlocking));
+  }
+  int chunk = chunk_frames > 0 ? chunk_frames : (nframes + 3) / 4;
+  if (chunk < 2) chunk = 2;
+  const int nchunks = (nframes + chunk - 1) / chunk;
+  while ((int)ctx->pipe_evs.size() < 2 * nchunks + 1) {
+    cudaEvent_t e;
+    SFM_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->pipe_evs.push_back(e);
+  }
+  // the copy stream must not overwrite frames an earlier call on the compute stream still reads
+  SFM_CUDA(ctx, cudaEventRecord(ctx->pipe_evs[2 * nchunks], ctx->stream));
+  SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->pipe_evs[2 * nchunks], 0));
+  SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->back_stream, ctx->pipe_evs[2 * nchunks], 0));
+  const size_t cap = (size_t)out->cap;
+  for (int c = 0; c < nchunks; c++) {
+    const int a = c * chunk, b = a + chunk < nframes ? a + chunk : nframes;
+    SFM_CUDA(ctx, cudaMemcpy2DAsync(f->lvl[0] + (size_t)a * f->fstride[0], f->pitch[0], host_pix + (size_t)a * f->w * f->h, f->w,
+                                    f->w, (size_t)f->h * (b - a), cudaMemcpyHostToDevice, ctx->copy_stream));
+    SFM_CUDA(ctx, cudaEventRecord(ctx->pipe_evs[2 * c], ctx->copy_stream));
+    SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_evs[2 * c], 0));
+    SFM_TRY(sfmgpu_pyramid_build(ctx, f, a, b - a));
+    // pairs whose second frame arrived with this chunk
+    const int p0 = a > 0 ? a - 1 : 0, p1 = b - 1;
+    if (p1 > p0) {
+      SFM_TRY(pair_range(ctx, f, p0, p0, p1 - p0, cfg, out));
+      SFM_CUDA(ctx, cudaEventRecord(ctx->pipe_evs[2 * c + 1], ctx->stream));
+      SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->back_stream, ctx->pipe_evs[2 * c + 1], 0));
+      const size_t np_ = (size_t)(p1 - p0);
+      if (li_xy)
+        SFM_CUDA(ctx, cudaMemcpyAsync(li_xy + 2 * p0 * cap, out->li + p0 * cap, np_ * cap * 16, cudaMemcpyDeviceToHost, ctx->back_stream));
+      if (lj_xy)
+        SFM_CUDA(ctx, cudaMemcpyAsync(lj_xy + 2 * p0 * cap, out->lj + p0 * cap, np_ * cap * 16, cudaMemcpyDeviceToHost, ctx->back_stream));
+      if (n_kept) SFM_CUDA(ctx, cudaMemcpyAsync(n_kept + p0, out->nkept + p0, np_ * 4, cudaMemcpyDeviceToHost, ctx->back_stream));
+      if (n_corners) SFM_CUDA(ctx, cudaMemcpyAsync(n_corners + p0, out->ncorn + p0, np_ * 4, cudaMemcpyDeviceToHost, ctx->back_stream));
+    }
+  }
+  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->back_stream));
+  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 

@@ -27,7 +27,7 @@ SYMBOLS = [
     "sfmgpu_host_free", "sfmgpu_frames_create", "sfmgpu_frames_destroy", "sfmgpu_frames_upload",
     "sfmgpu_frames_upload_device", "sfmgpu_frames_synth", "sfmgpu_pyramid_build", "sfmgpu_frames_level_size",
     "sfmgpu_frames_download", "sfmgpu_corner_candidates", "sfmgpu_corners", "sfmgpu_sort_perm_desc",
-    "sfmgpu_klt_track", "sfmgpu_klt_set_mode", "sfmgpu_pairs_create", "sfmgpu_pairs_destroy", "sfmgpu_pair_frontend", "sfmgpu_pairs_totals",
+    "sfmgpu_klt_track", "sfmgpu_klt_set_mode", "sfmgpu_pairs_create", "sfmgpu_pairs_destroy", "sfmgpu_pair_frontend", "sfmgpu_pair_frontend_host", "sfmgpu_pairs_totals",
     "sfmgpu_pairs_download", "sfmgpu_pairs_download_all", "sfmgpu_pairs_device_ptrs", "sfmgpu_tracker_create", "sfmgpu_tracker_destroy", "sfmgpu_tracker_reset",
     "sfmgpu_tracker_step", "sfmgpu_tracker_step_frames", "sfmgpu_tracker_tracks", "sfmgpu_tracker_totals",
     "sfmgpu_ransac_score", "sfmgpu_ransac_upload", "sfmgpu_ransac_score_resident", "sfmgpu_ransac_download",
@@ -98,6 +98,7 @@ def load_library():
         "sfmgpu_pairs_create": (_i, [_vp, _i, _i, C.POINTER(_vp)]),
         "sfmgpu_pairs_destroy": (None, [_vp, _vp]),
         "sfmgpu_pair_frontend": (_i, [_vp, _vp, _i, _i, C.POINTER(LKCfg), _vp]),
+        "sfmgpu_pair_frontend_host": (_i, [_vp, _vp, _vp, _i, C.POINTER(LKCfg), _vp, _i, _vp, _vp, _vp, _vp]),
         "sfmgpu_pairs_totals": (_i, [_vp, _vp, C.POINTER(_ll), C.POINTER(_ll), C.POINTER(_ll)]),
         "sfmgpu_pairs_download": (_i, [_vp, _vp, _i, _f64p, _f64p, _i, C.POINTER(_i), C.POINTER(_i)]),
         "sfmgpu_pairs_download_all": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
@@ -335,6 +336,13 @@ class Pairs:
 
     def run(self, frames, first_frame, npairs, cfg):
         self.ctx._ck(self.ctx.lib.sfmgpu_pair_frontend(self.ctx.h, frames.h_, first_frame, npairs, C.byref(cfg), self.h_))
+
+    def run_host(self, frames, host, cfg, li=None, lj=None, nkept=None, ncorn=None, chunk=0):
+        """Streaming front end over host frames [n, h, w] (uint8, ideally pinned): upload, pyramids, corners, KLT and
+        the download of the results are overlapped chunk by chunk; returns when li/lj/nkept/ncorn are filled."""
+        assert host.dtype == np.uint8 and host.flags["C_CONTIGUOUS"] and host.shape[1:] == (frames.h, frames.w)
+        self.ctx._ck(self.ctx.lib.sfmgpu_pair_frontend_host(self.ctx.h, frames.h_, host.ctypes.data_as(_vp), host.shape[0], C.byref(cfg),
+                                                            self.h_, chunk, _ptr(li), _ptr(lj), _ptr(nkept), _ptr(ncorn)))
 
     def totals(self):
         a, b, c = _ll(0), _ll(0), _ll(0)

@@ -299,6 +299,29 @@ def test_pair_frontend_batch(ctx, checker, g):
     assert nc == g["pair_nc"][0] and np.array_equal(li, g["pair_li"]) and _klt_close(lj, g["pair_lj"])
 
 
+@pytest.mark.parametrize("chunk", [0, 2, 3, 7, 100])
+def test_pair_frontend_streaming_equals_resident(ctx, chunk):
+    """sfmgpu_pair_frontend_host (chunked upload || compute || download) returns what the resident call returns."""
+    imgs = np.stack([synth.frame(SEED, t, W, H) for t in range(7)])
+    cfg = sfmgpu.lkcfg(max_tracks=300)
+    f = _frames(ctx, list(imgs))
+    pairs = ctx.pairs(6, 300)
+    pairs.run(f, 0, 6, cfg)
+    want_tot = pairs.totals()
+    li, lj = np.zeros((6, 300, 2)), np.zeros((6, 300, 2))
+    nk, nc = np.zeros(6, np.int32), np.zeros(6, np.int32)
+    pairs.download_all(li, lj, nk, nc)
+    f2 = ctx.frames(W, H, 7, 3)  # fresh storage: the streaming call must fill it itself
+    p2 = ctx.pairs(6, 300)
+    li2, lj2 = np.full((6, 300, 2), -1.0), np.full((6, 300, 2), -1.0)
+    nk2, nc2 = np.zeros(6, np.int32), np.zeros(6, np.int32)
+    p2.run_host(f2, imgs, cfg, li2, lj2, nk2, nc2, chunk=chunk)
+    assert p2.totals() == want_tot
+    assert np.array_equal(nk, nk2) and np.array_equal(nc, nc2)
+    for p in range(6):
+        assert np.array_equal(li[p, :nk[p]], li2[p, :nk[p]]) and np.array_equal(lj[p, :nk[p]], lj2[p, :nk[p]]), p
+
+
 def test_errors_are_loud(ctx):
     f = ctx.frames(64, 48, 2, 3)
     with pytest.raises(sfmgpu.SfmGpuError):
