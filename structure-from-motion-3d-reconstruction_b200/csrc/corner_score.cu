@@ -55,8 +55,17 @@ __global__ void __launch_bounds__(256) score_tile_kernel(const uint8_t* __restri
   __shared__ __align__(16) uint8_t taps[TAP_H * TAP_S];
   __shared__ int hxx[HS_ROWS * HS_S], hxy[HS_ROWS * HS_S], hyy[HS_ROWS * HS_S];
   __shared__ double wmax[8];
+  // MODE 1: pixels that pass the integer screen are queued (local index) and scored densely afterwards, so the
+  // FP64 sqrt path runs with full warps instead of once per warp-row that holds a single candidate
+  __shared__ unsigned short queue[MODE == 1 ? TW * TH : 1];
+  __shared__ unsigned tile_bm[MODE == 1 ? TH * 2 : 1];
+  __shared__ int qn;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fr = blockIdx.z;
+  if (MODE == 1) {
+    if (tid < TH * 2) tile_bm[tid] = 0;
+    if (tid == 0) qn = 0;
+  }
   const uint8_t* im = img + (size_t)(frame0 + fr) * fstride;
   const int X0 = blockIdx.x * TW, Y0 = blockIdx.y * TH;
 
@@ -164,32 +173,12 @@ __global__ void __launch_bounds__(256) score_tile_kernel(const uint8_t* __restri
         }
       }
     } else {
-      bool cand = false;
-      double u = 0.0;
       if (col_in && y < h) {
+        const int loc = (q * 7 + j) * TW + oc;
         if (interior) {
-          if (may_reach(a, b, c, theta_i)) {
-            u = exact_u(a, b, c);
-            cand = u >= thr8;
-          }
-        } else {
-          cand = 0.0 >= thr8;  // border score is exactly 0 (:240, :253-254)
-        }
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, cand);
-      if (y < h && (X0 + (oc & 32)) < w) {
-        if (lane == 0) wv.bitmap[(size_t)fr * wv.words_per_frame + (size_t)y * wv.wpr + ((X0 + (oc & 32)) >> 5)] = m;
-        if (m) {
-          unsigned base = 0;
-          if (lane == 0) base = atomicAdd(wv.ncand + fr, (unsigned)__popc(m));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (cand) {
-            const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
-            if (slot < (unsigned)wv.cand_cap) {
-              wv.tmp_idx[(size_t)fr * wv.cand_cap + slot] = (unsigned)y * (unsigned)w + (unsigned)x;
-              wv.tmp_key[(size_t)fr * wv.cand_cap + slot] = (unsigned long long)__double_as_longlong(0.125 * u);
-            }
-          }
+          if (may_reach(a, b, c, theta_i)) queue[atomicAdd(&qn, 1)] = (unsigned short)loc;
+        } else if (0.0 >= thr8) {
+          queue[atomicAdd(&qn, 1)] = (unsigned short)(loc | 0x8000);  // border score is exactly 0 (:240, :253-254)
         }
       }
     }
@@ -208,6 +197,50 @@ __global__ void __launch_bounds__(256) score_tile_kernel(const uint8_t* __restri
       for (int k = 1; k < 8; k++) m = fmax(m, wmax[k]);
       const unsigned long long mb = (unsigned long long)__double_as_longlong(m);
       if (mb > *(volatile unsigned long long*)maxbits) atomicMax(maxbits, mb);  // u >= 0: bit order == value order
+    }
+  } else {
+    __syncthreads();
+    const int nq = qn;
+    for (int e0 = 0; e0 < nq; e0 += 256) {  // uniform trip count: the ballots below are warp-complete
+      const int e = e0 + tid;
+      bool cand = false;
+      double u = 0.0;
+      int row = 0, col = 0;
+      if (e < nq) {
+        const int id = queue[e], loc = id & 0x7fff;
+        row = loc / TW;
+        col = loc - row * TW;
+        cand = true;
+        if (!(id & 0x8000)) {
+          const int* pxx = hxx + row * HS_S + col;
+          const int* pxy = hxy + row * HS_S + col;
+          const int* pyy = hyy + row * HS_S + col;
+          const int a = pxx[0] + pxx[HS_S] + pxx[2 * HS_S] + pxx[3 * HS_S] + pxx[4 * HS_S];
+          const int c = pxy[0] + pxy[HS_S] + pxy[2 * HS_S] + pxy[3 * HS_S] + pxy[4 * HS_S];
+          const int b = pyy[0] + pyy[HS_S] + pyy[2 * HS_S] + pyy[3 * HS_S] + pyy[4 * HS_S];
+          u = exact_u(a, b, c);
+          cand = u >= thr8;
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, cand);
+      if (m) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(wv.ncand + fr, (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (cand) {
+          atomicOr(&tile_bm[row * 2 + (col >> 5)], 1u << (col & 31));
+          const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
+          if (slot < (unsigned)wv.cand_cap) {
+            wv.tmp_idx[(size_t)fr * wv.cand_cap + slot] = (unsigned)(Y0 + row) * (unsigned)w + (unsigned)(X0 + col);
+            wv.tmp_key[(size_t)fr * wv.cand_cap + slot] = (unsigned long long)__double_as_longlong(0.125 * u);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (tid < TH * 2) {
+      const int y = Y0 + (tid >> 1), xw = X0 + 32 * (tid & 1);
+      if (y < h && xw < w) wv.bitmap[(size_t)fr * wv.words_per_frame + (size_t)y * wv.wpr + (xw >> 5)] = tile_bm[tid];
     }
   }
 }
