@@ -12,21 +12,44 @@
 // evaluate that single expression in FP64 (IEEE sqrt) — only for pixels that pass an exact INTEGER screen
 // D <= (T - theta)^2 against the running threshold, so the FP64 pipe sees a few percent of the pixels.
 //
-// Kernels (tile = 64 x 28 output pixels, 256 threads, taps staged once in shared memory with clamping):
+// FP32 is exact here: Gx, Gy are integers of magnitude <= 255, every product is <= 65025 and every window sum is
+// <= 25 * 65025 = 1,625,625 < 2^24, so the gradient products and both sliding 5-sums run as FFMA/FADD on
+// integer-valued floats without a single rounding.  Bytes become floats with one PRMT (0x4B000000 | b = 2^23 + b);
+// the offset cancels in the gradient differences.
+//
+// Which pixels see the FP64 expression: every pixel gets the FP32 ESTIMATE u~ = T - sqrt.approx(D) (error < 0.5:
+// T <= 1.63e6 has ulp 0.125, D carries two roundings, sqrt.approx 2^-23 relative).  A pixel can only matter if
+// u~ >= bound - 2 (bound = the tile's / frame's running maximum in the max pass, 8*thr in the candidate pass); those
+// few are queued and evaluated DENSELY with the exact FP64 expression afterwards, which alone decides.
+//
+// Kernels (tile = 64 x 60 output pixels, 256 threads, taps staged once in shared memory with clamping):
 //   score_tile_kernel<0>  per-frame maximum of u = 8*lmin  (atomicMax on the double's bit pattern)
-//   score_tile_kernel<1>  candidate bitmap (one ballot word per 32 pixels) + unordered (pixel, score) list
+//   score_tile_kernel<1>  candidate bitmap (one word per 32 pixels) + unordered (pixel, score) list
 //   bitmap_scan_kernel    exclusive prefix of the bitmap popcounts -> raster rank of every candidate
 //   order_kernel          scatter the unordered list to raster order (the order std::sort starts from)
-// Roofline: the structure tensor costs ~40 integer instructions per pixel against 1 B/pixel of traffic, so
-// this stage is bound by the integer/shared-memory pipes, not HBM.
+// Roofline: ~45 instructions per pixel and pass against 1 B/pixel of traffic: bound by instruction issue, not HBM
+// (DESIGN.md §corner-score).
 #include "common.cuh"
 #include "corner_work.cuh"
 
 namespace {
 
-constexpr int TW = 64, TH = 28;
-constexpr int TAP_W = TW + 6, TAP_H = TH + 6, TAP_S = 76;  // 19-word row stride: conflict-free column walks
-constexpr int HS_ROWS = TH + 4, HS_S = 65;                 // horizontal sums, padded rows
+constexpr int TW = 64, TH = 60;
+constexpr int TAP_H = TH + 6, TAP_S = 76;   // tap rows; 19-word row stride: conflict-free when lanes walk rows
+constexpr int HS_ROWS = TH + 4, HS_S = 65;  // horizontal sums: 64 rows, padded
+constexpr int RUN = 16;                     // phase 1: outputs per thread (64 rows x 4 runs)
+constexpr int VRUN = 15;                    // phase 2: outputs per thread (64 columns x 4 row groups)
+constexpr float EST_MARGIN = 2.0f;          // >= 4x the error bound of the FP32 estimate
+
+struct ScoreSmem {
+  float hxx[HS_ROWS * HS_S], hxy[HS_ROWS * HS_S], hyy[HS_ROWS * HS_S];
+  uint8_t taps[TAP_H * TAP_S];
+  unsigned short queue[TW * TH];
+  unsigned tile_bm[TH * 2];
+  float wmaxf[8];
+  double wmax[8];
+  int qn;
+};
 
 __device__ __forceinline__ double i2d(int v) {
   // exact int32 -> double without the slow conversion pipe: (2^52 + 2^31 + v) - (2^52 + 2^31)
@@ -40,38 +63,32 @@ __device__ __forceinline__ double exact_u(int a, int b, int c) {
   return i2d(a + b) - sqrt(D);
 }
 
-// Exact integer screen: can u reach theta_i (an integer <= theta - 1)?
-__device__ __forceinline__ bool may_reach(int a, int b, int c, int theta_i) {
-  if (theta_i <= 0) return true;
-  const int T = a + b;
-  if (T < theta_i) return false;
-  const long long d = a - b, cc = c, m = T - theta_i;
-  return d * d + 4 * cc * cc <= m * m;
+// byte k of w as the float 2^23 + byte (exact)
+__device__ __forceinline__ float bytef(uint32_t w, int k) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650 | k)); }
+
+__device__ __forceinline__ float est_u(float a, float b, float c) {
+  const float d = a - b, c2 = c + c;
+  const float D = fmaf(c2, c2, d * d);
+  float s;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(D));
+  return (a + b) - s;
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256) score_tile_kernel(const uint8_t* __restrict__ img, int w, int h, int pitch, size_t fstride,
-                                                        int frame0, CornerWorkView wv, double quality) {
-  __shared__ __align__(16) uint8_t taps[TAP_H * TAP_S];
-  __shared__ int hxx[HS_ROWS * HS_S], hxy[HS_ROWS * HS_S], hyy[HS_ROWS * HS_S];
-  __shared__ double wmax[8];
-  // MODE 1: pixels that pass the integer screen are queued (local index) and scored densely afterwards, so the
-  // FP64 sqrt path runs with full warps instead of once per warp-row that holds a single candidate
-  __shared__ unsigned short queue[MODE == 1 ? TW * TH : 1];
-  __shared__ unsigned tile_bm[MODE == 1 ? TH * 2 : 1];
-  __shared__ int qn;
+__global__ void __launch_bounds__(256, 3) score_tile_kernel(const uint8_t* __restrict__ img, int w, int h, int pitch, size_t fstride,
+                                                           int frame0, CornerWorkView wv, double quality) {
+  extern __shared__ __align__(16) unsigned char score_raw[];
+  ScoreSmem& sm = *reinterpret_cast<ScoreSmem*>(score_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fr = blockIdx.z;
-  if (MODE == 1) {
-    if (tid < TH * 2) tile_bm[tid] = 0;
-    if (tid == 0) qn = 0;
-  }
   const uint8_t* im = img + (size_t)(frame0 + fr) * fstride;
   const int X0 = blockIdx.x * TW, Y0 = blockIdx.y * TH;
+  if (tid < TH * 2) sm.tile_bm[tid] = 0;
+  if (tid == 0) sm.qn = 0;
 
   // phase 0: taps of image(X0-3 .., Y0-3 ..) with clamped coordinates (= the reference's clamped gradient taps).
-  // Shared rows start at image column X0-4 (4-aligned), so tap tx lives at byte tx+1.  Tiles whose halo lies
-  // inside the image are staged with aligned 32-bit loads (all loads issued before the stores); border tiles
+  // Shared rows start at image column X0-4 (4-aligned), so image column X0+c lives at byte c+4.  Tiles whose halo
+  // lies inside the image are staged with aligned 32-bit loads (all loads issued before the stores); border tiles
   // take the byte path, which implements the clamp.
   if (X0 >= 4 && X0 + 68 <= w && Y0 >= 3 && Y0 + TAP_H - 3 <= h) {
     constexpr int WPT = (TAP_H * 18 + 255) / 256;
@@ -85,150 +102,172 @@ __global__ void __launch_bounds__(256) score_tile_kernel(const uint8_t* __restri
 #pragma unroll
     for (int k = 0; k < WPT; k++) {
       const int idx = tid + 256 * k, r = idx / 18, c = idx - r * 18;
-      if (idx < TAP_H * 18) reinterpret_cast<uint32_t*>(taps)[r * (TAP_S / 4) + c] = v[k];
+      if (idx < TAP_H * 18) reinterpret_cast<uint32_t*>(sm.taps)[r * (TAP_S / 4) + c] = v[k];
     }
   } else {
-    for (int idx = tid; idx < TAP_H * TAP_W; idx += 256) {
-      const int ty = idx / TAP_W, tx = idx - ty * TAP_W;
-      int gx = X0 - 3 + tx, gy = Y0 - 3 + ty;
+    for (int idx = tid; idx < TAP_H * 72; idx += 256) {
+      const int ty = idx / 72, tb = idx - ty * 72;
+      int gx = X0 - 4 + tb, gy = Y0 - 3 + ty;
       gx = gx < 0 ? 0 : (gx > w - 1 ? w - 1 : gx);
       gy = gy < 0 ? 0 : (gy > h - 1 ? h - 1 : gy);
-      taps[ty * TAP_S + tx + 1] = __ldg(im + (size_t)gy * pitch + gx);
+      sm.taps[ty * TAP_S + tb] = __ldg(im + (size_t)gy * pitch + gx);
     }
   }
   __syncthreads();
 
-  // phase 1: horizontal 5-sums of the gradient products.  warp = column group (8 outputs), lane = row.
+  // phase 1: horizontal 5-sums of the gradient products.  lane = row (two row groups), warp pair = run of 16 columns.
+  // Output column c needs products of columns c-2..c+2; column cc's gradients are C[cc+5] - C[cc+3] (centre row) and
+  // P[cc+4] - M[cc+4] (rows below / above), byte offsets within the shared row.
   {
-    const int r = lane, cb = warp * 8;
-    const uint8_t* tm = taps + r * TAP_S + cb + 1;
-    const uint8_t* tc = tm + TAP_S;
-    const uint8_t* tp = tc + TAP_S;
-    int pxx[12], pxy[12], pyy[12];
+    const int r = (warp & 1) * 32 + lane, k0 = (warp >> 1) * RUN;  // h row r <-> image row Y0-2+r; tap rows r, r+1, r+2
+    const uint32_t* wm = reinterpret_cast<const uint32_t*>(sm.taps + r * TAP_S + k0);
+    const uint32_t* wc = reinterpret_cast<const uint32_t*>(sm.taps + (r + 1) * TAP_S + k0);
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(sm.taps + (r + 2) * TAP_S + k0);
+    uint32_t cw[6], pw[6], mw[6];
 #pragma unroll
-    for (int k = 0; k < 12; k++) {
-      const int gx = (int)tc[k + 2] - (int)tc[k];
-      const int gy = (int)tp[k + 1] - (int)tm[k + 1];
-      pxx[k] = gx * gx;
-      pxy[k] = gx * gy;
-      pyy[k] = gy * gy;
+    for (int i = 0; i < 6; i++) {
+      cw[i] = wc[i];
+      pw[i] = wp[i];
+      mw[i] = wm[i];
     }
-    int sxx = pxx[0] + pxx[1] + pxx[2] + pxx[3] + pxx[4];
-    int sxy = pxy[0] + pxy[1] + pxy[2] + pxy[3] + pxy[4];
-    int syy = pyy[0] + pyy[1] + pyy[2] + pyy[3] + pyy[4];
-    int* oxx = hxx + r * HS_S + cb;
-    int* oxy = hxy + r * HS_S + cb;
-    int* oyy = hyy + r * HS_S + cb;
-    oxx[0] = sxx;
-    oxy[0] = sxy;
-    oyy[0] = syy;
+    float gx[RUN + 4], gy[RUN + 4];
 #pragma unroll
-    for (int j = 1; j < 8; j++) {
-      sxx += pxx[j + 4] - pxx[j - 1];
-      sxy += pxy[j + 4] - pxy[j - 1];
-      syy += pyy[j + 4] - pyy[j - 1];
-      oxx[j] = sxx;
-      oxy[j] = sxy;
-      oyy[j] = syy;
+    for (int j = 0; j < RUN + 4; j++) {  // column cc = k0 - 2 + j: bytes (relative to k0) j+3, j+1 / j+2
+      gx[j] = bytef(cw[(j + 3) >> 2], (j + 3) & 3) - bytef(cw[(j + 1) >> 2], (j + 1) & 3);
+      gy[j] = bytef(pw[(j + 2) >> 2], (j + 2) & 3) - bytef(mw[(j + 2) >> 2], (j + 2) & 3);
+    }
+    float sxx = 0.f, sxy = 0.f, syy = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      sxx = fmaf(gx[j], gx[j], sxx);
+      sxy = fmaf(gx[j], gy[j], sxy);
+      syy = fmaf(gy[j], gy[j], syy);
+    }
+    float* oxx = sm.hxx + r * HS_S + k0;
+    float* oxy = sm.hxy + r * HS_S + k0;
+    float* oyy = sm.hyy + r * HS_S + k0;
+#pragma unroll
+    for (int t = 0; t < RUN; t++) {
+      sxx = fmaf(gx[t + 4], gx[t + 4], sxx);
+      sxy = fmaf(gx[t + 4], gy[t + 4], sxy);
+      syy = fmaf(gy[t + 4], gy[t + 4], syy);
+      oxx[t] = sxx;
+      oxy[t] = sxy;
+      oyy[t] = syy;
+      sxx = fmaf(-gx[t], gx[t], sxx);
+      sxy = fmaf(-gx[t], gy[t], sxy);
+      syy = fmaf(-gy[t], gy[t], syy);
     }
   }
   __syncthreads();
 
-  // phase 2: vertical 5-sums, score, max / candidate test.  thread = column, 7 consecutive rows.
+  // phase 2: vertical 5-sums and the FP32 estimate.  thread = column, VRUN consecutive rows.
   const int oc = tid & 63, q = tid >> 6;
   const int x = X0 + oc;
-  const int* cxx = hxx + (q * 7) * HS_S + oc;
-  const int* cxy = hxy + (q * 7) * HS_S + oc;
-  const int* cyy = hyy + (q * 7) * HS_S + oc;
-  int a = cxx[0] + cxx[HS_S] + cxx[2 * HS_S] + cxx[3 * HS_S];
-  int c = cxy[0] + cxy[HS_S] + cxy[2 * HS_S] + cxy[3 * HS_S];
-  int b = cyy[0] + cyy[HS_S] + cyy[2 * HS_S] + cyy[3 * HS_S];
-
+  const float* cxx = sm.hxx + (q * VRUN) * HS_S + oc;
+  const float* cxy = sm.hxy + (q * VRUN) * HS_S + oc;
+  const float* cyy = sm.hyy + (q * VRUN) * HS_S + oc;
   unsigned long long* maxbits = wv.maxbits + fr;
-  double thr8 = 0.0, best = 0.0;
-  int theta_i;
+  double thr8 = 0.0;
+  float bound;
   if (MODE == 0) {
-    best = __longlong_as_double(*(volatile unsigned long long*)maxbits);  // what earlier blocks already found
-    theta_i = (int)best - 1;
+    bound = __double2float_rd(__longlong_as_double(*(volatile unsigned long long*)maxbits));  // what earlier blocks found
   } else {
     const double maxv = 0.125 * __longlong_as_double(*maxbits);
     thr8 = 8.0 * (maxv * quality);  // thr = maxv*quality (:275); s >= thr  <=>  u >= 8*thr
-    theta_i = thr8 < 2.0e9 ? (int)thr8 - 1 : 2000000000;
+    bound = __double2float_rd(thr8);
   }
   const bool col_in = x < w, col_interior = x >= 2 && x < w - 2;
-
+  float ra[4], rb[4], rc[4];  // ring of the last four row sums; the fifth enters in the loop
 #pragma unroll
-  for (int j = 0; j < 7; j++) {
-    a += cxx[(j + 4) * HS_S];
-    c += cxy[(j + 4) * HS_S];
-    b += cyy[(j + 4) * HS_S];
-    const int y = Y0 + q * 7 + j;
+  for (int i = 0; i < 4; i++) {
+    ra[i] = cxx[i * HS_S];
+    rc[i] = cxy[i * HS_S];
+    rb[i] = cyy[i * HS_S];
+  }
+  float a = (ra[0] + ra[1]) + (ra[2] + ra[3]), c = (rc[0] + rc[1]) + (rc[2] + rc[3]), b = (rb[0] + rb[1]) + (rb[2] + rb[3]);
+  float uf[VRUN];
+  float tmax = 0.f;
+#pragma unroll
+  for (int j = 0; j < VRUN; j++) {
+    const float na = cxx[(j + 4) * HS_S], nc = cxy[(j + 4) * HS_S], nb = cyy[(j + 4) * HS_S];
+    a += na;
+    c += nc;
+    b += nb;
+    const int y = Y0 + q * VRUN + j;
     const bool interior = col_interior && y >= 2 && y < h - 2;
+    const float u = est_u(a, b, c);
     if (MODE == 0) {
-      if (interior && may_reach(a, b, c, theta_i)) {
-        const double u = exact_u(a, b, c);
-        if (u > best) {
-          best = u;
-          theta_i = (int)u - 1;
-        }
-      }
+      uf[j] = interior ? u : -1.0e30f;
+      tmax = fmaxf(tmax, uf[j]);
     } else {
       if (col_in && y < h) {
-        const int loc = (q * 7 + j) * TW + oc;
+        const int loc = (q * VRUN + j) * TW + oc;
         if (interior) {
-          if (may_reach(a, b, c, theta_i)) queue[atomicAdd(&qn, 1)] = (unsigned short)loc;
+          if (u >= bound - EST_MARGIN) sm.queue[atomicAdd(&sm.qn, 1)] = (unsigned short)loc;
         } else if (0.0 >= thr8) {
-          queue[atomicAdd(&qn, 1)] = (unsigned short)(loc | 0x8000);  // border score is exactly 0 (:240, :253-254)
+          sm.queue[atomicAdd(&sm.qn, 1)] = (unsigned short)(loc | 0x8000);  // border score is exactly 0 (:240, :253-254)
         }
       }
     }
-    a -= cxx[j * HS_S];
-    c -= cxy[j * HS_S];
-    b -= cyy[j * HS_S];
+    a -= ra[j & 3];
+    c -= rc[j & 3];
+    b -= rb[j & 3];
+    ra[j & 3] = na;
+    rc[j & 3] = nc;
+    rb[j & 3] = nb;
   }
 
   if (MODE == 0) {
+    // tile maximum of the estimates, then queue every pixel that can still be the frame maximum
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
-    if (lane == 0) wmax[warp] = best;
+    for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    if (lane == 0) sm.wmaxf[warp] = tmax;
     __syncthreads();
-    if (tid == 0) {
-      double m = wmax[0];
-      for (int k = 1; k < 8; k++) m = fmax(m, wmax[k]);
-      const unsigned long long mb = (unsigned long long)__double_as_longlong(m);
-      if (mb > *(volatile unsigned long long*)maxbits) atomicMax(maxbits, mb);  // u >= 0: bit order == value order
-    }
-  } else {
-    __syncthreads();
-    const int nq = qn;
-    for (int e0 = 0; e0 < nq; e0 += 256) {  // uniform trip count: the ballots below are warp-complete
-      const int e = e0 + tid;
-      bool cand = false;
-      double u = 0.0;
-      int row = 0, col = 0;
-      if (e < nq) {
-        const int id = queue[e], loc = id & 0x7fff;
-        row = loc / TW;
-        col = loc - row * TW;
-        cand = true;
-        if (!(id & 0x8000)) {
-          const int* pxx = hxx + row * HS_S + col;
-          const int* pxy = hxy + row * HS_S + col;
-          const int* pyy = hyy + row * HS_S + col;
-          const int a = pxx[0] + pxx[HS_S] + pxx[2 * HS_S] + pxx[3 * HS_S] + pxx[4 * HS_S];
-          const int c = pxy[0] + pxy[HS_S] + pxy[2 * HS_S] + pxy[3 * HS_S] + pxy[4 * HS_S];
-          const int b = pyy[0] + pyy[HS_S] + pyy[2 * HS_S] + pyy[3 * HS_S] + pyy[4 * HS_S];
-          u = exact_u(a, b, c);
-          cand = u >= thr8;
-        }
+    float bm = sm.wmaxf[0];
+#pragma unroll
+    for (int k = 1; k < 8; k++) bm = fmaxf(bm, sm.wmaxf[k]);
+    bound = fmaxf(bound, bm) - EST_MARGIN;
+#pragma unroll
+    for (int j = 0; j < VRUN; j++)
+      if (uf[j] >= bound) sm.queue[atomicAdd(&sm.qn, 1)] = (unsigned short)((q * VRUN + j) * TW + oc);
+  }
+  __syncthreads();
+
+  // dense exact evaluation of the queued pixels
+  const int nq = sm.qn;
+  double best = 0.0;
+  for (int e0 = 0; e0 < nq; e0 += 256) {  // uniform trip count: the ballots below are warp-complete
+    const int e = e0 + tid;
+    bool cand = false;
+    double u = 0.0;
+    int row = 0, col = 0;
+    if (e < nq) {
+      const int id = sm.queue[e], loc = id & 0x7fff;
+      row = loc / TW;
+      col = loc - row * TW;
+      cand = true;
+      if (!(id & 0x8000)) {
+        const float* pxx = sm.hxx + row * HS_S + col;
+        const float* pxy = sm.hxy + row * HS_S + col;
+        const float* pyy = sm.hyy + row * HS_S + col;
+        const int ia = __float2int_rn((pxx[0] + pxx[HS_S]) + (pxx[2 * HS_S] + pxx[3 * HS_S]) + pxx[4 * HS_S]);
+        const int ic = __float2int_rn((pxy[0] + pxy[HS_S]) + (pxy[2 * HS_S] + pxy[3 * HS_S]) + pxy[4 * HS_S]);
+        const int ib = __float2int_rn((pyy[0] + pyy[HS_S]) + (pyy[2 * HS_S] + pyy[3 * HS_S]) + pyy[4 * HS_S]);
+        u = exact_u(ia, ib, ic);
+        cand = u >= thr8;
       }
+    }
+    if (MODE == 0) {
+      best = fmax(best, u);
+    } else {
       const unsigned m = __ballot_sync(0xffffffffu, cand);
       if (m) {
         unsigned base = 0;
         if (lane == 0) base = atomicAdd(wv.ncand + fr, (unsigned)__popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
         if (cand) {
-          atomicOr(&tile_bm[row * 2 + (col >> 5)], 1u << (col & 31));
+          atomicOr(&sm.tile_bm[row * 2 + (col >> 5)], 1u << (col & 31));
           const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
           if (slot < (unsigned)wv.cand_cap) {
             wv.tmp_idx[(size_t)fr * wv.cand_cap + slot] = (unsigned)(Y0 + row) * (unsigned)w + (unsigned)(X0 + col);
@@ -237,10 +276,23 @@ __global__ void __launch_bounds__(256) score_tile_kernel(const uint8_t* __restri
         }
       }
     }
+  }
+  if (MODE == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) sm.wmax[warp] = best;
+    __syncthreads();
+    if (tid == 0) {
+      double m = sm.wmax[0];
+      for (int k = 1; k < 8; k++) m = fmax(m, sm.wmax[k]);
+      const unsigned long long mb = (unsigned long long)__double_as_longlong(m);
+      if (mb > *(volatile unsigned long long*)maxbits) atomicMax(maxbits, mb);  // u >= 0: bit order == value order
+    }
+  } else {
     __syncthreads();
     if (tid < TH * 2) {
       const int y = Y0 + (tid >> 1), xw = X0 + 32 * (tid & 1);
-      if (y < h && xw < w) wv.bitmap[(size_t)fr * wv.words_per_frame + (size_t)y * wv.wpr + (xw >> 5)] = tile_bm[tid];
+      if (y < h && xw < w) wv.bitmap[(size_t)fr * wv.words_per_frame + (size_t)y * wv.wpr + (xw >> 5)] = sm.tile_bm[tid];
     }
   }
 }
@@ -315,8 +367,16 @@ int sfm_corner_candidates_batch(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int fir
   SFM_CUDA(ctx, cudaMemsetAsync(wv.maxbits, 0, sizeof(unsigned long long) * count, ctx->stream));
   SFM_CUDA(ctx, cudaMemsetAsync(wv.ncand, 0, sizeof(unsigned) * count, ctx->stream));
   dim3 grid(sfm_cdiv(f->w, TW), sfm_cdiv(f->h, TH), count);
-  SFM_LAUNCH(ctx, score_tile_kernel<0>, grid, 256, 0, f->lvl[0], f->w, f->h, f->pitch[0], f->fstride[0], first, wv, quality);
-  SFM_LAUNCH(ctx, score_tile_kernel<1>, grid, 256, 0, f->lvl[0], f->w, f->h, f->pitch[0], f->fstride[0], first, wv, quality);
+  static bool configured = false;
+  if (!configured) {
+    SFM_CUDA(ctx, cudaFuncSetAttribute(score_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScoreSmem)));
+    SFM_CUDA(ctx, cudaFuncSetAttribute(score_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScoreSmem)));
+    configured = true;
+  }
+  SFM_LAUNCH(ctx, score_tile_kernel<0>, grid, 256, sizeof(ScoreSmem), f->lvl[0], f->w, f->h, f->pitch[0], f->fstride[0], first, wv,
+             quality);
+  SFM_LAUNCH(ctx, score_tile_kernel<1>, grid, 256, sizeof(ScoreSmem), f->lvl[0], f->w, f->h, f->pitch[0], f->fstride[0], first, wv,
+             quality);
   SFM_LAUNCH(ctx, bitmap_scan_kernel, count, 1024, 0, wv);
   SFM_LAUNCH(ctx, order_kernel, dim3(16, count), 256, 0, wv, f->w);
   return 0;
