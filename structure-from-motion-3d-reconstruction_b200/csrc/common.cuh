@@ -49,13 +49,15 @@ struct sfmgpu_ctx {
   int n_sm = SFM_NSM_FALLBACK;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr, back_stream = nullptr;  // H2D / D2H legs of the streaming front end
+  cudaStream_t aux_stream = nullptr;  // second compute lane of the chunk pipeline (frontend.cu)
+  int pipe_chunk = 0;                 // resident batches: pairs per sub-chunk of the two-lane pipeline, 0 = sequential
   std::vector<cudaEvent_t> pipe_evs;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
   long long launches = 0;
   // scratch, grown on demand (never shrunk)
   DevBuf flush;
-  DevBuf klt_in, klt_p1, klt_pb, klt_nit, klt_keep, klt_defer;
+  DevBuf klt_in, klt_p1, klt_pb, klt_nit, klt_keep, klt_defer, klt_defer2;
   int klt_mode = 0;  // 0 auto, 1 warp-per-feature, 2 lane-per-feature (tests / profiling)
   DevBuf cs_work;    // corner-score work area for single-frame calls
   DevBuf sel_work;   // corner-select work area

@@ -2,6 +2,8 @@
 //   * the stateless two-view front end (cpp/src/templering_sfm.cpp:1836-1857), batched over frame pairs;
 //   * the stateful KLTTracker (:323-391): reset / step / tracks, with the replenish rule (:374-389).
 // Everything stays on the device between stages; only survivors / counts are copied back when the caller asks.
+#include <utility>
+
 #include "common.cuh"
 
 // ---- small kernels -----------------------------------------------------------------------------------------------
@@ -179,7 +181,7 @@ struct sfmgpu_pairs {
   int *ncorn = nullptr, *nkept = nullptr, *nit = nullptr;
   uint8_t* keep = nullptr;
   unsigned long long* totals = nullptr;
-  DevBuf work;
+  DevBuf work, work2;  // corner work areas of the two compute lanes
   int last_npairs = 0;
 };
 
@@ -216,7 +218,7 @@ int sfmgpu_pairs_create(sfmgpu_ctx* ctx, int max_pairs, int max_corners, sfmgpu_
 void sfmgpu_pairs_destroy(sfmgpu_ctx* ctx, sfmgpu_pairs* p) {
   if (!p) return;
   if (ctx) cudaStreamSynchronize(ctx->stream);
-  void* ptrs[] = {p->xy0, p->p1, p->pb, p->li, p->lj, p->nit, p->keep, p->ncorn, p->nkept, p->totals, p->work.p};
+  void* ptrs[] = {p->xy0, p->p1, p->pb, p->li, p->lj, p->nit, p->keep, p->ncorn, p->nkept, p->totals, p->work.p, p->work2.p};
   for (void* q : ptrs)
     if (q) cudaFree(q);
   delete p;
@@ -225,19 +227,19 @@ void sfmgpu_pairs_destroy(sfmgpu_ctx* ctx, sfmgpu_pairs* p) {
 // Pairs (first_frame + k, first_frame + k + 1), k < npairs, written to slots [pair_off, pair_off + npairs) of `out`
 // on the context stream; totals are accumulated (the caller zeroes them).
 static int pair_range(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int pair_off, int npairs, const sfmgpu_lkcfg* cfg,
-                      sfmgpu_pairs* out) {
+                      sfmgpu_pairs* out, DevBuf& work) {
   if (npairs == 0) return 0;
   // corners, in chunks of frames that bound the work area
   const int cand_cap = default_cand_cap(f->w, f->h);
   const int md = cfg->min_distance < 0 ? -cfg->min_distance : cfg->min_distance;
   int chunk = npairs < 1024 ? npairs : 1024;  // frames per corner launch: >= 4 blocks per SM keeps the select kernel busy
   const size_t wb = sfm_corner_work_bytes_md(f->w, f->h, chunk, cand_cap, md);
-  SFM_TRY(sfm_reserve(ctx, out->work, wb));
+  SFM_TRY(sfm_reserve(ctx, work, wb));
   const size_t so = (size_t)pair_off * out->cap;
   for (int c0 = 0; c0 < npairs; c0 += chunk) {
     const int cnt = npairs - c0 < chunk ? npairs - c0 : chunk;
     SFM_TRY(sfm_corners_batch(ctx, f, first_frame + c0, cnt, cfg->max_tracks, cfg->quality, cfg->min_distance, cand_cap,
-                              out->work.p, out->work.cap, out->xy0 + so + (size_t)c0 * out->cap, out->ncorn + pair_off + c0));
+                              work.p, work.cap, out->xy0 + so + (size_t)c0 * out->cap, out->ncorn + pair_off + c0));
   }
   KltLaunch k;
   k.pv = f->view();
@@ -268,6 +270,61 @@ static int pair_range(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int pa
   return 0;
 }
 
+// ---- two-lane chunk pipeline ---------------------------------------------------------------------------------------
+// Sub-chunks of pairs can alternate between two compute streams (each with its own corner work area and KLT scratch),
+// so that the latency-bound corner-select blocks of one sub-chunk share the SMs with the score / KLT blocks of the
+// other.  Results are identical to the sequential order (sub-chunks are independent).  Measured on B200 (C2, 999
+// pairs): for a RESIDENT batch it loses (58.8 ms sequential vs 60.9 / 64.3 / 67.7 / 84.7 ms at 256 / 192 / 128 / 64
+// pairs per sub-chunk: a later kernel's blocks are only dispatched once the earlier kernel has none pending, and every
+// select launch pays its ~4.8 ms latency), so it is off by default there; the HOST-streaming call uses the two lanes
+// at upload-chunk granularity, where it wins (91 -> 77 ms end to end).
+struct LaneScope {  // run a piece of work on lane `l`: swaps the context's stream and per-stream scratch
+  sfmgpu_ctx* ctx;
+  int lane;
+  cudaStream_t saved;
+  LaneScope(sfmgpu_ctx* c, int l) : ctx(c), lane(l), saved(c->stream) {
+    if (l) {
+      c->stream = c->aux_stream;
+      std::swap(c->klt_defer, c->klt_defer2);
+    }
+  }
+  ~LaneScope() {
+    if (lane) {
+      ctx->stream = saved;
+      std::swap(ctx->klt_defer, ctx->klt_defer2);
+    }
+  }
+};
+
+static cudaEvent_t pipe_event(sfmgpu_ctx* ctx, size_t i) {
+  while (ctx->pipe_evs.size() <= i) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ctx->pipe_evs.push_back(e);
+  }
+  return ctx->pipe_evs[i];
+}
+
+static int pipe_streams(sfmgpu_ctx* ctx) {
+  if (!ctx->aux_stream) SFM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+  if (!ctx->copy_stream) SFM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  if (!ctx->back_stream) SFM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->back_stream, cudaStreamNonBlocking));
+  return 0;
+}
+
+// Scratch of both lanes is sized before any work is queued (growing a buffer frees and reallocates it).
+static int pipe_reserve(sfmgpu_ctx* ctx, sfmgpu_frames* f, const sfmgpu_lkcfg* cfg, sfmgpu_pairs* out, int sub) {
+  const int cand_cap = default_cand_cap(f->w, f->h);
+  const int md = cfg->min_distance < 0 ? -cfg->min_distance : cfg->min_distance;
+  const size_t wb = sfm_corner_work_bytes_md(f->w, f->h, sub < 1024 ? sub : 1024, cand_cap, md);
+  SFM_TRY(sfm_reserve(ctx, out->work, wb));
+  SFM_TRY(sfm_reserve(ctx, out->work2, wb));
+  const size_t db = ((size_t)sub * out->cap + 1) * sizeof(int);
+  SFM_TRY(sfm_reserve(ctx, ctx->klt_defer, db));
+  SFM_TRY(sfm_reserve(ctx, ctx->klt_defer2, db));
+  return 0;
+}
+
 static int pair_args_ok(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int npairs, const sfmgpu_lkcfg* cfg, sfmgpu_pairs* out) {
   if (npairs < 0 || npairs > out->max_pairs || first_frame < 0 || first_frame + npairs + (npairs > 0 ? 1 : 0) > f->n)
     return sfm_fail(ctx, SFMGPU_E_ARG, "pair_frontend: pair range [%d,%d) does not fit (frames %d, max_pairs %d)", first_frame,
@@ -278,18 +335,42 @@ static int pair_args_ok(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int 
   return 0;
 }
 
+int sfmgpu_pipeline_set(sfmgpu_ctx* ctx, int pairs_per_chunk) {
+  if (!ctx) return SFMGPU_E_ARG;
+  if (pairs_per_chunk < 0) return sfm_fail(ctx, SFMGPU_E_ARG, "pipeline_set: negative chunk");
+  ctx->pipe_chunk = pairs_per_chunk;
+  return 0;
+}
+
 int sfmgpu_pair_frontend(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int npairs, const sfmgpu_lkcfg* cfg,
                          sfmgpu_pairs* out) {
   if (!ctx || !f || !cfg || !out) return SFMGPU_E_ARG;
   SFM_TRY(pair_args_ok(ctx, f, first_frame, npairs, cfg, out));
   out->last_npairs = npairs;
   SFM_CUDA(ctx, cudaMemsetAsync(out->totals, 0, 64, ctx->stream));
-  return pair_range(ctx, f, first_frame, 0, npairs, cfg, out);
+  const int sub = ctx->pipe_chunk;
+  if (sub <= 0 || ctx->profile || npairs < 2 * sub)  // stage profiling wants the stages back to back on one stream
+    return pair_range(ctx, f, first_frame, 0, npairs, cfg, out, out->work);
+  SFM_TRY(pipe_streams(ctx));
+  SFM_TRY(pipe_reserve(ctx, f, cfg, out, sub));
+  cudaEvent_t fork = pipe_event(ctx, 0), join = pipe_event(ctx, 1);
+  if (!fork || !join) return sfm_fail(ctx, SFMGPU_E_CUDA, "pair_frontend: cudaEventCreate failed");
+  SFM_CUDA(ctx, cudaEventRecord(fork, ctx->stream));
+  SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, fork, 0));
+  int lane = 0;
+  for (int p0 = 0; p0 < npairs; p0 += sub, lane ^= 1) {
+    const int cnt = npairs - p0 < sub ? npairs - p0 : sub;
+    LaneScope ls(ctx, lane);
+    SFM_TRY(pair_range(ctx, f, first_frame + p0, p0, cnt, cfg, out, lane ? out->work2 : out->work));
+  }
+  SFM_CUDA(ctx, cudaEventRecord(join, ctx->aux_stream));
+  SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, join, 0));
+  return 0;
 }
 
 // Streaming variant for frames that live in HOST memory: frames [0, nframes) of `f` are filled from host_pix in
-// chunks on a copy stream while the compute stream builds pyramids and runs the pair front end on the chunks that
-// have arrived; each chunk's results go back on a third stream.  One synchronisation at the end.
+// chunks on a copy stream (which also builds their pyramids) while the two compute lanes run the pair front end on
+// the sub-chunks whose frames have arrived; each sub-chunk's results go back on a fourth stream.
 int sfmgpu_pair_frontend_host(sfmgpu_ctx* ctx, sfmgpu_frames* f, const uint8_t* host_pix, int nframes, const sfmgpu_lkcfg* cfg,
                               sfmgpu_pairs* out, int chunk_frames, double* li_xy, double* lj_xy, int32_t* n_kept,
                               int32_t* n_corners) {
@@ -300,46 +381,63 @@ int sfmgpu_pair_frontend_host(sfmgpu_ctx* ctx, sfmgpu_frames* f, const uint8_t* 
   out->last_npairs = npairs;
   SFM_CUDA(ctx, cudaMemsetAsync(out->totals, 0, 64, ctx->stream));
   if (nframes == 0) return 0;
-  if (!ctx->copy_stream) {
-    SFM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    SFM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->back_stream, cudaStreamNonBlocking));
-  }
-  int chunk = chunk_frames > 0 ? chunk_frames : (nframes + 3) / 4;
+  SFM_TRY(pipe_streams(ctx));
+  int chunk = chunk_frames > 0 ? chunk_frames : (nframes + 5) / 6;
   if (chunk < 2) chunk = 2;
   const int nchunks = (nframes + chunk - 1) / chunk;
-  while ((int)ctx->pipe_evs.size() < 2 * nchunks + 1) {
-    cudaEvent_t e;
-    SFM_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    ctx->pipe_evs.push_back(e);
-  }
-  // the copy stream must not overwrite frames an earlier call on the compute stream still reads
-  SFM_CUDA(ctx, cudaEventRecord(ctx->pipe_evs[2 * nchunks], ctx->stream));
-  SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->pipe_evs[2 * nchunks], 0));
-  SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->back_stream, ctx->pipe_evs[2 * nchunks], 0));
+  const bool two_lanes = !ctx->profile;
+  const int sub = ctx->pipe_chunk > 0 ? ctx->pipe_chunk : chunk;  // default: one sub-chunk per upload chunk, lanes alternate
+  SFM_TRY(pipe_reserve(ctx, f, cfg, out, sub < chunk ? sub : chunk));
+  size_t ev = 0;
+  cudaEvent_t fork = pipe_event(ctx, ev++);
+  if (!fork) return sfm_fail(ctx, SFMGPU_E_CUDA, "pair_frontend_host: cudaEventCreate failed");
+  // nothing may overwrite frames / results that an earlier call on the main stream still uses
+  SFM_CUDA(ctx, cudaEventRecord(fork, ctx->stream));
+  SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, fork, 0));
+  SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->back_stream, fork, 0));
+  SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, fork, 0));
   const size_t cap = (size_t)out->cap;
+  int lane = 0;
   for (int c = 0; c < nchunks; c++) {
     const int a = c * chunk, b = a + chunk < nframes ? a + chunk : nframes;
     SFM_CUDA(ctx, cudaMemcpy2DAsync(f->lvl[0] + (size_t)a * f->fstride[0], f->pitch[0], host_pix + (size_t)a * f->w * f->h, f->w,
                                     f->w, (size_t)f->h * (b - a), cudaMemcpyHostToDevice, ctx->copy_stream));
-    SFM_CUDA(ctx, cudaEventRecord(ctx->pipe_evs[2 * c], ctx->copy_stream));
-    SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_evs[2 * c], 0));
-    SFM_TRY(sfmgpu_pyramid_build(ctx, f, a, b - a));
+    cudaEvent_t up = pipe_event(ctx, ev++);
+    if (!up) return sfm_fail(ctx, SFMGPU_E_CUDA, "pair_frontend_host: cudaEventCreate failed");
+    {
+      cudaStream_t saved = ctx->stream;  // the pyramid of a chunk is built right behind its upload, on the copy stream
+      ctx->stream = ctx->copy_stream;
+      const int rc = sfmgpu_pyramid_build(ctx, f, a, b - a);
+      ctx->stream = saved;
+      SFM_TRY(rc);
+    }
+    SFM_CUDA(ctx, cudaEventRecord(up, ctx->copy_stream));
+    SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, up, 0));
+    SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, up, 0));
     // pairs whose second frame arrived with this chunk
-    const int p0 = a > 0 ? a - 1 : 0, p1 = b - 1;
-    if (p1 > p0) {
-      SFM_TRY(pair_range(ctx, f, p0, p0, p1 - p0, cfg, out));
-      SFM_CUDA(ctx, cudaEventRecord(ctx->pipe_evs[2 * c + 1], ctx->stream));
-      SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->back_stream, ctx->pipe_evs[2 * c + 1], 0));
-      const size_t np_ = (size_t)(p1 - p0);
+    const int P0 = a > 0 ? a - 1 : 0, P1 = b - 1;
+    for (int p0 = P0; p0 < P1; p0 += sub) {
+      const int cnt = P1 - p0 < sub ? P1 - p0 : sub;
+      cudaEvent_t done = pipe_event(ctx, ev++);
+      if (!done) return sfm_fail(ctx, SFMGPU_E_CUDA, "pair_frontend_host: cudaEventCreate failed");
+      {
+        LaneScope ls(ctx, lane);
+        SFM_TRY(pair_range(ctx, f, p0, p0, cnt, cfg, out, lane ? out->work2 : out->work));
+        SFM_CUDA(ctx, cudaEventRecord(done, ctx->stream));
+      }
+      if (two_lanes) lane ^= 1;
+      SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->back_stream, done, 0));
+      const size_t np_ = (size_t)cnt, o = (size_t)p0;
       if (li_xy)
-        SFM_CUDA(ctx, cudaMemcpyAsync(li_xy + 2 * p0 * cap, out->li + p0 * cap, np_ * cap * 16, cudaMemcpyDeviceToHost, ctx->back_stream));
+        SFM_CUDA(ctx, cudaMemcpyAsync(li_xy + 2 * o * cap, out->li + o * cap, np_ * cap * 16, cudaMemcpyDeviceToHost, ctx->back_stream));
       if (lj_xy)
-        SFM_CUDA(ctx, cudaMemcpyAsync(lj_xy + 2 * p0 * cap, out->lj + p0 * cap, np_ * cap * 16, cudaMemcpyDeviceToHost, ctx->back_stream));
-      if (n_kept) SFM_CUDA(ctx, cudaMemcpyAsync(n_kept + p0, out->nkept + p0, np_ * 4, cudaMemcpyDeviceToHost, ctx->back_stream));
-      if (n_corners) SFM_CUDA(ctx, cudaMemcpyAsync(n_corners + p0, out->ncorn + p0, np_ * 4, cudaMemcpyDeviceToHost, ctx->back_stream));
+        SFM_CUDA(ctx, cudaMemcpyAsync(lj_xy + 2 * o * cap, out->lj + o * cap, np_ * cap * 16, cudaMemcpyDeviceToHost, ctx->back_stream));
+      if (n_kept) SFM_CUDA(ctx, cudaMemcpyAsync(n_kept + o, out->nkept + o, np_ * 4, cudaMemcpyDeviceToHost, ctx->back_stream));
+      if (n_corners) SFM_CUDA(ctx, cudaMemcpyAsync(n_corners + o, out->ncorn + o, np_ * 4, cudaMemcpyDeviceToHost, ctx->back_stream));
     }
   }
   SFM_CUDA(ctx, cudaStreamSynchronize(ctx->back_stream));
+  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->aux_stream));
   SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
 }

@@ -27,7 +27,7 @@ SYMBOLS = [
     "sfmgpu_host_free", "sfmgpu_frames_create", "sfmgpu_frames_destroy", "sfmgpu_frames_upload",
     "sfmgpu_frames_upload_device", "sfmgpu_frames_synth", "sfmgpu_pyramid_build", "sfmgpu_frames_level_size",
     "sfmgpu_frames_download", "sfmgpu_corner_candidates", "sfmgpu_corners", "sfmgpu_sort_perm_desc",
-    "sfmgpu_klt_track", "sfmgpu_klt_set_mode", "sfmgpu_pairs_create", "sfmgpu_pairs_destroy", "sfmgpu_pair_frontend", "sfmgpu_pair_frontend_host", "sfmgpu_pairs_totals",
+    "sfmgpu_klt_track", "sfmgpu_klt_set_mode", "sfmgpu_pairs_create", "sfmgpu_pairs_destroy", "sfmgpu_pair_frontend", "sfmgpu_pipeline_set", "sfmgpu_pair_frontend_host", "sfmgpu_pairs_totals",
     "sfmgpu_pairs_download", "sfmgpu_pairs_download_all", "sfmgpu_pairs_device_ptrs", "sfmgpu_tracker_create", "sfmgpu_tracker_destroy", "sfmgpu_tracker_reset",
     "sfmgpu_tracker_step", "sfmgpu_tracker_step_frames", "sfmgpu_tracker_tracks", "sfmgpu_tracker_totals",
     "sfmgpu_ransac_score", "sfmgpu_ransac_upload", "sfmgpu_ransac_score_resident", "sfmgpu_ransac_download",
@@ -98,6 +98,7 @@ def load_library():
         "sfmgpu_pairs_create": (_i, [_vp, _i, _i, C.POINTER(_vp)]),
         "sfmgpu_pairs_destroy": (None, [_vp, _vp]),
         "sfmgpu_pair_frontend": (_i, [_vp, _vp, _i, _i, C.POINTER(LKCfg), _vp]),
+        "sfmgpu_pipeline_set": (_i, [_vp, _i]),
         "sfmgpu_pair_frontend_host": (_i, [_vp, _vp, _vp, _i, C.POINTER(LKCfg), _vp, _i, _vp, _vp, _vp, _vp]),
         "sfmgpu_pairs_totals": (_i, [_vp, _vp, C.POINTER(_ll), C.POINTER(_ll), C.POINTER(_ll)]),
         "sfmgpu_pairs_download": (_i, [_vp, _vp, _i, _f64p, _f64p, _i, C.POINTER(_i), C.POINTER(_i)]),
@@ -158,6 +159,10 @@ class Context:
 
     def launches(self):
         return int(self.lib.sfmgpu_launch_count(self.h))
+
+    def pipeline_set(self, pairs_per_chunk):
+        """Sub-chunk size of the two-lane chunk pipeline (0: sequential, one stream)."""
+        self._ck(self.lib.sfmgpu_pipeline_set(self.h, pairs_per_chunk))
 
     def klt_set_mode(self, mode):
         """0 auto, 1 warp-per-feature kernel only, 2 lane-per-feature kernel whenever win_radius == 5."""

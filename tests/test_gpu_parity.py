@@ -299,13 +299,15 @@ def test_pair_frontend_batch(ctx, checker, g):
     assert nc == g["pair_nc"][0] and np.array_equal(li, g["pair_li"]) and _klt_close(lj, g["pair_lj"])
 
 
-@pytest.mark.parametrize("chunk", [0, 2, 3, 7, 100])
-def test_pair_frontend_streaming_equals_resident(ctx, chunk):
-    """sfmgpu_pair_frontend_host (chunked upload || compute || download) returns what the resident call returns."""
+@pytest.mark.parametrize("chunk,pipe", [(0, 0), (2, 0), (3, 1), (7, 2), (100, 2), (4, 3)])
+def test_pair_frontend_streaming_equals_resident(ctx, chunk, pipe):
+    """sfmgpu_pair_frontend_host (chunked upload || two compute lanes || download) and the two-lane resident call
+    return what the sequential resident call returns."""
     imgs = np.stack([synth.frame(SEED, t, W, H) for t in range(7)])
     cfg = sfmgpu.lkcfg(max_tracks=300)
     f = _frames(ctx, list(imgs))
     pairs = ctx.pairs(6, 300)
+    ctx.pipeline_set(0)
     pairs.run(f, 0, 6, cfg)
     want_tot = pairs.totals()
     li, lj = np.zeros((6, 300, 2)), np.zeros((6, 300, 2))
@@ -315,11 +317,25 @@ def test_pair_frontend_streaming_equals_resident(ctx, chunk):
     p2 = ctx.pairs(6, 300)
     li2, lj2 = np.full((6, 300, 2), -1.0), np.full((6, 300, 2), -1.0)
     nk2, nc2 = np.zeros(6, np.int32), np.zeros(6, np.int32)
-    p2.run_host(f2, imgs, cfg, li2, lj2, nk2, nc2, chunk=chunk)
-    assert p2.totals() == want_tot
-    assert np.array_equal(nk, nk2) and np.array_equal(nc, nc2)
-    for p in range(6):
-        assert np.array_equal(li[p, :nk[p]], li2[p, :nk[p]]) and np.array_equal(lj[p, :nk[p]], lj2[p, :nk[p]]), p
+    ctx.pipeline_set(pipe)
+    try:
+        p2.run_host(f2, imgs, cfg, li2, lj2, nk2, nc2, chunk=chunk)
+        assert p2.totals() == want_tot
+        assert np.array_equal(nk, nk2) and np.array_equal(nc, nc2)
+        for p in range(6):
+            assert np.array_equal(li[p, :nk[p]], li2[p, :nk[p]]) and np.array_equal(lj[p, :nk[p]], lj2[p, :nk[p]]), p
+        # the resident call with the two-lane pipeline
+        p3 = ctx.pairs(6, 300)
+        p3.run(f, 0, 6, cfg)
+        assert p3.totals() == want_tot
+        li3, lj3 = np.zeros((6, 300, 2)), np.zeros((6, 300, 2))
+        nk3, nc3 = np.zeros(6, np.int32), np.zeros(6, np.int32)
+        p3.download_all(li3, lj3, nk3, nc3)
+        assert np.array_equal(nk, nk3) and np.array_equal(nc, nc3)
+        for p in range(6):
+            assert np.array_equal(li[p, :nk[p]], li3[p, :nk[p]]) and np.array_equal(lj[p, :nk[p]], lj3[p, :nk[p]]), p
+    finally:
+        ctx.pipeline_set(0)
 
 
 def test_errors_are_loud(ctx):
