@@ -319,7 +319,7 @@ static int pipe_reserve(sfmgpu_ctx* ctx, sfmgpu_frames* f, const sfmgpu_lkcfg* c
   const size_t wb = sfm_corner_work_bytes_md(f->w, f->h, sub < 1024 ? sub : 1024, cand_cap, md);
   SFM_TRY(sfm_reserve(ctx, out->work, wb));
   SFM_TRY(sfm_reserve(ctx, out->work2, wb));
-  const size_t db = ((size_t)sub * out->cap + 1) * sizeof(int);
+  const size_t db = 2 * ((size_t)sub * out->cap + 2) * sizeof(int);
   SFM_TRY(sfm_reserve(ctx, ctx->klt_defer, db));
   SFM_TRY(sfm_reserve(ctx, ctx->klt_defer2, db));
   return 0;

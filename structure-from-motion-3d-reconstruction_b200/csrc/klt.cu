@@ -295,6 +295,8 @@ int launch_r(sfmgpu_ctx* ctx, const KltLaunch& k, const int* list, const int* li
 
 // klt_lane.cu
 int sfm_klt_lane_launch(sfmgpu_ctx* ctx, const KltLaunch& k, int* defer_count, int* defer_list, int variant);
+int sfm_klt_lane_masked_launch(sfmgpu_ctx* ctx, const KltLaunch& k, const int* in_list, const int* in_count, int* defer_count,
+                               int* defer_list);
 
 // Batches of at least this many feature slots go to the lane-per-feature kernel (32 features per warp need many
 // features to fill 148 SMs); smaller ones (a single tracker step) keep one warp per feature.
@@ -309,13 +311,21 @@ int sfm_klt_launch(sfmgpu_ctx* ctx, const KltLaunch& k) {
   const int* list_count = nullptr;
   const int mode = ctx->klt_mode;  // 0 auto, 1 warp-per-feature only, 2 lane-per-feature (+ deferred) always, 10+v tuning variant v
   if (k.radius == 5 && total < (1ll << 31) && (mode >= 2 || (mode == 0 && total >= KLT_LANE_MIN))) {
-    SFM_TRY(sfm_reserve(ctx, ctx->klt_defer, (size_t)(total + 1) * sizeof(int)));
-    int* dcount = (int*)ctx->klt_defer.p;
-    int* dlist = dcount + 1;
-    SFM_CUDA(ctx, cudaMemsetAsync(dcount, 0, sizeof(int), ctx->stream));
-    SFM_TRY(sfm_klt_lane_launch(ctx, k, dcount, dlist, mode >= 10 ? mode - 10 : 0));
-    list = dlist;
-    list_count = dcount;
+    // chain: interior windows (lane kernel) -> border windows (masked lane kernel) -> the rest (warp-per-feature)
+    SFM_TRY(sfm_reserve(ctx, ctx->klt_defer, 2 * (size_t)(total + 2) * sizeof(int)));
+    int* dcount = (int*)ctx->klt_defer.p;  // [0] first list, [1] second list
+    int* dlist1 = dcount + 2;
+    int* dlist2 = dlist1 + total;
+    SFM_CUDA(ctx, cudaMemsetAsync(dcount, 0, 2 * sizeof(int), ctx->stream));
+    SFM_TRY(sfm_klt_lane_launch(ctx, k, dcount, dlist1, mode >= 10 ? mode - 10 : 0));
+    if (mode == 19) {  // tuning: skip the masked kernel
+      list = dlist1;
+      list_count = dcount;
+    } else {
+      SFM_TRY(sfm_klt_lane_masked_launch(ctx, k, dlist1, dcount, dcount + 1, dlist2));
+      list = dlist2;
+      list_count = dcount + 1;
+    }
   }
   if (k.radius == 5) return launch_r<5, true>(ctx, k, list, list_count);
   if (k.radius < 5) return launch_r<5, false>(ctx, k, list, list_count);

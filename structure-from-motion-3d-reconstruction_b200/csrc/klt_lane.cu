@@ -63,23 +63,30 @@ __device__ __forceinline__ void hlerp_row(const unsigned char* rowp, double fx, 
 // horizontal lerps of I1 row v, completes grid row v-1 of I1 into `snew`, and accumulates pixel row g = v-2 from
 // sold = S1[g-1], smid = S1[g], snew = S1[g+1] and S0[g] (I0 tap rows g = h0p and g+1 = tap row v-1).
 // ACC: accumulator sets (2 = even / odd columns: shorter dependent DFMA chains).
-template <int ACC>
-__device__ __forceinline__ void walk_row(const unsigned char* tile, int v, double fx, double fy, double (&h1p)[LNC], double (&h0p)[LNC],
-                                         const double (&sold)[LNC], const double (&smid)[LNC], double (&snew)[LNC],
-                                         double (&acc)[ACC][5]) {
+// MASKED: out-of-bounds rule of sample_bilinear (:188) - a sample whose tap pair leaves the image in x (bit i of cm
+// clear) or in y (bit of rm clear) is 0.0; cm / rm are per-lane masks over grid columns / rows.
+template <int ACC, bool MASKED>
+__device__ __forceinline__ void walk_row(const unsigned char* tile, int v, double fx, double fy, unsigned cm, unsigned rm,
+                                         double (&h1p)[LNC], double (&h0p)[LNC], const double (&sold)[LNC], const double (&smid)[LNC],
+                                         double (&snew)[LNC], double (&acc)[ACC][5]) {
   double px[LN];
   row_bytes(*reinterpret_cast<const uint4*>(tile + v * 16), px);
+  const unsigned cnew = MASKED ? (((rm >> (v - 1)) & 1u) ? cm : 0u) : 0u;  // grid row v-1
+  const unsigned cpix = MASKED ? (((rm >> (v - 2)) & 1u) ? cm : 0u) : 0u;  // grid row v-2 (the pixel row)
 #pragma unroll
   for (int i = 0; i < LNC; i++) {
     const double h = __fma_rn(fx, px[i + 1] - px[i], px[i]);
-    snew[i] = __fma_rn(fy, h - h1p[i], h1p[i]);  // grid row v-1 of I1
+    double sn = __fma_rn(fy, h - h1p[i], h1p[i]);  // grid row v-1 of I1
+    if (MASKED) sn = ((cnew >> i) & 1u) ? sn : 0.0;
+    snew[i] = sn;
     h1p[i] = h;
   }
   row_bytes(*reinterpret_cast<const uint4*>(tile + LIMG + (v - 1) * 16), px);
 #pragma unroll
   for (int i = 1; i <= LNC - 2; i++) {
     const double h = __fma_rn(fx, px[i + 1] - px[i], px[i]);
-    const double s0 = __fma_rn(fy, h - h0p[i], h0p[i]);
+    double s0 = __fma_rn(fy, h - h0p[i], h0p[i]);
+    if (MASKED) s0 = ((cpix >> i) & 1u) ? s0 : 0.0;
     h0p[i] = h;
     const double gx2 = smid[i + 1] - smid[i - 1];  // 2*Ix (:439)
     const double gy2 = snew[i] - sold[i];          // 2*Iy (:440)
@@ -100,9 +107,9 @@ __device__ __forceinline__ void walk_row(const unsigned char* tile, int v, doubl
 // groups of three rows (the three S1 row buffers rotate by argument order), so the hot code is ~16 KB and stays in
 // the 32 KB instruction cache.  Fully unrolled, the 14 rows are 53 KB and the kernel stalls on instruction fetch
 // (measured: 'no_instruction' was the top stall reason).  The 15th row of the last group does not exist and is skipped.
-template <int ACC>
-__device__ __forceinline__ void window_sums(const unsigned char* tile, double fx, double fy, double& a00, double& a01, double& a11,
-                                            double& b0, double& b1) {
+template <int ACC, bool MASKED>
+__device__ __forceinline__ void window_sums(const unsigned char* tile, double fx, double fy, unsigned cm, unsigned rm, double& a00,
+                                            double& a01, double& a11, double& b0, double& b1) {
   double h1p[LNC], h0p[LNC], s0[LNC], s1[LNC], s2[LNC], t[LNC];
   double acc[ACC][5];
 #pragma unroll
@@ -111,24 +118,27 @@ __device__ __forceinline__ void window_sums(const unsigned char* tile, double fx
     for (int q = 0; q < 5; q++) acc[j][q] = 0.0;
   hlerp_row<0, LNC>(tile, fx, h1p);  // I1 tap row 0
   hlerp_row<0, LNC>(tile + 16, fx, t);  // I1 tap row 1 -> grid row 0
+  const unsigned c0 = MASKED ? ((rm & 1u) ? cm : 0u) : 0u, c1 = MASKED ? ((rm & 2u) ? cm : 0u) : 0u;
 #pragma unroll
   for (int i = 0; i < LNC; i++) {
     s0[i] = __fma_rn(fy, t[i] - h1p[i], h1p[i]);
+    if (MASKED) s0[i] = ((c0 >> i) & 1u) ? s0[i] : 0.0;
     h1p[i] = t[i];
   }
   hlerp_row<0, LNC>(tile + 32, fx, t);  // I1 tap row 2 -> grid row 1
 #pragma unroll
   for (int i = 0; i < LNC; i++) {
     s1[i] = __fma_rn(fy, t[i] - h1p[i], h1p[i]);
+    if (MASKED) s1[i] = ((c1 >> i) & 1u) ? s1[i] : 0.0;
     h1p[i] = t[i];
   }
   hlerp_row<1, LNC - 1>(tile + LIMG + 16, fx, h0p);  // I0 tap row 1
   // step v writes grid row v-1 into buffer (v-1) % 3 and reads grid rows v-3, v-2 from the other two
 #pragma unroll 1
   for (int v = 3; v < LN; v += 3) {
-    walk_row<ACC>(tile, v, fx, fy, h1p, h0p, s0, s1, s2, acc);      // writes s2
-    walk_row<ACC>(tile, v + 1, fx, fy, h1p, h0p, s1, s2, s0, acc);  // writes s0
-    if (v + 2 < LN) walk_row<ACC>(tile, v + 2, fx, fy, h1p, h0p, s2, s0, s1, acc);  // writes s1
+    walk_row<ACC, MASKED>(tile, v, fx, fy, cm, rm, h1p, h0p, s0, s1, s2, acc);      // writes s2
+    walk_row<ACC, MASKED>(tile, v + 1, fx, fy, cm, rm, h1p, h0p, s1, s2, s0, acc);  // writes s0
+    if (v + 2 < LN) walk_row<ACC, MASKED>(tile, v + 2, fx, fy, cm, rm, h1p, h0p, s2, s0, s1, acc);  // writes s1
   }
   a00 = acc[0][0]; a01 = acc[0][1]; a11 = acc[0][2]; b0 = acc[0][3]; b1 = acc[0][4];
 #pragma unroll
@@ -144,14 +154,25 @@ struct StageRegs {
   uint4 lo, hi;
 };
 
+// CLAMP (border windows): rows are clamped to the image and each 16-byte chunk to the row's allocation; a chunk that
+// had to move only ever held taps outside the image, whose samples the masks zero (pitch is a multiple of 16, so a
+// chunk lies either entirely inside [0, pitch) or entirely outside).
+template <bool CLAMP>
 __device__ __forceinline__ void stage_load(StageRegs& r, const uint8_t* __restrict__ imgA, const uint8_t* __restrict__ imgB, int pitch,
-                                           int x0, int y0, int lane) {
+                                           int h, int x0, int y0, int lane) {
   const int img = lane >= LN ? 1 : 0, row = lane - img * LN;
-  const uint8_t* rowp = (img ? imgA : imgB) + (size_t)(y0 + row) * pitch;  // tile order: I1 (= image B) first
+  int y = y0 + row;
+  if (CLAMP) y = y < 0 ? 0 : (y > h - 1 ? h - 1 : y);
+  const uint8_t* rowp = (img ? imgA : imgB) + (size_t)y * pitch;  // tile order: I1 (= image B) first
   const int xa = x0 & ~15, o = x0 & 15;
-  r.lo = __ldg(reinterpret_cast<const uint4*>(rowp + xa));
+  int c0 = xa, c1 = xa + 16;
+  if (CLAMP) {
+    c0 = c0 < 0 ? 0 : (c0 > pitch - 16 ? pitch - 16 : c0);
+    c1 = c1 < 0 ? 0 : (c1 > pitch - 16 ? pitch - 16 : c1);
+  }
+  r.lo = __ldg(reinterpret_cast<const uint4*>(rowp + c0));
   r.hi = make_uint4(0, 0, 0, 0);
-  if (o > 2) r.hi = __ldg(reinterpret_cast<const uint4*>(rowp + xa + 16));  // needed bytes reach the next chunk
+  if (o > 2) r.hi = __ldg(reinterpret_cast<const uint4*>(rowp + c1));  // needed bytes reach the next chunk
 }
 
 __device__ __forceinline__ void stage_store(const StageRegs& r, unsigned char* tile_s, int x0, int lane) {
@@ -168,15 +189,26 @@ __device__ __forceinline__ void stage_store(const StageRegs& r, unsigned char* t
   *reinterpret_cast<uint4*>(tile_s + img * LIMG + row * 16) = out;
 }
 
-template <int ACC, int MINB, int LSTAGE>
-__global__ void __launch_bounds__(32 * LWARPS, MINB) klt_lane_kernel(KltLaunch k, int* __restrict__ defer_count, int* __restrict__ defer_list) {
+// MASKED = false: slots of the launch, interior windows only; everything else goes to defer_list.
+// MASKED = true : walks in_list (the first kernel's deferred features) with the out-of-bounds rule applied through
+//                 masks; what it still cannot do exactly (non-finite positions, a fractional part so close to 1 that
+//                 the reference's own floor(fl(x + dx)) may land on the next integer, degenerate level sizes) is
+//                 deferred once more, to the warp-per-feature kernel of klt.cu.
+template <int ACC, int MINB, int LSTAGE, bool MASKED>
+__global__ void __launch_bounds__(32 * LWARPS, MINB) klt_lane_kernel(KltLaunch k, const int* __restrict__ in_list,
+                                                                     const int* __restrict__ in_count, int* __restrict__ defer_count,
+                                                                     int* __restrict__ defer_list) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const unsigned FULL = 0xffffffffu;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* wtile = smem_raw + (size_t)warp * 32 * LSTRIDE;
   unsigned char* tile = wtile + lane * LSTRIDE;
   const long long total = (long long)k.npairs * k.cap;
-  const long long g = ((long long)blockIdx.x * LWARPS + warp) * 32 + lane;
+  const long long nwork = MASKED ? (long long)*in_count : total;
+  for (long long wbase = ((long long)blockIdx.x * LWARPS + warp) * 32; wbase < nwork; wbase += (long long)gridDim.x * LWARPS * 32) {
+  const long long widx = wbase + lane;
+  long long g = widx;
+  if (MASKED) g = widx < nwork ? (long long)in_list[widx] : total;
   const int pair = g < total ? (int)(g / k.cap) : 0;
   const int slot = (int)(g - (long long)pair * k.cap);
   const bool valid = g < total && (!k.counts || slot < k.counts[pair]);
@@ -203,14 +235,29 @@ __global__ void __launch_bounds__(32 * LWARPS, MINB) klt_lane_kernel(KltLaunch k
         const double x = plx + dlx, y = ply + dly;
         const double fxx = floor(x), fyy = floor(y);
         int FX = 0, FY = 0;
+        unsigned cm = 0, rm = 0;
         bool act = !done;
         if (act) {
           const bool finite_ok = (fabs(fxx) < 1.0e9) && (fabs(fyy) < 1.0e9);
           FX = finite_ok ? (int)fxx : 0;
           FY = finite_ok ? (int)fyy : 0;
-          const bool interior =
-              finite_ok && FX - LR - 1 >= 0 && FX + LR + 3 <= w - 1 && FY - LR - 1 >= 0 && FY + LR + 3 <= h - 1;
-          if (!interior) {  // border / non-finite: the exact kernel redoes this feature
+          bool ok;
+          if (!MASKED) {
+            ok = finite_ok && FX - LR - 1 >= 0 && FX + LR + 3 <= w - 1 && FY - LR - 1 >= 0 && FY + LR + 3 <= h - 1;
+          } else {
+            const double lim = 1.0 - 5.9604644775390625e-8;  // 1 - 2^-24 >> the ulp of any x + dx: the floors agree below it
+            ok = finite_ok && w >= 16 && h >= 16 && (x - fxx) <= lim && (y - fyy) <= lim;
+            if (ok) {
+              // grid column i / row j uses taps FX + i - r - 1 (+1): inside iff 0 <= tap <= w - 2
+#pragma unroll
+              for (int i = 0; i < LNC; i++) {
+                const int cx = FX + i - LR - 1, cy = FY + i - LR - 1;
+                cm |= (cx >= 0 && cx <= w - 2) ? (1u << i) : 0u;
+                rm |= (cy >= 0 && cy <= h - 2) ? (1u << i) : 0u;
+              }
+            }
+          }
+          if (!ok) {  // the next kernel in the chain redoes this feature from scratch
             alive = false;
             done = true;
             act = false;
@@ -232,8 +279,8 @@ __global__ void __launch_bounds__(32 * LWARPS, MINB) klt_lane_kernel(KltLaunch k
               const int sA = k.fa0 + spair * k.fa_step, sB = k.fb0 + spair * k.fb_step;
               sx0[j] = sFX - LR - 1;
               if (ss[j] >= 0 && lane < 2 * LN)
-                stage_load(sr[j], lbase + (size_t)(dir ? sB : sA) * fstride, lbase + (size_t)(dir ? sA : sB) * fstride, pitch, sx0[j],
-                           sFY - LR - 1, lane);
+                stage_load<MASKED>(sr[j], lbase + (size_t)(dir ? sB : sA) * fstride, lbase + (size_t)(dir ? sA : sB) * fstride, pitch, h,
+                                   sx0[j], sFY - LR - 1, lane);
             }
 #pragma unroll
             for (int j = 0; j < LSTAGE; j++)
@@ -245,7 +292,7 @@ __global__ void __launch_bounds__(32 * LWARPS, MINB) klt_lane_kernel(KltLaunch k
           tFX = FX;
           tFY = FY;
           double a00, a01, a11, b0, b1;
-          window_sums<ACC>(tile, x - fxx, y - fyy, a00, a01, a11, b0, b1);
+          window_sums<ACC, MASKED>(tile, x - fxx, y - fyy, cm, rm, a00, a01, a11, b0, b1);
           double sx = 0.0, sy = 0.0;
           const double det = a00 * a11 - a01 * a01;
           if (!(fabs(det) < 16.0 * 1e-9)) {  // |det| < 1e-9 of :452 on the 16x scaled determinant
@@ -285,33 +332,46 @@ __global__ void __launch_bounds__(32 * LWARPS, MINB) klt_lane_kernel(KltLaunch k
     base = __shfl_sync(FULL, base, 0);
     if (valid && !alive) defer_list[base + __popc(dm & ((1u << lane) - 1u))] = (int)g;
   }
+  __syncwarp();
+  }
 }
 
 }  // namespace
 
-template <int ACC, int MINB, int LSTAGE>
-static int lane_launch(sfmgpu_ctx* ctx, const KltLaunch& k, int* defer_count, int* defer_list) {
+template <int ACC, int MINB, int LSTAGE, bool MASKED>
+static int lane_launch(sfmgpu_ctx* ctx, const KltLaunch& k, const int* in_list, const int* in_count, int* defer_count, int* defer_list) {
   const size_t smem = (size_t)LWARPS * 32 * LSTRIDE;
   static bool configured = false;
   if (!configured) {
-    SFM_CUDA(ctx, cudaFuncSetAttribute(klt_lane_kernel<ACC, MINB, LSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SFM_CUDA(ctx, cudaFuncSetAttribute(klt_lane_kernel<ACC, MINB, LSTAGE, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
     configured = true;
   }
   const long long total = (long long)k.npairs * k.cap;
   if (total == 0) return 0;
-  const unsigned grid = sfm_cdiv(total, 32 * LWARPS);
-  SFM_LAUNCH(ctx, (klt_lane_kernel<ACC, MINB, LSTAGE>), grid, 32 * LWARPS, smem, k, defer_count, defer_list);
+  unsigned grid = sfm_cdiv(total, 32 * LWARPS);
+  if (MASKED) {  // a few % of the batch: a resident grid walks the list
+    const unsigned cap = (unsigned)ctx->n_sm * 8;
+    grid = grid < cap ? grid : cap;
+  }
+  SFM_LAUNCH(ctx, (klt_lane_kernel<ACC, MINB, LSTAGE, MASKED>), grid, 32 * LWARPS, smem, k, in_list, in_count, defer_count, defer_list);
   return 0;
 }
 
-// Runs the lane kernel over all slots; features it cannot handle are appended to defer_list (device), count in
-// *defer_count (device, must be zeroed by the caller on the same stream).  variant: tuning builds (A/B runs).
+// Interior windows of every slot; features it cannot handle are appended to defer_list (device), count in
+// *defer_count (device, zeroed by the caller on the same stream).  variant: tuning builds (A/B runs).
 int sfm_klt_lane_launch(sfmgpu_ctx* ctx, const KltLaunch& k, int* defer_count, int* defer_list, int variant) {
   // Measured on B200, C2 shape (scripts/klt_ab.py, KLT stage incl. the deferred pass, 238k tracks): <1,12,4> 4.43 ms
   // (168 registers, spills), <1,8,4> 3.57 ms, <2,8,4> 3.66 ms, <2,8,8> 3.97 ms: the schedule wants registers, not warps.
   switch (variant) {
-    case 1: return lane_launch<1, 12, 4>(ctx, k, defer_count, defer_list);
-    case 2: return lane_launch<2, 8, 4>(ctx, k, defer_count, defer_list);
-    default: return lane_launch<1, 8, 4>(ctx, k, defer_count, defer_list);
+    case 1: return lane_launch<1, 12, 4, false>(ctx, k, nullptr, nullptr, defer_count, defer_list);
+    case 2: return lane_launch<2, 8, 4, false>(ctx, k, nullptr, nullptr, defer_count, defer_list);
+    default: return lane_launch<1, 8, 4, false>(ctx, k, nullptr, nullptr, defer_count, defer_list);
   }
+}
+
+// Border windows: the features of in_list with the out-of-bounds rule as masks; the rest goes to defer_list.
+int sfm_klt_lane_masked_launch(sfmgpu_ctx* ctx, const KltLaunch& k, const int* in_list, const int* in_count, int* defer_count,
+                               int* defer_list) {
+  return lane_launch<1, 8, 4, true>(ctx, k, in_list, in_count, defer_count, defer_list);
 }
