@@ -130,10 +130,10 @@ int sfmgpu_pairs_create(sfmgpu_ctx* ctx, int max_pairs, int max_corners, sfmgpu_
 void sfmgpu_pairs_destroy(sfmgpu_ctx* ctx, sfmgpu_pairs* p);
 int sfmgpu_pair_frontend(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int npairs, const sfmgpu_lkcfg* cfg,
                          sfmgpu_pairs* out);
-/* pairs_per_chunk > 0: batches of at least 2*pairs_per_chunk pairs are cut into sub-chunks that alternate between two
- * compute streams, so the latency-bound corner selection of one sub-chunk overlaps the score / KLT kernels of the
- * other (results are identical).  Default 0: resident batches run on one stream, stages back to back (measured
- * faster); the host-streaming call alternates the two lanes per upload chunk. */
+/* Stage pipeline: with pairs_per_chunk > 0, a resident batch of at least 2*pairs_per_chunk pairs is cut into chunks
+ * that flow through three streams (score -> select on a high-priority stream -> KLT), so the latency-bound corner
+ * selection of one chunk shares the SMs with the score / KLT kernels of its neighbours (results are identical).
+ * 0 (default) = one stream, stages back to back.  The host-streaming call below always pipelines per upload chunk. */
 int sfmgpu_pipeline_set(sfmgpu_ctx* ctx, int pairs_per_chunk);
 /* Streaming variant for frames that live in HOST memory (pinned for full speed; nframes images of w*h bytes, stride
  * w).  Frames [0, nframes) of `f` are overwritten; pairs (k, k+1), k < nframes-1.  The upload of chunk c+1 overlaps

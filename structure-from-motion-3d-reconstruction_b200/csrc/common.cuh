@@ -49,15 +49,15 @@ struct sfmgpu_ctx {
   int n_sm = SFM_NSM_FALLBACK;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr, back_stream = nullptr;  // H2D / D2H legs of the streaming front end
-  cudaStream_t aux_stream = nullptr;  // second compute lane of the chunk pipeline (frontend.cu)
-  int pipe_chunk = 0;                 // resident batches: pairs per sub-chunk of the two-lane pipeline, 0 = sequential
+  cudaStream_t sel_stream = nullptr, klt_stream = nullptr;  // stage streams of the chunk pipeline (frontend.cu)
+  int pipe_chunk = 0;                 // resident batches: pairs per chunk of the stage pipeline, 0 = sequential
   std::vector<cudaEvent_t> pipe_evs;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
   long long launches = 0;
   // scratch, grown on demand (never shrunk)
   DevBuf flush;
-  DevBuf klt_in, klt_p1, klt_pb, klt_nit, klt_keep, klt_defer, klt_defer2;
+  DevBuf klt_in, klt_p1, klt_pb, klt_nit, klt_keep, klt_defer;
   int klt_mode = 0;  // 0 auto, 1 warp-per-feature, 2 lane-per-feature (tests / profiling)
   DevBuf cs_work;    // corner-score work area for single-frame calls
   DevBuf sel_work;   // corner-select work area
@@ -144,6 +144,10 @@ size_t sfm_corner_work_bytes_md(int w, int h, int nframes, int cand_cap, int min
 // out_n[count].  cand_cap = per-frame candidate capacity (overflow -> E_CAPACITY, reported via status word).
 int sfm_corners_batch(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first, int count, int max_corners, double quality,
                       int min_dist, int cand_cap, void* work, size_t work_bytes, double2* out_xy, int* out_n);
+int sfm_corners_score_stage(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first, int count, double quality, int min_dist, int cand_cap,
+                            void* work, size_t work_bytes);
+int sfm_corners_select_stage(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int count, int max_corners, int min_dist, int cand_cap, void* work,
+                             size_t work_bytes, double2* out_xy, int* out_n);
 int sfm_candidates_single(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int frame, double quality, int32_t* xy,
                           double* score, int cap, int* n_out, double* max_score);
 int sfm_sort_perm(sfmgpu_ctx* ctx, const double* keys, int n, int32_t* perm);

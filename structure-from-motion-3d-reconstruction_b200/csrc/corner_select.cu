@@ -28,7 +28,11 @@ namespace {
 constexpr int SEL_THREADS = 256;          // small blocks: several frames resident per SM hide the serial latencies
 constexpr int SEL_WARPS = SEL_THREADS / 32;
 constexpr int EPT = 4;                    // elements per thread / lane and pass
-constexpr int SMALL = 2048;               // segments up to this size are sorted by one warp
+// Measured on B200 (C2, 999 frames, select stage): SMALL/WINDOW 2048/8192 15.4 ms, 1024/8192 14.8, 512/8192 15.0,
+// 4096/8192 17.8, 2048/4096 17.1, 2048/16384 15.0.  (Also tried and dropped: 128-thread blocks x 8 per SM: 14.5 ms
+// resident but slower per launch; 16 candidates per thread in the selection rounds: 17.8 ms; staging segments <= 256
+// in shared memory with one-lane sequential finishing: 17.1 ms.)
+constexpr int SMALL = 1024;               // segments up to this size are sorted by one warp
 constexpr int WINDOW = 8192;              // the sorted prefix is extended in windows of about this many elements
 constexpr int CHUNK = SEL_THREADS * EPT;  // candidates examined per selection round
 constexpr int ALIVE_CAP = SEL_THREADS;    // survivors resolved per selection round

@@ -86,7 +86,7 @@ void sfmgpu_destroy(sfmgpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->flush,  &ctx->klt_in, &ctx->klt_p1, &ctx->klt_pb,    &ctx->klt_nit, &ctx->klt_keep, &ctx->klt_defer, &ctx->klt_defer2, &ctx->cs_work,
+  DevBuf* bufs[] = {&ctx->flush,  &ctx->klt_in, &ctx->klt_p1, &ctx->klt_pb,    &ctx->klt_nit, &ctx->klt_keep, &ctx->klt_defer, &ctx->cs_work,
                     &ctx->sel_work, &ctx->misc,   &ctx->rs_xi,  &ctx->rs_xj,     &ctx->rs_E,    &ctx->rs_counts, &ctx->rs_inl,
                     &ctx->rs_best};
   for (DevBuf* b : bufs)
@@ -95,7 +95,8 @@ void sfmgpu_destroy(sfmgpu_ctx* ctx) {
   for (cudaEvent_t e : ctx->pipe_evs) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->back_stream) cudaStreamDestroy(ctx->back_stream);
-  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+  if (ctx->sel_stream) cudaStreamDestroy(ctx->sel_stream);
+  if (ctx->klt_stream) cudaStreamDestroy(ctx->klt_stream);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);

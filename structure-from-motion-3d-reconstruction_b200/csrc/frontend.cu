@@ -2,7 +2,10 @@
 //   * the stateless two-view front end (cpp/src/templering_sfm.cpp:1836-1857), batched over frame pairs;
 //   * the stateful KLTTracker (:323-391): reset / step / tracks, with the replenish rule (:374-389).
 // Everything stays on the device between stages; only survivors / counts are copied back when the caller asks.
+#include <stdlib.h>
+
 #include <utility>
+#include <vector>
 
 #include "common.cuh"
 
@@ -181,7 +184,7 @@ struct sfmgpu_pairs {
   int *ncorn = nullptr, *nkept = nullptr, *nit = nullptr;
   uint8_t* keep = nullptr;
   unsigned long long* totals = nullptr;
-  DevBuf work, work2;  // corner work areas of the two compute lanes
+  DevBuf work[2];  // corner work areas (two, so that the stage pipeline can score one chunk while it selects another)
   int last_npairs = 0;
 };
 
@@ -218,42 +221,50 @@ int sfmgpu_pairs_create(sfmgpu_ctx* ctx, int max_pairs, int max_corners, sfmgpu_
 void sfmgpu_pairs_destroy(sfmgpu_ctx* ctx, sfmgpu_pairs* p) {
   if (!p) return;
   if (ctx) cudaStreamSynchronize(ctx->stream);
-  void* ptrs[] = {p->xy0, p->p1, p->pb, p->li, p->lj, p->nit, p->keep, p->ncorn, p->nkept, p->totals, p->work.p, p->work2.p};
+  void* ptrs[] = {p->xy0, p->p1, p->pb, p->li, p->lj, p->nit, p->keep, p->ncorn, p->nkept, p->totals, p->work[0].p, p->work[1].p};
   for (void* q : ptrs)
     if (q) cudaFree(q);
   delete p;
 }
 
-// Pairs (first_frame + k, first_frame + k + 1), k < npairs, written to slots [pair_off, pair_off + npairs) of `out`
-// on the context stream; totals are accumulated (the caller zeroes them).
-static int pair_range(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int pair_off, int npairs, const sfmgpu_lkcfg* cfg,
-                      sfmgpu_pairs* out, DevBuf& work) {
-  if (npairs == 0) return 0;
-  // corners, in chunks of frames that bound the work area
-  const int cand_cap = default_cand_cap(f->w, f->h);
-  const int md = cfg->min_distance < 0 ? -cfg->min_distance : cfg->min_distance;
-  int chunk = npairs < 1024 ? npairs : 1024;  // frames per corner launch: >= 4 blocks per SM keeps the select kernel busy
-  const size_t wb = sfm_corner_work_bytes_md(f->w, f->h, chunk, cand_cap, md);
-  SFM_TRY(sfm_reserve(ctx, work, wb));
-  const size_t so = (size_t)pair_off * out->cap;
-  for (int c0 = 0; c0 < npairs; c0 += chunk) {
-    const int cnt = npairs - c0 < chunk ? npairs - c0 : chunk;
-    SFM_TRY(sfm_corners_batch(ctx, f, first_frame + c0, cnt, cfg->max_tracks, cfg->quality, cfg->min_distance, cand_cap,
-                              work.p, work.cap, out->xy0 + so + (size_t)c0 * out->cap, out->ncorn + pair_off + c0));
-  }
+// ---- the three stages of a chunk of pairs --------------------------------------------------------------------------
+// Pairs (first_frame + k, first_frame + k + 1), k < npairs, go to slots [pair_off, pair_off + npairs) of `out`;
+// totals are accumulated (the caller zeroes them).  A chunk is at most 1024 frames (the corner work area).
+struct ChunkArgs {
+  sfmgpu_frames* f;
+  int first_frame, pair_off, npairs;
+  const sfmgpu_lkcfg* cfg;
+  sfmgpu_pairs* out;
+  DevBuf* work;
+  int cand_cap, md;
+};
+
+static int stage_score(sfmgpu_ctx* ctx, const ChunkArgs& c) {
+  return sfm_corners_score_stage(ctx, c.f, c.first_frame, c.npairs, c.cfg->quality, c.md, c.cand_cap, c.work->p, c.work->cap);
+}
+
+static int stage_select(sfmgpu_ctx* ctx, const ChunkArgs& c) {
+  const size_t so = (size_t)c.pair_off * c.out->cap;
+  return sfm_corners_select_stage(ctx, c.f, c.npairs, c.cfg->max_tracks, c.md, c.cand_cap, c.work->p, c.work->cap, c.out->xy0 + so,
+                                  c.out->ncorn + c.pair_off);
+}
+
+static int stage_klt(sfmgpu_ctx* ctx, const ChunkArgs& c) {
+  sfmgpu_pairs* out = c.out;
+  const size_t so = (size_t)c.pair_off * out->cap;
   KltLaunch k;
-  k.pv = f->view();
+  k.pv = c.f->view();
   k.p0 = out->xy0 + so;
-  k.counts = out->ncorn + pair_off;
-  k.npairs = npairs;
+  k.counts = out->ncorn + c.pair_off;
+  k.npairs = c.npairs;
   k.cap = out->cap;
-  k.fa0 = first_frame;
+  k.fa0 = c.first_frame;
   k.fa_step = 1;
-  k.fb0 = first_frame + 1;
+  k.fb0 = c.first_frame + 1;
   k.fb_step = 1;
-  k.radius = cfg->win_radius;
-  k.iters = cfg->iters;
-  k.fb_thresh = cfg->fb_thresh;
+  k.radius = c.cfg->win_radius;
+  k.iters = c.cfg->iters;
+  k.fb_thresh = c.cfg->fb_thresh;
   k.p1 = out->p1 + so;
   k.pb = out->pb + so;
   k.nit = out->nit + so;
@@ -263,37 +274,57 @@ static int pair_range(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int pa
     SFM_TRY(sfm_klt_launch(ctx, k));
   }
   StageTimer st(ctx, 3);
-  SFM_LAUNCH(ctx, compact_kernel, npairs, 1024, 0, out->xy0 + so, out->p1 + so, out->keep + so, (const int*)nullptr,
-             out->ncorn + pair_off, out->cap, out->li + so, out->lj + so, (int*)nullptr, out->nkept + pair_off);
-  SFM_LAUNCH(ctx, totals_kernel, 256, 256, 0, out->ncorn + pair_off, out->nkept + pair_off, out->nit + so, npairs, out->cap,
+  SFM_LAUNCH(ctx, compact_kernel, c.npairs, 1024, 0, out->xy0 + so, out->p1 + so, out->keep + so, (const int*)nullptr,
+             out->ncorn + c.pair_off, out->cap, out->li + so, out->lj + so, (int*)nullptr, out->nkept + c.pair_off);
+  SFM_LAUNCH(ctx, totals_kernel, 256, 256, 0, out->ncorn + c.pair_off, out->nkept + c.pair_off, out->nit + so, c.npairs, out->cap,
              out->totals);
   return 0;
 }
 
-// ---- two-lane chunk pipeline ---------------------------------------------------------------------------------------
-// Sub-chunks of pairs can alternate between two compute streams (each with its own corner work area and KLT scratch),
-// so that the latency-bound corner-select blocks of one sub-chunk share the SMs with the score / KLT blocks of the
-// other.  Results are identical to the sequential order (sub-chunks are independent).  Measured on B200 (C2, 999
-// pairs): for a RESIDENT batch it loses (58.8 ms sequential vs 60.9 / 64.3 / 67.7 / 84.7 ms at 256 / 192 / 128 / 64
-// pairs per sub-chunk: a later kernel's blocks are only dispatched once the earlier kernel has none pending, and every
-// select launch pays its ~4.8 ms latency), so it is off by default there; the HOST-streaming call uses the two lanes
-// at upload-chunk granularity, where it wins (91 -> 77 ms end to end).
-struct LaneScope {  // run a piece of work on lane `l`: swaps the context's stream and per-stream scratch
+static ChunkArgs chunk_args(sfmgpu_frames* f, int first_frame, int pair_off, int npairs, const sfmgpu_lkcfg* cfg, sfmgpu_pairs* out,
+                            DevBuf* work) {
+  ChunkArgs c;
+  c.f = f;
+  c.first_frame = first_frame;
+  c.pair_off = pair_off;
+  c.npairs = npairs;
+  c.cfg = cfg;
+  c.out = out;
+  c.work = work;
+  c.cand_cap = default_cand_cap(f->w, f->h);
+  c.md = cfg->min_distance < 0 ? -cfg->min_distance : cfg->min_distance;
+  return c;
+}
+
+// Everything back to back on the context stream (chunks of <= 1024 frames).
+static int pair_range(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int pair_off, int npairs, const sfmgpu_lkcfg* cfg,
+                      sfmgpu_pairs* out) {
+  if (npairs == 0) return 0;
+  const int chunk = npairs < 1024 ? npairs : 1024;  // frames per corner launch: >= 4 blocks per SM keeps the select kernel busy
+  ChunkArgs c0 = chunk_args(f, first_frame, pair_off, chunk, cfg, out, &out->work[0]);
+  SFM_TRY(sfm_reserve(ctx, out->work[0], sfm_corner_work_bytes_md(f->w, f->h, chunk, c0.cand_cap, c0.md)));
+  for (int p = 0; p < npairs; p += chunk) {
+    const int cnt = npairs - p < chunk ? npairs - p : chunk;
+    ChunkArgs c = chunk_args(f, first_frame + p, pair_off + p, cnt, cfg, out, &out->work[0]);
+    SFM_TRY(stage_score(ctx, c));
+    SFM_TRY(stage_select(ctx, c));
+    SFM_TRY(stage_klt(ctx, c));
+  }
+  return 0;
+}
+
+// ---- stage pipeline over chunks -------------------------------------------------------------------------------------
+// The corner-select kernel is latency bound: one block per frame walks the introsort tree and the greedy selection,
+// ~4.8 ms for a launch no matter how few frames it holds, at a fraction of the SM's issue rate.  Chunks of pairs
+// therefore flow through three streams, one per stage: score (context stream) -> select (HIGH-priority stream: its
+// few blocks are placed as soon as they are ready) -> KLT + compaction.  select(c) then shares the SMs with
+// score(c+1) and KLT(c-1).  Two corner work areas alternate; score(c+2) waits for select(c).  Results are identical
+// to the sequential order (chunks are independent).
+struct StageScope {  // run a piece of work on another stream: SFM_LAUNCH and friends use ctx->stream
   sfmgpu_ctx* ctx;
-  int lane;
   cudaStream_t saved;
-  LaneScope(sfmgpu_ctx* c, int l) : ctx(c), lane(l), saved(c->stream) {
-    if (l) {
-      c->stream = c->aux_stream;
-      std::swap(c->klt_defer, c->klt_defer2);
-    }
-  }
-  ~LaneScope() {
-    if (lane) {
-      ctx->stream = saved;
-      std::swap(ctx->klt_defer, ctx->klt_defer2);
-    }
-  }
+  StageScope(sfmgpu_ctx* c, cudaStream_t s) : ctx(c), saved(c->stream) { c->stream = s; }
+  ~StageScope() { ctx->stream = saved; }
 };
 
 static cudaEvent_t pipe_event(sfmgpu_ctx* ctx, size_t i) {
@@ -306,22 +337,93 @@ static cudaEvent_t pipe_event(sfmgpu_ctx* ctx, size_t i) {
 }
 
 static int pipe_streams(sfmgpu_ctx* ctx) {
-  if (!ctx->aux_stream) SFM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
-  if (!ctx->copy_stream) SFM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-  if (!ctx->back_stream) SFM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->back_stream, cudaStreamNonBlocking));
+  if (!ctx->sel_stream) {
+    int lo = 0, hi = 0;
+    SFM_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = numerically lowest = greatest priority
+    SFM_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->sel_stream, cudaStreamNonBlocking, hi));
+    SFM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->klt_stream, cudaStreamNonBlocking));
+    SFM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    SFM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->back_stream, cudaStreamNonBlocking));
+  }
   return 0;
 }
 
-// Scratch of both lanes is sized before any work is queued (growing a buffer frees and reallocates it).
-static int pipe_reserve(sfmgpu_ctx* ctx, sfmgpu_frames* f, const sfmgpu_lkcfg* cfg, sfmgpu_pairs* out, int sub) {
-  const int cand_cap = default_cand_cap(f->w, f->h);
-  const int md = cfg->min_distance < 0 ? -cfg->min_distance : cfg->min_distance;
-  const size_t wb = sfm_corner_work_bytes_md(f->w, f->h, sub < 1024 ? sub : 1024, cand_cap, md);
-  SFM_TRY(sfm_reserve(ctx, out->work, wb));
-  SFM_TRY(sfm_reserve(ctx, out->work2, wb));
-  const size_t db = 2 * ((size_t)sub * out->cap + 2) * sizeof(int);
-  SFM_TRY(sfm_reserve(ctx, ctx->klt_defer, db));
-  SFM_TRY(sfm_reserve(ctx, ctx->klt_defer2, db));
+// Scratch is sized before any work is queued (growing a buffer frees and reallocates it).
+static int pipe_reserve(sfmgpu_ctx* ctx, sfmgpu_frames* f, const sfmgpu_lkcfg* cfg, sfmgpu_pairs* out, int chunk) {
+  const ChunkArgs c = chunk_args(f, 0, 0, chunk, cfg, out, nullptr);
+  const size_t wb = sfm_corner_work_bytes_md(f->w, f->h, chunk, c.cand_cap, c.md);
+  SFM_TRY(sfm_reserve(ctx, out->work[0], wb));
+  SFM_TRY(sfm_reserve(ctx, out->work[1], wb));
+  SFM_TRY(sfm_reserve(ctx, ctx->klt_defer, 2 * ((size_t)chunk * out->cap + 2) * sizeof(int)));
+  return 0;
+}
+
+// Pipeline state of one call: event indices are handed out sequentially from ctx->pipe_evs.
+struct Pipe {
+  sfmgpu_ctx* ctx;
+  size_t ev = 0;
+  int nchunk = 0;
+  cudaEvent_t sel_done[2] = {nullptr, nullptr};  // select of the chunk that last used work area 0 / 1
+  cudaEvent_t next() { return pipe_event(ctx, ev++); }
+  // SFMGPU_PIPE_TRACE=1: timestamps around every stage of every chunk, printed by trace_dump() (diagnostics only)
+  bool trace = getenv("SFMGPU_PIPE_TRACE") != nullptr;
+  std::vector<cudaEvent_t> tev;
+  cudaEvent_t t0 = nullptr;
+  void mark(cudaStream_t s) {
+    if (!trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    tev.push_back(e);
+  }
+  void trace_dump() {
+    if (!trace || tev.empty()) return;
+    static const char* nm[3] = {"score", "select", "klt"};
+    for (size_t i = 0; i + 1 < tev.size(); i += 2) {
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, tev[0], tev[i]);
+      cudaEventElapsedTime(&b, tev[0], tev[i + 1]);
+      fprintf(stderr, "[pipe] chunk %zu %-6s %8.3f -> %8.3f ms\n", i / 6, nm[(i / 2) % 3], a, b);
+    }
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    tev.clear();
+  }
+};
+
+// Queue one chunk: score on the context stream (after `ready`, if given), select on the priority stream, KLT on its
+// stream; *done (if given) is recorded behind the chunk's last kernel.
+static int pipe_chunk(Pipe& p, sfmgpu_frames* f, int first_frame, int pair_off, int npairs, const sfmgpu_lkcfg* cfg, sfmgpu_pairs* out,
+                      cudaEvent_t ready, cudaEvent_t* done) {
+  sfmgpu_ctx* ctx = p.ctx;
+  const int wa = p.nchunk & 1;
+  p.nchunk++;
+  ChunkArgs c = chunk_args(f, first_frame, pair_off, npairs, cfg, out, &out->work[wa]);
+  cudaEvent_t e_score = p.next(), e_sel = p.next(), e_done = p.next();
+  if (!e_score || !e_sel || !e_done) return sfm_fail(ctx, SFMGPU_E_CUDA, "pair_frontend: cudaEventCreate failed");
+  if (ready) SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ready, 0));
+  if (p.sel_done[wa]) SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p.sel_done[wa], 0));  // work area free again
+  p.mark(ctx->stream);
+  SFM_TRY(stage_score(ctx, c));
+  p.mark(ctx->stream);
+  SFM_CUDA(ctx, cudaEventRecord(e_score, ctx->stream));
+  {
+    StageScope sc(ctx, ctx->sel_stream);
+    SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, e_score, 0));
+    p.mark(ctx->stream);
+    SFM_TRY(stage_select(ctx, c));
+    p.mark(ctx->stream);
+    SFM_CUDA(ctx, cudaEventRecord(e_sel, ctx->stream));
+  }
+  p.sel_done[wa] = e_sel;
+  {
+    StageScope sc(ctx, ctx->klt_stream);
+    SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, e_sel, 0));
+    p.mark(ctx->stream);
+    SFM_TRY(stage_klt(ctx, c));
+    p.mark(ctx->stream);
+    SFM_CUDA(ctx, cudaEventRecord(e_done, ctx->stream));
+  }
+  if (done) *done = e_done;
   return 0;
 }
 
@@ -338,7 +440,7 @@ static int pair_args_ok(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int 
 int sfmgpu_pipeline_set(sfmgpu_ctx* ctx, int pairs_per_chunk) {
   if (!ctx) return SFMGPU_E_ARG;
   if (pairs_per_chunk < 0) return sfm_fail(ctx, SFMGPU_E_ARG, "pipeline_set: negative chunk");
-  ctx->pipe_chunk = pairs_per_chunk;
+  ctx->pipe_chunk = pairs_per_chunk > 1024 ? 1024 : pairs_per_chunk;
   return 0;
 }
 
@@ -350,27 +452,28 @@ int sfmgpu_pair_frontend(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int
   SFM_CUDA(ctx, cudaMemsetAsync(out->totals, 0, 64, ctx->stream));
   const int sub = ctx->pipe_chunk;
   if (sub <= 0 || ctx->profile || npairs < 2 * sub)  // stage profiling wants the stages back to back on one stream
-    return pair_range(ctx, f, first_frame, 0, npairs, cfg, out, out->work);
+    return pair_range(ctx, f, first_frame, 0, npairs, cfg, out);
   SFM_TRY(pipe_streams(ctx));
   SFM_TRY(pipe_reserve(ctx, f, cfg, out, sub));
-  cudaEvent_t fork = pipe_event(ctx, 0), join = pipe_event(ctx, 1);
-  if (!fork || !join) return sfm_fail(ctx, SFMGPU_E_CUDA, "pair_frontend: cudaEventCreate failed");
+  Pipe p;
+  p.ctx = ctx;
+  cudaEvent_t fork = p.next();
+  if (!fork) return sfm_fail(ctx, SFMGPU_E_CUDA, "pair_frontend: cudaEventCreate failed");
   SFM_CUDA(ctx, cudaEventRecord(fork, ctx->stream));
-  SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, fork, 0));
-  int lane = 0;
-  for (int p0 = 0; p0 < npairs; p0 += sub, lane ^= 1) {
+  SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->sel_stream, fork, 0));
+  SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->klt_stream, fork, 0));
+  cudaEvent_t last = nullptr;
+  for (int p0 = 0; p0 < npairs; p0 += sub) {
     const int cnt = npairs - p0 < sub ? npairs - p0 : sub;
-    LaneScope ls(ctx, lane);
-    SFM_TRY(pair_range(ctx, f, first_frame + p0, p0, cnt, cfg, out, lane ? out->work2 : out->work));
+    SFM_TRY(pipe_chunk(p, f, first_frame + p0, p0, cnt, cfg, out, nullptr, &last));
   }
-  SFM_CUDA(ctx, cudaEventRecord(join, ctx->aux_stream));
-  SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, join, 0));
+  SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, last, 0));  // the KLT stream is in order: its last event covers all chunks
   return 0;
 }
 
 // Streaming variant for frames that live in HOST memory: frames [0, nframes) of `f` are filled from host_pix in
-// chunks on a copy stream (which also builds their pyramids) while the two compute lanes run the pair front end on
-// the sub-chunks whose frames have arrived; each sub-chunk's results go back on a fourth stream.
+// chunks on a copy stream (which also builds their pyramids); every chunk then flows through the stage pipeline and
+// its results go back on a fifth stream.
 int sfmgpu_pair_frontend_host(sfmgpu_ctx* ctx, sfmgpu_frames* f, const uint8_t* host_pix, int nframes, const sfmgpu_lkcfg* cfg,
                               sfmgpu_pairs* out, int chunk_frames, double* li_xy, double* lj_xy, int32_t* n_kept,
                               int32_t* n_corners) {
@@ -384,61 +487,50 @@ int sfmgpu_pair_frontend_host(sfmgpu_ctx* ctx, sfmgpu_frames* f, const uint8_t* 
   SFM_TRY(pipe_streams(ctx));
   int chunk = chunk_frames > 0 ? chunk_frames : (nframes + 5) / 6;
   if (chunk < 2) chunk = 2;
+  if (chunk > 1024) chunk = 1024;
   const int nchunks = (nframes + chunk - 1) / chunk;
-  const bool two_lanes = !ctx->profile;
-  const int sub = ctx->pipe_chunk > 0 ? ctx->pipe_chunk : chunk;  // default: one sub-chunk per upload chunk, lanes alternate
-  SFM_TRY(pipe_reserve(ctx, f, cfg, out, sub < chunk ? sub : chunk));
-  size_t ev = 0;
-  cudaEvent_t fork = pipe_event(ctx, ev++);
+  SFM_TRY(pipe_reserve(ctx, f, cfg, out, chunk));
+  Pipe p;
+  p.ctx = ctx;
+  cudaEvent_t fork = p.next();
   if (!fork) return sfm_fail(ctx, SFMGPU_E_CUDA, "pair_frontend_host: cudaEventCreate failed");
-  // nothing may overwrite frames / results that an earlier call on the main stream still uses
+  // nothing may overwrite frames / results that an earlier call on the context stream still uses
   SFM_CUDA(ctx, cudaEventRecord(fork, ctx->stream));
   SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, fork, 0));
   SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->back_stream, fork, 0));
-  SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, fork, 0));
+  SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->sel_stream, fork, 0));
+  SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->klt_stream, fork, 0));
   const size_t cap = (size_t)out->cap;
-  int lane = 0;
   for (int c = 0; c < nchunks; c++) {
     const int a = c * chunk, b = a + chunk < nframes ? a + chunk : nframes;
     SFM_CUDA(ctx, cudaMemcpy2DAsync(f->lvl[0] + (size_t)a * f->fstride[0], f->pitch[0], host_pix + (size_t)a * f->w * f->h, f->w,
                                     f->w, (size_t)f->h * (b - a), cudaMemcpyHostToDevice, ctx->copy_stream));
-    cudaEvent_t up = pipe_event(ctx, ev++);
+    cudaEvent_t up = p.next();
     if (!up) return sfm_fail(ctx, SFMGPU_E_CUDA, "pair_frontend_host: cudaEventCreate failed");
     {
-      cudaStream_t saved = ctx->stream;  // the pyramid of a chunk is built right behind its upload, on the copy stream
-      ctx->stream = ctx->copy_stream;
-      const int rc = sfmgpu_pyramid_build(ctx, f, a, b - a);
-      ctx->stream = saved;
-      SFM_TRY(rc);
+      StageScope sc(ctx, ctx->copy_stream);  // the pyramid of a chunk is built right behind its upload
+      SFM_TRY(sfmgpu_pyramid_build(ctx, f, a, b - a));
+      SFM_CUDA(ctx, cudaEventRecord(up, ctx->stream));
     }
-    SFM_CUDA(ctx, cudaEventRecord(up, ctx->copy_stream));
-    SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, up, 0));
-    SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, up, 0));
     // pairs whose second frame arrived with this chunk
     const int P0 = a > 0 ? a - 1 : 0, P1 = b - 1;
-    for (int p0 = P0; p0 < P1; p0 += sub) {
-      const int cnt = P1 - p0 < sub ? P1 - p0 : sub;
-      cudaEvent_t done = pipe_event(ctx, ev++);
-      if (!done) return sfm_fail(ctx, SFMGPU_E_CUDA, "pair_frontend_host: cudaEventCreate failed");
-      {
-        LaneScope ls(ctx, lane);
-        SFM_TRY(pair_range(ctx, f, p0, p0, cnt, cfg, out, lane ? out->work2 : out->work));
-        SFM_CUDA(ctx, cudaEventRecord(done, ctx->stream));
-      }
-      if (two_lanes) lane ^= 1;
-      SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->back_stream, done, 0));
-      const size_t np_ = (size_t)cnt, o = (size_t)p0;
-      if (li_xy)
-        SFM_CUDA(ctx, cudaMemcpyAsync(li_xy + 2 * o * cap, out->li + o * cap, np_ * cap * 16, cudaMemcpyDeviceToHost, ctx->back_stream));
-      if (lj_xy)
-        SFM_CUDA(ctx, cudaMemcpyAsync(lj_xy + 2 * o * cap, out->lj + o * cap, np_ * cap * 16, cudaMemcpyDeviceToHost, ctx->back_stream));
-      if (n_kept) SFM_CUDA(ctx, cudaMemcpyAsync(n_kept + o, out->nkept + o, np_ * 4, cudaMemcpyDeviceToHost, ctx->back_stream));
-      if (n_corners) SFM_CUDA(ctx, cudaMemcpyAsync(n_corners + o, out->ncorn + o, np_ * 4, cudaMemcpyDeviceToHost, ctx->back_stream));
-    }
+    if (P1 <= P0) continue;
+    cudaEvent_t done = nullptr;
+    SFM_TRY(pipe_chunk(p, f, P0, P0, P1 - P0, cfg, out, up, &done));
+    SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->back_stream, done, 0));
+    const size_t np_ = (size_t)(P1 - P0), o = (size_t)P0;
+    if (li_xy)
+      SFM_CUDA(ctx, cudaMemcpyAsync(li_xy + 2 * o * cap, out->li + o * cap, np_ * cap * 16, cudaMemcpyDeviceToHost, ctx->back_stream));
+    if (lj_xy)
+      SFM_CUDA(ctx, cudaMemcpyAsync(lj_xy + 2 * o * cap, out->lj + o * cap, np_ * cap * 16, cudaMemcpyDeviceToHost, ctx->back_stream));
+    if (n_kept) SFM_CUDA(ctx, cudaMemcpyAsync(n_kept + o, out->nkept + o, np_ * 4, cudaMemcpyDeviceToHost, ctx->back_stream));
+    if (n_corners) SFM_CUDA(ctx, cudaMemcpyAsync(n_corners + o, out->ncorn + o, np_ * 4, cudaMemcpyDeviceToHost, ctx->back_stream));
   }
   SFM_CUDA(ctx, cudaStreamSynchronize(ctx->back_stream));
-  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->aux_stream));
+  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->klt_stream));
+  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->sel_stream));
   SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  p.trace_dump();
   return 0;
 }
 

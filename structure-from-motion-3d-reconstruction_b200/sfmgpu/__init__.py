@@ -10,7 +10,7 @@ import subprocess
 import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "libsfmgpu.so")
+LIB_PATH = os.environ.get("SFMGPU_LIB") or os.path.join(_PKG, "libsfmgpu.so")  # SFMGPU_LIB: A/B builds of the same ABI
 
 _u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 _f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
