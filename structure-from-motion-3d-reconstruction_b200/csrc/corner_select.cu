@@ -535,24 +535,42 @@ int select_smem_config(sfmgpu_ctx* ctx) {
 }  // namespace
 
 // Detect corners for frames [first, first+count): out_xy [count][max(1,max_corners)], out_n[count] (device).
-int sfm_corners_batch(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first, int count, int max_corners, double quality,
-                      int min_dist, int cand_cap, void* work, size_t work_bytes, double2* out_xy, int* out_n) {
+// Two stages so that a caller can put them on different streams: score (max, candidates, raster order) and select
+// (std::sort permutation + greedy NMS); both use the work area carved for (count, cand_cap, min_dist).
+static int corners_args(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int count, int& min_dist, int cand_cap, void* work, size_t work_bytes,
+                        CornerWorkView& wv) {
   if (f->w > 65535 || f->h > 65535) return sfm_fail(ctx, SFMGPU_E_ARG, "corners: image larger than 65535 px");
   if (min_dist < 0) min_dist = -min_dist;  // the reference compares against (double)min_dist*min_dist (:295)
   if (min_dist > 30000) return sfm_fail(ctx, SFMGPU_E_ARG, "corners: min_dist too large");
-  CornerWorkView wv;
   const size_t need = corner_work_carve(wv, work, f->w, f->h, count, cand_cap, min_dist);
   if (need > work_bytes) return sfm_fail(ctx, SFMGPU_E_ARG, "corners: work area too small (%zu < %zu)", work_bytes, need);
+  return 0;
+}
+
+int sfm_corners_score_stage(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first, int count, double quality, int min_dist, int cand_cap,
+                            void* work, size_t work_bytes) {
+  CornerWorkView wv;
+  SFM_TRY(corners_args(ctx, f, count, min_dist, cand_cap, work, work_bytes, wv));
+  StageTimer st(ctx, 0);
+  return sfm_corner_candidates_batch(ctx, f, first, count, quality, wv);
+}
+
+int sfm_corners_select_stage(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int count, int max_corners, int min_dist, int cand_cap, void* work,
+                             size_t work_bytes, double2* out_xy, int* out_n) {
+  CornerWorkView wv;
+  SFM_TRY(corners_args(ctx, f, count, min_dist, cand_cap, work, work_bytes, wv));
   SFM_TRY(select_smem_config(ctx));
-  {
-    StageTimer st(ctx, 0);
-    SFM_TRY(sfm_corner_candidates_batch(ctx, f, first, count, quality, wv));
-  }
   StageTimer st(ctx, 1);
   if (wv.grid_per_frame)
     SFM_CUDA(ctx, cudaMemsetAsync(wv.grid, 0xFF, sizeof(unsigned) * wv.grid_per_frame * count, ctx->stream));
   SFM_LAUNCH(ctx, select_kernel, count, SEL_THREADS, sizeof(SelSmem), wv, f->w, max_corners, min_dist, 0, out_xy, out_n);
   return 0;
+}
+
+int sfm_corners_batch(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first, int count, int max_corners, double quality,
+                      int min_dist, int cand_cap, void* work, size_t work_bytes, double2* out_xy, int* out_n) {
+  SFM_TRY(sfm_corners_score_stage(ctx, f, first, count, quality, min_dist, cand_cap, work, work_bytes));
+  return sfm_corners_select_stage(ctx, f, count, max_corners, min_dist, cand_cap, work, work_bytes, out_xy, out_n);
 }
 
 size_t sfm_corner_work_bytes_md(int w, int h, int nframes, int cand_cap, int min_dist) {

@@ -338,6 +338,28 @@ def test_pair_frontend_streaming_equals_resident(ctx, chunk, pipe):
         ctx.pipeline_set(0)
 
 
+def test_c3_shape_4k_pair(ctx, checker):
+    """BASELINE.json config C3 at full size: one 3840x2160 pair, 8000 corners/frame (bit-exact against the checker),
+    tracks through the batched front end (lane kernel) within the KLT tolerance on a 1500-point sample."""
+    w, h, nmax = 3840, 2160, 8000
+    f0, f1 = synth.frame(SEED, 0, w, h), synth.frame(SEED, 1, w, h)
+    f = _frames(ctx, [f0, f1], 3)
+    cfg = sfmgpu.lkcfg(max_tracks=nmax, min_tracks=3273)
+    pairs = ctx.pairs(1, nmax)
+    pairs.run(f, 0, 1, cfg)
+    li, lj, nc = pairs.download(0)
+    want = checker.shi_tomasi(f0, nmax)
+    assert nc == len(want) == nmax
+    sel = np.r_[0:750, nmax - 750:nmax]
+    w1, wb = checker.klt_track(f0, f1, want[sel])
+    keep = ~(np.hypot(*(wb - want[sel]).T) >= 1.0)
+    # survivors keep corner order: map the sample through the kept mask of the full run
+    p1, pb = f.klt_track(0, 1, want)
+    kept_all = ~(np.hypot(*(pb - want).T) >= 1.0)
+    assert np.array_equal(li, want[kept_all]) and _klt_close(lj, p1[kept_all])
+    assert np.array_equal(kept_all[sel], keep) and _klt_close(p1[sel], w1) and _klt_close(pb[sel], wb)
+
+
 def test_errors_are_loud(ctx):
     f = ctx.frames(64, 48, 2, 3)
     with pytest.raises(sfmgpu.SfmGpuError):
