@@ -22,6 +22,7 @@
 // u~ >= bound - 2 (bound = the tile's / frame's running maximum in the max pass, 8*thr in the candidate pass); those
 // few are queued and evaluated DENSELY with the exact FP64 expression afterwards, which alone decides.
 //
+// (Tried and dropped: persistent blocks with cp.async double-buffered taps: 5.13 ms vs 4.46 ms per 299 frames.)
 // Kernels (tile = 64 x 60 output pixels, 256 threads, taps staged once in shared memory with clamping):
 //   score_tile_kernel<0>  per-frame maximum of u = 8*lmin  (atomicMax on the double's bit pattern)
 //   score_tile_kernel<1>  candidate bitmap (one word per 32 pixels) + unordered (pixel, score) list
@@ -182,6 +183,7 @@ __global__ void __launch_bounds__(256, 3) score_tile_kernel(const uint8_t* __res
     bound = __double2float_rd(thr8);
   }
   const bool col_in = x < w, col_interior = x >= 2 && x < w - 2;
+  const bool tile_inner = X0 >= 2 && X0 + TW <= w - 2 && Y0 >= 2 && Y0 + TH <= h - 2;  // no border pixel in this tile
   float ra[4], rb[4], rc[4];  // ring of the last four row sums; the fifth enters in the loop
 #pragma unroll
   for (int i = 0; i < 4; i++) {
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(256, 3) score_tile_kernel(const uint8_t* __res
     c += nc;
     b += nb;
     const int y = Y0 + q * VRUN + j;
-    const bool interior = col_interior && y >= 2 && y < h - 2;
+    const bool interior = tile_inner || (col_interior && y >= 2 && y < h - 2);
     const float u = est_u(a, b, c);
     if (MODE == 0) {
       uf[j] = interior ? u : -1.0e30f;
