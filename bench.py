@@ -362,6 +362,32 @@ def main():
     counts, bh, inl = ctx.ransac_score(xi, xj, E, 1e-3)
     rs_e2e_ms = (time.perf_counter() - t0) * 1e3
 
+    # ---- the reference's own two-view entry point through the C++ shim: host solver (bit-identical hypotheses) vs the
+    # opt-in device solver, TempleRing-sized call (2500 iterations x 2200 correspondences, sfm.cpp:1739)
+    find_e = None
+    if rank == 0:
+        try:
+            import ctypes as C
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import shimlib
+            from conftest import TEMPLE_K, two_view_scene
+            shim = shimlib.load()
+            pi, pj = two_view_scene(2200, seed=2200)
+            Kf = np.ascontiguousarray(TEMPLE_K.reshape(9))
+            Rr, tt, il, kk = np.zeros(9), np.zeros(3), np.zeros(2200, np.int32), C.c_int(0)
+            find_e = {"iters": 2500, "points": 2200}
+            for name, flag in (("host_solver_ms", 0), ("device_solver_ms", 1)):
+                shim.shim_set_device_solver(flag)
+                shim.shim_find_E_ransac(Kf, pi, pj, 2200, 2500, 1e-3, 60, Rr, tt, il, C.byref(kk))
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    shim.shim_find_E_ransac(Kf, pi, pj, 2200, 2500, 1e-3, 60, Rr, tt, il, C.byref(kk))
+                find_e[name] = (time.perf_counter() - t0) / 3 * 1e3
+                find_e[name.replace("_ms", "_inliers")] = int(kk.value)
+            shim.shim_set_device_solver(0)
+        except Exception as ex:  # the shim is optional for the bench line
+            find_e = {"error": str(ex)[:200]}
+
     # ---- reduce over ranks: max time, summed work; gather per-pair counts to rank 0 with NCCL --------------------------------
     ms_step = ms_total / args.steps
     vals = torch.tensor([ms_step, e2e_ms, rs_ms, pyr_ms, st["klt"], st["corner_score"], st["corner_select"]], device="cuda",
@@ -411,7 +437,8 @@ def main():
             "ransac": {"value": RS_H * RS_N / (rs_ms * 1e-3), "unit": "hyp*pts/s", "ms": rs_ms, "hypotheses": RS_H, "points": RS_N,
                        "e2e_value": RS_H * RS_N / (rs_e2e_ms * 1e-3), "best_h": int(bh), "best_inliers": int(len(inl)),
                        "fp64_frac": F_RS * RS_H * RS_N / (rs_ms * 1e-3) / 1e12 / fp64_peak,
-                       "hypotheses_source": "synthetic [t]x R around the C4 motion (scoring cost is value-independent)"},
+                       "hypotheses_source": "synthetic [t]x R around the C4 motion (scoring cost is value-independent)",
+                       "find_E_ransac": find_e},
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(host)

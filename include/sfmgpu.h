@@ -184,6 +184,16 @@ int sfmgpu_ransac_upload(sfmgpu_ctx* ctx, const double* xi_xy, const double* xj_
 int sfmgpu_ransac_score_resident(sfmgpu_ctx* ctx, double thr, int* best_h, int* best_n);
 int sfmgpu_ransac_download(sfmgpu_ctx* ctx, int32_t* counts, int32_t* best_inl, int cap_inl);
 
+
+/* ---- minimal solver on the device (opt-in): eight_point_E :609-627 + jacobi_eig_sym (linalg.hpp:133-201) ------------
+ * One hypothesis per sampled index octet idx8[H][8] (the host keeps the reference's seeded sampling :657-665).  Leaves
+ * the points and the H hypotheses resident, ready for sfmgpu_ransac_score_resident / sfmgpu_ransac_download; E_out
+ * (optional) receives the hypotheses, 9 doubles each.  NOT bit-identical to the reference's solver (CUDA vs glibc
+ * atan2 / sin / cos in the Jacobi rotations; ~1e-12 relative, eigenvector sign may differ): the default path of the
+ * drop-in keeps the host solver, whose hypotheses are bit-identical. */
+int sfmgpu_ransac_hypotheses(sfmgpu_ctx* ctx, const double* xi_xy, const double* xj_xy, int n, const int32_t* idx8, int H,
+                             double* E_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,7 +62,7 @@ struct sfmgpu_ctx {
   DevBuf cs_work;    // corner-score work area for single-frame calls
   DevBuf sel_work;   // corner-select work area
   DevBuf misc;       // small scalars
-  DevBuf rs_xi, rs_xj, rs_E, rs_counts, rs_inl, rs_best;
+  DevBuf rs_xi, rs_xj, rs_E, rs_counts, rs_inl, rs_best, rs_idx8;
   int rs_n = 0, rs_H = 0;
   bool profile = false;
   struct StageEv { int stage; cudaEvent_t a, b; };

@@ -63,6 +63,18 @@ inline void check(sfmgpu_ctx* ctx, int rc, const char* what) {
   if (rc != 0) throw std::runtime_error(std::string("sfmgpu: ") + what + ": " + sfmgpu_last_error(ctx));
 }
 
+// Opt-in: minimal solver on the device.  Default off: hypotheses come from the host solver and are
+// bit-identical to the reference's.
+inline bool& device_solver_flag() {
+  static bool on = [] {
+    const char* e = std::getenv("SFMGPU_DEVICE_SOLVER");
+    return e && *e && *e != '0';
+  }();
+  return on;
+}
+inline bool device_solver() { return device_solver_flag(); }
+inline void set_device_solver(bool on) { device_solver_flag() = on; }
+
 // Process-wide context.
 inline sfmgpu_ctx* context() {
   static sfmgpu_ctx* ctx = [] {
@@ -297,16 +309,27 @@ static std::optional<RelPose> find_E_ransac(const Mat33& K, const std::vector<Ve
   std::uniform_int_distribution<int> uni(0, n - 1);
   const int H = iters > 0 ? iters : 0;
   std::vector<double> E(9 * (size_t)H);
-  int idx8[8];
-  for (int it = 0; it < H; it++) {
-    for (int k = 0; k < 8; k++) idx8[k] = uni(rng);
-    sfmgpu_host::eight_point_E(xi.data(), xj.data(), idx8, &E[9 * (size_t)it]);
-  }
-  // scoring loop (:667-676) on the GPU: exact counts, first hypothesis with the strictly largest count
   sfmgpu_ctx* ctx = context();
   std::vector<int> inl((size_t)n);
   int best_h = -1, best_n = 0;
-  check(ctx, sfmgpu_ransac_score(ctx, xi.data(), xj.data(), n, E.data(), H, thr, nullptr, &best_h, inl.data(), &best_n), "ransac_score");
+  if (!device_solver()) {
+    int idx8[8];
+    for (int it = 0; it < H; it++) {
+      for (int k = 0; k < 8; k++) idx8[k] = uni(rng);
+      sfmgpu_host::eight_point_E(xi.data(), xj.data(), idx8, &E[9 * (size_t)it]);
+    }
+    // scoring loop (:667-676) on the GPU: exact counts, first hypothesis with the strictly largest count
+    check(ctx, sfmgpu_ransac_score(ctx, xi.data(), xj.data(), n, E.data(), H, thr, nullptr, &best_h, inl.data(), &best_n),
+          "ransac_score");
+  } else {
+    // opt-in (SFMGPU_DEVICE_SOLVER=1 or set_device_solver(true)): the same sampled octets, hypotheses solved on the
+    // device (not bit-identical to the host solver: CUDA vs glibc trig in the Jacobi rotations), scored as above
+    std::vector<std::int32_t> idx((size_t)8 * H);
+    for (size_t k = 0; k < idx.size(); k++) idx[k] = uni(rng);
+    check(ctx, sfmgpu_ransac_hypotheses(ctx, xi.data(), xj.data(), n, idx.data(), H, E.data()), "ransac_hypotheses");
+    check(ctx, sfmgpu_ransac_score_resident(ctx, thr, &best_h, &best_n), "ransac_score_resident");
+    check(ctx, sfmgpu_ransac_download(ctx, nullptr, inl.data(), n), "ransac_download");
+  }
   if (best_n < min_inliers) return std::nullopt;
   RelPose rp;
   double R[9], t[3];

@@ -160,6 +160,9 @@ int shim_find_E_ransac(const double* K, const double* pi, const double* pj, int 
   });
 }
 
+// opt-in device solver for find_E_ransac
+void shim_set_device_solver(int on) { sfmgpu_shim::set_device_solver(on != 0); }
+
 // ---- host-only pieces (no GPU needed): checked on the CPU against the compiled reference ----------------------
 int shim_host_norm_points(const double* K, const double* p, int n, double* out) {
   double Ki[9];

@@ -31,6 +31,7 @@ SYMBOLS = [
     "sfmgpu_pairs_download", "sfmgpu_pairs_download_all", "sfmgpu_pairs_device_ptrs", "sfmgpu_tracker_create", "sfmgpu_tracker_destroy", "sfmgpu_tracker_reset",
     "sfmgpu_tracker_step", "sfmgpu_tracker_step_frames", "sfmgpu_tracker_tracks", "sfmgpu_tracker_totals",
     "sfmgpu_ransac_score", "sfmgpu_ransac_upload", "sfmgpu_ransac_score_resident", "sfmgpu_ransac_download",
+    "sfmgpu_ransac_hypotheses",
 ]
 
 
@@ -115,6 +116,7 @@ def load_library():
         "sfmgpu_ransac_upload": (_i, [_vp, _f64p, _f64p, _i, _f64p, _i]),
         "sfmgpu_ransac_score_resident": (_i, [_vp, _d, C.POINTER(_i), C.POINTER(_i)]),
         "sfmgpu_ransac_download": (_i, [_vp, _vp, _vp, _i]),
+        "sfmgpu_ransac_hypotheses": (_i, [_vp, _f64p, _f64p, _i, _i32p, _i, _vp]),
     }
     for name, (res, args) in S.items():
         fn = getattr(lib, name)
@@ -231,6 +233,23 @@ class Context:
             return bh.value, bn.value
         self._ck(self.lib.sfmgpu_ransac_score_resident(self.h, thr, None, None))
         return None
+
+    def ransac_hypotheses(self, xi, xj, idx8, fetch=True):
+        """Device 8-point solver (opt-in, not bit-identical to the host solver): one hypothesis per index octet; the
+        points and hypotheses stay resident for ransac_score_resident / ransac_download."""
+        xi = np.ascontiguousarray(xi, np.float64).reshape(-1, 2)
+        xj = np.ascontiguousarray(xj, np.float64).reshape(-1, 2)
+        idx8 = np.ascontiguousarray(idx8, np.int32).reshape(-1, 8)
+        H = len(idx8)
+        E = np.zeros((max(H, 1), 9)) if fetch else None
+        self._ck(self.lib.sfmgpu_ransac_hypotheses(self.h, xi, xj, len(xi), idx8 if H else np.zeros((1, 8), np.int32), H, _ptr(E)))
+        return E[:H] if fetch else None
+
+    def ransac_download(self, H, n):
+        counts = np.zeros(max(H, 1), np.int32)
+        inl = np.full(max(n, 1), -1, np.int32)
+        self._ck(self.lib.sfmgpu_ransac_download(self.h, _ptr(counts), _ptr(inl), n))
+        return counts[:H], inl
 
     def sort_perm_desc(self, keys):
         keys = np.ascontiguousarray(keys, np.float64)

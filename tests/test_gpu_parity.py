@@ -280,6 +280,31 @@ def test_ransac_degenerate(ctx):
     assert counts.tolist() == [0, 0, 0] and bh == -1 and len(inl) == 0
 
 
+# ---- device minimal solver (opt-in) -------------------------------------------------------------
+@pytest.mark.parametrize("n,H", [(300, 200), (2200, 2500), (40, 64)])
+def test_device_solver_matches_host_hypotheses(ctx, port, n, H):
+    """sfmgpu_ransac_hypotheses: same sampled octets as the reference (its own RNG stream), hypotheses equal to the
+    host solver's up to sign and ~1e-9 relative (NOT bit-identical: CUDA vs glibc trig), same winner and inlier set."""
+    pi, pj = two_view_scene(n, seed=7 * n + H)
+    xi, xj = port.norm_points(TEMPLE_K, pi), port.norm_points(TEMPLE_K, pj)
+    Eh, idx = port.ransac_hypotheses(xi, xj, H)  # host solver + the reference's seeded sampling
+    assert np.array_equal(idx.ravel(), port.rng_draws(n, 8 * H))
+    Ed = ctx.ransac_hypotheses(xi, xj, idx)
+    sgn = np.sign((Ed * Eh).sum(1, keepdims=True))
+    scale = np.abs(Eh).max(1, keepdims=True)
+    err = np.abs(Ed * sgn - Eh) / scale
+    # degenerate samples (repeated indices: sampling is with replacement) have a multi-dimensional null space and
+    # may legitimately pick a different vector of it; they never win a RANSAC round
+    distinct = np.array([len(set(r)) == 8 for r in idx.tolist()])
+    print(f"device solver: max rel. deviation {err[distinct].max():.2e} over {distinct.sum()} non-degenerate hypotheses")
+    assert np.quantile(err[distinct], 0.99) < 1e-8
+    bh, bn = ctx.ransac_score_resident(1e-3)
+    counts, inl = ctx.ransac_download(H, n)
+    wc, wbh, wi = port.ransac_score(xi, xj, Eh, 1e-3)
+    assert bh == wbh and bn == len(wi) and np.array_equal(inl[:bn], wi)
+    assert (counts != wc)[distinct].mean() < 0.01  # borderline points may flip on a few hypotheses
+
+
 # ---- batched two-view front end ----------------------------------------------------------------------------------------
 def test_pair_frontend_batch(ctx, checker, g):
     imgs = [synth.frame(SEED, t, W, H) for t in range(6)]

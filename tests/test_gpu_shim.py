@@ -61,6 +61,23 @@ def test_tracker_class(shim, checker):
     shim.shim_tracker_destroy(t)
 
 
+def test_find_E_ransac_device_solver(shim, checker):
+    """Opt-in device solver behind the same find_E_ransac: same inlier set, pose within 1e-9 of the reference's."""
+    n, iters, thr, mi = 2200, 2500, 1e-3, 60
+    pi, pj = two_view_scene(n, seed=n)
+    K = np.ascontiguousarray(TEMPLE_K.reshape(9))
+    R, t, inl, k = np.zeros(9), np.zeros(3), np.zeros(n, np.int32), C.c_int(0)
+    shim.shim_set_device_solver(1)
+    try:
+        ok = shimlib.ck(shim, shim.shim_find_E_ransac(K, pi, pj, n, iters, thr, mi, R, t, inl, C.byref(k)))
+    finally:
+        shim.shim_set_device_solver(0)
+    want = checker.find_E_ransac(TEMPLE_K, pi, pj, iters, thr, mi)
+    assert ok == 1 and want is not None
+    assert np.array_equal(inl[:k.value], want[2])
+    assert np.abs(R.reshape(3, 3) - want[0]).max() < 1e-9 and np.abs(t - want[1]).max() < 1e-9
+
+
 @pytest.mark.parametrize("n,iters,thr,mi", [(400, 120, 1e-3, 60), (400, 60, 1e-9, 80), (7, 50, 1e-3, 1), (2200, 250, 1e-3, 60)])
 def test_find_E_ransac(shim, checker, n, iters, thr, mi):
     pi, pj = two_view_scene(n, seed=n)
