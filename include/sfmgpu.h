@@ -194,6 +194,15 @@ int sfmgpu_ransac_download(sfmgpu_ctx* ctx, int32_t* counts, int32_t* best_inl, 
 int sfmgpu_ransac_hypotheses(sfmgpu_ctx* ctx, const double* xi_xy, const double* xj_xy, int n, const int32_t* idx8, int H,
                              double* E_out);
 
+
+/* ---- loop-closure descriptor and candidate search: global_desc_32 :1100-1122, dot_desc :1124-1129, :1823-1831 ---------
+ * desc_out: count descriptors of 1024 floats (host) for frames [first, first+count) (level 0 is read; bit-exact). */
+int sfmgpu_global_desc32(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first, int count, float* desc_out);
+/* Dot product of `query` with each of the first n_search stored descriptors (host arrays): scores (optional),
+ * best_id = first index with the strictly largest score above 0 (-1: none), best_score (0 when none). */
+int sfmgpu_desc_search(sfmgpu_ctx* ctx, const float* descs, int n_search, const float* query, float* scores, int* best_id,
+                       float* best_score);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 _f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 
 
@@ -58,6 +59,8 @@ class CpuFrontEnd:
             "pair_frontend": (i, [_u8p, _u8p, i, i, i, d, i, i, i, i, d, _f64p, _f64p, C.POINTER(i)]),
             "pair_frontend_mt": (C.c_long, [_u8p, i, i, i, i, d, i, i, i, i, d, i, C.POINTER(C.c_long)]),
             "ransac_score_mt": (i, [_f64p, _f64p, i, _f64p, i, d, _i32p, i]),
+            "global_desc32": (i, [_u8p, i, i, _f32p]),
+            "desc_search": (i, [_f32p, i, _f32p, _f32p, C.POINTER(i), C.POINTER(C.c_float)]),
         }
         if self.prefix == "orc":
             S.update({
@@ -182,6 +185,23 @@ class CpuFrontEnd:
         counts = np.zeros(len(E), np.int32)
         self._f("ransac_score_mt")(xi, xj, len(xi), E, len(E), thr, counts, threads)
         return counts
+
+    # ---- loop-closure descriptor (:1100-1129) and candidate search (:1823-1831) -----------------------------
+    def global_desc32(self, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        out = np.zeros(1024, np.float32)
+        if self._f("global_desc32")(img, img.shape[1], img.shape[0], out) != 1024:
+            raise ValueError("degenerate image")
+        return out
+
+    def desc_search(self, descs, query, n_search=None):
+        descs = np.ascontiguousarray(descs, np.float32).reshape(-1, 1024)
+        query = np.ascontiguousarray(query, np.float32).reshape(1024)
+        n = len(descs) if n_search is None else n_search
+        scores = np.zeros(max(n, 1), np.float32)
+        bid, bs = C.c_int(-1), C.c_float(0)
+        self._f("desc_search")(descs if len(descs) else np.zeros((1, 1024), np.float32), n, query, scores, C.byref(bid), C.byref(bs))
+        return bid.value, np.float32(bs.value), scores[:n]
 
     def find_E_ransac(self, K, pi, pj, iters, thr, min_inliers):
         pi = np.ascontiguousarray(pi, np.float64).reshape(-1, 2)

@@ -11,7 +11,8 @@
 // Symbols reached (reference file:line, relative to cpp/src/templering_sfm.cpp):
 //   build_pyr :224-232, shi_tomasi :237-302, KLTTracker :323-466 (reset/step/track_one_public),
 //   norm_point/invert_K :471-501, eight_point_E :609-627, sampson_err :629-638,
-//   find_E_ransac :646-761, stateless two-view front end :1836-1857 (lifted, see ref_pair_frontend).
+//   find_E_ransac :646-761, stateless two-view front end :1836-1857 (lifted, see ref_pair_frontend),
+//   global_desc_32 :1100-1122, dot_desc :1124-1129, loop-candidate search :1823-1831 (lifted, see ref_desc_search).
 #define main ref_main_unused
 #include "cpp/src/templering_sfm.cpp"
 #undef main
@@ -297,4 +298,30 @@ int ref_ransac_score_mt(const double* xi, const double* xj, int n, const double*
 }
 
 const char* ref_kind() { return "reference"; }
+
+// Loop-closure descriptor (:1100-1122) of one image: 1024 floats.
+int ref_global_desc32(const uint8_t* pix, int w, int h, float* out) {
+  const std::vector<float> v = global_desc_32(wrap(pix, w, h));
+  std::memcpy(out, v.data(), v.size() * sizeof(float));
+  return (int)v.size();
+}
+
+// The candidate search of :1823-1831 over the first n_search descriptors: best_id (-1: none), best_score.
+int ref_desc_search(const float* descs, int n_search, const float* query, float* scores, int* best_id, float* best_score) {
+  const std::vector<float> q(query, query + 1024);
+  int bid = -1;
+  float bs = 0.0f;
+  for (int kk = 0; kk < n_search; ++kk) {
+    const std::vector<float> a(descs + (size_t)kk * 1024, descs + (size_t)(kk + 1) * 1024);
+    const float s = dot_desc(a, q);
+    if (scores) scores[kk] = s;
+    if (s > bs) {
+      bs = s;
+      bid = kk;
+    }
+  }
+  *best_id = bid;
+  *best_score = bs;
+  return 0;
+}
 }

@@ -822,5 +822,58 @@ int orc_synth_frames(uint32_t seed, int t0, int nframes, int w, int h, uint8_t* 
   return 0;
 }
 
+// ---- loop-closure descriptor (:1100-1122) and candidate search (:1124-1129, :1823-1831) ----------------------------
+// Halve until both sides are <= 32, nearest-sample to 32x32 (std::round), float values, mean in double, subtract
+// (float)mean in float, squared norm accumulated in double in raster order, scale by 1/sqrt(n2 + 1e-12) in double and
+// round to float.
+int orc_global_desc32(const uint8_t* pix, int w, int h, float* out) {
+  std::vector<uint8_t> a(pix, pix + (size_t)w * h), b;
+  int cw = w, ch = h;
+  while (cw > 32 || ch > 32) {
+    b.assign((size_t)(cw / 2) * (ch / 2), 0);
+    halve(a.data(), cw, ch, b.data());
+    a.swap(b);
+    cw /= 2;
+    ch /= 2;
+  }
+  if (cw < 1 || ch < 1) return -1;
+  double mean = 0.0;
+  for (int y = 0; y < 32; y++)
+    for (int x = 0; x < 32; x++) {
+      const int sx = std::min(cw - 1, (int)std::round((double)x * (cw - 1) / 31.0));
+      const int sy = std::min(ch - 1, (int)std::round((double)y * (ch - 1) / 31.0));
+      const float val = (float)a[(size_t)sy * cw + sx];
+      out[y * 32 + x] = val;
+      mean += val;
+    }
+  mean /= (32.0 * 32.0);
+  double n2 = 0.0;
+  for (int i = 0; i < 1024; i++) {
+    out[i] = (float)(out[i] - (float)mean);
+    n2 += (double)out[i] * (double)out[i];
+  }
+  const double invn = 1.0 / std::sqrt(n2 + 1e-12);
+  for (int i = 0; i < 1024; i++) out[i] = (float)(out[i] * invn);
+  return 1024;
+}
+
+int orc_desc_search(const float* descs, int n_search, const float* query, float* scores, int* best_id, float* best_score) {
+  int bid = -1;
+  float bs = 0.0f;
+  for (int kk = 0; kk < n_search; ++kk) {
+    const float* a = descs + (size_t)kk * 1024;
+    float s = 0.0f;
+    for (int i = 0; i < 1024; i++) s += a[i] * query[i];
+    if (scores) scores[kk] = s;
+    if (s > bs) {
+      bs = s;
+      bid = kk;
+    }
+  }
+  *best_id = bid;
+  *best_score = bs;
+  return 0;
+}
+
 const char* orc_kind() { return "port"; }
 }

@@ -285,6 +285,45 @@ class KLTTracker {
   int cap_ = 0;
 };
 
+// ---- loop-closure descriptor (:1100-1129) -------------------------------------------------------------------------------
+static std::vector<float> global_desc_32(const GrayImage& im) {
+  using namespace sfmgpu_shim;
+  if (im.w <= 0 || im.h <= 0) throw std::runtime_error("sfmgpu: global_desc_32: empty image");
+  sfmgpu_ctx* ctx = context();
+  auto dev = acquire_slot(im.w, im.h, 1);
+  sfmgpu_frames* f = dev->pool->frames;
+  check(ctx, sfmgpu_frames_upload(ctx, f, dev->slot, 1, im.pix.data()), "frames_upload");
+  std::vector<float> v(1024);
+  check(ctx, sfmgpu_global_desc32(ctx, f, dev->slot, 1, v.data()), "global_desc32");
+  return v;
+}
+
+// dot_desc :1124-1129 is a 1024-term loop: it stays a host inline (same float arithmetic, no contraction on x86-64);
+// the search over all stored keyframes (:1823-1831) has the batched device twin loop_candidate().
+static float dot_desc(const std::vector<float>& a, const std::vector<float>& b) {
+  float s = 0.0f;
+  const size_t n = std::min(a.size(), b.size());
+  for (size_t i = 0; i < n; i++) s += a[i] * b[i];
+  return s;
+}
+
+// best_id / best_score of the loop at :1823-1831 over kf_desc[0 .. n_search)
+static int loop_candidate(const std::vector<std::vector<float>>& kf_desc, int n_search, const std::vector<float>& query,
+                          float* best_score) {
+  using namespace sfmgpu_shim;
+  if (n_search <= 0) {
+    if (best_score) *best_score = 0.0f;
+    return -1;
+  }
+  std::vector<float> flat((size_t)n_search * 1024);
+  for (int k = 0; k < n_search; k++) std::copy(kf_desc[k].begin(), kf_desc[k].begin() + 1024, flat.begin() + (size_t)k * 1024);
+  int bid = -1;
+  float bs = 0.0f;
+  check(context(), sfmgpu_desc_search(context(), flat.data(), n_search, query.data(), nullptr, &bid, &bs), "desc_search");
+  if (best_score) *best_score = bs;
+  return bid;
+}
+
 // ---- find_E_ransac (:640-761) --------------------------------------------------------------------------------------
 struct RelPose {
   Mat33 R_ji;

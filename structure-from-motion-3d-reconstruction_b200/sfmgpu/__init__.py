@@ -31,7 +31,7 @@ SYMBOLS = [
     "sfmgpu_pairs_download", "sfmgpu_pairs_download_all", "sfmgpu_pairs_device_ptrs", "sfmgpu_tracker_create", "sfmgpu_tracker_destroy", "sfmgpu_tracker_reset",
     "sfmgpu_tracker_step", "sfmgpu_tracker_step_frames", "sfmgpu_tracker_tracks", "sfmgpu_tracker_totals",
     "sfmgpu_ransac_score", "sfmgpu_ransac_upload", "sfmgpu_ransac_score_resident", "sfmgpu_ransac_download",
-    "sfmgpu_ransac_hypotheses",
+    "sfmgpu_ransac_hypotheses", "sfmgpu_global_desc32", "sfmgpu_desc_search",
 ]
 
 
@@ -116,6 +116,8 @@ def load_library():
         "sfmgpu_ransac_upload": (_i, [_vp, _f64p, _f64p, _i, _f64p, _i]),
         "sfmgpu_ransac_score_resident": (_i, [_vp, _d, C.POINTER(_i), C.POINTER(_i)]),
         "sfmgpu_ransac_download": (_i, [_vp, _vp, _vp, _i]),
+        "sfmgpu_global_desc32": (_i, [_vp, _vp, _i, _i, _vp]),
+        "sfmgpu_desc_search": (_i, [_vp, _vp, _i, _vp, _vp, C.POINTER(_i), C.POINTER(C.c_float)]),
         "sfmgpu_ransac_hypotheses": (_i, [_vp, _f64p, _f64p, _i, _i32p, _i, _vp]),
     }
     for name, (res, args) in S.items():
@@ -251,6 +253,16 @@ class Context:
         self._ck(self.lib.sfmgpu_ransac_download(self.h, _ptr(counts), _ptr(inl), n))
         return counts[:H], inl
 
+    def desc_search(self, descs, query, n_search=None):
+        descs = np.ascontiguousarray(descs, np.float32).reshape(-1, 1024)
+        query = np.ascontiguousarray(query, np.float32).reshape(1024)
+        n = len(descs) if n_search is None else n_search
+        scores = np.zeros(max(n, 1), np.float32)
+        bid, bs = _i(-1), C.c_float(0)
+        self._ck(self.lib.sfmgpu_desc_search(self.h, _ptr(descs) if len(descs) else None, n, _ptr(query), _ptr(scores),
+                                             C.byref(bid), C.byref(bs)))
+        return bid.value, np.float32(bs.value), scores[:n]
+
     def sort_perm_desc(self, keys):
         keys = np.ascontiguousarray(keys, np.float64)
         perm = np.zeros(max(len(keys), 1), np.int32)
@@ -327,6 +339,12 @@ class Frames:
         n = _i(0)
         self.ctx._ck(self.ctx.lib.sfmgpu_corners(self.ctx.h, self.h_, frame, max_corners, quality, min_dist, xy, C.byref(n)))
         return xy[:n.value].copy()
+
+    def global_desc32(self, first, count):
+        """Loop-closure descriptors (1024 floats each) of frames [first, first+count)."""
+        out = np.zeros((max(count, 1), 1024), np.float32)
+        self.ctx._ck(self.ctx.lib.sfmgpu_global_desc32(self.ctx.h, self.h_, first, count, _ptr(out)))
+        return out[:count]
 
     def klt_track(self, frame_a, frame_b, p0, radius=5, iters=10, count=False):
         p0 = np.ascontiguousarray(p0, np.float64).reshape(-1, 2)

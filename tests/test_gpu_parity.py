@@ -305,6 +305,21 @@ def test_device_solver_matches_host_hypotheses(ctx, port, n, H):
     assert (counts != wc)[distinct].mean() < 0.01  # borderline points may flip on a few hypotheses
 
 
+# ---- loop-closure descriptor ----------------------------------------------------------------------
+@pytest.mark.parametrize("w,h", [(640, 480), (1920, 1080), (33, 70), (20, 15), (64, 64), (32, 32), (517, 129)])
+def test_loop_descriptor_bit_exact(ctx, checker, w, h):
+    imgs = [synth.frame(9, t, w, h) for t in (0, 5, 30, 31)]
+    f = _frames(ctx, imgs, 1)
+    got = f.global_desc32(0, 4)
+    want = np.stack([checker.global_desc32(i) for i in imgs])
+    assert np.array_equal(got, want)
+    bid, bs, sc = ctx.desc_search(got[:3], got[3])
+    wid, wbs, wsc = checker.desc_search(want[:3], want[3])
+    assert bid == wid and bs == wbs and np.array_equal(sc, wsc)
+    assert ctx.desc_search(got[:3], -got[0])[0] == -1 or checker.desc_search(want[:3], -want[0])[0] != -1
+    assert ctx.desc_search(got[:0], got[3])[:2] == (-1, 0.0)
+
+
 # ---- batched two-view front end ----------------------------------------------------------------------------------------
 def test_pair_frontend_batch(ctx, checker, g):
     imgs = [synth.frame(SEED, t, W, H) for t in range(6)]

@@ -109,3 +109,14 @@ def test_pair_frontend(port, ref):
     f0, f1 = synth.frame(41, 7, 256, 192), synth.frame(41, 8, 256, 192)
     a, b = ref.pair_frontend(f0, f1, 150), port.pair_frontend(f0, f1, 150)
     assert a[2] == b[2] and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("w,h", [(640, 480), (1920, 1080), (33, 70), (20, 15), (64, 64)])
+def test_loop_descriptor(w, h, port, ref):
+    """global_desc_32 :1100-1122 and the candidate search :1823-1831: restatement == compiled reference, bit for bit."""
+    from sfmgpu import synth
+    imgs = [synth.frame(9, t, w, h) for t in (0, 5, 30)]
+    da, db = [port.global_desc32(i) for i in imgs], [ref.global_desc32(i) for i in imgs]
+    assert all(np.array_equal(a, b) for a, b in zip(da, db))
+    ra, rb = port.desc_search(np.stack(da[:2]), da[2]), ref.desc_search(np.stack(db[:2]), db[2])
+    assert ra[0] == rb[0] and ra[1] == rb[1] and np.array_equal(ra[2], rb[2])
