@@ -195,6 +195,14 @@ int sfmgpu_ransac_hypotheses(sfmgpu_ctx* ctx, const double* xi_xy, const double*
                              double* E_out);
 
 
+/* ---- batched two-view DLT triangulation (opt-in): triangulate_dlt :1477-1516 -----------------------------------------------
+ * poses: P camera-to-world poses (PoseCW :157-168), 12 doubles each = R row-major + camera centre.  Track k observes
+ * pixel ui[k] in pose ia[k] and uj[k] in pose ib[k]; X_out [n][3] are the world points.  Same formulas as the
+ * reference; the 4x4 Jacobi uses CUDA's trig, so results agree to ~1e-10 relative, not bit for bit (the shim's
+ * single-track triangulate_dlt stays on the host and IS bit-identical). */
+int sfmgpu_triangulate_dlt(sfmgpu_ctx* ctx, const double* K, const double* poses, int P, const int32_t* ia, const int32_t* ib,
+                           const double* ui_xy, const double* uj_xy, int n, double* X_out);
+
 /* ---- loop-closure descriptor and candidate search: global_desc_32 :1100-1122, dot_desc :1124-1129, :1823-1831 ---------
  * desc_out: count descriptors of 1024 floats (host) for frames [first, first+count) (level 0 is read; bit-exact). */
 int sfmgpu_global_desc32(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first, int count, float* desc_out);

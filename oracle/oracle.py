@@ -60,6 +60,7 @@ class CpuFrontEnd:
             "pair_frontend_mt": (C.c_long, [_u8p, i, i, i, i, d, i, i, i, i, d, i, C.POINTER(C.c_long)]),
             "ransac_score_mt": (i, [_f64p, _f64p, i, _f64p, i, d, _i32p, i]),
             "global_desc32": (i, [_u8p, i, i, _f32p]),
+            "triangulate_dlt": (i, [_f64p, _f64p, i, _i32p, _i32p, _f64p, _f64p, i, _f64p]),
             "desc_search": (i, [_f32p, i, _f32p, _f32p, C.POINTER(i), C.POINTER(C.c_float)]),
         }
         if self.prefix == "orc":
@@ -185,6 +186,17 @@ class CpuFrontEnd:
         counts = np.zeros(len(E), np.int32)
         self._f("ransac_score_mt")(xi, xj, len(xi), E, len(E), thr, counts, threads)
         return counts
+
+    # ---- batched triangulate_dlt (:1477-1516) ------------------------------------------------------------------
+    def triangulate_dlt(self, K, poses, ia, ib, ui, uj):
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 12)
+        ia, ib = np.ascontiguousarray(ia, np.int32), np.ascontiguousarray(ib, np.int32)
+        ui = np.ascontiguousarray(ui, np.float64).reshape(-1, 2)
+        uj = np.ascontiguousarray(uj, np.float64).reshape(-1, 2)
+        X = np.zeros((max(len(ui), 1), 3))
+        if len(ui):
+            self._f("triangulate_dlt")(np.ascontiguousarray(K, np.float64).reshape(9), poses, len(poses), ia, ib, ui, uj, len(ui), X)
+        return X[:len(ui)]
 
     # ---- loop-closure descriptor (:1100-1129) and candidate search (:1823-1831) -----------------------------
     def global_desc32(self, img):

@@ -12,7 +12,8 @@
 //   build_pyr :224-232, shi_tomasi :237-302, KLTTracker :323-466 (reset/step/track_one_public),
 //   norm_point/invert_K :471-501, eight_point_E :609-627, sampson_err :629-638,
 //   find_E_ransac :646-761, stateless two-view front end :1836-1857 (lifted, see ref_pair_frontend),
-//   global_desc_32 :1100-1122, dot_desc :1124-1129, loop-candidate search :1823-1831 (lifted, see ref_desc_search).
+//   global_desc_32 :1100-1122, dot_desc :1124-1129, loop-candidate search :1823-1831 (lifted, see ref_desc_search),
+//   triangulate_dlt :1477-1516.
 #define main ref_main_unused
 #include "cpp/src/templering_sfm.cpp"
 #undef main
@@ -298,6 +299,25 @@ int ref_ransac_score_mt(const double* xi, const double* xj, int n, const double*
 }
 
 const char* ref_kind() { return "reference"; }
+
+// Batched triangulate_dlt (:1477-1516): poses are PoseCW (:157-168) as 9 doubles R (camera->world, row-major) + 3 doubles
+// camera centre; track k observes ui[k] in pose ia[k] and uj[k] in pose ib[k].
+int ref_triangulate_dlt(const double* K, const double* poses, int P, const int* ia, const int* ib, const double* ui, const double* uj,
+                        int n, double* X) {
+  std::vector<PoseCW> ps((size_t)P);
+  for (int p = 0; p < P; p++) {
+    for (int k = 0; k < 9; k++) ps[p].R.a[k] = poses[12 * p + k];
+    ps[p].t = Vec3{poses[12 * p + 9], poses[12 * p + 10], poses[12 * p + 11]};
+  }
+  const Mat33 Km = mat(K);
+  for (int k = 0; k < n; k++) {
+    const Vec3 x = triangulate_dlt(Km, ps[ia[k]], ps[ib[k]], Vec2{ui[2 * k], ui[2 * k + 1]}, Vec2{uj[2 * k], uj[2 * k + 1]});
+    X[3 * k] = x.x;
+    X[3 * k + 1] = x.y;
+    X[3 * k + 2] = x.z;
+  }
+  return 0;
+}
 
 // Loop-closure descriptor (:1100-1122) of one image: 1024 floats.
 int ref_global_desc32(const uint8_t* pix, int w, int h, float* out) {

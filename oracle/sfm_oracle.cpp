@@ -822,6 +822,40 @@ int orc_synth_frames(uint32_t seed, int t0, int nframes, int w, int h, uint8_t* 
   return 0;
 }
 
+// ---- batched triangulate_dlt (:1477-1516): poses = 9 doubles R (camera->world) + 3 doubles centre each ------------------
+int orc_triangulate_dlt(const double* K, const double* poses, int P, const int* ia, const int* ib, const double* ui, const double* uj,
+                        int n, double* X) {
+  (void)P;
+  double Ki[9];
+  if (!kinv(K, Ki)) return -1;
+  for (int k = 0; k < n; k++) {
+    double A[16];
+    for (int cam = 0; cam < 2; cam++) {
+      const double* pose = poses + 12 * (cam == 0 ? ia[k] : ib[k]);
+      const double* u = cam == 0 ? ui + 2 * k : uj + 2 * k;
+      double x, y;
+      normalise(Ki, u[0], u[1], x, y);
+      double Rw[9];
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) Rw[3 * r + c] = pose[3 * c + r];
+      const double tx = -(Rw[0] * pose[9] + Rw[1] * pose[10] + Rw[2] * pose[11]);
+      const double ty = -(Rw[3] * pose[9] + Rw[4] * pose[10] + Rw[5] * pose[11]);
+      const double tz = -(Rw[6] * pose[9] + Rw[7] * pose[10] + Rw[8] * pose[11]);
+      double* o = A + 8 * cam;
+      o[0] = x * Rw[6] - Rw[0]; o[1] = x * Rw[7] - Rw[1]; o[2] = x * Rw[8] - Rw[2]; o[3] = x * tz - tx;
+      o[4] = y * Rw[6] - Rw[3]; o[5] = y * Rw[7] - Rw[4]; o[6] = y * Rw[8] - Rw[5]; o[7] = y * tz - ty;
+    }
+    std::vector<double> G, w, V;
+    gram(A, 4, 4, G);
+    jacobi(G, 4, 80, w, V);
+    const double ww = V[12];
+    X[3 * k] = V[0] / ww;
+    X[3 * k + 1] = V[4] / ww;
+    X[3 * k + 2] = V[8] / ww;
+  }
+  return 0;
+}
+
 // ---- loop-closure descriptor (:1100-1122) and candidate search (:1124-1129, :1823-1831) ----------------------------
 // Halve until both sides are <= 32, nearest-sample to 32x32 (std::round), float values, mean in double, subtract
 // (float)mean in float, squared norm accumulated in double in raster order, scale by 1/sqrt(n2 + 1e-12) in double and

@@ -161,7 +161,88 @@ __global__ void __launch_bounds__(64) eight_point_kernel(const double2* __restri
     }
 }
 
+// Batched triangulate_dlt (:1477-1516), one thread per track.  Same formulas and order as the host
+// restatement (host/two_view_host.hpp: triangulate_dlt); the 4x4 Jacobi uses CUDA's trig, hence ~1e-10 relative, not
+// bit-identical.
+__global__ void __launch_bounds__(128) triangulate_kernel(const double* __restrict__ Kinv, const double* __restrict__ poses,
+                                                         const int* __restrict__ ia, const int* __restrict__ ib,
+                                                         const double2* __restrict__ ui, const double2* __restrict__ uj, int n, int P,
+                                                         double* __restrict__ X) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  double A[16], G[16], Q[16];
+  for (int cam = 0; cam < 2; cam++) {
+    int pi = cam == 0 ? ia[k] : ib[k];
+    pi = pi < 0 ? 0 : (pi >= P ? P - 1 : pi);
+    const double* pose = poses + 12 * (size_t)pi;
+    const double2 u = cam == 0 ? ui[k] : uj[k];
+    const double a = Kinv[0] * u.x + Kinv[1] * u.y + Kinv[2] * 1.0;
+    const double b = Kinv[3] * u.x + Kinv[4] * u.y + Kinv[5] * 1.0;
+    const double c = Kinv[6] * u.x + Kinv[7] * u.y + Kinv[8] * 1.0;
+    const double x = a / c, y = b / c;
+    double Rw[9];
+    for (int r = 0; r < 3; r++)
+      for (int cc = 0; cc < 3; cc++) Rw[3 * r + cc] = pose[3 * cc + r];
+    const double tx = -(Rw[0] * pose[9] + Rw[1] * pose[10] + Rw[2] * pose[11]);
+    const double ty = -(Rw[3] * pose[9] + Rw[4] * pose[10] + Rw[5] * pose[11]);
+    const double tz = -(Rw[6] * pose[9] + Rw[7] * pose[10] + Rw[8] * pose[11]);
+    double* o = A + 8 * cam;
+    o[0] = x * Rw[6] - Rw[0]; o[1] = x * Rw[7] - Rw[1]; o[2] = x * Rw[8] - Rw[2]; o[3] = x * tz - tx;
+    o[4] = y * Rw[6] - Rw[3]; o[5] = y * Rw[7] - Rw[4]; o[6] = y * Rw[8] - Rw[5]; o[7] = y * tz - ty;
+  }
+  for (int i = 0; i < 4; i++)
+    for (int j = i; j < 4; j++) {
+      double s = 0;
+      for (int r = 0; r < 4; r++) s += A[r * 4 + i] * A[r * 4 + j];
+      G[i * 4 + j] = s;
+      G[j * 4 + i] = s;
+    }
+  jacobi_dev<4>(G, Q, 80);
+  int m = 0;
+  for (int i = 1; i < 4; i++)
+    if (G[i * 5] < G[m * 5]) m = i;
+  const double ww = Q[12 + m];
+  X[3 * (size_t)k] = Q[m] / ww;
+  X[3 * (size_t)k + 1] = Q[4 + m] / ww;
+  X[3 * (size_t)k + 2] = Q[8 + m] / ww;
+}
+
 }  // namespace
+
+extern "C" int sfmgpu_triangulate_dlt(sfmgpu_ctx* ctx, const double* K, const double* poses, int P, const int32_t* ia, const int32_t* ib,
+                                      const double* ui_xy, const double* uj_xy, int n, double* X_out) {
+  if (!ctx || n < 0 || P < 0) return sfm_fail(ctx, SFMGPU_E_ARG, "triangulate_dlt: bad sizes");
+  if (n == 0) return 0;
+  if (!K || !poses || P < 1 || !ia || !ib || !ui_xy || !uj_xy || !X_out) return sfm_fail(ctx, SFMGPU_E_ARG, "triangulate_dlt: null pointer");
+  // K^-1 on the host, exactly as invert_K :471-486 (adjugate / determinant)
+  const double d = K[0] * (K[4] * K[8] - K[5] * K[7]) - K[1] * (K[3] * K[8] - K[5] * K[6]) + K[2] * (K[3] * K[7] - K[4] * K[6]);
+  if (fabs(d) < 1e-12) return sfm_fail(ctx, SFMGPU_E_ARG, "triangulate_dlt: singular K");
+  const double Ki[9] = {(K[4] * K[8] - K[5] * K[7]) / d,  -(K[1] * K[8] - K[2] * K[7]) / d, (K[1] * K[5] - K[2] * K[4]) / d,
+                        -(K[3] * K[8] - K[5] * K[6]) / d, (K[0] * K[8] - K[2] * K[6]) / d,  -(K[0] * K[5] - K[2] * K[3]) / d,
+                        (K[3] * K[7] - K[4] * K[6]) / d,  -(K[0] * K[7] - K[1] * K[6]) / d, (K[0] * K[4] - K[1] * K[3]) / d};
+  const size_t bK = 128, bP = ((size_t)P * 96 + 255) & ~(size_t)255, bI = ((size_t)n * 4 + 255) & ~(size_t)255,
+               bU = ((size_t)n * 16 + 255) & ~(size_t)255, bX = (size_t)n * 24;
+  SFM_TRY(sfm_reserve(ctx, ctx->cs_work, bK + bP + 2 * bI + 2 * bU + bX + 256));
+  char* base = (char*)ctx->cs_work.p;
+  double* dK = (double*)base;
+  double* dP = (double*)(base + bK);
+  int* dia = (int*)(base + bK + bP);
+  int* dib = (int*)(base + bK + bP + bI);
+  double2* dui = (double2*)(base + bK + bP + 2 * bI);
+  double2* duj = (double2*)(base + bK + bP + 2 * bI + bU);
+  double* dX = (double*)(base + bK + bP + 2 * bI + 2 * bU);
+  SFM_CUDA(ctx, cudaMemcpyAsync(dK, Ki, sizeof Ki, cudaMemcpyHostToDevice, ctx->stream));
+  SFM_CUDA(ctx, cudaMemcpyAsync(dP, poses, (size_t)P * 96, cudaMemcpyHostToDevice, ctx->stream));
+  SFM_CUDA(ctx, cudaMemcpyAsync(dia, ia, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  SFM_CUDA(ctx, cudaMemcpyAsync(dib, ib, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  SFM_CUDA(ctx, cudaMemcpyAsync(dui, ui_xy, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+  SFM_CUDA(ctx, cudaMemcpyAsync(duj, uj_xy, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+  SFM_LAUNCH(ctx, triangulate_kernel, sfm_cdiv(n, 128), 128, 0, (const double*)dK, (const double*)dP, (const int*)dia, (const int*)dib,
+             (const double2*)dui, (const double2*)duj, n, P, dX);
+  SFM_CUDA(ctx, cudaMemcpyAsync(X_out, dX, (size_t)n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
 
 extern "C" int sfmgpu_ransac_hypotheses(sfmgpu_ctx* ctx, const double* xi_xy, const double* xj_xy, int n, const int32_t* idx8, int H,
                                         double* E_out) {

@@ -324,6 +324,31 @@ static int loop_candidate(const std::vector<std::vector<float>>& kf_desc, int n_
   return bid;
 }
 
+// ---- triangulate_dlt (:1477-1516) -------------------------------------------------------------------------------------------
+// PoseCW is defined inside the reference TU (:157-168), after the point where this header is included, so the shim
+// takes the pose as (R camera->world, camera centre).  The single-track form runs on the host and is bit-identical;
+// triangulate_tracks() is the batched device twin (opt-in, ~1e-10 relative).
+static Vec3 triangulate_dlt_rt(const Mat33& K, const Mat33& Ri, const Vec3& Ci, const Mat33& Rj, const Vec3& Cj, Vec2 ui, Vec2 uj) {
+  double ki[9];
+  if (!sfmgpu_host::invert_K(K.a.data(), ki)) throw std::runtime_error("Singular K");
+  const double ci[3] = {Ci.x, Ci.y, Ci.z}, cj[3] = {Cj.x, Cj.y, Cj.z}, a[2] = {ui.x, ui.y}, b[2] = {uj.x, uj.y};
+  double X[3];
+  sfmgpu_host::triangulate_dlt(K.a.data(), Ri.a.data(), ci, Rj.a.data(), cj, a, b, X);
+  return Vec3{X[0], X[1], X[2]};
+}
+
+static std::vector<Vec3> triangulate_tracks(const Mat33& K, const std::vector<std::array<double, 12>>& poses, const std::vector<int>& ia,
+                                            const std::vector<int>& ib, const std::vector<Vec2>& ui, const std::vector<Vec2>& uj) {
+  using namespace sfmgpu_shim;
+  const int n = (int)ui.size();
+  std::vector<Vec3> out((size_t)n);
+  if (n == 0) return out;
+  static_assert(sizeof(Vec2) == 16 && sizeof(Vec3) == 24, "layout");
+  check(context(), sfmgpu_triangulate_dlt(context(), K.a.data(), poses[0].data(), (int)poses.size(), ia.data(), ib.data(), &ui[0].x, &uj[0].x,
+                                          n, &out[0].x), "triangulate_dlt");
+  return out;
+}
+
 // ---- find_E_ransac (:640-761) --------------------------------------------------------------------------------------
 struct RelPose {
   Mat33 R_ji;

@@ -160,6 +160,16 @@ int shim_find_E_ransac(const double* K, const double* pi, const double* pj, int 
   });
 }
 
+// host single-track triangulation (bit-identical to the reference), n tracks in a loop
+int shim_host_triangulate(const double* K, const double* poses, const int* ia, const int* ib, const double* ui, const double* uj, int n,
+                          double* X) {
+  for (int k = 0; k < n; k++) {
+    const double *pi = poses + 12 * ia[k], *pj = poses + 12 * ib[k];
+    sfmgpu_host::triangulate_dlt(K, pi, pi + 9, pj, pj + 9, ui + 2 * k, uj + 2 * k, X + 3 * k);
+  }
+  return 0;
+}
+
 // opt-in device solver for find_E_ransac
 void shim_set_device_solver(int on) { sfmgpu_shim::set_device_solver(on != 0); }
 

@@ -243,4 +243,38 @@ inline void recover_pose(const double* bestE, const double* xi, const double* xj
   t[2] = ts[bi].z;
 }
 
+// triangulate_dlt (:1477-1516): poses are camera-to-world (R row-major, camera centre C); ui / uj in pixels.
+inline void triangulate_dlt(const double* K, const double* Ri, const double* Ci, const double* Rj, const double* Cj, const double* ui,
+                            const double* uj, double* X) {
+  double Ki[9];
+  invert_K(K, Ki);  // the reference throws on a singular K before it gets here
+  double xi[2], xj[2];
+  norm_point(Ki, ui[0], ui[1], xi);
+  norm_point(Ki, uj[0], uj[1], xj);
+  double A[16];
+  auto rows = [&](const double* R, const double* C, const double* x, double* out) {
+    double Rw[9];
+    transp(R, Rw);  // world -> camera (:164-167)
+    const P3 m = mulv(Rw, P3{C[0], C[1], C[2]});
+    const P3 t{-m.x, -m.y, -m.z};
+    for (int which = 0; which < 2; which++) {
+      const double sgn = which == 0 ? x[0] : x[1];
+      double* o = out + 4 * which;
+      o[0] = sgn * Rw[6] - Rw[3 * which + 0];
+      o[1] = sgn * Rw[7] - Rw[3 * which + 1];
+      o[2] = sgn * Rw[8] - Rw[3 * which + 2];
+      o[3] = sgn * t.z - (which == 0 ? t.x : t.y);
+    }
+  };
+  rows(Ri, Ci, xi, A);
+  rows(Rj, Cj, xj, A + 8);
+  double G[16], w[4], V[16];
+  gram<4, 4>(A, G);
+  jacobi<4>(G, 80, w, V);
+  const double ww = V[12];
+  X[0] = V[0] / ww;
+  X[1] = V[4] / ww;
+  X[2] = V[8] / ww;
+}
+
 }  // namespace sfmgpu_host

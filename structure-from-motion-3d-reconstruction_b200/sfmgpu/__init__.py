@@ -31,7 +31,7 @@ SYMBOLS = [
     "sfmgpu_pairs_download", "sfmgpu_pairs_download_all", "sfmgpu_pairs_device_ptrs", "sfmgpu_tracker_create", "sfmgpu_tracker_destroy", "sfmgpu_tracker_reset",
     "sfmgpu_tracker_step", "sfmgpu_tracker_step_frames", "sfmgpu_tracker_tracks", "sfmgpu_tracker_totals",
     "sfmgpu_ransac_score", "sfmgpu_ransac_upload", "sfmgpu_ransac_score_resident", "sfmgpu_ransac_download",
-    "sfmgpu_ransac_hypotheses", "sfmgpu_global_desc32", "sfmgpu_desc_search",
+    "sfmgpu_ransac_hypotheses", "sfmgpu_global_desc32", "sfmgpu_desc_search", "sfmgpu_triangulate_dlt",
 ]
 
 
@@ -116,6 +116,7 @@ def load_library():
         "sfmgpu_ransac_upload": (_i, [_vp, _f64p, _f64p, _i, _f64p, _i]),
         "sfmgpu_ransac_score_resident": (_i, [_vp, _d, C.POINTER(_i), C.POINTER(_i)]),
         "sfmgpu_ransac_download": (_i, [_vp, _vp, _vp, _i]),
+        "sfmgpu_triangulate_dlt": (_i, [_vp, _f64p, _f64p, _i, _i32p, _i32p, _f64p, _f64p, _i, _f64p]),
         "sfmgpu_global_desc32": (_i, [_vp, _vp, _i, _i, _vp]),
         "sfmgpu_desc_search": (_i, [_vp, _vp, _i, _vp, _vp, C.POINTER(_i), C.POINTER(C.c_float)]),
         "sfmgpu_ransac_hypotheses": (_i, [_vp, _f64p, _f64p, _i, _i32p, _i, _vp]),
@@ -252,6 +253,18 @@ class Context:
         inl = np.full(max(n, 1), -1, np.int32)
         self._ck(self.lib.sfmgpu_ransac_download(self.h, _ptr(counts), _ptr(inl), n))
         return counts[:H], inl
+
+    def triangulate_dlt(self, K, poses, ia, ib, ui, uj):
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 12)
+        ia, ib = np.ascontiguousarray(ia, np.int32), np.ascontiguousarray(ib, np.int32)
+        ui = np.ascontiguousarray(ui, np.float64).reshape(-1, 2)
+        uj = np.ascontiguousarray(uj, np.float64).reshape(-1, 2)
+        n = len(ui)
+        X = np.zeros((max(n, 1), 3))
+        if n:
+            self._ck(self.lib.sfmgpu_triangulate_dlt(self.h, np.ascontiguousarray(K, np.float64).reshape(9), poses, len(poses), ia, ib,
+                                                     ui, uj, n, X))
+        return X[:n]
 
     def desc_search(self, descs, query, n_search=None):
         descs = np.ascontiguousarray(descs, np.float32).reshape(-1, 1024)

@@ -64,3 +64,33 @@ def two_view_scene(n, seed=777, outlier_frac=0.3, sigma=0.3):
     out = rng.random(n) < outlier_frac
     pj[out] = np.stack([rng.uniform(0, 640, out.sum()), rng.uniform(0, 480, out.sum())], 1)
     return np.ascontiguousarray(pi), np.ascontiguousarray(pj)
+
+
+def triangulation_scene(n, P=5, seed=3):
+    """P camera-to-world poses looking at a cloud of n points; every track is seen from two different poses."""
+    rng = np.random.default_rng(seed)
+    poses = np.zeros((P, 12))
+    Rs, Cs = [], []
+    for p in range(P):
+        w = rng.normal(0, 0.08, 3)
+        th = np.linalg.norm(w)
+        k = w / th
+        Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        R = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx  # camera -> world
+        Cc = rng.normal(0, 0.15, 3)
+        poses[p, :9], poses[p, 9:] = R.reshape(9), Cc
+        Rs.append(R)
+        Cs.append(Cc)
+    X = np.c_[rng.uniform(-0.5, 0.5, n), rng.uniform(-0.4, 0.4, n), rng.uniform(1.5, 2.5, n)]
+    ia = rng.integers(0, P, n).astype(np.int32)
+    ib = ((ia + rng.integers(1, P, n)) % P).astype(np.int32)
+
+    def proj(idx):
+        out = np.zeros((n, 2))
+        for t in range(n):
+            xc = Rs[idx[t]].T @ (X[t] - Cs[idx[t]])
+            u = TEMPLE_K @ (xc / xc[2])
+            out[t] = u[:2]
+        return out + rng.normal(0, 0.3, (n, 2))
+
+    return poses, ia, ib, proj(ia), proj(ib), X

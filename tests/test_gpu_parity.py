@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import TEMPLE_K, two_view_scene
+from conftest import TEMPLE_K, two_view_scene, triangulation_scene
 from sfmgpu import synth
 import sfmgpu
 
@@ -303,6 +303,17 @@ def test_device_solver_matches_host_hypotheses(ctx, port, n, H):
     wc, wbh, wi = port.ransac_score(xi, xj, Eh, 1e-3)
     assert bh == wbh and bn == len(wi) and np.array_equal(inl[:bn], wi)
     assert (counts != wc)[distinct].mean() < 0.01  # borderline points may flip on a few hypotheses
+
+
+# ---- batched DLT triangulation (opt-in) -----------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 333, 5000])
+def test_device_triangulation(ctx, checker, n):
+    poses, ia, ib, ui, uj, _ = triangulation_scene(n, seed=n)
+    got = ctx.triangulate_dlt(TEMPLE_K, poses, ia, ib, ui, uj)
+    want = checker.triangulate_dlt(TEMPLE_K, poses, ia, ib, ui, uj)
+    rel = np.abs(got - want).max(1) / np.abs(want).max(1)
+    print(f"device triangulation: max rel. deviation {rel.max():.2e} over {n} tracks")
+    assert rel.max() < 1e-7 and np.quantile(rel, 0.99) < 1e-9
 
 
 # ---- loop-closure descriptor ----------------------------------------------------------------------

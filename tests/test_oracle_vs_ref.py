@@ -5,7 +5,7 @@ The reference ships no tests or golden vectors; these cases are 
 import numpy as np
 import pytest
 
-from conftest import TEMPLE_K, two_view_scene
+from conftest import TEMPLE_K, two_view_scene, triangulation_scene
 from sfmgpu import synth
 
 
@@ -120,3 +120,11 @@ def test_loop_descriptor(w, h, port, ref):
     assert all(np.array_equal(a, b) for a, b in zip(da, db))
     ra, rb = port.desc_search(np.stack(da[:2]), da[2]), ref.desc_search(np.stack(db[:2]), db[2])
     assert ra[0] == rb[0] and ra[1] == rb[1] and np.array_equal(ra[2], rb[2])
+
+
+def test_triangulate_dlt(port, ref):
+    """triangulate_dlt :1477-1516: restatement == compiled reference, bit for bit; and close to the true points."""
+    poses, ia, ib, ui, uj, X = triangulation_scene(400)
+    a, b = ref.triangulate_dlt(TEMPLE_K, poses, ia, ib, ui, uj), port.triangulate_dlt(TEMPLE_K, poses, ia, ib, ui, uj)
+    assert np.array_equal(a, b)
+    assert np.median(np.linalg.norm(a - X, axis=1)) < 0.05

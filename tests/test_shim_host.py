@@ -42,3 +42,12 @@ def test_pose_recovery_bit_identical(shim, ref, n, iters, thr):
 
 def test_singular_K_is_reported(shim):
     assert shim.shim_host_norm_points(np.zeros(9), np.zeros((1, 2)), 1, np.zeros((1, 2))) == -1
+
+
+def test_host_triangulation_bit_identical(shim, ref):
+    """host/two_view_host.hpp: triangulate_dlt == the compiled reference (:1477-1516), bit for bit."""
+    from conftest import triangulation_scene
+    poses, ia, ib, ui, uj, _ = triangulation_scene(300, seed=11)
+    X = np.zeros((300, 3))
+    shim.shim_host_triangulate(np.ascontiguousarray(TEMPLE_K.reshape(9)), poses, ia, ib, ui, uj, 300, X)
+    assert np.array_equal(X, ref.triangulate_dlt(TEMPLE_K, poses, ia, ib, ui, uj))
