@@ -69,3 +69,24 @@ def gather_pair_results(n_kept, li, lj, dst=0):
     li_list = [fi[offs[k]:offs[k + 1]] for k in range(len(counts))]
     lj_list = [fj[offs[k]:offs[k + 1]] for k in range(len(counts))]
     return counts, li_list, lj_list
+
+
+def run_sequences(sequences, device=0, lkcfg_kw=None, max_workers=8):
+    """Sequence mode on ONE GPU (BASELINE.json config C5: several independent sequences per GPU): every sequence gets
+    its own context (= its own CUDA stream) and its own stateful tracker, stepped from its own host thread (ctypes
+    releases the GIL, so the trackers' kernels and copies overlap).  `sequences` is a list of iterables of uint8 frames;
+    returns per sequence the list of StepOut tuples (prev_xy, cur_xy, ids), identical to running them one by one."""
+    from concurrent.futures import ThreadPoolExecutor
+    import sfmgpu
+    lkcfg_kw = lkcfg_kw or {}
+
+    def one(seq):
+        ctx = sfmgpu.Context(device)
+        trk = ctx.tracker(**lkcfg_kw)
+        out = [trk.step(img) for img in seq]
+        del trk
+        ctx.close()
+        return out
+
+    with ThreadPoolExecutor(max_workers=max(1, min(max_workers, len(sequences)))) as ex:
+        return list(ex.map(one, sequences))

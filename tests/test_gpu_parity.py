@@ -244,6 +244,21 @@ def test_tracker_resident_frames_equals_host_fed(ctx):
             assert np.array_equal(x, y)
 
 
+def test_c5_sequences_in_parallel(ctx):
+    """BASELINE.json config C5 (several independent sequences per GPU): one context + tracker + host thread per
+    sequence; the results equal the one-by-one run."""
+    from sfmgpu import sched
+    seqs = [[synth.frame(100 + s, t, W, H) for t in range(5)] for s in range(4)]
+    kw = dict(max_tracks=150, min_tracks=120)
+    par = sched.run_sequences(seqs, 0, kw, max_workers=4)
+    for s, seq in enumerate(seqs):
+        trk = ctx.tracker(**kw)
+        for t, img in enumerate(seq):
+            want = trk.step(img)
+            for a, b in zip(par[s][t], want):
+                assert np.array_equal(a, b), (s, t)
+
+
 # ---- RANSAC scoring ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n,H", [(300, 40), (2200, 250), (10000, 64), (9, 3), (513, 129)])
 def test_ransac_counts_bit_exact(ctx, checker, port, n, H):
