@@ -110,6 +110,10 @@ int sfmgpu_corners(sfmgpu_ctx* ctx, sfmgpu_frames* f, int frame, int max_corners
 /* The libstdc++ std::sort permutation (:286) of n keys sorted descending, computed on the device:
  * perm[i] = original index of the element that std::sort leaves at position i. */
 int sfmgpu_sort_perm_desc(sfmgpu_ctx* ctx, const double* keys, int n, int32_t* perm);
+/* How every later corner selection of this context orders its candidates (results are bit-identical either way):
+ * 0 = radix sort by score, and the exact introsort emulation only for frames where two candidates with identical
+ * scores fall inside the consumed prefix (default); 1 = introsort emulation for every frame (tests, A/B timing). */
+int sfmgpu_select_set_mode(sfmgpu_ctx* ctx, int mode);
 
 /* ---- KLT: track_one / lk_step / sample_bilinear (:183-198, :396-460) ------------------------------- */
 /* Forward track frame a -> b and backward b -> a for n points (what :356-361 and :1846-1848 do per

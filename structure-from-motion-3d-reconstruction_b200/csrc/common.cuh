@@ -59,6 +59,7 @@ struct sfmgpu_ctx {
   DevBuf flush;
   DevBuf klt_in, klt_p1, klt_pb, klt_nit, klt_keep, klt_defer;
   int klt_mode = 0;  // 0 auto, 1 warp-per-feature, 2 lane-per-feature (tests / profiling)
+  int select_mode = 0;  // 0 radix sort + tie fallback, 1 introsort emulation only (tests / profiling)
   DevBuf cs_work;    // corner-score work area for single-frame calls
   DevBuf sel_work;   // corner-select work area
   DevBuf misc;       // small scalars

@@ -365,19 +365,33 @@ __global__ void __launch_bounds__(1024) bitmap_scan_kernel(CornerWorkView wv) {
   if (tid == 1023) wv.ntotal[fr] = run;  // chunk boundaries are monotone: the last thread ends at the total
 }
 
-// Scatter the unordered candidate list into raster order.
-__global__ void __launch_bounds__(256) order_kernel(CornerWorkView wv, int w) {
+// Scatter the unordered candidate list into raster order.  Also emits, per candidate, the packed word the radix
+// selection path sorts: (order code << 32) | y << 16 | x, where the code is the distance of the score's bit pattern
+// below the frame maximum, shifted so that the whole candidate range [thr, max] fits 32 bits (ascending code =
+// descending score; scores are non-negative doubles, so bit order is value order).
+__global__ void __launch_bounds__(256) order_kernel(CornerWorkView wv, int w, double quality) {
   const int fr = blockIdx.y;
   const unsigned n = min(wv.ncand[fr], (unsigned)wv.cand_cap);
   const size_t cb = (size_t)fr * wv.cand_cap, wb = (size_t)fr * wv.words_per_frame;
+  const double maxv = 0.125 * __longlong_as_double(wv.maxbits[fr]);
+  const double thr = maxv * quality;
+  const unsigned long long maxkey = (unsigned long long)__double_as_longlong(maxv);
+  const unsigned long long thrkey = thr > 0.0 ? (unsigned long long)__double_as_longlong(thr) : 0ull;
+  const unsigned long long range = maxkey > thrkey ? maxkey - thrkey : 0ull;
+  const int bits = 64 - __clzll((long long)range);
+  const int shift = bits > 32 ? bits - 32 : 0;
   for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
     const unsigned pix = wv.tmp_idx[cb + e];
     const unsigned y = pix / (unsigned)w, x = pix - y * (unsigned)w;
     const size_t word = wb + (size_t)y * wv.wpr + (x >> 5);
     const unsigned rank = wv.wordoff[word] + __popc(wv.bitmap[word] & ((1u << (x & 31)) - 1u));
     if (rank < (unsigned)wv.cand_cap) {
-      wv.key[cb + rank] = wv.tmp_key[cb + e];
-      wv.idx[cb + rank] = pix;
+      const unsigned long long k = wv.tmp_key[cb + e];
+      wv.key[cb + rank] = k;
+      const unsigned yx = (y << 16) | x;
+      wv.idx[cb + rank] = yx;
+      const unsigned long long code = (maxkey - k) >> shift;  // k in [thrkey, maxkey]: < 2^32
+      wv.pk_a[cb + rank] = (code << 32) | yx;
     }
   }
 }
@@ -408,12 +422,13 @@ int sfm_corner_candidates_batch(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int fir
   SFM_LAUNCH(ctx, score_tile_kernel<1>, grid, 256, sizeof(ScoreSmem), f->lvl[0], f->w, f->h, f->pitch[0], f->fstride[0], first, wv,
              quality);
   SFM_LAUNCH(ctx, bitmap_scan_kernel, count, 1024, 0, wv);
-  SFM_LAUNCH(ctx, order_kernel, dim3(16, count), 256, 0, wv, f->w);
+  SFM_LAUNCH(ctx, order_kernel, dim3(16, count), 256, 0, wv, f->w, quality);
   return 0;
 }
 
 int sfm_candidates_single(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int frame, double quality, int32_t* xy, double* score,
                           int cap, int* n_out, double* max_score) {
+  if (f->w > 32767 || f->h > 32767) return sfm_fail(ctx, SFMGPU_E_ARG, "corner_candidates: image larger than 32767 px");
   const int cand_cap = f->w * f->h;
   const size_t bytes = sfm_corner_work_bytes(f->w, f->h, 1, cand_cap);
   SFM_TRY(sfm_reserve(ctx, ctx->cs_work, bytes));
@@ -439,8 +454,8 @@ int sfm_candidates_single(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int frame, do
   SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (xy)
     for (unsigned i = 0; i < n; i++) {
-      xy[2 * i] = (int32_t)(idx[i] % (unsigned)f->w);
-      xy[2 * i + 1] = (int32_t)(idx[i] / (unsigned)f->w);
+      xy[2 * i] = (int32_t)(idx[i] & 0xFFFFu);  // idx holds y << 16 | x
+      xy[2 * i + 1] = (int32_t)(idx[i] >> 16);
     }
   return 0;
 }

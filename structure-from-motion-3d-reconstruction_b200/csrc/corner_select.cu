@@ -11,6 +11,13 @@
 // at a time, each warp finishing its segment completely (warp partitions, then one leaf per lane with the
 // stable insertion sort).  Depth-limit exhaustion takes the sequential heap-sort restatement.
 //
+// Fast path (default): the order std::sort produces is unique wherever the scores are distinct, so the candidates are
+// first sorted by a segmented LSD radix sort (radix_*_kernel: 4 passes of 8 bits over a 32-bit order code, then
+// radix_fixup_kernel orders the few candidates that share a code by their full 64-bit score) and the selection walks
+// that list.  Only if two candidates with IDENTICAL scores lie inside the prefix the selection consumed — the one
+// case where introsort's tie order is observable — is the frame redone with the exact introsort emulation above
+// (status 3 -> select_kernel mode 3).  Results are bit-identical either way (tests force both paths).
+//
 // Selection: greedy acceptance only ever depends on higher-priority candidates, so a chunk of the sorted
 // prefix is decided in parallel: (1) kill candidates within min_dist of corners accepted in earlier chunks
 // (lookup in a min_dist-cell grid holding <= 2 corners per cell), (2) resolve conflicts inside the chunk by
@@ -354,7 +361,394 @@ __device__ void produce_sorted(SelSmem& sm, sfm_key_t* key, uint32_t* idx, uint3
   }
 }
 
+// ---- radix path -------------------------------------------------------------------------------------------------------
+// One block owns one frame: a stable LSD radix sort of the packed words (order code << 32 | y << 16 | x), 8-bit digits
+// of the code.  Because the block sees the whole frame, the four digit histograms are order-independent and come from
+// ONE sweep; every pass is then a single sweep over the frame in tiles of THREADS*ITEMS words: rank inside the warp by
+// match_any rounds (round r of a warp covers 32 consecutive words, so rank order = position order), across warps and
+// tiles by running per-digit offsets in shared memory.  Passes whose digit is the same for every word are skipped.  A
+// final sweep puts runs of equal codes into descending order of the full 64-bit score (one thread per run, in place; a
+// run is a handful of words; the score is found through the candidate bitmap's raster rank) and records the first
+// position holding two IDENTICAL scores.
+constexpr int RX_PASSES = 4;   // 8-bit digits of the 32-bit code
+constexpr int RX_MAXRUN = 64;  // equal-code runs longer than this are treated like score ties
+
+template <int THREADS>
+struct RadixSmem {
+  unsigned hist[RX_PASSES][256];
+  unsigned goff[256];
+  unsigned wc[THREADS / 32][256];
+  unsigned wsum[8];
+  int skip[RX_PASSES];
+};
+
+__device__ __forceinline__ unsigned rx_digit(unsigned long long v, int pass) { return (unsigned)(v >> (32 + 8 * pass)) & 255u; }
+
+// score bits of the candidate at pixel yx: key[] is in raster order, the rank comes from the candidate bitmap
+__device__ __forceinline__ unsigned long long rx_key_of(const CornerWorkView& wv, int fr, unsigned yx) {
+  const unsigned x = yx & 0xFFFFu, y = yx >> 16;
+  const size_t word = (size_t)fr * wv.words_per_frame + (size_t)y * wv.wpr + (x >> 5);
+  const unsigned rank = wv.wordoff[word] + __popc(wv.bitmap[word] & ((1u << (x & 31)) - 1u));
+  return wv.key[(size_t)fr * wv.cand_cap + rank];
+}
+
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) radix_sort_frame_kernel(CornerWorkView wv) {
+  constexpr int WARPS = THREADS / 32, TILE = THREADS * ITEMS, WTILE = 32 * ITEMS;
+  extern __shared__ __align__(16) unsigned char rx_raw[];
+  RadixSmem<THREADS>& sm = *reinterpret_cast<RadixSmem<THREADS>*>(rx_raw);
+  const int fr = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned n = wv.ntotal[fr];
+  if (n > (unsigned)wv.cand_cap || n == 0) return;  // overflow is reported by nms_kernel
+  const size_t cb = (size_t)fr * wv.cand_cap;
+  unsigned long long* A = wv.pk_a + cb;
+  unsigned long long* B = wv.pk_b + cb;
+
+  // sweep 0: the four digit histograms (only the code half of every word is read)
+  for (int i = tid; i < RX_PASSES * 256; i += THREADS) (&sm.hist[0][0])[i] = 0;
+  __syncthreads();
+  {
+    const unsigned* hi = reinterpret_cast<const unsigned*>(A) + 1;
+    for (unsigned i0 = 0; i0 < n; i0 += THREADS * 8) {
+      unsigned c[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const unsigned i = i0 + k * THREADS + tid;
+        c[k] = i < n ? __ldcg(hi + 2 * (size_t)i) : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        if (i0 + k * THREADS + tid < n) {
+#pragma unroll
+          for (int p = 0; p < RX_PASSES; p++) atomicAdd(&sm.hist[p][(c[k] >> (8 * p)) & 255u], 1u);
+        }
+    }
+  }
+  __syncthreads();
+  if (tid < RX_PASSES) sm.skip[tid] = 0;
+  __syncthreads();
+  for (int i = tid; i < RX_PASSES * 256; i += THREADS)
+    if ((&sm.hist[0][0])[i] == n) sm.skip[i >> 8] = 1;  // every word carries this digit: the pass is the identity
+  __syncthreads();
+
+  unsigned long long* src = A;
+  unsigned long long* dst = B;
+  for (int pass = 0; pass < RX_PASSES; pass++) {
+    if (sm.skip[pass]) continue;  // block-uniform
+    // exclusive scan of this pass's histogram -> running output offset per digit
+    if (tid < 256) {
+      const unsigned c = sm.hist[pass][tid];
+      unsigned inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+      }
+      if (lane == 31) sm.wsum[warp] = inc;
+      sm.goff[tid] = inc - c;
+    }
+    __syncthreads();
+    if (tid < 256) {
+      unsigned base = 0;
+      for (int k = 0; k < warp; k++) base += sm.wsum[k];
+      sm.goff[tid] += base;
+    }
+    for (unsigned t0 = 0; t0 < n; t0 += TILE) {
+      __syncthreads();  // goff ready / previous tile's scatter has read wc
+#pragma unroll
+      for (int k = 0; k < WARPS; k += THREADS / 256) {
+        const int row = k + (tid >> 8);
+        if (row < WARPS) sm.wc[row][tid & 255] = 0;
+      }
+      __syncthreads();
+      unsigned long long v[ITEMS];
+      unsigned d[ITEMS], peers[ITEMS], old[ITEMS];
+      const unsigned base = t0 + warp * WTILE;
+#pragma unroll
+      for (int r = 0; r < ITEMS; r++) {
+        const unsigned i = base + r * 32 + lane;
+        v[r] = i < n ? __ldcg(src + i) : ~0ull;
+      }
+#pragma unroll
+      for (int r = 0; r < ITEMS; r++) {  // all matches first: they do not depend on each other
+        d[r] = base + r * 32 + lane < n ? rx_digit(v[r], pass) : 256u;  // 256: past the end
+        peers[r] = __match_any_sync(0xffffffffu, d[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < ITEMS; r++) {  // one shared-memory atomic per distinct digit and round, in round order
+        old[r] = 0;
+        if (d[r] < 256u && lane == __ffs(peers[r]) - 1) old[r] = atomicAdd(&sm.wc[warp][d[r]], (unsigned)__popc(peers[r]));
+        __syncwarp();
+      }
+      const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+      for (int r = 0; r < ITEMS; r++) old[r] = __shfl_sync(0xffffffffu, old[r], __ffs(peers[r]) - 1) + __popc(peers[r] & lt);
+      __syncthreads();
+      if (tid < 256) {
+        unsigned run = sm.goff[tid];
+#pragma unroll
+        for (int k = 0; k < WARPS; k++) {
+          const unsigned c = sm.wc[k][tid];
+          sm.wc[k][tid] = run;
+          run += c;
+        }
+        sm.goff[tid] = run;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < ITEMS; r++)
+        if (d[r] < 256u) dst[sm.wc[warp][d[r]] + old[r]] = v[r];
+    }
+    __syncthreads();  // the block's own global writes are visible to it from here on
+    unsigned long long* t = src;
+    src = dst;
+    dst = t;
+  }
+  if (src != A) {  // an odd number of passes ran: bring the sorted list home
+    for (unsigned i = tid; i < n; i += THREADS) A[i] = __ldcg(B + i);
+    __syncthreads();
+  }
+
+  // final sweep: order the equal-code runs by the full score, note score ties.  Eight consecutive positions per thread.
+  const unsigned* hi = reinterpret_cast<const unsigned*>(A) + 1;
+  for (unsigned i0 = 0; i0 < n; i0 += THREADS * 8) {
+    const unsigned ib = i0 + tid * 8;
+    unsigned c[10];  // codes of positions ib-1 .. ib+8
+#pragma unroll
+    for (int k = 0; k < 10; k++) {
+      const unsigned i = ib + k - 1;  // wraps for ib == 0, k == 0: rejected by i < n
+      c[k] = i < n ? __ldcg(hi + 2 * (size_t)i) : 0u;
+    }
+    unsigned starts = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const unsigned i = ib + k;
+      if (i + 1 < n && c[k + 1] == c[k + 2] && !(i > 0 && c[k] == c[k + 1])) starts |= 1u << k;
+    }
+    while (starts) {  // rare
+      const unsigned i = ib + __ffs(starts) - 1;
+      starts &= starts - 1;
+      const unsigned code = (unsigned)(A[i] >> 32);
+      unsigned j = i + 2;
+      while (j < n && j - i < RX_MAXRUN && (unsigned)(__ldcg(A + j) >> 32) == code) j++;
+      if (j < n && (unsigned)(__ldcg(A + j) >> 32) == code) {  // pathological pile-up: let the exact path decide
+        atomicMin(wv.tiepos + fr, i);
+        continue;
+      }
+      for (unsigned p = i + 1; p < j; p++) {
+        const unsigned long long e = A[p];
+        const unsigned long long ke = rx_key_of(wv, fr, (unsigned)e);
+        unsigned q = p;
+        while (q > i) {
+          const unsigned long long f = A[q - 1];
+          if (!(rx_key_of(wv, fr, (unsigned)f) < ke)) break;
+          A[q] = f;
+          q--;
+        }
+        A[q] = e;
+      }
+      for (unsigned p = i; p + 1 < j; p++)
+        if (rx_key_of(wv, fr, (unsigned)A[p]) == rx_key_of(wv, fr, (unsigned)A[p + 1])) {
+          atomicMin(wv.tiepos + fr, p);
+          break;
+        }
+    }
+  }
+}
+
+// ---- greedy selection over the sorted list ---------------------------------------------------------------------------
+// Same chunk scheme as select_kernel, but "is an accepted corner closer than min_dist?" is ONE bit: every accepted corner
+// marks the open disc dx^2 + dy^2 < min_dist^2 around it in a per-frame pixel bitmap (the candidate bitmap's storage, dead
+// after order_kernel), one (corner, row) pair per thread.  Integer arithmetic throughout: exact.
+constexpr int NMS_THREADS = 256, NMS_EPT = 8, NMS_CHUNK = NMS_THREADS * NMS_EPT, NMS_ALIVE = 256, NMS_WARPS = NMS_THREADS / 32;
+
+struct NmsSmem {
+  __align__(16) unsigned pxy[NMS_ALIVE];  // survivors of the chunk in priority order, y << 16 | x
+  unsigned accm[NMS_ALIVE / 32], deadm[NMS_ALIVE / 32];  // decided survivors, one bit each
+  unsigned short accl[NMS_ALIVE];
+  int wcnt[NMS_WARPS];
+  int consumed, accepted, cut;
+};
+
+__device__ __forceinline__ int nms_block_scan(NmsSmem& sm, int c, int& total) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int inc = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) sm.wcnt[warp] = inc;
+  __syncthreads();
+  int pre = 0, tot = 0;
+#pragma unroll
+  for (int k = 0; k < NMS_WARPS; k++) {
+    const int v = sm.wcnt[k];
+    if (k < warp) pre += v;
+    tot += v;
+  }
+  __syncthreads();  // wcnt is reused by the next scan
+  total = tot;
+  return inc - c + pre;
+}
+
+__global__ void __launch_bounds__(NMS_THREADS) nms_kernel(CornerWorkView wv, int w, int h, int max_corners, int min_dist,
+                                                          double2* __restrict__ out_xy, int* __restrict__ out_n) {
+  __shared__ NmsSmem sm;
+  const int fr = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned ntot = wv.ntotal[fr];
+  if (ntot > (unsigned)wv.cand_cap) {  // capacity exceeded: report, never truncate silently
+    if (tid == 0) {
+      wv.status[fr] = 1;
+      if (out_n) out_n[fr] = -1;
+    }
+    return;
+  }
+  const int n = (int)ntot;
+  const int cap_out = max_corners < 1 ? 1 : max_corners;  // the cap is tested after the push (:298-299)
+  const unsigned long long* sorted = wv.pk_a + (size_t)fr * wv.cand_cap;  // low word: y << 16 | x
+  unsigned* blocked = wv.bitmap + (size_t)fr * wv.words_per_frame;
+  double2* out = out_xy + (size_t)fr * cap_out;
+  const int d = min_dist, d2 = min_dist * min_dist, rows = 2 * d - 1;
+  const bool suppress = wv.cell > 0;
+  if (tid == 0) {
+    sm.consumed = 0;
+    sm.accepted = 0;
+  }
+  __syncthreads();
+  while (true) {
+    const int consumed = sm.consumed, acc0 = sm.accepted;
+    if (consumed >= n || acc0 >= cap_out) break;
+    const int cnt = min(NMS_CHUNK, n - consumed);
+    // (1) this chunk's candidates against the corners accepted in earlier chunks: NMS_EPT consecutive candidates per thread
+    unsigned yx[NMS_EPT], bw[NMS_EPT];
+#pragma unroll
+    for (int e = 0; e < NMS_EPT; e++) {
+      const int t = tid * NMS_EPT + e;
+      yx[e] = t < cnt ? (unsigned)__ldcg(sorted + consumed + t) : 0u;
+    }
+#pragma unroll
+    for (int e = 0; e < NMS_EPT; e++) {
+      const int t = tid * NMS_EPT + e;
+      const unsigned x = yx[e] & 0xFFFFu, y = yx[e] >> 16;
+      bw[e] = (suppress && t < cnt) ? __ldcg(blocked + (size_t)y * wv.wpr + (x >> 5)) : 0u;
+    }
+    unsigned am = 0;
+#pragma unroll
+    for (int e = 0; e < NMS_EPT; e++)
+      if (tid * NMS_EPT + e < cnt && !((bw[e] >> (yx[e] & 31u)) & 1u)) am |= 1u << e;
+    // ordered compaction of the survivors; at most NMS_ALIVE are resolved now, the chunk is cut after the last one
+    int na;
+    const int exc = nms_block_scan(sm, __popc(am), na);
+    if (tid == 0) sm.cut = cnt;
+    __syncthreads();
+    {
+      int r = exc;
+#pragma unroll
+      for (int e = 0; e < NMS_EPT; e++)
+        if (am & (1u << e)) {
+          if (r < NMS_ALIVE) sm.pxy[r] = yx[e];
+          if (r == NMS_ALIVE) sm.cut = tid * NMS_EPT + e;  // first candidate that does not fit: it starts the next chunk
+          r++;
+        }
+    }
+    if (tid < NMS_ALIVE / 32) sm.accm[tid] = sm.deadm[tid] = 0;
+    na = na < NMS_ALIVE ? na : NMS_ALIVE;
+    __syncthreads();
+    const int used = sm.cut;
+    // (2) conflicts inside the chunk.  Thread i first collects the set C_i of higher-priority survivors closer than
+    // min_dist as a bit row (branch-free, broadcast loads; warp w only needs words 0..w), then rounds of pure bit
+    // logic: dead if C_i meets an accepted survivor, accepted once every member of C_i is dead.
+    const unsigned me = sm.pxy[tid];
+    const int mx = (int)(me & 0xFFFFu), my = (int)(me >> 16);
+    unsigned C[NMS_ALIVE / 32];
+#pragma unroll
+    for (int wd = 0; wd < NMS_ALIVE / 32; wd++) {
+      C[wd] = 0;
+      if (suppress && wd <= warp && wd * 32 < na) {
+        unsigned bits = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const uint4 o = *reinterpret_cast<const uint4*>(&sm.pxy[wd * 32 + q * 4]);
+          const unsigned ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int dx = (int)(ov[k] & 0xFFFFu) - mx, dy = (int)(ov[k] >> 16) - my;
+            if (dx * dx + dy * dy < d2) bits |= 1u << (q * 4 + k);
+          }
+        }
+        if (wd == warp) bits &= (1u << lane) - 1u;  // strictly higher priority only
+        C[wd] = bits;
+      }
+    }
+    int state = tid < na ? ST_UNDEC : ST_DEAD;
+    if (!suppress && tid < na) state = ST_ACC;
+    while (true) {
+      if (state == ST_UNDEC) {
+        unsigned hit = 0, und = 0;
+#pragma unroll
+        for (int wd = 0; wd < NMS_ALIVE / 32; wd++) {
+          const unsigned a = sm.accm[wd], dd = sm.deadm[wd];
+          hit |= C[wd] & a;
+          und |= C[wd] & ~(a | dd);
+        }
+        state = hit ? ST_DEAD : (und ? ST_UNDEC : ST_ACC);
+      }
+      __syncthreads();  // everybody has read the masks of the previous round
+      const unsigned ba = __ballot_sync(0xffffffffu, state == ST_ACC), bd = __ballot_sync(0xffffffffu, state == ST_DEAD);
+      if (lane == 0) {
+        sm.accm[warp] = ba;
+        sm.deadm[warp] = bd;
+      }
+      if (__syncthreads_or(state == ST_UNDEC) == 0) break;
+    }
+    // (3) append accepted survivors in priority order, stop at the cap; mark their discs
+    const bool acc = state == ST_ACC;
+    int nacc;
+    const int rank = nms_block_scan(sm, acc ? 1 : 0, nacc);
+    if (acc && acc0 + rank < cap_out) {
+      out[acc0 + rank] = make_double2((double)mx, (double)my);
+      sm.accl[rank] = (unsigned short)tid;
+    }
+    __syncthreads();
+    const int nnew = min(nacc, cap_out - acc0);
+    if (suppress && acc0 + nnew < cap_out) {  // nothing is looked up once the cap is reached
+      for (int i = tid; i < nnew * rows; i += NMS_THREADS) {
+        const int c = i / rows, dy = i - c * rows - (d - 1);
+        const unsigned sp = sm.pxy[sm.accl[c]];
+        const int px = (int)(sp & 0xFFFFu), py = (int)(sp >> 16) + dy;
+        if (py < 0 || py >= h) continue;
+        const int r2 = d2 - 1 - dy * dy;  // dx^2 <= r2  <=>  dx^2 + dy^2 < d^2
+        int r = (int)sqrtf((float)r2);
+        while (r * r > r2) r--;
+        while ((r + 1) * (r + 1) <= r2) r++;
+        const int xa = max(px - r, 0), xb = min(px + r, w - 1);
+        unsigned* rowp = blocked + (size_t)py * wv.wpr;
+        for (int wd = xa >> 5; wd <= (xb >> 5); wd++) {
+          const int lo = max(xa - wd * 32, 0), hi = min(xb - wd * 32, 31);
+          atomicOr(rowp + wd, (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo));
+        }
+      }
+      __threadfence_block();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      sm.accepted = acc0 + nnew;
+      sm.consumed = consumed + used;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    wv.status[fr] = 0;
+    if (out_n) out_n[fr] = sm.accepted;
+    // two identical scores inside the consumed prefix (or straddling its end): std::sort's tie order is observable, the
+    // frame is redone by select_kernel mode 3
+    if (wv.tiepos[fr] < (unsigned)sm.consumed) wv.status[fr] = 3;
+  }
+}
+
 // mode 0: full shi_tomasi selection; mode 1: sort only (sfmgpu_sort_perm_desc).
+// mode 3: redo exactly the frames nms_kernel marked with status 3 (a consumed score tie) through the emulation.
 __global__ void __launch_bounds__(SEL_THREADS, 4) select_kernel(CornerWorkView wv, int w, int max_corners, int min_dist, int mode,
                                                                double2* __restrict__ out_xy, int* __restrict__ out_n) {
   extern __shared__ __align__(16) unsigned char sel_raw[];
@@ -365,6 +759,11 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) select_kernel(CornerWorkView w
   uint32_t* idx = wv.idx + cb;
   uint32_t* lpos = wv.lpos + cb;
   uint32_t* rpos = wv.rpos + cb;
+  if (mode == 3) {  // every thread reads the status before thread 0 resets it below
+    const bool redo = wv.status[fr] == 3;
+    __syncthreads();
+    if (!redo) return;
+  }
   const unsigned ntot = wv.ntotal[fr];
   if (ntot > (unsigned)wv.cand_cap) {  // capacity exceeded: report, never truncate silently
     if (tid == 0) {
@@ -395,6 +794,11 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) select_kernel(CornerWorkView w
   double2* out = out_xy + (size_t)fr * cap_out;
   const int d = min_dist, d2 = min_dist * min_dist;
   const bool suppress = wv.cell > 0;
+  if (mode == 3) {  // the fast path skips the host-side grid reset
+    for (size_t i = tid; i < wv.grid_per_frame; i += SEL_THREADS) gridw[i] = EMPTY;
+    __threadfence_block();
+    __syncthreads();
+  }
 
   while (true) {
     produce_sorted(sm, key, idx, lpos, rpos, CHUNK);
@@ -417,8 +821,8 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) select_kernel(CornerWorkView w
       const int t = tid * EPT + e;
       cx_[e] = cy_[e] = 0;
       if (t < cnt) {
-        const unsigned pix = idx[consumed + t];
-        const int y = (int)(pix / (unsigned)w), x = (int)(pix - (unsigned)y * (unsigned)w);
+        const unsigned pix = idx[consumed + t];  // y << 16 | x
+        const int y = (int)(pix >> 16), x = (int)(pix & 0xFFFFu);
         cx_[e] = x;
         cy_[e] = y;
         bool alive = true;
@@ -527,6 +931,8 @@ int select_smem_config(sfmgpu_ctx* ctx) {
   static bool done = false;
   if (!done) {
     SFM_CUDA(ctx, cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelSmem)));
+    SFM_CUDA(ctx, cudaFuncSetAttribute(radix_sort_frame_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem<512>)));
+    SFM_CUDA(ctx, cudaFuncSetAttribute(radix_sort_frame_kernel<1024, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem<1024>)));
     done = true;
   }
   return 0;
@@ -539,7 +945,8 @@ int select_smem_config(sfmgpu_ctx* ctx) {
 // (std::sort permutation + greedy NMS); both use the work area carved for (count, cand_cap, min_dist).
 static int corners_args(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int count, int& min_dist, int cand_cap, void* work, size_t work_bytes,
                         CornerWorkView& wv) {
-  if (f->w > 65535 || f->h > 65535) return sfm_fail(ctx, SFMGPU_E_ARG, "corners: image larger than 65535 px");
+  if (f->w > 32767 || f->h > 32767)  // packed 16-bit coordinates; squared distances stay below 2^31
+    return sfm_fail(ctx, SFMGPU_E_ARG, "corners: image larger than 32767 px");
   if (min_dist < 0) min_dist = -min_dist;  // the reference compares against (double)min_dist*min_dist (:295)
   if (min_dist > 30000) return sfm_fail(ctx, SFMGPU_E_ARG, "corners: min_dist too large");
   const size_t need = corner_work_carve(wv, work, f->w, f->h, count, cand_cap, min_dist);
@@ -561,9 +968,21 @@ int sfm_corners_select_stage(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int count,
   SFM_TRY(corners_args(ctx, f, count, min_dist, cand_cap, work, work_bytes, wv));
   SFM_TRY(select_smem_config(ctx));
   StageTimer st(ctx, 1);
-  if (wv.grid_per_frame)
-    SFM_CUDA(ctx, cudaMemsetAsync(wv.grid, 0xFF, sizeof(unsigned) * wv.grid_per_frame * count, ctx->stream));
-  SFM_LAUNCH(ctx, select_kernel, count, SEL_THREADS, sizeof(SelSmem), wv, f->w, max_corners, min_dist, 0, out_xy, out_n);
+  if (ctx->select_mode == 1) {  // exact introsort emulation for every frame (tests / A-B timing)
+    if (wv.grid_per_frame)
+      SFM_CUDA(ctx, cudaMemsetAsync(wv.grid, 0xFF, sizeof(unsigned) * wv.grid_per_frame * count, ctx->stream));
+    SFM_LAUNCH(ctx, select_kernel, count, SEL_THREADS, sizeof(SelSmem), wv, f->w, max_corners, min_dist, 0, out_xy, out_n);
+    return 0;
+  }
+  SFM_CUDA(ctx, cudaMemsetAsync(wv.tiepos, 0xFF, sizeof(unsigned) * count, ctx->stream));
+  if (count >= 2 * ctx->n_sm)
+    SFM_LAUNCH(ctx, (radix_sort_frame_kernel<512, 8>), count, 512, sizeof(RadixSmem<512>), wv);
+  else  // few frames: the widest block per frame
+    SFM_LAUNCH(ctx, (radix_sort_frame_kernel<1024, 4>), count, 1024, sizeof(RadixSmem<1024>), wv);
+  // the candidate bitmap has served its purpose (raster ranks); its storage becomes nms_kernel's "blocked pixel" map
+  SFM_CUDA(ctx, cudaMemsetAsync(wv.bitmap, 0, sizeof(unsigned) * wv.words_per_frame * count, ctx->stream));
+  SFM_LAUNCH(ctx, nms_kernel, count, NMS_THREADS, 0, wv, f->w, f->h, max_corners, min_dist, out_xy, out_n);
+  SFM_LAUNCH(ctx, select_kernel, count, SEL_THREADS, sizeof(SelSmem), wv, f->w, max_corners, min_dist, 3, out_xy, out_n);
   return 0;
 }
 
@@ -576,6 +995,13 @@ int sfm_corners_batch(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first, int co
 size_t sfm_corner_work_bytes_md(int w, int h, int nframes, int cand_cap, int min_dist) {
   CornerWorkView v;
   return corner_work_carve(v, nullptr, w, h, nframes, cand_cap, min_dist);
+}
+
+extern "C" int sfmgpu_select_set_mode(sfmgpu_ctx* ctx, int mode) {
+  if (!ctx) return SFMGPU_E_ARG;
+  if (mode != 0 && mode != 1) return sfm_fail(ctx, SFMGPU_E_ARG, "select_set_mode: mode %d not in {0,1}", mode);
+  ctx->select_mode = mode;
+  return 0;
 }
 
 extern "C" int sfmgpu_corners(sfmgpu_ctx* ctx, sfmgpu_frames* f, int frame, int max_corners, double quality, int min_dist,

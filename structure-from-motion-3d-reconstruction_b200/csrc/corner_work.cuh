@@ -13,10 +13,15 @@ struct CornerWorkView {
   unsigned* tmp_idx;            // [nframes][cand_cap] unordered pixel index
   unsigned long long* tmp_key;  // [nframes][cand_cap] unordered score bits   (aliases lpos/rpos)
   unsigned long long* key;      // [nframes][cand_cap] raster order, then sorted in place
-  unsigned* idx;                // [nframes][cand_cap]
+  unsigned* idx;                // [nframes][cand_cap] pixel as y << 16 | x
   unsigned* lpos;               // [nframes][cand_cap] partition scratch
   unsigned* rpos;               // [nframes][cand_cap]
   unsigned* grid;               // [nframes][grid_cells][2] accepted corners per min_dist cell (packed y<<16|x)
+  // radix selection path (corner_select.cu): packed (order code << 32 | y << 16 | x) ping-pong buffers and the first
+  // sorted position holding two candidates with identical scores
+  unsigned long long* pk_a;     // [nframes][cand_cap] written by order_kernel, holds the sorted result
+  unsigned long long* pk_b;     // [nframes][cand_cap] (aliases lpos/rpos: free until the emulation fallback runs)
+  unsigned* tiepos;             // [nframes]
   int wpr;
   size_t words_per_frame;
   int cand_cap;
@@ -54,5 +59,8 @@ static inline size_t corner_work_carve(CornerWorkView& v, void* base, int w, int
   v.key = (unsigned long long*)take(sizeof(unsigned long long) * (size_t)cand_cap * nframes);
   v.idx = (unsigned*)take(sizeof(unsigned) * (size_t)cand_cap * nframes);
   v.grid = (unsigned*)take(sizeof(unsigned) * (v.grid_per_frame ? v.grid_per_frame : 1) * nframes);
+  v.pk_a = (unsigned long long*)take(sizeof(unsigned long long) * (size_t)cand_cap * nframes);
+  v.pk_b = v.tmp_key;
+  v.tiepos = (unsigned*)take(sizeof(unsigned) * nframes);
   return off + 256;
 }

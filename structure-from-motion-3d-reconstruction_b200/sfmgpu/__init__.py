@@ -27,7 +27,7 @@ SYMBOLS = [
     "sfmgpu_host_free", "sfmgpu_frames_create", "sfmgpu_frames_destroy", "sfmgpu_frames_upload",
     "sfmgpu_frames_upload_device", "sfmgpu_frames_synth", "sfmgpu_pyramid_build", "sfmgpu_frames_level_size",
     "sfmgpu_frames_download", "sfmgpu_corner_candidates", "sfmgpu_corners", "sfmgpu_sort_perm_desc",
-    "sfmgpu_klt_track", "sfmgpu_klt_set_mode", "sfmgpu_pairs_create", "sfmgpu_pairs_destroy", "sfmgpu_pair_frontend", "sfmgpu_pipeline_set", "sfmgpu_pair_frontend_host", "sfmgpu_pairs_totals",
+    "sfmgpu_klt_track", "sfmgpu_klt_set_mode", "sfmgpu_select_set_mode", "sfmgpu_pairs_create", "sfmgpu_pairs_destroy", "sfmgpu_pair_frontend", "sfmgpu_pipeline_set", "sfmgpu_pair_frontend_host", "sfmgpu_pairs_totals",
     "sfmgpu_pairs_download", "sfmgpu_pairs_download_all", "sfmgpu_pairs_device_ptrs", "sfmgpu_tracker_create", "sfmgpu_tracker_destroy", "sfmgpu_tracker_reset",
     "sfmgpu_tracker_step", "sfmgpu_tracker_step_frames", "sfmgpu_tracker_tracks", "sfmgpu_tracker_totals",
     "sfmgpu_ransac_score", "sfmgpu_ransac_upload", "sfmgpu_ransac_score_resident", "sfmgpu_ransac_download",
@@ -96,6 +96,7 @@ def load_library():
         "sfmgpu_sort_perm_desc": (_i, [_vp, _f64p, _i, _i32p]),
         "sfmgpu_klt_track": (_i, [_vp, _vp, _i, _i, _f64p, _i, _i, _i, _f64p, _f64p, _vp]),
         "sfmgpu_klt_set_mode": (_i, [_vp, _i]),
+        "sfmgpu_select_set_mode": (_i, [_vp, _i]),
         "sfmgpu_pairs_create": (_i, [_vp, _i, _i, C.POINTER(_vp)]),
         "sfmgpu_pairs_destroy": (None, [_vp, _vp]),
         "sfmgpu_pair_frontend": (_i, [_vp, _vp, _i, _i, C.POINTER(LKCfg), _vp]),
@@ -172,6 +173,10 @@ class Context:
     def klt_set_mode(self, mode):
         """0 auto, 1 warp-per-feature kernel only, 2 lane-per-feature kernel whenever win_radius == 5."""
         self._ck(self.lib.sfmgpu_klt_set_mode(self.h, mode))
+
+    def select_set_mode(self, mode):
+        """0 radix sort + exact fallback on consumed score ties (default), 1 introsort emulation for every frame."""
+        self._ck(self.lib.sfmgpu_select_set_mode(self.h, mode))
 
     def timer_start(self):
         self._ck(self.lib.sfmgpu_timer_start(self.h))

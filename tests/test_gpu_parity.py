@@ -100,11 +100,35 @@ def test_device_std_sort_permutation(ctx, port, n, distinct):
 @pytest.mark.parametrize("name", list(_images()))
 @pytest.mark.parametrize("mc,q,d", [(2200, 0.01, 8), (50, 0.2, 3), (0, 0.01, 8), (300, 0.0, 1), (100, 0.01, 0), (4000, 0.001, 2),
                                     (500, 0.01, 25)])
-def test_corners_bit_exact(ctx, checker, name, mc, q, d):
+@pytest.mark.parametrize("select_mode", [0, 1])
+def test_corners_bit_exact(ctx, checker, name, mc, q, d, select_mode):
+    """select_mode 0: radix sort by score + exact introsort fallback on consumed score ties; 1: introsort emulation."""
     img = _images()[name]
     f = _frames(ctx, [img], 1)
-    got, want = f.corners(0, mc, q, d), checker.shi_tomasi(img, mc, q, d)
+    ctx.select_set_mode(select_mode)
+    try:
+        got = f.corners(0, mc, q, d)
+    finally:
+        ctx.select_set_mode(0)
+    want = checker.shi_tomasi(img, mc, q, d)
     assert got.shape == want.shape and np.array_equal(got, want), (name, mc, q, d, len(got), len(want))
+
+
+@pytest.mark.parametrize("period,mc,d", [(32, 3000, 8), (48, 500, 3), (17, 20000, 0), (64, 8000, 12)])
+def test_corners_periodic_image_ties(ctx, checker, period, mc, d):
+    """A periodic image: every score occurs dozens of times, so std::sort's tie order decides the corners from the first
+    candidate on (the radix path must hand every such frame to the exact emulation), next to tie-free frames in one batch."""
+    rng = np.random.default_rng(period)
+    cell = rng.integers(0, 256, (period, period), dtype=np.uint8)
+    w, h = 1280, 720
+    img = np.tile(cell, (h // period + 1, w // period + 1))[:h, :w]
+    mixed = img.copy()
+    mixed[:, w // 2:] = synth.frame(3, 1, w, h)[:, w // 2:]  # ties only in the left half
+    plain = synth.frame(4, 2, w, h)
+    f = _frames(ctx, [img, plain, mixed], 1)
+    for k, im in enumerate([img, plain, mixed]):
+        got, want = f.corners(k, mc, 0.01, d), checker.shi_tomasi(im, mc, 0.01, d)
+        assert got.shape == want.shape and np.array_equal(got, want), (period, k, len(got), len(want))
 
 
 def test_corners_golden(ctx, g):
@@ -363,6 +387,27 @@ def test_pair_frontend_batch(ctx, checker, g):
     assert (nc_tot, nk_tot) == (cs, ks) and nit_tot > 0
     li, lj, nc = pairs.download(2)
     assert nc == g["pair_nc"][0] and np.array_equal(li, g["pair_li"]) and _klt_close(lj, g["pair_lj"])
+
+
+def test_pair_frontend_batch_with_score_ties(ctx, checker):
+    """Quantised frames (many identical scores) between plain ones in ONE batch: the radix selection redoes exactly the
+    frames whose consumed prefix holds a tie, inside the batched launch."""
+    imgs = [synth.frame(31, t, W, H) for t in range(7)]
+    for t in (1, 2, 5):
+        imgs[t] = imgs[t] >> 4 << 4
+    f = _frames(ctx, imgs)
+    cfg = sfmgpu.lkcfg(max_tracks=900)
+    pairs = ctx.pairs(6, 900)
+    for mode in (0, 1):
+        ctx.select_set_mode(mode)
+        try:
+            pairs.run(f, 0, 6, cfg)
+        finally:
+            ctx.select_set_mode(0)
+        for p in range(6):
+            li, lj, nc = pairs.download(p)
+            wl, wj, wnc = checker.pair_frontend(imgs[p], imgs[p + 1], 900)
+            assert nc == wnc and np.array_equal(li, wl) and _klt_close(lj, wj), (mode, p)
 
 
 @pytest.mark.parametrize("chunk,pipe", [(0, 0), (2, 0), (3, 1), (7, 2), (100, 2), (4, 3)])
