@@ -175,12 +175,23 @@ __global__ void __launch_bounds__(256, 3) score_tile_kernel(const uint8_t* __res
   unsigned long long* maxbits = wv.maxbits + fr;
   double thr8 = 0.0;
   float bound;
+  unsigned long long maxkey = 0;
+  int shift = 0;
   if (MODE == 0) {
     bound = __double2float_rd(__longlong_as_double(*(volatile unsigned long long*)maxbits));  // what earlier blocks found
   } else {
     const double maxv = 0.125 * __longlong_as_double(*maxbits);
-    thr8 = 8.0 * (maxv * quality);  // thr = maxv*quality (:275); s >= thr  <=>  u >= 8*thr
+    const double thr = maxv * quality;  // (:275)
+    thr8 = 8.0 * thr;                   // s >= thr  <=>  u >= 8*thr
     bound = __double2float_rd(thr8);
+    // order code of the radix selection path: distance of the score's bit pattern below the frame maximum, shifted so
+    // that the whole candidate range [thr, max] fits 32 bits (ascending code = descending score; scores are
+    // non-negative doubles, so bit order is value order)
+    maxkey = (unsigned long long)__double_as_longlong(maxv);
+    const unsigned long long thrkey = thr > 0.0 ? (unsigned long long)__double_as_longlong(thr) : 0ull;
+    const unsigned long long range = maxkey > thrkey ? maxkey - thrkey : 0ull;
+    const int bits = 64 - __clzll((long long)range);
+    shift = bits > 32 ? bits - 32 : 0;
   }
   const bool col_in = x < w, col_interior = x >= 2 && x < w - 2;
   const bool tile_inner = X0 >= 2 && X0 + TW <= w - 2 && Y0 >= 2 && Y0 + TH <= h - 2;  // no border pixel in this tile
@@ -300,8 +311,10 @@ __global__ void __launch_bounds__(256, 3) score_tile_kernel(const uint8_t* __res
           atomicOr(&sm.tile_bm[row * 2 + (col >> 5)], 1u << (col & 31));
           const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
           if (slot < (unsigned)wv.cand_cap) {
-            wv.tmp_idx[(size_t)fr * wv.cand_cap + slot] = (unsigned)(Y0 + row) * (unsigned)w + (unsigned)(X0 + col);
-            wv.tmp_key[(size_t)fr * wv.cand_cap + slot] = (unsigned long long)__double_as_longlong(0.125 * u);
+            const unsigned long long k = (unsigned long long)__double_as_longlong(0.125 * u);
+            wv.tmp_idx[(size_t)fr * wv.cand_cap + slot] = ((unsigned)(Y0 + row) << 16) | (unsigned)(X0 + col);
+            wv.tmp_key[(size_t)fr * wv.cand_cap + slot] = k;
+            wv.pk_a[(size_t)fr * wv.cand_cap + slot] = (((maxkey - k) >> shift) << 32) | slot;  // k in [thr, max]: code < 2^32
           }
         }
       }
@@ -328,9 +341,10 @@ __global__ void __launch_bounds__(256, 3) score_tile_kernel(const uint8_t* __res
 }
 
 // Exclusive prefix sum of popc(bitmap word) over one frame (one block per frame).
-__global__ void __launch_bounds__(1024) bitmap_scan_kernel(CornerWorkView wv) {
+__global__ void __launch_bounds__(1024) bitmap_scan_kernel(CornerWorkView wv, int only_flagged) {
   __shared__ unsigned wsum[32];
   const int fr = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (only_flagged && wv.status[fr] != 3) return;
   const size_t nwords = wv.words_per_frame;
   const unsigned* bm = wv.bitmap + (size_t)fr * nwords;
   unsigned* off = wv.wordoff + (size_t)fr * nwords;
@@ -365,33 +379,20 @@ __global__ void __launch_bounds__(1024) bitmap_scan_kernel(CornerWorkView wv) {
   if (tid == 1023) wv.ntotal[fr] = run;  // chunk boundaries are monotone: the last thread ends at the total
 }
 
-// Scatter the unordered candidate list into raster order.  Also emits, per candidate, the packed word the radix
-// selection path sorts: (order code << 32) | y << 16 | x, where the code is the distance of the score's bit pattern
-// below the frame maximum, shifted so that the whole candidate range [thr, max] fits 32 bits (ascending code =
-// descending score; scores are non-negative doubles, so bit order is value order).
-__global__ void __launch_bounds__(256) order_kernel(CornerWorkView wv, int w, double quality) {
+// Scatter the unordered candidate list into raster order (the order std::sort starts from).
+__global__ void __launch_bounds__(256) order_kernel(CornerWorkView wv, int only_flagged) {
   const int fr = blockIdx.y;
+  if (only_flagged && wv.status[fr] != 3) return;
   const unsigned n = min(wv.ncand[fr], (unsigned)wv.cand_cap);
   const size_t cb = (size_t)fr * wv.cand_cap, wb = (size_t)fr * wv.words_per_frame;
-  const double maxv = 0.125 * __longlong_as_double(wv.maxbits[fr]);
-  const double thr = maxv * quality;
-  const unsigned long long maxkey = (unsigned long long)__double_as_longlong(maxv);
-  const unsigned long long thrkey = thr > 0.0 ? (unsigned long long)__double_as_longlong(thr) : 0ull;
-  const unsigned long long range = maxkey > thrkey ? maxkey - thrkey : 0ull;
-  const int bits = 64 - __clzll((long long)range);
-  const int shift = bits > 32 ? bits - 32 : 0;
   for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-    const unsigned pix = wv.tmp_idx[cb + e];
-    const unsigned y = pix / (unsigned)w, x = pix - y * (unsigned)w;
+    const unsigned yx = wv.tmp_idx[cb + e];
+    const unsigned y = yx >> 16, x = yx & 0xFFFFu;
     const size_t word = wb + (size_t)y * wv.wpr + (x >> 5);
     const unsigned rank = wv.wordoff[word] + __popc(wv.bitmap[word] & ((1u << (x & 31)) - 1u));
     if (rank < (unsigned)wv.cand_cap) {
-      const unsigned long long k = wv.tmp_key[cb + e];
-      wv.key[cb + rank] = k;
-      const unsigned yx = (y << 16) | x;
+      wv.key[cb + rank] = wv.tmp_key[cb + e];
       wv.idx[cb + rank] = yx;
-      const unsigned long long code = (maxkey - k) >> shift;  // k in [thrkey, maxkey]: < 2^32
-      wv.pk_a[cb + rank] = (code << 32) | yx;
     }
   }
 }
@@ -404,8 +405,17 @@ size_t sfm_corner_work_bytes(int w, int h, int nframes, int cand_cap) {
   return corner_work_carve(v, nullptr, w, h, nframes, cand_cap);
 }
 
-// Runs max -> candidates -> scan -> order for frames [first, first+count); leaves raster-ordered (key, idx)
-// and counts in the work area.
+// Raster order for the frames of the batch (all of them, or only those the selection flagged with status 3): ntotal,
+// key[], idx[].  Needed by the introsort emulation and the candidate-list API; the radix selection path works on the
+// unordered list.
+int sfm_corner_raster_order(sfmgpu_ctx* ctx, int count, const CornerWorkView& wv, int only_flagged) {
+  SFM_LAUNCH(ctx, bitmap_scan_kernel, count, 1024, 0, wv, only_flagged);
+  SFM_LAUNCH(ctx, order_kernel, dim3(16, count), 256, 0, wv, only_flagged);
+  return 0;
+}
+
+// Runs max -> candidates for frames [first, first+count); leaves the candidate bitmap, the unordered (pixel, score) list,
+// the packed sort words and the counts in the work area.
 int sfm_corner_candidates_batch(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first, int count, double quality,
                                 const CornerWorkView& wv) {
   SFM_CUDA(ctx, cudaMemsetAsync(wv.maxbits, 0, sizeof(unsigned long long) * count, ctx->stream));
@@ -421,8 +431,6 @@ int sfm_corner_candidates_batch(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int fir
              quality);
   SFM_LAUNCH(ctx, score_tile_kernel<1>, grid, 256, sizeof(ScoreSmem), f->lvl[0], f->w, f->h, f->pitch[0], f->fstride[0], first, wv,
              quality);
-  SFM_LAUNCH(ctx, bitmap_scan_kernel, count, 1024, 0, wv);
-  SFM_LAUNCH(ctx, order_kernel, dim3(16, count), 256, 0, wv, f->w, quality);
   return 0;
 }
 
@@ -435,6 +443,7 @@ int sfm_candidates_single(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int frame, do
   CornerWorkView wv;
   corner_work_carve(wv, ctx->cs_work.p, f->w, f->h, 1, cand_cap);
   SFM_TRY(sfm_corner_candidates_batch(ctx, f, frame, 1, quality, wv));
+  SFM_TRY(sfm_corner_raster_order(ctx, 1, wv, 0));
   unsigned long long mb = 0;
   unsigned n = 0;
   SFM_CUDA(ctx, cudaMemcpyAsync(&mb, wv.maxbits, 8, cudaMemcpyDeviceToHost, ctx->stream));

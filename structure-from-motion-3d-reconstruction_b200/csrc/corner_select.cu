@@ -29,6 +29,7 @@
 
 int sfm_corner_candidates_batch(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first, int count, double quality,
                                 const CornerWorkView& wv);
+int sfm_corner_raster_order(sfmgpu_ctx* ctx, int count, const CornerWorkView& wv, int only_flagged);
 
 namespace {
 
@@ -362,19 +363,22 @@ __device__ void produce_sorted(SelSmem& sm, sfm_key_t* key, uint32_t* idx, uint3
 }
 
 // ---- radix path -------------------------------------------------------------------------------------------------------
-// One block owns one frame: a stable LSD radix sort of the packed words (order code << 32 | y << 16 | x), 8-bit digits
-// of the code.  Because the block sees the whole frame, the four digit histograms are order-independent and come from
+// One block owns one frame: a stable LSD radix sort of the packed words (order code << 32 | slot in the frame's unordered
+// candidate list, as the candidate pass appended them), 8-bit digits of the code.  Because the block sees the whole frame, the four digit histograms are order-independent and come from
 // ONE sweep; every pass is then a single sweep over the frame in tiles of THREADS*ITEMS words: rank inside the warp by
 // match_any rounds (round r of a warp covers 32 consecutive words, so rank order = position order), across warps and
 // tiles by running per-digit offsets in shared memory.  Passes whose digit is the same for every word are skipped.  A
 // final sweep puts runs of equal codes into descending order of the full 64-bit score (one thread per run, in place; a
-// run is a handful of words; the score is found through the candidate bitmap's raster rank) and records the first
+// run is a handful of words) and records the first
 // position holding two IDENTICAL scores.
 constexpr int RX_PASSES = 4;   // 8-bit digits of the 32-bit code
 constexpr int RX_MAXRUN = 64;  // equal-code runs longer than this are treated like score ties
 
+constexpr int RX_TILE = 4096;  // words per tile (THREADS * ITEMS)
+
 template <int THREADS>
 struct RadixSmem {
+  __align__(16) unsigned long long tile[2][RX_TILE];  // cp.async double buffer
   unsigned hist[RX_PASSES][256];
   unsigned goff[256];
   unsigned wc[THREADS / 32][256];
@@ -384,21 +388,23 @@ struct RadixSmem {
 
 __device__ __forceinline__ unsigned rx_digit(unsigned long long v, int pass) { return (unsigned)(v >> (32 + 8 * pass)) & 255u; }
 
-// score bits of the candidate at pixel yx: key[] is in raster order, the rank comes from the candidate bitmap
-__device__ __forceinline__ unsigned long long rx_key_of(const CornerWorkView& wv, int fr, unsigned yx) {
-  const unsigned x = yx & 0xFFFFu, y = yx >> 16;
-  const size_t word = (size_t)fr * wv.words_per_frame + (size_t)y * wv.wpr + (x >> 5);
-  const unsigned rank = wv.wordoff[word] + __popc(wv.bitmap[word] & ((1u << (x & 31)) - 1u));
-  return wv.key[(size_t)fr * wv.cand_cap + rank];
+// score bits of the candidate in slot `slot` of the frame's unordered list
+__device__ __forceinline__ unsigned long long rx_key_of(const CornerWorkView& wv, int fr, unsigned slot) {
+  return wv.tmp_key[(size_t)fr * wv.cand_cap + slot];
 }
 
-template <int THREADS, int ITEMS>
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+
+template <int THREADS, int ITEMS, int BALLOT>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS) radix_sort_frame_kernel(CornerWorkView wv) {
   constexpr int WARPS = THREADS / 32, TILE = THREADS * ITEMS, WTILE = 32 * ITEMS;
+  static_assert(TILE == RX_TILE, "tile buffer size");
   extern __shared__ __align__(16) unsigned char rx_raw[];
   RadixSmem<THREADS>& sm = *reinterpret_cast<RadixSmem<THREADS>*>(rx_raw);
   const int fr = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const unsigned n = wv.ntotal[fr];
+  const unsigned n = wv.ncand[fr];
   if (n > (unsigned)wv.cand_cap || n == 0) return;  // overflow is reported by nms_kernel
   const size_t cb = (size_t)fr * wv.cand_cap;
   unsigned long long* A = wv.pk_a + cb;
@@ -453,31 +459,58 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) radix_sort_frame_kern
       for (int k = 0; k < warp; k++) base += sm.wsum[k];
       sm.goff[tid] += base;
     }
-    for (unsigned t0 = 0; t0 < n; t0 += TILE) {
-      __syncthreads();  // goff ready / previous tile's scatter has read wc
+    // tiles stream through a cp.async double buffer: tile t+1 is in flight while tile t is ranked and scattered
+    auto fetch = [&](int buf, unsigned t0) {
+      const unsigned words = n - t0 < (unsigned)TILE ? n - t0 : (unsigned)TILE, chunks = (words + 1) / 2;  // 16-byte chunks
+      for (unsigned c = tid; c < chunks; c += THREADS) cp_async16(&sm.tile[buf][2 * c], src + t0 + 2 * c);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    fetch(0, 0);
+    int it = 0;
+    for (unsigned t0 = 0; t0 < n; t0 += TILE, it++) {
+      if (t0 + TILE < n) {
+        fetch((it + 1) & 1, t0 + TILE);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();  // tile landed for every thread / goff ready / previous tile's scatter has read wc
 #pragma unroll
       for (int k = 0; k < WARPS; k += THREADS / 256) {
         const int row = k + (tid >> 8);
         if (row < WARPS) sm.wc[row][tid & 255] = 0;
       }
-      __syncthreads();
       unsigned long long v[ITEMS];
       unsigned d[ITEMS], peers[ITEMS], old[ITEMS];
       const unsigned base = t0 + warp * WTILE;
 #pragma unroll
-      for (int r = 0; r < ITEMS; r++) {
-        const unsigned i = base + r * 32 + lane;
-        v[r] = i < n ? __ldcg(src + i) : ~0ull;
-      }
+      for (int r = 0; r < ITEMS; r++) v[r] = sm.tile[it & 1][warp * WTILE + r * 32 + lane];
+      __syncthreads();
 #pragma unroll
       for (int r = 0; r < ITEMS; r++) {  // all matches first: they do not depend on each other
-        d[r] = base + r * 32 + lane < n ? rx_digit(v[r], pass) : 256u;  // 256: past the end
-        peers[r] = __match_any_sync(0xffffffffu, d[r]);
+        // positions past the end sit behind every valid word of the last tile: digit 255 keeps them behind, never stored
+        d[r] = base + r * 32 + lane < n ? rx_digit(v[r], pass) : 255u;
+        if (BALLOT) {
+          unsigned pm = 0xffffffffu;
+#pragma unroll
+          for (int b = 0; b < 8; b++) {
+            const bool bit = (d[r] >> b) & 1u;
+            const unsigned bal = __ballot_sync(0xffffffffu, bit);
+            pm &= bit ? bal : ~bal;
+          }
+          peers[r] = pm;
+        } else {
+          peers[r] = __match_any_sync(0xffffffffu, d[r]);
+        }
       }
 #pragma unroll
-      for (int r = 0; r < ITEMS; r++) {  // one shared-memory atomic per distinct digit and round, in round order
+      for (int r = 0; r < ITEMS; r++) {  // the leader of every digit group bumps the warp's counter, in round order
+        // (plain load + store: shared-memory atomics cost 2 cycles per active lane and were the bottleneck)
         old[r] = 0;
-        if (d[r] < 256u && lane == __ffs(peers[r]) - 1) old[r] = atomicAdd(&sm.wc[warp][d[r]], (unsigned)__popc(peers[r]));
+        if (lane == __ffs(peers[r]) - 1) {
+          old[r] = sm.wc[warp][d[r]];
+          sm.wc[warp][d[r]] = old[r] + (unsigned)__popc(peers[r]);
+        }
         __syncwarp();
       }
       const unsigned lt = (1u << lane) - 1u;
@@ -497,9 +530,10 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) radix_sort_frame_kern
       __syncthreads();
 #pragma unroll
       for (int r = 0; r < ITEMS; r++)
-        if (d[r] < 256u) dst[sm.wc[warp][d[r]] + old[r]] = v[r];
+        if (base + r * 32 + lane < n) dst[sm.wc[warp][d[r]] + old[r]] = v[r];
     }
-    __syncthreads();  // the block's own global writes are visible to it from here on
+    __threadfence();  // the next pass reads these words back through cp.async (L2)
+    __syncthreads();
     unsigned long long* t = src;
     src = dst;
     dst = t;
@@ -558,8 +592,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) radix_sort_frame_kern
 
 // ---- greedy selection over the sorted list ---------------------------------------------------------------------------
 // Same chunk scheme as select_kernel, but "is an accepted corner closer than min_dist?" is ONE bit: every accepted corner
-// marks the open disc dx^2 + dy^2 < min_dist^2 around it in a per-frame pixel bitmap (the candidate bitmap's storage, dead
-// after order_kernel), one (corner, row) pair per thread.  Integer arithmetic throughout: exact.
+// marks the open disc dx^2 + dy^2 < min_dist^2 around it in a per-frame pixel bitmap (the storage of the bitmap's prefix
+// sums, unused unless a frame falls back), one (corner, row) pair per thread.  Integer arithmetic throughout: exact.
 constexpr int NMS_THREADS = 256, NMS_EPT = 8, NMS_CHUNK = NMS_THREADS * NMS_EPT, NMS_ALIVE = 256, NMS_WARPS = NMS_THREADS / 32;
 
 struct NmsSmem {
@@ -596,7 +630,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(CornerWorkView wv, int
                                                           double2* __restrict__ out_xy, int* __restrict__ out_n) {
   __shared__ NmsSmem sm;
   const int fr = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const unsigned ntot = wv.ntotal[fr];
+  const unsigned ntot = wv.ncand[fr];
   if (ntot > (unsigned)wv.cand_cap) {  // capacity exceeded: report, never truncate silently
     if (tid == 0) {
       wv.status[fr] = 1;
@@ -606,8 +640,9 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(CornerWorkView wv, int
   }
   const int n = (int)ntot;
   const int cap_out = max_corners < 1 ? 1 : max_corners;  // the cap is tested after the push (:298-299)
-  const unsigned long long* sorted = wv.pk_a + (size_t)fr * wv.cand_cap;  // low word: y << 16 | x
-  unsigned* blocked = wv.bitmap + (size_t)fr * wv.words_per_frame;
+  const unsigned long long* sorted = wv.pk_a + (size_t)fr * wv.cand_cap;  // low word: slot in the unordered list
+  const unsigned* slot_yx = wv.tmp_idx + (size_t)fr * wv.cand_cap;
+  unsigned* blocked = wv.wordoff + (size_t)fr * wv.words_per_frame;  // free until a fallback frame needs raster ranks
   double2* out = out_xy + (size_t)fr * cap_out;
   const int d = min_dist, d2 = min_dist * min_dist, rows = 2 * d - 1;
   const bool suppress = wv.cell > 0;
@@ -626,6 +661,11 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(CornerWorkView wv, int
     for (int e = 0; e < NMS_EPT; e++) {
       const int t = tid * NMS_EPT + e;
       yx[e] = t < cnt ? (unsigned)__ldcg(sorted + consumed + t) : 0u;
+    }
+#pragma unroll
+    for (int e = 0; e < NMS_EPT; e++) {
+      const int t = tid * NMS_EPT + e;
+      yx[e] = t < cnt ? __ldg(slot_yx + yx[e]) : 0u;
     }
 #pragma unroll
     for (int e = 0; e < NMS_EPT; e++) {
@@ -931,8 +971,9 @@ int select_smem_config(sfmgpu_ctx* ctx) {
   static bool done = false;
   if (!done) {
     SFM_CUDA(ctx, cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelSmem)));
-    SFM_CUDA(ctx, cudaFuncSetAttribute(radix_sort_frame_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem<512>)));
-    SFM_CUDA(ctx, cudaFuncSetAttribute(radix_sort_frame_kernel<1024, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem<1024>)));
+    SFM_CUDA(ctx, cudaFuncSetAttribute(radix_sort_frame_kernel<512, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem<512>)));
+    SFM_CUDA(ctx, cudaFuncSetAttribute(radix_sort_frame_kernel<512, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem<512>)));
+    SFM_CUDA(ctx, cudaFuncSetAttribute(radix_sort_frame_kernel<1024, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem<1024>)));
     done = true;
   }
   return 0;
@@ -969,19 +1010,27 @@ int sfm_corners_select_stage(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int count,
   SFM_TRY(select_smem_config(ctx));
   StageTimer st(ctx, 1);
   if (ctx->select_mode == 1) {  // exact introsort emulation for every frame (tests / A-B timing)
+    SFM_TRY(sfm_corner_raster_order(ctx, count, wv, 0));
     if (wv.grid_per_frame)
       SFM_CUDA(ctx, cudaMemsetAsync(wv.grid, 0xFF, sizeof(unsigned) * wv.grid_per_frame * count, ctx->stream));
     SFM_LAUNCH(ctx, select_kernel, count, SEL_THREADS, sizeof(SelSmem), wv, f->w, max_corners, min_dist, 0, out_xy, out_n);
     return 0;
   }
   SFM_CUDA(ctx, cudaMemsetAsync(wv.tiepos, 0xFF, sizeof(unsigned) * count, ctx->stream));
-  if (count >= 2 * ctx->n_sm)
-    SFM_LAUNCH(ctx, (radix_sort_frame_kernel<512, 8>), count, 512, sizeof(RadixSmem<512>), wv);
-  else  // few frames: the widest block per frame
-    SFM_LAUNCH(ctx, (radix_sort_frame_kernel<1024, 4>), count, 1024, sizeof(RadixSmem<1024>), wv);
-  // the candidate bitmap has served its purpose (raster ranks); its storage becomes nms_kernel's "blocked pixel" map
-  SFM_CUDA(ctx, cudaMemsetAsync(wv.bitmap, 0, sizeof(unsigned) * wv.words_per_frame * count, ctx->stream));
+  SFM_CUDA(ctx, cudaMemsetAsync(wv.wordoff, 0, sizeof(unsigned) * wv.words_per_frame * count, ctx->stream));  // nms_kernel's blocked-pixel map
+  static const bool ballot = getenv("SFMGPU_RX_MATCH") == nullptr;  // default: ballot-built peer masks (5.1 vs 5.7 ms select stage)
+  if (count >= 2 * ctx->n_sm) {
+    if (ballot)
+      SFM_LAUNCH(ctx, (radix_sort_frame_kernel<512, 8, 1>), count, 512, sizeof(RadixSmem<512>), wv);
+    else
+      SFM_LAUNCH(ctx, (radix_sort_frame_kernel<512, 8, 0>), count, 512, sizeof(RadixSmem<512>), wv);
+  } else {  // few frames: the widest block per frame
+    SFM_LAUNCH(ctx, (radix_sort_frame_kernel<1024, 4, 0>), count, 1024, sizeof(RadixSmem<1024>), wv);
+  }
   SFM_LAUNCH(ctx, nms_kernel, count, NMS_THREADS, 0, wv, f->w, f->h, max_corners, min_dist, out_xy, out_n);
+  // frames where a score tie was consumed (status 3): raster order, then the exact emulation.  Blocks of all other
+  // frames return at once.
+  SFM_TRY(sfm_corner_raster_order(ctx, count, wv, 1));
   SFM_LAUNCH(ctx, select_kernel, count, SEL_THREADS, sizeof(SelSmem), wv, f->w, max_corners, min_dist, 3, out_xy, out_n);
   return 0;
 }

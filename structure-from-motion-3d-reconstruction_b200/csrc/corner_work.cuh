@@ -10,17 +10,17 @@ struct CornerWorkView {
   int* status;                  // [nframes] 0 ok, 1 candidate capacity exceeded
   unsigned* bitmap;             // [nframes][h][wpr] one bit per pixel
   unsigned* wordoff;            // [nframes][h][wpr] exclusive prefix of popcounts
-  unsigned* tmp_idx;            // [nframes][cand_cap] unordered pixel index
-  unsigned long long* tmp_key;  // [nframes][cand_cap] unordered score bits   (aliases lpos/rpos)
+  unsigned* tmp_idx;            // [nframes][cand_cap] unordered list: pixel as y << 16 | x
+  unsigned long long* tmp_key;  // [nframes][cand_cap] unordered list: score bits
   unsigned long long* key;      // [nframes][cand_cap] raster order, then sorted in place
   unsigned* idx;                // [nframes][cand_cap] pixel as y << 16 | x
-  unsigned* lpos;               // [nframes][cand_cap] partition scratch
+  unsigned* lpos;               // [nframes][cand_cap] partition scratch of the emulation (aliases pk_b)
   unsigned* rpos;               // [nframes][cand_cap]
   unsigned* grid;               // [nframes][grid_cells][2] accepted corners per min_dist cell (packed y<<16|x)
-  // radix selection path (corner_select.cu): packed (order code << 32 | y << 16 | x) ping-pong buffers and the first
-  // sorted position holding two candidates with identical scores
-  unsigned long long* pk_a;     // [nframes][cand_cap] written by order_kernel, holds the sorted result
-  unsigned long long* pk_b;     // [nframes][cand_cap] (aliases lpos/rpos: free until the emulation fallback runs)
+  // radix selection path (corner_select.cu): packed (order code << 32 | slot in the unordered list) ping-pong buffers
+  // and the first sorted position holding two candidates with identical scores
+  unsigned long long* pk_a;     // [nframes][cand_cap] written by the candidate pass, holds the sorted result
+  unsigned long long* pk_b;     // [nframes][cand_cap]
   unsigned* tiepos;             // [nframes]
   int wpr;
   size_t words_per_frame;
@@ -39,6 +39,7 @@ static inline size_t corner_work_carve(CornerWorkView& v, void* base, int w, int
     off += (bytes + 255) / 256 * 256;
     return p;
   };
+  cand_cap = (cand_cap + 1) & ~1;  // per-frame strides of the 8-byte arrays stay 16-byte aligned (cp.async)
   v.wpr = (w + 31) / 32;
   v.words_per_frame = (size_t)v.wpr * h;
   v.cand_cap = cand_cap;
@@ -54,13 +55,13 @@ static inline size_t corner_work_carve(CornerWorkView& v, void* base, int w, int
   v.wordoff = (unsigned*)take(sizeof(unsigned) * v.words_per_frame * nframes);
   v.tmp_idx = (unsigned*)take(sizeof(unsigned) * (size_t)cand_cap * nframes);
   v.tmp_key = (unsigned long long*)take(sizeof(unsigned long long) * (size_t)cand_cap * nframes);
-  v.lpos = (unsigned*)v.tmp_key;  // the unordered list is dead once order_kernel has run
-  v.rpos = v.lpos ? v.lpos + (size_t)cand_cap * nframes : nullptr;
   v.key = (unsigned long long*)take(sizeof(unsigned long long) * (size_t)cand_cap * nframes);
   v.idx = (unsigned*)take(sizeof(unsigned) * (size_t)cand_cap * nframes);
   v.grid = (unsigned*)take(sizeof(unsigned) * (v.grid_per_frame ? v.grid_per_frame : 1) * nframes);
   v.pk_a = (unsigned long long*)take(sizeof(unsigned long long) * (size_t)cand_cap * nframes);
-  v.pk_b = v.tmp_key;
+  v.pk_b = (unsigned long long*)take(sizeof(unsigned long long) * (size_t)cand_cap * nframes);
+  v.lpos = (unsigned*)v.pk_b;  // the emulation runs after (or instead of) the radix sort
+  v.rpos = v.lpos ? v.lpos + (size_t)cand_cap * nframes : nullptr;
   v.tiepos = (unsigned*)take(sizeof(unsigned) * nframes);
   return off + 256;
 }
