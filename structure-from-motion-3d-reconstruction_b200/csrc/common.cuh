@@ -147,7 +147,7 @@ int sfm_corners_batch(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first, int co
                       int min_dist, int cand_cap, void* work, size_t work_bytes, double2* out_xy, int* out_n);
 int sfm_corners_score_stage(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first, int count, double quality, int min_dist, int cand_cap,
                             void* work, size_t work_bytes);
-int sfm_corners_select_stage(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int count, int max_corners, int min_dist, int cand_cap, void* work,
+int sfm_corners_select_stage(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int count, int max_corners, double quality, int min_dist, int cand_cap, void* work,
                              size_t work_bytes, double2* out_xy, int* out_n);
 int sfm_candidates_single(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int frame, double quality, int32_t* xy,
                           double* score, int cap, int* n_out, double* max_score);

@@ -76,15 +76,15 @@ __device__ __forceinline__ float est_u(float a, float b, float c) {
   return (a + b) - s;
 }
 
+// One tile of one frame.  MODE 0: frame maximum only.  MODE 1: candidates against the FINAL threshold (maximum known).
+// MODE 2: maximum AND candidates in one pass, against a PROVISIONAL threshold quality * L where L <= final maximum is what
+// is known when the block starts (running maximum, which a sparse probe pass has seeded, and this tile's own estimate):
+// multiplication by quality > 0 is monotone, so the provisional threshold never exceeds the final one and the list is a
+// superset of the candidates; candidate_finalize_kernel drops the surplus once the maximum is final.
 template <int MODE>
-__global__ void __launch_bounds__(256, 3) score_tile_kernel(const uint8_t* __restrict__ img, int w, int h, int pitch, size_t fstride,
-                                                           int frame0, CornerWorkView wv, double quality) {
-  extern __shared__ __align__(16) unsigned char score_raw[];
-  ScoreSmem& sm = *reinterpret_cast<ScoreSmem*>(score_raw);
+__device__ __forceinline__ void score_tile(ScoreSmem& sm, const uint8_t* __restrict__ im, int w, int h, int pitch, int X0, int Y0,
+                                           int fr, const CornerWorkView& wv, double quality) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int fr = blockIdx.z;
-  const uint8_t* im = img + (size_t)(frame0 + fr) * fstride;
-  const int X0 = blockIdx.x * TW, Y0 = blockIdx.y * TH;
   if (tid < TH * 2) sm.tile_bm[tid] = 0;
   if (tid == 0) sm.qn = 0;
 
@@ -177,8 +177,10 @@ __global__ void __launch_bounds__(256, 3) score_tile_kernel(const uint8_t* __res
   float bound;
   unsigned long long maxkey = 0;
   int shift = 0;
-  if (MODE == 0) {
-    bound = __double2float_rd(__longlong_as_double(*(volatile unsigned long long*)maxbits));  // what earlier blocks found
+  double runmax = 0.0;
+  if (MODE == 0 || MODE == 2) {
+    runmax = __longlong_as_double(*(volatile unsigned long long*)maxbits);  // what earlier blocks found
+    bound = __double2float_rd(runmax);
   } else {
     const double maxv = 0.125 * __longlong_as_double(*maxbits);
     const double thr = maxv * quality;  // (:275)
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(256, 3) score_tile_kernel(const uint8_t* __res
     const int y = Y0 + q * VRUN + j;
     const bool interior = tile_inner || (col_interior && y >= 2 && y < h - 2);
     const float u = est_u(a, b, c);
-    if (MODE == 0) {
+    if (MODE == 0 || MODE == 2) {
       uf[j] = interior ? u : -1.0e30f;
       tmax = fmaxf(tmax, uf[j]);
     } else {
@@ -235,8 +237,8 @@ __global__ void __launch_bounds__(256, 3) score_tile_kernel(const uint8_t* __res
     rb[j & 3] = nb;
   }
 
-  if (MODE == 0) {
-    // tile maximum of the estimates, then queue every pixel that can still be the frame maximum
+  if (MODE == 0 || MODE == 2) {
+    // tile maximum of the estimates
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
     if (lane == 0) sm.wmaxf[warp] = tmax;
@@ -244,7 +246,29 @@ __global__ void __launch_bounds__(256, 3) score_tile_kernel(const uint8_t* __res
     float bm = sm.wmaxf[0];
 #pragma unroll
     for (int k = 1; k < 8; k++) bm = fmaxf(bm, sm.wmaxf[k]);
-    bound = fmaxf(bound, bm) - EST_MARGIN;
+    bound = fmaxf(bound, bm) - EST_MARGIN;  // a pixel below this cannot be the frame maximum
+    if (MODE == 2) {
+      // provisional threshold from a lower bound of the frame maximum: the running maximum (an exact score) or this
+      // tile's best estimate minus the margin (estimate error < margin / 4)
+      const double lb = fmax(runmax, fmax(0.0, (double)bm - (double)EST_MARGIN));
+      thr8 = 8.0 * ((0.125 * lb) * quality);
+      bound = fminf(bound, __double2float_rd(thr8) - EST_MARGIN);
+#pragma unroll
+      for (int j = 0; j < VRUN; j++) {
+        const int y = Y0 + q * VRUN + j;
+        if (col_in && y < h) {
+          const bool interior = tile_inner || (col_interior && y >= 2 && y < h - 2);
+          if (interior) {
+            if (uf[j] >= bound) pmask |= 1u << j;
+          } else if (0.0 >= thr8) {
+            pmask |= (1u << j) | (1u << (16 + j));  // border score is exactly 0 (:240, :253-254)
+          }
+        }
+      }
+    }
+  }
+  if (MODE == 0) {
+    // queue every pixel that can still be the frame maximum
 #pragma unroll
     for (int j = 0; j < VRUN; j++)
       if (uf[j] >= bound) sm.queue[atomicAdd(&sm.qn, 1)] = (unsigned short)((q * VRUN + j) * TW + oc);
@@ -299,13 +323,12 @@ __global__ void __launch_bounds__(256, 3) score_tile_kernel(const uint8_t* __res
         cand = u >= thr8;
       }
     }
-    if (MODE == 0) {
-      best = fmax(best, u);
-    } else {
+    if (MODE == 0 || MODE == 2) best = fmax(best, u);
+    if (MODE != 0) {
       const unsigned m = __ballot_sync(0xffffffffu, cand);
       if (m) {
         unsigned base = 0;
-        if (lane == 0) base = atomicAdd(wv.ncand + fr, (unsigned)__popc(m));
+        if (lane == 0) base = atomicAdd((MODE == 1 ? wv.nfinal : wv.ncand) + fr, (unsigned)__popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
         if (cand) {
           atomicOr(&sm.tile_bm[row * 2 + (col >> 5)], 1u << (col & 31));
@@ -314,13 +337,14 @@ __global__ void __launch_bounds__(256, 3) score_tile_kernel(const uint8_t* __res
             const unsigned long long k = (unsigned long long)__double_as_longlong(0.125 * u);
             wv.tmp_idx[(size_t)fr * wv.cand_cap + slot] = ((unsigned)(Y0 + row) << 16) | (unsigned)(X0 + col);
             wv.tmp_key[(size_t)fr * wv.cand_cap + slot] = k;
-            wv.pk_a[(size_t)fr * wv.cand_cap + slot] = (((maxkey - k) >> shift) << 32) | slot;  // k in [thr, max]: code < 2^32
+            if (MODE == 1)  // k in [thr, max]: code < 2^32 (MODE 2: candidate_finalize_kernel writes the sort words)
+              wv.pk_a[(size_t)fr * wv.cand_cap + slot] = (((maxkey - k) >> shift) << 32) | slot;
           }
         }
       }
     }
   }
-  if (MODE == 0) {
+  if (MODE == 0 || MODE == 2) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
     if (lane == 0) sm.wmax[warp] = best;
@@ -331,11 +355,89 @@ __global__ void __launch_bounds__(256, 3) score_tile_kernel(const uint8_t* __res
       const unsigned long long mb = (unsigned long long)__double_as_longlong(m);
       if (mb > *(volatile unsigned long long*)maxbits) atomicMax(maxbits, mb);  // u >= 0: bit order == value order
     }
-  } else {
+  }
+  if (MODE != 0) {
     __syncthreads();
     if (tid < TH * 2) {
       const int y = Y0 + (tid >> 1), xw = X0 + 32 * (tid & 1);
       if (y < h && xw < w) wv.bitmap[(size_t)fr * wv.words_per_frame + (size_t)y * wv.wpr + (xw >> 5)] = sm.tile_bm[tid];
+    }
+  }
+}
+
+// Full grid: tile (blockIdx.x, blockIdx.y) of frame blockIdx.z.  Probe (tmul > 1): every tmul-th tile in x and y only, to
+// seed the running maximum before the fused pass.
+template <int MODE>
+__global__ void __launch_bounds__(256, 3) score_tile_kernel(const uint8_t* __restrict__ img, int w, int h, int pitch, size_t fstride,
+                                                           int frame0, CornerWorkView wv, double quality, int tmul) {
+  extern __shared__ __align__(16) unsigned char score_raw[];
+  ScoreSmem& sm = *reinterpret_cast<ScoreSmem*>(score_raw);
+  const int fr = blockIdx.z;
+  int tx = blockIdx.x, ty = blockIdx.y;
+  if (tmul > 1) {
+    const int ntx = (w + TW - 1) / TW, nty = (h + TH - 1) / TH;
+    tx = min(tx * tmul + tmul / 2, ntx - 1);
+    ty = min(ty * tmul + tmul / 2, nty - 1);
+  }
+  score_tile<MODE>(sm, img + (size_t)(frame0 + fr) * fstride, w, h, pitch, tx * TW, ty * TH, fr, wv, quality);
+}
+
+// Frames whose PROVISIONAL list overflowed the capacity are redone against the final threshold (their exact list may
+// still fit): a small persistent grid walks the rescue list.
+__global__ void __launch_bounds__(256, 3) score_rescue_kernel(const uint8_t* __restrict__ img, int w, int h, int pitch, size_t fstride,
+                                                             int frame0, CornerWorkView wv, double quality) {
+  extern __shared__ __align__(16) unsigned char score_raw[];
+  ScoreSmem& sm = *reinterpret_cast<ScoreSmem*>(score_raw);
+  const int nres = *wv.rescue_count;
+  for (int k = blockIdx.z; k < nres; k += gridDim.z) {
+    const int fr = wv.rescue_list[k];
+    score_tile<1>(sm, img + (size_t)(frame0 + fr) * fstride, w, h, pitch, blockIdx.x * TW, blockIdx.y * TH, fr, wv, quality);
+    __syncthreads();
+  }
+}
+
+// After the fused pass: frames whose provisional list overflowed go on the rescue list (one thread per frame).
+__global__ void rescue_mark_kernel(CornerWorkView wv, int count) {
+  const int fr = blockIdx.x * blockDim.x + threadIdx.x;
+  if (fr >= count || wv.ncand[fr] <= (unsigned)wv.cand_cap) return;
+  wv.nfinal[fr] = 0;
+  wv.exact_list[fr] = 1;
+  wv.rescue_list[atomicAdd(wv.rescue_count, 1)] = fr;
+}
+
+// Provisional list -> final list, for the paths that do not run the radix sort (which does the same in its first sweep):
+// keeps the entries that reach the final threshold (dense sort words (order code << 32 | slot) in pk_a, count in nfinal)
+// and clears the candidate-bitmap bit of every other entry.
+__global__ void __launch_bounds__(256) candidate_finalize_kernel(CornerWorkView wv, double quality) {
+  const int fr = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  if (wv.exact_list[fr]) return;
+  const unsigned nprov = wv.ncand[fr];
+  const size_t cb = (size_t)fr * wv.cand_cap, wb = (size_t)fr * wv.words_per_frame;
+  const double maxv = 0.125 * __longlong_as_double(wv.maxbits[fr]);
+  const double thr = maxv * quality;
+  const unsigned long long maxkey = (unsigned long long)__double_as_longlong(maxv);
+  const unsigned long long thrkey = thr > 0.0 ? (unsigned long long)__double_as_longlong(thr) : 0ull;
+  const unsigned long long range = maxkey > thrkey ? maxkey - thrkey : 0ull;
+  const int bits = 64 - __clzll((long long)range);
+  const int shift = bits > 32 ? bits - 32 : 0;
+  for (unsigned e0 = blockIdx.x * blockDim.x; e0 < nprov; e0 += gridDim.x * blockDim.x) {  // warp-uniform trip count
+    const unsigned e = e0 + tid;
+    unsigned long long k = 0;
+    bool keep = false;
+    if (e < nprov) {
+      k = wv.tmp_key[cb + e];
+      keep = __longlong_as_double((long long)k) >= thr;  // s >= thr (:282)
+      if (!keep) {
+        const unsigned yx = wv.tmp_idx[cb + e], x = yx & 0xFFFFu, y = yx >> 16;
+        atomicAnd(wv.bitmap + wb + (size_t)y * wv.wpr + (x >> 5), ~(1u << (x & 31)));
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (m) {
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(wv.nfinal + fr, (unsigned)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (keep) wv.pk_a[cb + base + __popc(m & ((1u << lane) - 1u))] = (((maxkey - k) >> shift) << 32) | e;
     }
   }
 }
@@ -379,19 +481,24 @@ __global__ void __launch_bounds__(1024) bitmap_scan_kernel(CornerWorkView wv, in
   if (tid == 1023) wv.ntotal[fr] = run;  // chunk boundaries are monotone: the last thread ends at the total
 }
 
-// Scatter the unordered candidate list into raster order (the order std::sort starts from).
-__global__ void __launch_bounds__(256) order_kernel(CornerWorkView wv, int only_flagged) {
+// Scatter the candidate list into raster order (the order std::sort starts from).  A provisional list (fused pass) still
+// holds the entries below the final threshold: they are skipped, their bitmap bits are already cleared.
+__global__ void __launch_bounds__(256) order_kernel(CornerWorkView wv, double quality, int only_flagged) {
   const int fr = blockIdx.y;
   if (only_flagged && wv.status[fr] != 3) return;
-  const unsigned n = min(wv.ncand[fr], (unsigned)wv.cand_cap);
+  const bool exact = wv.exact_list[fr] != 0;
+  const unsigned n = min(exact ? wv.nfinal[fr] : wv.ncand[fr], (unsigned)wv.cand_cap);
+  const double thr = (0.125 * __longlong_as_double(wv.maxbits[fr])) * quality;
   const size_t cb = (size_t)fr * wv.cand_cap, wb = (size_t)fr * wv.words_per_frame;
   for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const unsigned long long k = wv.tmp_key[cb + e];
+    if (!exact && !(__longlong_as_double((long long)k) >= thr)) continue;
     const unsigned yx = wv.tmp_idx[cb + e];
     const unsigned y = yx >> 16, x = yx & 0xFFFFu;
     const size_t word = wb + (size_t)y * wv.wpr + (x >> 5);
     const unsigned rank = wv.wordoff[word] + __popc(wv.bitmap[word] & ((1u << (x & 31)) - 1u));
     if (rank < (unsigned)wv.cand_cap) {
-      wv.key[cb + rank] = wv.tmp_key[cb + e];
+      wv.key[cb + rank] = k;
       wv.idx[cb + rank] = yx;
     }
   }
@@ -408,29 +515,51 @@ size_t sfm_corner_work_bytes(int w, int h, int nframes, int cand_cap) {
 // Raster order for the frames of the batch (all of them, or only those the selection flagged with status 3): ntotal,
 // key[], idx[].  Needed by the introsort emulation and the candidate-list API; the radix selection path works on the
 // unordered list.
-int sfm_corner_raster_order(sfmgpu_ctx* ctx, int count, const CornerWorkView& wv, int only_flagged) {
+int sfm_corner_raster_order(sfmgpu_ctx* ctx, int count, const CornerWorkView& wv, double quality, int only_flagged) {
+  // only_flagged: the radix sort has already reduced the provisional lists (and bitmaps) to the final candidates
+  if (!only_flagged) SFM_LAUNCH(ctx, candidate_finalize_kernel, dim3(32, count), 256, 0, wv, quality);
   SFM_LAUNCH(ctx, bitmap_scan_kernel, count, 1024, 0, wv, only_flagged);
-  SFM_LAUNCH(ctx, order_kernel, dim3(16, count), 256, 0, wv, only_flagged);
+  SFM_LAUNCH(ctx, order_kernel, dim3(16, count), 256, 0, wv, quality, only_flagged);
   return 0;
 }
 
-// Runs max -> candidates for frames [first, first+count); leaves the candidate bitmap, the unordered (pixel, score) list,
-// the packed sort words and the counts in the work area.
+// Maximum and candidates for frames [first, first+count); leaves the candidate bitmap, the unordered (pixel, score) list,
+// the packed sort words (pk_a, nfinal of them) in the work area.  quality > 0: sparse probe pass + ONE fused pass + a
+// sweep over the list; otherwise (the provisional-threshold argument needs quality > 0) the two full passes.
 int sfm_corner_candidates_batch(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first, int count, double quality,
                                 const CornerWorkView& wv) {
   SFM_CUDA(ctx, cudaMemsetAsync(wv.maxbits, 0, sizeof(unsigned long long) * count, ctx->stream));
   SFM_CUDA(ctx, cudaMemsetAsync(wv.ncand, 0, sizeof(unsigned) * count, ctx->stream));
-  dim3 grid(sfm_cdiv(f->w, TW), sfm_cdiv(f->h, TH), count);
+  SFM_CUDA(ctx, cudaMemsetAsync(wv.nfinal, 0, sizeof(unsigned) * count, ctx->stream));
+  SFM_CUDA(ctx, cudaMemsetAsync(wv.rescue_count, 0, sizeof(int), ctx->stream));
+  const int ntx = sfm_cdiv(f->w, TW), nty = sfm_cdiv(f->h, TH);
+  dim3 grid(ntx, nty, count);
   static bool configured = false;
   if (!configured) {
     SFM_CUDA(ctx, cudaFuncSetAttribute(score_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScoreSmem)));
     SFM_CUDA(ctx, cudaFuncSetAttribute(score_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScoreSmem)));
+    SFM_CUDA(ctx, cudaFuncSetAttribute(score_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScoreSmem)));
+    SFM_CUDA(ctx, cudaFuncSetAttribute(score_rescue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScoreSmem)));
     configured = true;
   }
-  SFM_LAUNCH(ctx, score_tile_kernel<0>, grid, 256, sizeof(ScoreSmem), f->lvl[0], f->w, f->h, f->pitch[0], f->fstride[0], first, wv,
-             quality);
-  SFM_LAUNCH(ctx, score_tile_kernel<1>, grid, 256, sizeof(ScoreSmem), f->lvl[0], f->w, f->h, f->pitch[0], f->fstride[0], first, wv,
-             quality);
+  static const bool two_pass = getenv("SFMGPU_SCORE_TWO_PASS") != nullptr;  // A/B timing
+  if (quality > 0.0 && !two_pass) {
+    constexpr int PROBE = 4;  // every 4th tile in x and y seeds the running maximum (1/16 of a pass)
+    SFM_CUDA(ctx, cudaMemsetAsync(wv.exact_list, 0, sizeof(int) * count, ctx->stream));
+    SFM_LAUNCH(ctx, score_tile_kernel<0>, dim3(sfm_cdiv(ntx, PROBE), sfm_cdiv(nty, PROBE), count), 256, sizeof(ScoreSmem), f->lvl[0], f->w,
+               f->h, f->pitch[0], f->fstride[0], first, wv, quality, PROBE);
+    SFM_LAUNCH(ctx, score_tile_kernel<2>, grid, 256, sizeof(ScoreSmem), f->lvl[0], f->w, f->h, f->pitch[0], f->fstride[0], first, wv,
+               quality, 1);
+    SFM_LAUNCH(ctx, rescue_mark_kernel, sfm_cdiv(count, 256), 256, 0, wv, count);
+    SFM_LAUNCH(ctx, score_rescue_kernel, dim3(ntx, nty, count < 2 ? count : 2), 256, sizeof(ScoreSmem), f->lvl[0], f->w, f->h,
+               f->pitch[0], f->fstride[0], first, wv, quality);
+  } else {
+    SFM_CUDA(ctx, cudaMemsetAsync(wv.exact_list, 1, sizeof(int) * count, ctx->stream));
+    SFM_LAUNCH(ctx, score_tile_kernel<0>, grid, 256, sizeof(ScoreSmem), f->lvl[0], f->w, f->h, f->pitch[0], f->fstride[0], first, wv,
+               quality, 1);
+    SFM_LAUNCH(ctx, score_tile_kernel<1>, grid, 256, sizeof(ScoreSmem), f->lvl[0], f->w, f->h, f->pitch[0], f->fstride[0], first, wv,
+               quality, 1);
+  }
   return 0;
 }
 
@@ -443,7 +572,7 @@ int sfm_candidates_single(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int frame, do
   CornerWorkView wv;
   corner_work_carve(wv, ctx->cs_work.p, f->w, f->h, 1, cand_cap);
   SFM_TRY(sfm_corner_candidates_batch(ctx, f, frame, 1, quality, wv));
-  SFM_TRY(sfm_corner_raster_order(ctx, 1, wv, 0));
+  SFM_TRY(sfm_corner_raster_order(ctx, 1, wv, quality, 0));
   unsigned long long mb = 0;
   unsigned n = 0;
   SFM_CUDA(ctx, cudaMemcpyAsync(&mb, wv.maxbits, 8, cudaMemcpyDeviceToHost, ctx->stream));

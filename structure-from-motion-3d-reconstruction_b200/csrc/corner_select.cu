@@ -29,7 +29,7 @@
 
 int sfm_corner_candidates_batch(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first, int count, double quality,
                                 const CornerWorkView& wv);
-int sfm_corner_raster_order(sfmgpu_ctx* ctx, int count, const CornerWorkView& wv, int only_flagged);
+int sfm_corner_raster_order(sfmgpu_ctx* ctx, int count, const CornerWorkView& wv, double quality, int only_flagged);
 
 namespace {
 
@@ -384,6 +384,7 @@ struct RadixSmem {
   unsigned wc[THREADS / 32][256];
   unsigned wsum[8];
   int skip[RX_PASSES];
+  unsigned nkeep;
 };
 
 __device__ __forceinline__ unsigned rx_digit(unsigned long long v, int pass) { return (unsigned)(v >> (32 + 8 * pass)) & 255u; }
@@ -398,22 +399,23 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 }
 
 template <int THREADS, int ITEMS, int BALLOT>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS) radix_sort_frame_kernel(CornerWorkView wv) {
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) radix_sort_frame_kernel(CornerWorkView wv, double quality) {
   constexpr int WARPS = THREADS / 32, TILE = THREADS * ITEMS, WTILE = 32 * ITEMS;
   static_assert(TILE == RX_TILE, "tile buffer size");
   extern __shared__ __align__(16) unsigned char rx_raw[];
   RadixSmem<THREADS>& sm = *reinterpret_cast<RadixSmem<THREADS>*>(rx_raw);
   const int fr = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const unsigned n = wv.ncand[fr];
-  if (n > (unsigned)wv.cand_cap || n == 0) return;  // overflow is reported by nms_kernel
   const size_t cb = (size_t)fr * wv.cand_cap;
   unsigned long long* A = wv.pk_a + cb;
   unsigned long long* B = wv.pk_b + cb;
-
-  // sweep 0: the four digit histograms (only the code half of every word is read)
   for (int i = tid; i < RX_PASSES * 256; i += THREADS) (&sm.hist[0][0])[i] = 0;
+  if (tid == 0) sm.nkeep = 0;
   __syncthreads();
-  {
+  unsigned n;
+  if (wv.exact_list[fr]) {
+    // the list is exact and the candidate pass wrote the sort words: sweep 0 only builds the four digit histograms
+    n = wv.nfinal[fr];
+    if (n > (unsigned)wv.cand_cap || n == 0) return;  // overflow is reported by nms_kernel
     const unsigned* hi = reinterpret_cast<const unsigned*>(A) + 1;
     for (unsigned i0 = 0; i0 < n; i0 += THREADS * 8) {
       unsigned c[8];
@@ -429,6 +431,58 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) radix_sort_frame_kern
           for (int p = 0; p < RX_PASSES; p++) atomicAdd(&sm.hist[p][(c[k] >> (8 * p)) & 255u], 1u);
         }
     }
+  } else {
+    // provisional list of the fused score pass: the frame maximum is final now.  Sweep 0 keeps the entries that reach
+    // the final threshold (s >= thr, :282) as sort words (order code << 32 | list slot), clears the candidate-bitmap
+    // bit of every other entry, and builds the histograms on the way.  The order code is the distance of the score's bit
+    // pattern below the maximum, shifted so that [thr, max] fits 32 bits (ascending code = descending score).
+    const unsigned nprov = wv.ncand[fr];
+    if (nprov > (unsigned)wv.cand_cap) return;  // such frames are on the rescue list (exact_list) - unreachable
+    const double maxv = 0.125 * __longlong_as_double(wv.maxbits[fr]);
+    const double thr = maxv * quality;
+    const unsigned long long maxkey = (unsigned long long)__double_as_longlong(maxv);
+    const unsigned long long thrkey = thr > 0.0 ? (unsigned long long)__double_as_longlong(thr) : 0ull;
+    const unsigned long long range = maxkey > thrkey ? maxkey - thrkey : 0ull;
+    const int bits = 64 - __clzll((long long)range);
+    const int shift = bits > 32 ? bits - 32 : 0;
+    const unsigned long long* lkey = wv.tmp_key + cb;
+    const unsigned* lyx = wv.tmp_idx + cb;
+    unsigned* bitmap = wv.bitmap + (size_t)fr * wv.words_per_frame;
+    for (unsigned i0 = 0; i0 < nprov; i0 += THREADS * 4) {  // block-uniform trip count
+      unsigned long long k[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const unsigned e = i0 + q * THREADS + tid;
+        k[q] = e < nprov ? __ldcg(lkey + e) : 0ull;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const unsigned e = i0 + q * THREADS + tid;
+        const bool in = e < nprov;
+        const bool keep = in && __longlong_as_double((long long)k[q]) >= thr;
+        if (in && !keep) {
+          const unsigned yx = lyx[e], x = yx & 0xFFFFu, y = yx >> 16;
+          atomicAnd(bitmap + (size_t)y * wv.wpr + (x >> 5), ~(1u << (x & 31)));
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (m) {
+          unsigned base = 0;
+          if (lane == 0) base = atomicAdd(&sm.nkeep, (unsigned)__popc(m));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (keep) {
+            const unsigned code = (unsigned)((maxkey - k[q]) >> shift);
+            A[base + __popc(m & ((1u << lane) - 1u))] = ((unsigned long long)code << 32) | e;
+#pragma unroll
+            for (int p = 0; p < RX_PASSES; p++) atomicAdd(&sm.hist[p][(code >> (8 * p)) & 255u], 1u);
+          }
+        }
+      }
+    }
+    __threadfence();  // the first pass reads A back through cp.async (L2)
+    __syncthreads();
+    n = sm.nkeep;
+    if (tid == 0) wv.nfinal[fr] = n;
+    if (n == 0) return;
   }
   __syncthreads();
   if (tid < RX_PASSES) sm.skip[tid] = 0;
@@ -630,7 +684,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(CornerWorkView wv, int
                                                           double2* __restrict__ out_xy, int* __restrict__ out_n) {
   __shared__ NmsSmem sm;
   const int fr = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const unsigned ntot = wv.ncand[fr];
+  const unsigned ntot = wv.nfinal[fr];
   if (ntot > (unsigned)wv.cand_cap) {  // capacity exceeded: report, never truncate silently
     if (tid == 0) {
       wv.status[fr] = 1;
@@ -1003,14 +1057,14 @@ int sfm_corners_score_stage(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first, 
   return sfm_corner_candidates_batch(ctx, f, first, count, quality, wv);
 }
 
-int sfm_corners_select_stage(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int count, int max_corners, int min_dist, int cand_cap, void* work,
+int sfm_corners_select_stage(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int count, int max_corners, double quality, int min_dist, int cand_cap, void* work,
                              size_t work_bytes, double2* out_xy, int* out_n) {
   CornerWorkView wv;
   SFM_TRY(corners_args(ctx, f, count, min_dist, cand_cap, work, work_bytes, wv));
   SFM_TRY(select_smem_config(ctx));
   StageTimer st(ctx, 1);
   if (ctx->select_mode == 1) {  // exact introsort emulation for every frame (tests / A-B timing)
-    SFM_TRY(sfm_corner_raster_order(ctx, count, wv, 0));
+    SFM_TRY(sfm_corner_raster_order(ctx, count, wv, quality, 0));
     if (wv.grid_per_frame)
       SFM_CUDA(ctx, cudaMemsetAsync(wv.grid, 0xFF, sizeof(unsigned) * wv.grid_per_frame * count, ctx->stream));
     SFM_LAUNCH(ctx, select_kernel, count, SEL_THREADS, sizeof(SelSmem), wv, f->w, max_corners, min_dist, 0, out_xy, out_n);
@@ -1021,16 +1075,16 @@ int sfm_corners_select_stage(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int count,
   static const bool ballot = getenv("SFMGPU_RX_MATCH") == nullptr;  // default: ballot-built peer masks (5.1 vs 5.7 ms select stage)
   if (count >= 2 * ctx->n_sm) {
     if (ballot)
-      SFM_LAUNCH(ctx, (radix_sort_frame_kernel<512, 8, 1>), count, 512, sizeof(RadixSmem<512>), wv);
+      SFM_LAUNCH(ctx, (radix_sort_frame_kernel<512, 8, 1>), count, 512, sizeof(RadixSmem<512>), wv, quality);
     else
-      SFM_LAUNCH(ctx, (radix_sort_frame_kernel<512, 8, 0>), count, 512, sizeof(RadixSmem<512>), wv);
+      SFM_LAUNCH(ctx, (radix_sort_frame_kernel<512, 8, 0>), count, 512, sizeof(RadixSmem<512>), wv, quality);
   } else {  // few frames: the widest block per frame
-    SFM_LAUNCH(ctx, (radix_sort_frame_kernel<1024, 4, 0>), count, 1024, sizeof(RadixSmem<1024>), wv);
+    SFM_LAUNCH(ctx, (radix_sort_frame_kernel<1024, 4, 0>), count, 1024, sizeof(RadixSmem<1024>), wv, quality);
   }
   SFM_LAUNCH(ctx, nms_kernel, count, NMS_THREADS, 0, wv, f->w, f->h, max_corners, min_dist, out_xy, out_n);
   // frames where a score tie was consumed (status 3): raster order, then the exact emulation.  Blocks of all other
   // frames return at once.
-  SFM_TRY(sfm_corner_raster_order(ctx, count, wv, 1));
+  SFM_TRY(sfm_corner_raster_order(ctx, count, wv, quality, 1));
   SFM_LAUNCH(ctx, select_kernel, count, SEL_THREADS, sizeof(SelSmem), wv, f->w, max_corners, min_dist, 3, out_xy, out_n);
   return 0;
 }
@@ -1038,7 +1092,7 @@ int sfm_corners_select_stage(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int count,
 int sfm_corners_batch(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first, int count, int max_corners, double quality,
                       int min_dist, int cand_cap, void* work, size_t work_bytes, double2* out_xy, int* out_n) {
   SFM_TRY(sfm_corners_score_stage(ctx, f, first, count, quality, min_dist, cand_cap, work, work_bytes));
-  return sfm_corners_select_stage(ctx, f, count, max_corners, min_dist, cand_cap, work, work_bytes, out_xy, out_n);
+  return sfm_corners_select_stage(ctx, f, count, max_corners, quality, min_dist, cand_cap, work, work_bytes, out_xy, out_n);
 }
 
 size_t sfm_corner_work_bytes_md(int w, int h, int nframes, int cand_cap, int min_dist) {

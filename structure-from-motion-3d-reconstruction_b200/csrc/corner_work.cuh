@@ -5,7 +5,11 @@
 
 struct CornerWorkView {
   unsigned long long* maxbits;  // [nframes] bit pattern of max u = 8*lmin
-  unsigned* ncand;              // [nframes] candidates appended (may exceed cand_cap: overflow)
+  unsigned* ncand;              // [nframes] entries appended to the provisional list by the fused pass (may exceed cand_cap)
+  unsigned* nfinal;             // [nframes] candidates = sort words in pk_a (may exceed cand_cap: overflow)
+  int* exact_list;              // [nframes] != 0: the unordered list holds exactly the nfinal candidates (two-pass / rescued)
+  int* rescue_list;             // [nframes] frames whose provisional list overflowed
+  int* rescue_count;            // [1]
   unsigned* ntotal;             // [nframes] candidates counted by the bitmap scan
   int* status;                  // [nframes] 0 ok, 1 candidate capacity exceeded
   unsigned* bitmap;             // [nframes][h][wpr] one bit per pixel
@@ -49,6 +53,10 @@ static inline size_t corner_work_carve(CornerWorkView& v, void* base, int w, int
   v.grid_per_frame = (size_t)v.gw * v.gh * 2;
   v.maxbits = (unsigned long long*)take(sizeof(unsigned long long) * nframes);
   v.ncand = (unsigned*)take(sizeof(unsigned) * nframes);
+  v.nfinal = (unsigned*)take(sizeof(unsigned) * nframes);
+  v.exact_list = (int*)take(sizeof(int) * nframes);
+  v.rescue_list = (int*)take(sizeof(int) * nframes);
+  v.rescue_count = (int*)take(sizeof(int));
   v.ntotal = (unsigned*)take(sizeof(unsigned) * nframes);
   v.status = (int*)take(sizeof(int) * nframes);
   v.bitmap = (unsigned*)take(sizeof(unsigned) * v.words_per_frame * nframes);

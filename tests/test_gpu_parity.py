@@ -389,6 +389,29 @@ def test_pair_frontend_batch(ctx, checker, g):
     assert nc == g["pair_nc"][0] and np.array_equal(li, g["pair_li"]) and _klt_close(lj, g["pair_lj"])
 
 
+def test_pair_frontend_batch_provisional_list_overflow(ctx, checker):
+    """Weak texture everywhere and ONE strong corner in a tile the probe pass does not visit: the fused score pass works
+    with a far too low provisional threshold, its list overflows the batch capacity (w*h/6), and the frame is redone
+    against the final threshold on the device (score_rescue_kernel).  Plain frames share the batch."""
+    rng = np.random.default_rng(8)
+    weak = (100 + rng.integers(0, 4, (H, W))).astype(np.uint8)
+    strong = weak.copy()
+    strong[200:216, 16:32] = 0
+    strong[208:216, 24:32] = 255
+    imgs = [strong, np.roll(strong, 1, axis=1), synth.frame(41, 0, W, H), synth.frame(41, 1, W, H), weak]
+    f = _frames(ctx, imgs)
+    cfg = sfmgpu.lkcfg(max_tracks=500)
+    pairs = ctx.pairs(4, 500)
+    pairs.run(f, 0, 4, cfg)
+    for p in range(4):
+        li, lj, nc = pairs.download(p)
+        wl, wj, wnc = checker.pair_frontend(imgs[p], imgs[p + 1], 500)
+        assert nc == wnc and np.array_equal(li, wl) and _klt_close(lj, wj), p
+    # the single-frame entry points (capacity w*h) on the same images
+    for k, im in enumerate(imgs):
+        assert np.array_equal(f.corners(k, 500), checker.shi_tomasi(im, 500)), k
+
+
 def test_pair_frontend_batch_with_score_ties(ctx, checker):
     """Quantised frames (many identical scores) between plain ones in ONE batch: the radix selection redoes exactly the
     frames whose consumed prefix holds a tie, inside the batched launch."""
