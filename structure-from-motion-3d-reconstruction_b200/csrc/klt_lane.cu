@@ -336,6 +336,352 @@ __global__ void __launch_bounds__(32 * LWARPS, MINB) klt_lane_kernel(KltLaunch k
   }
 }
 
+
+// ---- quadratic-form kernel (interior windows) ---------------------------------------------------------------------------
+// Every sample of lk_step's window is taken at the SAME fractional offset (fx, fy), so a bilinear sample is the dot
+// product w . n of the weight vector w = ((1-fx)(1-fy), fx(1-fy), (1-fx)fy, fx fy) with four INTEGER tap values, and
+// 2*Ix, 2*Iy and the error I0 - I1 (:439-442) are w . vx, w . vy, w . ve with integer tap differences.  The five sums
+// of :443-447 are therefore quadratic forms  w^T M w  with 4x4 INTEGER matrices M = sum over the window of v v'^T that
+// depend only on the two images and the integer window position.  While the position stays inside one pixel - steps
+// are a few hundredths of a pixel - an LK iteration costs ~90 FP64 instructions instead of ~2,500; the matrices are
+// rebuilt (exact int32 arithmetic, ~5,000 IMAD) only when floor(position) or the pyramid level changes.  The matrices
+// are exact, so the sums differ from the reference's 121-term FP64 loops only by rounding (measured: DESIGN.md §4).
+//
+// Build: with D[r][c] the tap-difference images (DX[r][c] = T1[r][c+1] - T1[r][c-1], DY[r][c] = T1[r+1][c] - T1[r-1][c],
+// DE[r][c] = T0[r][c] - T1[r][c]; r, c = 1..12 in tile coordinates), window pixel (r, c), r, c = 1..11, has
+// v = (D[r][c], D[r][c+1], D[r+1][c], D[r+1][c+1]).  Entry (k, l) of M is a sum of products A[.]B[.] over a shifted
+// 11 x 11 window of the 12 x 12 grid, so the ten entries of a family come from FIVE product sums over the grid (same
+// position, right neighbour, lower neighbour, the two diagonals) minus boundary rows / columns.
+//
+// Lanes of a warp advance independently (level, iteration): a lane iterates while its matrices are valid and waits when
+// it needs new ones; when every unfinished lane waits, all of them stage their tiles and build together.
+constexpr int QM = 50;                         // doubles per lane: XX, YY, XY, XE, YE x 10 upper-triangle entries
+constexpr int QSTRIDE = QM * 8;                // 400 B = 25 x 16 B: LDS.128 conflict free across a quarter warp
+
+struct QuadFam {
+  int T00, R1_00, R12_00, C1_00, C12_00, K11, K1c, Kc1, Kcc, T01, R1_01, R12_01, T02, C1_02, C12_02, M03, M12;
+};
+
+__device__ __forceinline__ void quad_zero(QuadFam& f) {
+  f.T00 = f.R1_00 = f.R12_00 = f.C1_00 = f.C12_00 = f.K11 = f.K1c = f.Kc1 = f.Kcc = 0;
+  f.T01 = f.R1_01 = f.R12_01 = f.T02 = f.C1_02 = f.C12_02 = f.M03 = f.M12 = 0;
+}
+
+// products inside grid row rr (a, b: that row's difference values, index c-1)
+template <bool SYM>
+__device__ __forceinline__ void quad_same_row(QuadFam& f, const int (&a)[12], const int (&b)[12], bool first, bool last) {
+  const int p1 = a[0] * b[0], p12 = a[11] * b[11];
+  int rs = p1 + p12;
+#pragma unroll
+  for (int c = 1; c < 11; c++) rs += a[c] * b[c];
+  f.T00 += rs;
+  f.C1_00 += p1;
+  f.C12_00 += p12;
+  int rs01 = 0;
+#pragma unroll
+  for (int c = 0; c < 11; c++) {
+    rs01 += a[c] * b[c + 1];
+    if (!SYM) rs01 += b[c] * a[c + 1];
+  }
+  f.T01 += rs01;
+  if (first) {
+    f.R1_00 = rs;
+    f.K11 = p1;
+    f.K1c = p12;
+    f.R1_01 = rs01;
+  }
+  if (last) {
+    f.R12_00 = rs;
+    f.Kc1 = p1;
+    f.Kcc = p12;
+    f.R12_01 = rs01;
+  }
+}
+
+// products between grid rows rr-1 (ap, bp) and rr (ac, bc)
+template <bool SYM>
+__device__ __forceinline__ void quad_cross_row(QuadFam& f, const int (&ap)[12], const int (&bp)[12], const int (&ac)[12],
+                                               const int (&bc)[12]) {
+  int q1 = ap[0] * bc[0], q12 = ap[11] * bc[11];
+  if (!SYM) {
+    q1 += bp[0] * ac[0];
+    q12 += bp[11] * ac[11];
+  }
+  int rs = q1 + q12;
+#pragma unroll
+  for (int c = 1; c < 11; c++) {
+    rs += ap[c] * bc[c];
+    if (!SYM) rs += bp[c] * ac[c];
+  }
+  f.T02 += rs;
+  f.C1_02 += q1;
+  f.C12_02 += q12;
+  int m03 = 0, m12 = 0;
+#pragma unroll
+  for (int c = 0; c < 11; c++) {
+    m03 += ap[c] * bc[c + 1];
+    m12 += ap[c + 1] * bc[c];
+    if (!SYM) {
+      m03 += bp[c] * ac[c + 1];
+      m12 += bp[c + 1] * ac[c];
+    }
+  }
+  f.M03 += m03;
+  f.M12 += m12;
+}
+
+// entries (0,0) (0,1) (0,2) (0,3) (1,1) (1,2) (1,3) (2,2) (2,3) (3,3); off-diagonals of a symmetric family count twice
+template <bool SYM>
+__device__ __forceinline__ void quad_store(const QuadFam& f, double* m) {
+  const int od = SYM ? 2 : 1;
+  m[0] = (double)(f.T00 - f.R12_00 - f.C12_00 + f.Kcc);
+  m[1] = (double)(od * (f.T01 - f.R12_01));
+  m[2] = (double)(od * (f.T02 - f.C12_02));
+  m[3] = (double)(od * f.M03);
+  m[4] = (double)(f.T00 - f.R12_00 - f.C1_00 + f.Kc1);
+  m[5] = (double)(od * f.M12);
+  m[6] = (double)(od * (f.T02 - f.C1_02));
+  m[7] = (double)(f.T00 - f.R1_00 - f.C12_00 + f.K1c);
+  m[8] = (double)(od * (f.T01 - f.R1_01));
+  m[9] = (double)(f.T00 - f.R1_00 - f.C1_00 + f.K11);
+}
+
+__device__ __forceinline__ void row_ints(const uint4 q, int (&v)[LN]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < LN; i++) v[i] = (int)__byte_perm(w[i >> 2], 0, 0x4440 | (i & 3));
+}
+
+// tile: this lane's staged taps (I1 rows, then I0 rows); m: this lane's 50 doubles in shared memory
+__device__ __forceinline__ void quad_build(const unsigned char* tile, double* m) {
+  QuadFam xx, yy, xy, xe, ye;
+  quad_zero(xx);
+  quad_zero(yy);
+  quad_zero(xy);
+  quad_zero(xe);
+  quad_zero(ye);
+  int t1m[LN], t1c[LN];
+  int dxp[12], dyp[12], dep[12];
+  row_ints(*reinterpret_cast<const uint4*>(tile), t1m);
+  row_ints(*reinterpret_cast<const uint4*>(tile + 16), t1c);
+#pragma unroll
+  for (int c = 0; c < 12; c++) dxp[c] = dyp[c] = dep[c] = 0;
+#pragma unroll 1
+  for (int rr = 1; rr <= 12; rr++) {
+    int t1p[LN], t0[LN];
+    row_ints(*reinterpret_cast<const uint4*>(tile + (rr + 1) * 16), t1p);
+    row_ints(*reinterpret_cast<const uint4*>(tile + LIMG + rr * 16), t0);
+    int dxc[12], dyc[12], dec[12];
+#pragma unroll
+    for (int c = 1; c <= 12; c++) {
+      dxc[c - 1] = t1c[c + 1] - t1c[c - 1];
+      dyc[c - 1] = t1p[c] - t1m[c];
+      dec[c - 1] = t0[c] - t1c[c];
+    }
+    const bool first = rr == 1, last = rr == 12;
+    quad_same_row<true>(xx, dxc, dxc, first, last);
+    quad_same_row<true>(yy, dyc, dyc, first, last);
+    quad_same_row<false>(xy, dxc, dyc, first, last);
+    quad_same_row<false>(xe, dxc, dec, first, last);
+    quad_same_row<false>(ye, dyc, dec, first, last);
+    if (rr >= 2) {
+      quad_cross_row<true>(xx, dxp, dxp, dxc, dxc);
+      quad_cross_row<true>(yy, dyp, dyp, dyc, dyc);
+      quad_cross_row<false>(xy, dxp, dyp, dxc, dyc);
+      quad_cross_row<false>(xe, dxp, dep, dxc, dec);
+      quad_cross_row<false>(ye, dyp, dep, dyc, dec);
+    }
+#pragma unroll
+    for (int c = 0; c < 12; c++) {
+      dxp[c] = dxc[c];
+      dyp[c] = dyc[c];
+      dep[c] = dec[c];
+    }
+#pragma unroll
+    for (int c = 0; c < LN; c++) {
+      t1m[c] = t1c[c];
+      t1c[c] = t1p[c];
+    }
+  }
+  quad_store<true>(xx, m);
+  quad_store<true>(yy, m + 10);
+  quad_store<false>(xy, m + 20);
+  quad_store<false>(xe, m + 30);
+  quad_store<false>(ye, m + 40);
+}
+
+// the five sums from the matrices: 4*Sxx, 4*Sxy, 4*Syy, 2*bx, 2*by in the conventions of window_sums
+__device__ __forceinline__ void quad_eval(const double* m, double fx, double fy, double& a00, double& a01, double& a11, double& b0,
+                                          double& b1) {
+  const double gx = 1.0 - fx, gy = 1.0 - fy;
+  const double w0 = gx * gy, w1 = fx * gy, w2 = gx * fy, w3 = fx * fy;
+  const double ww[10] = {w0 * w0, w0 * w1, w0 * w2, w0 * w3, w1 * w1, w1 * w2, w1 * w3, w2 * w2, w2 * w3, w3 * w3};
+  double s[5];
+#pragma unroll
+  for (int f = 0; f < 5; f++) {
+    double mm[10];
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+      const double2 t = *reinterpret_cast<const double2*>(m + f * 10 + 2 * q);
+      mm[2 * q] = t.x;
+      mm[2 * q + 1] = t.y;
+    }
+    double acc = mm[0] * ww[0];
+#pragma unroll
+    for (int q = 1; q < 10; q++) acc = __fma_rn(mm[q], ww[q], acc);
+    s[f] = acc;
+  }
+  a00 = s[0];
+  a11 = s[1];
+  a01 = s[2];
+  b0 = s[3];
+  b1 = s[4];
+}
+
+template <int MINB, int LSTAGE>
+__global__ void __launch_bounds__(32, MINB) klt_quad_kernel(KltLaunch k, int* __restrict__ defer_count, int* __restrict__ defer_list) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  unsigned char* wtile = smem_raw;
+  unsigned char* tile = wtile + lane * LSTRIDE;
+  double* mq = reinterpret_cast<double*>(smem_raw + 32 * LSTRIDE + lane * QSTRIDE);
+  const long long total = (long long)k.npairs * k.cap;
+  const int ndir = k.pb ? 2 : 1;
+  for (long long wbase = (long long)blockIdx.x * 32; wbase < total; wbase += (long long)gridDim.x * 32) {
+    const long long g = wbase + lane;
+    const int pair = g < total ? (int)(g / k.cap) : 0;
+    const int slot = (int)(g - (long long)pair * k.cap);
+    const bool valid = g < total && (!k.counts || slot < k.counts[pair]);
+    double2 p0 = make_double2(0.0, 0.0);
+    if (valid) p0 = k.p0[g];
+    double px = p0.x, py = p0.y, x1 = 0.0, y1 = 0.0;
+    int n_it = 0;
+    bool alive = valid, finished = !valid;
+    // per-lane progress
+    int dir = 0, l = k.pv.levels - 1, it = 0;
+    bool leveldone = false;
+    double plx = px * (1.0 / (double)(1 << l)), ply = py * (1.0 / (double)(1 << l)), dlx = 0.0, dly = 0.0;
+    int tFX = INT_MIN, tFY = INT_MIN, tkey = -1;  // position / (dir, level) the lane's matrices belong to
+
+    while (true) {
+      // a finished level hands its result to the next one (:404-420)
+      if (!finished && (leveldone || it >= k.iters)) {
+        const double up = (double)(1 << l);
+        px = (plx + dlx) * up;
+        py = (ply + dly) * up;
+        if (l > 0) {
+          l--;
+        } else {
+          if (dir == 0) {
+            x1 = px;
+            y1 = py;
+          }
+          dir++;
+          l = k.pv.levels - 1;
+          if (dir >= ndir) finished = true;
+        }
+        const double scale = 1.0 / (double)(1 << l);
+        plx = px * scale;
+        ply = py * scale;
+        dlx = dly = 0.0;
+        it = 0;
+        leveldone = false;
+      }
+      if (!__any_sync(FULL, !finished)) break;
+      const bool canwork = !finished && it < k.iters && !leveldone;
+      const double x = plx + dlx, y = ply + dly;
+      const double fxx = floor(x), fyy = floor(y);
+      int FX = 0, FY = 0;
+      bool act = canwork;
+      if (act) {
+        const int w = k.pv.w[l], h = k.pv.h[l];
+        const bool finite_ok = (fabs(fxx) < 1.0e9) && (fabs(fyy) < 1.0e9);
+        FX = finite_ok ? (int)fxx : 0;
+        FY = finite_ok ? (int)fyy : 0;
+        const bool ok = finite_ok && FX - LR - 1 >= 0 && FX + LR + 3 <= w - 1 && FY - LR - 1 >= 0 && FY + LR + 3 <= h - 1;
+        if (!ok) {  // the next kernel in the chain redoes this feature from scratch
+          alive = false;
+          finished = true;
+          act = false;
+        }
+      }
+      const int key = dir * SFM_MAXL + l;
+      const bool hit = act && FX == tFX && FY == tFY && key == tkey;
+      if (__any_sync(FULL, hit)) {
+        if (hit) {
+          double a00, a01, a11, b0, b1;
+          quad_eval(mq, x - fxx, y - fyy, a00, a01, a11, b0, b1);
+          double sx = 0.0, sy = 0.0;
+          const double det = a00 * a11 - a01 * a01;
+          if (!(fabs(det) < 16.0 * 1e-9)) {  // |det| < 1e-9 of :452 on the 16x scaled determinant
+            const double rd = 2.0 / det;
+            sx = (a11 * b0 - a01 * b1) * rd;
+            sy = (a00 * b1 - a01 * b0) * rd;
+          }
+          n_it++;
+          it++;
+          dlx += sx;
+          dly += sy;
+          if (sx * sx + sy * sy < 1e-6) leveldone = true;  // hypot(step) < 1e-3 (:416), tested on the step just added
+        }
+        continue;
+      }
+      // nobody can iterate: every lane that still has work needs matrices for its position
+      unsigned need = __ballot_sync(FULL, act);
+      if (!need) continue;  // only level hand-overs are pending
+      __syncwarp();
+      while (need) {
+        int ss[LSTAGE], sx0[LSTAGE];
+        StageRegs sr[LSTAGE];
+#pragma unroll
+        for (int j = 0; j < LSTAGE; j++) {
+          ss[j] = need ? __ffs(need) - 1 : -1;
+          need &= need - 1;
+          const int src = ss[j] < 0 ? 0 : ss[j];
+          const int sFX = __shfl_sync(FULL, FX, src), sFY = __shfl_sync(FULL, FY, src), spair = __shfl_sync(FULL, pair, src);
+          const int sl = __shfl_sync(FULL, l, src), sdir = __shfl_sync(FULL, dir, src);
+          const int sA = k.fa0 + spair * k.fa_step, sB = k.fb0 + spair * k.fb_step;
+          const uint8_t* lbase = k.pv.base[sl];
+          const size_t fstride = k.pv.fstride[sl];
+          sx0[j] = sFX - LR - 1;
+          if (ss[j] >= 0 && lane < 2 * LN)
+            stage_load<false>(sr[j], lbase + (size_t)(sdir ? sB : sA) * fstride, lbase + (size_t)(sdir ? sA : sB) * fstride,
+                              k.pv.pitch[sl], k.pv.h[sl], sx0[j], sFY - LR - 1, lane);
+        }
+#pragma unroll
+        for (int j = 0; j < LSTAGE; j++)
+          if (ss[j] >= 0 && lane < 2 * LN) stage_store(sr[j], wtile + ss[j] * LSTRIDE, sx0[j], lane);
+      }
+      __syncwarp();
+      if (act) {
+        quad_build(tile, mq);
+        tFX = FX;
+        tFY = FY;
+        tkey = key;
+      }
+      __syncwarp();
+    }
+    if (alive) {
+      k.p1[g] = make_double2(x1, y1);
+      if (k.pb) k.pb[g] = make_double2(px, py);
+      if (k.nit) k.nit[g] = n_it;
+      if (k.keep) {
+        const double fbd = hypot(px - p0.x, py - p0.y);
+        k.keep[g] = (fbd >= k.fb_thresh) ? 0 : 1;  // NaN is kept (:362)
+      }
+    }
+    const unsigned dm = __ballot_sync(FULL, valid && !alive);
+    if (dm) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(defer_count, __popc(dm));
+      base = __shfl_sync(FULL, base, 0);
+      if (valid && !alive) defer_list[base + __popc(dm & ((1u << lane) - 1u))] = (int)g;
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace
 
 template <int ACC, int MINB, int LSTAGE, bool MASKED>
@@ -360,13 +706,28 @@ static int lane_launch(sfmgpu_ctx* ctx, const KltLaunch& k, const int* in_list, 
 
 // Interior windows of every slot; features it cannot handle are appended to defer_list (device), count in
 // *defer_count (device, zeroed by the caller on the same stream).  variant: tuning builds (A/B runs).
+template <int MINB, int LSTAGE>
+static int quad_launch(sfmgpu_ctx* ctx, const KltLaunch& k, int* defer_count, int* defer_list) {
+  const size_t smem = (size_t)32 * (LSTRIDE + QSTRIDE);
+  static bool configured = false;
+  if (!configured) {
+    SFM_CUDA(ctx, cudaFuncSetAttribute(klt_quad_kernel<MINB, LSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const long long total = (long long)k.npairs * k.cap;
+  if (total == 0) return 0;
+  SFM_LAUNCH(ctx, (klt_quad_kernel<MINB, LSTAGE>), sfm_cdiv(total, 32), 32, smem, k, defer_count, defer_list);
+  return 0;
+}
+
 int sfm_klt_lane_launch(sfmgpu_ctx* ctx, const KltLaunch& k, int* defer_count, int* defer_list, int variant) {
   // Measured on B200, C2 shape (scripts/klt_ab.py, KLT stage incl. the deferred pass, 238k tracks): <1,12,4> 4.43 ms
   // (168 registers, spills), <1,8,4> 3.57 ms, <2,8,4> 3.66 ms, <2,8,8> 3.97 ms: the schedule wants registers, not warps.
   switch (variant) {
     case 1: return lane_launch<1, 12, 4, false>(ctx, k, nullptr, nullptr, defer_count, defer_list);
     case 2: return lane_launch<2, 8, 4, false>(ctx, k, nullptr, nullptr, defer_count, defer_list);
-    default: return lane_launch<1, 8, 4, false>(ctx, k, nullptr, nullptr, defer_count, defer_list);
+    case 3: return lane_launch<1, 8, 4, false>(ctx, k, nullptr, nullptr, defer_count, defer_list);  // the FP64 window walk
+    default: return quad_launch<8, 4>(ctx, k, defer_count, defer_list);  // quadratic forms over integer matrices
   }
 }
 

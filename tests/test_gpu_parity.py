@@ -195,9 +195,10 @@ def test_klt_iteration_count(ctx, port):
     assert np.array_equal(nit, want)
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 13])
 def test_klt_kernel_modes(ctx, checker, port, mode):
-    """Both KLT kernels (warp-per-feature, lane-per-feature + deferred border features) against the checker on
+    """The KLT kernels (1: warp-per-feature; 2: lane-per-feature with quadratic forms over integer matrices + deferred border
+    features; 13: lane-per-feature with the FP64 window walk) against the checker on
     the same points, including border, out-of-image and non-finite ones; iteration counts must be identical."""
     rng = np.random.default_rng(15)
     f0, f1 = synth.frame(21, 0, 320, 240), synth.frame(21, 3, 320, 240)
