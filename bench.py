@@ -211,6 +211,7 @@ def main():
     ap.add_argument("--frames", type=int, default=NFRAMES, help="frames per GPU (default: the C2 sequence length)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipe", type=int, default=-1, help="pairs per sub-chunk of the two-lane pipeline (-1: library default, 0: off)")
+    ap.add_argument("--klt-mode", type=int, default=0, help="sfmgpu_klt_set_mode value (A/B timing of kernel variants)")
     ap.add_argument("--chunk", type=int, default=0, help="frames per chunk of the streaming e2e call (0: a quarter of the sequence)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -234,6 +235,8 @@ def main():
     ctx = sfmgpu.Context(local)  # raises without the CUDA library / device: there is no CPU fallback
     if args.pipe >= 0:
         ctx.pipeline_set(args.pipe)
+    if args.klt_mode:
+        ctx.klt_set_mode(args.klt_mode)
     nfr, npairs = args.frames, args.frames - 1
     cfg = sfmgpu.lkcfg(max_tracks=MAX_CORNERS, pyr_levels=LEVELS)
     frames = ctx.frames(W, H, nfr, LEVELS)

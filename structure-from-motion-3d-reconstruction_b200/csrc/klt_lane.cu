@@ -353,161 +353,184 @@ __global__ void __launch_bounds__(32 * LWARPS, MINB) klt_lane_kernel(KltLaunch k
 // 11 x 11 window of the 12 x 12 grid, so the ten entries of a family come from FIVE product sums over the grid (same
 // position, right neighbour, lower neighbour, the two diagonals) minus boundary rows / columns.
 //
+// (Tried and dropped: the build in FP32 on integer-valued floats - FFMA issues on both FP32 pipes - needs two more
+// accumulators per mixed family to stay below 2^24 and spills: 23.8 ms vs 16.1 ms; staging rounds of 8 / 16 features
+// instead of 4: 27 / 57 ms, spills again.)
+//
 // Lanes of a warp advance independently (level, iteration): a lane iterates while its matrices are valid and waits when
 // it needs new ones; when every unfinished lane waits, all of them stage their tiles and build together.
 constexpr int QM = 50;                         // doubles per lane: XX, YY, XY, XE, YE x 10 upper-triangle entries
 constexpr int QSTRIDE = QM * 8;                // 400 B = 25 x 16 B: LDS.128 conflict free across a quarter warp
 
+// Scalar type of the build: int32 (IMAD) or FP32 on integer-valued floats (FFMA, exact below 2^24: the largest entry is a
+// sum of 2 x 121 products of magnitude <= 65,025 = 15.7e6).
+template <typename T>
 struct QuadFam {
-  int T00, R1_00, R12_00, C1_00, C12_00, K11, K1c, Kc1, Kcc, T01, R1_01, R12_01, T02, C1_02, C12_02, M03, M12;
+  T m[10];  // entries (0,0) (0,1) (0,2) (0,3) (1,1) (1,2) (1,3) (2,2) (2,3) (3,3)
 };
 
-__device__ __forceinline__ void quad_zero(QuadFam& f) {
-  f.T00 = f.R1_00 = f.R12_00 = f.C1_00 = f.C12_00 = f.K11 = f.K1c = f.Kc1 = f.Kcc = 0;
-  f.T01 = f.R1_01 = f.R12_01 = f.T02 = f.C1_02 = f.C12_02 = f.M03 = f.M12 = 0;
-}
+__device__ __forceinline__ int qmad(int a, int b, int c) { return a * b + c; }
+__device__ __forceinline__ float qmad(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 
-// products inside grid row rr (a, b: that row's difference values, index c-1)
-template <bool SYM>
-__device__ __forceinline__ void quad_same_row(QuadFam& f, const int (&a)[12], const int (&b)[12], bool first, bool last) {
-  const int p1 = a[0] * b[0], p12 = a[11] * b[11];
-  int rs = p1 + p12;
+// Products inside grid row rr (a, b: that row's difference values, index c-1).  The row's "same position" sum feeds the
+// diagonal entries (columns 1..11 for k = 0, 2; columns 2..12 for k = 1, 3; rows 1..11 for k = 0, 1; rows 2..12 for
+// k = 2, 3), the "right neighbour" sum feeds (0,1) (rows 1..11) and (2,3) (rows 2..12).
+template <bool SYM, typename T>
+__device__ __forceinline__ void quad_same_row(QuadFam<T>& f, const T (&a)[12], const T (&b)[12], bool first, bool last) {
+  const T p1 = a[0] * b[0], p12 = a[11] * b[11];
+  T mid = a[1] * b[1];
 #pragma unroll
-  for (int c = 1; c < 11; c++) rs += a[c] * b[c];
-  f.T00 += rs;
-  f.C1_00 += p1;
-  f.C12_00 += p12;
-  int rs01 = 0;
-#pragma unroll
-  for (int c = 0; c < 11; c++) {
-    rs01 += a[c] * b[c + 1];
-    if (!SYM) rs01 += b[c] * a[c + 1];
-  }
-  f.T01 += rs01;
-  if (first) {
-    f.R1_00 = rs;
-    f.K11 = p1;
-    f.K1c = p12;
-    f.R1_01 = rs01;
-  }
-  if (last) {
-    f.R12_00 = rs;
-    f.Kc1 = p1;
-    f.Kcc = p12;
-    f.R12_01 = rs01;
-  }
-}
-
-// products between grid rows rr-1 (ap, bp) and rr (ac, bc)
-template <bool SYM>
-__device__ __forceinline__ void quad_cross_row(QuadFam& f, const int (&ap)[12], const int (&bp)[12], const int (&ac)[12],
-                                               const int (&bc)[12]) {
-  int q1 = ap[0] * bc[0], q12 = ap[11] * bc[11];
-  if (!SYM) {
-    q1 += bp[0] * ac[0];
-    q12 += bp[11] * ac[11];
-  }
-  int rs = q1 + q12;
+  for (int c = 2; c < 11; c++) mid = qmad(a[c], b[c], mid);
+  const T left = mid + p1, right = mid + p12;  // columns 1..11 / 2..12
+  T rs01 = a[0] * b[1];
+  if (!SYM) rs01 = qmad(b[0], a[1], rs01);
 #pragma unroll
   for (int c = 1; c < 11; c++) {
-    rs += ap[c] * bc[c];
-    if (!SYM) rs += bp[c] * ac[c];
+    rs01 = qmad(a[c], b[c + 1], rs01);
+    if (!SYM) rs01 = qmad(b[c], a[c + 1], rs01);
   }
-  f.T02 += rs;
-  f.C1_02 += q1;
-  f.C12_02 += q12;
-  int m03 = 0, m12 = 0;
+  const T zero = (T)0;
+  f.m[0] += last ? zero : left;
+  f.m[4] += last ? zero : right;
+  f.m[1] += last ? zero : rs01;
+  f.m[7] += first ? zero : left;
+  f.m[9] += first ? zero : right;
+  f.m[8] += first ? zero : rs01;
+}
+
+// products between grid rows rr-1 (ap, bp) and rr (ac, bc): entries (0,2) (columns 1..11), (1,3) (columns 2..12), (0,3), (1,2)
+template <bool SYM, typename T>
+__device__ __forceinline__ void quad_cross_row(QuadFam<T>& f, const T (&ap)[12], const T (&bp)[12], const T (&ac)[12],
+                                               const T (&bc)[12]) {
+  T q1 = ap[0] * bc[0], q12 = ap[11] * bc[11], mid = ap[1] * bc[1];
+  if (!SYM) {
+    q1 = qmad(bp[0], ac[0], q1);
+    q12 = qmad(bp[11], ac[11], q12);
+    mid = qmad(bp[1], ac[1], mid);
+  }
+#pragma unroll
+  for (int c = 2; c < 11; c++) {
+    mid = qmad(ap[c], bc[c], mid);
+    if (!SYM) mid = qmad(bp[c], ac[c], mid);
+  }
+  f.m[2] += mid + q1;
+  f.m[6] += mid + q12;
+  T m03 = f.m[3], m12 = f.m[5];
 #pragma unroll
   for (int c = 0; c < 11; c++) {
-    m03 += ap[c] * bc[c + 1];
-    m12 += ap[c + 1] * bc[c];
+    m03 = qmad(ap[c], bc[c + 1], m03);
+    m12 = qmad(ap[c + 1], bc[c], m12);
     if (!SYM) {
-      m03 += bp[c] * ac[c + 1];
-      m12 += bp[c + 1] * ac[c];
+      m03 = qmad(bp[c], ac[c + 1], m03);
+      m12 = qmad(bp[c + 1], ac[c], m12);
     }
   }
-  f.M03 += m03;
-  f.M12 += m12;
+  f.m[3] = m03;
+  f.m[5] = m12;
 }
 
-// entries (0,0) (0,1) (0,2) (0,3) (1,1) (1,2) (1,3) (2,2) (2,3) (3,3); off-diagonals of a symmetric family count twice
-template <bool SYM>
-__device__ __forceinline__ void quad_store(const QuadFam& f, double* m) {
-  const int od = SYM ? 2 : 1;
-  m[0] = (double)(f.T00 - f.R12_00 - f.C12_00 + f.Kcc);
-  m[1] = (double)(od * (f.T01 - f.R12_01));
-  m[2] = (double)(od * (f.T02 - f.C12_02));
-  m[3] = (double)(od * f.M03);
-  m[4] = (double)(f.T00 - f.R12_00 - f.C1_00 + f.Kc1);
-  m[5] = (double)(od * f.M12);
-  m[6] = (double)(od * (f.T02 - f.C1_02));
-  m[7] = (double)(f.T00 - f.R1_00 - f.C12_00 + f.K1c);
-  m[8] = (double)(od * (f.T01 - f.R1_01));
-  m[9] = (double)(f.T00 - f.R1_00 - f.C1_00 + f.K11);
+// off-diagonal entries of a symmetric family count twice in the quadratic form
+template <bool SYM, typename T>
+__device__ __forceinline__ void quad_store(const QuadFam<T>& f, double* m) {
+#pragma unroll
+  for (int e = 0; e < 10; e++) {
+    const bool diag = e == 0 || e == 4 || e == 7 || e == 9;
+    const double v = (double)f.m[e];
+    m[e] = (SYM && !diag) ? v + v : v;
+  }
 }
 
-__device__ __forceinline__ void row_ints(const uint4 q, int (&v)[LN]) {
+__device__ __forceinline__ void row_vals(const uint4 q, int (&v)[LN]) {
   const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
   for (int i = 0; i < LN; i++) v[i] = (int)__byte_perm(w[i >> 2], 0, 0x4440 | (i & 3));
 }
-
-// tile: this lane's staged taps (I1 rows, then I0 rows); m: this lane's 50 doubles in shared memory
-__device__ __forceinline__ void quad_build(const unsigned char* tile, double* m) {
-  QuadFam xx, yy, xy, xe, ye;
-  quad_zero(xx);
-  quad_zero(yy);
-  quad_zero(xy);
-  quad_zero(xe);
-  quad_zero(ye);
-  int t1m[LN], t1c[LN];
-  int dxp[12], dyp[12], dep[12];
-  row_ints(*reinterpret_cast<const uint4*>(tile), t1m);
-  row_ints(*reinterpret_cast<const uint4*>(tile + 16), t1c);
+// floats 2^23 + byte (one PRMT each); the offset cancels in every difference
+__device__ __forceinline__ void row_vals(const uint4 q, float (&v)[LN]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-  for (int c = 0; c < 12; c++) dxp[c] = dyp[c] = dep[c] = 0;
+  for (int i = 0; i < LN; i++) v[i] = __uint_as_float(__byte_perm(w[i >> 2], 0x4B000000u, 0x7650 | (i & 3)));
+}
+
+// One sweep over the 12 grid rows for a subset of the families (PASS 0: xx, yy, xy; 1: xe; 2: ye), taps re-read from the
+// lane's tile every row: three short sweeps keep ~100 registers live instead of ~200 for a single one, which is what lets
+// twice as many warps share an SM (the kernel is latency-bound: 2 warps per scheduler issue half of the time).
+template <typename T, int PASS>
+__device__ __forceinline__ void quad_sweep(const unsigned char* tile, QuadFam<T>& f0, QuadFam<T>& f1, QuadFam<T>& f2) {
+  constexpr bool NX = PASS != 2, NY = PASS != 1, NE = PASS != 0;  // which difference images the pass needs
+  T dxp[12], dyp[12], dep[12];
+#pragma unroll
+  for (int c = 0; c < 12; c++) dxp[c] = dyp[c] = dep[c] = (T)0;
 #pragma unroll 1
   for (int rr = 1; rr <= 12; rr++) {
-    int t1p[LN], t0[LN];
-    row_ints(*reinterpret_cast<const uint4*>(tile + (rr + 1) * 16), t1p);
-    row_ints(*reinterpret_cast<const uint4*>(tile + LIMG + rr * 16), t0);
-    int dxc[12], dyc[12], dec[12];
+    T dxc[12], dyc[12], dec[12];
+    {
+      T t1c[LN];
+      if (NX || NE) row_vals(*reinterpret_cast<const uint4*>(tile + rr * 16), t1c);
+      if (NX) {
 #pragma unroll
-    for (int c = 1; c <= 12; c++) {
-      dxc[c - 1] = t1c[c + 1] - t1c[c - 1];
-      dyc[c - 1] = t1p[c] - t1m[c];
-      dec[c - 1] = t0[c] - t1c[c];
+        for (int c = 1; c <= 12; c++) dxc[c - 1] = t1c[c + 1] - t1c[c - 1];
+      }
+      if (NE) {
+        T t0[LN];
+        row_vals(*reinterpret_cast<const uint4*>(tile + LIMG + rr * 16), t0);
+#pragma unroll
+        for (int c = 1; c <= 12; c++) dec[c - 1] = t0[c] - t1c[c];
+      }
+    }
+    if (NY) {
+      T t1m[LN], t1p[LN];
+      row_vals(*reinterpret_cast<const uint4*>(tile + (rr - 1) * 16), t1m);
+      row_vals(*reinterpret_cast<const uint4*>(tile + (rr + 1) * 16), t1p);
+#pragma unroll
+      for (int c = 1; c <= 12; c++) dyc[c - 1] = t1p[c] - t1m[c];
     }
     const bool first = rr == 1, last = rr == 12;
-    quad_same_row<true>(xx, dxc, dxc, first, last);
-    quad_same_row<true>(yy, dyc, dyc, first, last);
-    quad_same_row<false>(xy, dxc, dyc, first, last);
-    quad_same_row<false>(xe, dxc, dec, first, last);
-    quad_same_row<false>(ye, dyc, dec, first, last);
-    if (rr >= 2) {
-      quad_cross_row<true>(xx, dxp, dxp, dxc, dxc);
-      quad_cross_row<true>(yy, dyp, dyp, dyc, dyc);
-      quad_cross_row<false>(xy, dxp, dyp, dxc, dyc);
-      quad_cross_row<false>(xe, dxp, dep, dxc, dec);
-      quad_cross_row<false>(ye, dyp, dep, dyc, dec);
+    if (PASS == 0) {
+      quad_same_row<true>(f0, dxc, dxc, first, last);
+      quad_same_row<true>(f1, dyc, dyc, first, last);
+      quad_same_row<false>(f2, dxc, dyc, first, last);
+      if (rr >= 2) {
+        quad_cross_row<true>(f0, dxp, dxp, dxc, dxc);
+        quad_cross_row<true>(f1, dyp, dyp, dyc, dyc);
+        quad_cross_row<false>(f2, dxp, dyp, dxc, dyc);
+      }
+    } else if (PASS == 1) {
+      quad_same_row<false>(f0, dxc, dec, first, last);
+      if (rr >= 2) quad_cross_row<false>(f0, dxp, dep, dxc, dec);
+    } else {
+      quad_same_row<false>(f0, dyc, dec, first, last);
+      if (rr >= 2) quad_cross_row<false>(f0, dyp, dep, dyc, dec);
     }
 #pragma unroll
     for (int c = 0; c < 12; c++) {
-      dxp[c] = dxc[c];
-      dyp[c] = dyc[c];
-      dep[c] = dec[c];
-    }
-#pragma unroll
-    for (int c = 0; c < LN; c++) {
-      t1m[c] = t1c[c];
-      t1c[c] = t1p[c];
+      if (NX) dxp[c] = dxc[c];
+      if (NY) dyp[c] = dyc[c];
+      if (NE) dep[c] = dec[c];
     }
   }
-  quad_store<true>(xx, m);
-  quad_store<true>(yy, m + 10);
-  quad_store<false>(xy, m + 20);
-  quad_store<false>(xe, m + 30);
-  quad_store<false>(ye, m + 40);
+}
+
+// tile: this lane's staged taps (I1 rows, then I0 rows); m: where the lane's 50 doubles go.  m may alias the tile: the
+// results are held in registers (as doubles) until the last sweep has read its taps.
+template <typename T>
+__device__ __forceinline__ void quad_build(const unsigned char* tile, double* m) {
+  QuadFam<T> a, b, c, dummy;
+#pragma unroll
+  for (int e = 0; e < 10; e++) a.m[e] = b.m[e] = c.m[e] = (T)0;
+  quad_sweep<T, 0>(tile, a, b, c);
+  double r[30];
+  quad_store<true>(a, r);
+  quad_store<true>(b, r + 10);
+  quad_store<false>(c, r + 20);
+#pragma unroll
+  for (int e = 0; e < 10; e++) a.m[e] = b.m[e] = (T)0;
+  quad_sweep<T, 1>(tile, a, dummy, dummy);
+  quad_sweep<T, 2>(tile, b, dummy, dummy);
+#pragma unroll
+  for (int e = 0; e < 30; e++) m[e] = r[e];
+  quad_store<false>(a, m + 30);
+  quad_store<false>(b, m + 40);
 }
 
 // the five sums from the matrices: 4*Sxx, 4*Sxy, 4*Syy, 2*bx, 2*by in the conventions of window_sums
@@ -538,14 +561,14 @@ __device__ __forceinline__ void quad_eval(const double* m, double fx, double fy,
   b1 = s[4];
 }
 
-template <int MINB, int LSTAGE>
+template <int MINB, int LSTAGE, typename T>
 __global__ void __launch_bounds__(32, MINB) klt_quad_kernel(KltLaunch k, int* __restrict__ defer_count, int* __restrict__ defer_list) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   unsigned char* wtile = smem_raw;
   unsigned char* tile = wtile + lane * LSTRIDE;
-  double* mq = reinterpret_cast<double*>(smem_raw + 32 * LSTRIDE + lane * QSTRIDE);
+  double* mq = reinterpret_cast<double*>(tile);  // the matrices replace the taps they were built from (400 B <= 448 B)
   const long long total = (long long)k.npairs * k.cap;
   const int ndir = k.pb ? 2 : 1;
   for (long long wbase = (long long)blockIdx.x * 32; wbase < total; wbase += (long long)gridDim.x * 32) {
@@ -655,7 +678,7 @@ __global__ void __launch_bounds__(32, MINB) klt_quad_kernel(KltLaunch k, int* __
       }
       __syncwarp();
       if (act) {
-        quad_build(tile, mq);
+        quad_build<T>(tile, mq);
         tFX = FX;
         tFY = FY;
         tkey = key;
@@ -706,17 +729,17 @@ static int lane_launch(sfmgpu_ctx* ctx, const KltLaunch& k, const int* in_list, 
 
 // Interior windows of every slot; features it cannot handle are appended to defer_list (device), count in
 // *defer_count (device, zeroed by the caller on the same stream).  variant: tuning builds (A/B runs).
-template <int MINB, int LSTAGE>
+template <int MINB, int LSTAGE, typename T>
 static int quad_launch(sfmgpu_ctx* ctx, const KltLaunch& k, int* defer_count, int* defer_list) {
-  const size_t smem = (size_t)32 * (LSTRIDE + QSTRIDE);
+  const size_t smem = (size_t)32 * LSTRIDE;
   static bool configured = false;
   if (!configured) {
-    SFM_CUDA(ctx, cudaFuncSetAttribute(klt_quad_kernel<MINB, LSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SFM_CUDA(ctx, cudaFuncSetAttribute(klt_quad_kernel<MINB, LSTAGE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   const long long total = (long long)k.npairs * k.cap;
   if (total == 0) return 0;
-  SFM_LAUNCH(ctx, (klt_quad_kernel<MINB, LSTAGE>), sfm_cdiv(total, 32), 32, smem, k, defer_count, defer_list);
+  SFM_LAUNCH(ctx, (klt_quad_kernel<MINB, LSTAGE, T>), sfm_cdiv(total, 32), 32, smem, k, defer_count, defer_list);
   return 0;
 }
 
@@ -727,7 +750,12 @@ int sfm_klt_lane_launch(sfmgpu_ctx* ctx, const KltLaunch& k, int* defer_count, i
     case 1: return lane_launch<1, 12, 4, false>(ctx, k, nullptr, nullptr, defer_count, defer_list);
     case 2: return lane_launch<2, 8, 4, false>(ctx, k, nullptr, nullptr, defer_count, defer_list);
     case 3: return lane_launch<1, 8, 4, false>(ctx, k, nullptr, nullptr, defer_count, defer_list);  // the FP64 window walk
-    default: return quad_launch<8, 4>(ctx, k, defer_count, defer_list);  // quadratic forms over integer matrices
+    case 4: return quad_launch<8, 4, int>(ctx, k, defer_count, defer_list);
+    case 5: return quad_launch<8, 4, float>(ctx, k, defer_count, defer_list);
+    case 6: return quad_launch<12, 8, float>(ctx, k, defer_count, defer_list);
+    // Measured on B200 (C2, KLT stage incl. the border pass): <8,4,int> 16.8 ms, <8,4,float> 16.6, <10,4,float> 15.6,
+    // <12,4,float> 15.0, <16,4,float> 24.2 (spills); a single-sweep build (255 registers, 8 warps) 15.2 ms.
+    default: return quad_launch<12, 4, float>(ctx, k, defer_count, defer_list);  // quadratic forms over integer matrices
   }
 }
 
