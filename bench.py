@@ -100,6 +100,22 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def profile_metrics():
+    """ncu-derived numbers of the committed captures (profiles/r1_metrics.json, C2 shape): static evidence, not re-measured."""
+    p = os.path.join(ROOT, "profiles", "r1_metrics.json")
+    try:
+        with open(p) as fh:
+            m = json.load(fh)
+    except Exception:
+        return {}
+    out = {}
+    for name, d in m.items():
+        for short in ("klt_quad_kernel", "score_tile_kernel<2>", "radix_sort_frame_kernel", "nms_kernel", "ransac_count_kernel", "pyr_down_kernel"):
+            if short in name and short not in out:
+                out[short] = d
+    return out
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -410,6 +426,10 @@ def main():
         value = tracks_all / (ms_step * 1e-3)
         e2e_val = tracks_all / (e2e_ms * 1e-3)
         per_rank_tracks = tracks_all / world
+        prof = profile_metrics()
+        kq = prof.get("klt_quad_kernel", {})
+        traffic = (kq.get("dram_read_bytes", 0) + kq.get("dram_write_bytes", 0)) or None
+        klt_kernels = "klt_quad_kernel (+ klt_lane_kernel<...,masked> / klt_kernel<5,true> on border features)"
         klt_bytes = B_KLT * per_rank_tracks
         achieved = klt_bytes / (klt_ms * 1e-3) / 1e9
         pyr_bytes = nfr * W * H * sum(0.25 ** l for l in range(LEVELS))
@@ -422,13 +442,22 @@ def main():
                     "ms_per_step": e2e_ms, "steps": e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "klt_lane_kernel (+ klt_kernel<5,true> on deferred border features)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                         "note": "KLT is bound by the FP64 CUDA-core pipe, not HBM (SURVEY.md §8d): see roofline_fp64"},
-            "roofline_fp64": {"kernel": "klt_lane_kernel (+ klt_kernel<5,true> on deferred border features)", "achieved_tflops": F_KLT_IT * (it_all / world) / (klt_ms * 1e-3) / 1e12,
-                              "peak_tflops": fp64_peak, "peak_source": "in-run DFMA micro-benchmark (sfmgpu_fp64_peak)",
-                              "frac": F_KLT_IT * (it_all / world) / (klt_ms * 1e-3) / 1e12 / fp64_peak,
-                              "flop_per_lk_iteration": F_KLT_IT, "lk_iterations": it_all // world},
+            "roofline": {"bound": "hbm", "kernel": klt_kernels, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": traffic,
+                         "traffic_source": "dram__bytes_read+write of one klt_quad_kernel launch, ncu --set full on 998 C2 pairs (profiles/r1_metrics.json)",
+                         "peak_source": peak_src,
+                         "note": "KLT is bound by instruction issue (integer-valued FP32 matrix build + FP64 iterations), not HBM "
+                                 "(SURVEY.md §8d: ~140 flop/B): see roofline_issue"},
+            # The reference formulation costs 5,045 FP64 flop per LK iteration; the kernel evaluates the same sums as quadratic
+            # forms over exact integer matrices, so "reference flops per second" may exceed the FP64 peak - it is a speed
+            # figure, not a utilisation.  Utilisation = issue slots (ncu, committed capture).
+            "roofline_issue": {"kernel": "klt_quad_kernel", "bound": "instruction issue",
+                               "issue_active_frac": (kq.get("issue_active_pct") or 0) / 100.0 or None,
+                               "fp64_pipe_frac": (kq.get("fp64_pipe_pct") or 0) / 100.0 or None,
+                               "source": "profiles/r1_metrics.json (ncu smsp__issue_active / sm__pipe_fp64_cycles_active, not re-measured here)",
+                               "reference_formulation_tflops": F_KLT_IT * (it_all / world) / (klt_ms * 1e-3) / 1e12,
+                               "fp64_peak_tflops": fp64_peak, "fp64_peak_source": "in-run DFMA micro-benchmark (sfmgpu_fp64_peak)",
+                               "flop_per_lk_iteration_reference": F_KLT_IT, "lk_iterations": it_all // world},
             "stages_ms": {"pyramid": pyr_ms, "corner_score": cs_ms, "corner_select": sel_ms, "klt": klt_ms, "compact": st["compact"]},
             "stage_rooflines": {
                 "pyramid": {"bound": "hbm", "achieved": pyr_bytes / (pyr_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

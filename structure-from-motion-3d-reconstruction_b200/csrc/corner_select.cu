@@ -1027,7 +1027,7 @@ int select_smem_config(sfmgpu_ctx* ctx) {
     SFM_CUDA(ctx, cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelSmem)));
     SFM_CUDA(ctx, cudaFuncSetAttribute(radix_sort_frame_kernel<512, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem<512>)));
     SFM_CUDA(ctx, cudaFuncSetAttribute(radix_sort_frame_kernel<512, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem<512>)));
-    SFM_CUDA(ctx, cudaFuncSetAttribute(radix_sort_frame_kernel<1024, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem<1024>)));
+    SFM_CUDA(ctx, cudaFuncSetAttribute(radix_sort_frame_kernel<1024, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem<1024>)));
     done = true;
   }
   return 0;
@@ -1079,7 +1079,7 @@ int sfm_corners_select_stage(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int count,
     else
       SFM_LAUNCH(ctx, (radix_sort_frame_kernel<512, 8, 0>), count, 512, sizeof(RadixSmem<512>), wv, quality);
   } else {  // few frames: the widest block per frame
-    SFM_LAUNCH(ctx, (radix_sort_frame_kernel<1024, 4, 0>), count, 1024, sizeof(RadixSmem<1024>), wv, quality);
+    SFM_LAUNCH(ctx, (radix_sort_frame_kernel<1024, 4, 1>), count, 1024, sizeof(RadixSmem<1024>), wv, quality);
   }
   SFM_LAUNCH(ctx, nms_kernel, count, NMS_THREADS, 0, wv, f->w, f->h, max_corners, min_dist, out_xy, out_n);
   // frames where a score tie was consumed (status 3): raster order, then the exact emulation.  Blocks of all other
