@@ -334,10 +334,9 @@ def main():
             # the library's streaming call: H2D of chunk c+1 || pyramid + corners + KLT of chunk c || D2H of chunk c-1
             pairs.run_host(frames, host, cfg, li, lj, nk, nc, chunk=args.chunk)
             return
-        frames.upload_ptr(0, nfr, host.ctypes.data)
-        frames.build_pyramid(0, nfr)
-        pairs.run(frames, 0, npairs, cfg)
-        ctx.sync()  # results are written on the library's stream; NCCL runs on torch's
+        # same streaming call (chunked H2D || pyramids + corners + KLT), results stay on the device for the NCCL gather
+        pairs.run_host(frames, host, cfg, None, None, None, None, chunk=args.chunk)
+        ctx.sync()  # results are written on the library's streams; NCCL runs on torch's
         dist.gather(v_nk, g_nk, dst=0)
         dist.gather(v_nc, g_nc, dst=0)
         dist.gather(v_li, g_li, dst=0)

@@ -15,12 +15,14 @@
 // atomics and added to counts[h] with one global atomic per (block, hypothesis).  Operand traffic is
 // negligible (~4000 flop/B at 64k x 10k): the bound is the FP64 CUDA-core pipe, tensor cores are not used
 // (no dense contraction).
+#include <math.h>
+
 #include "common.cuh"
 
 namespace {
 
 constexpr int RS_THREADS = 256;
-constexpr int RS_PTS = 2;        // points per thread
+constexpr int RS_PTS = 4;        // points per thread
 constexpr int RS_HCHUNK = 64;    // hypotheses staged per block iteration
 
 // Reference-order Sampson pieces; returns n2 = num*num and den.
@@ -42,15 +44,36 @@ __device__ __forceinline__ bool is_inlier(double n2, double den, double thr, dou
   return (n2 / den) < thr;               // inside the band: the reference's literal test
 }
 
+// ---- FP32 screen -------------------------------------------------------------------------------------------------------
+// Most pairs are far from the threshold: the same quantities are evaluated in FP32 (FMA) together with a rigorous bound of
+// their distance to the EXACT real values, and only pairs the bound cannot decide run the FP64 code above.  With
+// u = 2^-24, P = max(|x|,|y|,1), P' = max(|x'|,|y'|,1), Pm = max(P,P'), Esum = sum |E_ij|, Emax = the largest absolute
+// row / column sum of E that enters ex, ey, ez, tx, ty:
+//   |v_f - v| <= 6u Emax Pm               for v in {ex, ey, ez, tx, ty}   (inputs rounded to FP32, two FMAs: <= 4.1u S)
+//   |num_f - num| <= 32u Esum P' Pm       (three such terms scaled by |x'|, |y'|, 1 plus two FMA roundings: <= 21u ...)
+//   |den_f - den| <= 64u (Emax Pm)^2 + 8u den_f   (v^2 error <= dv(2|v| + dv), |v| <= Emax Pm; four FMA roundings)
+// The FP64 reference's own value differs from the exact one by < 1e-13 relative to the same magnitudes, which the slack
+// between 21u and 32u (resp. 48u and 64u) covers.  Then  e < thr  is certain when (|num_f| + dn)^2 < thr_lo (den_f - dd)
+// and  e >= thr  is certain when (|num_f| - dn)^2 > thr_hi (den_f + dd), with thr_lo / thr_hi = thr (1 -/+ 2e-6) rounded
+// outwards and divided / multiplied by 1 + 2^-20 for the FP32 roundings of the bound arithmetic itself (< 7u).  NaNs,
+// infinities and overflowing magnitudes fail both tests and take the FP64 path.
+struct RsHyp {
+  float e[9];
+  float cn;   // 32u * Esum (rounded up, floored at 1e-30: subnormal hypotheses)
+  float qd;   // sqrt(64u) * Emax (rounded up)
+};
+
 __global__ void __launch_bounds__(RS_THREADS) ransac_count_kernel(const double2* __restrict__ xi, const double2* __restrict__ xj,
                                                                  int n, const double* __restrict__ E, int H, int h_per_block,
-                                                                 double thr, double thr_lo, double thr_hi,
-                                                                 int* __restrict__ counts) {
+                                                                 double thr, double thr_lo, double thr_hi, float thr_lo_f,
+                                                                 float thr_hi_f, int* __restrict__ counts) {
   __shared__ double sE[RS_HCHUNK * 9];
+  __shared__ RsHyp sH[RS_HCHUNK];
   __shared__ int sC[RS_HCHUNK];
   const int tid = threadIdx.x, lane = tid & 31;
   const int p0 = (blockIdx.x * RS_THREADS + tid) * RS_PTS;
   double x[RS_PTS], y[RS_PTS], xp[RS_PTS], yp[RS_PTS];
+  float xf[RS_PTS], yf[RS_PTS], xpf[RS_PTS], ypf[RS_PTS], pp[RS_PTS], pm[RS_PTS];
   bool valid[RS_PTS];
 #pragma unroll
   for (int k = 0; k < RS_PTS; k++) {
@@ -61,23 +84,70 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_count_kernel(const double2*
     y[k] = a.y;
     xp[k] = b.x;
     yp[k] = b.y;
+    xf[k] = (float)a.x;
+    yf[k] = (float)a.y;
+    xpf[k] = (float)b.x;
+    ypf[k] = (float)b.y;
+    const double P = fmax(fmax(fabs(a.x), fabs(a.y)), 1.0), Pp = fmax(fmax(fabs(b.x), fabs(b.y)), 1.0), Pm = fmax(P, Pp);
+    pm[k] = __double2float_ru(Pm);                 // NaN / inf propagate and end in the FP64 path
+    pp[k] = __double2float_ru(Pp * Pm * 1.000001);
   }
+  const float U8 = 4.76837158203125e-7f;  // 8u
   const int h_begin = blockIdx.y * h_per_block;
   const int h_end = min(H, h_begin + h_per_block);
   for (int hc = h_begin; hc < h_end; hc += RS_HCHUNK) {
     const int nh = min(RS_HCHUNK, h_end - hc);
     __syncthreads();
-    for (int i = tid; i < nh * 9; i += RS_THREADS) sE[i] = E[(size_t)hc * 9 + i];
+    for (int i = tid; i < nh * 9; i += RS_THREADS) {
+      const double v = E[(size_t)hc * 9 + i];
+      sE[i] = v;
+      sH[i / 9].e[i % 9] = (float)v;
+    }
     if (tid < RS_HCHUNK) sC[tid] = 0;
     __syncthreads();
+    if (tid < nh) {
+      const double* e = sE + tid * 9;
+      double a[9];
+#pragma unroll
+      for (int i = 0; i < 9; i++) a[i] = fabs(e[i]);
+      const double r0 = a[0] + a[1] + a[2], r1 = a[3] + a[4] + a[5], r2 = a[6] + a[7] + a[8];
+      const double c0 = a[0] + a[3] + a[6], c1 = a[1] + a[4] + a[7];
+      const double emax = fmax(fmax(fmax(r0, r1), fmax(r2, c0)), c1), esum = r0 + r1 + r2;
+      sH[tid].cn = fmaxf(__double2float_ru(esum * (32.0 * 5.9604644775390625e-8 * 1.000001)), 1e-30f);
+      sH[tid].qd = fmaxf(__double2float_ru(emax * (0.0019531250 * 1.000001)), 1e-18f);  // sqrt(64u) = 2^-9
+    }
+    __syncthreads();
     for (int h = 0; h < nh; h++) {
-      const double* e = sE + h * 9;
+      const RsHyp& hy = sH[h];
       int c = 0;
+      unsigned undecided = 0;
 #pragma unroll
       for (int k = 0; k < RS_PTS; k++) {
-        double n2, den;
-        sampson_parts(e, x[k], y[k], xp[k], yp[k], n2, den);
-        c += (valid[k] && is_inlier(n2, den, thr, thr_lo, thr_hi)) ? 1 : 0;
+        const float ex = fmaf(hy.e[0], xf[k], fmaf(hy.e[1], yf[k], hy.e[2]));
+        const float ey = fmaf(hy.e[3], xf[k], fmaf(hy.e[4], yf[k], hy.e[5]));
+        const float ez = fmaf(hy.e[6], xf[k], fmaf(hy.e[7], yf[k], hy.e[8]));
+        const float tx = fmaf(hy.e[0], xpf[k], fmaf(hy.e[3], ypf[k], hy.e[6]));
+        const float ty = fmaf(hy.e[1], xpf[k], fmaf(hy.e[4], ypf[k], hy.e[7]));
+        const float num = fabsf(fmaf(xpf[k], ex, fmaf(ypf[k], ey, ez)));
+        const float den = fmaf(ty, ty, fmaf(tx, tx, fmaf(ey, ey, fmaf(ex, ex, 1e-12f))));
+        const float dn = hy.cn * pp[k];
+        const float q = hy.qd * pm[k];
+        const float dd = fmaf(q, q, U8 * den);
+        const float a = num + dn, b = fmaxf(num - dn, 0.f);
+        const bool in = a * a < thr_lo_f * (den - dd);
+        const bool out = (b * b > thr_hi_f * (den + dd)) && (a < 1.0e18f);
+        c += (in && valid[k]) ? 1 : 0;
+        undecided |= (!in && !out && valid[k]) ? (1u << k) : 0u;
+      }
+      if (__any_sync(0xffffffffu, undecided != 0)) {  // rare: the reference's FP64 arithmetic decides
+        const double* e = sE + h * 9;
+#pragma unroll
+        for (int k = 0; k < RS_PTS; k++)
+          if (undecided & (1u << k)) {
+            double n2, den;
+            sampson_parts(e, x[k], y[k], xp[k], yp[k], n2, den);
+            c += is_inlier(n2, den, thr, thr_lo, thr_hi) ? 1 : 0;
+          }
       }
       c = __reduce_add_sync(0xffffffffu, c);
       if (lane == 0 && c) atomicAdd(&sC[h], c);
@@ -169,8 +239,20 @@ int score_resident(sfmgpu_ctx* ctx, double thr) {
     const unsigned gy = sfm_cdiv(H, hpb);
     // thr_lo / thr_hi bracket thr by 2^-50 relative (see is_inlier)
     const double eps = 8.8817841970012523e-16;  // 2^-50
+    // FP32 screen thresholds: thr (1 -/+ 2e-6), rounded outwards, with the 1 + 2^-20 of the bound arithmetic folded in.
+    // A threshold the screen cannot represent (<= 0, non-finite, outside the FP32 range) disables it: every pair is
+    // then undecided and takes the FP64 path.
+    const double kk = 1.0 + 9.5367431640625e-7;
+    float tlo = (float)(thr * (1.0 - 2e-6) / kk), thi = (float)(thr * (1.0 + 2e-6) * kk);
+    tlo = nextafterf(tlo, -INFINITY);
+    thi = nextafterf(thi, INFINITY);
+    if (!(thr > 1e-30 && thr < 1e30)) {
+      tlo = -INFINITY;  // "a*a < -inf" never holds
+      thi = INFINITY;   // "b*b > inf" never holds
+    }
     SFM_LAUNCH(ctx, ransac_count_kernel, dim3(gx, gy), RS_THREADS, 0, (const double2*)ctx->rs_xi.p, (const double2*)ctx->rs_xj.p,
-               n, (const double*)ctx->rs_E.p, H, (int)hpb, thr, thr * (1.0 - eps), thr * (1.0 + eps), (int*)ctx->rs_counts.p);
+               n, (const double*)ctx->rs_E.p, H, (int)hpb, thr, thr * (1.0 - eps), thr * (1.0 + eps), tlo, thi,
+               (int*)ctx->rs_counts.p);
   }
   SFM_LAUNCH(ctx, ransac_argmax_kernel, 1, 1024, 0, (const int*)ctx->rs_counts.p, H, best);
   if (H > 0 && n > 0)

@@ -310,6 +310,29 @@ def test_ransac_threshold_band_takes_the_literal_division(ctx, port):
                 assert np.array_equal(counts, wc) and bh == wb and np.array_equal(inl, wi)
 
 
+@pytest.mark.parametrize("scale_pts,scale_e", [(1.0, 1.0), (1520.0, 1.0), (1.0, 1e-20), (1.0, 1e20), (1e6, 1e-3), (1e-4, 1.0),
+                                                (1e25, 1e25)])
+def test_ransac_fp32_screen_is_rigorous(ctx, port, scale_pts, scale_e):
+    """The FP32 screen decides only what its error bound allows, whatever the magnitudes: pixel-unit coordinates,
+    tiny / huge hypotheses, values that overflow FP32, thresholds of every size (incl. <= 0, inf, nan), and thresholds
+    placed just beside computed errors.  Counts, winner and inlier list stay bit-exact."""
+    pi, pj = two_view_scene(1500, seed=77)
+    xi, xj = port.norm_points(TEMPLE_K, pi) * scale_pts, port.norm_points(TEMPLE_K, pj) * scale_pts
+    E, _ = port.ransac_hypotheses(port.norm_points(TEMPLE_K, pi), port.norm_points(TEMPLE_K, pj), 96)
+    E = E * scale_e
+    rng = np.random.default_rng(5)
+    E[5] = rng.normal(0, 1, 9)
+    E[6] = 0.0
+    with np.errstate(all="ignore"):
+        errs = np.array([port.sampson(E[h], xi[i], xj[i]) for h in (0, 1, 5) for i in range(0, 1500, 97)])
+    errs = errs[np.isfinite(errs) & (errs > 0)]
+    near = np.concatenate([errs * f for f in (1.0, 1 - 1e-6, 1 + 1e-6, 1 - 3e-6, 1 + 3e-6, 1 - 1e-4, 1 + 1e-4)]) if len(errs) else np.zeros(0)
+    for thr in [1e-3, 1e-9, 1.0, 1e6, 1e-40, 1e35, 0.0, -1.0, np.inf, np.nan] + near[::5].tolist():
+        counts, bh, inl = ctx.ransac_score(xi, xj, E, float(thr))
+        wc, wb, wi = port.ransac_score(xi, xj, E, float(thr))
+        assert np.array_equal(counts, wc) and bh == wb and np.array_equal(inl, wi), (scale_pts, scale_e, thr)
+
+
 def test_ransac_golden(ctx, g):
     counts, bh, inl = ctx.ransac_score(g["rs_xi"], g["rs_xj"], g["rs_E"], 1e-3)
     assert np.array_equal(counts, g["rs_counts"]) and bh == g["rs_best"][0] and np.array_equal(inl, g["rs_inl"])
