@@ -467,7 +467,10 @@ def main():
             "kept_fraction": kept_all / max(tracks_all, 1),
             "ransac": {"value": RS_H * RS_N / (rs_ms * 1e-3), "unit": "hyp*pts/s", "ms": rs_ms, "hypotheses": RS_H, "points": RS_N,
                        "e2e_value": RS_H * RS_N / (rs_e2e_ms * 1e-3), "best_h": int(bh), "best_inliers": int(len(inl)),
-                       "fp64_frac": F_RS * RS_H * RS_N / (rs_ms * 1e-3) / 1e12 / fp64_peak,
+                       # 35 flop per pair in the reference formulation; the kernel screens in FP32 and runs the FP64
+                       # arithmetic only for undecided pairs, so this is a speed figure relative to the DFMA peak
+                       "reference_formulation_tflops_over_fp64_peak": F_RS * RS_H * RS_N / (rs_ms * 1e-3) / 1e12 / fp64_peak,
+                       "issue_active_frac": (prof.get("ransac_count_kernel", {}).get("issue_active_pct") or 0) / 100.0 or None,
                        "hypotheses_source": "synthetic [t]x R around the C4 motion (scoring cost is value-independent)",
                        "find_E_ransac": find_e},
         }
