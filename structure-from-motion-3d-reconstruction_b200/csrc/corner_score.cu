@@ -187,13 +187,13 @@ __device__ __forceinline__ void score_tile(ScoreSmem& sm, const uint8_t* __restr
     thr8 = 8.0 * thr;                   // s >= thr  <=>  u >= 8*thr
     bound = __double2float_rd(thr8);
     // order code of the radix selection path: distance of the score's bit pattern below the frame maximum, shifted so
-    // that the whole candidate range [thr, max] fits 32 bits (ascending code = descending score; scores are
+    // that the whole candidate range [thr, max] fits CORNER_CODE_BITS bits (ascending code = descending score; scores are
     // non-negative doubles, so bit order is value order)
     maxkey = (unsigned long long)__double_as_longlong(maxv);
     const unsigned long long thrkey = thr > 0.0 ? (unsigned long long)__double_as_longlong(thr) : 0ull;
     const unsigned long long range = maxkey > thrkey ? maxkey - thrkey : 0ull;
     const int bits = 64 - __clzll((long long)range);
-    shift = bits > 32 ? bits - 32 : 0;
+    shift = bits > CORNER_CODE_BITS ? bits - CORNER_CODE_BITS : 0;
   }
   const bool col_in = x < w, col_interior = x >= 2 && x < w - 2;
   const bool tile_inner = X0 >= 2 && X0 + TW <= w - 2 && Y0 >= 2 && Y0 + TH <= h - 2;  // no border pixel in this tile
@@ -337,7 +337,7 @@ __device__ __forceinline__ void score_tile(ScoreSmem& sm, const uint8_t* __restr
             const unsigned long long k = (unsigned long long)__double_as_longlong(0.125 * u);
             wv.tmp_idx[(size_t)fr * wv.cand_cap + slot] = ((unsigned)(Y0 + row) << 16) | (unsigned)(X0 + col);
             wv.tmp_key[(size_t)fr * wv.cand_cap + slot] = k;
-            if (MODE == 1)  // k in [thr, max]: code < 2^32 (MODE 2: candidate_finalize_kernel writes the sort words)
+            if (MODE == 1)  // k in [thr, max]: code < 2^CORNER_CODE_BITS (MODE 2: candidate_finalize_kernel writes the sort words)
               wv.pk_a[(size_t)fr * wv.cand_cap + slot] = (((maxkey - k) >> shift) << 32) | slot;
           }
         }
@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(256) candidate_finalize_kernel(CornerWorkView 
   const unsigned long long thrkey = thr > 0.0 ? (unsigned long long)__double_as_longlong(thr) : 0ull;
   const unsigned long long range = maxkey > thrkey ? maxkey - thrkey : 0ull;
   const int bits = 64 - __clzll((long long)range);
-  const int shift = bits > 32 ? bits - 32 : 0;
+  const int shift = bits > CORNER_CODE_BITS ? bits - CORNER_CODE_BITS : 0;
   for (unsigned e0 = blockIdx.x * blockDim.x; e0 < nprov; e0 += gridDim.x * blockDim.x) {  // warp-uniform trip count
     const unsigned e = e0 + tid;
     unsigned long long k = 0;

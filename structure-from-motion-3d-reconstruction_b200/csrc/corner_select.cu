@@ -12,8 +12,8 @@
 // stable insertion sort).  Depth-limit exhaustion takes the sequential heap-sort restatement.
 //
 // Fast path (default): the order std::sort produces is unique wherever the scores are distinct, so the candidates are
-// first sorted by a segmented LSD radix sort (radix_*_kernel: 4 passes of 8 bits over a 32-bit order code, then
-// radix_fixup_kernel orders the few candidates that share a code by their full 64-bit score) and the selection walks
+// first sorted by a segmented LSD radix sort (radix_sort_frame_kernel: LSD passes of 8 bits over a 24-bit order code, then
+// the candidates that share a code are ordered by their full 64-bit score) and the selection walks
 // that list.  Only if two candidates with IDENTICAL scores lie inside the prefix the selection consumed — the one
 // case where introsort's tie order is observable — is the frame redone with the exact introsort emulation above
 // (status 3 -> select_kernel mode 3).  Results are bit-identical either way (tests force both paths).
@@ -371,7 +371,7 @@ __device__ void produce_sorted(SelSmem& sm, sfm_key_t* key, uint32_t* idx, uint3
 // final sweep puts runs of equal codes into descending order of the full 64-bit score (one thread per run, in place; a
 // run is a handful of words) and records the first
 // position holding two IDENTICAL scores.
-constexpr int RX_PASSES = 4;   // 8-bit digits of the 32-bit code
+constexpr int RX_PASSES = CORNER_CODE_BITS / 8;  // 8-bit digits of the order code
 constexpr int RX_MAXRUN = 64;  // equal-code runs longer than this are treated like score ties
 
 constexpr int RX_TILE = 4096;  // words per tile (THREADS * ITEMS)
@@ -408,6 +408,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) radix_sort_frame_kern
   const size_t cb = (size_t)fr * wv.cand_cap;
   unsigned long long* A = wv.pk_a + cb;
   unsigned long long* B = wv.pk_b + cb;
+  if (tid == 0) wv.sorted_in_b[fr] = 0;
   for (int i = tid; i < RX_PASSES * 256; i += THREADS) (&sm.hist[0][0])[i] = 0;
   if (tid == 0) sm.nkeep = 0;
   __syncthreads();
@@ -435,7 +436,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) radix_sort_frame_kern
     // provisional list of the fused score pass: the frame maximum is final now.  Sweep 0 keeps the entries that reach
     // the final threshold (s >= thr, :282) as sort words (order code << 32 | list slot), clears the candidate-bitmap
     // bit of every other entry, and builds the histograms on the way.  The order code is the distance of the score's bit
-    // pattern below the maximum, shifted so that [thr, max] fits 32 bits (ascending code = descending score).
+    // pattern below the maximum, shifted so that [thr, max] fits CORNER_CODE_BITS bits (ascending code = descending score).
     const unsigned nprov = wv.ncand[fr];
     if (nprov > (unsigned)wv.cand_cap) return;  // such frames are on the rescue list (exact_list) - unreachable
     const double maxv = 0.125 * __longlong_as_double(wv.maxbits[fr]);
@@ -444,7 +445,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) radix_sort_frame_kern
     const unsigned long long thrkey = thr > 0.0 ? (unsigned long long)__double_as_longlong(thr) : 0ull;
     const unsigned long long range = maxkey > thrkey ? maxkey - thrkey : 0ull;
     const int bits = 64 - __clzll((long long)range);
-    const int shift = bits > 32 ? bits - 32 : 0;
+    const int shift = bits > CORNER_CODE_BITS ? bits - CORNER_CODE_BITS : 0;
     const unsigned long long* lkey = wv.tmp_key + cb;
     const unsigned* lyx = wv.tmp_idx + cb;
     unsigned* bitmap = wv.bitmap + (size_t)fr * wv.words_per_frame;
@@ -592,10 +593,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) radix_sort_frame_kern
     src = dst;
     dst = t;
   }
-  if (src != A) {  // an odd number of passes ran: bring the sorted list home
-    for (unsigned i = tid; i < n; i += THREADS) A[i] = __ldcg(B + i);
-    __syncthreads();
-  }
+  if (tid == 0) wv.sorted_in_b[fr] = src != A;  // nms_kernel reads the list where the last pass left it
+  A = src;
 
   // final sweep: order the equal-code runs by the full score, note score ties.  Eight consecutive positions per thread.
   const unsigned* hi = reinterpret_cast<const unsigned*>(A) + 1;
@@ -694,7 +693,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(CornerWorkView wv, int
   }
   const int n = (int)ntot;
   const int cap_out = max_corners < 1 ? 1 : max_corners;  // the cap is tested after the push (:298-299)
-  const unsigned long long* sorted = wv.pk_a + (size_t)fr * wv.cand_cap;  // low word: slot in the unordered list
+  const unsigned long long* sorted = (wv.sorted_in_b[fr] ? wv.pk_b : wv.pk_a) + (size_t)fr * wv.cand_cap;  // low word: list slot
   const unsigned* slot_yx = wv.tmp_idx + (size_t)fr * wv.cand_cap;
   unsigned* blocked = wv.wordoff + (size_t)fr * wv.words_per_frame;  // free until a fallback frame needs raster ranks
   double2* out = out_xy + (size_t)fr * cap_out;

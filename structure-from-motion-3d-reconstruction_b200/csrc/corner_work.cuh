@@ -3,6 +3,10 @@
 #include <stddef.h>
 #include <stdint.h>
 
+// Width of the radix selection path's order code (a multiple of 8: one LSD pass per byte).  24 bits: ~10^3 pairs of
+// candidates per 1080p frame share a code and are ordered by their full score afterwards, one pass less than 32 bits.
+constexpr int CORNER_CODE_BITS = 24;
+
 struct CornerWorkView {
   unsigned long long* maxbits;  // [nframes] bit pattern of max u = 8*lmin
   unsigned* ncand;              // [nframes] entries appended to the provisional list by the fused pass (may exceed cand_cap)
@@ -26,6 +30,7 @@ struct CornerWorkView {
   unsigned long long* pk_a;     // [nframes][cand_cap] written by the candidate pass, holds the sorted result
   unsigned long long* pk_b;     // [nframes][cand_cap]
   unsigned* tiepos;             // [nframes]
+  int* sorted_in_b;             // [nframes] != 0: the sorted list ended in pk_b (odd number of passes ran)
   int wpr;
   size_t words_per_frame;
   int cand_cap;
@@ -71,5 +76,6 @@ static inline size_t corner_work_carve(CornerWorkView& v, void* base, int w, int
   v.lpos = (unsigned*)v.pk_b;  // the emulation runs after (or instead of) the radix sort
   v.rpos = v.lpos ? v.lpos + (size_t)cand_cap * nframes : nullptr;
   v.tiepos = (unsigned*)take(sizeof(unsigned) * nframes);
+  v.sorted_in_b = (int*)take(sizeof(int) * nframes);
   return off + 256;
 }
