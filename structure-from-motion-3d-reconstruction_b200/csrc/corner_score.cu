@@ -30,6 +30,8 @@
 //   order_kernel          scatter the unordered list to raster order (the order std::sort starts from)
 // Roofline: ~45 instructions per pixel and pass against 1 B/pixel of traffic: bound by instruction issue, not HBM
 // (DESIGN.md §corner-score).
+#include <type_traits>
+
 #include "common.cuh"
 #include "corner_work.cuh"
 
@@ -208,34 +210,42 @@ __device__ __forceinline__ void score_tile(ScoreSmem& sm, const uint8_t* __restr
   float uf[VRUN];
   float tmax = 0.f;
   unsigned pmask = 0;  // MODE 1: rows of this thread that go to the queue (bit 15: as border pixels)
+  // the walk exists twice: tiles without border pixels (the vast majority) skip every per-pixel position test
+  auto walk = [&](auto inner_tag) {
+    constexpr bool INNER = decltype(inner_tag)::value;
 #pragma unroll
-  for (int j = 0; j < VRUN; j++) {
-    const float na = cxx[(j + 4) * HS_S], nc = cxy[(j + 4) * HS_S], nb = cyy[(j + 4) * HS_S];
-    a += na;
-    c += nc;
-    b += nb;
-    const int y = Y0 + q * VRUN + j;
-    const bool interior = tile_inner || (col_interior && y >= 2 && y < h - 2);
-    const float u = est_u(a, b, c);
-    if (MODE == 0 || MODE == 2) {
-      uf[j] = interior ? u : -1.0e30f;
-      tmax = fmaxf(tmax, uf[j]);
-    } else {
-      if (col_in && y < h) {
-        if (interior) {
-          if (u >= bound - EST_MARGIN) pmask |= 1u << j;
-        } else if (0.0 >= thr8) {
-          pmask |= (1u << j) | (1u << (16 + j));  // border score is exactly 0 (:240, :253-254)
+    for (int j = 0; j < VRUN; j++) {
+      const float na = cxx[(j + 4) * HS_S], nc = cxy[(j + 4) * HS_S], nb = cyy[(j + 4) * HS_S];
+      a += na;
+      c += nc;
+      b += nb;
+      const int y = Y0 + q * VRUN + j;
+      const bool interior = INNER || (col_interior && y >= 2 && y < h - 2);
+      const float u = est_u(a, b, c);
+      if (MODE == 0 || MODE == 2) {
+        uf[j] = interior ? u : -1.0e30f;
+        tmax = fmaxf(tmax, uf[j]);
+      } else {
+        if (INNER || (col_in && y < h)) {
+          if (interior) {
+            if (u >= bound - EST_MARGIN) pmask |= 1u << j;
+          } else if (0.0 >= thr8) {
+            pmask |= (1u << j) | (1u << (16 + j));  // border score is exactly 0 (:240, :253-254)
+          }
         }
       }
+      a -= ra[j & 3];
+      c -= rc[j & 3];
+      b -= rb[j & 3];
+      ra[j & 3] = na;
+      rc[j & 3] = nc;
+      rb[j & 3] = nb;
     }
-    a -= ra[j & 3];
-    c -= rc[j & 3];
-    b -= rb[j & 3];
-    ra[j & 3] = na;
-    rc[j & 3] = nc;
-    rb[j & 3] = nb;
-  }
+  };
+  if (tile_inner)
+    walk(std::true_type{});
+  else
+    walk(std::false_type{});
 
   if (MODE == 0 || MODE == 2) {
     // tile maximum of the estimates
@@ -253,15 +263,21 @@ __device__ __forceinline__ void score_tile(ScoreSmem& sm, const uint8_t* __restr
       const double lb = fmax(runmax, fmax(0.0, (double)bm - (double)EST_MARGIN));
       thr8 = 8.0 * ((0.125 * lb) * quality);
       bound = fminf(bound, __double2float_rd(thr8) - EST_MARGIN);
+      if (tile_inner) {
 #pragma unroll
-      for (int j = 0; j < VRUN; j++) {
-        const int y = Y0 + q * VRUN + j;
-        if (col_in && y < h) {
-          const bool interior = tile_inner || (col_interior && y >= 2 && y < h - 2);
-          if (interior) {
-            if (uf[j] >= bound) pmask |= 1u << j;
-          } else if (0.0 >= thr8) {
-            pmask |= (1u << j) | (1u << (16 + j));  // border score is exactly 0 (:240, :253-254)
+        for (int j = 0; j < VRUN; j++)
+          if (uf[j] >= bound) pmask |= 1u << j;
+      } else {
+#pragma unroll
+        for (int j = 0; j < VRUN; j++) {
+          const int y = Y0 + q * VRUN + j;
+          if (col_in && y < h) {
+            const bool interior = col_interior && y >= 2 && y < h - 2;
+            if (interior) {
+              if (uf[j] >= bound) pmask |= 1u << j;
+            } else if (0.0 >= thr8) {
+              pmask |= (1u << j) | (1u << (16 + j));  // border score is exactly 0 (:240, :253-254)
+            }
           }
         }
       }

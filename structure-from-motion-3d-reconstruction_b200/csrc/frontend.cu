@@ -485,7 +485,9 @@ int sfmgpu_pair_frontend_host(sfmgpu_ctx* ctx, sfmgpu_frames* f, const uint8_t* 
   SFM_CUDA(ctx, cudaMemsetAsync(out->totals, 0, 64, ctx->stream));
   if (nframes == 0) return 0;
   SFM_TRY(pipe_streams(ctx));
-  int chunk = chunk_frames > 0 ? chunk_frames : (nframes + 5) / 6;
+  // default: a tenth of the sequence (measured on C2, 1000 frames: chunks of 84-125 frames 43.0 ms end to end, 167: 44.1,
+  // 250: 46.3, 50: 47.8 - smaller chunks shorten the pipeline fill, too small ones under-fill the per-frame kernels)
+  int chunk = chunk_frames > 0 ? chunk_frames : (nframes + 9) / 10;
   if (chunk < 2) chunk = 2;
   if (chunk > 1024) chunk = 1024;
   const int nchunks = (nframes + chunk - 1) / chunk;
