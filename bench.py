@@ -41,7 +41,7 @@ RS_N, RS_H = 10000, 65536
 
 def workload_cfg(n_gpus, nframes):
     return {
-        "workload": f"C2: synthetic 1080p {nframes}-frame sequence per GPU, pair-mode front end "
+        "workload": f"{'C2' if W == 1920 else 'C3'}: synthetic {W}x{H} {nframes}-frame sequence per GPU, pair-mode front end "
                     f"(pyramid L=3 + Shi-Tomasi/NMS {MAX_CORNERS} corners/frame + fwd/bwd KLT r=5 iters=10 + fb<1.0)",
         "frames_per_gpu": nframes, "pairs_per_gpu": nframes - 1, "width": W, "height": H, "max_corners": MAX_CORNERS,
         "pyr_levels": LEVELS, "sharding": f"sequence-per-rank x{n_gpus} (no data-path collective; NCCL gather of results)",
@@ -227,10 +227,15 @@ def main():
     ap.add_argument("--frames", type=int, default=NFRAMES, help="frames per GPU (default: the C2 sequence length)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipe", type=int, default=-1, help="pairs per sub-chunk of the two-lane pipeline (-1: library default, 0: off)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
+                    help="c2 (default, the bench line): 1080p, 2000 corners; c3: 4K, 8000 corners (side measurement, use --frames <= 300)")
     ap.add_argument("--klt-mode", type=int, default=0, help="sfmgpu_klt_set_mode value (A/B timing of kernel variants)")
     ap.add_argument("--chunk", type=int, default=0, help="frames per chunk of the streaming e2e call (0: a quarter of the sequence)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if args.workload == "c3":
+        global W, H, MAX_CORNERS
+        W, H, MAX_CORNERS = 3840, 2160, 8000
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -1,0 +1,84 @@
+#!/usr/bin/env python
+"""Side measurements for the configurations bench.py does not time (BASELINE.json C3, C4 sweep, C5, tracker mode) on ONE
+GPU, bounded samples.  Prints one JSON object; the round's copy is profiles/r1_configs.json.  Not a bench line."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "structure-from-motion-3d-reconstruction_b200"))
+sys.path.insert(0, ROOT)
+import sfmgpu  # noqa: E402
+from sfmgpu import sched  # noqa: E402
+import bench  # noqa: E402  (C4 scene helpers)
+
+out = {}
+ctx = sfmgpu.Context(0)
+
+# ---- C3: 4K, 8000 corners per frame, pair mode, resident ------------------------------------------------------------------
+W, H, NF, MC = 3840, 2160, 120, 8000
+cfg = sfmgpu.lkcfg(max_tracks=MC, pyr_levels=3)
+frames = ctx.frames(W, H, NF, 3)
+pairs = ctx.pairs(NF - 1, MC)
+frames.synth(0, NF, 20261018, 0)
+for _ in range(2):
+    frames.build_pyramid(0, NF)
+    pairs.run(frames, 0, NF - 1, cfg)
+ctx.sync()
+ctx.timer_start()
+REP = 3
+for _ in range(REP):
+    frames.build_pyramid(0, NF)
+    pairs.run(frames, 0, NF - 1, cfg)
+ms = ctx.timer_stop() / REP
+nt, nk, nit = pairs.totals()
+ctx.profile(True)
+pairs.run(frames, 0, NF - 1, cfg)
+st = ctx.stage_times()
+ctx.profile(False)
+out["C3_4k_pairs"] = {"frames": NF, "pairs": NF - 1, "max_corners": MC, "ms_per_step": ms, "ms_per_pair": ms / (NF - 1),
+                      "feature_tracks_per_s": nt / (ms * 1e-3), "tracks": nt, "kept_fraction": nk / max(nt, 1), "stages_ms": st}
+del pairs, frames
+
+# ---- C4: scoring sweep, 10 000 correspondences ---------------------------------------------------------------------------
+xi, xj = bench.c4_points(10000)
+sweep = {}
+for Hh in (1024, 2048, 4096, 8192, 16384, 32768, 65536):
+    E = bench.synthetic_hypotheses(Hh)
+    ctx.ransac_upload(xi, xj, E)
+    for _ in range(3):
+        ctx.ransac_score_resident(1e-3, fetch=False)
+    ctx.sync()
+    ctx.timer_start()
+    for _ in range(20):
+        ctx.ransac_score_resident(1e-3, fetch=False)
+    t = ctx.timer_stop() / 20
+    sweep[str(Hh)] = {"ms": t, "hyp_pts_per_s": Hh * 10000 / (t * 1e-3)}
+out["C4_sweep_10k_points"] = sweep
+
+# ---- C5 / tracker mode: stateful KLTTracker twin, 1080p, 2000 tracks, host-fed frames ---------------------------------------
+from sfmgpu import synth  # noqa: E402
+NSEQ, LEN = 8, 24
+seqs = [[synth.frame(20261018 + s, t, 1920, 1080) for t in range(LEN)] for s in range(NSEQ)]
+kw = dict(max_tracks=2000, min_tracks=818)
+trk = ctx.tracker(**kw)
+for img in seqs[0][:3]:  # warm-up (allocations)
+    trk.step(img)
+trk.reset(seqs[0][0])
+t0 = time.perf_counter()
+for img in seqs[0][1:]:
+    trk.step(img)
+one = time.perf_counter() - t0
+n_tr = trk.totals()[0]
+out["tracker_one_sequence_1080p"] = {"frames": LEN, "s": one, "steps_per_s": (LEN - 1) / one, "feature_tracks_per_s": n_tr / one}
+del trk
+t0 = time.perf_counter()
+res = sched.run_sequences(seqs, 0, kw, max_workers=NSEQ)
+par = time.perf_counter() - t0
+out["C5_8_sequences_one_gpu"] = {"sequences": NSEQ, "frames_each": LEN, "s": par, "steps_per_s": NSEQ * (LEN - 1) / par,
+                                 "speedup_vs_one_by_one": one * NSEQ / par}
+ctx.close()
+print(json.dumps(out, indent=1))

@@ -369,8 +369,7 @@ __device__ void produce_sorted(SelSmem& sm, sfm_key_t* key, uint32_t* idx, uint3
 // match_any rounds (round r of a warp covers 32 consecutive words, so rank order = position order), across warps and
 // tiles by running per-digit offsets in shared memory.  Passes whose digit is the same for every word are skipped.  A
 // final sweep puts runs of equal codes into descending order of the full 64-bit score (one thread per run, in place; a
-// run is a handful of words) and records the first
-// position holding two IDENTICAL scores.
+// run is a handful of words) and flags the candidates whose score is IDENTICAL to a neighbour's.
 constexpr int RX_PASSES = CORNER_CODE_BITS / 8;  // 8-bit digits of the order code
 constexpr int RX_MAXRUN = 64;  // equal-code runs longer than this are treated like score ties
 
@@ -390,8 +389,12 @@ struct RadixSmem {
 __device__ __forceinline__ unsigned rx_digit(unsigned long long v, int pass) { return (unsigned)(v >> (32 + 8 * pass)) & 255u; }
 
 // score bits of the candidate in slot `slot` of the frame's unordered list
-__device__ __forceinline__ unsigned long long rx_key_of(const CornerWorkView& wv, int fr, unsigned slot) {
-  return wv.tmp_key[(size_t)fr * wv.cand_cap + slot];
+// Low word of a sort word: list slot (< 2^30: images are at most 32767 x 32767) and, after the final sweep, two flags:
+// RX_TIE = identical score as the predecessor in the sorted list, RX_BIG = member of a group of >= 3 identical scores.
+constexpr unsigned RX_SLOT = 0x3FFFFFFFu, RX_TIE = 0x80000000u, RX_BIG = 0x40000000u;
+
+__device__ __forceinline__ unsigned long long rx_key_of(const CornerWorkView& wv, int fr, unsigned low) {
+  return wv.tmp_key[(size_t)fr * wv.cand_cap + (low & RX_SLOT)];
 }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -634,10 +637,15 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) radix_sort_frame_kern
         }
         A[q] = e;
       }
+      // identical scores inside the run: flag the later member of every pair, every member of larger groups
       for (unsigned p = i; p + 1 < j; p++)
         if (rx_key_of(wv, fr, (unsigned)A[p]) == rx_key_of(wv, fr, (unsigned)A[p + 1])) {
-          atomicMin(wv.tiepos + fr, p);
-          break;
+          A[p + 1] |= RX_TIE;
+          if (p > i && (A[p] & RX_TIE)) {
+            A[p - 1] |= RX_BIG;
+            A[p] |= RX_BIG;
+            A[p + 1] |= RX_BIG;
+          }
         }
     }
   }
@@ -654,7 +662,7 @@ struct NmsSmem {
   unsigned accm[NMS_ALIVE / 32], deadm[NMS_ALIVE / 32];  // decided survivors, one bit each
   unsigned short accl[NMS_ALIVE];
   int wcnt[NMS_WARPS];
-  int consumed, accepted, cut;
+  int consumed, accepted, cut, tiehit;
 };
 
 __device__ __forceinline__ int nms_block_scan(NmsSmem& sm, int c, int& total) {
@@ -702,6 +710,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(CornerWorkView wv, int
   if (tid == 0) {
     sm.consumed = 0;
     sm.accepted = 0;
+    sm.tiehit = 0;
   }
   __syncthreads();
   while (true) {
@@ -715,10 +724,13 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(CornerWorkView wv, int
       const int t = tid * NMS_EPT + e;
       yx[e] = t < cnt ? (unsigned)__ldcg(sorted + consumed + t) : 0u;
     }
+    unsigned tie = 0, big = 0;  // per candidate of this thread: RX_TIE / RX_BIG
 #pragma unroll
     for (int e = 0; e < NMS_EPT; e++) {
       const int t = tid * NMS_EPT + e;
-      yx[e] = t < cnt ? __ldg(slot_yx + yx[e]) : 0u;
+      tie |= (yx[e] >> 31) << e;
+      big |= ((yx[e] >> 30) & 1u) << e;
+      yx[e] = t < cnt ? __ldg(slot_yx + (yx[e] & RX_SLOT)) : 0u;
     }
 #pragma unroll
     for (int e = 0; e < NMS_EPT; e++) {
@@ -730,6 +742,14 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(CornerWorkView wv, int
 #pragma unroll
     for (int e = 0; e < NMS_EPT; e++)
       if (tid * NMS_EPT + e < cnt && !((bw[e] >> (yx[e] & 31u)) & 1u)) am |= 1u << e;
+    {
+      // std::sort's order inside a group of identical scores is only observable if at least two of its members are still
+      // unblocked: they would be accepted in that order, or one would suppress the other.  Conservative test on the
+      // survivors of the bitmap check (predecessors outside the warp / chunk count as unblocked).
+      const unsigned up = __shfl_up_sync(0xffffffffu, am, 1);
+      const unsigned prev_alive = (am << 1) | (lane > 0 ? (up >> (NMS_EPT - 1)) & 1u : 1u);
+      if (am & (big | (tie & prev_alive))) sm.tiehit = 1;
+    }
     // ordered compaction of the survivors; at most NMS_ALIVE are resolved now, the chunk is cut after the last one
     int na;
     const int exc = nms_block_scan(sm, __popc(am), na);
@@ -834,9 +854,9 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(CornerWorkView wv, int
   if (tid == 0) {
     wv.status[fr] = 0;
     if (out_n) out_n[fr] = sm.accepted;
-    // two identical scores inside the consumed prefix (or straddling its end): std::sort's tie order is observable, the
-    // frame is redone by select_kernel mode 3
-    if (wv.tiepos[fr] < (unsigned)sm.consumed) wv.status[fr] = 3;
+    // an observable tie (above), or a pile-up of equal order codes the sort did not resolve, inside the consumed prefix:
+    // the frame is redone by select_kernel mode 3
+    if (sm.tiehit || wv.tiepos[fr] < (unsigned)sm.consumed) wv.status[fr] = 3;
   }
 }
 
