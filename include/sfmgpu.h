@@ -43,6 +43,7 @@ typedef struct sfmgpu_ctx sfmgpu_ctx;
 typedef struct sfmgpu_frames sfmgpu_frames;   /* F frames of one size + their pyramids, resident in HBM */
 typedef struct sfmgpu_pairs sfmgpu_pairs;     /* device-resident results of a batch of frame pairs */
 typedef struct sfmgpu_tracker sfmgpu_tracker; /* stateful KLTTracker twin */
+typedef struct sfmgpu_multitracker sfmgpu_multitracker; /* S KLTTracker twins advanced in lock step */
 
 /* LKConfig, :307-316 (same field meaning and defaults). */
 typedef struct sfmgpu_lkcfg {
@@ -176,6 +177,18 @@ int sfmgpu_tracker_step_frames(sfmgpu_ctx* ctx, sfmgpu_tracker* t, sfmgpu_frames
 int sfmgpu_tracker_tracks(sfmgpu_ctx* ctx, sfmgpu_tracker* t, double* xy, int32_t* ids, int cap, int* n_out);
 /* Sum of track-list sizes entering step() so far, and LK iterations executed. */
 int sfmgpu_tracker_totals(sfmgpu_ctx* ctx, sfmgpu_tracker* t, long long* n_track_steps, long long* n_lk_iters);
+
+/* ---- S independent KLTTrackers advanced in lock step (several sequences per GPU) ------------------------ */
+/* Per sequence exactly KLTTracker::step (:340-391); one batched launch per stage for all sequences.  All images are
+ * w x h.  The first step resets every sequence (n_out = 0 everywhere). */
+int sfmgpu_multitracker_create(sfmgpu_ctx* ctx, const sfmgpu_lkcfg* cfg, int n_sequences, int w, int h, sfmgpu_multitracker** out);
+void sfmgpu_multitracker_destroy(sfmgpu_ctx* ctx, sfmgpu_multitracker* t);
+/* host_pix: [n_sequences][h][w], the next frame of every sequence.  prev_xy / cur_xy: [n_sequences][max(max_tracks,1)+1][2],
+ * ids: [n_sequences][max(max_tracks,1)+1], n_out: [n_sequences] survivors per sequence (any output may be NULL). */
+int sfmgpu_multitracker_step(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, const uint8_t* host_pix, double* prev_xy, double* cur_xy,
+                             int32_t* ids, int32_t* n_out);
+int sfmgpu_multitracker_tracks(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, int sequence, double* xy, int32_t* ids, int cap, int* n_out);
+int sfmgpu_multitracker_totals(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, long long* n_track_steps, long long* n_lk_iters);
 
 /* ---- RANSAC scoring: sampson_err + the loop at :667-676 ------------------------------------------------- */
 /* xi/xj: n normalised correspondences; E: H hypotheses, 9 doubles each.  counts[h] = #{i : e_i < thr};

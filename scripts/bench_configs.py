@@ -17,9 +17,10 @@ import bench  # noqa: E402  (C4 scene helpers)
 
 out = {}
 ctx = sfmgpu.Context(0)
+SECTIONS = set(sys.argv[1:]) or {"c3", "c4", "c5"}
 
 # ---- C3: 4K, 8000 corners per frame, pair mode, resident ------------------------------------------------------------------
-W, H, NF, MC = 3840, 2160, 120, 8000
+W, H, NF, MC = 3840, 2160, (120 if "c3" in SECTIONS else 3), 8000
 cfg = sfmgpu.lkcfg(max_tracks=MC, pyr_levels=3)
 frames = ctx.frames(W, H, NF, 3)
 pairs = ctx.pairs(NF - 1, MC)
@@ -46,7 +47,7 @@ del pairs, frames
 # ---- C4: scoring sweep, 10 000 correspondences ---------------------------------------------------------------------------
 xi, xj = bench.c4_points(10000)
 sweep = {}
-for Hh in (1024, 2048, 4096, 8192, 16384, 32768, 65536):
+for Hh in ((1024, 2048, 4096, 8192, 16384, 32768, 65536) if "c4" in SECTIONS else (1024,)):
     E = bench.synthetic_hypotheses(Hh)
     ctx.ransac_upload(xi, xj, E)
     for _ in range(3):
@@ -61,7 +62,7 @@ out["C4_sweep_10k_points"] = sweep
 
 # ---- C5 / tracker mode: stateful KLTTracker twin, 1080p, 2000 tracks, host-fed frames ---------------------------------------
 from sfmgpu import synth  # noqa: E402
-NSEQ, LEN = 8, 24
+NSEQ, LEN = 8, (24 if "c5" in SECTIONS else 4)
 seqs = [[synth.frame(20261018 + s, t, 1920, 1080) for t in range(LEN)] for s in range(NSEQ)]
 kw = dict(max_tracks=2000, min_tracks=818)
 trk = ctx.tracker(**kw)
@@ -76,9 +77,32 @@ n_tr = trk.totals()[0]
 out["tracker_one_sequence_1080p"] = {"frames": LEN, "s": one, "steps_per_s": (LEN - 1) / one, "feature_tracks_per_s": n_tr / one}
 del trk
 t0 = time.perf_counter()
-res = sched.run_sequences(seqs, 0, kw, max_workers=NSEQ)
+res = sched.run_sequences(seqs, 0, kw, max_workers=NSEQ, lockstep=False)
 par = time.perf_counter() - t0
-out["C5_8_sequences_one_gpu"] = {"sequences": NSEQ, "frames_each": LEN, "s": par, "steps_per_s": NSEQ * (LEN - 1) / par,
+out["C5_8_sequences_threads"] = {"sequences": NSEQ, "frames_each": LEN, "s": par, "steps_per_s": NSEQ * (LEN - 1) / par,
                                  "speedup_vs_one_by_one": one * NSEQ / par}
+for nseq in (8, 32):
+    # frames of step t for all sequences, staged in PINNED host memory (pageable input is limited to ~8 GB/s by the driver's
+    # staging copy); the 32-sequence case reuses the 8 generated sequences four times
+    stack = ctx.pinned_empty((LEN, nseq, 1080, 1920), np.uint8)
+    for t in range(LEN):
+        for s in range(nseq):
+            stack[t, s] = seqs[s % NSEQ][t]
+    mt = ctx.multitracker(nseq, 1920, 1080, **kw)
+    for t in range(3):
+        mt.step(stack[t])
+    mt.close()
+    mt = ctx.multitracker(nseq, 1920, 1080, **kw)
+    mt.step(stack[0])
+    t0 = time.perf_counter()
+    for t in range(1, LEN):
+        mt.step(stack[t])
+    lock = time.perf_counter() - t0
+    out[f"C5_{nseq}_sequences_lockstep"] = {"sequences": nseq, "frames_each": LEN, "s": lock, "steps_per_s": nseq * (LEN - 1) / lock,
+                                            "feature_tracks_per_s": mt.totals()[0] / lock,
+                                            "speedup_vs_one_by_one": one * nseq / lock,
+                                            "h2d_gb_per_s": nseq * (LEN - 1) * 1920 * 1080 / lock / 1e9}
+    mt.close()
+    del stack
 ctx.close()
 print(json.dumps(out, indent=1))

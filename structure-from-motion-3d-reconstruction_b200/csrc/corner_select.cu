@@ -866,7 +866,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) select_kernel(CornerWorkView w
                                                                double2* __restrict__ out_xy, int* __restrict__ out_n) {
   extern __shared__ __align__(16) unsigned char sel_raw[];
   SelSmem& sm = *reinterpret_cast<SelSmem*>(sel_raw);
-  const int fr = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fr = blockIdx.x, tid = threadIdx.x;
   const size_t cb = (size_t)fr * wv.cand_cap;
   sfm_key_t* key = wv.key + cb;
   uint32_t* idx = wv.idx + cb;

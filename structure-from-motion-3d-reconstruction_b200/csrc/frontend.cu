@@ -620,6 +620,38 @@ int tracker_detect(sfmgpu_ctx* ctx, sfmgpu_tracker* t, sfmgpu_frames* f, int fra
                            ctx->cs_work.cap, out, d_n);
 }
 
+// Replenish one track list (:374-389): detect need*3 corners on the current frame, drop those within min_distance of a live
+// track, append survivors with consecutive ids until max_tracks (tested after the append: at least one is added).
+int replenish_row(sfmgpu_ctx* ctx, const sfmgpu_lkcfg& cfg, sfmgpu_frames* f, int frame, double2* trk, int* ids, int* n_io, int* next_id_io,
+                  double2* fresh, int fresh_cap, uint8_t* ok, int* scal) {
+  const int need = cfg.max_tracks - *n_io;
+  long long want = (long long)need * 3;
+  if (want > fresh_cap) want = fresh_cap;  // fresh_cap = 3*max_tracks >= need*3
+  const int cand_cap = f->w * f->h;        // single frame: always room for the worst case
+  const int md = cfg.min_distance < 0 ? -cfg.min_distance : cfg.min_distance;
+  SFM_TRY(sfm_reserve(ctx, ctx->cs_work, sfm_corner_work_bytes_md(f->w, f->h, 1, cand_cap, md)));
+  SFM_TRY(sfm_corners_batch(ctx, f, frame, 1, (int)want, cfg.quality, cfg.min_distance, cand_cap, ctx->cs_work.p, ctx->cs_work.cap, fresh,
+                            scal + 1));
+  int nf = 0;
+  SFM_CUDA(ctx, cudaMemcpyAsync(&nf, scal + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (nf < 0) return sfm_fail(ctx, SFMGPU_E_CAPACITY, "tracker: candidate capacity exceeded");
+  if (nf > 0) {
+    const double d2 = (double)cfg.min_distance * cfg.min_distance;
+    SFM_LAUNCH(ctx, replenish_filter_kernel, sfm_cdiv(nf, 256), 256, 0, fresh, (const int*)(scal + 1), trk, *n_io, d2, ok);
+    // the reference appends first and tests the cap afterwards (:386-387): at least one corner is added
+    int room = cfg.max_tracks - *n_io;
+    if (room < 1) room = 1;
+    SFM_LAUNCH(ctx, replenish_append_kernel, 1, 1024, 0, fresh, (const int*)(scal + 1), ok, trk, ids, *n_io, room, *next_id_io, scal + 2);
+    int na = 0;
+    SFM_CUDA(ctx, cudaMemcpyAsync(&na, scal + 2, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_io += na;
+    *next_id_io += na;
+  }
+  return 0;
+}
+
 int tracker_reset_on(sfmgpu_ctx* ctx, sfmgpu_tracker* t, sfmgpu_frames* f, int frame) {
   // reset(gray) :327-332: prev_ = gray; tracks_ = shi_tomasi(...) with ids next_id_++
   SFM_TRY(tracker_detect(ctx, t, f, frame, t->cfg.max_tracks, t->trk, t->scal + 1));
@@ -680,31 +712,8 @@ int tracker_step_on(sfmgpu_ctx* ctx, sfmgpu_tracker* t, sfmgpu_frames* f, int fr
   t->prev_index = frame;
   if (n_out) *n_out = nk;
   // replenish (:374-389)
-  if (t->n < t->cfg.min_tracks) {
-    const int need = t->cfg.max_tracks - t->n;
-    long long want = (long long)need * 3;
-    if (want > t->fresh_cap) want = t->fresh_cap;  // fresh_cap = 3*max_tracks >= need*3
-    SFM_TRY(tracker_detect(ctx, t, f, frame, (int)want, t->fresh, t->scal + 1));
-    int nf = 0;
-    SFM_CUDA(ctx, cudaMemcpyAsync(&nf, t->scal + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (nf < 0) return sfm_fail(ctx, SFMGPU_E_CAPACITY, "tracker: candidate capacity exceeded");
-    if (nf > 0) {
-      const double d2 = (double)t->cfg.min_distance * t->cfg.min_distance;
-      SFM_LAUNCH(ctx, replenish_filter_kernel, sfm_cdiv(nf, 256), 256, 0, t->fresh, (const int*)(t->scal + 1), t->trk, t->n, d2,
-                 t->ok);
-      // the reference appends first and tests the cap afterwards (:386-387): at least one corner is added
-      int room = t->cfg.max_tracks - t->n;
-      if (room < 1) room = 1;
-      SFM_LAUNCH(ctx, replenish_append_kernel, 1, 1024, 0, t->fresh, (const int*)(t->scal + 1), t->ok, t->trk, t->ids, t->n, room,
-                 t->next_id, t->scal + 2);
-      int na = 0;
-      SFM_CUDA(ctx, cudaMemcpyAsync(&na, t->scal + 2, 4, cudaMemcpyDeviceToHost, ctx->stream));
-      SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      t->n += na;
-      t->next_id += na;
-    }
-  }
+  if (t->n < t->cfg.min_tracks)
+    SFM_TRY(replenish_row(ctx, t->cfg, f, frame, t->trk, t->ids, &t->n, &t->next_id, t->fresh, t->fresh_cap, t->ok, t->scal));
   return 0;
 }
 
@@ -807,6 +816,198 @@ int sfmgpu_tracker_tracks(sfmgpu_ctx* ctx, sfmgpu_tracker* t, double* xy, int32_
 }
 
 int sfmgpu_tracker_totals(sfmgpu_ctx* ctx, sfmgpu_tracker* t, long long* n_track_steps, long long* n_lk_iters) {
+  if (!ctx || !t) return SFMGPU_E_ARG;
+  unsigned long long tt[4];
+  SFM_CUDA(ctx, cudaMemcpyAsync(tt, t->tot, sizeof tt, cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n_track_steps) *n_track_steps = t->track_steps;
+  if (n_lk_iters) *n_lk_iters = (long long)tt[2];
+  return 0;
+}
+
+}  // extern "C"
+
+// ---- lock-step tracker over S independent sequences (BASELINE.json C5: several sequences per GPU) -------------------------------
+// The same KLTTracker semantics per sequence (:323-391), but ONE batched launch per stage and step for all of them: frame t of
+// every sequence arrives together, the S x max_tracks feature-tracks share a KLT launch (large enough for the lane-per-feature
+// kernels), survivors are compacted per sequence.  Results are identical to S separate sfmgpu_tracker objects.  Replenishment
+// (rare: a track list below min_tracks) is done sequence by sequence with the single-tracker code.
+struct sfmgpu_multitracker {
+  sfmgpu_lkcfg cfg;
+  int S = 0, w = 0, h = 0, cap = 0, fresh_cap = 0;
+  sfmgpu_frames* frames = nullptr;  // 2*S slots: parity p of sequence s lives in slot p*S + s
+  int parity = -1;                  // slot parity of the previous frames, -1: nothing tracked yet
+  std::vector<int> n, next_id;      // host copies
+  double2 *trk = nullptr, *p1 = nullptr, *pb = nullptr, *oa = nullptr, *ob = nullptr, *fresh = nullptr;
+  int *ids = nullptr, *oid = nullptr, *nit = nullptr, *dn = nullptr, *dnk = nullptr, *scal = nullptr;
+  uint8_t *keep = nullptr, *ok = nullptr;
+  long long track_steps = 0;
+  unsigned long long* tot = nullptr;
+};
+
+namespace {
+
+// after a batched detection: row s of the track list = the first n[s] corners with ids next_id[s]..
+__global__ void multi_take_corners_kernel(const double2* __restrict__ fresh, int fresh_stride, const int* __restrict__ n,
+                                          const int* __restrict__ next_id, double2* __restrict__ trk, int* __restrict__ ids, int cap) {
+  const int s = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n[s] || i >= cap) return;
+  trk[(size_t)s * cap + i] = fresh[(size_t)s * fresh_stride + i];
+  ids[(size_t)s * cap + i] = next_id[s] + i;
+}
+
+int multi_reset(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, int par) {
+  const int S = t->S, mc = t->cfg.max_tracks, cap_out = mc < 1 ? 1 : mc;
+  const int cand_cap = t->w * t->h;
+  const int md = t->cfg.min_distance < 0 ? -t->cfg.min_distance : t->cfg.min_distance;
+  SFM_TRY(sfm_reserve(ctx, ctx->cs_work, sfm_corner_work_bytes_md(t->w, t->h, S, cand_cap, md)));
+  SFM_TRY(sfm_corners_batch(ctx, t->frames, par * S, S, mc, t->cfg.quality, t->cfg.min_distance, cand_cap, ctx->cs_work.p,
+                            ctx->cs_work.cap, t->fresh, t->dn));
+  SFM_CUDA(ctx, cudaMemcpyAsync(t->n.data(), t->dn, (size_t)S * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(ctx, cudaMemcpyAsync(t->dnk, t->next_id.data(), (size_t)S * 4, cudaMemcpyHostToDevice, ctx->stream));
+  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int s = 0; s < S; s++)
+    if (t->n[s] < 0) return sfm_fail(ctx, SFMGPU_E_CAPACITY, "multitracker: candidate capacity exceeded (sequence %d)", s);
+  SFM_LAUNCH(ctx, multi_take_corners_kernel, dim3(sfm_cdiv(cap_out, 256), S), 256, 0, t->fresh, cap_out, (const int*)t->dn,
+             (const int*)t->dnk, t->trk, t->ids, t->cap);
+  for (int s = 0; s < S; s++) t->next_id[s] += t->n[s];
+  t->parity = par;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sfmgpu_multitracker_create(sfmgpu_ctx* ctx, const sfmgpu_lkcfg* cfg, int n_sequences, int w, int h, sfmgpu_multitracker** out) {
+  if (!ctx || !cfg || !out) return SFMGPU_E_ARG;
+  if (n_sequences < 1 || n_sequences > 512 || w < 1 || h < 1 || cfg->pyr_levels < 1 || cfg->pyr_levels > SFM_MAXL ||
+      cfg->max_tracks > (1 << 24))
+    return sfm_fail(ctx, SFMGPU_E_ARG, "multitracker_create: bad configuration");
+  sfmgpu_multitracker* t = new sfmgpu_multitracker();
+  t->cfg = *cfg;
+  t->S = n_sequences;
+  t->w = w;
+  t->h = h;
+  t->cap = (cfg->max_tracks < 1 ? 1 : cfg->max_tracks) + 1;  // one overshoot entry from replenish, as in sfmgpu_tracker
+  t->fresh_cap = 3 * (cfg->max_tracks < 1 ? 1 : cfg->max_tracks);
+  t->n.assign(n_sequences, 0);
+  t->next_id.assign(n_sequences, 0);
+  int rc = sfmgpu_frames_create(ctx, w, h, 2 * n_sequences, cfg->pyr_levels, &t->frames);
+  if (rc != 0) {
+    delete t;
+    return rc;
+  }
+  cudaError_t e = cudaSuccess;
+  auto al = [&](void** q, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(q, bytes + 256);
+  };
+  const size_t n = (size_t)t->cap * n_sequences;
+  al((void**)&t->trk, n * 16);
+  al((void**)&t->p1, n * 16);
+  al((void**)&t->pb, n * 16);
+  al((void**)&t->oa, n * 16);
+  al((void**)&t->ob, n * 16);
+  al((void**)&t->ids, n * 4);
+  al((void**)&t->oid, n * 4);
+  al((void**)&t->nit, n * 4);
+  al((void**)&t->keep, n);
+  al((void**)&t->fresh, (size_t)t->fresh_cap * 16 * n_sequences);
+  al((void**)&t->ok, (size_t)t->fresh_cap);
+  al((void**)&t->dn, (size_t)n_sequences * 4);
+  al((void**)&t->dnk, (size_t)n_sequences * 4);
+  al((void**)&t->scal, 64);
+  al((void**)&t->tot, 64);
+  if (e == cudaSuccess) e = cudaMemsetAsync(t->tot, 0, 64, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(t->scal, 0, 64, ctx->stream);
+  if (e != cudaSuccess) {
+    sfmgpu_multitracker_destroy(ctx, t);
+    return sfm_fail(ctx, SFMGPU_E_CUDA, "multitracker_create: CUDA allocation failed: %s", cudaGetErrorString(e));
+  }
+  *out = t;
+  return 0;
+}
+
+void sfmgpu_multitracker_destroy(sfmgpu_ctx* ctx, sfmgpu_multitracker* t) {
+  if (!t) return;
+  if (ctx) cudaStreamSynchronize(ctx->stream);
+  void* ptrs[] = {t->trk, t->p1, t->pb, t->oa, t->ob, t->ids, t->oid, t->nit, t->keep, t->fresh, t->ok, t->dn, t->dnk, t->scal, t->tot};
+  for (void* q : ptrs)
+    if (q) cudaFree(q);
+  if (t->frames) sfmgpu_frames_destroy(ctx, t->frames);
+  delete t;
+}
+
+int sfmgpu_multitracker_step(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, const uint8_t* host_pix, double* prev_xy, double* cur_xy,
+                             int32_t* ids, int32_t* n_out) {
+  if (!ctx || !t || !host_pix) return SFMGPU_E_ARG;
+  const int S = t->S, cap = t->cap;
+  const int par = t->parity == 0 ? 1 : 0;
+  SFM_TRY(sfmgpu_frames_upload(ctx, t->frames, par * S, S, host_pix));
+  SFM_TRY(sfmgpu_pyramid_build(ctx, t->frames, par * S, S));
+  if (n_out)
+    for (int s = 0; s < S; s++) n_out[s] = 0;
+  if (t->parity < 0) return multi_reset(ctx, t, par);  // first frames: reset every sequence (:341-344)
+  bool any_empty = false;
+  for (int s = 0; s < S; s++) any_empty = any_empty || t->n[s] == 0;
+  if (any_empty) return sfm_fail(ctx, SFMGPU_E_STATE, "multitracker: a sequence lost all its tracks (use sfmgpu_tracker for it)");
+  SFM_CUDA(ctx, cudaMemcpyAsync(t->dn, t->n.data(), (size_t)S * 4, cudaMemcpyHostToDevice, ctx->stream));
+  KltLaunch k;
+  k.pv = t->frames->view();
+  k.p0 = t->trk;
+  k.counts = t->dn;
+  k.npairs = S;
+  k.cap = cap;
+  k.fa0 = t->parity * S;
+  k.fa_step = 1;
+  k.fb0 = par * S;
+  k.fb_step = 1;
+  k.radius = t->cfg.win_radius;
+  k.iters = t->cfg.iters;
+  k.fb_thresh = t->cfg.fb_thresh;
+  k.p1 = t->p1;
+  k.pb = t->pb;
+  k.nit = t->nit;
+  k.keep = t->keep;
+  SFM_TRY(sfm_klt_launch(ctx, k));
+  for (int s = 0; s < S; s++) t->track_steps += t->n[s];
+  // survivors per sequence in track order: (p0, p1, id) (:364-371); LK iterations into the totals
+  SFM_LAUNCH(ctx, compact_kernel, S, 1024, 0, t->trk, t->p1, t->keep, (const int*)t->ids, (const int*)t->dn, cap, t->oa, t->ob, t->oid,
+             t->dnk);
+  SFM_LAUNCH(ctx, totals_kernel, 64, 256, 0, (const int*)t->dn, (const int*)t->dnk, (const int*)t->nit, S, cap, t->tot);
+  SFM_CUDA(ctx, cudaMemcpyAsync(t->n.data(), t->dnk, (size_t)S * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  const size_t rows = (size_t)S * cap;
+  if (prev_xy) SFM_CUDA(ctx, cudaMemcpyAsync(prev_xy, t->oa, rows * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cur_xy) SFM_CUDA(ctx, cudaMemcpyAsync(cur_xy, t->ob, rows * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ids) SFM_CUDA(ctx, cudaMemcpyAsync(ids, t->oid, rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(ctx, cudaMemcpyAsync(t->trk, t->ob, rows * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+  SFM_CUDA(ctx, cudaMemcpyAsync(t->ids, t->oid, rows * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  t->parity = par;
+  if (n_out)
+    for (int s = 0; s < S; s++) n_out[s] = t->n[s];
+  for (int s = 0; s < S; s++)
+    if (t->n[s] < t->cfg.min_tracks)
+      SFM_TRY(replenish_row(ctx, t->cfg, t->frames, par * S + s, t->trk + (size_t)s * cap, t->ids + (size_t)s * cap, &t->n[s],
+                            &t->next_id[s], t->fresh, t->fresh_cap, t->ok, t->scal));
+  return 0;
+}
+
+int sfmgpu_multitracker_tracks(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, int sequence, double* xy, int32_t* ids, int cap, int* n_out) {
+  if (!ctx || !t) return SFMGPU_E_ARG;
+  if (sequence < 0 || sequence >= t->S) return sfm_fail(ctx, SFMGPU_E_ARG, "multitracker_tracks: bad sequence index");
+  const int n = t->n[sequence];
+  if (n_out) *n_out = n;
+  if (n > cap) return sfm_fail(ctx, SFMGPU_E_CAPACITY, "multitracker_tracks: %d tracks, room for %d", n, cap);
+  if (n > 0) {
+    if (xy) SFM_CUDA(ctx, cudaMemcpyAsync(xy, t->trk + (size_t)sequence * t->cap, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ids) SFM_CUDA(ctx, cudaMemcpyAsync(ids, t->ids + (size_t)sequence * t->cap, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return 0;
+}
+
+int sfmgpu_multitracker_totals(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, long long* n_track_steps, long long* n_lk_iters) {
   if (!ctx || !t) return SFMGPU_E_ARG;
   unsigned long long tt[4];
   SFM_CUDA(ctx, cudaMemcpyAsync(tt, t->tot, sizeof tt, cudaMemcpyDeviceToHost, ctx->stream));

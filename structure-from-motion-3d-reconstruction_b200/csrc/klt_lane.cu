@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(32 * LWARPS, MINB) klt_lane_kernel(KltLaunch k
 // Lanes of a warp advance independently (level, iteration): a lane iterates while its matrices are valid and waits when
 // it needs new ones; when every unfinished lane waits, all of them stage their tiles and build together.
 constexpr int QM = 50;                         // doubles per lane: XX, YY, XY, XE, YE x 10 upper-triangle entries
-constexpr int QSTRIDE = QM * 8;                // 400 B = 25 x 16 B: LDS.128 conflict free across a quarter warp
+static_assert(QM * 8 <= 2 * LIMG, "the matrices alias the lane's tile");
 
 // Scalar type of the build: int32 (IMAD) or FP32 on integer-valued floats (FFMA, exact below 2^24: the largest entry is a
 // sum of 2 x 121 products of magnitude <= 65,025 = 15.7e6).

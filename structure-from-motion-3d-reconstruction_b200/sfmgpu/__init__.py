@@ -30,6 +30,8 @@ SYMBOLS = [
     "sfmgpu_klt_track", "sfmgpu_klt_set_mode", "sfmgpu_select_set_mode", "sfmgpu_pairs_create", "sfmgpu_pairs_destroy", "sfmgpu_pair_frontend", "sfmgpu_pipeline_set", "sfmgpu_pair_frontend_host", "sfmgpu_pairs_totals",
     "sfmgpu_pairs_download", "sfmgpu_pairs_download_all", "sfmgpu_pairs_device_ptrs", "sfmgpu_tracker_create", "sfmgpu_tracker_destroy", "sfmgpu_tracker_reset",
     "sfmgpu_tracker_step", "sfmgpu_tracker_step_frames", "sfmgpu_tracker_tracks", "sfmgpu_tracker_totals",
+    "sfmgpu_multitracker_create", "sfmgpu_multitracker_destroy", "sfmgpu_multitracker_step", "sfmgpu_multitracker_tracks",
+    "sfmgpu_multitracker_totals",
     "sfmgpu_ransac_score", "sfmgpu_ransac_upload", "sfmgpu_ransac_score_resident", "sfmgpu_ransac_download",
     "sfmgpu_ransac_hypotheses", "sfmgpu_global_desc32", "sfmgpu_desc_search", "sfmgpu_triangulate_dlt",
 ]
@@ -113,6 +115,11 @@ def load_library():
         "sfmgpu_tracker_step_frames": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, C.POINTER(_i)]),
         "sfmgpu_tracker_tracks": (_i, [_vp, _vp, _f64p, _i32p, _i, C.POINTER(_i)]),
         "sfmgpu_tracker_totals": (_i, [_vp, _vp, C.POINTER(_ll), C.POINTER(_ll)]),
+        "sfmgpu_multitracker_create": (_i, [_vp, C.POINTER(LKCfg), _i, _i, _i, C.POINTER(_vp)]),
+        "sfmgpu_multitracker_destroy": (None, [_vp, _vp]),
+        "sfmgpu_multitracker_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+        "sfmgpu_multitracker_tracks": (_i, [_vp, _vp, _i, _vp, _vp, _i, C.POINTER(_i)]),
+        "sfmgpu_multitracker_totals": (_i, [_vp, _vp, C.POINTER(_ll), C.POINTER(_ll)]),
         "sfmgpu_ransac_score": (_i, [_vp, _f64p, _f64p, _i, _f64p, _i, _d, _vp, C.POINTER(_i), _vp, C.POINTER(_i)]),
         "sfmgpu_ransac_upload": (_i, [_vp, _f64p, _f64p, _i, _f64p, _i]),
         "sfmgpu_ransac_score_resident": (_i, [_vp, _d, C.POINTER(_i), C.POINTER(_i)]),
@@ -293,6 +300,9 @@ class Context:
     def tracker(self, cfg=None, **kw):
         return Tracker(self, cfg if cfg is not None else lkcfg(**kw))
 
+    def multitracker(self, n_sequences, w, h, cfg=None, **kw):
+        return MultiTracker(self, n_sequences, w, h, cfg if cfg is not None else lkcfg(**kw))
+
 
 class Frames:
     """sfmgpu_frames: F images of one size with their pyramids, resident in HBM."""
@@ -439,6 +449,55 @@ class Pairs:
         nk, nc = _i(0), _i(0)
         self.ctx._ck(self.ctx.lib.sfmgpu_pairs_download(self.ctx.h, self.h_, pair, li, lj, self.cap, C.byref(nk), C.byref(nc)))
         return li[:nk.value].copy(), lj[:nk.value].copy(), nc.value
+
+
+class MultiTracker:
+    """sfmgpu_multitracker: S KLTTracker twins advanced in lock step (one batched launch per stage and step)."""
+
+    def __init__(self, ctx, n_sequences, w, h, cfg):
+        self.ctx, self.cfg, self.S, self.w, self.h = ctx, cfg, n_sequences, w, h
+        p = _vp()
+        ctx._ck(ctx.lib.sfmgpu_multitracker_create(ctx.h, C.byref(cfg), n_sequences, w, h, C.byref(p)))
+        self.h_ = p
+        self.cap = max(1, cfg.max_tracks) + 1
+        self.prev = ctx.pinned_empty((n_sequences, self.cap, 2), np.float64)
+        self.cur = ctx.pinned_empty((n_sequences, self.cap, 2), np.float64)
+        self.ids = ctx.pinned_empty((n_sequences, self.cap), np.int32)
+        self.n = np.zeros(n_sequences, np.int32)
+
+    def close(self):
+        if getattr(self, "h_", None) and self.ctx.h:
+            self.ctx.lib.sfmgpu_multitracker_destroy(self.ctx.h, self.h_)
+        self.h_ = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def step(self, imgs, fetch=True):
+        """imgs: [S, h, w] uint8, the next frame of every sequence.  Returns per sequence (prev_xy, cur_xy, ids) of the
+        survivors (copies), or the survivor counts when fetch is False."""
+        imgs = np.ascontiguousarray(imgs, np.uint8)
+        assert imgs.shape == (self.S, self.h, self.w)
+        a = (self.prev, self.cur, self.ids) if fetch else (None, None, None)
+        self.ctx._ck(self.ctx.lib.sfmgpu_multitracker_step(self.ctx.h, self.h_, imgs.ctypes.data_as(_vp), _ptr(a[0]), _ptr(a[1]), _ptr(a[2]),
+                                                           self.n.ctypes.data_as(_vp)))
+        if not fetch:
+            return self.n.copy()
+        return [(self.prev[s, :self.n[s]].copy(), self.cur[s, :self.n[s]].copy(), self.ids[s, :self.n[s]].copy()) for s in range(self.S)]
+
+    def tracks(self, s):
+        xy, ids = np.zeros((self.cap, 2)), np.zeros(self.cap, np.int32)
+        n = _i(0)
+        self.ctx._ck(self.ctx.lib.sfmgpu_multitracker_tracks(self.ctx.h, self.h_, s, _ptr(xy), _ptr(ids), self.cap, C.byref(n)))
+        return xy[:n.value].copy(), ids[:n.value].copy()
+
+    def totals(self):
+        a, b = _ll(0), _ll(0)
+        self.ctx._ck(self.ctx.lib.sfmgpu_multitracker_totals(self.ctx.h, self.h_, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
 
 class Tracker:

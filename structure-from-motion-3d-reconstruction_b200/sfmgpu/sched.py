@@ -71,14 +71,33 @@ def gather_pair_results(n_kept, li, lj, dst=0):
     return counts, li_list, lj_list
 
 
-def run_sequences(sequences, device=0, lkcfg_kw=None, max_workers=8):
-    """Sequence mode on ONE GPU (BASELINE.json config C5: several independent sequences per GPU): every sequence gets
-    its own context (= its own CUDA stream) and its own stateful tracker, stepped from its own host thread (ctypes
-    releases the GIL, so the trackers' kernels and copies overlap).  `sequences` is a list of iterables of uint8 frames;
-    returns per sequence the list of StepOut tuples (prev_xy, cur_xy, ids), identical to running them one by one."""
-    from concurrent.futures import ThreadPoolExecutor
+def run_sequences(sequences, device=0, lkcfg_kw=None, max_workers=8, lockstep=True):
+    """Sequence mode on ONE GPU (BASELINE.json config C5: several independent sequences per GPU).  `sequences` is a list of
+    lists of uint8 frames; returns per sequence the list of StepOut tuples (prev_xy, cur_xy, ids), identical to running
+    them one by one.
+
+    lockstep (default, sequences of equal length and frame size): one sfmgpu_multitracker advances all sequences with ONE
+    batched launch per stage and step.  Otherwise every sequence gets its own context (= its own CUDA stream) and tracker,
+    stepped from its own host thread (ctypes releases the GIL) - measured SLOWER than one by one on a B200 (driver-lock
+    contention of many small launches), kept for ragged inputs."""
+    import numpy as np
     import sfmgpu
     lkcfg_kw = lkcfg_kw or {}
+    same = len(sequences) > 0 and len({(len(q), q[0].shape if len(q) else None) for q in sequences}) == 1
+    if lockstep and same and len(sequences[0]) > 0:
+        ctx = sfmgpu.Context(device)
+        h, w = sequences[0][0].shape
+        mt = ctx.multitracker(len(sequences), w, h, **lkcfg_kw)
+        out = [[] for _ in sequences]
+        for t in range(len(sequences[0])):
+            got = mt.step(np.stack([q[t] for q in sequences]))
+            for s in range(len(sequences)):
+                out[s].append(got[s])
+        mt.close()
+        ctx.close()
+        return out
+
+    from concurrent.futures import ThreadPoolExecutor
 
     def one(seq):
         ctx = sfmgpu.Context(device)

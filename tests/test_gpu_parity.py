@@ -269,19 +269,43 @@ def test_tracker_resident_frames_equals_host_fed(ctx):
             assert np.array_equal(x, y)
 
 
+def test_multitracker_equals_separate_trackers(ctx, checker):
+    """BASELINE.json config C5 in lock step: S sequences advanced by ONE batched launch per stage equal S separate
+    KLTTracker twins step by step (survivors, ids, track lists incl. replenishment), and the reference tracker."""
+    S, T = 5, 7
+    seqs = [[synth.frame(200 + s, t, W, H) for t in range(T)] for s in range(S)]
+    seqs[3] = [f >> 3 << 3 for f in seqs[3]]  # a sequence with many identical scores
+    kw = dict(max_tracks=150, min_tracks=140)  # replenishment triggers within a few frames
+    mt = ctx.multitracker(S, W, H, **kw)
+    singles = [ctx.tracker(**kw) for _ in range(S)]
+    ref = checker.tracker(**kw)
+    for t in range(T):
+        got = mt.step(np.stack([seqs[s][t] for s in range(S)]))
+        for s in range(S):
+            want = singles[s].step(seqs[s][t])
+            for a, b in zip(got[s], want):
+                assert np.array_equal(a, b), (t, s)
+            for a, b in zip(mt.tracks(s), singles[s].tracks()):
+                assert np.array_equal(a, b), (t, s)
+        r = ref.step(seqs[0][t])
+        assert np.array_equal(got[0][2], r[2]) and _klt_close(got[0][1], r[1]), t
+    assert mt.totals()[0] == sum(tr.totals()[0] for tr in singles)
+
+
 def test_c5_sequences_in_parallel(ctx):
     """BASELINE.json config C5 (several independent sequences per GPU): one context + tracker + host thread per
     sequence; the results equal the one-by-one run."""
     from sfmgpu import sched
     seqs = [[synth.frame(100 + s, t, W, H) for t in range(5)] for s in range(4)]
     kw = dict(max_tracks=150, min_tracks=120)
-    par = sched.run_sequences(seqs, 0, kw, max_workers=4)
+    par = sched.run_sequences(seqs, 0, kw, max_workers=4, lockstep=False)
+    lock = sched.run_sequences(seqs, 0, kw)
     for s, seq in enumerate(seqs):
         trk = ctx.tracker(**kw)
         for t, img in enumerate(seq):
             want = trk.step(img)
-            for a, b in zip(par[s][t], want):
-                assert np.array_equal(a, b), (s, t)
+            for a, b, c in zip(par[s][t], want, lock[s][t]):
+                assert np.array_equal(a, b) and np.array_equal(c, b), (s, t)
 
 
 # ---- RANSAC scoring ---------------------------------------------------------------------------------------------------
