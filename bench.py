@@ -354,6 +354,13 @@ def main():
                 h_nc[r].copy_(g_nc[r], non_blocking=True)
         torch.cuda.synchronize()
 
+    # the PCIe floor of the e2e step: the same frames, upload only
+    frames.upload_ptr(0, nfr, host.ctypes.data)
+    ctx.sync()
+    ctx.timer_start()
+    frames.upload_ptr(0, nfr, host.ctypes.data)
+    h2d_only_ms = ctx.timer_stop()
+
     e2e_steps = max(1, min(args.steps, 3))
     step_e2e()
     barrier()
@@ -443,7 +450,9 @@ def main():
             "data": "synthetic", "config": workload_cfg(world, nfr),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * (world if world == 1 else 1),
                     "gather": "none (1 GPU)" if world == 1 else f"NCCL gather of tracks + counts to rank 0, {world} ranks",
-                    "ms_per_step": e2e_ms, "steps": e2e_steps},
+                    "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "h2d_only_ms": h2d_only_ms, "h2d_only_gb_per_s": h2d / (h2d_only_ms * 1e-3) / 1e9,
+                    "note": "upload of the frames alone takes h2d_only_ms on rank 0: the end-to-end step is PCIe-bound"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": klt_kernels, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
