@@ -357,6 +357,10 @@ __global__ void __launch_bounds__(32 * LWARPS, MINB) klt_lane_kernel(KltLaunch k
 // accumulators per mixed family to stay below 2^24 and spills: 23.8 ms vs 16.1 ms; staging rounds of 8 / 16 features
 // instead of 4: 27 / 57 ms, spills again.)
 //
+// (Also tried: a quadratic-form variant for BORDER windows.  The out-of-bounds rule zeroes whole samples, so the mask
+// does not shift with the tap index and all 68 products per pixel must be accumulated directly: ~12 k instructions per
+// build, no faster than the FP64 masked walk of klt_lane_kernel<..., true> - 15.05 vs 14.96 ms for the stage.)
+//
 // Lanes of a warp advance independently (level, iteration): a lane iterates while its matrices are valid and waits when
 // it needs new ones; when every unfinished lane waits, all of them stage their tiles and build together.
 constexpr int QM = 50;                         // doubles per lane: XX, YY, XY, XE, YE x 10 upper-triangle entries
