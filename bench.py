@@ -100,6 +100,24 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_near_gpu(index):
+    """Pin this rank (and therefore its first-touch pinned allocations) to the CPUs NVML reports as local to its GPU: with
+    8 ranks uploading 2 GB per step each, remote-socket host memory is the first bottleneck.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {i * 64 + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def profile_metrics():
     """ncu-derived numbers of the committed captures (profiles/r1_metrics.json, C2 shape): static evidence, not re-measured."""
     p = os.path.join(ROOT, "profiles", "r1_metrics.json")
@@ -250,6 +268,7 @@ def main():
     import sfmgpu
 
     torch.cuda.set_device(local)
+    near_cpus = bind_near_gpu(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -340,12 +359,16 @@ def main():
             pairs.run_host(frames, host, cfg, li, lj, nk, nc, chunk=args.chunk)
             return
         # same streaming call (chunked H2D || pyramids + corners + KLT), results stay on the device for the NCCL gather
+        t_a = time.perf_counter()
         pairs.run_host(frames, host, cfg, None, None, None, None, chunk=args.chunk)
         ctx.sync()  # results are written on the library's streams; NCCL runs on torch's
+        t_b = time.perf_counter()
         dist.gather(v_nk, g_nk, dst=0)
         dist.gather(v_nc, g_nc, dst=0)
         dist.gather(v_li, g_li, dst=0)
         dist.gather(v_lj, g_lj, dst=0)
+        torch.cuda.synchronize()
+        t_c = time.perf_counter()
         if rank == 0:
             for r in range(world):
                 h_li[r].copy_(g_li[r], non_blocking=True)
@@ -353,7 +376,9 @@ def main():
                 h_nk[r].copy_(g_nk[r], non_blocking=True)
                 h_nc[r].copy_(g_nc[r], non_blocking=True)
         torch.cuda.synchronize()
+        e2e_parts.update(stream_call_ms=(t_b - t_a) * 1e3, nccl_gather_ms=(t_c - t_b) * 1e3, d2h_rank0_ms=(time.perf_counter() - t_c) * 1e3)
 
+    e2e_parts = {}
     # the PCIe floor of the e2e step: the same frames, upload only
     frames.upload_ptr(0, nfr, host.ctypes.data)
     ctx.sync()
@@ -450,6 +475,7 @@ def main():
             "data": "synthetic", "config": workload_cfg(world, nfr),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * (world if world == 1 else 1),
                     "gather": "none (1 GPU)" if world == 1 else f"NCCL gather of tracks + counts to rank 0, {world} ranks",
+                    "cpus_bound_near_gpu": near_cpus, "rank0_parts_ms": e2e_parts or None,
                     "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "h2d_only_ms": h2d_only_ms, "h2d_only_gb_per_s": h2d / (h2d_only_ms * 1e-3) / 1e9,
                     "note": "upload of the frames alone takes h2d_only_ms on rank 0: the end-to-end step is PCIe-bound"},
