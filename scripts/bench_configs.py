@@ -76,6 +76,19 @@ one = time.perf_counter() - t0
 n_tr = trk.totals()[0]
 out["tracker_one_sequence_1080p"] = {"frames": LEN, "s": one, "steps_per_s": (LEN - 1) / one, "feature_tracks_per_s": n_tr / one}
 del trk
+for mode in (1, 2):  # KLT kernel forced: 1 warp per feature, 2 lane per feature (quadratic forms)
+    ctx.klt_set_mode(mode)
+    trk = ctx.tracker(**kw)
+    for img in seqs[0][:3]:
+        trk.step(img)
+    trk.reset(seqs[0][0])
+    t0 = time.perf_counter()
+    for img in seqs[0][1:]:
+        trk.step(img)
+    dt = time.perf_counter() - t0
+    out[f"tracker_one_sequence_klt_mode_{mode}"] = {"steps_per_s": (LEN - 1) / dt}
+    del trk
+ctx.klt_set_mode(0)
 t0 = time.perf_counter()
 res = sched.run_sequences(seqs, 0, kw, max_workers=NSEQ, lockstep=False)
 par = time.perf_counter() - t0
