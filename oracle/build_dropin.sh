@@ -23,7 +23,7 @@ awk '
 ' "$SRC" > "$TMP/templering_sfm_dropin.cpp"
 CXXF="-std=c++20 -O3 -DNDEBUG -w -I$REF_DIR/cpp/include"
 g++ $CXXF "$SRC" -o "$HERE/_ref/templering_sfm_ref"
-g++ $CXXF -ffp-contract=off -DUSE_SFMGPU -I"$PKG/host" "$TMP/templering_sfm_dropin.cpp" -o "$HERE/_ref/templering_sfm_gpu" \
+g++ $CXXF -pthread -ffp-contract=off -DUSE_SFMGPU -I"$PKG/host" "$TMP/templering_sfm_dropin.cpp" -o "$HERE/_ref/templering_sfm_gpu" \
     -L"$PKG" -lsfmgpu -Wl,-rpath,'$ORIGIN/../../structure-from-motion-3d-reconstruction_b200'
 rm -rf "$TMP"
 echo "built $HERE/_ref/templering_sfm_ref and templering_sfm_gpu"

@@ -16,8 +16,10 @@
 // Errors: CUDA / library failures throw std::runtime_error (the reference's main catches std::exception at
 // :1913); two-view failure is std::nullopt; step() on the first frame returns empty vectors.  There is no CPU
 // fallback: without libsfmgpu.so and a GPU every call throws.
-// Threading: like the reference, single-threaded; one process-wide context (device SFMGPU_DEVICE, default 0).
+// Threading: like the reference, one calling thread and one process-wide context (device SFMGPU_DEVICE, default 0);
+// find_E_ransac spreads its independent 8-point solves over a few host threads (link with -pthread).
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <cstdlib>
@@ -26,6 +28,7 @@
 #include <random>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sfmgpu.h"
@@ -73,6 +76,15 @@ inline bool& device_solver_flag() {
   return on;
 }
 inline bool device_solver() { return device_solver_flag(); }
+// Host threads for the 8-point solves of find_E_ransac (SFMGPU_SOLVER_THREADS, default: the hardware's, at most 16).
+inline int solver_threads() {
+  static int n = [] {
+    const char* e = std::getenv("SFMGPU_SOLVER_THREADS");
+    int v = e && *e ? std::atoi(e) : (int)std::thread::hardware_concurrency();
+    return v < 1 ? 1 : (v > 16 ? 16 : v);
+  }();
+  return n;
+}
 inline void set_device_solver(bool on) { device_solver_flag() = on; }
 
 // Process-wide context.
@@ -377,10 +389,23 @@ static std::optional<RelPose> find_E_ransac(const Mat33& K, const std::vector<Ve
   std::vector<int> inl((size_t)n);
   int best_h = -1, best_n = 0;
   if (!device_solver()) {
-    int idx8[8];
-    for (int it = 0; it < H; it++) {
-      for (int k = 0; k < 8; k++) idx8[k] = uni(rng);
-      sfmgpu_host::eight_point_E(xi.data(), xj.data(), idx8, &E[9 * (size_t)it]);
+    // all octets first (the RNG stream is sequential), then the hypotheses: each solve is a pure function of its octet,
+    // so solving them on several host threads leaves every hypothesis bit-identical to the reference's
+    std::vector<int> idx((size_t)8 * H);
+    for (size_t k = 0; k < idx.size(); k++) idx[k] = uni(rng);
+    const int nthr = H >= 64 ? solver_threads() : 1;
+    auto solve = [&](int h0, int h1) {
+      for (int it = h0; it < h1; it++) sfmgpu_host::eight_point_E(xi.data(), xj.data(), &idx[8 * (size_t)it], &E[9 * (size_t)it]);
+    };
+    if (nthr <= 1) {
+      solve(0, H);
+    } else {
+      std::vector<std::thread> pool;
+      const int per = (H + nthr - 1) / nthr;
+      for (int t = 1; t < nthr; t++)
+        if (t * per < H) pool.emplace_back(solve, t * per, std::min(H, (t + 1) * per));
+      solve(0, std::min(H, per));
+      for (auto& th : pool) th.join();
     }
     // scoring loop (:667-676) on the GPU: exact counts, first hypothesis with the strictly largest count
     check(ctx, sfmgpu_ransac_score(ctx, xi.data(), xj.data(), n, E.data(), H, thr, nullptr, &best_h, inl.data(), &best_n),
