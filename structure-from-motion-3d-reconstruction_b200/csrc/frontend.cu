@@ -948,9 +948,9 @@ int sfmgpu_multitracker_step(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, const uint
   if (n_out)
     for (int s = 0; s < S; s++) n_out[s] = 0;
   if (t->parity < 0) return multi_reset(ctx, t, par);  // first frames: reset every sequence (:341-344)
-  bool any_empty = false;
-  for (int s = 0; s < S; s++) any_empty = any_empty || t->n[s] == 0;
-  if (any_empty) return sfm_fail(ctx, SFMGPU_E_STATE, "multitracker: a sequence lost all its tracks (use sfmgpu_tracker for it)");
+  std::vector<int> empties;  // sequences without tracks are reset on this frame instead of stepped (:341-344)
+  for (int s = 0; s < S; s++)
+    if (t->n[s] == 0) empties.push_back(s);
   SFM_CUDA(ctx, cudaMemcpyAsync(t->dn, t->n.data(), (size_t)S * 4, cudaMemcpyHostToDevice, ctx->stream));
   KltLaunch k;
   k.pv = t->frames->view();
@@ -986,10 +986,29 @@ int sfmgpu_multitracker_step(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, const uint
   t->parity = par;
   if (n_out)
     for (int s = 0; s < S; s++) n_out[s] = t->n[s];
-  for (int s = 0; s < S; s++)
-    if (t->n[s] < t->cfg.min_tracks)
+  for (int s : empties) {
+    // reset(gray): tracks_ = shi_tomasi(gray, max_tracks, ...) with ids next_id_++; the step returns nothing for it
+    const int cand_cap = t->w * t->h;
+    const int md = t->cfg.min_distance < 0 ? -t->cfg.min_distance : t->cfg.min_distance;
+    SFM_TRY(sfm_reserve(ctx, ctx->cs_work, sfm_corner_work_bytes_md(t->w, t->h, 1, cand_cap, md)));
+    SFM_TRY(sfm_corners_batch(ctx, t->frames, par * S + s, 1, t->cfg.max_tracks, t->cfg.quality, t->cfg.min_distance, cand_cap,
+                              ctx->cs_work.p, ctx->cs_work.cap, t->trk + (size_t)s * cap, t->scal + 1));
+    int n = 0;
+    SFM_CUDA(ctx, cudaMemcpyAsync(&n, t->scal + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n < 0) return sfm_fail(ctx, SFMGPU_E_CAPACITY, "multitracker: candidate capacity exceeded (sequence %d)", s);
+    if (n > 0) SFM_LAUNCH(ctx, iota_ids_kernel, sfm_cdiv(n, 256), 256, 0, t->ids + (size_t)s * cap, (const int*)(t->scal + 1), t->next_id[s]);
+    t->n[s] = n;
+    t->next_id[s] += n;
+    if (n_out) n_out[s] = 0;
+  }
+  for (int s = 0; s < S; s++) {
+    bool was_empty = false;
+    for (int e : empties) was_empty = was_empty || e == s;
+    if (!was_empty && t->n[s] < t->cfg.min_tracks)
       SFM_TRY(replenish_row(ctx, t->cfg, t->frames, par * S + s, t->trk + (size_t)s * cap, t->ids + (size_t)s * cap, &t->n[s],
                             &t->next_id[s], t->fresh, t->fresh_cap, t->ok, t->scal));
+  }
   return 0;
 }
 

@@ -292,6 +292,24 @@ def test_multitracker_equals_separate_trackers(ctx, checker):
     assert mt.totals()[0] == sum(tr.totals()[0] for tr in singles)
 
 
+def test_multitracker_total_track_loss(ctx):
+    """Every track fails the forward-backward test in every step (fb_thresh = -1): the track lists drop to zero and are
+    refilled by the replenish rule (:374-389) inside the same step, identically in the lock-step and the single tracker."""
+    S, T = 3, 5
+    seqs = [[synth.frame(300 + s, t, W, H) for t in range(T)] for s in range(S)]
+    kw = dict(max_tracks=120, min_tracks=100, fb_thresh=-1.0)  # fb >= -1 for every finite fb: every track is dropped each step
+    mt = ctx.multitracker(S, W, H, **kw)
+    singles = [ctx.tracker(**kw) for _ in range(S)]
+    for t in range(T):
+        got = mt.step(np.stack([seqs[s][t] for s in range(S)]))
+        for s in range(S):
+            want = singles[s].step(seqs[s][t])
+            for a, b in zip(got[s], want):
+                assert np.array_equal(a, b), (t, s)
+            for a, b in zip(mt.tracks(s), singles[s].tracks()):
+                assert np.array_equal(a, b), (t, s)
+
+
 def test_c5_sequences_in_parallel(ctx):
     """BASELINE.json config C5 (several independent sequences per GPU): one context + tracker + host thread per
     sequence; the results equal the one-by-one run."""
