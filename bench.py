@@ -539,7 +539,10 @@ def cpu_baseline(host_frames):
     t1 = time.perf_counter()
     chk.ransac_score_mt(xi, xj, E, 1e-3, threads)
     rs = Hs * RS_N / (time.perf_counter() - t1)
-    return {"value": tracks / dt, "unit": UNIT, "cores": threads, "kind": kind,
+    t2 = time.perf_counter()
+    one_tracks, _ = chk.pair_frontend_mt(sample[:2], MAX_CORNERS, 1)  # the reference is single-threaded: one pair on one core
+    one_core = one_tracks / (time.perf_counter() - t2)
+    return {"value": tracks / dt, "unit": UNIT, "cores": threads, "kind": kind, "one_core_value": one_core,
             "sample": f"first {threads} pairs of the same sequence, one per host thread ({tracks} feature-tracks in {dt:.2f} s wall)",
             "ransac_hyp_pts_per_s": rs}
 

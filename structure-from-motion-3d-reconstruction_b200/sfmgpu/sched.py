@@ -3,7 +3,9 @@
 The front end shards with NO data-path collective:
   * pair mode     — the stateless two-view unit (cpp/src/templering_sfm.cpp:1836-1857): pairs (t, t+1) are independent;
                     rank g owns a contiguous block of pairs plus one halo frame;
-  * sequence mode — whole sequences per rank (a KLTTracker chain cannot be split across frames, :370-371).
+  * sequence mode — whole sequences per rank (a KLTTracker chain cannot be split across frames, :370-371); several
+                    sequences per GPU advance in lock step (run_sequences -> sfmgpu_multitracker);
+  * segment mode  — contiguous segments of one sequence per rank, each restarting the tracker (segment_shard).
 The only communication is the gather of results (tracks, survivor counts, inlier sets) to rank 0: an all_gather of
 per-rank sizes followed by one padded gather (NCCL has no gatherv).  Works on NCCL (GPU tensors) and gloo (CPU tests).
 """
@@ -27,6 +29,13 @@ def pair_shard(n_frames, world, rank):
 
 def sequence_shard(n_sequences, world, rank):
     return shard_range(n_sequences, world, rank)
+
+
+def segment_shard(n_frames, world, rank):
+    """Segment mode: frames [f0, f1) of ONE long sequence for a tracker that starts with reset() on f0.
+    Equals the reference run on each segment separately (track ids restart per segment), NOT the unsegmented run: a
+    KLTTracker chain cannot be cut without changing its state (cpp/src/templering_sfm.cpp:364-371)."""
+    return shard_range(n_frames, world, rank)
 
 
 def _dev(t):
