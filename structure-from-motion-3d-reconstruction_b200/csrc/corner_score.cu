@@ -569,6 +569,13 @@ int sfm_corner_candidates_batch(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int fir
     SFM_LAUNCH(ctx, rescue_mark_kernel, sfm_cdiv(count, 256), 256, 0, wv, count);
     SFM_LAUNCH(ctx, score_rescue_kernel, dim3(ntx, nty, count < 2 ? count : 2), 256, sizeof(ScoreSmem), f->lvl[0], f->w, f->h,
                f->pitch[0], f->fstride[0], first, wv, quality);
+    static const bool trace = getenv("SFMGPU_TRACE_RESCUE") != nullptr;  // diagnostics only (synchronises)
+    if (trace) {
+      int nres = 0;
+      SFM_CUDA(ctx, cudaMemcpyAsync(&nres, wv.rescue_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      fprintf(stderr, "[score] %d of %d frames redone against the final threshold (provisional list overflow)\n", nres, count);
+    }
   } else {
     SFM_CUDA(ctx, cudaMemsetAsync(wv.exact_list, 1, sizeof(int) * count, ctx->stream));
     SFM_LAUNCH(ctx, score_tile_kernel<0>, grid, 256, sizeof(ScoreSmem), f->lvl[0], f->w, f->h, f->pitch[0], f->fstride[0], first, wv,
