@@ -187,6 +187,13 @@ void sfmgpu_multitracker_destroy(sfmgpu_ctx* ctx, sfmgpu_multitracker* t);
  * ids: [n_sequences][max(max_tracks,1)+1], n_out: [n_sequences] survivors per sequence (any output may be NULL). */
 int sfmgpu_multitracker_step(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, const uint8_t* host_pix, double* prev_xy, double* cur_xy,
                              int32_t* ids, int32_t* n_out);
+/* Pipelined form: next_host_pix (may be NULL) = the frames of the FOLLOWING step; they are uploaded and their pyramids built
+ * on a second stream while this step computes, and the next call passes host_pix = NULL to consume them.  Page-locked
+ * host memory (sfmgpu_host_alloc) is needed for the overlap.  sfmgpu_multitracker_prefetch primes the pipeline before
+ * the first step.  Results are identical to the plain step. */
+int sfmgpu_multitracker_prefetch(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, const uint8_t* host_pix);
+int sfmgpu_multitracker_step_pipelined(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, const uint8_t* host_pix, const uint8_t* next_host_pix,
+                                       double* prev_xy, double* cur_xy, int32_t* ids, int32_t* n_out);
 int sfmgpu_multitracker_tracks(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, int sequence, double* xy, int32_t* ids, int cap, int* n_out);
 int sfmgpu_multitracker_totals(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, long long* n_track_steps, long long* n_lk_iters);
 

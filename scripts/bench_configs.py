@@ -116,6 +116,16 @@ for nseq in (8, 32):
                                             "speedup_vs_one_by_one": one * nseq / lock,
                                             "h2d_gb_per_s": nseq * (LEN - 1) * 1920 * 1080 / lock / 1e9}
     mt.close()
+    mt = ctx.multitracker(nseq, 1920, 1080, **kw)
+    mt.prefetch(stack[0])
+    mt.step(None, next_imgs=stack[1])
+    t0 = time.perf_counter()
+    for t in range(1, LEN):
+        mt.step(None, next_imgs=stack[t + 1] if t + 1 < LEN else None)
+    piped = time.perf_counter() - t0
+    out[f"C5_{nseq}_sequences_lockstep"]["pipelined_steps_per_s"] = nseq * (LEN - 1) / piped
+    out[f"C5_{nseq}_sequences_lockstep"]["pipelined_feature_tracks_per_s"] = mt.totals()[0] / piped
+    mt.close()
     del stack
 ctx.close()
 print(json.dumps(out, indent=1))

@@ -835,8 +835,10 @@ int sfmgpu_tracker_totals(sfmgpu_ctx* ctx, sfmgpu_tracker* t, long long* n_track
 struct sfmgpu_multitracker {
   sfmgpu_lkcfg cfg;
   int S = 0, w = 0, h = 0, cap = 0, fresh_cap = 0;
-  sfmgpu_frames* frames = nullptr;  // 2*S slots: parity p of sequence s lives in slot p*S + s
-  int parity = -1;                  // slot parity of the previous frames, -1: nothing tracked yet
+  sfmgpu_frames* frames = nullptr;  // 3*S slots: group g of sequence s lives in slot g*S + s (previous / current / prefetched)
+  int parity = -1;                  // slot group of the previous frames, -1: nothing tracked yet
+  bool prefetched = false;          // group (parity+1)%3 holds the next frames (uploaded + pyramids), ready at pf_done
+  cudaEvent_t pf_done = nullptr;
   std::vector<int> n, next_id;      // host copies
   double2 *trk = nullptr, *p1 = nullptr, *pb = nullptr, *oa = nullptr, *ob = nullptr, *fresh = nullptr;
   int *ids = nullptr, *oid = nullptr, *nit = nullptr, *dn = nullptr, *dnk = nullptr, *scal = nullptr;
@@ -893,7 +895,7 @@ int sfmgpu_multitracker_create(sfmgpu_ctx* ctx, const sfmgpu_lkcfg* cfg, int n_s
   t->fresh_cap = 3 * (cfg->max_tracks < 1 ? 1 : cfg->max_tracks);
   t->n.assign(n_sequences, 0);
   t->next_id.assign(n_sequences, 0);
-  int rc = sfmgpu_frames_create(ctx, w, h, 2 * n_sequences, cfg->pyr_levels, &t->frames);
+  int rc = sfmgpu_frames_create(ctx, w, h, 3 * n_sequences, cfg->pyr_levels, &t->frames);
   if (rc != 0) {
     delete t;
     return rc;
@@ -935,16 +937,55 @@ void sfmgpu_multitracker_destroy(sfmgpu_ctx* ctx, sfmgpu_multitracker* t) {
   for (void* q : ptrs)
     if (q) cudaFree(q);
   if (t->frames) sfmgpu_frames_destroy(ctx, t->frames);
+  if (t->pf_done) cudaEventDestroy(t->pf_done);
   delete t;
+}
+
+// Upload + pyramids of the frames of a LATER step on the copy stream, into the slot group after `after_group`.
+static int multi_prefetch(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, int after_group, const uint8_t* host_pix) {
+  SFM_TRY(pipe_streams(ctx));
+  if (!t->pf_done && cudaEventCreateWithFlags(&t->pf_done, cudaEventDisableTiming) != cudaSuccess)
+    return sfm_fail(ctx, SFMGPU_E_CUDA, "multitracker: cudaEventCreate failed");
+  const int S = t->S, g = (after_group + 1) % 3;
+  sfmgpu_frames* f = t->frames;
+  SFM_CUDA(ctx, cudaMemcpy2DAsync(f->lvl[0] + (size_t)g * S * f->fstride[0], f->pitch[0], host_pix, f->w, f->w, (size_t)f->h * S,
+                                  cudaMemcpyHostToDevice, ctx->copy_stream));
+  {
+    StageScope sc(ctx, ctx->copy_stream);
+    SFM_TRY(sfmgpu_pyramid_build(ctx, f, g * S, S));
+    SFM_CUDA(ctx, cudaEventRecord(t->pf_done, ctx->stream));
+  }
+  t->prefetched = true;
+  return 0;
+}
+
+int sfmgpu_multitracker_prefetch(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, const uint8_t* host_pix) {
+  if (!ctx || !t || !host_pix) return SFMGPU_E_ARG;
+  if (t->prefetched) return sfm_fail(ctx, SFMGPU_E_STATE, "multitracker_prefetch: the prefetched frames have not been stepped yet");
+  return multi_prefetch(ctx, t, t->parity < 0 ? 2 : t->parity, host_pix);
 }
 
 int sfmgpu_multitracker_step(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, const uint8_t* host_pix, double* prev_xy, double* cur_xy,
                              int32_t* ids, int32_t* n_out) {
-  if (!ctx || !t || !host_pix) return SFMGPU_E_ARG;
+  return sfmgpu_multitracker_step_pipelined(ctx, t, host_pix, nullptr, prev_xy, cur_xy, ids, n_out);
+}
+
+int sfmgpu_multitracker_step_pipelined(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, const uint8_t* host_pix, const uint8_t* next_host_pix,
+                                       double* prev_xy, double* cur_xy, int32_t* ids, int32_t* n_out) {
+  if (!ctx || !t) return SFMGPU_E_ARG;
+  if (!host_pix && !t->prefetched) return sfm_fail(ctx, SFMGPU_E_STATE, "multitracker_step: no frames given and none prefetched");
+  if (host_pix && t->prefetched) return sfm_fail(ctx, SFMGPU_E_STATE, "multitracker_step: frames given but others are prefetched");
   const int S = t->S, cap = t->cap;
-  const int par = t->parity == 0 ? 1 : 0;
-  SFM_TRY(sfmgpu_frames_upload(ctx, t->frames, par * S, S, host_pix));
-  SFM_TRY(sfmgpu_pyramid_build(ctx, t->frames, par * S, S));
+  const int par = t->parity < 0 ? 0 : (t->parity + 1) % 3;
+  if (host_pix) {
+    SFM_TRY(sfmgpu_frames_upload(ctx, t->frames, par * S, S, host_pix));
+    SFM_TRY(sfmgpu_pyramid_build(ctx, t->frames, par * S, S));
+  } else {
+    SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, t->pf_done, 0));
+    t->prefetched = false;
+  }
+  // the frames of the NEXT step travel while this one computes (their slot group is neither previous nor current)
+  if (next_host_pix) SFM_TRY(multi_prefetch(ctx, t, par, next_host_pix));
   if (n_out)
     for (int s = 0; s < S; s++) n_out[s] = 0;
   if (t->parity < 0) return multi_reset(ctx, t, par);  // first frames: reset every sequence (:341-344)

@@ -31,6 +31,7 @@ SYMBOLS = [
     "sfmgpu_pairs_download", "sfmgpu_pairs_download_all", "sfmgpu_pairs_device_ptrs", "sfmgpu_tracker_create", "sfmgpu_tracker_destroy", "sfmgpu_tracker_reset",
     "sfmgpu_tracker_step", "sfmgpu_tracker_step_frames", "sfmgpu_tracker_tracks", "sfmgpu_tracker_totals",
     "sfmgpu_multitracker_create", "sfmgpu_multitracker_destroy", "sfmgpu_multitracker_step", "sfmgpu_multitracker_tracks",
+    "sfmgpu_multitracker_prefetch", "sfmgpu_multitracker_step_pipelined",
     "sfmgpu_multitracker_totals",
     "sfmgpu_ransac_score", "sfmgpu_ransac_upload", "sfmgpu_ransac_score_resident", "sfmgpu_ransac_download",
     "sfmgpu_ransac_hypotheses", "sfmgpu_global_desc32", "sfmgpu_desc_search", "sfmgpu_triangulate_dlt",
@@ -118,6 +119,8 @@ def load_library():
         "sfmgpu_multitracker_create": (_i, [_vp, C.POINTER(LKCfg), _i, _i, _i, C.POINTER(_vp)]),
         "sfmgpu_multitracker_destroy": (None, [_vp, _vp]),
         "sfmgpu_multitracker_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+        "sfmgpu_multitracker_prefetch": (_i, [_vp, _vp, _vp]),
+        "sfmgpu_multitracker_step_pipelined": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
         "sfmgpu_multitracker_tracks": (_i, [_vp, _vp, _i, _vp, _vp, _i, C.POINTER(_i)]),
         "sfmgpu_multitracker_totals": (_i, [_vp, _vp, C.POINTER(_ll), C.POINTER(_ll)]),
         "sfmgpu_ransac_score": (_i, [_vp, _f64p, _f64p, _i, _f64p, _i, _d, _vp, C.POINTER(_i), _vp, C.POINTER(_i)]),
@@ -476,14 +479,26 @@ class MultiTracker:
         except Exception:
             pass
 
-    def step(self, imgs, fetch=True):
-        """imgs: [S, h, w] uint8, the next frame of every sequence.  Returns per sequence (prev_xy, cur_xy, ids) of the
-        survivors (copies), or the survivor counts when fetch is False."""
+    def _frames(self, imgs):
+        if imgs is None:
+            return None
         imgs = np.ascontiguousarray(imgs, np.uint8)
         assert imgs.shape == (self.S, self.h, self.w)
+        return imgs
+
+    def prefetch(self, imgs):
+        """Start uploading the frames of the next step (page-locked memory for the overlap); step(None, ...) consumes them."""
+        self._pf = self._frames(imgs)  # keep the buffer alive while the copy runs
+        self.ctx._ck(self.ctx.lib.sfmgpu_multitracker_prefetch(self.ctx.h, self.h_, _ptr(self._pf)))
+
+    def step(self, imgs, fetch=True, next_imgs=None):
+        """imgs: [S, h, w] uint8, the next frame of every sequence (None: the prefetched ones); next_imgs: the frames of
+        the following step, uploaded while this one computes.  Returns per sequence (prev_xy, cur_xy, ids) of the
+        survivors (copies), or the survivor counts when fetch is False."""
+        imgs, self._pf = self._frames(imgs), self._frames(next_imgs)
         a = (self.prev, self.cur, self.ids) if fetch else (None, None, None)
-        self.ctx._ck(self.ctx.lib.sfmgpu_multitracker_step(self.ctx.h, self.h_, imgs.ctypes.data_as(_vp), _ptr(a[0]), _ptr(a[1]), _ptr(a[2]),
-                                                           self.n.ctypes.data_as(_vp)))
+        self.ctx._ck(self.ctx.lib.sfmgpu_multitracker_step_pipelined(self.ctx.h, self.h_, _ptr(imgs), _ptr(self._pf), _ptr(a[0]), _ptr(a[1]),
+                                                                     _ptr(a[2]), self.n.ctypes.data_as(_vp)))
         if not fetch:
             return self.n.copy()
         return [(self.prev[s, :self.n[s]].copy(), self.cur[s, :self.n[s]].copy(), self.ids[s, :self.n[s]].copy()) for s in range(self.S)]

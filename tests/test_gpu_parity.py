@@ -292,6 +292,28 @@ def test_multitracker_equals_separate_trackers(ctx, checker):
     assert mt.totals()[0] == sum(tr.totals()[0] for tr in singles)
 
 
+def test_multitracker_pipelined_equals_plain(ctx):
+    """Prefetching the next frames on the copy stream while a step computes does not change any result."""
+    S, T = 4, 8
+    kw = dict(max_tracks=150, min_tracks=140)
+    stack = ctx.pinned_empty((T, S, H, W), np.uint8)
+    for t in range(T):
+        for s in range(S):
+            stack[t, s] = synth.frame(400 + s, t, W, H)
+    plain, piped = ctx.multitracker(S, W, H, **kw), ctx.multitracker(S, W, H, **kw)
+    piped.prefetch(stack[0])
+    for t in range(T):
+        want = plain.step(stack[t])
+        got = piped.step(None, next_imgs=stack[t + 1] if t + 1 < T else None)
+        for s in range(S):
+            for a, b in zip(got[s], want[s]):
+                assert np.array_equal(a, b), (t, s)
+            for a, b in zip(piped.tracks(s), plain.tracks(s)):
+                assert np.array_equal(a, b), (t, s)
+    with pytest.raises(sfmgpu.SfmGpuError):
+        piped.step(None)  # nothing prefetched
+
+
 def test_multitracker_total_track_loss(ctx):
     """Every track fails the forward-backward test in every step (fb_thresh = -1): the track lists drop to zero and are
     refilled by the replenish rule (:374-389) inside the same step, identically in the lock-step and the single tracker."""
