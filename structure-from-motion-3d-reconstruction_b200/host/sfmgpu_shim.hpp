@@ -297,6 +297,75 @@ class KLTTracker {
   int cap_ = 0;
 };
 
+// S KLTTrackers advanced in lock step (no counterpart in the reference, which tracks one sequence: this is the C++ face of
+// sfmgpu_multitracker for callers with several independent sequences per GPU).  Per sequence the results equal a
+// KLTTracker's; all images must be w x h.
+class MultiKLTTracker {
+ public:
+  MultiKLTTracker(LKConfig cfg, int n_sequences, int w, int h) : S_(n_sequences), w_(w), h_(h) {
+    sfmgpu_lkcfg c;
+    c.max_tracks = cfg.max_tracks;
+    c.min_tracks = cfg.min_tracks;
+    c.quality = cfg.quality;
+    c.min_distance = cfg.min_distance;
+    c.pyr_levels = cfg.pyr_levels;
+    c.win_radius = cfg.win_radius;
+    c.iters = cfg.iters;
+    c.fb_thresh = cfg.fb_thresh;
+    sfmgpu_multitracker* t = nullptr;
+    auto* ctx = sfmgpu_shim::context();
+    sfmgpu_shim::check(ctx, sfmgpu_multitracker_create(ctx, &c, n_sequences, w, h, &t), "multitracker_create");
+    trk_ = std::shared_ptr<sfmgpu_multitracker>(t, [](sfmgpu_multitracker* p) { sfmgpu_multitracker_destroy(sfmgpu_shim::context(), p); });
+    cap_ = (cfg.max_tracks < 1 ? 1 : cfg.max_tracks) + 1;
+    void* pin = nullptr;  // page-locked staging for the S frames of a step
+    sfmgpu_shim::check(ctx, sfmgpu_host_alloc(ctx, (size_t)S_ * w * h, &pin), "host_alloc");
+    stage_ = std::shared_ptr<uint8_t>((uint8_t*)pin, [](uint8_t* p) { sfmgpu_host_free(sfmgpu_shim::context(), p); });
+  }
+
+  // frames[s] = the next frame of sequence s; returns one StepOut per sequence (empty on the first call)
+  std::vector<KLTTracker::StepOut> step(const std::vector<const GrayImage*>& frames) {
+    auto* ctx = sfmgpu_shim::context();
+    if ((int)frames.size() != S_) throw std::runtime_error("sfmgpu: MultiKLTTracker::step: one frame per sequence expected");
+    const size_t px = (size_t)w_ * h_;
+    for (int s = 0; s < S_; s++) {
+      if (!frames[s] || frames[s]->w != w_ || frames[s]->h != h_) throw std::runtime_error("sfmgpu: MultiKLTTracker::step: frame size differs");
+      std::copy(frames[s]->pix.begin(), frames[s]->pix.begin() + px, stage_.get() + (size_t)s * px);
+    }
+    std::vector<double> prev(2 * (size_t)S_ * cap_), cur(2 * (size_t)S_ * cap_);
+    std::vector<std::int32_t> ids((size_t)S_ * cap_), n((size_t)S_);
+    sfmgpu_shim::check(ctx, sfmgpu_multitracker_step(ctx, trk_.get(), stage_.get(), prev.data(), cur.data(), ids.data(), n.data()),
+                       "multitracker_step");
+    std::vector<KLTTracker::StepOut> out((size_t)S_);
+    for (int s = 0; s < S_; s++) {
+      const size_t o = (size_t)s * cap_;
+      out[s].prev_pts.resize((size_t)n[s]);
+      out[s].cur_pts.resize((size_t)n[s]);
+      out[s].ids.assign(ids.begin() + o, ids.begin() + o + n[s]);
+      for (int i = 0; i < n[s]; i++) {
+        out[s].prev_pts[i] = Vec2{prev[2 * (o + i)], prev[2 * (o + i) + 1]};
+        out[s].cur_pts[i] = Vec2{cur[2 * (o + i)], cur[2 * (o + i) + 1]};
+      }
+    }
+    return out;
+  }
+
+  std::vector<Track> tracks(int sequence) const {
+    auto* ctx = sfmgpu_shim::context();
+    std::vector<double> xy(2 * (size_t)cap_);
+    std::vector<std::int32_t> ids((size_t)cap_);
+    int n = 0;
+    sfmgpu_shim::check(ctx, sfmgpu_multitracker_tracks(ctx, trk_.get(), sequence, xy.data(), ids.data(), cap_, &n), "multitracker_tracks");
+    std::vector<Track> out((size_t)n);
+    for (int i = 0; i < n; i++) out[i] = Track{ids[i], Vec2{xy[2 * i], xy[2 * i + 1]}};
+    return out;
+  }
+
+ private:
+  int S_, w_, h_, cap_ = 0;
+  std::shared_ptr<sfmgpu_multitracker> trk_;
+  std::shared_ptr<uint8_t> stage_;
+};
+
 // ---- loop-closure descriptor (:1100-1129) -------------------------------------------------------------------------------
 static std::vector<float> global_desc_32(const GrayImage& im) {
   using namespace sfmgpu_shim;

@@ -111,6 +111,52 @@ void* shim_tracker_create(int max_tracks, int min_tracks, double quality, int mi
   }
 }
 void shim_tracker_destroy(void* t) { delete (KLTTracker*)t; }
+
+// MultiKLTTracker: pix = [n_sequences][h][w]; outputs [n_sequences][cap][2] / [n_sequences][cap] / [n_sequences]
+void* shim_multitracker_create(int n_sequences, int w, int h, int max_tracks, int min_tracks) {
+  try {
+    LKConfig c;
+    c.max_tracks = max_tracks;
+    c.min_tracks = min_tracks;
+    return new MultiKLTTracker(c, n_sequences, w, h);
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+void shim_multitracker_destroy(void* t) { delete (MultiKLTTracker*)t; }
+int shim_multitracker_step(void* t, const uint8_t* pix, int n_sequences, int w, int h, double* prev_xy, double* cur_xy, int* ids,
+                           int* n_out, int cap, double* tracks_xy, int* tracks_ids, int* tracks_n) {
+  return guarded([&] {
+    std::vector<GrayImage> imgs;
+    for (int s = 0; s < n_sequences; s++) imgs.push_back(wrap(pix + (size_t)s * w * h, w, h));
+    std::vector<const GrayImage*> ptrs;
+    for (auto& im : imgs) ptrs.push_back(&im);
+    auto* mt = (MultiKLTTracker*)t;
+    auto out = mt->step(ptrs);
+    for (int s = 0; s < n_sequences; s++) {
+      const int n = (int)out[s].ids.size();
+      n_out[s] = n;
+      for (int i = 0; i < n && i < cap; i++) {
+        const size_t o = (size_t)s * cap + i;
+        prev_xy[2 * o] = out[s].prev_pts[i].x;
+        prev_xy[2 * o + 1] = out[s].prev_pts[i].y;
+        cur_xy[2 * o] = out[s].cur_pts[i].x;
+        cur_xy[2 * o + 1] = out[s].cur_pts[i].y;
+        ids[o] = out[s].ids[i];
+      }
+      const auto tr = mt->tracks(s);
+      tracks_n[s] = (int)tr.size();
+      for (int i = 0; i < (int)tr.size() && i < cap; i++) {
+        const size_t o = (size_t)s * cap + i;
+        tracks_xy[2 * o] = tr[i].p.x;
+        tracks_xy[2 * o + 1] = tr[i].p.y;
+        tracks_ids[o] = tr[i].id;
+      }
+    }
+    return 0;
+  });
+}
 int shim_tracker_step(void* t, const uint8_t* pix, int w, int h, double* prev_xy, double* cur_xy, int* ids, int cap) {
   return guarded([&] {
     auto out = ((KLTTracker*)t)->step(wrap(pix, w, h));

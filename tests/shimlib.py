@@ -26,6 +26,10 @@ def load():
     lib.shim_tracker_destroy.argtypes = [_vp]
     lib.shim_tracker_step.argtypes = [_vp, _u8, _i, _i, _f8, _f8, _i4, _i]
     lib.shim_tracker_tracks.argtypes = [_vp, _f8, _i4, _i]
+    lib.shim_multitracker_create.restype = _vp
+    lib.shim_multitracker_create.argtypes = [_i, _i, _i, _i, _i]
+    lib.shim_multitracker_destroy.argtypes = [_vp]
+    lib.shim_multitracker_step.argtypes = [_vp, _u8, _i, _i, _i, _f8, _f8, _i4, _i4, _i, _f8, _i4, _i4]
     lib.shim_find_E_ransac.argtypes = [_f8, _f8, _f8, _i, _i, _d, _i, _f8, _f8, _i4, C.POINTER(_i)]
     lib.shim_host_triangulate.argtypes = [_f8, _f8, _i4, _i4, _f8, _f8, _i, _f8]
     lib.shim_set_device_solver.argtypes = [_i]

@@ -61,6 +61,28 @@ def test_tracker_class(shim, checker):
     shim.shim_tracker_destroy(t)
 
 
+def test_multitracker_class(shim, checker):
+    """MultiKLTTracker (C++ face of sfmgpu_multitracker): every sequence equals the reference's KLTTracker run on it."""
+    S, cap = 3, 200
+    wants = [checker.tracker(max_tracks=150, min_tracks=120) for _ in range(S)]
+    t = shim.shim_multitracker_create(S, W, H, 150, 120)
+    assert t
+    for fr in range(5):
+        imgs = np.stack([synth.frame(SEED + 7 * s, fr, W, H) for s in range(S)])
+        prev, cur, ids = np.zeros((S, cap, 2)), np.zeros((S, cap, 2)), np.zeros((S, cap), np.int32)
+        n, txy, tid, tn = np.zeros(S, np.int32), np.zeros((S, cap, 2)), np.zeros((S, cap), np.int32), np.zeros(S, np.int32)
+        shimlib.ck(shim, shim.shim_multitracker_step(t, imgs, S, W, H, prev, cur, ids, n, cap, txy, tid, tn))
+        for s in range(S):
+            wp, wc, wi = wants[s].step(imgs[s])
+            k = int(n[s])
+            assert k == len(wi) and np.array_equal(ids[s, :k], wi), (fr, s)
+            assert k == 0 or (np.abs(prev[s, :k] - wp).max() <= KLT_TOL and np.abs(cur[s, :k] - wc).max() <= KLT_TOL)
+            wxy, wid = wants[s].tracks()
+            m = int(tn[s])
+            assert m == len(wid) and np.array_equal(tid[s, :m], wid) and np.abs(txy[s, :m] - wxy).max() <= KLT_TOL
+    shim.shim_multitracker_destroy(t)
+
+
 def test_find_E_ransac_device_solver(shim, checker):
     """Opt-in device solver behind the same find_E_ransac: same inlier set, pose within 1e-9 of the reference's."""
     n, iters, thr, mi = 2200, 2500, 1e-3, 60
