@@ -756,10 +756,11 @@ int sfm_klt_lane_launch(sfmgpu_ctx* ctx, const KltLaunch& k, int* defer_count, i
     case 3: return lane_launch<1, 8, 4, false>(ctx, k, nullptr, nullptr, defer_count, defer_list);  // the FP64 window walk
     case 4: return quad_launch<8, 4, int>(ctx, k, defer_count, defer_list);
     case 5: return quad_launch<8, 4, float>(ctx, k, defer_count, defer_list);
-    case 6: return quad_launch<12, 8, float>(ctx, k, defer_count, defer_list);
+    case 6: return quad_launch<12, 4, float>(ctx, k, defer_count, defer_list);
     // Measured on B200 (C2, KLT stage incl. the border pass): <8,4,int> 16.8 ms, <8,4,float> 16.6, <10,4,float> 15.6,
-    // <12,4,float> 15.0, <16,4,float> 24.2 (spills); a single-sweep build (255 registers, 8 warps) 15.2 ms.
-    default: return quad_launch<12, 4, float>(ctx, k, defer_count, defer_list);  // quadratic forms over integer matrices
+    // <12,4,float> 15.0, <12,2,float> 14.8 (no spills), <16,4,float> 24.2 (spills), staging rounds of 8: 20.2 (spills); a
+    // single-sweep build (255 registers, 8 warps) 15.2 ms.
+    default: return quad_launch<12, 2, float>(ctx, k, defer_count, defer_list);  // quadratic forms over integer matrices
   }
 }
 
