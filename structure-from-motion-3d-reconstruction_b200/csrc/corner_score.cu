@@ -22,7 +22,8 @@
 // u~ >= bound - 2 (bound = the tile's / frame's running maximum in the max pass, 8*thr in the candidate pass); those
 // few are queued and evaluated DENSELY with the exact FP64 expression afterwards, which alone decides.
 //
-// (Tried and dropped: persistent blocks with cp.async double-buffered taps: 5.13 ms vs 4.46 ms per 299 frames.)
+// (Tried and dropped: persistent blocks with cp.async double-buffered taps: 5.13 ms vs 4.46 ms per 299 frames; 64 x 48
+// tiles at 4 blocks per SM and 63 registers: 8.06 vs 8.11 ms per 998 frames - occupancy is not what limits it.)
 // Kernels (tile = 64 x 60 output pixels, 256 threads, taps staged once in shared memory with clamping):
 //   score_tile_kernel<0>  per-frame maximum of u = 8*lmin  (atomicMax on the double's bit pattern)
 //   score_tile_kernel<1>  candidate bitmap (one word per 32 pixels) + unordered (pixel, score) list
