@@ -1,28 +1,28 @@
-// corner_select.cu — exact std::sort permutation + greedy min-distance selection, one thread block per frame.
+// corner_select.cu — the order std::sort gives the candidates + greedy min-distance selection, one thread block per frame.
 //
 // Replaces (reference cpp/src/templering_sfm.cpp) shi_tomasi :286-301: std::sort of the candidates by score
 // descending (unstable: libstdc++ introsort decides the order of ties), then the sequential greedy loop that
 // accepts a candidate iff no already accepted corner lies at squared distance < min_dist^2, capped at
 // max_corners (tested after the push, so at least one corner comes back whenever a candidate exists).
 //
-// Sort: the introsort segment tree is walked LEFT-FIRST and LAZILY (sort_emul.h facts 1-4): only as much of
-// the array is sorted as the selection consumes.  Segments larger than SMALL are partitioned by the whole
-// block (two ordered compactions of the misfits + pairwise swaps); smaller ones are handed to warps, up to 32
-// at a time, each warp finishing its segment completely (warp partitions, then one leaf per lane with the
-// stable insertion sort).  Depth-limit exhaustion takes the sequential heap-sort restatement.
+// Fast path (default): radix_sort_frame_kernel + nms_kernel.  The order std::sort produces is unique wherever the scores
+// are distinct, so the candidates are sorted by a per-frame LSD radix sort (8-bit passes over a 24-bit order code, then
+// the candidates that share a code are ordered by their full 64-bit score) and the selection walks that list.  Inside a
+// group of IDENTICAL scores introsort's order is only observable if at least two members are still unblocked when the
+// selection reaches them; nms_kernel detects that conservatively and such a frame (status 3) is redone by
+// the exact emulation below (select_kernel mode 3).  Results are bit-identical either way (tests force both paths).
 //
-// Fast path (default): the order std::sort produces is unique wherever the scores are distinct, so the candidates are
-// first sorted by a segmented LSD radix sort (radix_sort_frame_kernel: LSD passes of 8 bits over a 24-bit order code, then
-// the candidates that share a code are ordered by their full 64-bit score) and the selection walks
-// that list.  Only if two candidates with IDENTICAL scores lie inside the prefix the selection consumed — the one
-// case where introsort's tie order is observable — is the frame redone with the exact introsort emulation above
-// (status 3 -> select_kernel mode 3).  Results are bit-identical either way (tests force both paths).
+// Exact emulation (select_kernel): the introsort segment tree is walked LEFT-FIRST and LAZILY (sort_emul.h facts 1-4):
+// only as much of the array is sorted as the selection consumes.  Segments larger than SMALL are partitioned by the
+// whole block (two ordered compactions of the misfits + pairwise swaps); smaller ones are handed to warps, up to 32 at a
+// time, each warp finishing its segment completely (warp partitions, then one leaf per lane with the stable insertion
+// sort).  Depth-limit exhaustion takes the sequential heap-sort restatement.
 //
-// Selection: greedy acceptance only ever depends on higher-priority candidates, so a chunk of the sorted
-// prefix is decided in parallel: (1) kill candidates within min_dist of corners accepted in earlier chunks
-// (lookup in a min_dist-cell grid holding <= 2 corners per cell), (2) resolve conflicts inside the chunk by
-// rounds (a candidate is accepted once every closer, higher-priority survivor is decided), (3) append the
-// accepted ones in priority order.  Coordinates are integers: the arithmetic is exact.
+// Selection (both paths): greedy acceptance only ever depends on higher-priority candidates, so a chunk of the sorted
+// prefix is decided in parallel: (1) kill candidates within min_dist of corners accepted in earlier chunks (nms_kernel: one
+// bit per pixel, accepted corners mark their disc; select_kernel: a min_dist-cell grid holding <= 2 corners per cell),
+// (2) resolve conflicts inside the chunk by rounds (a candidate is accepted once every closer, higher-priority survivor
+// is decided), (3) append the accepted ones in priority order.  Coordinates are integers: the arithmetic is exact.
 #include "common.cuh"
 #include "corner_work.cuh"
 #include "sort_emul.h"
