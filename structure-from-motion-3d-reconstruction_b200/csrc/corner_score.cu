@@ -424,10 +424,12 @@ __global__ void rescue_mark_kernel(CornerWorkView wv, int count) {
 
 // Provisional list -> final list, for the paths that do not run the radix sort (which does the same in its first sweep):
 // keeps the entries that reach the final threshold (dense sort words (order code << 32 | slot) in pk_a, count in nfinal)
-// and clears the candidate-bitmap bit of every other entry.
-__global__ void __launch_bounds__(256) candidate_finalize_kernel(CornerWorkView wv, double quality) {
+// and clears the candidate-bitmap bit of every other entry (the raster ranks need the exact bitmap).
+// flagged_only: only frames the selection flagged (status 3), and only the bitmap is cleaned (their sort words exist).
+__global__ void __launch_bounds__(256) candidate_finalize_kernel(CornerWorkView wv, double quality, int flagged_only) {
   const int fr = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
   if (wv.exact_list[fr]) return;
+  if (flagged_only && wv.status[fr] != 3) return;
   const unsigned nprov = wv.ncand[fr];
   const size_t cb = (size_t)fr * wv.cand_cap, wb = (size_t)fr * wv.words_per_frame;
   const double maxv = 0.125 * __longlong_as_double(wv.maxbits[fr]);
@@ -449,7 +451,7 @@ __global__ void __launch_bounds__(256) candidate_finalize_kernel(CornerWorkView 
         atomicAnd(wv.bitmap + wb + (size_t)y * wv.wpr + (x >> 5), ~(1u << (x & 31)));
       }
     }
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    const unsigned m = __ballot_sync(0xffffffffu, keep && !flagged_only);
     if (m) {
       unsigned base = 0;
       if (lane == 0) base = atomicAdd(wv.nfinal + fr, (unsigned)__popc(m));
@@ -533,8 +535,9 @@ size_t sfm_corner_work_bytes(int w, int h, int nframes, int cand_cap) {
 // key[], idx[].  Needed by the introsort emulation and the candidate-list API; the radix selection path works on the
 // unordered list.
 int sfm_corner_raster_order(sfmgpu_ctx* ctx, int count, const CornerWorkView& wv, double quality, int only_flagged) {
-  // only_flagged: the radix sort has already reduced the provisional lists (and bitmaps) to the final candidates
-  if (!only_flagged) SFM_LAUNCH(ctx, candidate_finalize_kernel, dim3(32, count), 256, 0, wv, quality);
+  // provisional lists (fused score pass): drop the surplus bits from the candidate bitmap; without the radix sort
+  // (only_flagged == 0) also produce the final count and sort words
+  SFM_LAUNCH(ctx, candidate_finalize_kernel, dim3(32, count), 256, 0, wv, quality, only_flagged);
   SFM_LAUNCH(ctx, bitmap_scan_kernel, count, 1024, 0, wv, only_flagged);
   SFM_LAUNCH(ctx, order_kernel, dim3(16, count), 256, 0, wv, quality, only_flagged);
   return 0;

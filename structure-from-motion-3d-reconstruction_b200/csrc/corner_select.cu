@@ -437,8 +437,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) radix_sort_frame_kern
     }
   } else {
     // provisional list of the fused score pass: the frame maximum is final now.  Sweep 0 keeps the entries that reach
-    // the final threshold (s >= thr, :282) as sort words (order code << 32 | list slot), clears the candidate-bitmap
-    // bit of every other entry, and builds the histograms on the way.  The order code is the distance of the score's bit
+    // the final threshold (s >= thr, :282) as sort words (order code << 32 | list slot) and builds the histograms on the
+    // way (the candidate bitmap keeps the surplus bits: only the raster path needs it exact and cleans it itself).  The order code is the distance of the score's bit
     // pattern below the maximum, shifted so that [thr, max] fits CORNER_CODE_BITS bits (ascending code = descending score).
     const unsigned nprov = wv.ncand[fr];
     if (nprov > (unsigned)wv.cand_cap) return;  // such frames are on the rescue list (exact_list) - unreachable
@@ -450,8 +450,6 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) radix_sort_frame_kern
     const int bits = 64 - __clzll((long long)range);
     const int shift = bits > CORNER_CODE_BITS ? bits - CORNER_CODE_BITS : 0;
     const unsigned long long* lkey = wv.tmp_key + cb;
-    const unsigned* lyx = wv.tmp_idx + cb;
-    unsigned* bitmap = wv.bitmap + (size_t)fr * wv.words_per_frame;
     for (unsigned i0 = 0; i0 < nprov; i0 += THREADS * 4) {  // block-uniform trip count
       unsigned long long k[4];
 #pragma unroll
@@ -464,10 +462,6 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) radix_sort_frame_kern
         const unsigned e = i0 + q * THREADS + tid;
         const bool in = e < nprov;
         const bool keep = in && __longlong_as_double((long long)k[q]) >= thr;
-        if (in && !keep) {
-          const unsigned yx = lyx[e], x = yx & 0xFFFFu, y = yx >> 16;
-          atomicAnd(bitmap + (size_t)y * wv.wpr + (x >> 5), ~(1u << (x & 31)));
-        }
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         if (m) {
           unsigned base = 0;
