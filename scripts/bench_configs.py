@@ -17,7 +17,7 @@ import bench  # noqa: E402  (C4 scene helpers)
 
 out = {}
 ctx = sfmgpu.Context(0)
-SECTIONS = set(sys.argv[1:]) or {"c3", "c4", "c5"}
+SECTIONS = set(sys.argv[1:]) or {"c1", "c3", "c4", "c5"}
 
 # ---- C3: 4K, 8000 corners per frame, pair mode, resident ------------------------------------------------------------------
 W, H, NF, MC = 3840, 2160, (120 if "c3" in SECTIONS else 3), 8000
@@ -127,5 +127,65 @@ for nseq in (8, 32):
     out[f"C5_{nseq}_sequences_lockstep"]["pipelined_feature_tracks_per_s"] = mt.totals()[0] / piped
     mt.close()
     del stack
+# ---- C1 shape: the reference's own loop (tracker.step + find_E_ransac per frame) through the C++ shim, 640 x 480 -------------------
+if "c1" in SECTIONS:
+    import ctypes as C
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import shimlib
+    import oracle
+    from conftest import TEMPLE_K
+    shim = shimlib.load()
+    chk, kind = oracle.best()
+    NFR1, W1, H1 = 47, 640, 480
+    fr1 = [synth.frame(20261018, t, W1, H1) for t in range(NFR1)]
+    Kf = np.ascontiguousarray(TEMPLE_K.reshape(9))
+
+    def run_shim(device_solver):
+        shim.shim_set_device_solver(1 if device_solver else 0)
+        t = shim.shim_tracker_create(2200, 900, 0.01, 8, 3, 5, 10, 1.0)
+        prev, cur, ids = np.zeros((2300, 2)), np.zeros((2300, 2)), np.zeros(2300, np.int32)
+        R, tt, il, kk = np.zeros(9), np.zeros(3), np.zeros(2300, np.int32), C.c_int(0)
+        t_trk = t_e = 0.0
+        n_e = 0
+        for img in fr1:
+            t0 = time.perf_counter()
+            n = shimlib.ck(shim, shim.shim_tracker_step(t, img, W1, H1, prev, cur, ids, 2300))
+            t1 = time.perf_counter()
+            if n >= 8:
+                shimlib.ck(shim, shim.shim_find_E_ransac(Kf, np.ascontiguousarray(prev[:n]), np.ascontiguousarray(cur[:n]), n, 2500, 1e-3, 60,
+                                                         R, tt, il, C.byref(kk)))
+                n_e += 1
+            t2 = time.perf_counter()
+            t_trk += t1 - t0
+            t_e += t2 - t1
+        shim.shim_tracker_destroy(t)
+        shim.shim_set_device_solver(0)
+        return {"tracker_step_ms_per_frame": 1e3 * t_trk / NFR1, "find_E_ransac_ms_per_call": 1e3 * t_e / max(n_e, 1),
+                "front_end_ms_per_frame": 1e3 * (t_trk + t_e) / NFR1}
+
+    run_shim(False)  # warm-up (allocations, first launches)
+    c1 = {"frames": NFR1, "shape": [W1, H1], "max_tracks": 2200, "ransac": [2500, 1e-3, 60],
+          "gpu_host_solver": run_shim(False), "gpu_device_solver": run_shim(True)}
+    # the reference itself on ONE host core (it is single-threaded), first frames only
+    trk = chk.tracker(max_tracks=2200, min_tracks=900)
+    t_trk = t_e = 0.0
+    n_e = 0
+    NREF = 6
+    for img in fr1[:NREF]:
+        t0 = time.perf_counter()
+        p, c, i = trk.step(img)
+        t1 = time.perf_counter()
+        if len(i) >= 8:
+            chk.find_E_ransac(TEMPLE_K, p, c, 2500, 1e-3, 60)
+            n_e += 1
+        t2 = time.perf_counter()
+        t_trk += t1 - t0
+        t_e += t2 - t1
+    c1["cpu_reference_one_core"] = {"kind": kind, "frames": NREF, "tracker_step_ms_per_frame": 1e3 * t_trk / NREF,
+                                    "find_E_ransac_ms_per_call": 1e3 * t_e / max(n_e, 1),
+                                    "front_end_ms_per_frame": 1e3 * (t_trk + t_e) / NREF}
+    out["C1_shape_dropin_loop"] = c1
+
 ctx.close()
 print(json.dumps(out, indent=1))
