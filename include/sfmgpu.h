@@ -162,7 +162,9 @@ int sfmgpu_pairs_download_all(sfmgpu_ctx* ctx, sfmgpu_pairs* p, double* li_xy, d
 /* Device addresses of the same arrays (for NCCL gathers by the scheduler); valid until pairs_destroy. */
 int sfmgpu_pairs_device_ptrs(sfmgpu_pairs* p, void** li_xy, void** lj_xy, void** n_kept, void** n_corners);
 
-/* ---- stateful tracker: KLTTracker (:323-391) ---------------------------------------------------------- */
+/* ---- stateful tracker: KLTTracker (:323-391) ----------------------------------------------------------
+ * A track list never holds more than ROWS = max(max_tracks, min_tracks, 1) + 1 entries; `cap` arguments of that size
+ * always suffice. */
 int sfmgpu_tracker_create(sfmgpu_ctx* ctx, const sfmgpu_lkcfg* cfg, sfmgpu_tracker** out);
 void sfmgpu_tracker_destroy(sfmgpu_ctx* ctx, sfmgpu_tracker* t);
 /* reset(gray) :327-332 */
@@ -183,8 +185,9 @@ int sfmgpu_tracker_totals(sfmgpu_ctx* ctx, sfmgpu_tracker* t, long long* n_track
  * w x h.  The first step resets every sequence (n_out = 0 everywhere). */
 int sfmgpu_multitracker_create(sfmgpu_ctx* ctx, const sfmgpu_lkcfg* cfg, int n_sequences, int w, int h, sfmgpu_multitracker** out);
 void sfmgpu_multitracker_destroy(sfmgpu_ctx* ctx, sfmgpu_multitracker* t);
-/* host_pix: [n_sequences][h][w], the next frame of every sequence.  prev_xy / cur_xy: [n_sequences][max(max_tracks,1)+1][2],
- * ids: [n_sequences][max(max_tracks,1)+1], n_out: [n_sequences] survivors per sequence (any output may be NULL). */
+/* host_pix: [n_sequences][h][w], the next frame of every sequence.  With ROWS = max(max_tracks, min_tracks, 1) + 1 (the
+ * longest a track list can get: replenish appends before it tests the cap, :386-387): prev_xy / cur_xy are
+ * [n_sequences][ROWS][2], ids [n_sequences][ROWS], n_out [n_sequences] survivors per sequence (any output may be NULL). */
 int sfmgpu_multitracker_step(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, const uint8_t* host_pix, double* prev_xy, double* cur_xy,
                              int32_t* ids, int32_t* n_out);
 /* Pipelined form: next_host_pix (may be NULL) = the frames of the FOLLOWING step; they are uploaded and their pyramids built

@@ -71,7 +71,22 @@ struct sfmgpu_ctx {
   float stage_ms[4] = {0, 0, 0, 0};
   void* pinned = nullptr;  // staging for small D2H results
   size_t pinned_cap = 0;
+  // kernels whose >48 KB dynamic shared memory opt-in has been set ON THIS CONTEXT'S DEVICE (the attribute is per device)
+  std::vector<bool> smem_cfg;
 };
+
+// One id per call site / template instantiation that opts a kernel into large dynamic shared memory.
+int sfm_next_cfg_id();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (context, kernel): `id` comes from a function-local
+// `static const int id = sfm_next_cfg_id();`
+#define SFM_SMEM_OPTIN(ctx, id, kernel, bytes)                                                                    \
+  do {                                                                                                            \
+    if ((int)(ctx)->smem_cfg.size() <= (id)) (ctx)->smem_cfg.resize((id) + 1, false);                             \
+    if (!(ctx)->smem_cfg[(id)]) {                                                                                 \
+      SFM_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));     \
+      (ctx)->smem_cfg[(id)] = true;                                                                               \
+    }                                                                                                             \
+  } while (0)
 
 int sfm_fail(sfmgpu_ctx* ctx, int code, const char* fmt, ...);
 int sfm_reserve(sfmgpu_ctx* ctx, DevBuf& b, size_t bytes);
@@ -83,6 +98,21 @@ int sfm_pinned(sfmgpu_ctx* ctx, size_t bytes);
     if (e__ != cudaSuccess)                                                                          \
       return sfm_fail(ctx, SFMGPU_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),   \
                       __FILE__, __LINE__);                                                           \
+  } while (0)
+
+// Every extern "C" entry point that takes a context makes the context's device current first (one context = one device;
+// the caller's thread may have another device selected).
+#define SFM_ENTER(ctx)                                                                                \
+  do {                                                                                                \
+    if (ctx) {                                                                                        \
+      cudaError_t e__ = cudaSetDevice((ctx)->device);                                                 \
+      if (e__ != cudaSuccess)                                                                         \
+        return sfm_fail(ctx, SFMGPU_E_CUDA, "cudaSetDevice(%d) failed: %s", (ctx)->device, cudaGetErrorString(e__)); \
+    }                                                                                                 \
+  } while (0)
+#define SFM_ENTER_VOID(ctx)                  \
+  do {                                       \
+    if (ctx) cudaSetDevice((ctx)->device);   \
   } while (0)
 
 #define SFM_TRY(expr)        \
@@ -116,6 +146,18 @@ struct StageTimer {
     if (idx >= 0) cudaEventRecord(ctx->stage_evs[idx].b, ctx->stream);
   }
 };
+
+// The LK early exit `std::hypot(step) < 1e-3` (:413-416).  The squared norm decides everything outside a 1 % band around
+// the threshold (its rounding error is ~1e-16 relative); inside the band the reference's own form is evaluated, so the
+// discontinuity sits where the reference has it (up to hypot's last-ulp differences between libm implementations).
+#ifdef __CUDACC__
+__device__ __forceinline__ bool sfm_lk_step_small(double sx, double sy) {
+  const double q = sx * sx + sy * sy;
+  if (q < 0.98e-6) return true;
+  if (q > 1.02e-6) return false;
+  return hypot(sx, sy) < 1e-3;  // also reached by NaN steps: false, as in the reference
+}
+#endif
 
 static inline int sfm_align16(int v) { return v <= 0 ? 16 : ((v + 15) / 16) * 16; }
 static inline unsigned sfm_cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }

@@ -554,14 +554,11 @@ int sfm_corner_candidates_batch(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int fir
   SFM_CUDA(ctx, cudaMemsetAsync(wv.rescue_count, 0, sizeof(int), ctx->stream));
   const int ntx = sfm_cdiv(f->w, TW), nty = sfm_cdiv(f->h, TH);
   dim3 grid(ntx, nty, count);
-  static bool configured = false;
-  if (!configured) {
-    SFM_CUDA(ctx, cudaFuncSetAttribute(score_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScoreSmem)));
-    SFM_CUDA(ctx, cudaFuncSetAttribute(score_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScoreSmem)));
-    SFM_CUDA(ctx, cudaFuncSetAttribute(score_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScoreSmem)));
-    SFM_CUDA(ctx, cudaFuncSetAttribute(score_rescue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScoreSmem)));
-    configured = true;
-  }
+  static const int cfg_id[4] = {sfm_next_cfg_id(), sfm_next_cfg_id(), sfm_next_cfg_id(), sfm_next_cfg_id()};
+  SFM_SMEM_OPTIN(ctx, cfg_id[0], score_tile_kernel<0>, sizeof(ScoreSmem));
+  SFM_SMEM_OPTIN(ctx, cfg_id[1], score_tile_kernel<1>, sizeof(ScoreSmem));
+  SFM_SMEM_OPTIN(ctx, cfg_id[2], score_tile_kernel<2>, sizeof(ScoreSmem));
+  SFM_SMEM_OPTIN(ctx, cfg_id[3], score_rescue_kernel, sizeof(ScoreSmem));
   static const bool two_pass = getenv("SFMGPU_SCORE_TWO_PASS") != nullptr;  // A/B timing
   if (quality > 0.0 && !two_pass) {
     constexpr int PROBE = 4;  // every 4th tile in x and y seeds the running maximum (1/16 of a pass)
@@ -627,6 +624,7 @@ int sfm_candidates_single(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int frame, do
 
 extern "C" int sfmgpu_corner_candidates(sfmgpu_ctx* ctx, sfmgpu_frames* f, int frame, double quality, int32_t* xy,
                                         double* score, int cap, int* n_out, double* max_score) {
+  SFM_ENTER(ctx);
   if (!ctx || !f) return SFMGPU_E_ARG;
   if (frame < 0 || frame >= f->n || cap < 0) return sfm_fail(ctx, SFMGPU_E_ARG, "corner_candidates: bad frame/cap");
   return sfm_candidates_single(ctx, f, frame, quality, xy, score, cap, n_out, max_score);

@@ -1033,13 +1033,10 @@ __global__ void __launch_bounds__(SEL_THREADS, 4) select_kernel(CornerWorkView w
 }
 
 int select_smem_config(sfmgpu_ctx* ctx) {
-  static bool done = false;
-  if (!done) {
-    SFM_CUDA(ctx, cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelSmem)));
-    SFM_CUDA(ctx, cudaFuncSetAttribute(radix_sort_frame_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem<512>)));
-    SFM_CUDA(ctx, cudaFuncSetAttribute(radix_sort_frame_kernel<1024, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem<1024>)));
-    done = true;
-  }
+  static const int cfg_id[3] = {sfm_next_cfg_id(), sfm_next_cfg_id(), sfm_next_cfg_id()};
+  SFM_SMEM_OPTIN(ctx, cfg_id[0], select_kernel, sizeof(SelSmem));
+  SFM_SMEM_OPTIN(ctx, cfg_id[1], (radix_sort_frame_kernel<512, 8>), sizeof(RadixSmem<512>));
+  SFM_SMEM_OPTIN(ctx, cfg_id[2], (radix_sort_frame_kernel<1024, 4>), sizeof(RadixSmem<1024>));
   return 0;
 }
 
@@ -1106,6 +1103,7 @@ size_t sfm_corner_work_bytes_md(int w, int h, int nframes, int cand_cap, int min
 }
 
 extern "C" int sfmgpu_select_set_mode(sfmgpu_ctx* ctx, int mode) {
+  SFM_ENTER(ctx);
   if (!ctx) return SFMGPU_E_ARG;
   if (mode != 0 && mode != 1) return sfm_fail(ctx, SFMGPU_E_ARG, "select_set_mode: mode %d not in {0,1}", mode);
   ctx->select_mode = mode;
@@ -1114,6 +1112,7 @@ extern "C" int sfmgpu_select_set_mode(sfmgpu_ctx* ctx, int mode) {
 
 extern "C" int sfmgpu_corners(sfmgpu_ctx* ctx, sfmgpu_frames* f, int frame, int max_corners, double quality, int min_dist,
                               double* xy_out, int* n_out) {
+  SFM_ENTER(ctx);
   if (!ctx || !f || !xy_out || !n_out) return SFMGPU_E_ARG;
   if (frame < 0 || frame >= f->n) return sfm_fail(ctx, SFMGPU_E_ARG, "corners: bad frame index");
   const int cap_out = max_corners < 1 ? 1 : max_corners;
@@ -1161,6 +1160,7 @@ int sfm_sort_perm(sfmgpu_ctx* ctx, const double* keys, int n, int32_t* perm) {
 }
 
 extern "C" int sfmgpu_sort_perm_desc(sfmgpu_ctx* ctx, const double* keys, int n, int32_t* perm) {
+  SFM_ENTER(ctx);
   if (!ctx || (n > 0 && (!keys || !perm))) return SFMGPU_E_ARG;
   return sfm_sort_perm(ctx, keys, n, perm);
 }

@@ -8,6 +8,8 @@
 // (the reference copies it; we alias it), so one pyramid costs W*H*(1 + 1/4 + 1/16 ...) bytes of traffic.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 int sfm_fail(sfmgpu_ctx* ctx, int code, const char* fmt, ...) {
@@ -18,6 +20,11 @@ int sfm_fail(sfmgpu_ctx* ctx, int code, const char* fmt, ...) {
   va_end(ap);
   if (ctx) ctx->err = buf;
   return code;
+}
+
+int sfm_next_cfg_id() {
+  static std::atomic<int> next{0};
+  return next.fetch_add(1);
 }
 
 int sfm_reserve(sfmgpu_ctx* ctx, DevBuf& b, size_t bytes) {
@@ -106,6 +113,7 @@ void sfmgpu_destroy(sfmgpu_ctx* ctx) {
 const char* sfmgpu_last_error(sfmgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (CUDA device unavailable?)"; }
 
 int sfmgpu_sync(sfmgpu_ctx* ctx) {
+  SFM_ENTER(ctx);
   if (!ctx) return SFMGPU_E_ARG;
   SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -114,11 +122,13 @@ int sfmgpu_sync(sfmgpu_ctx* ctx) {
 long long sfmgpu_launch_count(sfmgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int sfmgpu_timer_start(sfmgpu_ctx* ctx) {
+  SFM_ENTER(ctx);
   if (!ctx) return SFMGPU_E_ARG;
   SFM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   return 0;
 }
 int sfmgpu_timer_stop(sfmgpu_ctx* ctx, float* ms) {
+  SFM_ENTER(ctx);
   if (!ctx || !ms) return SFMGPU_E_ARG;
   SFM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   SFM_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
@@ -127,6 +137,7 @@ int sfmgpu_timer_stop(sfmgpu_ctx* ctx, float* ms) {
 }
 
 int sfmgpu_flush_l2(sfmgpu_ctx* ctx, size_t bytes) {
+  SFM_ENTER(ctx);
   if (!ctx) return SFMGPU_E_ARG;
   SFM_TRY(sfm_reserve(ctx, ctx->flush, bytes));
   SFM_CUDA(ctx, cudaMemsetAsync(ctx->flush.p, 0x5a, bytes, ctx->stream));
@@ -134,11 +145,13 @@ int sfmgpu_flush_l2(sfmgpu_ctx* ctx, size_t bytes) {
 }
 
 int sfmgpu_host_alloc(sfmgpu_ctx* ctx, size_t bytes, void** out) {
+  SFM_ENTER(ctx);
   if (!ctx || !out) return SFMGPU_E_ARG;
   SFM_CUDA(ctx, cudaMallocHost(out, bytes));
   return 0;
 }
 int sfmgpu_host_free(sfmgpu_ctx* ctx, void* p) {
+  SFM_ENTER(ctx);
   if (!ctx) return SFMGPU_E_ARG;
   SFM_CUDA(ctx, cudaFreeHost(p));
   return 0;
@@ -146,6 +159,7 @@ int sfmgpu_host_free(sfmgpu_ctx* ctx, void* p) {
 
 // ---- frames ----------------------------------------------------------------------------------------------
 int sfmgpu_frames_create(sfmgpu_ctx* ctx, int w, int h, int nframes, int levels, sfmgpu_frames** out) {
+  SFM_ENTER(ctx);
   if (!ctx || !out || w <= 0 || h <= 0 || nframes <= 0 || levels < 1 || levels > SFM_MAXL)
     return sfm_fail(ctx, SFMGPU_E_ARG, "frames_create: bad arguments (w=%d h=%d n=%d levels=%d)", w, h, nframes, levels);
   sfmgpu_frames* f = new sfmgpu_frames();
@@ -177,6 +191,7 @@ int sfmgpu_frames_create(sfmgpu_ctx* ctx, int w, int h, int nframes, int levels,
 }
 
 void sfmgpu_frames_destroy(sfmgpu_ctx* ctx, sfmgpu_frames* f) {
+  SFM_ENTER_VOID(ctx);
   if (!f) return;
   if (ctx) cudaStreamSynchronize(ctx->stream);
   for (int l = 0; l < f->levels; l++)
@@ -199,6 +214,7 @@ static int check_range(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first, int c
 }
 
 int sfmgpu_frames_upload(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first, int count, const uint8_t* host_pix) {
+  SFM_ENTER(ctx);
   SFM_TRY(check_range(ctx, f, first, count, "frames_upload"));
   if (!host_pix) return sfm_fail(ctx, SFMGPU_E_ARG, "frames_upload: null host pointer");
   if (count == 0) return 0;
@@ -210,6 +226,7 @@ int sfmgpu_frames_upload(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first, int count
 
 int sfmgpu_frames_upload_device(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first, int count, const uint8_t* dev_pix,
                                 size_t pitch) {
+  SFM_ENTER(ctx);
   SFM_TRY(check_range(ctx, f, first, count, "frames_upload_device"));
   if (!dev_pix || pitch < (size_t)f->w) return sfm_fail(ctx, SFMGPU_E_ARG, "frames_upload_device: bad pointer/pitch");
   if (count == 0) return 0;
@@ -219,6 +236,7 @@ int sfmgpu_frames_upload_device(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first, in
 }
 
 int sfmgpu_frames_download(sfmgpu_ctx* ctx, sfmgpu_frames* f, int frame, int level, uint8_t* host_out) {
+  SFM_ENTER(ctx);
   SFM_TRY(check_range(ctx, f, frame, 1, "frames_download"));
   if (level < 0 || level >= f->levels || !host_out) return sfm_fail(ctx, SFMGPU_E_ARG, "frames_download: bad level");
   if (f->lw[level] == 0 || f->lh[level] == 0) return 0;
@@ -242,6 +260,7 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) 
 }
 
 extern "C" int sfmgpu_fp64_peak(sfmgpu_ctx* ctx, double* tflops) {
+  SFM_ENTER(ctx);
   if (!ctx || !tflops) return SFMGPU_E_ARG;
   SFM_TRY(sfm_reserve(ctx, ctx->misc, 256));
   const int iters = 20000, blocks = ctx->n_sm * 8, threads = 256;
@@ -260,12 +279,14 @@ extern "C" int sfmgpu_fp64_peak(sfmgpu_ctx* ctx, double* tflops) {
 }
 
 extern "C" int sfmgpu_profile(sfmgpu_ctx* ctx, int enable) {
+  SFM_ENTER(ctx);
   if (!ctx) return SFMGPU_E_ARG;
   ctx->profile = enable != 0;
   return 0;
 }
 
 extern "C" int sfmgpu_stage_times(sfmgpu_ctx* ctx, float* ms4) {
+  SFM_ENTER(ctx);
   if (!ctx || !ms4) return SFMGPU_E_ARG;
   SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   for (auto& e : ctx->stage_evs) {
@@ -328,6 +349,7 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(const uint8_t* __restrict
 }
 
 extern "C" int sfmgpu_pyramid_build(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first, int count) {
+  SFM_ENTER(ctx);
   SFM_TRY(check_range(ctx, f, first, count, "pyramid_build"));
   if (count == 0) return 0;
   int l = 0;
@@ -408,6 +430,7 @@ __global__ void __launch_bounds__(256) synth_kernel(uint8_t* __restrict__ dst, i
 }
 
 extern "C" int sfmgpu_frames_synth(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first, int count, uint32_t seed, int t0) {
+  SFM_ENTER(ctx);
   SFM_TRY(check_range(ctx, f, first, count, "frames_synth"));
   if (count == 0) return 0;
   dim3 block(64, 4);

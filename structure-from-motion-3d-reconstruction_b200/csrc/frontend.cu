@@ -167,6 +167,15 @@ __global__ void iota_ids_kernel(int* ids, const int* n, int next_id) {
   if (i < *n) ids[i] = next_id + i;
 }
 
+// Rows of a track list: after reset at most max(max_tracks, 1) entries; replenish appends first and tests the cap afterwards
+// (:386-387), so a list below min_tracks grows to max_tracks, or by ONE entry when it is already at / above max_tracks
+// (min_tracks > max_tracks): the list never exceeds max(max_tracks, min_tracks, 1), plus one overshoot entry.
+int track_rows(const sfmgpu_lkcfg& c) {
+  int m = c.max_tracks < 1 ? 1 : c.max_tracks;
+  if (c.min_tracks > m) m = c.min_tracks;
+  return m + 1;
+}
+
 int default_cand_cap(int w, int h) {
   long long px = (long long)w * h;
   long long cap = px / 6;
@@ -191,6 +200,7 @@ struct sfmgpu_pairs {
 extern "C" {
 
 int sfmgpu_pairs_create(sfmgpu_ctx* ctx, int max_pairs, int max_corners, sfmgpu_pairs** out) {
+  SFM_ENTER(ctx);
   if (!ctx || !out || max_pairs <= 0) return sfm_fail(ctx, SFMGPU_E_ARG, "pairs_create: bad arguments");
   sfmgpu_pairs* p = new sfmgpu_pairs();
   p->max_pairs = max_pairs;
@@ -219,6 +229,7 @@ int sfmgpu_pairs_create(sfmgpu_ctx* ctx, int max_pairs, int max_corners, sfmgpu_
 }
 
 void sfmgpu_pairs_destroy(sfmgpu_ctx* ctx, sfmgpu_pairs* p) {
+  SFM_ENTER_VOID(ctx);
   if (!p) return;
   if (ctx) cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {p->xy0, p->p1, p->pb, p->li, p->lj, p->nit, p->keep, p->ncorn, p->nkept, p->totals, p->work[0].p, p->work[1].p};
@@ -438,6 +449,7 @@ static int pair_args_ok(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int 
 }
 
 int sfmgpu_pipeline_set(sfmgpu_ctx* ctx, int pairs_per_chunk) {
+  SFM_ENTER(ctx);
   if (!ctx) return SFMGPU_E_ARG;
   if (pairs_per_chunk < 0) return sfm_fail(ctx, SFMGPU_E_ARG, "pipeline_set: negative chunk");
   ctx->pipe_chunk = pairs_per_chunk > 1024 ? 1024 : pairs_per_chunk;
@@ -446,6 +458,7 @@ int sfmgpu_pipeline_set(sfmgpu_ctx* ctx, int pairs_per_chunk) {
 
 int sfmgpu_pair_frontend(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int npairs, const sfmgpu_lkcfg* cfg,
                          sfmgpu_pairs* out) {
+  SFM_ENTER(ctx);
   if (!ctx || !f || !cfg || !out) return SFMGPU_E_ARG;
   SFM_TRY(pair_args_ok(ctx, f, first_frame, npairs, cfg, out));
   out->last_npairs = npairs;
@@ -477,6 +490,7 @@ int sfmgpu_pair_frontend(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int
 int sfmgpu_pair_frontend_host(sfmgpu_ctx* ctx, sfmgpu_frames* f, const uint8_t* host_pix, int nframes, const sfmgpu_lkcfg* cfg,
                               sfmgpu_pairs* out, int chunk_frames, double* li_xy, double* lj_xy, int32_t* n_kept,
                               int32_t* n_corners) {
+  SFM_ENTER(ctx);
   if (!ctx || !f || !cfg || !out || !host_pix) return SFMGPU_E_ARG;
   if (nframes < 0 || nframes > f->n) return sfm_fail(ctx, SFMGPU_E_ARG, "pair_frontend_host: %d frames do not fit (%d)", nframes, f->n);
   const int npairs = nframes > 0 ? nframes - 1 : 0;
@@ -537,6 +551,7 @@ int sfmgpu_pair_frontend_host(sfmgpu_ctx* ctx, sfmgpu_frames* f, const uint8_t* 
 }
 
 int sfmgpu_pairs_totals(sfmgpu_ctx* ctx, sfmgpu_pairs* p, long long* n_corners, long long* n_kept, long long* n_lk_iters) {
+  SFM_ENTER(ctx);
   if (!ctx || !p) return SFMGPU_E_ARG;
   unsigned long long t[4];
   SFM_CUDA(ctx, cudaMemcpyAsync(t, p->totals, sizeof t, cudaMemcpyDeviceToHost, ctx->stream));
@@ -551,6 +566,7 @@ int sfmgpu_pairs_totals(sfmgpu_ctx* ctx, sfmgpu_pairs* p, long long* n_corners, 
 
 int sfmgpu_pairs_download_all(sfmgpu_ctx* ctx, sfmgpu_pairs* p, double* li_xy, double* lj_xy, int32_t* n_kept,
                               int32_t* n_corners) {
+  SFM_ENTER(ctx);
   if (!ctx || !p) return SFMGPU_E_ARG;
   const size_t np_ = (size_t)p->last_npairs;
   if (np_ == 0) return 0;
@@ -573,6 +589,7 @@ int sfmgpu_pairs_device_ptrs(sfmgpu_pairs* p, void** li_xy, void** lj_xy, void**
 
 int sfmgpu_pairs_download(sfmgpu_ctx* ctx, sfmgpu_pairs* p, int pair, double* li_xy, double* lj_xy, int cap, int* n_kept,
                           int* n_corners) {
+  SFM_ENTER(ctx);
   if (!ctx || !p || pair < 0 || pair >= p->last_npairs) return sfm_fail(ctx, SFMGPU_E_ARG, "pairs_download: bad pair index");
   int nk = 0, nc = 0;
   SFM_CUDA(ctx, cudaMemcpyAsync(&nk, p->nkept + pair, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -623,7 +640,7 @@ int tracker_detect(sfmgpu_ctx* ctx, sfmgpu_tracker* t, sfmgpu_frames* f, int fra
 // Replenish one track list (:374-389): detect need*3 corners on the current frame, drop those within min_distance of a live
 // track, append survivors with consecutive ids until max_tracks (tested after the append: at least one is added).
 int replenish_row(sfmgpu_ctx* ctx, const sfmgpu_lkcfg& cfg, sfmgpu_frames* f, int frame, double2* trk, int* ids, int* n_io, int* next_id_io,
-                  double2* fresh, int fresh_cap, uint8_t* ok, int* scal) {
+                  double2* fresh, int fresh_cap, uint8_t* ok, int* scal, int row_cap) {
   const int need = cfg.max_tracks - *n_io;
   long long want = (long long)need * 3;
   if (want > fresh_cap) want = fresh_cap;  // fresh_cap = 3*max_tracks >= need*3
@@ -642,6 +659,8 @@ int replenish_row(sfmgpu_ctx* ctx, const sfmgpu_lkcfg& cfg, sfmgpu_frames* f, in
     // the reference appends first and tests the cap afterwards (:386-387): at least one corner is added
     int room = cfg.max_tracks - *n_io;
     if (room < 1) room = 1;
+    if (*n_io + room > row_cap)  // cannot happen with rows sized by track_rows(); never write past the row
+      return sfm_fail(ctx, SFMGPU_E_CAPACITY, "tracker: track list of %d + %d exceeds its %d rows", *n_io, room, row_cap);
     SFM_LAUNCH(ctx, replenish_append_kernel, 1, 1024, 0, fresh, (const int*)(scal + 1), ok, trk, ids, *n_io, room, *next_id_io, scal + 2);
     int na = 0;
     SFM_CUDA(ctx, cudaMemcpyAsync(&na, scal + 2, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -706,6 +725,8 @@ int tracker_step_on(sfmgpu_ctx* ctx, sfmgpu_tracker* t, sfmgpu_frames* f, int fr
     if (ids) SFM_CUDA(ctx, cudaMemcpyAsync(ids, t->oid, (size_t)nk * 4, cudaMemcpyDeviceToHost, ctx->stream));
     SFM_CUDA(ctx, cudaMemcpyAsync(t->trk, t->ob, (size_t)nk * 16, cudaMemcpyDeviceToDevice, ctx->stream));
     SFM_CUDA(ctx, cudaMemcpyAsync(t->ids, t->oid, (size_t)nk * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    // the header's promise: results are in the caller's (possibly pinned) buffers when the call returns
+    SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   t->n = nk;
   t->prev_frames = f;
@@ -713,7 +734,7 @@ int tracker_step_on(sfmgpu_ctx* ctx, sfmgpu_tracker* t, sfmgpu_frames* f, int fr
   if (n_out) *n_out = nk;
   // replenish (:374-389)
   if (t->n < t->cfg.min_tracks)
-    SFM_TRY(replenish_row(ctx, t->cfg, f, frame, t->trk, t->ids, &t->n, &t->next_id, t->fresh, t->fresh_cap, t->ok, t->scal));
+    SFM_TRY(replenish_row(ctx, t->cfg, f, frame, t->trk, t->ids, &t->n, &t->next_id, t->fresh, t->fresh_cap, t->ok, t->scal, t->cap));
   return 0;
 }
 
@@ -730,13 +751,13 @@ int tracker_own_frames(sfmgpu_ctx* ctx, sfmgpu_tracker* t, int w, int h) {
 extern "C" {
 
 int sfmgpu_tracker_create(sfmgpu_ctx* ctx, const sfmgpu_lkcfg* cfg, sfmgpu_tracker** out) {
+  SFM_ENTER(ctx);
   if (!ctx || !cfg || !out) return SFMGPU_E_ARG;
-  if (cfg->pyr_levels < 1 || cfg->pyr_levels > SFM_MAXL || cfg->max_tracks > (1 << 24))
+  if (cfg->pyr_levels < 1 || cfg->pyr_levels > SFM_MAXL || cfg->max_tracks > (1 << 24) || cfg->min_tracks > (1 << 24))
     return sfm_fail(ctx, SFMGPU_E_ARG, "tracker_create: bad configuration");
   sfmgpu_tracker* t = new sfmgpu_tracker();
   t->cfg = *cfg;
-  // the track list can hold max(max_tracks, 1) entries after reset, plus one overshoot entry from replenish
-  t->cap = (cfg->max_tracks < 1 ? 1 : cfg->max_tracks) + 1;
+  t->cap = track_rows(*cfg);
   t->fresh_cap = 3 * (cfg->max_tracks < 1 ? 1 : cfg->max_tracks);
   cudaError_t e = cudaSuccess;
   auto al = [&](void** q, size_t bytes) {
@@ -767,6 +788,7 @@ int sfmgpu_tracker_create(sfmgpu_ctx* ctx, const sfmgpu_lkcfg* cfg, sfmgpu_track
 }
 
 void sfmgpu_tracker_destroy(sfmgpu_ctx* ctx, sfmgpu_tracker* t) {
+  SFM_ENTER_VOID(ctx);
   if (!t) return;
   if (ctx) cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {t->trk, t->p1, t->pb, t->oa, t->ob, t->ids, t->oid, t->nit, t->keep, t->fresh, t->ok, t->scal, t->tot};
@@ -777,6 +799,7 @@ void sfmgpu_tracker_destroy(sfmgpu_ctx* ctx, sfmgpu_tracker* t) {
 }
 
 int sfmgpu_tracker_reset(sfmgpu_ctx* ctx, sfmgpu_tracker* t, const uint8_t* host_pix, int w, int h) {
+  SFM_ENTER(ctx);
   if (!ctx || !t || !host_pix) return SFMGPU_E_ARG;
   SFM_TRY(tracker_own_frames(ctx, t, w, h));
   const int slot = (t->prev_frames == t->own && t->prev_index == 0) ? 1 : 0;
@@ -787,6 +810,7 @@ int sfmgpu_tracker_reset(sfmgpu_ctx* ctx, sfmgpu_tracker* t, const uint8_t* host
 
 int sfmgpu_tracker_step(sfmgpu_ctx* ctx, sfmgpu_tracker* t, const uint8_t* host_pix, int w, int h, double* prev_xy,
                         double* cur_xy, int32_t* ids, int cap, int* n_out) {
+  SFM_ENTER(ctx);
   if (!ctx || !t || !host_pix) return SFMGPU_E_ARG;
   SFM_TRY(tracker_own_frames(ctx, t, w, h));
   const int slot = (t->prev_frames == t->own && t->prev_index == 0) ? 1 : 0;
@@ -797,6 +821,7 @@ int sfmgpu_tracker_step(sfmgpu_ctx* ctx, sfmgpu_tracker* t, const uint8_t* host_
 
 int sfmgpu_tracker_step_frames(sfmgpu_ctx* ctx, sfmgpu_tracker* t, sfmgpu_frames* f, int frame, double* prev_xy,
                                double* cur_xy, int32_t* ids, int cap, int* n_out) {
+  SFM_ENTER(ctx);
   if (!ctx || !t || !f) return SFMGPU_E_ARG;
   if (frame < 0 || frame >= f->n) return sfm_fail(ctx, SFMGPU_E_ARG, "tracker_step_frames: bad frame index");
   if (f->levels != t->cfg.pyr_levels) return sfm_fail(ctx, SFMGPU_E_ARG, "tracker_step_frames: pyramid levels differ from cfg");
@@ -804,6 +829,7 @@ int sfmgpu_tracker_step_frames(sfmgpu_ctx* ctx, sfmgpu_tracker* t, sfmgpu_frames
 }
 
 int sfmgpu_tracker_tracks(sfmgpu_ctx* ctx, sfmgpu_tracker* t, double* xy, int32_t* ids, int cap, int* n_out) {
+  SFM_ENTER(ctx);
   if (!ctx || !t) return SFMGPU_E_ARG;
   if (n_out) *n_out = t->n;
   if (t->n > cap) return sfm_fail(ctx, SFMGPU_E_CAPACITY, "tracker_tracks: %d tracks, room for %d", t->n, cap);
@@ -816,6 +842,7 @@ int sfmgpu_tracker_tracks(sfmgpu_ctx* ctx, sfmgpu_tracker* t, double* xy, int32_
 }
 
 int sfmgpu_tracker_totals(sfmgpu_ctx* ctx, sfmgpu_tracker* t, long long* n_track_steps, long long* n_lk_iters) {
+  SFM_ENTER(ctx);
   if (!ctx || !t) return SFMGPU_E_ARG;
   unsigned long long tt[4];
   SFM_CUDA(ctx, cudaMemcpyAsync(tt, t->tot, sizeof tt, cudaMemcpyDeviceToHost, ctx->stream));
@@ -882,16 +909,17 @@ int multi_reset(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, int par) {
 extern "C" {
 
 int sfmgpu_multitracker_create(sfmgpu_ctx* ctx, const sfmgpu_lkcfg* cfg, int n_sequences, int w, int h, sfmgpu_multitracker** out) {
+  SFM_ENTER(ctx);
   if (!ctx || !cfg || !out) return SFMGPU_E_ARG;
   if (n_sequences < 1 || n_sequences > 512 || w < 1 || h < 1 || cfg->pyr_levels < 1 || cfg->pyr_levels > SFM_MAXL ||
-      cfg->max_tracks > (1 << 24))
+      cfg->max_tracks > (1 << 24) || cfg->min_tracks > (1 << 24))
     return sfm_fail(ctx, SFMGPU_E_ARG, "multitracker_create: bad configuration");
   sfmgpu_multitracker* t = new sfmgpu_multitracker();
   t->cfg = *cfg;
   t->S = n_sequences;
   t->w = w;
   t->h = h;
-  t->cap = (cfg->max_tracks < 1 ? 1 : cfg->max_tracks) + 1;  // one overshoot entry from replenish, as in sfmgpu_tracker
+  t->cap = track_rows(*cfg);  // as in sfmgpu_tracker
   t->fresh_cap = 3 * (cfg->max_tracks < 1 ? 1 : cfg->max_tracks);
   t->n.assign(n_sequences, 0);
   t->next_id.assign(n_sequences, 0);
@@ -931,6 +959,7 @@ int sfmgpu_multitracker_create(sfmgpu_ctx* ctx, const sfmgpu_lkcfg* cfg, int n_s
 }
 
 void sfmgpu_multitracker_destroy(sfmgpu_ctx* ctx, sfmgpu_multitracker* t) {
+  SFM_ENTER_VOID(ctx);
   if (!t) return;
   if (ctx) cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {t->trk, t->p1, t->pb, t->oa, t->ob, t->ids, t->oid, t->nit, t->keep, t->fresh, t->ok, t->dn, t->dnk, t->scal, t->tot};
@@ -960,6 +989,7 @@ static int multi_prefetch(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, int after_gro
 }
 
 int sfmgpu_multitracker_prefetch(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, const uint8_t* host_pix) {
+  SFM_ENTER(ctx);
   if (!ctx || !t || !host_pix) return SFMGPU_E_ARG;
   if (t->prefetched) return sfm_fail(ctx, SFMGPU_E_STATE, "multitracker_prefetch: the prefetched frames have not been stepped yet");
   return multi_prefetch(ctx, t, t->parity < 0 ? 2 : t->parity, host_pix);
@@ -967,11 +997,13 @@ int sfmgpu_multitracker_prefetch(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, const 
 
 int sfmgpu_multitracker_step(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, const uint8_t* host_pix, double* prev_xy, double* cur_xy,
                              int32_t* ids, int32_t* n_out) {
+  SFM_ENTER(ctx);
   return sfmgpu_multitracker_step_pipelined(ctx, t, host_pix, nullptr, prev_xy, cur_xy, ids, n_out);
 }
 
 int sfmgpu_multitracker_step_pipelined(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, const uint8_t* host_pix, const uint8_t* next_host_pix,
                                        double* prev_xy, double* cur_xy, int32_t* ids, int32_t* n_out) {
+  SFM_ENTER(ctx);
   if (!ctx || !t) return SFMGPU_E_ARG;
   if (!host_pix && !t->prefetched) return sfm_fail(ctx, SFMGPU_E_STATE, "multitracker_step: no frames given and none prefetched");
   if (host_pix && t->prefetched) return sfm_fail(ctx, SFMGPU_E_STATE, "multitracker_step: frames given but others are prefetched");
@@ -1048,12 +1080,13 @@ int sfmgpu_multitracker_step_pipelined(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, 
     for (int e : empties) was_empty = was_empty || e == s;
     if (!was_empty && t->n[s] < t->cfg.min_tracks)
       SFM_TRY(replenish_row(ctx, t->cfg, t->frames, par * S + s, t->trk + (size_t)s * cap, t->ids + (size_t)s * cap, &t->n[s],
-                            &t->next_id[s], t->fresh, t->fresh_cap, t->ok, t->scal));
+                            &t->next_id[s], t->fresh, t->fresh_cap, t->ok, t->scal, cap));
   }
   return 0;
 }
 
 int sfmgpu_multitracker_tracks(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, int sequence, double* xy, int32_t* ids, int cap, int* n_out) {
+  SFM_ENTER(ctx);
   if (!ctx || !t) return SFMGPU_E_ARG;
   if (sequence < 0 || sequence >= t->S) return sfm_fail(ctx, SFMGPU_E_ARG, "multitracker_tracks: bad sequence index");
   const int n = t->n[sequence];
@@ -1068,6 +1101,7 @@ int sfmgpu_multitracker_tracks(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, int sequ
 }
 
 int sfmgpu_multitracker_totals(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, long long* n_track_steps, long long* n_lk_iters) {
+  SFM_ENTER(ctx);
   if (!ctx || !t) return SFMGPU_E_ARG;
   unsigned long long tt[4];
   SFM_CUDA(ctx, cudaMemcpyAsync(tt, t->tot, sizeof tt, cudaMemcpyDeviceToHost, ctx->stream));

@@ -229,7 +229,7 @@ __device__ void track_one(KltSmem<R>& sm, const PyrView& pv, int fa, int fb, int
       n_it++;
       dlx += sx;
       dly += sy;
-      if (sx * sx + sy * sy < 1e-6) break;  // hypot(step) < 1e-3 (:416)
+      if (sfm_lk_step_small(sx, sy)) break;  // hypot(step) < 1e-3 (:416)
     }
     const double up = (double)(1 << l);
     px = (plx + dlx) * up;
@@ -275,11 +275,8 @@ template <int R, bool FIXED>
 int launch_r(sfmgpu_ctx* ctx, const KltLaunch& k, const int* list, const int* list_count) {
   const int warps_per_block = 4;
   const size_t smem = sizeof(KltSmem<R>) * warps_per_block;
-  static bool configured = false;
-  if (!configured) {
-    SFM_CUDA(ctx, cudaFuncSetAttribute(klt_kernel<R, FIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  static const int cfg_id = sfm_next_cfg_id();  // one per template instantiation
+  SFM_SMEM_OPTIN(ctx, cfg_id, (klt_kernel<R, FIXED>), smem);
   const long long total = (long long)k.npairs * k.cap;
   if (total == 0) return 0;
   unsigned grid = sfm_cdiv(total, warps_per_block);
@@ -334,6 +331,7 @@ int sfm_klt_launch(sfmgpu_ctx* ctx, const KltLaunch& k) {
 }
 
 extern "C" int sfmgpu_klt_set_mode(sfmgpu_ctx* ctx, int mode) {
+  SFM_ENTER(ctx);
   if (!ctx) return SFMGPU_E_ARG;
   if (mode < 0 || (mode > 2 && (mode < 10 || mode > 19)))
     return sfm_fail(ctx, SFMGPU_E_ARG, "klt_set_mode: mode %d not in {0,1,2} (10..19: tuning variants)", mode);
@@ -343,6 +341,7 @@ extern "C" int sfmgpu_klt_set_mode(sfmgpu_ctx* ctx, int mode) {
 
 extern "C" int sfmgpu_klt_track(sfmgpu_ctx* ctx, sfmgpu_frames* f, int frame_a, int frame_b, const double* p0_xy, int n,
                                 int win_radius, int iters, double* p1_xy, double* p0_back_xy, int32_t* n_iters) {
+  SFM_ENTER(ctx);
   if (!ctx || !f) return SFMGPU_E_ARG;
   if (frame_a < 0 || frame_a >= f->n || frame_b < 0 || frame_b >= f->n || n < 0)
     return sfm_fail(ctx, SFMGPU_E_ARG, "klt_track: bad frame index or count");

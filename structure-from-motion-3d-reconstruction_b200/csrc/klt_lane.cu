@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(32 * LWARPS, MINB) klt_lane_kernel(KltLaunch k
           n_it++;
           dlx += sx;
           dly += sy;
-          if (sx * sx + sy * sy < 1e-6) done = true;  // hypot(step) < 1e-3 (:416), tested on the step just added
+          if (sfm_lk_step_small(sx, sy)) done = true;  // hypot(step) < 1e-3 (:416), tested on the step just added
         }
       }
       const double up = (double)(1 << l);
@@ -650,7 +650,7 @@ __global__ void __launch_bounds__(32, MINB) klt_quad_kernel(KltLaunch k, int* __
           it++;
           dlx += sx;
           dly += sy;
-          if (sx * sx + sy * sy < 1e-6) leveldone = true;  // hypot(step) < 1e-3 (:416), tested on the step just added
+          if (sfm_lk_step_small(sx, sy)) leveldone = true;  // hypot(step) < 1e-3 (:416), tested on the step just added
         }
         continue;
       }
@@ -714,12 +714,8 @@ __global__ void __launch_bounds__(32, MINB) klt_quad_kernel(KltLaunch k, int* __
 template <int ACC, int MINB, int LSTAGE, bool MASKED>
 static int lane_launch(sfmgpu_ctx* ctx, const KltLaunch& k, const int* in_list, const int* in_count, int* defer_count, int* defer_list) {
   const size_t smem = (size_t)LWARPS * 32 * LSTRIDE;
-  static bool configured = false;
-  if (!configured) {
-    SFM_CUDA(ctx, cudaFuncSetAttribute(klt_lane_kernel<ACC, MINB, LSTAGE, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
-    configured = true;
-  }
+  static const int cfg_id = sfm_next_cfg_id();  // one per template instantiation
+  SFM_SMEM_OPTIN(ctx, cfg_id, (klt_lane_kernel<ACC, MINB, LSTAGE, MASKED>), smem);
   const long long total = (long long)k.npairs * k.cap;
   if (total == 0) return 0;
   unsigned grid = sfm_cdiv(total, 32 * LWARPS);
@@ -736,11 +732,8 @@ static int lane_launch(sfmgpu_ctx* ctx, const KltLaunch& k, const int* in_list, 
 template <int MINB, int LSTAGE, typename T>
 static int quad_launch(sfmgpu_ctx* ctx, const KltLaunch& k, int* defer_count, int* defer_list) {
   const size_t smem = (size_t)32 * LSTRIDE;
-  static bool configured = false;
-  if (!configured) {
-    SFM_CUDA(ctx, cudaFuncSetAttribute(klt_quad_kernel<MINB, LSTAGE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  static const int cfg_id = sfm_next_cfg_id();  // one per template instantiation
+  SFM_SMEM_OPTIN(ctx, cfg_id, (klt_quad_kernel<MINB, LSTAGE, T>), smem);
   const long long total = (long long)k.npairs * k.cap;
   if (total == 0) return 0;
   SFM_LAUNCH(ctx, (klt_quad_kernel<MINB, LSTAGE, T>), sfm_cdiv(total, 32), 32, smem, k, defer_count, defer_list);

@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(128) desc_dot_kernel(const float* __restrict__
 extern "C" {
 
 int sfmgpu_global_desc32(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first, int count, float* desc_out) {
+  SFM_ENTER(ctx);
   if (!ctx || !f) return SFMGPU_E_ARG;
   if (first < 0 || count < 0 || first + count > f->n) return sfm_fail(ctx, SFMGPU_E_ARG, "global_desc32: bad frame range");
   if (count == 0) return 0;
@@ -103,6 +104,7 @@ int sfmgpu_global_desc32(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first, int count
 
 int sfmgpu_desc_search(sfmgpu_ctx* ctx, const float* descs, int n_search, const float* query, float* scores, int* best_id,
                        float* best_score) {
+  SFM_ENTER(ctx);
   if (!ctx || n_search < 0 || !query || (n_search > 0 && !descs)) return sfm_fail(ctx, SFMGPU_E_ARG, "desc_search: bad arguments");
   int bid = -1;
   float bs = 0.0f;

@@ -266,6 +266,7 @@ int score_resident(sfmgpu_ctx* ctx, double thr) {
 extern "C" {
 
 int sfmgpu_ransac_upload(sfmgpu_ctx* ctx, const double* xi_xy, const double* xj_xy, int n, const double* E, int H) {
+  SFM_ENTER(ctx);
   if (!ctx || n < 0 || H < 0) return sfm_fail(ctx, SFMGPU_E_ARG, "ransac_upload: bad sizes");
   if ((n > 0 && (!xi_xy || !xj_xy)) || (H > 0 && !E)) return sfm_fail(ctx, SFMGPU_E_ARG, "ransac_upload: null pointer");
   SFM_TRY(sfm_reserve(ctx, ctx->rs_xi, (size_t)(n + 1) * 16));
@@ -285,6 +286,7 @@ int sfmgpu_ransac_upload(sfmgpu_ctx* ctx, const double* xi_xy, const double* xj_
 }
 
 int sfmgpu_ransac_score_resident(sfmgpu_ctx* ctx, double thr, int* best_h, int* best_n) {
+  SFM_ENTER(ctx);
   if (!ctx) return SFMGPU_E_ARG;
   if (!ctx->rs_best.p) return sfm_fail(ctx, SFMGPU_E_STATE, "ransac_score_resident: nothing uploaded");
   SFM_TRY(score_resident(ctx, thr));
@@ -299,6 +301,7 @@ int sfmgpu_ransac_score_resident(sfmgpu_ctx* ctx, double thr, int* best_h, int* 
 }
 
 int sfmgpu_ransac_download(sfmgpu_ctx* ctx, int32_t* counts, int32_t* best_inl, int cap_inl) {
+  SFM_ENTER(ctx);
   if (!ctx) return SFMGPU_E_ARG;
   if (!ctx->rs_best.p) return sfm_fail(ctx, SFMGPU_E_STATE, "ransac_download: nothing scored");
   int hb[2];
@@ -316,6 +319,7 @@ int sfmgpu_ransac_download(sfmgpu_ctx* ctx, int32_t* counts, int32_t* best_inl, 
 
 int sfmgpu_ransac_score(sfmgpu_ctx* ctx, const double* xi_xy, const double* xj_xy, int n, const double* E, int H, double thr,
                         int32_t* counts, int* best_h, int32_t* best_inl, int* best_n) {
+  SFM_ENTER(ctx);
   if (!ctx) return SFMGPU_E_ARG;
   SFM_TRY(sfmgpu_ransac_upload(ctx, xi_xy, xj_xy, n, E, H));
   int bh = -1, bn = 0;

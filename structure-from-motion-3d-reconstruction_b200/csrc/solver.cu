@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(128) triangulate_kernel(const double* __restri
 
 extern "C" int sfmgpu_triangulate_dlt(sfmgpu_ctx* ctx, const double* K, const double* poses, int P, const int32_t* ia, const int32_t* ib,
                                       const double* ui_xy, const double* uj_xy, int n, double* X_out) {
+  SFM_ENTER(ctx);
   if (!ctx || n < 0 || P < 0) return sfm_fail(ctx, SFMGPU_E_ARG, "triangulate_dlt: bad sizes");
   if (n == 0) return 0;
   if (!K || !poses || P < 1 || !ia || !ib || !ui_xy || !uj_xy || !X_out) return sfm_fail(ctx, SFMGPU_E_ARG, "triangulate_dlt: null pointer");
@@ -246,6 +247,7 @@ extern "C" int sfmgpu_triangulate_dlt(sfmgpu_ctx* ctx, const double* K, const do
 
 extern "C" int sfmgpu_ransac_hypotheses(sfmgpu_ctx* ctx, const double* xi_xy, const double* xj_xy, int n, const int32_t* idx8, int H,
                                         double* E_out) {
+  SFM_ENTER(ctx);
   if (!ctx || n < 0 || H < 0) return sfm_fail(ctx, SFMGPU_E_ARG, "ransac_hypotheses: bad sizes");
   if (n < 1 && H > 0) return sfm_fail(ctx, SFMGPU_E_ARG, "ransac_hypotheses: no correspondences");
   if ((n > 0 && (!xi_xy || !xj_xy)) || (H > 0 && !idx8)) return sfm_fail(ctx, SFMGPU_E_ARG, "ransac_hypotheses: null pointer");

@@ -87,6 +87,13 @@ inline int solver_threads() {
 }
 inline void set_device_solver(bool on) { device_solver_flag() = on; }
 
+// Rows of a track list / of the per-sequence output arrays: max(max_tracks, min_tracks, 1) + 1 (see sfmgpu.h, tracker).
+inline int track_rows(int max_tracks, int min_tracks) {
+  int m = max_tracks < 1 ? 1 : max_tracks;
+  if (min_tracks > m) m = min_tracks;
+  return m + 1;
+}
+
 // Process-wide context.
 inline sfmgpu_ctx* context() {
   static sfmgpu_ctx* ctx = [] {
@@ -238,8 +245,14 @@ class KLTTracker {
     sfmgpu_tracker* t = nullptr;
     sfmgpu_shim::check(sfmgpu_shim::context(), sfmgpu_tracker_create(sfmgpu_shim::context(), &c, &t), "tracker_create");
     trk_ = std::shared_ptr<sfmgpu_tracker>(t, [](sfmgpu_tracker* p) { sfmgpu_tracker_destroy(sfmgpu_shim::context(), p); });
-    cap_ = (cfg.max_tracks < 1 ? 1 : cfg.max_tracks) + 1;
+    cap_ = sfmgpu_shim::track_rows(cfg.max_tracks, cfg.min_tracks);
   }
+  // The device state is owned, not shared: a copy would alias one tracker (stepping the copy would advance the
+  // original).  The reference class is copyable but never copied (:1688, :1841); the drop-in is move-only.
+  KLTTracker(const KLTTracker&) = delete;
+  KLTTracker& operator=(const KLTTracker&) = delete;
+  KLTTracker(KLTTracker&&) = default;
+  KLTTracker& operator=(KLTTracker&&) = default;
 
   void reset(const GrayImage& gray) {
     auto* ctx = sfmgpu_shim::context();
@@ -302,6 +315,8 @@ class KLTTracker {
 // KLTTracker's; all images must be w x h.
 class MultiKLTTracker {
  public:
+  MultiKLTTracker(const MultiKLTTracker&) = delete;
+  MultiKLTTracker& operator=(const MultiKLTTracker&) = delete;
   MultiKLTTracker(LKConfig cfg, int n_sequences, int w, int h) : S_(n_sequences), w_(w), h_(h) {
     sfmgpu_lkcfg c;
     c.max_tracks = cfg.max_tracks;
@@ -316,7 +331,7 @@ class MultiKLTTracker {
     auto* ctx = sfmgpu_shim::context();
     sfmgpu_shim::check(ctx, sfmgpu_multitracker_create(ctx, &c, n_sequences, w, h, &t), "multitracker_create");
     trk_ = std::shared_ptr<sfmgpu_multitracker>(t, [](sfmgpu_multitracker* p) { sfmgpu_multitracker_destroy(sfmgpu_shim::context(), p); });
-    cap_ = (cfg.max_tracks < 1 ? 1 : cfg.max_tracks) + 1;
+    cap_ = sfmgpu_shim::track_rows(cfg.max_tracks, cfg.min_tracks);
     void* pin = nullptr;  // page-locked staging for the S frames of a step
     sfmgpu_shim::check(ctx, sfmgpu_host_alloc(ctx, (size_t)S_ * w * h, &pin), "host_alloc");
     stage_ = std::shared_ptr<uint8_t>((uint8_t*)pin, [](uint8_t* p) { sfmgpu_host_free(sfmgpu_shim::context(), p); });

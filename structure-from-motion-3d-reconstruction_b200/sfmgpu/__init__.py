@@ -462,7 +462,7 @@ class MultiTracker:
         p = _vp()
         ctx._ck(ctx.lib.sfmgpu_multitracker_create(ctx.h, C.byref(cfg), n_sequences, w, h, C.byref(p)))
         self.h_ = p
-        self.cap = max(1, cfg.max_tracks) + 1
+        self.cap = max(1, cfg.max_tracks, cfg.min_tracks) + 1
         self.prev = ctx.pinned_empty((n_sequences, self.cap, 2), np.float64)
         self.cur = ctx.pinned_empty((n_sequences, self.cap, 2), np.float64)
         self.ids = ctx.pinned_empty((n_sequences, self.cap), np.int32)
@@ -523,7 +523,7 @@ class Tracker:
         p = _vp()
         ctx._ck(ctx.lib.sfmgpu_tracker_create(ctx.h, C.byref(cfg), C.byref(p)))
         self.h_ = p
-        self.cap = max(1, cfg.max_tracks) + 1
+        self.cap = max(1, cfg.max_tracks, cfg.min_tracks) + 1
 
     def close(self):
         if getattr(self, "h_", None) and self.ctx.h:

@@ -29,11 +29,17 @@ def ref():
     return r
 
 
-@pytest.fixture(scope="session")
-def checker():
-    """The strongest CPU checker available: the compiled reference if present, else the port."""
+@pytest.fixture
+def checker(request):
+    """The CPU checker: the compiled reference.  GPU parity tests FAIL (they do not downgrade to the builder's own port)
+    when oracle/_ref/libsfmref.so is missing; CPU-side tests may fall back to the port, which test_oracle_vs_ref.py pins
+    to the reference."""
     import oracle
-    return oracle.best()[0]
+    chk, kind = oracle.best()
+    if kind != "reference" and request.node.get_closest_marker("gpu") is not None:
+        pytest.fail("oracle/_ref/libsfmref.so (the compiled reference) is missing: GPU parity tests do not fall back to "
+                    "the port - build it with `make -C oracle` where /root/reference is present")
+    return chk
 
 
 @pytest.fixture(scope="session")

@@ -6,7 +6,7 @@ import numpy as np
 
 import sfmgpu
 
-PATH = os.path.join(os.path.dirname(sfmgpu.LIB_PATH), "libsfmshim.so")
+PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsfmshim.so")
 _u8 = np.ctypeslib.ndpointer(np.uint8, flags="C")
 _f8 = np.ctypeslib.ndpointer(np.float64, flags="C")
 _i4 = np.ctypeslib.ndpointer(np.int32, flags="C")
