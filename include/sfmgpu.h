@@ -77,6 +77,8 @@ int sfmgpu_flush_l2(sfmgpu_ctx* ctx, size_t bytes);
  * Reading synchronises the stream and resets the accumulators. */
 int sfmgpu_profile(sfmgpu_ctx* ctx, int enable);
 int sfmgpu_stage_times(sfmgpu_ctx* ctx, float* ms4);
+/* Same with n values: ms[4] = the RANSAC stage of the two-view unit (sfmgpu_pairs_set_ransac). */
+int sfmgpu_stage_times_n(sfmgpu_ctx* ctx, float* ms, int n);
 /* Measured non-tensor FP64 throughput of this GPU (DFMA micro-benchmark, ~10 ms): the KLT / RANSAC roofline. */
 int sfmgpu_fp64_peak(sfmgpu_ctx* ctx, double* tflops);
 /* Pinned host memory for callers that want asynchronous uploads. */
@@ -130,7 +132,10 @@ int sfmgpu_klt_set_mode(sfmgpu_ctx* ctx, int mode);
 /* ---- stateless two-view front end over a batch of pairs (:1836-1857) -------------------------------- */
 /* For every pair (first_frame+k, first_frame+k+1), k < npairs: pyramids must be built; detect up to
  * cfg->max_tracks corners on the first frame, track fwd/bwd, keep iff !(fb >= fb_thresh).
- * Results stay on the device in `out` (create once, reuse). */
+ * Results stay on the device in `out` (create once, reuse).  The call returns when the batch has finished: candidate
+ * lists are sized for w*h/6 entries per frame, and frames that need more (flat / weak-texture images, where up to every
+ * pixel is a candidate, :274-285) are redone with the full capacity before the call returns, so every frame carries the
+ * reference's result; an error (SFMGPU_E_CAPACITY included) is reported by this call, not by a later download. */
 int sfmgpu_pairs_create(sfmgpu_ctx* ctx, int max_pairs, int max_corners, sfmgpu_pairs** out);
 void sfmgpu_pairs_destroy(sfmgpu_ctx* ctx, sfmgpu_pairs* p);
 int sfmgpu_pair_frontend(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int npairs, const sfmgpu_lkcfg* cfg,
@@ -159,8 +164,55 @@ int sfmgpu_pairs_download(sfmgpu_ctx* ctx, sfmgpu_pairs* p, int pair, double* li
  * Any pointer may be NULL.  Use pinned buffers (sfmgpu_host_alloc) for full-speed copies. */
 int sfmgpu_pairs_download_all(sfmgpu_ctx* ctx, sfmgpu_pairs* p, double* li_xy, double* lj_xy, int32_t* n_kept,
                               int32_t* n_corners);
+/* Correspondences that do not come from the tracker (e.g. the keyframe observations of :1784-1793): li/lj are
+ * [npairs][max_corners] (x,y) pairs, the first n_kept[k] of pair k valid.  They become "the last batch", ready for
+ * sfmgpu_pairs_ransac. */
+int sfmgpu_pairs_set_matches(sfmgpu_ctx* ctx, sfmgpu_pairs* p, int npairs, const double* li_xy, const double* lj_xy,
+                             const int32_t* n_kept);
 /* Device addresses of the same arrays (for NCCL gathers by the scheduler); valid until pairs_destroy. */
 int sfmgpu_pairs_device_ptrs(sfmgpu_pairs* p, void** li_xy, void** lj_xy, void** n_kept, void** n_corners);
+
+/* ---- RANSAC stage of the two-view unit, batched over the pairs of a batch (:1855-1857; find_E_ransac :640-761) -----------
+ * What the loop-closure block does with the survivors of a pair:
+ *     if (li.size() >= 120) { auto lopt = find_E_ransac(K, li, lj, 4000, 2e-3, 80); ... }
+ * for every pair of a batch in one launch set per stage: K^-1 normalisation (:649-655), the seeded sampling (:657-665:
+ * std::mt19937(12345) + uniform_int_distribution, bit-exact index octets incl. the distribution's rejection loop),
+ * eight_point_E per octet (device solver: hypotheses equal to the reference's to ~1e-9, see sfmgpu_ransac_hypotheses),
+ * the scoring loop (:667-676: counts, winner, ascending inlier list - bit-exact for the hypotheses scored), the
+ * min_inliers test (:678) and the pose tail (:680-760; device arithmetic, R and t agree to ~1e-10).
+ * Passing the caller's own hypotheses (E_host, e.g. from the reference's solver) makes counts, winner and inlier lists
+ * bit-identical to find_E_ransac's. */
+typedef struct sfmgpu_ransac_cfg {
+  int iters;        /* hypotheses per pair: 4000 at :1856, 2500 at :1739 */
+  double thr;       /* Sampson threshold: 2e-3 / 1e-3 */
+  int min_inliers;  /* fewer inliers: no pose, std::nullopt (:678): 80 / 60 */
+  int min_points;   /* the caller's guard li.size() >= 120 (:1855); pairs below it are skipped; 0: none */
+} sfmgpu_ransac_cfg;
+/* Per-pair status after the stage. */
+#define SFMGPU_TV_SKIPPED 0 /* fewer than min_points survivors: find_E_ransac was not called */
+#define SFMGPU_TV_NONE 1    /* std::nullopt: fewer than 8 points, or the winner has fewer than min_inliers inliers */
+#define SFMGPU_TV_OK 2      /* R, t and the inlier list are valid */
+/* Make the stage part of sfmgpu_pair_frontend / sfmgpu_pair_frontend_host for this pairs object (rc == NULL: off again).
+ * K: 9 doubles row-major; a singular K is SFMGPU_E_ARG ("Singular K", :474). */
+int sfmgpu_pairs_set_ransac(sfmgpu_ctx* ctx, sfmgpu_pairs* p, const double* K, const sfmgpu_ransac_cfg* rc);
+/* Host arrays the streaming front end fills chunk by chunk when the stage is on: status / best_n [npairs], inliers
+ * [npairs][max_corners] (first best_n valid), R [npairs][9], t [npairs][3]; any may be NULL; pinned memory for overlap. */
+int sfmgpu_pairs_ransac_host_outputs(sfmgpu_ctx* ctx, sfmgpu_pairs* p, int32_t* status, int32_t* best_n, int32_t* inliers,
+                                     double* R, double* t);
+/* Run the stage now on the pairs of the last batch.  E_host: NULL (device solver) or [npairs][iters][9] hypotheses. */
+int sfmgpu_pairs_ransac(sfmgpu_ctx* ctx, sfmgpu_pairs* p, const double* K, const sfmgpu_ransac_cfg* rc, const double* E_host);
+/* One pair: status, winner (-1: none), its count, inlier indices ascending (into the pair's survivor list; cap entries of
+ * room), the winning hypothesis, R_ji, t_ji.  Any output may be NULL. */
+int sfmgpu_pairs_ransac_download(sfmgpu_ctx* ctx, sfmgpu_pairs* p, int pair, int* status, int* best_h, int* best_n,
+                                 int32_t* inliers, int cap, double* E9, double* R9, double* t3);
+/* All pairs of the last batch (layout as in sfmgpu_pairs_ransac_host_outputs). */
+int sfmgpu_pairs_ransac_download_all(sfmgpu_ctx* ctx, sfmgpu_pairs* p, int32_t* status, int32_t* best_n, int32_t* inliers,
+                                     double* R, double* t);
+/* Device addresses for NCCL gathers: status int32 [npairs], best int32 [npairs][2] = (winner, count), inliers int32
+ * [npairs][max_corners], R double [npairs][9], t double [npairs][3]. */
+int sfmgpu_pairs_ransac_device_ptrs(sfmgpu_pairs* p, void** status, void** best, void** inliers, void** R, void** t);
+/* `count` draws of std::uniform_int_distribution<int>(0, n-1) on std::mt19937(12345), produced by the device sampler. */
+int sfmgpu_ransac_sample(sfmgpu_ctx* ctx, int n, int count, int32_t* out);
 
 /* ---- stateful tracker: KLTTracker (:323-391) ----------------------------------------------------------
  * A track list never holds more than ROWS = max(max_tracks, min_tracks, 1) + 1 entries; `cap` arguments of that size

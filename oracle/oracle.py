@@ -59,6 +59,7 @@ class CpuFrontEnd:
             "pair_frontend": (i, [_u8p, _u8p, i, i, i, d, i, i, i, i, d, _f64p, _f64p, C.POINTER(i)]),
             "pair_frontend_mt": (C.c_long, [_u8p, i, i, i, i, d, i, i, i, i, d, i, C.POINTER(C.c_long)]),
             "ransac_score_mt": (i, [_f64p, _f64p, i, _f64p, i, d, _i32p, i]),
+            "two_view_mt": (C.c_long, [_u8p, i, i, i, i, d, i, i, i, i, d, vp, i, d, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
             "global_desc32": (i, [_u8p, i, i, _f32p]),
             "triangulate_dlt": (i, [_f64p, _f64p, i, _i32p, _i32p, _f64p, _f64p, i, _f64p]),
             "desc_search": (i, [_f32p, i, _f32p, _f32p, C.POINTER(i), C.POINTER(C.c_float)]),
@@ -239,6 +240,25 @@ class CpuFrontEnd:
                                      min_dist, levels, radius, iters, fb, li, lj, C.byref(nc))
         return li[:k].copy(), lj[:k].copy(), nc.value
 
+    def two_view_mt(self, frames, max_corners, threads, K=None, rs_iters=4000, rs_thr=2e-3, rs_min_inliers=80, min_points=120,
+                    quality=0.01, min_dist=8, levels=3, radius=5, iters=10, fb=1.0, detail=True):
+        """The whole two-view unit (:1836-1857) for every consecutive pair of `frames` on `threads` host threads: front end
+        plus `if (li.size() >= min_points) find_E_ransac(K, li, lj, rs_iters, rs_thr, rs_min_inliers)` (K None: front end
+        only).  Returns (corners processed, dict of per-pair arrays) - the dict is None when detail is False."""
+        f, h, w = frames.shape
+        P, cap = f - 1, max(1, max_corners)
+        out = None
+        if detail:
+            out = dict(n_corners=np.zeros(P, np.int32), n_kept=np.zeros(P, np.int32), li=np.zeros((P, cap, 2)), lj=np.zeros((P, cap, 2)),
+                       status=np.zeros(P, np.int32), n_inl=np.zeros(P, np.int32), inliers=np.zeros((P, cap), np.int32),
+                       R=np.zeros((P, 9)), t=np.zeros((P, 3)))
+        g = (lambda k: _p(out[k])) if detail else (lambda k: None)
+        Kc = None if K is None else np.ascontiguousarray(K, np.float64).reshape(9)
+        tracks = self._f("two_view_mt")(np.ascontiguousarray(frames).reshape(-1), f, w, h, max_corners, quality, min_dist, levels, radius,
+                                        iters, fb, _p(Kc), rs_iters, rs_thr, rs_min_inliers, min_points, threads, g("n_corners"),
+                                        g("n_kept"), g("li"), g("lj"), g("status"), g("n_inl"), g("inliers"), g("R"), g("t"))
+        return int(tracks), out
+
     def pair_frontend_mt(self, frames, max_corners, threads, quality=0.01, min_dist=8, levels=3, radius=5, iters=10,
                          fb=1.0):
         f, h, w = frames.shape
@@ -246,6 +266,10 @@ class CpuFrontEnd:
         tracks = self._f("pair_frontend_mt")(np.ascontiguousarray(frames).reshape(-1), f, w, h, max_corners, quality,
                                              min_dist, levels, radius, iters, fb, threads, C.byref(kept))
         return int(tracks), int(kept.value)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
 class _Tracker:

@@ -277,6 +277,49 @@ long ref_pair_frontend_mt(const uint8_t* frames, int nframes, int w, int h, int 
   return tt;
 }
 
+
+// The whole two-view unit (:1836-1857) for `npairs` independent pairs (frames[i], frames[i+1]) on `threads` host threads:
+// detect + fwd/bwd track + fb filter, then `if (li.size() >= min_points) find_E_ransac(K, li, lj, rs_iters, rs_thr,
+// rs_min_inliers)`.  Per pair: n_corners, n_kept, li / lj [max_corners][2], status (0 skipped, 1 nullopt, 2 pose),
+// n_inl, inliers [max_corners], R [9], t [3].  Any per-pair output may be null.  Returns the corners processed.
+long ref_two_view_mt(const uint8_t* frames, int nframes, int w, int h, int max_corners, double quality, int min_dist,
+                     int levels, int radius, int iters, double fb_thresh, const double* K, int rs_iters, double rs_thr,
+                     int rs_min_inliers, int min_points, int threads, int* n_corners, int* n_kept, double* li_out,
+                     double* lj_out, int* status, int* n_inl, int* inliers, double* R_out, double* t_out) {
+  const int npairs = nframes - 1;
+  const int cap = max_corners < 1 ? 1 : max_corners;
+  std::vector<long> tracks(threads, 0);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; t++) {
+    pool.emplace_back([&, t]() {
+      std::vector<double> li((size_t)2 * cap), lj((size_t)2 * cap);
+      std::vector<int> inl((size_t)cap);
+      for (int p = t; p < npairs; p += threads) {
+        int nc = 0;
+        const int k = ref_pair_frontend(frames + (size_t)p * w * h, frames + (size_t)(p + 1) * w * h, w, h, max_corners,
+                                        quality, min_dist, levels, radius, iters, fb_thresh, li.data(), lj.data(), &nc);
+        tracks[t] += nc;
+        int st = 0, ni = 0;
+        double R[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, tt[3] = {0, 0, 0};
+        if (K && k >= min_points) st = ref_find_E_ransac(K, li.data(), lj.data(), k, rs_iters, rs_thr, rs_min_inliers, R, tt, inl.data(), &ni) ? 2 : 1;
+        if (n_corners) n_corners[p] = nc;
+        if (n_kept) n_kept[p] = k;
+        if (li_out) std::copy(li.begin(), li.begin() + 2 * (size_t)k, li_out + (size_t)p * 2 * cap);
+        if (lj_out) std::copy(lj.begin(), lj.begin() + 2 * (size_t)k, lj_out + (size_t)p * 2 * cap);
+        if (status) status[p] = st;
+        if (n_inl) n_inl[p] = st == 2 ? ni : 0;
+        if (inliers && st == 2) std::copy(inl.begin(), inl.begin() + ni, inliers + (size_t)p * cap);
+        if (R_out) std::copy(R, R + 9, R_out + (size_t)p * 9);
+        if (t_out) std::copy(tt, tt + 3, t_out + (size_t)p * 3);
+      }
+    });
+  }
+  for (auto& th : pool) th.join();
+  long total = 0;
+  for (int t = 0; t < threads; t++) total += tracks[t];
+  return total;
+}
+
 // Multi-threaded scoring baseline: hypotheses split across threads.
 int ref_ransac_score_mt(const double* xi, const double* xj, int n, const double* E, int H, double thr, int* counts,
                         int threads) {

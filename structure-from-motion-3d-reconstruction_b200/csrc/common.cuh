@@ -68,7 +68,7 @@ struct sfmgpu_ctx {
   bool profile = false;
   struct StageEv { int stage; cudaEvent_t a, b; };
   std::vector<StageEv> stage_evs;
-  float stage_ms[4] = {0, 0, 0, 0};
+  float stage_ms[5] = {0, 0, 0, 0, 0};  // corner score, corner select, KLT, compaction, RANSAC stage
   void* pinned = nullptr;  // staging for small D2H results
   size_t pinned_cap = 0;
   // kernels whose >48 KB dynamic shared memory opt-in has been set ON THIS CONTEXT'S DEVICE (the attribute is per device)
@@ -87,6 +87,23 @@ int sfm_next_cfg_id();
       (ctx)->smem_cfg[(id)] = true;                                                                               \
     }                                                                                                             \
   } while (0)
+
+// Device-resident results of a batch of frame pairs (frontend.cu) and of their RANSAC stage (two_view.cu).
+struct TwoViewState;  // two_view.cu
+struct sfmgpu_pairs {
+  int max_pairs = 0, cap = 0;
+  double2 *xy0 = nullptr, *p1 = nullptr, *pb = nullptr, *li = nullptr, *lj = nullptr;
+  int *ncorn = nullptr, *nkept = nullptr, *nit = nullptr;
+  uint8_t* keep = nullptr;
+  unsigned long long* totals = nullptr;
+  DevBuf work[2];  // corner work areas (two, so that the stage pipeline can score one chunk while it selects another)
+  int last_npairs = 0;
+  TwoViewState* tv = nullptr;  // allocated by the first sfmgpu_pairs_ransac call
+};
+void sfm_two_view_free(sfmgpu_ctx* ctx, sfmgpu_pairs* p);
+bool sfm_two_view_enabled(const sfmgpu_pairs* p);
+int sfm_two_view_stage(sfmgpu_ctx* ctx, sfmgpu_pairs* p, int pair_off, int npairs, const double* E_host);
+int sfm_two_view_download(sfmgpu_ctx* ctx, sfmgpu_pairs* p, int pair_off, int npairs, cudaStream_t s);
 
 int sfm_fail(sfmgpu_ctx* ctx, int code, const char* fmt, ...);
 int sfm_reserve(sfmgpu_ctx* ctx, DevBuf& b, size_t bytes);
@@ -194,3 +211,10 @@ int sfm_corners_select_stage(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int count,
 int sfm_candidates_single(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int frame, double quality, int32_t* xy,
                           double* score, int cap, int* n_out, double* max_score);
 int sfm_sort_perm(sfmgpu_ctx* ctx, const double* keys, int n, int32_t* perm);
+// solver.cu / ransac.cu: batched over correspondence sets
+int sfm_eight_point_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, const int* npts, int n_single,
+                            int npairs, const int* idx8, int H, double* Eout);
+int sfm_pose_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, int npairs, const int* status,
+                     const int* best, const int* inl, const double* bestE, double* R, double* t);
+int sfm_ransac_score_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, const int* npts, int n_max,
+                             int npairs, const double* E, int H, double thr, int* counts, int* best, int* inl);

@@ -285,23 +285,23 @@ extern "C" int sfmgpu_profile(sfmgpu_ctx* ctx, int enable) {
   return 0;
 }
 
-extern "C" int sfmgpu_stage_times(sfmgpu_ctx* ctx, float* ms4) {
+extern "C" int sfmgpu_stage_times_n(sfmgpu_ctx* ctx, float* ms, int n) {
   SFM_ENTER(ctx);
-  if (!ctx || !ms4) return SFMGPU_E_ARG;
+  if (!ctx || !ms || n < 0) return SFMGPU_E_ARG;
   SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   for (auto& e : ctx->stage_evs) {
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess && e.stage >= 0 && e.stage < 4) ctx->stage_ms[e.stage] += ms;
+    float t = 0;
+    if (cudaEventElapsedTime(&t, e.a, e.b) == cudaSuccess && e.stage >= 0 && e.stage < 5) ctx->stage_ms[e.stage] += t;
     cudaEventDestroy(e.a);
     cudaEventDestroy(e.b);
   }
   ctx->stage_evs.clear();
-  for (int i = 0; i < 4; i++) {
-    ms4[i] = ctx->stage_ms[i];
-    ctx->stage_ms[i] = 0;
-  }
+  for (int i = 0; i < n; i++) ms[i] = i < 5 ? ctx->stage_ms[i] : 0.f;
+  for (int i = 0; i < 5; i++) ctx->stage_ms[i] = 0;
   return 0;
 }
+
+extern "C" int sfmgpu_stage_times(sfmgpu_ctx* ctx, float* ms4) { return sfmgpu_stage_times_n(ctx, ms4, 4); }
 
 // ---- fused pyramid kernel ------------------------------------------------------------------------------------
 // One thread owns a 16 x 4 block of the source level (four 16 B loads), emits 8 x 2 pixels of the next level

@@ -187,16 +187,6 @@ int default_cand_cap(int w, int h) {
 }  // namespace
 
 // ---- batched pair front end -------------------------------------------------------------------------------------------
-struct sfmgpu_pairs {
-  int max_pairs = 0, cap = 0;
-  double2 *xy0 = nullptr, *p1 = nullptr, *pb = nullptr, *li = nullptr, *lj = nullptr;
-  int *ncorn = nullptr, *nkept = nullptr, *nit = nullptr;
-  uint8_t* keep = nullptr;
-  unsigned long long* totals = nullptr;
-  DevBuf work[2];  // corner work areas (two, so that the stage pipeline can score one chunk while it selects another)
-  int last_npairs = 0;
-};
-
 extern "C" {
 
 int sfmgpu_pairs_create(sfmgpu_ctx* ctx, int max_pairs, int max_corners, sfmgpu_pairs** out) {
@@ -232,6 +222,7 @@ void sfmgpu_pairs_destroy(sfmgpu_ctx* ctx, sfmgpu_pairs* p) {
   SFM_ENTER_VOID(ctx);
   if (!p) return;
   if (ctx) cudaStreamSynchronize(ctx->stream);
+  sfm_two_view_free(ctx, p);
   void* ptrs[] = {p->xy0, p->p1, p->pb, p->li, p->lj, p->nit, p->keep, p->ncorn, p->nkept, p->totals, p->work[0].p, p->work[1].p};
   for (void* q : ptrs)
     if (q) cudaFree(q);
@@ -289,6 +280,10 @@ static int stage_klt(sfmgpu_ctx* ctx, const ChunkArgs& c) {
              out->ncorn + c.pair_off, out->cap, out->li + so, out->lj + so, (int*)nullptr, out->nkept + c.pair_off);
   SFM_LAUNCH(ctx, totals_kernel, 256, 256, 0, out->ncorn + c.pair_off, out->nkept + c.pair_off, out->nit + so, c.npairs, out->cap,
              out->totals);
+  if (sfm_two_view_enabled(out)) {  // the unit's last step: find_E_ransac on the survivors of every pair (:1855-1857)
+    StageTimer rt(ctx, 4);
+    SFM_TRY(sfm_two_view_stage(ctx, out, c.pair_off, c.npairs, nullptr));
+  }
   return 0;
 }
 
@@ -448,6 +443,39 @@ static int pair_args_ok(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int 
   return 0;
 }
 
+// Batch calls size the candidate lists for W*H/6 entries per frame.  A frame whose FINAL list is longer (flat or
+// weak-texture image: thr = 0 makes every pixel a candidate, :274-285) comes back with n_corners < 0; it is redone here
+// through the single-frame path, whose work area holds the worst case (W*H candidates), so the batch returns what the
+// reference returns for every frame.  Synchronises the context stream (the overflow flags are read on the host).
+// redone (optional) receives the pair slots that were recomputed.
+static int pair_fix_overflow(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int npairs, const sfmgpu_lkcfg* cfg, sfmgpu_pairs* out,
+                             std::vector<int>* redone) {
+  if (npairs <= 0) return 0;
+  SFM_TRY(sfm_pinned(ctx, (size_t)npairs * sizeof(int)));
+  int* hn = (int*)ctx->pinned;
+  SFM_CUDA(ctx, cudaMemcpyAsync(hn, out->ncorn, (size_t)npairs * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  std::vector<int> bad;
+  for (int p = 0; p < npairs; p++)
+    if (hn[p] < 0) bad.push_back(p);
+  if (bad.empty()) return 0;
+  const int full_cap = f->w * f->h, md = cfg->min_distance < 0 ? -cfg->min_distance : cfg->min_distance;
+  SFM_TRY(sfm_reserve(ctx, ctx->cs_work, sfm_corner_work_bytes_md(f->w, f->h, 1, full_cap, md)));
+  for (int p : bad) {
+    SFM_TRY(sfm_corners_batch(ctx, f, first_frame + p, 1, cfg->max_tracks, cfg->quality, cfg->min_distance, full_cap, ctx->cs_work.p,
+                              ctx->cs_work.cap, out->xy0 + (size_t)p * out->cap, out->ncorn + p));
+    ChunkArgs c = chunk_args(f, first_frame + p, p, 1, cfg, out, nullptr);
+    SFM_TRY(stage_klt(ctx, c));  // adds this pair's corners / survivors / iterations to the totals
+  }
+  SFM_CUDA(ctx, cudaMemcpyAsync(hn, out->ncorn, (size_t)npairs * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(ctx, cudaMemsetAsync(out->totals + 3, 0, sizeof(unsigned long long), ctx->stream));
+  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int p : bad)
+    if (hn[p] < 0) return sfm_fail(ctx, SFMGPU_E_CAPACITY, "pair_frontend: pair %d exceeded the full candidate capacity", p);
+  if (redone) *redone = bad;
+  return 0;
+}
+
 int sfmgpu_pipeline_set(sfmgpu_ctx* ctx, int pairs_per_chunk) {
   SFM_ENTER(ctx);
   if (!ctx) return SFMGPU_E_ARG;
@@ -464,8 +492,10 @@ int sfmgpu_pair_frontend(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int
   out->last_npairs = npairs;
   SFM_CUDA(ctx, cudaMemsetAsync(out->totals, 0, 64, ctx->stream));
   const int sub = ctx->pipe_chunk;
-  if (sub <= 0 || ctx->profile || npairs < 2 * sub)  // stage profiling wants the stages back to back on one stream
-    return pair_range(ctx, f, first_frame, 0, npairs, cfg, out);
+  if (sub <= 0 || ctx->profile || npairs < 2 * sub) {  // stage profiling wants the stages back to back on one stream
+    SFM_TRY(pair_range(ctx, f, first_frame, 0, npairs, cfg, out));
+    return pair_fix_overflow(ctx, f, first_frame, npairs, cfg, out, nullptr);
+  }
   SFM_TRY(pipe_streams(ctx));
   SFM_TRY(pipe_reserve(ctx, f, cfg, out, sub));
   Pipe p;
@@ -481,7 +511,7 @@ int sfmgpu_pair_frontend(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int
     SFM_TRY(pipe_chunk(p, f, first_frame + p0, p0, cnt, cfg, out, nullptr, &last));
   }
   SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, last, 0));  // the KLT stream is in order: its last event covers all chunks
-  return 0;
+  return pair_fix_overflow(ctx, f, first_frame, npairs, cfg, out, nullptr);
 }
 
 // Streaming variant for frames that live in HOST memory: frames [0, nframes) of `f` are filled from host_pix in
@@ -541,12 +571,24 @@ int sfmgpu_pair_frontend_host(sfmgpu_ctx* ctx, sfmgpu_frames* f, const uint8_t* 
       SFM_CUDA(ctx, cudaMemcpyAsync(lj_xy + 2 * o * cap, out->lj + o * cap, np_ * cap * 16, cudaMemcpyDeviceToHost, ctx->back_stream));
     if (n_kept) SFM_CUDA(ctx, cudaMemcpyAsync(n_kept + o, out->nkept + o, np_ * 4, cudaMemcpyDeviceToHost, ctx->back_stream));
     if (n_corners) SFM_CUDA(ctx, cudaMemcpyAsync(n_corners + o, out->ncorn + o, np_ * 4, cudaMemcpyDeviceToHost, ctx->back_stream));
+    if (sfm_two_view_enabled(out)) SFM_TRY(sfm_two_view_download(ctx, out, P0, P1 - P0, ctx->back_stream));
   }
   SFM_CUDA(ctx, cudaStreamSynchronize(ctx->back_stream));
   SFM_CUDA(ctx, cudaStreamSynchronize(ctx->klt_stream));
   SFM_CUDA(ctx, cudaStreamSynchronize(ctx->sel_stream));
   SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   p.trace_dump();
+  std::vector<int> redone;
+  SFM_TRY(pair_fix_overflow(ctx, f, 0, npairs, cfg, out, &redone));
+  for (int q : redone) {  // rare: frames redone with the full candidate capacity go back once more
+    const size_t o = (size_t)q;
+    if (li_xy) SFM_CUDA(ctx, cudaMemcpyAsync(li_xy + 2 * o * cap, out->li + o * cap, cap * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (lj_xy) SFM_CUDA(ctx, cudaMemcpyAsync(lj_xy + 2 * o * cap, out->lj + o * cap, cap * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_kept) SFM_CUDA(ctx, cudaMemcpyAsync(n_kept + o, out->nkept + o, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_corners) SFM_CUDA(ctx, cudaMemcpyAsync(n_corners + o, out->ncorn + o, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (sfm_two_view_enabled(out)) SFM_TRY(sfm_two_view_download(ctx, out, q, 1, ctx->stream));
+  }
+  if (!redone.empty()) SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 
@@ -575,6 +617,26 @@ int sfmgpu_pairs_download_all(sfmgpu_ctx* ctx, sfmgpu_pairs* p, double* li_xy, d
   if (n_kept) SFM_CUDA(ctx, cudaMemcpyAsync(n_kept, p->nkept, np_ * 4, cudaMemcpyDeviceToHost, ctx->stream));
   if (n_corners) SFM_CUDA(ctx, cudaMemcpyAsync(n_corners, p->ncorn, np_ * 4, cudaMemcpyDeviceToHost, ctx->stream));
   SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int sfmgpu_pairs_set_matches(sfmgpu_ctx* ctx, sfmgpu_pairs* p, int npairs, const double* li_xy, const double* lj_xy,
+                             const int32_t* n_kept) {
+  SFM_ENTER(ctx);
+  if (!ctx || !p || !n_kept || (npairs > 0 && (!li_xy || !lj_xy))) return SFMGPU_E_ARG;
+  if (npairs < 0 || npairs > p->max_pairs) return sfm_fail(ctx, SFMGPU_E_ARG, "pairs_set_matches: %d pairs, room for %d", npairs, p->max_pairs);
+  for (int k = 0; k < npairs; k++)
+    if (n_kept[k] < 0 || n_kept[k] > p->cap)
+      return sfm_fail(ctx, SFMGPU_E_ARG, "pairs_set_matches: pair %d has %d matches, room for %d", k, n_kept[k], p->cap);
+  const size_t n = (size_t)npairs * p->cap;
+  if (npairs > 0) {
+    SFM_CUDA(ctx, cudaMemcpyAsync(p->li, li_xy, n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    SFM_CUDA(ctx, cudaMemcpyAsync(p->lj, lj_xy, n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    SFM_CUDA(ctx, cudaMemcpyAsync(p->nkept, n_kept, (size_t)npairs * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SFM_CUDA(ctx, cudaMemcpyAsync(p->ncorn, n_kept, (size_t)npairs * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the caller's arrays may be pageable / reused
+  }
+  p->last_npairs = npairs;
   return 0;
 }
 

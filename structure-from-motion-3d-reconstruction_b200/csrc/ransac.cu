@@ -63,14 +63,24 @@ struct RsHyp {
   float qd;   // sqrt(64u) * Emax (rounded up)
 };
 
+// blockIdx.z = correspondence set ("pair") of a batch: points at xi/xj + pair * pt_stride, npts[pair] of them (npts == nullptr:
+// n_single), hypotheses E + pair * H * 9, counts + pair * H.  Sets with fewer than 8 points are not scored (:648).
 __global__ void __launch_bounds__(RS_THREADS) ransac_count_kernel(const double2* __restrict__ xi, const double2* __restrict__ xj,
-                                                                 int n, const double* __restrict__ E, int H, int h_per_block,
+                                                                 size_t pt_stride, const int* __restrict__ npts, int n_single,
+                                                                 const double* __restrict__ E, int H, int h_per_block,
                                                                  double thr, double thr_lo, double thr_hi, float thr_lo_f,
                                                                  float thr_hi_f, int* __restrict__ counts) {
   __shared__ double sE[RS_HCHUNK * 9];
   __shared__ RsHyp sH[RS_HCHUNK];
   __shared__ int sC[RS_HCHUNK];
   const int tid = threadIdx.x, lane = tid & 31;
+  const int pair = blockIdx.z;
+  const int n = npts ? npts[pair] : n_single;
+  if ((npts && n < 8) || (int)(blockIdx.x * RS_THREADS * RS_PTS) >= n) return;  // block-uniform
+  xi += (size_t)pair * pt_stride;
+  xj += (size_t)pair * pt_stride;
+  E += (size_t)pair * H * 9;
+  counts += (size_t)pair * H;
   const int p0 = (blockIdx.x * RS_THREADS + tid) * RS_PTS;
   double x[RS_PTS], y[RS_PTS], xp[RS_PTS], yp[RS_PTS];
   float xf[RS_PTS], yf[RS_PTS], xpf[RS_PTS], ypf[RS_PTS], pp[RS_PTS], pm[RS_PTS];
@@ -160,6 +170,8 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_count_kernel(const double2*
 // Winner: largest count, lowest index on ties; -1 when every count is 0 (best_inl starts empty, :673).
 __global__ void __launch_bounds__(1024) ransac_argmax_kernel(const int* __restrict__ counts, int H, int* __restrict__ best) {
   __shared__ unsigned long long sbest[32];
+  counts += (size_t)blockIdx.x * H;  // one block per correspondence set
+  best += 2 * blockIdx.x;
   // key = count << 32 | (0xFFFFFFFF - h): max key = max count then min h
   unsigned long long key = 0;
   for (int h = threadIdx.x; h < H; h += blockDim.x) {
@@ -189,13 +201,21 @@ __global__ void __launch_bounds__(1024) ransac_argmax_kernel(const int* __restri
 }
 
 // Inlier indices of the winner, ascending (:669-672), by one block with an ordered ballot compaction.
-__global__ void __launch_bounds__(1024) ransac_mask_kernel(const double2* __restrict__ xi, const double2* __restrict__ xj, int n,
-                                                          const double* __restrict__ E, const int* __restrict__ best, double thr,
+__global__ void __launch_bounds__(1024) ransac_mask_kernel(const double2* __restrict__ xi, const double2* __restrict__ xj,
+                                                          size_t pt_stride, const int* __restrict__ npts, int n_single,
+                                                          const double* __restrict__ E, int H, const int* __restrict__ best, double thr,
                                                           int* __restrict__ inl) {
   __shared__ int swarp[32];
   __shared__ int sbase;
+  const int pair = blockIdx.x;  // one block per correspondence set
+  const int n = npts ? npts[pair] : n_single;
+  xi += (size_t)pair * pt_stride;
+  xj += (size_t)pair * pt_stride;
+  E += (size_t)pair * H * 9;
+  inl += (size_t)pair * pt_stride;
+  best += 2 * pair;
   const int bh = best[0];
-  if (bh < 0) return;
+  if (bh < 0 || (npts && n < 8)) return;
   const double* e = E + (size_t)bh * 9;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) sbase = 0;
@@ -226,14 +246,20 @@ __global__ void __launch_bounds__(1024) ransac_mask_kernel(const double2* __rest
   }
 }
 
-int score_resident(sfmgpu_ctx* ctx, double thr) {
-  const int n = ctx->rs_n, H = ctx->rs_H;
-  SFM_CUDA(ctx, cudaMemsetAsync(ctx->rs_counts.p, 0, (size_t)(H > 0 ? H : 1) * sizeof(int), ctx->stream));
-  int* best = (int*)ctx->rs_best.p;
+}  // namespace
+
+// Scoring loop (:667-676) for `npairs` correspondence sets in one launch set: counts [npairs][H], best [npairs][2] =
+// (winner or -1, its count), inl [npairs][pt_stride] the winner's inlier indices ascending.  n_max bounds the points of a
+// set (grid size); npts (device, may be null: n_max points in every set) holds the actual numbers.
+int sfm_ransac_score_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, const int* npts, int n_max,
+                             int npairs, const double* E, int H, double thr, int* counts, int* best, int* inl) {
+  const int n = n_max;
+  if (npairs <= 0) return 0;
+  SFM_CUDA(ctx, cudaMemsetAsync(counts, 0, (size_t)npairs * (H > 0 ? H : 1) * sizeof(int), ctx->stream));
   if (H > 0 && n > 0) {
     const unsigned gx = sfm_cdiv(n, RS_THREADS * RS_PTS);
     // enough blocks to fill the machine several times over, whole chunks of hypotheses per block
-    long long want_y = ((long long)ctx->n_sm * 8 + gx - 1) / gx;
+    long long want_y = ((long long)ctx->n_sm * 8 + (long long)gx * npairs - 1) / ((long long)gx * npairs);
     long long hpb = (H + want_y - 1) / want_y;
     hpb = ((hpb + RS_HCHUNK - 1) / RS_HCHUNK) * RS_HCHUNK;
     const unsigned gy = sfm_cdiv(H, hpb);
@@ -250,15 +276,25 @@ int score_resident(sfmgpu_ctx* ctx, double thr) {
       tlo = -INFINITY;  // "a*a < -inf" never holds
       thi = INFINITY;   // "b*b > inf" never holds
     }
-    SFM_LAUNCH(ctx, ransac_count_kernel, dim3(gx, gy), RS_THREADS, 0, (const double2*)ctx->rs_xi.p, (const double2*)ctx->rs_xj.p,
-               n, (const double*)ctx->rs_E.p, H, (int)hpb, thr, thr * (1.0 - eps), thr * (1.0 + eps), tlo, thi,
-               (int*)ctx->rs_counts.p);
+    for (int z0 = 0; z0 < npairs; z0 += 65535) {  // grid.z limit
+      const int nz = npairs - z0 < 65535 ? npairs - z0 : 65535;
+      SFM_LAUNCH(ctx, ransac_count_kernel, dim3(gx, gy, nz), RS_THREADS, 0, xi + (size_t)z0 * pt_stride, xj + (size_t)z0 * pt_stride,
+                 pt_stride, npts ? npts + z0 : nullptr, n, E + (size_t)z0 * H * 9, H, (int)hpb, thr, thr * (1.0 - eps),
+                 thr * (1.0 + eps), tlo, thi, counts + (size_t)z0 * H);
+    }
   }
-  SFM_LAUNCH(ctx, ransac_argmax_kernel, 1, 1024, 0, (const int*)ctx->rs_counts.p, H, best);
+  SFM_LAUNCH(ctx, ransac_argmax_kernel, npairs, 1024, 0, (const int*)counts, H, best);
   if (H > 0 && n > 0)
-    SFM_LAUNCH(ctx, ransac_mask_kernel, 1, 1024, 0, (const double2*)ctx->rs_xi.p, (const double2*)ctx->rs_xj.p, n,
-               (const double*)ctx->rs_E.p, (const int*)best, thr, (int*)ctx->rs_inl.p);
+    SFM_LAUNCH(ctx, ransac_mask_kernel, npairs, 1024, 0, xi, xj, pt_stride, npts, n, E, H, (const int*)best, thr, inl);
   return 0;
+}
+
+namespace {
+
+int score_resident(sfmgpu_ctx* ctx, double thr) {
+  return sfm_ransac_score_batched(ctx, (const double2*)ctx->rs_xi.p, (const double2*)ctx->rs_xj.p, 0, nullptr, ctx->rs_n, 1,
+                                  (const double*)ctx->rs_E.p, ctx->rs_H, thr, (int*)ctx->rs_counts.p, (int*)ctx->rs_best.p,
+                                  (int*)ctx->rs_inl.p);
 }
 
 }  // namespace

@@ -66,48 +66,103 @@ __device__ __forceinline__ void unit3(double& x, double& y, double& z) {
   }
 }
 
-// eight_point_E for hypothesis h: rows of A from the 8 sampled correspondences, AtA, smallest eigenvector, rank 2.
-__global__ void __launch_bounds__(64) eight_point_kernel(const double2* __restrict__ xi, const double2* __restrict__ xj,
-                                                        const int* __restrict__ idx8, int H, int n, double* __restrict__ Eout) {
-  const int hyp = blockIdx.x * blockDim.x + threadIdx.x;
-  if (hyp >= H) return;
-  double A[72], G[81], Q[81];
-  for (int r = 0; r < 8; r++) {
-    int i = idx8[(size_t)hyp * 8 + r];
-    i = i < 0 ? 0 : (i >= n ? n - 1 : i);
-    const double2 a = xi[i], b = xj[i];
-    const double x = a.x, y = a.y, xp = b.x, yp = b.y;
-    double* row = A + r * 9;
-    row[0] = xp * x; row[1] = xp * y; row[2] = xp;
-    row[3] = yp * x; row[4] = yp * y; row[5] = yp;
-    row[6] = x;      row[7] = y;      row[8] = 1.0;
-  }
-  for (int i = 0; i < 9; i++)
-    for (int j = i; j < 9; j++) {
-      double s = 0;
-      for (int r = 0; r < 8; r++) s += A[r * 9 + i] * A[r * 9 + j];
-      G[i * 9 + j] = s;
-      G[j * 9 + i] = s;
-    }
-  jacobi_dev<9>(G, Q, 120);
-  // eigenvalues ascending: column of the smallest diagonal entry (first one on ties, like a stable sort)
-  int m = 0;
-  for (int i = 1; i < 9; i++)
-    if (G[i * 9 + i] < G[m * 9 + m]) m = i;
-  double E0[9];
-  for (int r = 0; r < 9; r++) E0[r] = Q[r * 9 + m];
+// ---- 8-point solver: one thread per hypothesis, working set in shared memory ------------------------------------------------
+// The 9x9 Gram matrix is symmetric and the reference's row-then-column rotation keeps it EXACTLY symmetric outside the
+// 2x2 pivot block (entry (k,p) gets only the column update c*a_kp - s*a_kq, entry (p,k) only the row update
+// c*a_pk - s*a_qk: same operands, same operations), so the packed upper triangle (45 doubles) carries the whole state.
+// It lives in shared memory, thread-interleaved (element e of thread t at e*TPB + t): every lane owns its own pair of
+// banks, so the data-dependent pivot indices never conflict.  The eigenvector matrix is not accumulated: the rotations
+// are recorded (c, s, p, q) and applied backwards to the unit vector of the smallest eigenvalue - 4 instead of 54
+// multiply-adds per rotation (V = J1 J2 ... Jn, column m = J1 (J2 (... (Jn e_m)))).
+// The rotation angle phi = atan2(2 a_pq, a_qq - a_pp) / 2 is evaluated algebraically (half-angle formulas, 1 sqrt + 1 div +
+// 1 sqrt + 1 div) instead of atan2 / sincos: cos and sin agree with libm's to a few ulp, which is the same class of
+// deviation CUDA's own trigonometry has against glibc's.
+constexpr int SV_TPB = 128;
+constexpr int SV_TRI = 45;
+constexpr int SV_ROT9 = 120, SV_ROT3 = 80;  // the reference's rotation caps (:622, :551)
 
-  // svd3(E0) through eig(E0^T E0); singular values descending (stable), U re-orthonormalised, u2 = u0 x u1
+__device__ __forceinline__ int tri_idx(int i, int j) { return (i * (17 - i)) / 2 + j; }  // i <= j < 9
+
+__device__ __forceinline__ void half_angle(double y, double x, double& c, double& s) {
+  const double r = sqrt(x * x + y * y);
+  if (!(r > 0.0)) {  // atan2(0, 0) = 0
+    c = 1.0;
+    s = 0.0;
+    return;
+  }
+  const double ct = x / r;
+  if (x >= 0.0) {
+    c = sqrt(0.5 * (1.0 + ct));
+    s = (y / r) / (2.0 * c);
+  } else {
+    const double sa = sqrt(0.5 * (1.0 - ct));
+    s = copysign(sa, y);
+    c = (fabs(y) / r) / (2.0 * sa);
+  }
+}
+
+// One rotation of a 3x3 symmetric problem held in registers, pivot (P, Q) static: rows, columns, zero, V (the
+// reference's order, linalg.hpp:164-188).
+template <int P, int Q>
+__device__ __forceinline__ void rot3(double* A, double* V) {
+  double c, s;
+  half_angle(2.0 * A[P * 3 + Q], A[Q * 3 + Q] - A[P * 3 + P], c, s);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const double u = A[P * 3 + k], v = A[Q * 3 + k];
+    A[P * 3 + k] = c * u - s * v;
+    A[Q * 3 + k] = s * u + c * v;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const double u = A[k * 3 + P], v = A[k * 3 + Q];
+    A[k * 3 + P] = c * u - s * v;
+    A[k * 3 + Q] = s * u + c * v;
+  }
+  A[P * 3 + Q] = 0.0;
+  A[Q * 3 + P] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const double u = V[k * 3 + P], v = V[k * 3 + Q];
+    V[k * 3 + P] = c * u - s * v;
+    V[k * 3 + Q] = s * u + c * v;
+  }
+}
+
+__device__ __forceinline__ void jacobi3(double* A, double* V) {
+#pragma unroll
+  for (int i = 0; i < 9; i++) V[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  for (int it = 0; it < SV_ROT3; it++) {
+    const double a01 = fabs(A[1]), a02 = fabs(A[2]), a12 = fabs(A[5]);
+    int piv = 0;
+    double big = 0.0;
+    if (a01 > big) { big = a01; piv = 0; }
+    if (a02 > big) { big = a02; piv = 1; }
+    if (a12 > big) { big = a12; piv = 2; }
+    if (big < 1e-12) break;
+    if (piv == 0) rot3<0, 1>(A, V);
+    else if (piv == 1) rot3<0, 2>(A, V);
+    else rot3<1, 2>(A, V);
+  }
+}
+
+// svd3 (:537-593) of E0 (row-major): singular values descending in s, V (columns), the first two columns of the
+// re-orthonormalised U (the third never contributes to U diag(s0, s1, 0) V^T; u2 = u0 x u1 is returned for the pose tail).
+__device__ __forceinline__ void svd3_dev(const double* E0, double* U, double* s, double* V) {
   double G3[9], V3[9];
+#pragma unroll
   for (int r = 0; r < 3; r++)
+#pragma unroll
     for (int c = 0; c < 3; c++) {
       double t = 0;
+#pragma unroll
       for (int k = 0; k < 3; k++) t += E0[3 * k + r] * E0[3 * k + c];
       G3[3 * r + c] = t;
     }
-  jacobi_dev<3>(G3, V3, 80);
+  jacobi3(G3, V3);
   // jacobi's ascending order first (stable on the diagonal), then the descending order of sqrt(max(0, w))
   int asc[3] = {0, 1, 2};
+#pragma unroll
   for (int i = 1; i < 3; i++)
     for (int j = i; j > 0 && G3[asc[j] * 4] < G3[asc[j - 1] * 4]; j--) {
       const int t = asc[j];
@@ -115,20 +170,25 @@ __global__ void __launch_bounds__(64) eight_point_kernel(const double2* __restri
       asc[j - 1] = t;
     }
   double sv[3];
+#pragma unroll
   for (int c = 0; c < 3; c++) sv[c] = sqrt(fmax(0.0, G3[asc[c] * 4]));
   int ord[3] = {0, 1, 2};
+#pragma unroll
   for (int i = 1; i < 3; i++)
     for (int j = i; j > 0 && sv[ord[j]] > sv[ord[j - 1]]; j--) {
       const int t = ord[j];
       ord[j] = ord[j - 1];
       ord[j - 1] = t;
     }
-  double s[3], V[9];
+#pragma unroll
   for (int c = 0; c < 3; c++) {
     s[c] = sv[ord[c]];
-    for (int r = 0; r < 3; r++) V[3 * r + c] = V3[3 * r + asc[ord[c]]];
+    const int src = asc[ord[c]];
+#pragma unroll
+    for (int r = 0; r < 3; r++) V[3 * r + c] = V3[3 * r + src];
   }
   double u[3][3];
+#pragma unroll
   for (int c = 0; c < 3; c++) {
     const double vx = V[c], vy = V[3 + c], vz = V[6 + c];
     double tx = E0[0] * vx + E0[1] * vy + E0[2] * vz, ty = E0[3] * vx + E0[4] * vy + E0[5] * vz,
@@ -147,18 +207,129 @@ __global__ void __launch_bounds__(64) eight_point_kernel(const double2* __restri
   const double d01 = u0x * u[1][0] + u0y * u[1][1] + u0z * u[1][2];
   double u1x = u[1][0] - d01 * u0x, u1y = u[1][1] - d01 * u0y, u1z = u[1][2] - d01 * u0z;
   unit3(u1x, u1y, u1z);
-  // E = U diag(s0, s1, 0) V^T: the third column of U never contributes
-  double* E = Eout + (size_t)hyp * 9;
-  const double U0[3] = {u0x, u0y, u0z}, U1[3] = {u1x, u1y, u1z};
+  double u2x = u0y * u1z - u0z * u1y, u2y = u0z * u1x - u0x * u1z, u2z = u0x * u1y - u0y * u1x;
+  unit3(u2x, u2y, u2z);
+  U[0] = u0x; U[3] = u0y; U[6] = u0z;
+  U[1] = u1x; U[4] = u1y; U[7] = u1z;
+  U[2] = u2x; U[5] = u2y; U[8] = u2z;
+}
+
+// eight_point_E (:609-627) for one index octet; sA = this thread's shared-memory column (stride TPB doubles).
+template <int TPB>
+__device__ void eight_point_solve(const double2* __restrict__ xi, const double2* __restrict__ xj, const int* __restrict__ idx8, int n,
+                                  double* sA, double* __restrict__ E) {
+  {
+    // Gram matrix of the 8 x 9 design matrix, every entry summed over the rows in order (AtA_from_A :503-517)
+    double g[SV_TRI];
+#pragma unroll
+    for (int e = 0; e < SV_TRI; e++) g[e] = 0.0;
+#pragma unroll 1
+    for (int r = 0; r < 8; r++) {
+      int i = idx8[r];
+      i = i < 0 ? 0 : (i >= n ? n - 1 : i);
+      const double2 a = xi[i], b = xj[i];
+      const double row[9] = {b.x * a.x, b.x * a.y, b.x, b.y * a.x, b.y * a.y, b.y, a.x, a.y, 1.0};
+#pragma unroll
+      for (int p = 0; p < 9; p++)
+#pragma unroll
+        for (int q = p; q < 9; q++) g[(p * (17 - p)) / 2 + q] += row[p] * row[q];
+    }
+#pragma unroll
+    for (int e = 0; e < SV_TRI; e++) sA[e * TPB] = g[e];
+  }
+  double rc[SV_ROT9], rs[SV_ROT9];
+  unsigned char rpq[SV_ROT9];
+  int nrot = 0;
+  for (; nrot < SV_ROT9; nrot++) {
+    // largest off-diagonal, first in raster order (strict >)
+    int p = 0, q = 1;
+    double big = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; i++)
+#pragma unroll
+      for (int j = i + 1; j < 9; j++) {
+        const double v = fabs(sA[((i * (17 - i)) / 2 + j) * TPB]);
+        if (v > big) {
+          big = v;
+          p = i;
+          q = j;
+        }
+      }
+    if (big < 1e-12) break;
+    const int ipp = tri_idx(p, p), iqq = tri_idx(q, q), ipq = tri_idx(p, q);
+    const double app = sA[ipp * TPB], aqq = sA[iqq * TPB], apq = sA[ipq * TPB];
+    double c, s;
+    half_angle(2.0 * apq, aqq - app, c, s);
+    rc[nrot] = c;
+    rs[nrot] = s;
+    rpq[nrot] = (unsigned char)(p * 16 + q);
+    for (int k = 0; k < 9; k++) {
+      if (k == p || k == q) continue;
+      const int ikp = k < p ? tri_idx(k, p) : tri_idx(p, k), ikq = k < q ? tri_idx(k, q) : tri_idx(q, k);
+      const double u = sA[ikp * TPB], v = sA[ikq * TPB];
+      sA[ikp * TPB] = c * u - s * v;
+      sA[ikq * TPB] = s * u + c * v;
+    }
+    // the pivot block sees both updates (rows first, then columns)
+    const double tpp = c * app - s * apq, tpq = c * apq - s * aqq, tqp = s * app + c * apq, tqq = s * apq + c * aqq;
+    sA[ipp * TPB] = c * tpp - s * tpq;
+    sA[iqq * TPB] = s * tqp + c * tqq;
+    sA[ipq * TPB] = 0.0;
+  }
+  // eigenvalues ascending: the smallest diagonal entry (first one on ties, like the stable sort of linalg.hpp:190-193)
+  int m = 0;
+  {
+    double best = sA[0];
+#pragma unroll
+    for (int i = 1; i < 9; i++) {
+      const double d = sA[((i * (17 - i)) / 2 + i) * TPB];
+      if (d < best) {
+        best = d;
+        m = i;
+      }
+    }
+  }
+  // column m of V = J1 J2 ... Jn, rotations applied backwards to e_m (elements 0..8 of the thread's column reused)
+#pragma unroll
+  for (int i = 0; i < 9; i++) sA[i * TPB] = i == m ? 1.0 : 0.0;
+  for (int r = nrot - 1; r >= 0; r--) {
+    const int p = rpq[r] >> 4, q = rpq[r] & 15;
+    const double c = rc[r], s = rs[r];
+    const double u = sA[p * TPB], v = sA[q * TPB];
+    sA[p * TPB] = c * u + s * v;
+    sA[q * TPB] = c * v - s * u;
+  }
+  double E0[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) E0[i] = sA[i * TPB];
+  // enforce_rank2 (:595-607): E = U diag(s0, s1, 0) V^T
+  double U[9], sv[3], V[9];
+  svd3_dev(E0, U, sv, V);
+#pragma unroll
   for (int r = 0; r < 3; r++)
+#pragma unroll
     for (int c = 0; c < 3; c++) {
       // (U S)(r,k) = U(r,k) s_k ; row-by-column products in the reference's order (k = 0, 1, 2 with a zero third term)
       double acc = 0;
-      acc += (U0[r] * s[0]) * V[3 * c + 0];
-      acc += (U1[r] * s[1]) * V[3 * c + 1];
+      acc += (U[3 * r] * sv[0]) * V[3 * c + 0];
+      acc += (U[3 * r + 1] * sv[1]) * V[3 * c + 1];
       acc += 0.0 * V[3 * c + 2];
       E[3 * r + c] = acc;
     }
+}
+
+// Hypothesis h of pair blockIdx.y: octet idx8[pair][h][8], points xi/xj[pair * stride ...], n = npts[pair] (npts == nullptr:
+// n_single); pairs with fewer than 8 points produce nothing.
+__global__ void __launch_bounds__(SV_TPB, 3) eight_point_kernel(const double2* __restrict__ xi, const double2* __restrict__ xj,
+                                                               size_t pt_stride, const int* __restrict__ npts, int n_single,
+                                                               const int* __restrict__ idx8, int H, double* __restrict__ Eout) {
+  extern __shared__ double sv_smem[];
+  const int pair = blockIdx.y, hyp = blockIdx.x * SV_TPB + threadIdx.x;
+  const int n = npts ? npts[pair] : n_single;
+  if (hyp >= H || n < 8) return;
+  const size_t ho = (size_t)pair * H + hyp;
+  eight_point_solve<SV_TPB>(xi + (size_t)pair * pt_stride, xj + (size_t)pair * pt_stride, idx8 + ho * 8, n, sv_smem + threadIdx.x,
+                            Eout + ho * 9);
 }
 
 // Batched triangulate_dlt (:1477-1516), one thread per track.  Same formulas and order as the host
@@ -209,6 +380,115 @@ __global__ void __launch_bounds__(128) triangulate_kernel(const double* __restri
 
 }  // namespace
 
+// ---- pose recovery, batched (find_E_ransac tail :680-760): one block per correspondence set --------------------------------
+// E -> (R1, R2) x (+t, -t) by svd3, cheirality vote over the first min(best_n, 20) inliers (two-view DLT through a 4x4
+// Jacobi each), first candidate with the strictly largest vote wins.  Device trigonometry-free Jacobi (half-angle form)
+// for svd3, CUDA trig in jacobi_dev<4>: R, t agree with the host tail to ~1e-10, not bit for bit.
+// status[pair] must be 2 (a pose is wanted); E = bestE [npairs][9]; writes R [npairs][9], t [npairs][3].
+__global__ void __launch_bounds__(96) pose_kernel(const double2* __restrict__ xi, const double2* __restrict__ xj, size_t pt_stride,
+                                                  const int* __restrict__ status, const int* __restrict__ best,
+                                                  const int* __restrict__ inl, const double* __restrict__ bestE, double* __restrict__ Rout,
+                                                  double* __restrict__ tout) {
+  __shared__ double sR[2][9];
+  __shared__ double st[3];
+  __shared__ int votes[4];
+  const int pair = blockIdx.x, tid = threadIdx.x;
+  if (status[pair] != 2) return;
+  xi += (size_t)pair * pt_stride;
+  xj += (size_t)pair * pt_stride;
+  inl += (size_t)pair * pt_stride;
+  if (tid < 4) votes[tid] = 0;
+  if (tid == 0) {
+    double E[9], U[9], sv[3], V[9];
+    for (int i = 0; i < 9; i++) E[i] = bestE[(size_t)pair * 9 + i];
+    svd3_dev(E, U, sv, V);
+    // R1 = (U W) V^T, R2 = (U W^T) V^T with W = [0 -1 0; 1 0 0; 0 0 1]: U W = [u1, -u0, u2], U W^T = [-u1, u0, u2] (columns)
+    for (int which = 0; which < 2; which++) {
+      const double sg = which == 0 ? 1.0 : -1.0;
+      double UW[9];
+      for (int r = 0; r < 3; r++) {
+        UW[3 * r + 0] = sg * U[3 * r + 1];
+        UW[3 * r + 1] = -sg * U[3 * r + 0];
+        UW[3 * r + 2] = U[3 * r + 2];
+      }
+      double R[9];
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) {
+          double acc = 0;
+          for (int k = 0; k < 3; k++) acc += UW[3 * r + k] * V[3 * c + k];  // V^T(k, c) = V(c, k)
+          R[3 * r + c] = acc;
+        }
+      const double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
+      for (int i = 0; i < 9; i++) sR[which][i] = det < 0 ? -R[i] : R[i];
+    }
+    double tx = U[2], ty = U[5], tz = U[8];
+    unit3(tx, ty, tz);
+    st[0] = tx; st[1] = ty; st[2] = tz;
+  }
+  __syncthreads();
+  const int bn = best[2 * pair + 1];
+  const int M = bn < 20 ? bn : 20;
+  if (tid < 4 * M) {
+    const int cand = tid / M, k = tid - cand * M;
+    const double* R = sR[cand >> 1];
+    const double sg = (cand & 1) ? -1.0 : 1.0;
+    const double t0 = sg * st[0], t1 = sg * st[1], t2 = sg * st[2];
+    const int i = inl[k];
+    const double2 x = xi[i], xp = xj[i];
+    double A[16], G[16], Q[16];
+    A[0] = -1; A[1] = 0; A[2] = x.x; A[3] = 0;
+    A[4] = 0; A[5] = -1; A[6] = x.y; A[7] = 0;
+    A[8] = xp.x * R[6] - R[0]; A[9] = xp.x * R[7] - R[1]; A[10] = xp.x * R[8] - R[2]; A[11] = xp.x * t2 - t0;
+    A[12] = xp.y * R[6] - R[3]; A[13] = xp.y * R[7] - R[4]; A[14] = xp.y * R[8] - R[5]; A[15] = xp.y * t2 - t1;
+    for (int a = 0; a < 4; a++)
+      for (int b = a; b < 4; b++) {
+        double acc = 0;
+        for (int r = 0; r < 4; r++) acc += A[r * 4 + a] * A[r * 4 + b];
+        G[a * 4 + b] = acc;
+        G[b * 4 + a] = acc;
+      }
+    jacobi_dev<4>(G, Q, 80);
+    int m = 0;
+    for (int a = 1; a < 4; a++)
+      if (G[a * 5] < G[m * 5]) m = a;
+    const double w = Q[12 + m];
+    const double X0 = Q[m] / w, X1 = Q[4 + m] / w, X2 = Q[8 + m] / w;
+    const double z2 = (R[6] * X0 + R[7] * X1 + R[8] * X2) + t2;
+    if (X2 > 0 && z2 > 0) atomicAdd(&votes[cand], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int bi = 0, bok = -1;
+    for (int c = 0; c < 4; c++)
+      if (votes[c] > bok) {
+        bok = votes[c];
+        bi = c;
+      }
+    const double sg = (bi & 1) ? -1.0 : 1.0;
+    for (int i = 0; i < 9; i++) Rout[(size_t)pair * 9 + i] = sR[bi >> 1][i];
+    for (int i = 0; i < 3; i++) tout[(size_t)pair * 3 + i] = sg * st[i];
+  }
+}
+
+int sfm_pose_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, int npairs, const int* status,
+                     const int* best, const int* inl, const double* bestE, double* R, double* t) {
+  if (npairs <= 0) return 0;
+  SFM_LAUNCH(ctx, pose_kernel, npairs, 96, 0, xi, xj, pt_stride, status, best, inl, bestE, R, t);
+  return 0;
+}
+
+// Hypotheses for `npairs` correspondence sets in one launch: xi/xj + pair * pt_stride, npts[pair] points (npts may be null:
+// n_single for all), idx8 [npairs][H][8], Eout [npairs][H][9].
+int sfm_eight_point_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, const int* npts, int n_single,
+                            int npairs, const int* idx8, int H, double* Eout) {
+  if (npairs <= 0 || H <= 0) return 0;
+  static const int cfg_id = sfm_next_cfg_id();
+  const size_t smem = (size_t)SV_TRI * SV_TPB * sizeof(double);
+  SFM_SMEM_OPTIN(ctx, cfg_id, eight_point_kernel, smem);
+  SFM_LAUNCH(ctx, eight_point_kernel, dim3(sfm_cdiv(H, SV_TPB), npairs), SV_TPB, smem, xi, xj, pt_stride, npts, n_single, idx8, H, Eout);
+  return 0;
+}
+
 extern "C" int sfmgpu_triangulate_dlt(sfmgpu_ctx* ctx, const double* K, const double* poses, int P, const int32_t* ia, const int32_t* ib,
                                       const double* ui_xy, const double* uj_xy, int n, double* X_out) {
   SFM_ENTER(ctx);
@@ -258,8 +538,8 @@ extern "C" int sfmgpu_ransac_hypotheses(sfmgpu_ctx* ctx, const double* xi_xy, co
   ctx->rs_H = H;
   if (H == 0) return 0;
   SFM_CUDA(ctx, cudaMemcpyAsync(ctx->rs_idx8.p, idx8, (size_t)H * 32, cudaMemcpyHostToDevice, ctx->stream));
-  SFM_LAUNCH(ctx, eight_point_kernel, sfm_cdiv(H, 64), 64, 0, (const double2*)ctx->rs_xi.p, (const double2*)ctx->rs_xj.p,
-             (const int*)ctx->rs_idx8.p, H, n, (double*)ctx->rs_E.p);
+  SFM_TRY(sfm_eight_point_batched(ctx, (const double2*)ctx->rs_xi.p, (const double2*)ctx->rs_xj.p, 0, nullptr, n, 1,
+                                  (const int*)ctx->rs_idx8.p, H, (double*)ctx->rs_E.p));
   if (E_out) {
     SFM_CUDA(ctx, cudaMemcpyAsync(E_out, ctx->rs_E.p, (size_t)H * 72, cudaMemcpyDeviceToHost, ctx->stream));
     SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

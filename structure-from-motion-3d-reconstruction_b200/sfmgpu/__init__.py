@@ -35,7 +35,15 @@ SYMBOLS = [
     "sfmgpu_multitracker_totals",
     "sfmgpu_ransac_score", "sfmgpu_ransac_upload", "sfmgpu_ransac_score_resident", "sfmgpu_ransac_download",
     "sfmgpu_ransac_hypotheses", "sfmgpu_global_desc32", "sfmgpu_desc_search", "sfmgpu_triangulate_dlt",
+    "sfmgpu_stage_times_n", "sfmgpu_pairs_set_ransac", "sfmgpu_pairs_ransac_host_outputs", "sfmgpu_pairs_ransac",
+    "sfmgpu_pairs_ransac_download", "sfmgpu_pairs_ransac_download_all", "sfmgpu_pairs_ransac_device_ptrs", "sfmgpu_ransac_sample",
+    "sfmgpu_pairs_set_matches",
 ]
+
+
+class RansacCfg(C.Structure):
+    """sfmgpu_ransac_cfg: the arguments of find_E_ransac(K, li, lj, iters, thr, min_inliers) plus the caller's size guard."""
+    _fields_ = [("iters", _i), ("thr", _d), ("min_inliers", _i), ("min_points", _i)]
 
 
 class LKCfg(C.Structure):
@@ -131,6 +139,15 @@ def load_library():
         "sfmgpu_global_desc32": (_i, [_vp, _vp, _i, _i, _vp]),
         "sfmgpu_desc_search": (_i, [_vp, _vp, _i, _vp, _vp, C.POINTER(_i), C.POINTER(C.c_float)]),
         "sfmgpu_ransac_hypotheses": (_i, [_vp, _f64p, _f64p, _i, _i32p, _i, _vp]),
+        "sfmgpu_stage_times_n": (_i, [_vp, C.POINTER(C.c_float), _i]),
+        "sfmgpu_pairs_set_ransac": (_i, [_vp, _vp, _vp, C.POINTER(RansacCfg)]),
+        "sfmgpu_pairs_ransac_host_outputs": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+        "sfmgpu_pairs_ransac": (_i, [_vp, _vp, _f64p, C.POINTER(RansacCfg), _vp]),
+        "sfmgpu_pairs_ransac_download": (_i, [_vp, _vp, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _vp, _i, _vp, _vp, _vp]),
+        "sfmgpu_pairs_ransac_download_all": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+        "sfmgpu_pairs_ransac_device_ptrs": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+        "sfmgpu_ransac_sample": (_i, [_vp, _i, _i, _i32p]),
+        "sfmgpu_pairs_set_matches": (_i, [_vp, _vp, _i, _f64p, _f64p, _i32p]),
     }
     for name, (res, args) in S.items():
         fn = getattr(lib, name)
@@ -203,9 +220,15 @@ class Context:
         self._ck(self.lib.sfmgpu_profile(self.h, int(on)))
 
     def stage_times(self):
-        ms = (C.c_float * 4)()
-        self._ck(self.lib.sfmgpu_stage_times(self.h, ms))
-        return dict(corner_score=ms[0], corner_select=ms[1], klt=ms[2], compact=ms[3])
+        ms = (C.c_float * 5)()
+        self._ck(self.lib.sfmgpu_stage_times_n(self.h, ms, 5))
+        return dict(corner_score=ms[0], corner_select=ms[1], klt=ms[2], compact=ms[3], ransac=ms[4])
+
+    def ransac_sample(self, n, count):
+        """count draws of uniform_int_distribution<int>(0, n-1) on mt19937(12345), from the device sampler."""
+        out = np.zeros(max(count, 1), np.int32)
+        self._ck(self.lib.sfmgpu_ransac_sample(self.h, n, count, out))
+        return out[:count]
 
     def fp64_peak(self):
         t = _d(0)
@@ -446,6 +469,69 @@ class Pairs:
                 torch.as_tensor(_View(lj, (npairs, self.cap, 2), "<f8"), device=dev),
                 torch.as_tensor(_View(nk, (npairs,), "<i4"), device=dev),
                 torch.as_tensor(_View(nc, (npairs,), "<i4"), device=dev))
+
+    # ---- RANSAC stage of the two-view unit (find_E_ransac per pair) ----------------------------------------------------
+    def set_ransac(self, K, iters=4000, thr=2e-3, min_inliers=80, min_points=120):
+        """Make find_E_ransac(K, li, lj, iters, thr, min_inliers) part of run() / run_host() (K None: off again)."""
+        if K is None:
+            self.ctx._ck(self.ctx.lib.sfmgpu_pairs_set_ransac(self.ctx.h, self.h_, None, None))
+            return
+        K = np.ascontiguousarray(K, np.float64).reshape(9)
+        rc = RansacCfg(iters, thr, min_inliers, min_points)
+        self.ctx._ck(self.ctx.lib.sfmgpu_pairs_set_ransac(self.ctx.h, self.h_, K.ctypes.data_as(_vp), C.byref(rc)))
+
+    def set_matches(self, li_list, lj_list):
+        """Correspondences from elsewhere than the tracker: one (n_k, 2) array pair per slot; they become the last batch."""
+        P = len(li_list)
+        li, lj = np.zeros((max(P, 1), self.cap, 2)), np.zeros((max(P, 1), self.cap, 2))
+        nk = np.zeros(max(P, 1), np.int32)
+        for k, (a, b) in enumerate(zip(li_list, lj_list)):
+            a, b = np.asarray(a, np.float64).reshape(-1, 2), np.asarray(b, np.float64).reshape(-1, 2)
+            nk[k] = len(a)
+            li[k, :len(a)], lj[k, :len(b)] = a, b
+        self.ctx._ck(self.ctx.lib.sfmgpu_pairs_set_matches(self.ctx.h, self.h_, P, li, lj, nk))
+
+    def ransac_host_outputs(self, status=None, best_n=None, inliers=None, R=None, t=None):
+        self._tv_host = (status, best_n, inliers, R, t)  # keep the arrays alive
+        self.ctx._ck(self.ctx.lib.sfmgpu_pairs_ransac_host_outputs(self.ctx.h, self.h_, _ptr(status), _ptr(best_n), _ptr(inliers),
+                                                                   _ptr(R), _ptr(t)))
+
+    def ransac(self, K, iters=4000, thr=2e-3, min_inliers=80, min_points=120, E_host=None):
+        """Run the stage now on the last batch.  E_host [npairs, iters, 9]: the caller's hypotheses (bit-identical path)."""
+        K = np.ascontiguousarray(K, np.float64).reshape(9)
+        rc = RansacCfg(iters, thr, min_inliers, min_points)
+        if E_host is not None:
+            E_host = np.ascontiguousarray(E_host, np.float64)
+        self.ctx._ck(self.ctx.lib.sfmgpu_pairs_ransac(self.ctx.h, self.h_, K, C.byref(rc), _ptr(E_host)))
+
+    def ransac_download(self, pair):
+        """(status, best_h, inlier indices, E [3,3], R [3,3], t [3]) of one pair."""
+        st, bh, bn = _i(0), _i(-1), _i(0)
+        inl = np.zeros(self.cap, np.int32)
+        E, R, t = np.zeros(9), np.zeros(9), np.zeros(3)
+        self.ctx._ck(self.ctx.lib.sfmgpu_pairs_ransac_download(self.ctx.h, self.h_, pair, C.byref(st), C.byref(bh), C.byref(bn), _ptr(inl),
+                                                               self.cap, _ptr(E), _ptr(R), _ptr(t)))
+        return st.value, bh.value, inl[:max(bn.value, 0)].copy(), E.reshape(3, 3), R.reshape(3, 3), t
+
+    def ransac_download_all(self, status=None, best_n=None, inliers=None, R=None, t=None):
+        self.ctx._ck(self.ctx.lib.sfmgpu_pairs_ransac_download_all(self.ctx.h, self.h_, _ptr(status), _ptr(best_n), _ptr(inliers), _ptr(R),
+                                                                   _ptr(t)))
+
+    def ransac_torch_views(self, npairs):
+        """Zero-copy torch views of the stage's device results: status [npairs], best [npairs, 2] (winner, count), inliers
+        [npairs, cap] (int32), R [npairs, 9], t [npairs, 3] (float64)."""
+        import torch
+
+        class _View:
+            def __init__(self, ptr, shape, typestr):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+
+        a, b, c, d, e = _vp(), _vp(), _vp(), _vp(), _vp()
+        self.ctx._ck(self.ctx.lib.sfmgpu_pairs_ransac_device_ptrs(self.h_, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e)))
+        dev = f"cuda:{self.ctx.device}"
+        return (torch.as_tensor(_View(a.value, (npairs,), "<i4"), device=dev), torch.as_tensor(_View(b.value, (npairs, 2), "<i4"), device=dev),
+                torch.as_tensor(_View(c.value, (npairs, self.cap), "<i4"), device=dev),
+                torch.as_tensor(_View(d.value, (npairs, 9), "<f8"), device=dev), torch.as_tensor(_View(e.value, (npairs, 3), "<f8"), device=dev))
 
     def download(self, pair):
         li, lj = np.zeros((self.cap, 2)), np.zeros((self.cap, 2))

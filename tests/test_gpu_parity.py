@@ -360,6 +360,25 @@ def test_ransac_counts_bit_exact(ctx, checker, port, n, H):
         assert np.array_equal(counts, wc) and bh == wb and np.array_equal(inl, wi), (n, H, thr)
 
 
+def test_ransac_counts_c4_full_scale(ctx, checker):
+    """BASELINE.json C4 at its largest point: 65,536 hypotheses x 10,000 correspondences, hypotheses from the reference's own
+    seeded sampler + eight_point_E (cycled: the solver costs 24 us each on the host), every count against the reference's
+    sampson_err loop on all host threads."""
+    n, H, Hu = 10000, 65536, 2048
+    pi, pj = two_view_scene(n)
+    xi, xj = checker.norm_points(TEMPLE_K, pi), checker.norm_points(TEMPLE_K, pj)
+    Eu, _ = checker.ransac_hypotheses(xi, xj, Hu)
+    # 32 scaled copies: scaling E by s scales numerator^2 and denominator by s^2 except for the +1e-12, so counts differ
+    # slightly from copy to copy and every copy exercises different roundings
+    scales = np.repeat(1.0 + 0.37 * np.arange(H // Hu), Hu)[:, None]
+    E = np.ascontiguousarray(np.tile(Eu, (H // Hu, 1)) * scales)
+    counts, bh, inl = ctx.ransac_score(xi, xj, E, 1e-3)
+    want = checker.ransac_score_mt(xi, xj, E, 1e-3, os.cpu_count() or 1)
+    assert np.array_equal(counts, want)
+    wbh = int(np.argmax(want)) if want.max() > 0 else -1
+    assert bh == wbh and len(inl) == want[wbh]
+
+
 def test_ransac_threshold_band_takes_the_literal_division(ctx, port):
     # thresholds placed exactly ON computed errors: the division-free screen must hand over to the exact test
     pi, pj = two_view_scene(400, seed=4)
@@ -498,6 +517,53 @@ def test_pair_frontend_batch_provisional_list_overflow(ctx, checker):
     # the single-frame entry points (capacity w*h) on the same images
     for k, im in enumerate(imgs):
         assert np.array_equal(f.corners(k, 500), checker.shi_tomasi(im, 500)), k
+
+
+@pytest.mark.parametrize("streaming", [False, True])
+def test_pair_frontend_batch_flat_and_weak_frames(ctx, checker, streaming):
+    """A flat frame (thr = 0: every pixel incl. the zeroed border is a candidate, :274-285) and a weak-texture frame (almost
+    every pixel reaches 1 % of the maximum) inside a batch: their FINAL candidate lists exceed the batch capacity
+    (max(w*h/6, 65536) < w*h), so the call redoes them with the full capacity and returns the reference's result -
+    no SFMGPU_E_CAPACITY, nothing truncated."""
+    rng = np.random.default_rng(21)
+    flat = np.full((H, W), 131, np.uint8)
+    weak = (90 + rng.integers(0, 3, (H, W))).astype(np.uint8)
+    imgs = [synth.frame(51, 0, W, H), flat, synth.frame(51, 1, W, H), weak, np.roll(weak, 1, axis=0), flat, flat]
+    cfg = sfmgpu.lkcfg(max_tracks=400)
+    pairs = ctx.pairs(6, 400)
+    if streaming:
+        f = ctx.frames(W, H, len(imgs), 3)
+        li, lj = np.full((6, 400, 2), -1.0), np.full((6, 400, 2), -1.0)
+        nk, nc = np.zeros(6, np.int32), np.zeros(6, np.int32)
+        pairs.run_host(f, np.stack(imgs), cfg, li, lj, nk, nc, chunk=3)
+    else:
+        f = _frames(ctx, imgs)
+        pairs.run(f, 0, 6, cfg)
+    tot_c, tot_k, _ = pairs.totals()  # raises if a frame were still marked as overflowed
+    cs = ks = 0
+    for p in range(6):
+        wl, wj, wnc = checker.pair_frontend(imgs[p], imgs[p + 1], 400)
+        if streaming:
+            gl, gj, gnc = li[p, :nk[p]], lj[p, :nk[p]], int(nc[p])
+        else:
+            gl, gj, gnc = pairs.download(p)
+        assert gnc == wnc and np.array_equal(gl, wl) and _klt_close(gj, wj), p
+        cs, ks = cs + gnc, ks + len(gl)
+    assert (tot_c, tot_k) == (cs, ks)
+
+
+def test_pair_frontend_bench_shape_pair(ctx, checker):
+    """One pair of bench.py's own C2 sequence (1920x1080, seed 20261018, 2000 corners, frames 500/501) against the
+    compiled reference: corner count, survivors, li bit-exact, lj within the KLT tolerance."""
+    w, h, nmax = 1920, 1080, 2000
+    f0, f1 = synth.frame(SEED, 500, w, h), synth.frame(SEED, 501, w, h)
+    f = _frames(ctx, [f0, f1], 3)
+    cfg = sfmgpu.lkcfg(max_tracks=nmax)
+    pairs = ctx.pairs(1, nmax)
+    pairs.run(f, 0, 1, cfg)
+    li, lj, nc = pairs.download(0)
+    wl, wj, wnc = checker.pair_frontend(f0, f1, nmax)
+    assert nc == wnc and len(li) == len(wl) and np.array_equal(li, wl) and _klt_close(lj, wj)
 
 
 def test_pair_frontend_batch_with_score_ties(ctx, checker):

@@ -128,3 +128,24 @@ def test_triangulate_dlt(port, ref):
     a, b = ref.triangulate_dlt(TEMPLE_K, poses, ia, ib, ui, uj), port.triangulate_dlt(TEMPLE_K, poses, ia, ib, ui, uj)
     assert np.array_equal(a, b)
     assert np.median(np.linalg.norm(a - X, axis=1)) < 0.05
+
+
+def test_two_view_unit(port, ref):
+    """The whole two-view unit (:1836-1857: front end, size guard, find_E_ransac) per pair: restatement == compiled
+    reference, bit for bit; and equal to the single-pair entry points."""
+    fr = np.stack([synth.frame(20261018, t, 320, 240) for t in range(4)])
+    ta, a = ref.two_view_mt(fr, 300, 3, K=TEMPLE_K, rs_iters=150, rs_thr=2e-3, rs_min_inliers=80, min_points=120)
+    tb, b = port.two_view_mt(fr, 300, 2, K=TEMPLE_K, rs_iters=150, rs_thr=2e-3, rs_min_inliers=80, min_points=120)
+    assert ta == tb and all(np.array_equal(a[k], b[k]) for k in a)
+    for p in range(3):
+        li, lj, nc = ref.pair_frontend(fr[p], fr[p + 1], 300)
+        assert nc == a["n_corners"][p] and np.array_equal(li, a["li"][p, :len(li)]) and np.array_equal(lj, a["lj"][p, :len(lj)])
+        if len(li) < 120:
+            assert a["status"][p] == 0
+            continue
+        r = ref.find_E_ransac(TEMPLE_K, li, lj, 150, 2e-3, 80)
+        assert (r is None) == (a["status"][p] == 1)
+        if r is not None:
+            assert np.array_equal(r[0].reshape(9), a["R"][p]) and np.array_equal(r[1], a["t"][p])
+            assert np.array_equal(r[2], a["inliers"][p, :a["n_inl"][p]])
+    assert {0, 2} <= set(a["status"].tolist())
