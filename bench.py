@@ -1,20 +1,26 @@
 #!/usr/bin/env python
 """bench.py — the front-end hot path on synthetic sequences, one JSON line on stdout.
 
-Workload at N GPUs (BASELINE.json configs[1], "C2"): every rank owns ONE synthetic 1080p 1,000-frame sequence
-(seed 20261018 + rank, integer generator of sfmgpu/synth.py) and runs the stateless two-view front end
-(cpp/src/templering_sfm.cpp:1836-1857) on all 999 frame pairs: 3-level pyramid for every frame, Shi-Tomasi +
-exact std::sort + greedy NMS (2000 corners/frame), forward+backward pyramidal LK with the fb test.  One "step" =
-one pass over the whole sequence.  Sequences are independent, so ranks shard with no data-path collective
-(weak scaling, SURVEY.md §8e mode 2); tracks and counts are gathered to rank 0 with NCCL at the end of a step.
+Workload (BASELINE.json configs[2], "C3", the configuration north_star names for scaling): ONE synthetic 3840x2160
+2,000-frame sequence (seed 20261018, integer generator of sfmgpu/synth.py), 8,000 corners per frame, run as the
+reference's stateless two-view unit (cpp/src/templering_sfm.cpp:1836-1857) over all 1,999 frame pairs:
+    3-level pyramid -> Shi-Tomasi + exact std::sort order + greedy NMS -> forward + backward pyramidal LK -> fb filter ->
+    if (li.size() >= 120) find_E_ransac(K, li, lj, 4000, 2e-3, 80)   (sampling, 8-point solver, Sampson scoring, pose)
+One "step" = one pass over the whole sequence.  With N GPUs the PAIRS are sharded: rank g owns a contiguous block of
+pairs plus one halo frame (SURVEY.md §8e mode 1), total work fixed -> "scaling": "strong"; no data-path collective, the
+results (tracks, counts, inlier sets, poses) are gathered to rank 0 over NCCL at the end of an end-to-end step.
+`--workload c2` runs configs[1] (1080p x 1000 frames, 2000 corners) the same way; at N=1 a shorter C2 measurement is
+attached to the line as "c2".
 
-metric  : KLT feature-tracks/s (1 feature-track = fwd + bwd track_one + fb test of one corner);
-          the RANSAC half of BASELINE.json's metric (hyp x pts / s, config C4) is reported under "ransac".
-value   : inputs resident in HBM, CUDA events on the library's stream, max over ranks.
-e2e     : same step through the C ABI with HOST (pinned) frames: H2D of the sequence and D2H of all tracks inside
-          the timed region.
---impl reference : the reference's own CPU front end (oracle/_ref = the unmodified TU compiled where it lies,
-          else the oracle port) on all host cores, bounded sample of the same workload.
+metric  : KLT feature-tracks/s (1 feature-track = fwd + bwd track_one + fb test of one corner) for the
+          whole unit incl. its RANSAC stage; the RANSAC half of BASELINE.json's metric (hyp x pts / s, config C4) is
+          reported under "ransac".
+value   : frames resident in HBM, CUDA events on the library's stream, max over ranks.
+e2e     : the same step through the C ABI with HOST (pinned) frames: H2D of the frames and D2H of tracks, inlier sets and
+          poses inside the timed region (N > 1: plus the NCCL gather to rank 0, which then reads everything back).
+parity_in_bench : the reference (oracle/_ref) runs the same unit on sample pairs of the same frames on the host; corner
+          counts, survivor counts, li, RANSAC status / inlier lists must be identical, lj within 1e-3 px.
+--impl reference : the reference's own CPU implementation of the unit on all host cores, bounded sample per step.
 """
 import argparse
 import json
@@ -29,24 +35,43 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "structure-from-motion-3d-reconstruction_b200"))
 
-W, H, NFRAMES, MAX_CORNERS, LEVELS = 1920, 1080, 1000, 2000, 3
+WORKLOADS = {
+    "c3": dict(name="C3", W=3840, H=2160, frames=2000, corners=8000),
+    "c2": dict(name="C2", W=1920, H=1080, frames=1000, corners=2000),
+}
+LEVELS = 3
 SEED0 = 20261018
+RANSAC = dict(iters=4000, thr=2e-3, min_inliers=80, min_points=120)  # the unit's own call, :1855-1857
 METRIC = "KLT feature-tracks/sec (+ RANSAC hyp*pts/sec under 'ransac')"
 UNIT = "feature-tracks/s"
 B_KLT = 2092.0      # algorithmic bytes per feature-track
 F_KLT_IT = 5045.0   # algorithmic FP64 flop per LK iteration
 F_RS = 35.0         # flop per hyp x pt
 RS_N, RS_H = 10000, 65536
+KLT_TOL = 1e-3      # px, north_star's tolerance for tracked positions
+POSE_TOL = 1e-4     # R, t entries through the device solver + device pose tail (inlier lists are compared bit for bit)
 
 
-def workload_cfg(n_gpus, nframes):
+def temple_K():
+    return np.array([1520.4, 0, 302.32, 0, 1525.9, 246.87, 0, 0, 1.0])
+
+
+def shard_range(n_items, world, rank):
+    base, extra = divmod(n_items, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def workload_cfg(wl, n_gpus, nframes):
     return {
-        "workload": f"{'C2' if W == 1920 else 'C3'}: synthetic {W}x{H} {nframes}-frame sequence per GPU, pair-mode front end "
-                    f"(pyramid L=3 + Shi-Tomasi/NMS {MAX_CORNERS} corners/frame + fwd/bwd KLT r=5 iters=10 + fb<1.0)",
-        "frames_per_gpu": nframes, "pairs_per_gpu": nframes - 1, "width": W, "height": H, "max_corners": MAX_CORNERS,
-        "pyr_levels": LEVELS, "sharding": f"sequence-per-rank x{n_gpus} (no data-path collective; NCCL gather of results)",
-        "l2_policy": "inputs (2.07 GB of frames per GPU) exceed the 126 MB L2; no explicit flush needed",
-        "ransac_workload": f"C4: {RS_H} hypotheses x {RS_N} correspondences, thr 1e-3",
+        "workload": f"{wl['name']}: ONE synthetic {wl['W']}x{wl['H']} {nframes}-frame sequence, two-view unit over all {nframes - 1} pairs "
+                    f"(pyramid L={LEVELS} + Shi-Tomasi/NMS {wl['corners']} corners/frame + fwd/bwd KLT r=5 iters=10 + fb<1.0 + "
+                    f"find_E_ransac({RANSAC['iters']}, {RANSAC['thr']}, {RANSAC['min_inliers']}) per pair with >= {RANSAC['min_points']} survivors)",
+        "frames": nframes, "pairs": nframes - 1, "width": wl["W"], "height": wl["H"], "max_corners": wl["corners"],
+        "pyr_levels": LEVELS, "ransac": RANSAC,
+        "sharding": f"pair blocks + one halo frame per rank x{n_gpus} (no data-path collective; NCCL gather of results to rank 0)",
+        "l2_policy": f"inputs ({wl['W'] * wl['H'] * nframes / n_gpus / 1e9:.2f} GB of frames per GPU) exceed the 126 MB L2; no explicit flush needed",
+        "ransac_workload": f"C4: {RS_H} hypotheses x {RS_N} correspondences, thr 1e-3, hypotheses = the seeded sampler's octets through the 8-point solver",
     }
 
 
@@ -101,8 +126,7 @@ class ClockSampler:
 
 
 def bind_near_gpu(index):
-    """Pin this rank (and therefore its first-touch pinned allocations) to the CPUs NVML reports as local to its GPU: with
-    8 ranks uploading 2 GB per step each, remote-socket host memory is the first bottleneck.  Best effort."""
+    """Pin this rank (and therefore its first-touch pinned allocations) to the CPUs NVML reports as local to its GPU.  Best effort."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -119,18 +143,19 @@ def bind_near_gpu(index):
 
 
 def profile_metrics():
-    """ncu-derived numbers of the committed captures (profiles/r1_metrics.json, C2 shape): static evidence, not re-measured."""
-    p = os.path.join(ROOT, "profiles", "r1_metrics.json")
-    try:
-        with open(p) as fh:
-            m = json.load(fh)
-    except Exception:
-        return {}
+    """ncu-derived numbers of the committed captures (profiles/*_metrics.json): static evidence, labelled as such."""
     out = {}
-    for name, d in m.items():
-        for short in ("klt_quad_kernel", "score_tile_kernel<2>", "radix_sort_frame_kernel", "nms_kernel", "ransac_count_kernel", "pyr_down_kernel"):
-            if short in name and short not in out:
-                out[short] = d
+    for fn in ("r2_metrics.json", "r1_metrics.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", fn)) as fh:
+                m = json.load(fh)
+        except Exception:
+            continue
+        for name, d in m.items():
+            for short in ("klt_quad_kernel", "score_tile_kernel<2>", "radix_sort_frame_kernel", "nms_kernel", "ransac_count_kernel", "pyr_down_kernel",
+                          "eight_point_kernel"):
+                if short in name and short not in out:
+                    out[short] = dict(d, source=f"profiles/{fn}")
     return out
 
 
@@ -144,67 +169,58 @@ def measured_peaks():
     return 6650.0, "B200_PROFILING.md fallback (of fallback)"
 
 
-def synthetic_hypotheses(H, seed=5):
-    """Essential matrices [t]x R around the C4 scene's true motion (scoring cost does not depend on the values)."""
-    rng = np.random.default_rng(seed)
-    w = np.array([0.02, -0.15, 0.01]) + rng.normal(0, 0.05, (H, 3))
-    t = np.array([0.2, 0.01, 0.03]) + rng.normal(0, 0.05, (H, 3))
-    th = np.linalg.norm(w, axis=1, keepdims=True)
-    k = w / th
-    Kx = np.zeros((H, 3, 3))
-    Kx[:, 0, 1], Kx[:, 0, 2], Kx[:, 1, 0], Kx[:, 1, 2], Kx[:, 2, 0], Kx[:, 2, 1] = -k[:, 2], k[:, 1], k[:, 2], -k[:, 0], -k[:, 1], k[:, 0]
-    R = np.eye(3) + np.sin(th)[:, :, None] * Kx + (1 - np.cos(th))[:, :, None] * (Kx @ Kx)
-    t = t / np.linalg.norm(t, axis=1, keepdims=True)
-    Tx = np.zeros((H, 3, 3))
-    Tx[:, 0, 1], Tx[:, 0, 2], Tx[:, 1, 0], Tx[:, 1, 2], Tx[:, 2, 0], Tx[:, 2, 1] = -t[:, 2], t[:, 1], t[:, 2], -t[:, 0], -t[:, 1], t[:, 0]
-    return np.ascontiguousarray((Tx @ R).reshape(H, 9))
-
-
 def c4_points(n):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from conftest import TEMPLE_K, two_view_scene
     pi, pj = two_view_scene(n)
     Kinv = np.linalg.inv(TEMPLE_K)
+
     def norm(p):
         hp = np.concatenate([p, np.ones((len(p), 1))], 1) @ Kinv.T
         return np.ascontiguousarray(hp[:, :2] / hp[:, 2:3])
     return norm(pi), norm(pj)
 
 
+def host_threads():
+    return max(1, min(len(os.sched_getaffinity(0)), 64))
+
+
 # ---------------------------------------------------------------------------------------------------------------
-def run_reference(args, rank, world):
-    """The reference's CPU front end on all host cores (rank 0 only), bounded sample of C2."""
+def run_reference(args, wl, rank):
+    """The reference's CPU implementation of the unit on all host cores (rank 0 only): every step runs `threads` pairs of the
+    same sequence (one per host thread) through detection, KLT, fb filter and find_E_ransac."""
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle
     chk, kind = oracle.best()
     gen = oracle.port()
-    cores = os.cpu_count() or 1
-    threads = max(1, min(cores, 64))
-    nfr = threads + 1  # one pair per thread and step
-    frames = gen.synth_frames(SEED0, 0, nfr, W, H, threads=threads)
+    threads = host_threads()
+    frames = gen.synth_frames(SEED0, 0, threads + 1, wl["W"], wl["H"], threads=threads)
+    K = temple_K()
     times, tracks = [], 0
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        tracks, kept = chk.pair_frontend_mt(frames, MAX_CORNERS, threads)
+        tracks, _ = chk.two_view_mt(frames, wl["corners"], threads, K=K, rs_iters=RANSAC["iters"], rs_thr=RANSAC["thr"],
+                                    rs_min_inliers=RANSAC["min_inliers"], min_points=RANSAC["min_points"], detail=False)
         dt = time.perf_counter() - t0
         if it >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times)) if times else float("nan")
     val = tracks / (ms * 1e-3) if times else 0.0
-    # RANSAC scoring half, same threads
     xi, xj = c4_points(RS_N)
     Hs = 64 * threads
-    E = synthetic_hypotheses(Hs)
+    E = chk.ransac_hypotheses(xi, xj, 64)[0]
+    E = np.ascontiguousarray(np.tile(E, (threads, 1)))
     t0 = time.perf_counter()
     chk.ransac_score_mt(xi, xj, E, 1e-3, threads)
     rs = Hs * RS_N / (time.perf_counter() - t0)
-    sample = f"{threads} pairs of the C2 sequence per step (one per host thread), {tracks} feature-tracks; RANSAC {Hs} x {RS_N}"
+    sample = (f"{threads} pairs of the {wl['name']} sequence per step (one per host thread), {tracks} feature-tracks, front end + "
+              f"find_E_ransac; RANSAC scoring {Hs} x {RS_N}")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_cfg(args.gpus, NFRAMES),
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_cfg(wl, args.gpus, args.frames or wl["frames"]),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
                          "ransac_hyp_pts_per_s": rs},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -235,6 +251,327 @@ def emit(line):
         os.write(_REAL_STDOUT, data)
 
 
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class Unit:
+    """One rank's share of a workload: its frames (resident), the pairs object with the RANSAC stage on, host buffers."""
+
+    def __init__(self, ctx, wl, nframes_total, rank, world):
+        import sfmgpu
+        self.ctx, self.wl, self.rank, self.world = ctx, wl, rank, world
+        self.W, self.H, self.cap = wl["W"], wl["H"], wl["corners"]
+        self.P_total = nframes_total - 1
+        self.p0, self.p1 = shard_range(self.P_total, world, rank)
+        self.npairs = self.p1 - self.p0
+        self.nfr = self.npairs + 1 if self.npairs > 0 else 0
+        self.cfg = sfmgpu.lkcfg(max_tracks=self.cap, pyr_levels=LEVELS)
+        self.frames = ctx.frames(self.W, self.H, max(self.nfr, 2), LEVELS)
+        self.pairs = ctx.pairs(max(self.npairs, 1), self.cap)
+        self.pairs.set_ransac(temple_K(), **RANSAC)
+        if self.nfr:
+            self.frames.synth(0, self.nfr, SEED0, self.p0)  # this rank's frames of THE sequence: time indices p0 .. p1
+        ctx.sync()
+
+    def step_resident(self):
+        self.frames.build_pyramid(0, self.nfr)
+        self.pairs.run(self.frames, 0, self.npairs, self.cfg)
+
+    def host_buffers(self, with_outputs):
+        ctx, P, cap = self.ctx, max(self.npairs, 1), self.cap
+        self.host = ctx.pinned_empty((max(self.nfr, 1), self.H, self.W), np.uint8)
+        for j in range(self.nfr):  # the device generator is the numpy generator's twin (tests): fill the pinned frames from it
+            self.host[j] = self.frames.download(j, 0)
+        self.out = None
+        if with_outputs:
+            self.out = dict(li=ctx.pinned_empty((P, cap, 2), np.float64), lj=ctx.pinned_empty((P, cap, 2), np.float64),
+                            nk=ctx.pinned_empty((P,), np.int32), nc=ctx.pinned_empty((P,), np.int32),
+                            status=ctx.pinned_empty((P,), np.int32), best_n=ctx.pinned_empty((P,), np.int32),
+                            inliers=ctx.pinned_empty((P, cap), np.int32), R=ctx.pinned_empty((P, 9), np.float64),
+                            t=ctx.pinned_empty((P, 3), np.float64))
+            o = self.out
+            self.pairs.ransac_host_outputs(o["status"], o["best_n"], o["inliers"], o["R"], o["t"])
+        else:
+            self.pairs.ransac_host_outputs()
+
+    def step_host(self, chunk=0):
+        o = self.out
+        if o is not None:
+            self.pairs.run_host(self.frames, self.host[:self.nfr], self.cfg, o["li"], o["lj"], o["nk"], o["nc"], chunk=chunk)
+        else:
+            self.pairs.run_host(self.frames, self.host[:self.nfr], self.cfg, None, None, None, None, chunk=chunk)
+
+    def close(self):
+        self.ctx.sync()
+        self.pairs.close()
+        self.frames.close()
+        for a in [getattr(self, "host", None)] + list((getattr(self, "out", None) or {}).values()):
+            if a is not None:
+                self.ctx.pinned_free(a)
+        self.host = self.out = None
+
+
+def gather_to_rank0(unit, torch, dist, shards, hbuf, parts):
+    """N > 1: every rank's device-resident results go to rank 0 over NCCL (one group of point-to-point transfers per rank),
+    rank 0 reads each rank's block back to pinned host memory on a side stream while the next block arrives.  li is
+    integer-valued (corner coordinates) and inlier indices are < max_corners: both travel as int16."""
+    rank, world, n = unit.rank, unit.world, unit.npairs
+    v_li, v_lj, v_nk, v_nc = unit.pairs.torch_views(max(n, 1))
+    v_st, v_best, v_inl, v_R, v_t = unit.pairs.ransac_torch_views(max(n, 1))
+    t_a = time.perf_counter()
+    mine = [v_li[:n].to(torch.int16), v_lj[:n], v_nk[:n], v_nc[:n], v_st[:n], v_best[:n], v_inl[:n].to(torch.int16), v_R[:n], v_t[:n]]
+    if rank != 0:
+        reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, t.contiguous(), 0) for t in mine])
+        for q in reqs:
+            q.wait()
+        torch.cuda.synchronize()
+        return
+    side = hbuf["stream"]
+    for r in range(world):
+        a, b = shards[r]
+        if b <= a:
+            continue
+        if r == 0:
+            got = mine
+        else:
+            got = hbuf["dev"][r]
+            reqs = dist.batch_isend_irecv([dist.P2POp(dist.irecv, t, r) for t in got])
+            for q in reqs:
+                q.wait()
+        ev = torch.cuda.Event()
+        ev.record()
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            for key, src in zip(hbuf["keys"], got):
+                hbuf["host"][key][a:b].copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    parts["gather_and_d2h_ms"] = (time.perf_counter() - t_a) * 1e3
+
+
+def parity_check(chk, gen, wl, sample_pairs, frames_of, got, threads):
+    """Reference (chk) on the sampled pairs vs the GPU results `got` (dict of arrays indexed by global pair).  Returns the
+    parity_in_bench object."""
+    from concurrent.futures import ThreadPoolExecutor
+    K = temple_K()
+
+    def one(p):
+        fr = frames_of(p)
+        _, d = chk.two_view_mt(fr, wl["corners"], 1, K=K, rs_iters=RANSAC["iters"], rs_thr=RANSAC["thr"],
+                               rs_min_inliers=RANSAC["min_inliers"], min_points=RANSAC["min_points"])
+        return p, d
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=max(1, min(threads, len(sample_pairs)))) as ex:
+        res = list(ex.map(one, sample_pairs))
+    dt = time.perf_counter() - t0
+    ok, worst_lj, worst_R, fails, tracks = True, 0.0, 0.0, [], 0
+    for p, d in res:
+        nk, nc = int(d["n_kept"][0]), int(d["n_corners"][0])
+        tracks += nc
+        c = {"n_corners": int(got["nc"][p]) == nc, "n_kept": int(got["nk"][p]) == nk}
+        if c["n_kept"]:
+            c["li"] = bool(np.array_equal(np.asarray(got["li"][p][:nk], np.float64), d["li"][0, :nk]))
+            dev = float(np.abs(got["lj"][p][:nk] - d["lj"][0, :nk]).max()) if nk else 0.0
+            worst_lj = max(worst_lj, dev)
+            c["lj"] = dev <= KLT_TOL
+            c["ransac_status"] = int(got["status"][p]) == int(d["status"][0])
+            if c["ransac_status"] and int(d["status"][0]) == 2:
+                ni = int(d["n_inl"][0])
+                c["ransac_best_n"] = int(got["best_n"][p]) == ni
+                c["ransac_inliers"] = c["ransac_best_n"] and bool(np.array_equal(np.asarray(got["inliers"][p][:ni], np.int32), d["inliers"][0, :ni]))
+                devR = float(max(np.abs(got["R"][p] - d["R"][0]).max(), np.abs(got["t"][p] - d["t"][0]).max()))
+                worst_R = max(worst_R, devR)
+                c["pose"] = devR <= POSE_TOL
+        if not all(c.values()):
+            ok = False
+            fails.append({"pair": int(p), "failed": [k for k, v in c.items() if not v]})
+    return {"ok": ok, "pairs_checked": [int(p) for p in sample_pairs], "max_lj_dev_px": worst_lj, "lj_tolerance_px": KLT_TOL,
+            "max_pose_dev": worst_R, "pose_tolerance": POSE_TOL,
+            "pose_note": "R, t come from the device solver's winning hypothesis (equal to the reference's to ~1e-9) through the device "
+                         "pose tail; the synthetic sequence has a sub-pixel baseline, so E -> (R, t) is ill-conditioned and amplifies that",
+            "bit_exact": ["n_corners", "n_kept", "li", "ransac_status", "ransac_best_n", "ransac_inliers"], "failures": fails,
+            "checker": chk.kind}, tracks, dt
+
+
+def measure_workload(args, ctx, wl, nframes_total, rank, local, world, torch, dist, full):
+    """Resident value, stage times, e2e, parity for one workload.  full = the bench line's main workload (clock sampling,
+    cpu_baseline); otherwise the shorter side measurement."""
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.sync()
+
+    steps = args.steps if full else max(1, min(args.steps, 5))
+    warm = args.warmup if full else max(1, min(args.warmup, 2))
+    unit = Unit(ctx, wl, nframes_total, rank, world)
+    shards = [shard_range(unit.P_total, world, r) for r in range(world)]
+    # ---- value: frames resident in HBM ---------------------------------------------------------------------------
+    for _ in range(warm):
+        unit.step_resident()
+    ctx.sync()
+    unit.pairs.totals()
+    barrier()
+    sampler = ClockSampler(local) if (full and rank == 0) else None
+    if sampler:
+        sampler.start()
+    l0 = ctx.launches()
+    ctx.timer_start()
+    for _ in range(steps):
+        unit.step_resident()
+    ms_total = ctx.timer_stop()
+    launches = ctx.launches() - l0
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    n_tracks, n_kept, n_it = unit.pairs.totals()
+
+    # ---- per-stage times (separate pass, stages back to back on one stream) ------------------------------------------
+    ctx.profile(True)
+    ctx.timer_start()
+    unit.frames.build_pyramid(0, unit.nfr)
+    pyr_ms = ctx.timer_stop()
+    unit.pairs.run(unit.frames, 0, unit.npairs, unit.cfg)
+    st = ctx.stage_times()
+    ctx.profile(False)
+
+    # ---- e2e: host (pinned) frames in, tracks + inlier sets + poses out ---------------------------------------------------
+    unit.host_buffers(with_outputs=(world == 1))
+    o = unit.out
+    h2d = unit.nfr * unit.W * unit.H
+    d2h = sum(a.nbytes for a in o.values()) if o else 0
+    hbuf, parts = None, {}
+    if world > 1:
+        P, cap = unit.P_total, unit.cap
+        keys = ["li", "lj", "nk", "nc", "status", "best", "inliers", "R", "t"]
+        if rank == 0:
+            shapes = {"li": ((cap, 2), torch.int16), "lj": ((cap, 2), torch.float64), "nk": ((), torch.int32), "nc": ((), torch.int32),
+                      "status": ((), torch.int32), "best": ((2,), torch.int32), "inliers": ((cap,), torch.int16),
+                      "R": ((9,), torch.float64), "t": ((3,), torch.float64)}
+            host = {k: torch.empty((P,) + shp, dtype=dt, pin_memory=True) for k, (shp, dt) in shapes.items()}
+            dev = {r: [torch.empty((shards[r][1] - shards[r][0],) + shapes[k][0], dtype=shapes[k][1], device="cuda") for k in keys]
+                   for r in range(1, world)}
+            hbuf = {"keys": keys, "host": host, "dev": dev, "stream": torch.cuda.Stream()}
+            d2h = sum(t.numel() * t.element_size() for t in host.values())
+        else:
+            hbuf = {"keys": keys}
+
+    def step_e2e():
+        if world == 1:
+            unit.step_host(chunk=args.chunk)
+            return
+        t_a = time.perf_counter()
+        unit.step_host(chunk=args.chunk)
+        ctx.sync()  # results are written on the library's streams; NCCL runs on torch's
+        parts["stream_call_ms"] = (time.perf_counter() - t_a) * 1e3
+        gather_to_rank0(unit, torch, dist, shards, hbuf, parts)
+
+    # the PCIe floor: every rank uploads its frames at the same time, nothing else (max over ranks below)
+    unit.frames.upload_ptr(0, unit.nfr, unit.host.ctypes.data)
+    barrier()
+    t0 = time.perf_counter()
+    unit.frames.upload_ptr(0, unit.nfr, unit.host.ctypes.data)
+    ctx.sync()
+    h2d_floor_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+
+    e2e_steps = max(1, min(steps, 3))
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    ctx.timer_start()
+    for _ in range(e2e_steps):
+        step_e2e()
+    e2e_ms_dev = ctx.timer_stop()
+    barrier()
+    e2e_wall = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e2e_ms_dev, e2e_wall) / e2e_steps
+
+    # results of the e2e step, indexed by global pair, on rank 0
+    got = None
+    if world == 1:
+        assert int(o["nc"].sum()) == n_tracks and int(o["nk"].sum()) == n_kept, "e2e results differ from the resident run"
+        got = dict(o)
+    elif rank == 0:
+        h = {k: v.numpy() for k, v in hbuf["host"].items()}
+        got = dict(li=h["li"], lj=h["lj"], nk=h["nk"], nc=h["nc"], status=h["status"], best_n=h["best"][:, 1], inliers=h["inliers"],
+                   R=h["R"], t=h["t"])
+        a, b = shards[0]
+        assert int(got["nc"][a:b].sum()) == n_tracks and int(got["nk"][a:b].sum()) == n_kept, "gathered results differ from the resident run"
+
+    # ---- parity inside the bench + CPU baseline (rank 0) ---------------------------------------------------------------------
+    parity, cpu = None, None
+    if rank == 0 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle
+        chk, kind = oracle.best()
+        gen = oracle.port()
+        threads = host_threads()
+        if world == 1:
+            sample = list(range(min(threads, unit.P_total)))
+            frames_of = lambda p: np.ascontiguousarray(unit.host[p:p + 2])
+        else:
+            # the first pair of every rank's block (offsets and halo frames of the sharding), then the pairs after them
+            sample = []
+            for k in range(max(1, threads // world)):
+                sample += [a + k for a, b in shards if a + k < b]
+            sample = sorted(set(sample))[:threads]
+            frames_of = lambda p: gen.synth_frames(SEED0, p, 2, unit.W, unit.H, threads=1)
+        parity, ptracks, pdt = parity_check(chk, gen, wl, sample, frames_of, got, threads)
+        if full and world == 1:
+            xi, xj = c4_points(RS_N)
+            Hs = 64 * threads
+            E = np.ascontiguousarray(np.tile(chk.ransac_hypotheses(xi, xj, 64)[0], (threads, 1)))
+            t1 = time.perf_counter()
+            chk.ransac_score_mt(xi, xj, E, 1e-3, threads)
+            rs = Hs * RS_N / (time.perf_counter() - t1)
+            t2 = time.perf_counter()
+            one_tracks, _ = chk.two_view_mt(np.ascontiguousarray(unit.host[:2]), wl["corners"], 1, K=temple_K(), rs_iters=RANSAC["iters"],
+                                            rs_thr=RANSAC["thr"], rs_min_inliers=RANSAC["min_inliers"], min_points=RANSAC["min_points"],
+                                            detail=False)
+            one_core = one_tracks / (time.perf_counter() - t2)
+            cpu = {"value": ptracks / pdt, "unit": UNIT, "cores": min(threads, len(sample)), "kind": kind, "one_core_value": one_core,
+                   "sample": f"first {len(sample)} pairs of the same sequence, one per host thread, front end + find_E_ransac "
+                             f"({ptracks} feature-tracks in {pdt:.2f} s wall); the same run is the parity_in_bench check",
+                   "ransac_hyp_pts_per_s": rs}
+
+    # ---- reduce over ranks ------------------------------------------------------------------------------------------------
+    ms_step = ms_total / steps
+    vals = torch.tensor([ms_step, e2e_ms, pyr_ms, st["klt"], st["corner_score"], st["corner_select"], st["ransac"], st["compact"], h2d_floor_ms],
+                        device="cuda", dtype=torch.float64)
+    work = torch.tensor([n_tracks, n_kept, n_it, launches, h2d], device="cuda", dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    ms_step, e2e_ms, pyr_ms, klt_ms, cs_ms, sel_ms, rs_ms, cp_ms, h2d_floor_ms = [float(v) for v in vals.tolist()]
+    tracks_all, kept_all, it_all, launches_all, h2d_all = [int(v) for v in work.tolist()]
+    unit.close()
+    res = dict(ms_step=ms_step, e2e_ms=e2e_ms, e2e_steps=e2e_steps, pyr_ms=pyr_ms, klt_ms=klt_ms, cs_ms=cs_ms, sel_ms=sel_ms, rs_ms=rs_ms,
+               cp_ms=cp_ms, h2d_floor_ms=h2d_floor_ms, tracks=tracks_all, kept=kept_all, iters=it_all, launches=launches_all, h2d=h2d_all,
+               d2h=d2h, parity=parity, cpu=cpu, clocks=clocks, parts=parts, steps=steps, warmup=warm, nframes=nframes_total,
+               pairs_rank0=unit.npairs, frames_rank0=unit.nfr)
+    return res
+
+
+def stage_block(wl, r, world, hbm_peak):
+    per_rank_tracks = r["tracks"] / world
+    nfr, W, H = r["frames_rank0"], wl["W"], wl["H"]
+    pyr_bytes = nfr * W * H * sum(0.25 ** l for l in range(LEVELS))
+    cs_bytes = r["pairs_rank0"] * W * H
+    klt_gbs = B_KLT * per_rank_tracks / (r["klt_ms"] * 1e-3) / 1e9
+    return {
+        "stages_ms": {"pyramid": r["pyr_ms"], "corner_score": r["cs_ms"], "corner_select": r["sel_ms"], "klt": r["klt_ms"],
+                      "compact": r["cp_ms"], "ransac": r["rs_ms"]},
+        "stage_rooflines": {
+            "pyramid": {"bound": "hbm", "achieved": pyr_bytes / (r["pyr_ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": pyr_bytes / (r["pyr_ms"] * 1e-3) / 1e9 / hbm_peak},
+            "corner_score": {"bound": "hbm", "achieved": cs_bytes / (r["cs_ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": cs_bytes / (r["cs_ms"] * 1e-3) / 1e9 / hbm_peak, "mpx_per_s": cs_bytes / (r["cs_ms"] * 1e-3) / 1e6},
+            "klt": {"bound": "hbm", "achieved": klt_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": klt_gbs / hbm_peak},
+        },
+    }
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -242,25 +579,25 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=NFRAMES, help="frames per GPU (default: the C2 sequence length)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pipe", type=int, default=-1, help="pairs per sub-chunk of the two-lane pipeline (-1: library default, 0: off)")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
-                    help="c2 (default, the bench line): 1080p, 2000 corners; c3: 4K, 8000 corners (side measurement, use --frames <= 300)")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2"],
+                    help="c3 (default): 4K x 2000 frames, 8000 corners, pair-sharded; c2: 1080p x 1000 frames, 2000 corners")
+    ap.add_argument("--frames", type=int, default=0, help="frames of the sequence (default: the workload's own length)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (cpu_baseline, parity_in_bench)")
+    ap.add_argument("--no-c2", action="store_true", help="skip the C2 side measurement of the default line")
+    ap.add_argument("--pipe", type=int, default=-1, help="pairs per sub-chunk of the stage pipeline (-1: library default, 0: off)")
     ap.add_argument("--klt-mode", type=int, default=0, help="sfmgpu_klt_set_mode value (A/B timing of kernel variants)")
-    ap.add_argument("--chunk", type=int, default=0, help="frames per chunk of the streaming e2e call (0: a quarter of the sequence)")
+    ap.add_argument("--chunk", type=int, default=0, help="frames per chunk of the streaming e2e call (0: a tenth of the rank's frames)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
-    if args.workload == "c3":
-        global W, H, MAX_CORNERS
-        W, H, MAX_CORNERS = 3840, 2160, 8000
+    wl = WORKLOADS[args.workload]
+    nframes_total = args.frames or wl["frames"]
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, wl, rank)
         return
 
     import torch
@@ -277,134 +614,22 @@ def main():
         ctx.pipeline_set(args.pipe)
     if args.klt_mode:
         ctx.klt_set_mode(args.klt_mode)
-    nfr, npairs = args.frames, args.frames - 1
-    cfg = sfmgpu.lkcfg(max_tracks=MAX_CORNERS, pyr_levels=LEVELS)
-    frames = ctx.frames(W, H, nfr, LEVELS)
-    pairs = ctx.pairs(npairs, MAX_CORNERS)
-    frames.synth(0, nfr, SEED0 + rank, 0)  # this rank's sequence, generated in HBM
-    ctx.sync()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        ctx.sync()
-
-    def step_resident():
-        frames.build_pyramid(0, nfr)
-        pairs.run(frames, 0, npairs, cfg)
-
-    # ---- value: inputs resident in HBM ---------------------------------------------------------------------------
-    for _ in range(args.warmup):
-        step_resident()
-    ctx.sync()
-    tot = pairs.totals()  # raises if a frame overflowed the candidate capacity
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    l0 = ctx.launches()
-    ctx.timer_start()
-    for _ in range(args.steps):
-        step_resident()
-    ms_total = ctx.timer_stop()
-    launches = ctx.launches() - l0
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    n_tracks, n_kept, n_it = pairs.totals()
-
-    # ---- per-stage times (separate, untimed-for-value pass) + FP64 peak ---------------------------------------------
-    ctx.profile(True)
-    ctx.timer_start()
-    frames.build_pyramid(0, nfr)
-    pyr_ms = ctx.timer_stop()
-    pairs.run(frames, 0, npairs, cfg)
-    st = ctx.stage_times()
-    ctx.profile(False)
+    r = measure_workload(args, ctx, wl, nframes_total, rank, local, world, torch, dist, full=True)
+    c2 = None
+    if args.workload == "c3" and world == 1 and not args.no_c2 and not args.frames:
+        c2 = measure_workload(args, ctx, WORKLOADS["c2"], WORKLOADS["c2"]["frames"], rank, local, world, torch, dist, full=False)
     fp64_peak = ctx.fp64_peak()
 
-    # ---- e2e: host (pinned) frames in, all tracks out, copies inside the timed region --------------------------------
-    host = ctx.pinned_empty((nfr, H, W), np.uint8)
-    for k in range(0, nfr, 50):  # fill the pinned buffer with this rank's sequence (device generator == numpy twin)
-        for j in range(k, min(k + 50, nfr)):
-            host[j] = frames.download(j, 0)
-    li = ctx.pinned_empty((npairs, MAX_CORNERS, 2), np.float64)
-    lj = ctx.pinned_empty((npairs, MAX_CORNERS, 2), np.float64)
-    nk = ctx.pinned_empty((npairs,), np.int32)
-    nc = ctx.pinned_empty((npairs,), np.int32)
-    h2d = host.nbytes
-    d2h = li.nbytes + lj.nbytes + nk.nbytes + nc.nbytes
-
-    if world > 1:
-        # multi-GPU: every rank's tracks go to rank 0 over NCCL (padded gather of the device-resident results),
-        # rank 0 then reads everything back to pinned host memory
-        v_li, v_lj, v_nk, v_nc = pairs.torch_views(npairs)
-        if rank == 0:
-            g_li = [torch.empty_like(v_li) for _ in range(world)]
-            g_lj = [torch.empty_like(v_lj) for _ in range(world)]
-            g_nk = [torch.empty_like(v_nk) for _ in range(world)]
-            g_nc = [torch.empty_like(v_nc) for _ in range(world)]
-            h_li = torch.empty((world,) + tuple(v_li.shape), dtype=v_li.dtype, pin_memory=True)
-            h_lj = torch.empty((world,) + tuple(v_lj.shape), dtype=v_lj.dtype, pin_memory=True)
-            h_nk = torch.empty((world, npairs), dtype=torch.int32, pin_memory=True)
-            h_nc = torch.empty((world, npairs), dtype=torch.int32, pin_memory=True)
-            d2h = h_li.numel() * 8 + h_lj.numel() * 8 + h_nk.numel() * 4 + h_nc.numel() * 4
-        else:
-            g_li = g_lj = g_nk = g_nc = None
-            d2h = 0
-
-    def step_e2e():
-        if world == 1:
-            # the library's streaming call: H2D of chunk c+1 || pyramid + corners + KLT of chunk c || D2H of chunk c-1
-            pairs.run_host(frames, host, cfg, li, lj, nk, nc, chunk=args.chunk)
-            return
-        # same streaming call (chunked H2D || pyramids + corners + KLT), results stay on the device for the NCCL gather
-        t_a = time.perf_counter()
-        pairs.run_host(frames, host, cfg, None, None, None, None, chunk=args.chunk)
-        ctx.sync()  # results are written on the library's streams; NCCL runs on torch's
-        t_b = time.perf_counter()
-        dist.gather(v_nk, g_nk, dst=0)
-        dist.gather(v_nc, g_nc, dst=0)
-        dist.gather(v_li, g_li, dst=0)
-        dist.gather(v_lj, g_lj, dst=0)
-        torch.cuda.synchronize()
-        t_c = time.perf_counter()
-        if rank == 0:
-            for r in range(world):
-                h_li[r].copy_(g_li[r], non_blocking=True)
-                h_lj[r].copy_(g_lj[r], non_blocking=True)
-                h_nk[r].copy_(g_nk[r], non_blocking=True)
-                h_nc[r].copy_(g_nc[r], non_blocking=True)
-        torch.cuda.synchronize()
-        e2e_parts.update(stream_call_ms=(t_b - t_a) * 1e3, nccl_gather_ms=(t_c - t_b) * 1e3, d2h_rank0_ms=(time.perf_counter() - t_c) * 1e3)
-
-    e2e_parts = {}
-    # the PCIe floor of the e2e step: the same frames, upload only
-    frames.upload_ptr(0, nfr, host.ctypes.data)
+    # ---- RANSAC half of the metric (C4), rank-local: the seeded sampler's octets through the device solver, then scoring ------
+    xi, xj = c4_points(RS_N)
+    idx8 = ctx.ransac_sample(RS_N, RS_H * 8).reshape(RS_H, 8)
+    t0 = time.perf_counter()
+    ctx.ransac_hypotheses(xi, xj, idx8, fetch=False)
     ctx.sync()
     ctx.timer_start()
-    frames.upload_ptr(0, nfr, host.ctypes.data)
-    h2d_only_ms = ctx.timer_stop()
-
-    e2e_steps = max(1, min(args.steps, 3))
-    step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    ctx.timer_start()
-    for _ in range(e2e_steps):
-        step_e2e()
-    e2e_ms_dev = ctx.timer_stop()
-    e2e_wall = (time.perf_counter() - t0) * 1e3
-    e2e_ms = max(e2e_ms_dev, e2e_wall) / e2e_steps
-    if world == 1:
-        assert int(nc.sum()) == n_tracks and int(nk.sum()) == n_kept, "e2e results differ from the resident run"
-    elif rank == 0:
-        assert int(h_nc[0].sum()) == n_tracks and int(h_nk[0].sum()) == n_kept, "gathered results differ from the resident run"
-
-    # ---- RANSAC half of the metric (C4), rank-local ---------------------------------------------------------------------
-    xi, xj = c4_points(RS_N)
-    E = synthetic_hypotheses(RS_H)
-    ctx.ransac_upload(xi, xj, E)
+    ctx.ransac_hypotheses(xi, xj, idx8, fetch=False)
+    solver_ms = ctx.timer_stop()
     for _ in range(3):
         ctx.ransac_score_resident(1e-3, fetch=False)
     ctx.sync()
@@ -413,12 +638,9 @@ def main():
     for _ in range(RS_REP):
         ctx.ransac_score_resident(1e-3, fetch=False)
     rs_ms = ctx.timer_stop() / RS_REP
-    t0 = time.perf_counter()
-    counts, bh, inl = ctx.ransac_score(xi, xj, E, 1e-3)
-    rs_e2e_ms = (time.perf_counter() - t0) * 1e3
+    bh, bn = ctx.ransac_score_resident(1e-3)
 
-    # ---- the reference's own two-view entry point through the C++ shim: host solver (bit-identical hypotheses) vs the
-    # opt-in device solver, TempleRing-sized call (2500 iterations x 2200 correspondences, sfm.cpp:1739)
+    # ---- the reference's own two-view entry point through the C++ shim (TempleRing-sized call, sfm.cpp:1739) ---------------------
     find_e = None
     if rank == 0:
         try:
@@ -443,108 +665,74 @@ def main():
         except Exception as ex:  # the shim is optional for the bench line
             find_e = {"error": str(ex)[:200]}
 
-    # ---- reduce over ranks: max time, summed work; gather per-pair counts to rank 0 with NCCL --------------------------------
-    ms_step = ms_total / args.steps
-    vals = torch.tensor([ms_step, e2e_ms, rs_ms, pyr_ms, st["klt"], st["corner_score"], st["corner_select"]], device="cuda",
-                        dtype=torch.float64)
-    work = torch.tensor([n_tracks, n_kept, n_it], device="cuda", dtype=torch.int64)
+    rs_t = torch.tensor([rs_ms, solver_ms], device="cuda", dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-        dist.all_reduce(work, op=dist.ReduceOp.SUM)
-        d2h_t = torch.tensor([d2h], device="cuda", dtype=torch.int64)
-        dist.all_reduce(d2h_t, op=dist.ReduceOp.SUM)
-        d2h = int(d2h_t.item())
-    ms_step, e2e_ms, rs_ms, pyr_ms, klt_ms, cs_ms, sel_ms = [float(v) for v in vals.tolist()]
-    tracks_all, kept_all, it_all = [int(v) for v in work.tolist()]
+        dist.all_reduce(rs_t, op=dist.ReduceOp.MAX)
+    rs_ms, solver_ms = [float(v) for v in rs_t.tolist()]
 
     if rank == 0:
         hbm_peak, peak_src = measured_peaks()
-        value = tracks_all / (ms_step * 1e-3)
-        e2e_val = tracks_all / (e2e_ms * 1e-3)
-        per_rank_tracks = tracks_all / world
         prof = profile_metrics()
+        value = r["tracks"] / (r["ms_step"] * 1e-3)
+        e2e_val = r["tracks"] / (r["e2e_ms"] * 1e-3)
+        blk = stage_block(wl, r, world, hbm_peak)
+        stage = blk["stages_ms"]
+        dominant = max(("klt", "corner_score", "corner_select", "ransac"), key=lambda k: stage[k])
         kq = prof.get("klt_quad_kernel", {})
         traffic = (kq.get("dram_read_bytes", 0) + kq.get("dram_write_bytes", 0)) or None
-        klt_kernels = "klt_quad_kernel (+ klt_lane_kernel<...,masked> / klt_kernel<5,true> on border features)"
-        klt_bytes = B_KLT * per_rank_tracks
-        achieved = klt_bytes / (klt_ms * 1e-3) / 1e9
-        pyr_bytes = nfr * W * H * sum(0.25 ** l for l in range(LEVELS))
+        klt_gbs = blk["stage_rooflines"]["klt"]["achieved"]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_cfg(world, nfr),
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * (world if world == 1 else 1),
-                    "gather": "none (1 GPU)" if world == 1 else f"NCCL gather of tracks + counts to rank 0, {world} ranks",
-                    "cpus_bound_near_gpu": near_cpus, "rank0_parts_ms": e2e_parts or None,
-                    "ms_per_step": e2e_ms, "steps": e2e_steps,
-                    "h2d_only_ms": h2d_only_ms, "h2d_only_gb_per_s": h2d / (h2d_only_ms * 1e-3) / 1e9,
-                    "note": "upload of the frames alone takes h2d_only_ms on rank 0: the end-to-end step is PCIe-bound"},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": klt_kernels, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": traffic,
-                         "traffic_source": "dram__bytes_read+write of one klt_quad_kernel launch, ncu --set full on 998 C2 pairs (profiles/r1_metrics.json)",
-                         "peak_source": peak_src,
-                         "note": "KLT is bound by instruction issue (integer-valued FP32 matrix build + FP64 iterations), not HBM "
-                                 "(SURVEY.md §8d: ~140 flop/B): see roofline_issue"},
-            # The reference formulation costs 5,045 FP64 flop per LK iteration; the kernel evaluates the same sums as quadratic
-            # forms over exact integer matrices, so "reference flops per second" may exceed the FP64 peak - it is a speed
-            # figure, not a utilisation.  Utilisation = issue slots (ncu, committed capture).
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": r["steps"], "warmup": r["warmup"],
+            "ms_per_step": r["ms_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_cfg(wl, world, nframes_total),
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": int(r["d2h"]),
+                    "gather": "none (1 GPU)" if world == 1 else f"NCCL point-to-point blocks to rank 0 ({world} ranks), li and inlier indices as int16; "
+                              "rank 0 reads each block back while the next arrives",
+                    "cpus_bound_near_gpu": near_cpus, "rank0_parts_ms": r["parts"] or None, "ms_per_step": r["e2e_ms"], "steps": r["e2e_steps"],
+                    "h2d_floor_ms": r["h2d_floor_ms"], "h2d_floor_gb_per_s": r["h2d"] / (r["h2d_floor_ms"] * 1e-3) / 1e9,
+                    "floor_over_e2e": r["h2d_floor_ms"] / r["e2e_ms"],
+                    "note": "h2d_floor_ms = all ranks upload their frames at the same time and do nothing else (max over ranks): the "
+                            "PCIe / host-memory floor of the end-to-end step at this N"},
+            "parity_in_bench": r["parity"]["ok"] if r["parity"] else None,
+            "parity_detail": r["parity"],
+            "gpu_launches": r["launches"],
+            "clocks": r["clocks"],
+            "roofline": {"bound": "hbm", "kernel": "klt_quad_kernel (+ klt_lane_kernel<...,masked> / klt_kernel<5,true> on border features)",
+                         "achieved": klt_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": klt_gbs / hbm_peak, "traffic": traffic,
+                         "traffic_source": f"dram__bytes_read+write of one klt_quad_kernel launch, ncu --set full ({kq.get('source', 'profiles/')}; static, not re-measured)",
+                         "peak_source": peak_src, "dominant_stage_by_time": dominant,
+                         "note": "KLT is the largest front-end stage; it is bound by instruction issue (integer-valued FP32 matrix build + FP64 "
+                                 "iterations), not HBM (SURVEY.md §8d: ~140 flop/B), so the HBM fraction is a few percent by construction; "
+                                 "stage_rooflines has the HBM-bound stages (pyramid, corner score)"},
             "roofline_issue": {"kernel": "klt_quad_kernel", "bound": "instruction issue",
-                               "issue_active_frac": (kq.get("issue_active_pct") or 0) / 100.0 or None,
-                               "fp64_pipe_frac": (kq.get("fp64_pipe_pct") or 0) / 100.0 or None,
-                               "source": "profiles/r1_metrics.json (ncu smsp__issue_active / sm__pipe_fp64_cycles_active, not re-measured here)",
-                               "reference_formulation_tflops": F_KLT_IT * (it_all / world) / (klt_ms * 1e-3) / 1e12,
+                               "issue_active_frac_static": (kq.get("issue_active_pct") or 0) / 100.0 or None,
+                               "fp64_pipe_frac_static": (kq.get("fp64_pipe_pct") or 0) / 100.0 or None,
+                               "source": f"{kq.get('source', 'profiles/')} (ncu smsp__issue_active / sm__pipe_fp64_cycles_active: STATIC quote of the committed capture, not measured in this run)",
+                               "reference_formulation_tflops": F_KLT_IT * (r["iters"] / world) / (r["klt_ms"] * 1e-3) / 1e12,
                                "fp64_peak_tflops": fp64_peak, "fp64_peak_source": "in-run DFMA micro-benchmark (sfmgpu_fp64_peak)",
-                               "flop_per_lk_iteration_reference": F_KLT_IT, "lk_iterations": it_all // world},
-            "stages_ms": {"pyramid": pyr_ms, "corner_score": cs_ms, "corner_select": sel_ms, "klt": klt_ms, "compact": st["compact"]},
-            "stage_rooflines": {
-                "pyramid": {"bound": "hbm", "achieved": pyr_bytes / (pyr_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                            "frac": pyr_bytes / (pyr_ms * 1e-3) / 1e9 / hbm_peak},
-                "corner_score": {"bound": "hbm", "achieved": npairs * W * H / (cs_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                 "frac": npairs * W * H / (cs_ms * 1e-3) / 1e9 / hbm_peak, "mpx_per_s": npairs * W * H / (cs_ms * 1e-3) / 1e6},
-            },
-            "kept_fraction": kept_all / max(tracks_all, 1),
+                               "flop_per_lk_iteration_reference": F_KLT_IT, "lk_iterations": r["iters"]},
+            "stages_ms": blk["stages_ms"], "stage_rooflines": blk["stage_rooflines"],
+            "kept_fraction": r["kept"] / max(r["tracks"], 1),
             "ransac": {"value": RS_H * RS_N / (rs_ms * 1e-3), "unit": "hyp*pts/s", "ms": rs_ms, "hypotheses": RS_H, "points": RS_N,
-                       "e2e_value": RS_H * RS_N / (rs_e2e_ms * 1e-3), "best_h": int(bh), "best_inliers": int(len(inl)),
-                       # 35 flop per pair in the reference formulation; the kernel screens in FP32 and runs the FP64
-                       # arithmetic only for undecided pairs, so this is a speed figure relative to the DFMA peak
+                       "solver_ms": solver_ms, "solver_hyp_per_s": RS_H / (solver_ms * 1e-3), "best_h": int(bh), "best_inliers": int(bn),
                        "reference_formulation_tflops_over_fp64_peak": F_RS * RS_H * RS_N / (rs_ms * 1e-3) / 1e12 / fp64_peak,
-                       "issue_active_frac": (prof.get("ransac_count_kernel", {}).get("issue_active_pct") or 0) / 100.0 or None,
-                       "hypotheses_source": "synthetic [t]x R around the C4 motion (scoring cost is value-independent)",
+                       "issue_active_frac_static": (prof.get("ransac_count_kernel", {}).get("issue_active_pct") or 0) / 100.0 or None,
+                       "hypotheses_source": "device sampler (std::mt19937(12345) + uniform_int_distribution, bit-exact octets) + device 8-point solver on the C4 points",
                        "find_E_ransac": find_e},
         }
-        if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(host)
+        if r["cpu"]:
+            line["cpu_baseline"] = r["cpu"]
+        if c2:
+            b2 = stage_block(WORKLOADS["c2"], c2, world, hbm_peak)
+            line["c2"] = {"config": workload_cfg(WORKLOADS["c2"], world, c2["nframes"])["workload"], "value": c2["tracks"] / (c2["ms_step"] * 1e-3),
+                          "ms_per_step": c2["ms_step"], "steps": c2["steps"], "warmup": c2["warmup"],
+                          "e2e_value": c2["tracks"] / (c2["e2e_ms"] * 1e-3), "e2e_ms_per_step": c2["e2e_ms"], "h2d_floor_ms": c2["h2d_floor_ms"],
+                          "parity_in_bench": c2["parity"]["ok"] if c2["parity"] else None, "parity_detail": c2["parity"],
+                          "stages_ms": b2["stages_ms"], "stage_rooflines": b2["stage_rooflines"], "kept_fraction": c2["kept"] / max(c2["tracks"], 1)}
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-
-
-def cpu_baseline(host_frames):
-    """The reference's CPU path on this box's host cores, bounded sample of the same frames (reported, not the target)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle
-    chk, kind = oracle.best()
-    cores = os.cpu_count() or 1
-    threads = max(1, min(cores, 64))
-    sample = np.ascontiguousarray(host_frames[:threads + 1])
-    t0 = time.perf_counter()
-    tracks, kept = chk.pair_frontend_mt(sample, MAX_CORNERS, threads)
-    dt = time.perf_counter() - t0
-    xi, xj = c4_points(RS_N)
-    Hs = 64 * threads
-    E = synthetic_hypotheses(Hs)
-    t1 = time.perf_counter()
-    chk.ransac_score_mt(xi, xj, E, 1e-3, threads)
-    rs = Hs * RS_N / (time.perf_counter() - t1)
-    t2 = time.perf_counter()
-    one_tracks, _ = chk.pair_frontend_mt(sample[:2], MAX_CORNERS, 1)  # the reference is single-threaded: one pair on one core
-    one_core = one_tracks / (time.perf_counter() - t2)
-    return {"value": tracks / dt, "unit": UNIT, "cores": threads, "kind": kind, "one_core_value": one_core,
-            "sample": f"first {threads} pairs of the same sequence, one per host thread ({tracks} feature-tracks in {dt:.2f} s wall)",
-            "ransac_hyp_pts_per_s": rs}
 
 
 if __name__ == "__main__":

@@ -275,11 +275,13 @@ static int stage_klt(sfmgpu_ctx* ctx, const ChunkArgs& c) {
     StageTimer st(ctx, 2);
     SFM_TRY(sfm_klt_launch(ctx, k));
   }
-  StageTimer st(ctx, 3);
-  SFM_LAUNCH(ctx, compact_kernel, c.npairs, 1024, 0, out->xy0 + so, out->p1 + so, out->keep + so, (const int*)nullptr,
-             out->ncorn + c.pair_off, out->cap, out->li + so, out->lj + so, (int*)nullptr, out->nkept + c.pair_off);
-  SFM_LAUNCH(ctx, totals_kernel, 256, 256, 0, out->ncorn + c.pair_off, out->nkept + c.pair_off, out->nit + so, c.npairs, out->cap,
-             out->totals);
+  {
+    StageTimer st(ctx, 3);
+    SFM_LAUNCH(ctx, compact_kernel, c.npairs, 1024, 0, out->xy0 + so, out->p1 + so, out->keep + so, (const int*)nullptr,
+               out->ncorn + c.pair_off, out->cap, out->li + so, out->lj + so, (int*)nullptr, out->nkept + c.pair_off);
+    SFM_LAUNCH(ctx, totals_kernel, 256, 256, 0, out->ncorn + c.pair_off, out->nkept + c.pair_off, out->nit + so, c.npairs, out->cap,
+               out->totals);
+  }
   if (sfm_two_view_enabled(out)) {  // the unit's last step: find_E_ransac on the survivors of every pair (:1855-1857)
     StageTimer rt(ctx, 4);
     SFM_TRY(sfm_two_view_stage(ctx, out, c.pair_off, c.npairs, nullptr));
@@ -306,7 +308,14 @@ static ChunkArgs chunk_args(sfmgpu_frames* f, int first_frame, int pair_off, int
 static int pair_range(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int pair_off, int npairs, const sfmgpu_lkcfg* cfg,
                       sfmgpu_pairs* out) {
   if (npairs == 0) return 0;
-  const int chunk = npairs < 1024 ? npairs : 1024;  // frames per corner launch: >= 4 blocks per SM keeps the select kernel busy
+  // frames per corner launch: >= 4 blocks per SM keeps the one-block-per-frame selection kernels busy; large frames are
+  // limited by the work area instead (57 MB per 4K frame: 16 GiB hold 280 of them - still two waves of blocks)
+  ChunkArgs c1 = chunk_args(f, first_frame, pair_off, 1, cfg, out, &out->work[0]);
+  const size_t per_frame = sfm_corner_work_bytes_md(f->w, f->h, 1, c1.cand_cap, c1.md);
+  long long by_mem = (long long)(((size_t)16 << 30) / (per_frame ? per_frame : 1));
+  if (by_mem < 2 * ctx->n_sm) by_mem = 2 * ctx->n_sm;
+  int chunk = npairs < 1024 ? npairs : 1024;
+  if (chunk > by_mem) chunk = (int)by_mem;
   ChunkArgs c0 = chunk_args(f, first_frame, pair_off, chunk, cfg, out, &out->work[0]);
   SFM_TRY(sfm_reserve(ctx, out->work[0], sfm_corner_work_bytes_md(f->w, f->h, chunk, c0.cand_cap, c0.md)));
   for (int p = 0; p < npairs; p += chunk) {

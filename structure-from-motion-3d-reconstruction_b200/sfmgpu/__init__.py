@@ -243,6 +243,10 @@ class Context:
         buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
         return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
+    def pinned_free(self, arr):
+        """Release an array obtained from pinned_empty (it must not be used afterwards)."""
+        self._ck(self.lib.sfmgpu_host_free(self.h, _vp(arr.ctypes.data)))
+
     # ---- frames / pyramid ----------------------------------------------------------------------
     def frames(self, w, h, nframes, levels=3):
         return Frames(self, w, h, nframes, levels)
