@@ -214,6 +214,35 @@ int sfmgpu_pairs_ransac_device_ptrs(sfmgpu_pairs* p, void** status, void** best,
 /* `count` draws of std::uniform_int_distribution<int>(0, n-1) on std::mt19937(12345), produced by the device sampler. */
 int sfmgpu_ransac_sample(sfmgpu_ctx* ctx, int n, int count, int32_t* out);
 
+/* ---- multi-GPU frame-pair scheduler: one rank (process or thread) per GPU ---------------------------------
+ * The two-view unit (:1836-1857) is stateless per frame pair: ONE sequence shards by contiguous blocks of pairs plus one
+ * halo frame per rank (whole sequences shard the same way), with no data-path collective; the only communication is the
+ * gather of the per-pair results to one rank, ncclSend / ncclRecv grouped into one launch.  NCCL is bound at run time
+ * (dlopen of libnccl.so.2, or SFMGPU_NCCL_LIB): a single-GPU user never needs it. */
+typedef struct sfmgpu_sched sfmgpu_sched;
+#define SFMGPU_SCHED_ID_BYTES 128 /* sizeof(ncclUniqueId) */
+/* Contiguous block [begin, end) of n_items for `rank` of `world` (sizes differ by at most one, lower ranks get the extra). */
+int sfmgpu_sched_shard(int n_items, int world, int rank, int* begin, int* end);
+/* Rank 0 creates the id (ncclGetUniqueId) and hands it to the other ranks out of band (file, MPI, socket ...). */
+int sfmgpu_sched_unique_id(void* id128);
+/* One scheduler per rank, on the context's device.  Either id128 (SFMGPU_SCHED_ID_BYTES from sfmgpu_sched_unique_id:
+ * the communicator is created here, collectively) or nccl_comm (the caller's ncclComm_t, adopted, not destroyed);
+ * world == 1 needs neither. */
+int sfmgpu_sched_create(sfmgpu_ctx* ctx, int world, int rank, const void* id128, void* nccl_comm, sfmgpu_sched** out);
+void sfmgpu_sched_destroy(sfmgpu_ctx* ctx, sfmgpu_sched* s);
+/* Pair-mode shard of a sequence of n_frames for this rank: pairs [pair_begin, pair_end) and the frames
+ * [frame_begin, frame_end) it must hold (frame_end = pair_end + 1: one halo frame). */
+int sfmgpu_sched_pair_shard(const sfmgpu_sched* s, int n_frames, int* pair_begin, int* pair_end, int* frame_begin,
+                            int* frame_end);
+/* Collective: every rank passes its pairs object, whose last batch is its block of the n_pairs_total pairs (in order).
+ * On `root` the host arrays receive the whole sequence: li / lj [n_pairs_total][max_corners][2], n_kept / n_corners
+ * [n_pairs_total]; with_ransac != 0 adds status / best_n [n_pairs_total], inliers [n_pairs_total][max_corners],
+ * R [n_pairs_total][9], t [n_pairs_total][3] (sfmgpu_pairs_ransac*).  Host pointers are ignored on other ranks and may
+ * be NULL on the root.  Returns after the data has landed. */
+int sfmgpu_sched_gather_pairs(sfmgpu_ctx* ctx, sfmgpu_sched* s, sfmgpu_pairs* p, int n_pairs_total, int root, int with_ransac,
+                              double* li_xy, double* lj_xy, int32_t* n_kept, int32_t* n_corners, int32_t* status,
+                              int32_t* best_n, int32_t* inliers, double* R, double* t);
+
 /* ---- stateful tracker: KLTTracker (:323-391) ----------------------------------------------------------
  * A track list never holds more than ROWS = max(max_tracks, min_tracks, 1) + 1 entries; `cap` arguments of that size
  * always suffice. */

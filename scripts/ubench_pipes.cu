@@ -23,8 +23,16 @@ __global__ void probe(double* out, long long* cyc, int seed) {
   const double m = 1.0 + 1e-12 * seed, c = 1e-13 * seed;
   const float mf = 1.0f + 1e-6f * seed, cf = 1e-7f * seed;
   const int hi = 0x43300000 + (seed & 0);
+  unsigned long long q[8];
+  for (int i = 0; i < 8; i++) {
+    const float2 v = make_float2(f[i], f[i] * 1.5f);
+    q[i] = *reinterpret_cast<const unsigned long long*>(&v);
+  }
+  const float2 mv = make_float2(mf, mf), cv = make_float2(cf, cf);
+  const unsigned long long mq = *reinterpret_cast<const unsigned long long*>(&mv), cq = *reinterpret_cast<const unsigned long long*>(&cv);
   __syncthreads();
   const long long t0 = clock64();
+#pragma unroll 1
   for (int it = 0; it < ITER; it++) {
     if (MODE == 0) {  // DFMA
 #define S(i) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(m), "d"(c));
@@ -74,6 +82,30 @@ __global__ void probe(double* out, long long* cyc, int seed) {
 #define S(i) { float t; asm volatile("cvt.rn.f32.s32 %0, %1;" : "=f"(t) : "r"(n[i])); n[i] ^= __float_as_int(t); }
       BODY8(S)
 #undef S
+    } else if (MODE == 12) {  // FFMA2 (fma.rn.f32x2: two FP32 FMAs per lane and instruction, sm_100+)
+#define S(i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(q[i]) : "l"(mq), "l"(cq));
+      BODY8(S)
+#undef S
+    } else if (MODE == 13) {  // FFMA2 + LOP3 1:1 (does the packed FMA free issue slots for the integer pipe?)
+#define S(i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(q[i]) : "l"(mq), "l"(cq)); \
+             asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(n[i]) : "r"(seed), "r"(hi));
+      BODY8(S)
+#undef S
+    } else if (MODE == 14) {  // FFMA + LOP3 1:1
+#define S(i) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[i]) : "f"(mf), "f"(cf)); \
+             asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(n[i]) : "r"(seed), "r"(hi));
+      BODY8(S)
+#undef S
+    } else if (MODE == 15) {  // FFMA2 + 2 LOP3
+#define S(i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(q[i]) : "l"(mq), "l"(cq)); \
+             asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(n[i]) : "r"(seed), "r"(hi)); \
+             asm volatile("lop3.b32 %0, %0, %1, %2, 0x69;" : "+r"(n[i]) : "r"(hi), "r"(seed));
+      BODY8(S)
+#undef S
+    } else if (MODE == 16) {  // FADD2
+#define S(i) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(q[i]) : "l"(cq));
+      BODY8(S)
+#undef S
     } else if (MODE == 11) {  // DMUL
 #define S(i) asm volatile("mul.rn.f64 %0, %0, %1;" : "+d"(d[i]) : "d"(m));
       BODY8(S)
@@ -82,7 +114,7 @@ __global__ void probe(double* out, long long* cyc, int seed) {
   }
   const long long t1 = clock64();
   double s = 0;
-  for (int i = 0; i < 8; i++) s += d[i] + n[i] + f[i];
+  for (int i = 0; i < 8; i++) s += d[i] + n[i] + f[i] + (double)(q[i] & 0xffff);
   out[threadIdx.x] = s;
   if ((threadIdx.x & 31) == 0) cyc[threadIdx.x >> 5] = t1 - t0;
 }
@@ -118,6 +150,11 @@ int main() {
   run<8>("DFMA + FFMA pair", 1, out, cyc);
   run<9>("DFMA + 2 FFMA triple", 1, out, cyc);
   run<10>("I2F.F32.S32 (+LOP)", 1, out, cyc);
+  run<12>("FFMA2 (f32x2)", 1, out, cyc);
+  run<16>("FADD2 (f32x2)", 1, out, cyc);
+  run<14>("FFMA + LOP3 pair", 1, out, cyc);
+  run<13>("FFMA2 + LOP3 pair", 1, out, cyc);
+  run<15>("FFMA2 + 2 LOP3 triple", 1, out, cyc);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
   return 0;
