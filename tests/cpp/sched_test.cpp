@@ -45,6 +45,9 @@ static int run_rank(int world, int rank, int device, const void* id, int frames,
     fprintf(stderr, "rank %d: no CUDA device %d\n", rank, device);
     return 1;
   }
+  // KLT kernel selection depends on the batch size (lane-per-feature from 6000 features on, warp-per-feature below); the
+  // kernels agree to ~1e-13 px, not bit for bit, so a byte comparison between shardings pins ONE kernel family
+  CK(ctx, sfmgpu_klt_set_mode(ctx, 2));
   sfmgpu_sched* s = nullptr;
   CK(ctx, sfmgpu_sched_create(ctx, world, rank, id, nullptr, &s));
   int p0, p1, f0, f1;
