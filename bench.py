@@ -196,6 +196,8 @@ def run_reference(args, wl, rank):
     chk, kind = oracle.best()
     gen = oracle.port()
     threads = host_threads()
+    if args.workload == "c5":
+        return run_reference_c5(args, chk, gen, kind, threads)
     frames = gen.synth_frames(SEED0, 0, threads + 1, wl["W"], wl["H"], threads=threads)
     K = temple_K()
     times, tracks = [], 0
@@ -227,6 +229,36 @@ def run_reference(args, wl, rank):
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def run_reference_c5(args, chk, gen, kind, threads):
+    """C5 on the host: `threads` independent sequences, one KLTTracker each (one per host thread), 4 frames per step."""
+    from concurrent.futures import ThreadPoolExecutor
+    NF = 4
+    seqs = [gen.synth_frames(SEED0 + q, 0, NF, C5["W"], C5["H"], threads=1) for q in range(threads)]
+
+    def one(q):
+        tr = chk.tracker(max_tracks=C5["corners"], min_tracks=C5["min_tracks"])
+        n = 0
+        for t in range(NF):
+            n += len(tr.tracks()[1]) if t else 0  # tracks entering the step (the first step only resets)
+            tr.step(seqs[q][t])
+        return n
+    times, tracks = [], 0
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            tracks = sum(ex.map(one, range(threads)))
+        if it >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(times)) if times else float("nan")
+    val = tracks / (ms * 1e-3) if times else 0.0
+    sample = f"{threads} sequences x {NF} frames per step (one KLTTracker per host thread), {tracks} feature-tracks"
+    emit({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+          "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+          "config": {"workload": f"C5: independent {C5['W']}x{C5['H']} sequences, tracker mode ({C5['corners']} tracks, replenish below {C5['min_tracks']})"},
+          "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -578,6 +610,139 @@ def measure_workload(args, ctx, wl, nframes_total, rank, local, world, torch, di
     return res
 
 
+C5 = dict(name="C5", W=1920, H=1080, sequences=64, frames=64, corners=2000, min_tracks=818)
+
+
+def measure_c5(args, ctx, rank, local, world, torch, dist, steps, warm, frames_per_seq, check=True):
+    """BASELINE.json configs[4]: a batch of 64 independent 1080p sequences across the GPUs of the box, TRACKER mode
+    (KLTTracker::step semantics per sequence, cpp/src/templering_sfm.cpp:340-391: tracks chain from frame to frame, replenish
+    below min_tracks).  Rank g owns sequences [g*64/N, (g+1)*64/N) and advances them in lock step (sfmgpu_multitracker: one
+    batched launch per stage and step; the next frames travel while the current ones compute).  One bench step = all frames
+    of all sequences.  value: source frames resident in HBM; e2e: source frames in pinned host memory."""
+    import sfmgpu
+    W, H, T = C5["W"], C5["H"], frames_per_seq
+    s0, s1 = shard_range(C5["sequences"], world, rank)
+    S = s1 - s0
+    cfg = sfmgpu.lkcfg(max_tracks=C5["corners"], min_tracks=C5["min_tracks"], pyr_levels=LEVELS)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.sync()
+
+    res = dict(S=S, T=T, tracks=0, ms=float("nan"), e2e_ms=float("nan"), parity=None, launches=0, h2d=0)
+    if S > 0:
+        store = ctx.frames(W, H, T * S, 1)  # frame t of sequence s at index t*S + s: one lock-step's frames are contiguous
+        for t in range(T):
+            for q in range(S):
+                store.synth(t * S + q, 1, SEED0 + s0 + q, t)
+        base, pitch, fstride = store.device_ptr(0)
+        assert pitch == W and fstride == W * H, "1080p rows are 16-byte multiples: the store is dense"
+        host = ctx.pinned_empty((T, S, H, W), np.uint8)
+        for k in range(T * S):
+            host.reshape(T * S, H, W)[k] = store.download(k, 0)
+        mt = ctx.multitracker(S, W, H, cfg)
+        step_bytes = S * W * H
+
+        def one_pass(src):
+            mt.reset()
+            for t in range(T):
+                nxt = src + (t + 1) * step_bytes if t + 1 < T else None
+                mt.step_ptr(src if t == 0 else None, nxt)
+            return mt.totals()[0]
+
+        for _ in range(warm):
+            one_pass(base)
+    barrier()
+    if S > 0:
+        l0 = ctx.launches()
+        t0 = time.perf_counter()
+        ctx.timer_start()
+        for _ in range(steps):
+            tracks = one_pass(base)
+        ms_dev = ctx.timer_stop()
+        res["ms"] = max(ms_dev, (time.perf_counter() - t0) * 1e3) / steps  # the lock-step loop synchronises every step: wall == device
+        res["launches"] = ctx.launches() - l0
+        res["tracks"] = tracks
+    barrier()
+    if S > 0:
+        one_pass(host.ctypes.data)
+    barrier()
+    if S > 0:
+        e2e_steps = max(1, min(steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            one_pass(host.ctypes.data)
+        ctx.sync()
+        res["e2e_ms"] = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        res["h2d"] = T * step_bytes
+    barrier()
+    # parity: the first and the last sequence of rank 0 against the reference tracker on the first frames (ids bit-exact,
+    # positions within the KLT tolerance, the track list after every step)
+    if check and rank == 0 and S > 0 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle
+        from concurrent.futures import ThreadPoolExecutor
+        chk, kind = oracle.best()
+        nchk = min(T, 8)
+        seqs = sorted({0, S - 1})
+        mt.reset()
+        got = []
+        for t in range(nchk):
+            out = mt.step(host[t])
+            got.append([(out[q], mt.tracks(q)) for q in seqs])
+
+        def ref_seq(q):
+            tr = chk.tracker(max_tracks=C5["corners"], min_tracks=C5["min_tracks"])
+            outs = []
+            for t in range(nchk):
+                o = tr.step(host[t, q])
+                outs.append((o, tr.tracks()))
+            return outs
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=len(seqs)) as ex:
+            want = list(ex.map(ref_seq, seqs))
+        ok, worst, nsteps = True, 0.0, 0
+        for k, q in enumerate(seqs):
+            for t in range(nchk):
+                (gp, gc, gi), (gxy, gids) = got[t][k]
+                (wp, wc, wi), (wxy, wids) = want[k][t]
+                same = len(gi) == len(wi) and np.array_equal(gi, wi) and np.array_equal(gids, wids)
+                if same and len(gi):
+                    dev = max(float(np.abs(gp - wp).max()), float(np.abs(gc - wc).max()), float(np.abs(gxy - wxy).max()))
+                    worst = max(worst, dev)
+                    same = dev <= KLT_TOL
+                ok = ok and same
+                nsteps += 1
+        res["parity"] = {"ok": ok, "sequences_checked": [int(s0 + q) for q in seqs], "steps_each": nchk, "max_pos_dev_px": worst,
+                         "tolerance_px": KLT_TOL, "bit_exact": ["survivor ids", "track-list ids"], "checker": kind,
+                         "reference_s": time.perf_counter() - t0}
+    if S > 0:
+        mt.close()
+        store.close()
+        ctx.pinned_free(host)
+    vals = torch.tensor([res["ms"] if S else 0.0, res["e2e_ms"] if S else 0.0], device="cuda", dtype=torch.float64)
+    work = torch.tensor([res["tracks"], res["launches"], res["h2d"]], device="cuda", dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    res["ms"], res["e2e_ms"] = [float(v) for v in vals.tolist()]
+    res["tracks"], res["launches"], res["h2d"] = [int(v) for v in work.tolist()]
+    return res
+
+
+def c5_block(r, world, steps, warm):
+    return {"config": f"C5: {C5['sequences']} independent synthetic {C5['W']}x{C5['H']} sequences x {r['T']} frames, tracker mode "
+                      f"(KLTTracker::step per sequence: {C5['corners']} tracks, replenish below {C5['min_tracks']}), "
+                      f"{C5['sequences'] // world if C5['sequences'] % world == 0 else str(C5['sequences']) + '/' + str(world)} sequences per GPU in lock step",
+            "value": r["tracks"] / (r["ms"] * 1e-3), "unit": UNIT, "ms_per_step": r["ms"], "steps": steps, "warmup": warm,
+            "lockstep_steps_per_s": C5["sequences"] * r["T"] / (r["ms"] * 1e-3),
+            "e2e_value": r["tracks"] / (r["e2e_ms"] * 1e-3), "e2e_ms_per_step": r["e2e_ms"], "h2d_bytes_per_step": r["h2d"],
+            "feature_tracks_per_step": r["tracks"], "gpu_launches": r["launches"], "scaling": "strong",
+            "parity_in_bench": r["parity"]["ok"] if r["parity"] else None, "parity_detail": r["parity"]}
+
+
 def stage_block(wl, r, world, hbm_peak):
     per_rank_tracks = r["tracks"] / world
     nfr, W, H = r["frames_rank0"], wl["W"], wl["H"]
@@ -604,8 +769,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c2"],
-                    help="c3 (default): 4K x 2000 frames, 8000 corners, pair-sharded; c2: 1080p x 1000 frames, 2000 corners")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c5"],
+                    help="c3 (default): 4K x 2000 frames, 8000 corners, pair-sharded; c2: 1080p x 1000 frames, 2000 corners; "
+                         "c5: 64 independent 1080p sequences in tracker mode (attached to the default line as 'c5')")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 side measurement of the default line")
     ap.add_argument("--frames", type=int, default=0, help="frames of the sequence (default: the workload's own length)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (cpu_baseline, parity_in_bench)")
     ap.add_argument("--no-c2", action="store_true", help="skip the C2 side measurement of the default line")
@@ -614,7 +781,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="frames per chunk of the streaming e2e call (0: a tenth of the rank's frames)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
-    wl = WORKLOADS[args.workload]
+    wl = WORKLOADS["c3" if args.workload == "c5" else args.workload]
     nframes_total = args.frames or wl["frames"]
 
     rank = int(os.environ.get("RANK", "0"))
@@ -640,7 +807,13 @@ def main():
     if args.klt_mode:
         ctx.klt_set_mode(args.klt_mode)
 
+    if args.workload == "c5":
+        run_c5_line(args, ctx, rank, local, world, torch, dist, near_cpus)
+        return
     r = measure_workload(args, ctx, wl, nframes_total, rank, local, world, torch, dist, full=True)
+    c5 = None
+    if args.workload == "c3" and not args.no_c5 and not args.frames:
+        c5 = measure_c5(args, ctx, rank, local, world, torch, dist, max(1, min(args.steps, 3)), 1, C5["frames"], check=(world == 1))
     c2 = None
     if args.workload == "c3" and world == 1 and not args.no_c2 and not args.frames:
         c2 = measure_workload(args, ctx, WORKLOADS["c2"], WORKLOADS["c2"]["frames"], rank, local, world, torch, dist, full=False)
@@ -754,6 +927,41 @@ def main():
                           "e2e_value": c2["tracks"] / (c2["e2e_ms"] * 1e-3), "e2e_ms_per_step": c2["e2e_ms"], "h2d_floor_ms": c2["h2d_floor_ms"],
                           "parity_in_bench": c2["parity"]["ok"] if c2["parity"] else None, "parity_detail": c2["parity"],
                           "stages_ms": b2["stages_ms"], "stage_rooflines": b2["stage_rooflines"], "kept_fraction": c2["kept"] / max(c2["tracks"], 1)}
+        if c5:
+            line["c5"] = c5_block(c5, world, max(1, min(args.steps, 3)), 1)
+        emit(line)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_c5_line(args, ctx, rank, local, world, torch, dist, near_cpus):
+    """--workload c5 as the bench line itself."""
+    T = args.frames or C5["frames"]
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    r = measure_c5(args, ctx, rank, local, world, torch, dist, args.steps, args.warmup, T)
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        blk = c5_block(r, world, args.steps, args.warmup)
+        hbm_peak, peak_src = measured_peaks()
+        klt_gbs = B_KLT * r["tracks"] / world / (r["ms"] * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": blk["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": {"workload": blk["config"], "sequences": C5["sequences"], "frames_per_sequence": T,
+                                                "width": C5["W"], "height": C5["H"], "max_tracks": C5["corners"], "min_tracks": C5["min_tracks"],
+                                                "sharding": f"whole sequences per rank x{world}, lock step per rank, no collective",
+                                                "l2_policy": "every lock-step reads fresh frames (133 MB per 64 sequences): no reuse across steps"},
+                "e2e": {"value": blk["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": 4 * C5["sequences"] * T,
+                        "ms_per_step": r["e2e_ms"], "cpus_bound_near_gpu": near_cpus,
+                        "note": "frames come from pinned host memory, the next lock-step's frames travel while the current one computes; "
+                                "survivor counts return every step (the track lists stay on the device until asked for)"},
+                "parity_in_bench": blk["parity_in_bench"], "parity_detail": blk["parity_detail"], "gpu_launches": r["launches"], "clocks": clocks,
+                "roofline": {"bound": "hbm", "kernel": "KLT chain of the lock-step tracker", "achieved": klt_gbs, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": klt_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                             "note": "whole lock-step (upload wait + pyramid + KLT + compaction + replenish) over the KLT algorithmic bytes"},
+                "lockstep_steps_per_s": blk["lockstep_steps_per_s"]}
         emit(line)
     if world > 1:
         dist.barrier()

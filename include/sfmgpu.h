@@ -89,7 +89,9 @@ int sfmgpu_host_free(sfmgpu_ctx* ctx, void* p);
 /* Storage for `nframes` images of w x h with `levels` pyramid levels (level 0 = the image itself). */
 int sfmgpu_frames_create(sfmgpu_ctx* ctx, int w, int h, int nframes, int levels, sfmgpu_frames** out);
 void sfmgpu_frames_destroy(sfmgpu_ctx* ctx, sfmgpu_frames* f);
-/* Host -> level 0 of frames [first, first+count); host_pix = count images, each w*h bytes, stride w. */
+/* Host -> level 0 of frames [first, first+count); host_pix = count images, each w*h bytes, stride w.  Here and in the
+ * tracker / multitracker / streaming entry points an image pointer may also be DEVICE memory of the context's GPU
+ * (unified addressing: the copy is then device to device). */
 int sfmgpu_frames_upload(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first, int count, const uint8_t* host_pix);
 /* Same from device memory (row pitch in bytes). */
 int sfmgpu_frames_upload_device(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first, int count, const uint8_t* dev_pix,
@@ -101,6 +103,9 @@ int sfmgpu_pyramid_build(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first, int count
 /* Level geometry and download (parity checks): out = w_l*h_l bytes, stride w_l. */
 int sfmgpu_frames_level_size(const sfmgpu_frames* f, int level, int* w, int* h);
 int sfmgpu_frames_download(sfmgpu_ctx* ctx, sfmgpu_frames* f, int frame, int level, uint8_t* host_out);
+/* Device address of a level (frame k starts at ptr + k * frame_stride, rows are pitch bytes apart): interop with the
+ * caller's own kernels, NCCL, or as an image source for the entry points that accept device pointers. */
+int sfmgpu_frames_device_ptr(const sfmgpu_frames* f, int level, void** ptr, size_t* pitch, size_t* frame_stride);
 
 /* ---- corners: shi_tomasi (:237-302) ---------------------------------------------------------------- */
 /* Raster-ordered candidate list {s >= max*quality} of one frame (:274-285): pixel (x,y) and exact score.
@@ -278,6 +283,8 @@ int sfmgpu_multitracker_step(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, const uint
 int sfmgpu_multitracker_prefetch(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, const uint8_t* host_pix);
 int sfmgpu_multitracker_step_pipelined(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, const uint8_t* host_pix, const uint8_t* next_host_pix,
                                        double* prev_xy, double* cur_xy, int32_t* ids, int32_t* n_out);
+/* Back to the state after create (the next step resets every sequence, ids restart at 0). */
+int sfmgpu_multitracker_reset(sfmgpu_ctx* ctx, sfmgpu_multitracker* t);
 int sfmgpu_multitracker_tracks(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, int sequence, double* xy, int32_t* ids, int cap, int* n_out);
 int sfmgpu_multitracker_totals(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, long long* n_track_steps, long long* n_lk_iters);
 

@@ -42,3 +42,20 @@ for rep in range(2):
 print(f"  batched stage {P} x 4000 x {n}: {dt * 1e3:.1f} ms")
 st, bhh, inl, E, R, t = pairs.ransac_download(3)
 print("  pair 3:", st, bhh, len(inl))
+# solver alone: C4 hypotheses, then a C2-like batch (999 pairs x 4000 hypotheses x 1750 points)
+ctx.sync()
+ctx.timer_start()
+for _ in range(5):
+    ctx.ransac_hypotheses(xi, xj, idx8, fetch=False)
+print(f"  solver {RS_H} hypotheses: {ctx.timer_stop() / 5:.3f} ms")
+P, n, cap = 999, 1750, 2000
+pi, pj = two_view_scene(n, seed=6)
+pairs2 = ctx.pairs(P, cap)
+pairs2.set_matches([pi] * P, [pj] * P)
+for rep in range(2):
+    ctx.sync()
+    t0 = time.perf_counter()
+    pairs2.ransac(temple_K(), 4000, 2e-3, 80, 120)
+    ctx.sync()
+    dt = time.perf_counter() - t0
+print(f"  batched stage {P} x 4000 x {n}: {dt * 1e3:.1f} ms")

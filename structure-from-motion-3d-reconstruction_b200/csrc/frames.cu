@@ -220,7 +220,7 @@ int sfmgpu_frames_upload(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first, int count
   if (count == 0) return 0;
   // frames are contiguous rows on both sides -> one 2D copy of count*h rows
   SFM_CUDA(ctx, cudaMemcpy2DAsync(f->lvl[0] + (size_t)first * f->fstride[0], f->pitch[0], host_pix, f->w, f->w,
-                                  (size_t)f->h * count, cudaMemcpyHostToDevice, ctx->stream));
+                                  (size_t)f->h * count, cudaMemcpyDefault, ctx->stream));
   return 0;
 }
 
@@ -232,6 +232,14 @@ int sfmgpu_frames_upload_device(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first, in
   if (count == 0) return 0;
   SFM_CUDA(ctx, cudaMemcpy2DAsync(f->lvl[0] + (size_t)first * f->fstride[0], f->pitch[0], dev_pix, pitch, f->w,
                                   (size_t)f->h * count, cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
+
+int sfmgpu_frames_device_ptr(const sfmgpu_frames* f, int level, void** ptr, size_t* pitch, size_t* frame_stride) {
+  if (!f || level < 0 || level >= f->levels) return SFMGPU_E_ARG;
+  if (ptr) *ptr = f->lvl[level];
+  if (pitch) *pitch = (size_t)f->pitch[level];
+  if (frame_stride) *frame_stride = f->fstride[level];
   return 0;
 }
 

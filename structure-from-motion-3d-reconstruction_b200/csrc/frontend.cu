@@ -559,7 +559,7 @@ int sfmgpu_pair_frontend_host(sfmgpu_ctx* ctx, sfmgpu_frames* f, const uint8_t* 
   for (int c = 0; c < nchunks; c++) {
     const int a = c * chunk, b = a + chunk < nframes ? a + chunk : nframes;
     SFM_CUDA(ctx, cudaMemcpy2DAsync(f->lvl[0] + (size_t)a * f->fstride[0], f->pitch[0], host_pix + (size_t)a * f->w * f->h, f->w,
-                                    f->w, (size_t)f->h * (b - a), cudaMemcpyHostToDevice, ctx->copy_stream));
+                                    f->w, (size_t)f->h * (b - a), cudaMemcpyDefault, ctx->copy_stream));
     cudaEvent_t up = p.next();
     if (!up) return sfm_fail(ctx, SFMGPU_E_CUDA, "pair_frontend_host: cudaEventCreate failed");
     {
@@ -1049,13 +1049,28 @@ static int multi_prefetch(sfmgpu_ctx* ctx, sfmgpu_multitracker* t, int after_gro
   const int S = t->S, g = (after_group + 1) % 3;
   sfmgpu_frames* f = t->frames;
   SFM_CUDA(ctx, cudaMemcpy2DAsync(f->lvl[0] + (size_t)g * S * f->fstride[0], f->pitch[0], host_pix, f->w, f->w, (size_t)f->h * S,
-                                  cudaMemcpyHostToDevice, ctx->copy_stream));
+                                  cudaMemcpyDefault, ctx->copy_stream));
   {
     StageScope sc(ctx, ctx->copy_stream);
     SFM_TRY(sfmgpu_pyramid_build(ctx, f, g * S, S));
     SFM_CUDA(ctx, cudaEventRecord(t->pf_done, ctx->stream));
   }
   t->prefetched = true;
+  return 0;
+}
+
+// Back to the state after create: the next step resets every sequence again (ids restart at 0).
+int sfmgpu_multitracker_reset(sfmgpu_ctx* ctx, sfmgpu_multitracker* t) {
+  SFM_ENTER(ctx);
+  if (!ctx || !t) return SFMGPU_E_ARG;
+  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->copy_stream) SFM_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  t->parity = -1;
+  t->prefetched = false;
+  t->n.assign(t->S, 0);
+  t->next_id.assign(t->S, 0);
+  t->track_steps = 0;
+  SFM_CUDA(ctx, cudaMemsetAsync(t->tot, 0, 64, ctx->stream));
   return 0;
 }
 

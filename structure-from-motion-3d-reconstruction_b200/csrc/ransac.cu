@@ -74,8 +74,8 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_count_kernel(const double2*
                                                                  float thr_hi_f, int* __restrict__ counts) {
   __shared__ double sE[RS_HCHUNK * 9];
   __shared__ RsHyp sH[RS_HCHUNK];
-  __shared__ int sC[RS_HCHUNK];
-  const int tid = threadIdx.x, lane = tid & 31;
+  __shared__ int sC[RS_THREADS / 32][RS_HCHUNK];  // per-warp counts of the chunk: plain stores, summed once per chunk
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pair = blockIdx.z;
   const int n = npts ? npts[pair] : n_single;
   if ((npts && n < 8) || (int)(blockIdx.x * RS_THREADS * RS_PTS) >= n) return;  // block-uniform
@@ -118,7 +118,6 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_count_kernel(const double2*
       sE[i] = v;
       sH[i / 9].e[i % 9] = (float)v;
     }
-    if (tid < RS_HCHUNK) sC[tid] = 0;
     __syncthreads();
     if (tid < nh) {
       const double* e = sE + tid * 9;
@@ -169,10 +168,15 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_count_kernel(const double2*
           }
       }
       c = __reduce_add_sync(0xffffffffu, c);
-      if (lane == 0 && c) atomicAdd(&sC[h], c);
+      if (lane == 0) sC[warp][h] = c;
     }
     __syncthreads();
-    if (tid < nh && sC[tid]) atomicAdd(&counts[hc + tid], sC[tid]);
+    if (tid < nh) {
+      int t = 0;
+#pragma unroll
+      for (int wq = 0; wq < RS_THREADS / 32; wq++) t += sC[wq][tid];
+      if (t) atomicAdd(&counts[hc + tid], t);
+    }
   }
 }
 

@@ -77,7 +77,13 @@ __device__ __forceinline__ void unit3(double& x, double& y, double& z) {
 // The rotation angle phi = atan2(2 a_pq, a_qq - a_pp) / 2 is evaluated algebraically (half-angle formulas, 1 sqrt + 1 div +
 // 1 sqrt + 1 div) instead of atan2 / sincos: cos and sin agree with libm's to a few ulp, which is the same class of
 // deviation CUDA's own trigonometry has against glibc's.
-constexpr int SV_TPB = 128;
+#ifndef SV_TPB_V
+#define SV_TPB_V 128
+#endif
+#ifndef SV_MINB_V
+#define SV_MINB_V 4
+#endif
+constexpr int SV_TPB = SV_TPB_V, SV_MINB = SV_MINB_V;  // 128 x 4: 16 warps per SM in 184 KB of shared memory, <= 128 registers
 constexpr int SV_TRI = 45;
 constexpr int SV_ROT9 = 120, SV_ROT3 = 80;  // the reference's rotation caps (:622, :551)
 
@@ -241,8 +247,8 @@ __device__ void eight_point_solve(const double2* __restrict__ xi, const double2*
   unsigned char rpq[SV_ROT9];
   int nrot = 0;
   for (; nrot < SV_ROT9; nrot++) {
-    // largest off-diagonal, first in raster order (strict >)
-    int p = 0, q = 1;
+    // largest off-diagonal, first in raster order (strict >); the pivot travels as one code (p * 16 + q)
+    int code = 1;
     double big = 0.0;
 #pragma unroll
     for (int i = 0; i < 9; i++)
@@ -251,18 +257,18 @@ __device__ void eight_point_solve(const double2* __restrict__ xi, const double2*
         const double v = fabs(sA[((i * (17 - i)) / 2 + j) * TPB]);
         if (v > big) {
           big = v;
-          p = i;
-          q = j;
+          code = i * 16 + j;
         }
       }
     if (big < 1e-12) break;
+    const int p = code >> 4, q = code & 15;
     const int ipp = tri_idx(p, p), iqq = tri_idx(q, q), ipq = tri_idx(p, q);
     const double app = sA[ipp * TPB], aqq = sA[iqq * TPB], apq = sA[ipq * TPB];
     double c, s;
     half_angle(2.0 * apq, aqq - app, c, s);
     rc[nrot] = c;
     rs[nrot] = s;
-    rpq[nrot] = (unsigned char)(p * 16 + q);
+    rpq[nrot] = (unsigned char)code;
     for (int k = 0; k < 9; k++) {
       if (k == p || k == q) continue;
       const int ikp = k < p ? tri_idx(k, p) : tri_idx(p, k), ikq = k < q ? tri_idx(k, q) : tri_idx(q, k);
@@ -320,7 +326,7 @@ __device__ void eight_point_solve(const double2* __restrict__ xi, const double2*
 
 // Hypothesis h of pair blockIdx.y: octet idx8[pair][h][8], points xi/xj[pair * stride ...], n = npts[pair] (npts == nullptr:
 // n_single); pairs with fewer than 8 points produce nothing.
-__global__ void __launch_bounds__(SV_TPB, 3) eight_point_kernel(const double2* __restrict__ xi, const double2* __restrict__ xj,
+__global__ void __launch_bounds__(SV_TPB, SV_MINB) eight_point_kernel(const double2* __restrict__ xi, const double2* __restrict__ xj,
                                                                size_t pt_stride, const int* __restrict__ npts, int n_single,
                                                                const int* __restrict__ idx8, int H, double* __restrict__ Eout) {
   extern __shared__ double sv_smem[];

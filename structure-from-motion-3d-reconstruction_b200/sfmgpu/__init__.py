@@ -39,7 +39,7 @@ SYMBOLS = [
     "sfmgpu_pairs_ransac_download", "sfmgpu_pairs_ransac_download_all", "sfmgpu_pairs_ransac_device_ptrs", "sfmgpu_ransac_sample",
     "sfmgpu_pairs_set_matches",
     "sfmgpu_sched_shard", "sfmgpu_sched_unique_id", "sfmgpu_sched_create", "sfmgpu_sched_destroy", "sfmgpu_sched_pair_shard",
-    "sfmgpu_sched_gather_pairs",
+    "sfmgpu_sched_gather_pairs", "sfmgpu_frames_device_ptr", "sfmgpu_multitracker_reset",
 ]
 
 
@@ -150,6 +150,8 @@ def load_library():
         "sfmgpu_pairs_ransac_device_ptrs": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
         "sfmgpu_ransac_sample": (_i, [_vp, _i, _i, _i32p]),
         "sfmgpu_pairs_set_matches": (_i, [_vp, _vp, _i, _f64p, _f64p, _i32p]),
+        "sfmgpu_frames_device_ptr": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+        "sfmgpu_multitracker_reset": (_i, [_vp, _vp]),
         "sfmgpu_sched_shard": (_i, [_i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
         "sfmgpu_sched_unique_id": (_i, [_vp]),
         "sfmgpu_sched_create": (_i, [_vp, _i, _i, _vp, _vp, C.POINTER(_vp)]),
@@ -379,6 +381,12 @@ class Frames:
     def build_pyramid(self, first=0, count=None):
         self.ctx._ck(self.ctx.lib.sfmgpu_pyramid_build(self.ctx.h, self.h_, first, self.n - first if count is None else count))
 
+    def device_ptr(self, level=0):
+        """(device address, row pitch, frame stride) of a level."""
+        ptr, pitch, fs = _vp(), C.c_size_t(0), C.c_size_t(0)
+        self.ctx._ck(self.ctx.lib.sfmgpu_frames_device_ptr(self.h_, level, C.byref(ptr), C.byref(pitch), C.byref(fs)))
+        return ptr.value, pitch.value, fs.value
+
     def level_size(self, level):
         w, h = _i(0), _i(0)
         self.ctx._ck(self.ctx.lib.sfmgpu_frames_level_size(self.h_, level, C.byref(w), C.byref(h)))
@@ -600,6 +608,19 @@ class MultiTracker:
         if not fetch:
             return self.n.copy()
         return [(self.prev[s, :self.n[s]].copy(), self.cur[s, :self.n[s]].copy(), self.ids[s, :self.n[s]].copy()) for s in range(self.S)]
+
+    def step_ptr(self, ptr, next_ptr=None, fetch=False):
+        """step() on raw addresses ([S, h, w] uint8 each; host - ideally pinned - or device memory of this GPU)."""
+        a = (self.prev, self.cur, self.ids) if fetch else (None, None, None)
+        self.ctx._ck(self.ctx.lib.sfmgpu_multitracker_step_pipelined(self.ctx.h, self.h_, _vp(ptr) if ptr else None,
+                                                                     _vp(next_ptr) if next_ptr else None, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]),
+                                                                     self.n.ctypes.data_as(_vp)))
+        if not fetch:
+            return self.n
+        return [(self.prev[s, :self.n[s]].copy(), self.cur[s, :self.n[s]].copy(), self.ids[s, :self.n[s]].copy()) for s in range(self.S)]
+
+    def reset(self):
+        self.ctx._ck(self.ctx.lib.sfmgpu_multitracker_reset(self.ctx.h, self.h_))
 
     def tracks(self, s):
         xy, ids = np.zeros((self.cap, 2)), np.zeros(self.cap, np.int32)
