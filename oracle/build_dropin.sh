@@ -14,11 +14,13 @@ SRC=$REF_DIR/cpp/src/templering_sfm.cpp
 mkdir -p "$HERE/_ref"
 TMP=$(mktemp -d /tmp/sfm_dropin.XXXXXX)
 # guard ranges (1-based, inclusive) of the pinned reference: sample_bilinear, Pyramid+build_pyr, shi_tomasi,
-# LKConfig..KLTTracker, RelPose+find_E_ransac, global_desc_32+dot_desc; the shim is included after the using-declarations (line 30)
+# LKConfig..KLTTracker, RelPose+find_E_ransac (replaced in place by sfmgpu_two_view.hpp, which calls the TU's own solver and SVD),
+# global_desc_32+dot_desc; the front-end shim is included after the using-declarations (line 30)
 awk '
   NR==31  { print "#ifdef USE_SFMGPU"; print "#include \"sfmgpu_shim.hpp\""; print "#endif" }
   NR==183 || NR==220 || NR==237 || NR==307 || NR==640 || NR==1100 { print "#ifndef USE_SFMGPU" }
   { print }
+  NR==761 { print "#else"; print "#include \"sfmgpu_two_view.hpp\"  // RelPose + find_E_ransac on the GPU, with this TU own invert_K / eight_point_E / svd3" }
   NR==198 || NR==232 || NR==302 || NR==466 || NR==761 || NR==1129 { print "#endif" }
 ' "$SRC" > "$TMP/templering_sfm_dropin.cpp"
 CXXF="-std=c++20 -O3 -DNDEBUG -w -I$REF_DIR/cpp/include"

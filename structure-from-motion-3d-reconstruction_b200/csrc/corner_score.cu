@@ -399,6 +399,333 @@ __global__ void __launch_bounds__(256, 3) score_tile_kernel(const uint8_t* __res
   score_tile<MODE>(sm, img + (size_t)(frame0 + fr) * fstride, w, h, pitch, tx * TW, ty * TH, fr, wv, quality);
 }
 
+// ---- fused pass, walk-down form ---------------------------------------------------------------------------------------------
+// One WARP owns a strip of 256 columns (8 per lane) and walks down a segment of rows; a block is 4 horizontally adjacent
+// strips of the same segment.  Per tap row a lane reads its 8 bytes with ONE 64-bit load (a warp reads 256 contiguous
+// bytes, a block 2 KB; two rows are in flight ahead of the arithmetic), takes the 3 + 3 halo bytes from its neighbours'
+// words by shuffle, and keeps the last three rows as integer-valued floats in registers: the gradients of the middle
+// row, their products and the horizontal 5-sums (sliding FFMA in / out, all exact) never leave the register file.  The
+// vertical 5-sum is a running sum per column: add the new row of horizontal sums, subtract the one five rows back,
+// which comes from a per-warp ring in shared memory (lane-contiguous float4: conflict-free, no block barrier anywhere
+// in the kernel).  ~31 instructions per pixel against ~82 of the tile kernel (3 rows converted per thread and row
+// there, two shared-memory round trips, three block barriers per tile).
+// Candidates: as in score_tile<2> - FP32 estimate for every pixel, the exact FP64 score for pixels within the estimate's
+// error of the provisional threshold quality * L, L = max(frame maximum so far, this warp's own exact maximum) <= final
+// maximum; appended to the unordered list with one atomic per warp and row; candidate bitmap words written whole.
+constexpr int WK_COLS = 8, WK_WARPS = 4, WK_MINB = 3, WK_STRIP = 32 * WK_COLS;  // 12 warps per SM: 184 KB of rings, <= 170 registers
+constexpr int WK_RING = 5 * 6 * 32;  // float4 per warp: 5 rows x (24 sums = 6 float4) x 32 lanes
+constexpr int WK_STAGE = 128;        // candidates staged per warp and buffer before their list slots are reserved
+struct WalkStage {                   // two buffers: one fills while the other waits for its reservation (a global atomic)
+  unsigned long long key[2][WK_STAGE];
+  unsigned idx[2][WK_STAGE];
+};
+constexpr size_t WK_SMEM_WARP = WK_RING * sizeof(float4) + sizeof(WalkStage);
+
+__global__ void __launch_bounds__(WK_WARPS * 32, WK_MINB) score_walk_kernel(const uint8_t* __restrict__ img, int w, int h, int pitch,
+                                                                      size_t fstride, int frame0, CornerWorkView wv, double quality,
+                                                                      int seg_rows) {
+  extern __shared__ __align__(16) unsigned char score_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int strip = blockIdx.x * WK_WARPS + warp;
+  const int xs = strip * WK_STRIP;  // first column of the strip
+  if (xs >= w) return;               // no block barrier below: a warp may leave
+  const int x0 = xs + lane * WK_COLS;
+  const int fr = blockIdx.z;
+  const int y_begin = blockIdx.y * seg_rows, y_end = min(h, y_begin + seg_rows);
+  const uint8_t* im = img + (size_t)(frame0 + fr) * fstride;
+  unsigned char* wbase = score_raw + (size_t)warp * WK_SMEM_WARP;
+  float4* ring = reinterpret_cast<float4*>(wbase) + lane;  // [row % 5][k] at ring[(row5 * 6 + k) * 32]
+  WalkStage& stg = *reinterpret_cast<WalkStage*>(wbase + WK_RING * sizeof(float4));
+  // candidate staging: list slots are reserved with ONE global atomic per ~128 candidates, and its result is only needed
+  // when the buffer is written out - one flush later - so the warp never waits for the atomic's round trip
+  int st_cur = 0, st_n = 0, pend_n = 0;
+  unsigned pend_base = 0;  // lane 0: start of the reserved range of the pending buffer
+  const size_t lb_off = (size_t)fr * wv.cand_cap;
+  auto write_out = [&](int buf, int cnt, unsigned base0) {  // staged entries -> their reserved list slots
+    const unsigned base = __shfl_sync(0xffffffffu, base0, 0);
+    for (int e = lane; e < cnt; e += 32) {
+      const unsigned slot = base + (unsigned)e;
+      if (slot < (unsigned)wv.cand_cap) {
+        wv.tmp_idx[lb_off + slot] = stg.idx[buf][e];
+        wv.tmp_key[lb_off + slot] = stg.key[buf][e];
+      }
+    }
+  };
+  auto flush = [&]() {  // write the pending buffer out, reserve slots for the current one, swap
+    __syncwarp();
+    if (pend_n > 0) write_out(st_cur ^ 1, pend_n, pend_base);
+    pend_n = st_n;
+    if (st_n > 0 && lane == 0) pend_base = atomicAdd(wv.ncand + fr, (unsigned)st_n);
+    st_cur ^= 1;
+    st_n = 0;
+    __syncwarp();
+  };
+  unsigned long long* maxbits = wv.maxbits + fr;
+  const int wm1 = w - 1;
+  // a lane whose 14 tap columns x0-3 .. x0+10 are not all inside the image clamps them one by one (image borders only)
+  const bool edge_lane = x0 < 3 || x0 + 10 > wm1;
+  const bool own_inside = x0 + 7 <= wm1;  // the 64-bit load stays inside the row's w bytes
+
+  // raw taps of one row: the lane's 8 bytes + the 4 bytes before the strip (lane 0) / after it (lane 31)
+  struct Raw {
+    uint32_t lo, hi, ext;
+  };
+  auto load_row = [&](int t) {
+    Raw r;
+    t = t < 0 ? 0 : (t > h - 1 ? h - 1 : t);  // clamped tap rows (:242-249)
+    const uint8_t* row = im + (size_t)t * pitch;
+    if (own_inside) {
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(row + x0));
+      r.lo = v.x;
+      r.hi = v.y;
+    } else {  // the lane straddles or lies beyond the right border: clamped byte loads
+      r.lo = r.hi = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        r.lo |= (uint32_t)__ldg(row + min(x0 + k, wm1)) << (8 * k);
+        r.hi |= (uint32_t)__ldg(row + min(x0 + 4 + k, wm1)) << (8 * k);
+      }
+    }
+    r.ext = 0;
+    if (lane == 0) {  // bytes x0-4 .. x0-1 (clamped at the left border)
+      if (x0 >= 4) r.ext = __ldg(reinterpret_cast<const uint32_t*>(row + x0 - 4));
+      else r.ext = 0x01010101u * (uint32_t)__ldg(row);
+    } else if (lane == 31) {  // bytes x0+8 .. x0+11 (clamped at the right border)
+      if (x0 + 11 <= wm1) {
+        r.ext = __ldg(reinterpret_cast<const uint32_t*>(row + x0 + 8));
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) r.ext |= (uint32_t)__ldg(row + min(x0 + 8 + k, wm1)) << (8 * k);
+      }
+    }
+    return r;
+  };
+  // 14 integer-valued floats (2^23 + byte) of tap columns x0-3 .. x0+10
+  auto convert = [&](const Raw& r, float* F) {
+    uint32_t left = __shfl_up_sync(0xffffffffu, r.hi, 1), right = __shfl_down_sync(0xffffffffu, r.lo, 1);
+    if (lane == 0) left = r.ext;
+    if (lane == 31) right = r.ext;
+    uint32_t lo = r.lo, hi = r.hi;
+    if (edge_lane) {  // clamp every tap column into [0, w-1]: replicate the border byte
+      if (x0 < 3) {  // left border: columns < 0 take column 0 (x0 == 0 here: strips start at multiples of 256)
+        left = 0x01010101u * (lo & 0xffu);
+      }
+      if (x0 + 10 > wm1) {  // right border: columns > w-1 take column w-1
+        const int last = wm1 - x0;  // index of the last valid own byte (may be < 0 or >= 8)
+        uint32_t b;
+        if (last < 0) b = 0;  // whole lane beyond the image: its values are never used
+        else if (last < 4) b = (lo >> (8 * last)) & 0xffu;
+        else if (last < 8) b = (hi >> (8 * (last - 4))) & 0xffu;
+        else b = (right >> (8 * (last - 8))) & 0xffu;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (k > last) lo = (lo & ~(0xffu << (8 * k))) | (b << (8 * k));
+          if (4 + k > last) hi = (hi & ~(0xffu << (8 * k))) | (b << (8 * k));
+          if (8 + k > last) right = (right & ~(0xffu << (8 * k))) | (b << (8 * k));
+        }
+      }
+    }
+    F[0] = bytef(left, 1);
+    F[1] = bytef(left, 2);
+    F[2] = bytef(left, 3);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      F[3 + k] = bytef(lo, k);
+      F[7 + k] = bytef(hi, k);
+    }
+    F[11] = bytef(right, 0);
+    F[12] = bytef(right, 1);
+    F[13] = bytef(right, 2);
+  };
+
+  float Fm[14], Fc[14], Fp[14];  // tap rows T-2, T-1, T as floats
+  float V[24];                   // vertical running sums: xx[0..7], xy[0..7], yy[0..7]
+#pragma unroll
+  for (int k = 0; k < 24; k++) V[k] = 0.f;
+  {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 30; k++) ring[k * 32] = z;
+  }
+  __syncwarp();
+  double wmax = 0.0;      // this warp's exact maximum so far (lane-local until published)
+  double lb = 0.0;        // lower bound of the frame maximum the threshold was derived from
+  double thr8 = 0.0;      // provisional 8 * thr
+  float boundf = -EST_MARGIN;
+  unsigned long long gmax_bits = *(volatile unsigned long long*)maxbits;
+  const int T0 = y_begin - 3;  // first tap row
+  Raw r0 = load_row(T0), r1 = load_row(T0 + 1), r2 = load_row(T0 + 2);
+  convert(r0, Fm);
+  convert(r1, Fc);
+  r0 = load_row(T0 + 3);
+  r1 = load_row(T0 + 4);
+  // iteration i: tap row T = T0 + 2 + i arrives, gradient row G = T - 1 = y_begin - 2 + i, and once five rows of horizontal
+  // sums are in (i >= 4) the output row y = G - 2 = y_begin + i - 4 is complete
+  const int n_iter = (y_end - y_begin) + 4;
+  for (int i = 0; i < n_iter; i++) {
+    convert(r2, Fp);
+    r2 = r0;
+    r0 = r1;
+    r1 = load_row(T0 + 5 + i);
+    const int G = T0 + 1 + i;   // gradient / h row
+    const int y = G - 2;        // output row once five h rows are in
+    // running lower bound of the frame maximum -> provisional threshold (re-read every 8 rows; the load is issued four
+    // rows before its value is used)
+    if ((i & 7) == 4) gmax_bits = *(volatile unsigned long long*)maxbits;
+    if ((i & 7) == 0) {
+      const double g = __longlong_as_double(gmax_bits);
+      const double nl = fmax(g, wmax);
+      if (nl > lb || i == 0) {
+        lb = nl;
+        thr8 = 8.0 * ((0.125 * lb) * quality);
+        boundf = __double2float_rd(thr8) - EST_MARGIN;
+      }
+    }
+    // gradients of row G at columns x0-2 .. x0+9, horizontal 5-sums of their products at x0 .. x0+7
+    float gx[12], gy[12];
+#pragma unroll
+    for (int c = 0; c < 12; c++) {
+      gx[c] = Fc[c + 2] - Fc[c];
+      gy[c] = Fp[c + 1] - Fm[c + 1];
+    }
+    float hx[8], hxy[8], hy[8];
+    {
+      float sxx = 0.f, sxy = 0.f, syy = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        sxx = fmaf(gx[c], gx[c], sxx);
+        sxy = fmaf(gx[c], gy[c], sxy);
+        syy = fmaf(gy[c], gy[c], syy);
+      }
+#pragma unroll
+      for (int t = 0; t < 8; t++) {
+        sxx = fmaf(gx[t + 4], gx[t + 4], sxx);
+        sxy = fmaf(gx[t + 4], gy[t + 4], sxy);
+        syy = fmaf(gy[t + 4], gy[t + 4], syy);
+        hx[t] = sxx;
+        hxy[t] = sxy;
+        hy[t] = syy;
+        sxx = fmaf(-gx[t], gx[t], sxx);
+        sxy = fmaf(-gx[t], gy[t], sxy);
+        syy = fmaf(-gy[t], gy[t], syy);
+      }
+    }
+    // vertical: V += h[G] - h[G-5]; the ring slot of row G-5 is the one row G takes
+    {
+      const int slot = (i % 5) * 6 * 32;
+      float4 o[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) o[k] = ring[slot + k * 32];
+      ring[slot + 0 * 32] = make_float4(hx[0], hx[1], hx[2], hx[3]);
+      ring[slot + 1 * 32] = make_float4(hx[4], hx[5], hx[6], hx[7]);
+      ring[slot + 2 * 32] = make_float4(hxy[0], hxy[1], hxy[2], hxy[3]);
+      ring[slot + 3 * 32] = make_float4(hxy[4], hxy[5], hxy[6], hxy[7]);
+      ring[slot + 4 * 32] = make_float4(hy[0], hy[1], hy[2], hy[3]);
+      ring[slot + 5 * 32] = make_float4(hy[4], hy[5], hy[6], hy[7]);
+      const float* of = reinterpret_cast<const float*>(o);
+#pragma unroll
+      for (int t = 0; t < 8; t++) {
+        V[t] += hx[t] - of[t];
+        V[8 + t] += hxy[t] - of[8 + t];
+        V[16 + t] += hy[t] - of[16 + t];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 14; c++) {
+      Fm[c] = Fc[c];
+      Fc[c] = Fp[c];
+    }
+    if (i < 4 || y >= y_end) continue;  // warm-up rows (warp-uniform)
+    // estimates, screen, exact scores of the screened pixels
+    const bool row_interior = y >= 2 && y < h - 2;
+    unsigned flags = 0, border = 0;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+      const int x = x0 + t;
+      const float u = est_u(V[t], V[16 + t], V[8 + t]);
+      const bool interior = row_interior && x >= 2 && x < w - 2;
+      if (interior) {
+        if (u >= boundf) flags |= 1u << t;
+      } else if (x < w && 0.0 >= thr8) {
+        border |= 1u << t;  // border score is exactly 0 (:240, :253-254)
+      }
+    }
+    double ue[8];
+    unsigned cand = border;
+    if (__any_sync(0xffffffffu, flags != 0)) {
+#pragma unroll
+      for (int t = 0; t < 8; t++) {
+        ue[t] = 0.0;
+        if (flags & (1u << t)) {
+          const double u = exact_u(__float2int_rn(V[t]), __float2int_rn(V[16 + t]), __float2int_rn(V[8 + t]));
+          ue[t] = u;
+          wmax = fmax(wmax, u);
+          if (u >= thr8) cand |= 1u << t;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; t++) ue[t] = 0.0;
+    }
+    // candidate bitmap: 4 lanes make one 32-pixel word; every word of the strip's row is written (zeros too)
+    {
+      unsigned wbits = cand;
+      wbits |= __shfl_down_sync(0xffffffffu, wbits, 1) << 8;
+      wbits |= __shfl_down_sync(0xffffffffu, wbits, 2) << 16;
+      if ((lane & 3) == 0 && x0 < w) wv.bitmap[(size_t)fr * wv.words_per_frame + (size_t)y * wv.wpr + (x0 >> 5)] = wbits;
+    }
+    // list append through the staging buffers
+    if (__any_sync(0xffffffffu, cand != 0)) {
+      const int cnt = __popc(cand);
+      int inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+      }
+      const int total = __shfl_sync(0xffffffffu, inc, 31);
+      if (st_n + total > WK_STAGE) flush();
+      if (total > WK_STAGE) {  // a row with more candidates than a buffer holds (flat / weak frames): straight to the list
+        unsigned base = 0;
+        if (lane == 31) base = atomicAdd(wv.ncand + fr, (unsigned)total);
+        base = __shfl_sync(0xffffffffu, base, 31) + (unsigned)(inc - cnt);
+#pragma unroll
+        for (int t = 0; t < 8; t++)
+          if (cand & (1u << t)) {
+            if (base < (unsigned)wv.cand_cap) {
+              wv.tmp_idx[lb_off + base] = ((unsigned)y << 16) | (unsigned)(x0 + t);
+              wv.tmp_key[lb_off + base] = (unsigned long long)__double_as_longlong(0.125 * ue[t]);
+            }
+            base++;
+          }
+      } else {
+        int e = st_n + inc - cnt;
+#pragma unroll
+        for (int t = 0; t < 8; t++)
+          if (cand & (1u << t)) {
+            stg.idx[st_cur][e] = ((unsigned)y << 16) | (unsigned)(x0 + t);
+            stg.key[st_cur][e] = (unsigned long long)__double_as_longlong(0.125 * ue[t]);
+            e++;
+          }
+        st_n += total;
+      }
+    }
+    // publish a new maximum as soon as it is known (other warps' thresholds follow it)
+    if ((i & 7) == 7 || y == y_end - 1) {
+      double m = wmax;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+      wmax = m;
+      if (lane == 0) {
+        const unsigned long long mb = (unsigned long long)__double_as_longlong(m);
+        if (mb > *(volatile unsigned long long*)maxbits) atomicMax(maxbits, mb);  // u >= 0: bit order == value order
+      }
+    }
+  }
+  flush();  // reserve the last buffer ...
+  flush();  // ... and write it out
+}
+
 // Frames whose PROVISIONAL list overflowed the capacity are redone against the final threshold (their exact list may
 // still fit): a small persistent grid walks the rescue list.
 __global__ void __launch_bounds__(256, 3) score_rescue_kernel(const uint8_t* __restrict__ img, int w, int h, int pitch, size_t fstride,
@@ -560,13 +887,24 @@ int sfm_corner_candidates_batch(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int fir
   SFM_SMEM_OPTIN(ctx, cfg_id[2], score_tile_kernel<2>, sizeof(ScoreSmem));
   SFM_SMEM_OPTIN(ctx, cfg_id[3], score_rescue_kernel, sizeof(ScoreSmem));
   static const bool two_pass = getenv("SFMGPU_SCORE_TWO_PASS") != nullptr;  // A/B timing
-  if (quality > 0.0 && !two_pass) {
+  if (quality > 0.0 && quality <= 1.0 && !two_pass) {  // (quality > 1: a pixel between the maximum and the threshold would be skipped)
     constexpr int PROBE = 4;  // every 4th tile in x and y seeds the running maximum (1/16 of a pass)
     SFM_CUDA(ctx, cudaMemsetAsync(wv.exact_list, 0, sizeof(int) * count, ctx->stream));
     SFM_LAUNCH(ctx, score_tile_kernel<0>, dim3(sfm_cdiv(ntx, PROBE), sfm_cdiv(nty, PROBE), count), 256, sizeof(ScoreSmem), f->lvl[0], f->w,
                f->h, f->pitch[0], f->fstride[0], first, wv, quality, PROBE);
-    SFM_LAUNCH(ctx, score_tile_kernel<2>, grid, 256, sizeof(ScoreSmem), f->lvl[0], f->w, f->h, f->pitch[0], f->fstride[0], first, wv,
-               quality, 1);
+    static const bool use_tiles = getenv("SFMGPU_SCORE_TILES") != nullptr;  // A/B: the tile kernel of the earlier sessions
+    if (use_tiles) {
+      SFM_LAUNCH(ctx, score_tile_kernel<2>, grid, 256, sizeof(ScoreSmem), f->lvl[0], f->w, f->h, f->pitch[0], f->fstride[0], first, wv,
+                 quality, 1);
+    } else {
+      // segments of ~270 rows (6 warm-up rows each: 2 %), 4 strips of 256 columns per block
+      const int nseg = f->h > 400 ? (f->h + 269) / 270 : 1, seg_rows = (f->h + nseg - 1) / nseg;
+      static const int walk_id = sfm_next_cfg_id();
+      const size_t wsm = (size_t)WK_WARPS * WK_SMEM_WARP;
+      SFM_SMEM_OPTIN(ctx, walk_id, score_walk_kernel, wsm);
+      SFM_LAUNCH(ctx, score_walk_kernel, dim3(sfm_cdiv(f->w, WK_WARPS * WK_STRIP), sfm_cdiv(f->h, seg_rows), count), WK_WARPS * 32, wsm,
+                 f->lvl[0], f->w, f->h, f->pitch[0], f->fstride[0], first, wv, quality, seg_rows);
+    }
     SFM_LAUNCH(ctx, rescue_mark_kernel, sfm_cdiv(count, 256), 256, 0, wv, count);
     SFM_LAUNCH(ctx, score_rescue_kernel, dim3(ntx, nty, count < 2 ? count : 2), 256, sizeof(ScoreSmem), f->lvl[0], f->w, f->h,
                f->pitch[0], f->fstride[0], first, wv, quality);

@@ -22,7 +22,10 @@
 namespace {
 
 constexpr int RS_THREADS = 256;
-constexpr int RS_PTS = 2;        // points per thread (4: same speed, 1.33 vs 1.35 ms per 65536 x 10000)
+#ifndef RS_PTS_V
+#define RS_PTS_V 2
+#endif
+constexpr int RS_PTS = RS_PTS_V;  // points per thread, packed two by two (FFMA2)
 constexpr int RS_HCHUNK = 64;    // hypotheses staged per block iteration
 
 __device__ __forceinline__ float2 B2(float s) { return make_float2(s, s); }  // scalar broadcast operand of a packed instruction
@@ -104,9 +107,18 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_count_kernel(const double2*
     pm[k] = __double2float_ru(Pm);                 // NaN / inf propagate and end in the FP64 path
     pp[k] = __double2float_ru(Pp * Pm * 1.000001);
   }
-  static_assert(RS_PTS == 2, "the FP32 screen packs the thread's two points into one float2");
-  const float2 X = make_float2(xf[0], xf[1]), Y = make_float2(yf[0], yf[1]), XP = make_float2(xpf[0], xpf[1]), YP = make_float2(ypf[0], ypf[1]);
-  const float2 PP = make_float2(pp[0], pp[1]), PM = make_float2(pm[0], pm[1]);
+  static_assert(RS_PTS % 2 == 0, "the FP32 screen packs the thread's points two by two into float2");
+  constexpr int NP = RS_PTS / 2;
+  float2 X[NP], Y[NP], XP[NP], YP[NP], PP[NP], PM[NP];
+#pragma unroll
+  for (int g = 0; g < NP; g++) {
+    X[g] = make_float2(xf[2 * g], xf[2 * g + 1]);
+    Y[g] = make_float2(yf[2 * g], yf[2 * g + 1]);
+    XP[g] = make_float2(xpf[2 * g], xpf[2 * g + 1]);
+    YP[g] = make_float2(ypf[2 * g], ypf[2 * g + 1]);
+    PP[g] = make_float2(pp[2 * g], pp[2 * g + 1]);
+    PM[g] = make_float2(pm[2 * g], pm[2 * g + 1]);
+  }
   const float U8 = 4.76837158203125e-7f;  // 8u
   const int h_begin = blockIdx.y * h_per_block;
   const int h_end = min(H, h_begin + h_per_block);
@@ -133,30 +145,35 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_count_kernel(const double2*
     __syncthreads();
     for (int h = 0; h < nh; h++) {
       const RsHyp& hy = sH[h];
-      // both points of the thread at once: FFMA2 / FMUL2 / FADD2 (sm_100a packed FP32, one issue slot for two lanes'
+      // the thread's points two at a time: FFMA2 / FMUL2 / FADD2 (sm_100a packed FP32, one issue slot for two points'
       // worth of work; a scalar coefficient is a broadcast operand).  Every half is the correctly rounded FP32 operation
       // the bound derivation assumes.
-      const float2 ex = __ffma2_rn(B2(hy.e[0]), X, __ffma2_rn(B2(hy.e[1]), Y, B2(hy.e[2])));
-      const float2 ey = __ffma2_rn(B2(hy.e[3]), X, __ffma2_rn(B2(hy.e[4]), Y, B2(hy.e[5])));
-      const float2 ez = __ffma2_rn(B2(hy.e[6]), X, __ffma2_rn(B2(hy.e[7]), Y, B2(hy.e[8])));
-      const float2 tx = __ffma2_rn(B2(hy.e[0]), XP, __ffma2_rn(B2(hy.e[3]), YP, B2(hy.e[6])));
-      const float2 ty = __ffma2_rn(B2(hy.e[1]), XP, __ffma2_rn(B2(hy.e[4]), YP, B2(hy.e[7])));
-      const float2 nv = __ffma2_rn(XP, ex, __ffma2_rn(YP, ey, ez));
-      const float2 num = make_float2(fabsf(nv.x), fabsf(nv.y));
-      const float2 den = __ffma2_rn(ty, ty, __ffma2_rn(tx, tx, __ffma2_rn(ey, ey, __ffma2_rn(ex, ex, B2(1e-12f)))));
-      const float2 dn = __fmul2_rn(B2(hy.cn), PP);
-      const float2 q = __fmul2_rn(B2(hy.qd), PM);
-      const float2 dd = __ffma2_rn(q, q, __fmul2_rn(B2(U8), den));
-      const float2 a = __fadd2_rn(num, dn);
-      const float2 bm = __fadd2_rn(num, make_float2(-dn.x, -dn.y));
-      const float2 b = make_float2(fmaxf(bm.x, 0.f), fmaxf(bm.y, 0.f));
-      const float2 a2 = __fmul2_rn(a, a), b2 = __fmul2_rn(b, b);
-      const float2 lo = __fmul2_rn(B2(thr_lo_f), __fadd2_rn(den, make_float2(-dd.x, -dd.y)));
-      const float2 hi = __fmul2_rn(B2(thr_hi_f), __fadd2_rn(den, dd));
-      const bool in0 = a2.x < lo.x, in1 = a2.y < lo.y;
-      const bool out0 = (b2.x > hi.x) && (a.x < 1.0e18f), out1 = (b2.y > hi.y) && (a.y < 1.0e18f);
-      int c = ((in0 && valid[0]) ? 1 : 0) + ((in1 && valid[1]) ? 1 : 0);
-      const unsigned undecided = ((!in0 && !out0 && valid[0]) ? 1u : 0u) | ((!in1 && !out1 && valid[1]) ? 2u : 0u);
+      int c = 0;
+      unsigned undecided = 0;
+#pragma unroll
+      for (int g = 0; g < NP; g++) {
+        const float2 ex = __ffma2_rn(B2(hy.e[0]), X[g], __ffma2_rn(B2(hy.e[1]), Y[g], B2(hy.e[2])));
+        const float2 ey = __ffma2_rn(B2(hy.e[3]), X[g], __ffma2_rn(B2(hy.e[4]), Y[g], B2(hy.e[5])));
+        const float2 ez = __ffma2_rn(B2(hy.e[6]), X[g], __ffma2_rn(B2(hy.e[7]), Y[g], B2(hy.e[8])));
+        const float2 tx = __ffma2_rn(B2(hy.e[0]), XP[g], __ffma2_rn(B2(hy.e[3]), YP[g], B2(hy.e[6])));
+        const float2 ty = __ffma2_rn(B2(hy.e[1]), XP[g], __ffma2_rn(B2(hy.e[4]), YP[g], B2(hy.e[7])));
+        const float2 nv = __ffma2_rn(XP[g], ex, __ffma2_rn(YP[g], ey, ez));
+        const float2 num = make_float2(fabsf(nv.x), fabsf(nv.y));
+        const float2 den = __ffma2_rn(ty, ty, __ffma2_rn(tx, tx, __ffma2_rn(ey, ey, __ffma2_rn(ex, ex, B2(1e-12f)))));
+        const float2 dn = __fmul2_rn(B2(hy.cn), PP[g]);
+        const float2 q = __fmul2_rn(B2(hy.qd), PM[g]);
+        const float2 dd = __ffma2_rn(q, q, __fmul2_rn(B2(U8), den));
+        const float2 a = __fadd2_rn(num, dn);
+        const float2 bm = __fadd2_rn(num, make_float2(-dn.x, -dn.y));
+        const float2 b = make_float2(fmaxf(bm.x, 0.f), fmaxf(bm.y, 0.f));
+        const float2 a2 = __fmul2_rn(a, a), b2 = __fmul2_rn(b, b);
+        const float2 lo = __fmul2_rn(B2(thr_lo_f), __fadd2_rn(den, make_float2(-dd.x, -dd.y)));
+        const float2 hi = __fmul2_rn(B2(thr_hi_f), __fadd2_rn(den, dd));
+        const bool in0 = a2.x < lo.x, in1 = a2.y < lo.y;
+        const bool out0 = (b2.x > hi.x) && (a.x < 1.0e18f), out1 = (b2.y > hi.y) && (a.y < 1.0e18f);
+        c += ((in0 && valid[2 * g]) ? 1 : 0) + ((in1 && valid[2 * g + 1]) ? 1 : 0);
+        undecided |= ((!in0 && !out0 && valid[2 * g]) ? (1u << (2 * g)) : 0u) | ((!in1 && !out1 && valid[2 * g + 1]) ? (2u << (2 * g)) : 0u);
+      }
       if (__any_sync(0xffffffffu, undecided != 0)) {  // rare: the reference's FP64 arithmetic decides
         const double* e = sE + h * 9;
 #pragma unroll

@@ -5,13 +5,16 @@
 //     std::vector<Vec2> shi_tomasi(const GrayImage&, int max_corners, double q, int d)  :237-302
 //     struct LKConfig / struct Track / class KLTTracker {reset, step, tracks,
 //                                                        track_one_public}             :307-466
-//     struct RelPose; std::optional<RelPose> find_E_ransac(K, pi, pj, iters, thr, mi)   :640-761
+//     struct RelPose; std::optional<RelPose> find_E_ransac(K, pi, pj, iters, thr, mi)   :640-761   (sfmgpu_two_view.hpp)
 // plus one batched extra, track_pairs(), for callers that loop over track_one_public (:1845-1849).
 //
 // Two ways to use it:
-//   * inside the reference TU: include it after the reference's own headers (its sfm::GrayImage / Vec2 / Vec3 /
-//     Mat33 are used as they are) in place of the reference's definitions of the functions above;
-//   * stand-alone: define SFMGPU_SHIM_STANDALONE first and the minimal PODs below are provided.
+//   * inside the reference TU: include this header after the reference's own headers (its sfm::GrayImage / Vec2 / Vec3 /
+//     Mat33 are used as they are) in place of the reference's front-end definitions, and sfmgpu_two_view.hpp where the
+//     reference defines RelPose / find_E_ransac (:640-761) - there the TU's OWN invert_K, norm_point, eight_point_E, svd3,
+//     AtA_from_A and sfm::jacobi_eig_sym are in scope and are what find_E_ransac calls (nothing of them is restated);
+//   * stand-alone: define SFMGPU_SHIM_STANDALONE first: the minimal PODs below are provided, two_view_host.hpp supplies
+//     the host-side linear algebra, and sfmgpu_two_view.hpp is included at the end of this header.
 //
 // Errors: CUDA / library failures throw std::runtime_error (the reference's main catches std::exception at
 // :1913); two-view failure is std::nullopt; step() on the first frame returns empty vectors.  There is no CPU
@@ -32,7 +35,9 @@
 #include <vector>
 
 #include "../../include/sfmgpu.h"
-#include "two_view_host.hpp"
+#ifdef SFMGPU_SHIM_STANDALONE
+#include "two_view_host.hpp"  // stand-alone builds have no reference TU to take invert_K / eight_point_E / svd3 from
+#endif
 
 #ifdef SFMGPU_SHIM_STANDALONE
 // Layout-compatible stand-ins for cpp/include/pgm_io.hpp:10-15 and cpp/include/linalg.hpp:15-35.
@@ -424,6 +429,7 @@ static int loop_candidate(const std::vector<std::vector<float>>& kf_desc, int n_
 // PoseCW is defined inside the reference TU (:157-168), after the point where this header is included, so the shim
 // takes the pose as (R camera->world, camera centre).  The single-track form runs on the host and is bit-identical;
 // triangulate_tracks() is the batched device twin (opt-in, ~1e-10 relative).
+#ifdef SFMGPU_SHIM_STANDALONE
 static Vec3 triangulate_dlt_rt(const Mat33& K, const Mat33& Ri, const Vec3& Ci, const Mat33& Rj, const Vec3& Cj, Vec2 ui, Vec2 uj) {
   double ki[9];
   if (!sfmgpu_host::invert_K(K.a.data(), ki)) throw std::runtime_error("Singular K");
@@ -432,6 +438,7 @@ static Vec3 triangulate_dlt_rt(const Mat33& K, const Mat33& Ri, const Vec3& Ci, 
   sfmgpu_host::triangulate_dlt(K.a.data(), Ri.a.data(), ci, Rj.a.data(), cj, a, b, X);
   return Vec3{X[0], X[1], X[2]};
 }
+#endif  // inside the reference TU its own triangulate_dlt (:1477-1516) stays in place
 
 static std::vector<Vec3> triangulate_tracks(const Mat33& K, const std::vector<std::array<double, 12>>& poses, const std::vector<int>& ia,
                                             const std::vector<int>& ib, const std::vector<Vec2>& ui, const std::vector<Vec2>& uj) {
@@ -445,72 +452,6 @@ static std::vector<Vec3> triangulate_tracks(const Mat33& K, const std::vector<st
   return out;
 }
 
-// ---- find_E_ransac (:640-761) --------------------------------------------------------------------------------------
-struct RelPose {
-  Mat33 R_ji;
-  Vec3 t_ji;
-  std::vector<int> inliers;
-};
-
-static std::optional<RelPose> find_E_ransac(const Mat33& K, const std::vector<Vec2>& pi, const std::vector<Vec2>& pj, int iters = 2000,
-                                            double thr = 1e-4, int min_inliers = 80) {
-  using namespace sfmgpu_shim;
-  if (pi.size() < 8) return std::nullopt;  // before any RNG use (:648)
-  const int n = (int)pi.size();
-  double Ki[9];
-  if (!sfmgpu_host::invert_K(K.a.data(), Ki)) throw std::runtime_error("Singular K");
-  std::vector<double> xi(2 * (size_t)n), xj(2 * (size_t)n);
-  for (int i = 0; i < n; i++) {
-    sfmgpu_host::norm_point(Ki, pi[i].x, pi[i].y, &xi[2 * i]);
-    sfmgpu_host::norm_point(Ki, pj[i].x, pj[i].y, &xj[2 * i]);
-  }
-  // the reference's seeded sampling (:657-665), one continuing stream, re-seeded on every call
-  std::mt19937 rng(12345);
-  std::uniform_int_distribution<int> uni(0, n - 1);
-  const int H = iters > 0 ? iters : 0;
-  std::vector<double> E(9 * (size_t)H);
-  sfmgpu_ctx* ctx = context();
-  std::vector<int> inl((size_t)n);
-  int best_h = -1, best_n = 0;
-  if (!device_solver()) {
-    // all octets first (the RNG stream is sequential), then the hypotheses: each solve is a pure function of its octet,
-    // so solving them on several host threads leaves every hypothesis bit-identical to the reference's
-    std::vector<int> idx((size_t)8 * H);
-    for (size_t k = 0; k < idx.size(); k++) idx[k] = uni(rng);
-    const int nthr = H >= 64 ? solver_threads() : 1;
-    auto solve = [&](int h0, int h1) {
-      for (int it = h0; it < h1; it++) sfmgpu_host::eight_point_E(xi.data(), xj.data(), &idx[8 * (size_t)it], &E[9 * (size_t)it]);
-    };
-    if (nthr <= 1) {
-      solve(0, H);
-    } else {
-      std::vector<std::thread> pool;
-      const int per = (H + nthr - 1) / nthr;
-      for (int t = 1; t < nthr; t++)
-        if (t * per < H) pool.emplace_back(solve, t * per, std::min(H, (t + 1) * per));
-      solve(0, std::min(H, per));
-      for (auto& th : pool) th.join();
-    }
-    // scoring loop (:667-676) on the GPU: exact counts, first hypothesis with the strictly largest count
-    check(ctx, sfmgpu_ransac_score(ctx, xi.data(), xj.data(), n, E.data(), H, thr, nullptr, &best_h, inl.data(), &best_n),
-          "ransac_score");
-  } else {
-    // opt-in (SFMGPU_DEVICE_SOLVER=1 or set_device_solver(true)): the same sampled octets, hypotheses solved on the
-    // device (not bit-identical to the host solver: CUDA vs glibc trig in the Jacobi rotations), scored as above
-    std::vector<std::int32_t> idx((size_t)8 * H);
-    for (size_t k = 0; k < idx.size(); k++) idx[k] = uni(rng);
-    check(ctx, sfmgpu_ransac_hypotheses(ctx, xi.data(), xj.data(), n, idx.data(), H, E.data()), "ransac_hypotheses");
-    check(ctx, sfmgpu_ransac_score_resident(ctx, thr, &best_h, &best_n), "ransac_score_resident");
-    check(ctx, sfmgpu_ransac_download(ctx, nullptr, inl.data(), n), "ransac_download");
-  }
-  if (best_n < min_inliers) return std::nullopt;
-  RelPose rp;
-  double R[9], t[3];
-  // best_h < 0 means "no hypothesis won": the reference then decomposes the zero matrix
-  const double zeroE[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  sfmgpu_host::recover_pose(best_h >= 0 ? &E[9 * (size_t)best_h] : zeroE, xi.data(), xj.data(), inl.data(), best_n, R, t);
-  for (int k = 0; k < 9; k++) rp.R_ji.a[k] = R[k];
-  rp.t_ji = Vec3{t[0], t[1], t[2]};
-  rp.inliers.assign(inl.begin(), inl.begin() + best_n);
-  return rp;
-}
+#ifdef SFMGPU_SHIM_STANDALONE
+#include "sfmgpu_two_view.hpp"
+#endif
