@@ -411,15 +411,68 @@ __global__ void __launch_bounds__(256, 3) score_tile_kernel(const uint8_t* __res
 // there, two shared-memory round trips, three block barriers per tile).
 // Candidates: as in score_tile<2> - FP32 estimate for every pixel, the exact FP64 score for pixels within the estimate's
 // error of the provisional threshold quality * L, L = max(frame maximum so far, this warp's own exact maximum) <= final
-// maximum; appended to the unordered list with one atomic per warp and row; candidate bitmap words written whole.
-constexpr int WK_COLS = 8, WK_WARPS = 4, WK_MINB = 3, WK_STRIP = 32 * WK_COLS;  // 12 warps per SM: 184 KB of rings, <= 170 registers
+// maximum; the screened pixels are queued per warp and evaluated densely (see drain below).
+constexpr int WK_COLS = 8, WK_WARPS = 4, WK_MINB = 3, WK_STRIP = 32 * WK_COLS;  // 12 warps per SM: 222 KB of rings + queues, <= 170 registers
 constexpr int WK_RING = 5 * 6 * 32;  // float4 per warp: 5 rows x (24 sums = 6 float4) x 32 lanes
-constexpr int WK_STAGE = 128;        // candidates staged per warp and buffer before their list slots are reserved
-struct WalkStage {                   // two buffers: one fills while the other waits for its reservation (a global atomic)
-  unsigned long long key[2][WK_STAGE];
-  unsigned idx[2][WK_STAGE];
-};
-constexpr size_t WK_SMEM_WARP = WK_RING * sizeof(float4) + sizeof(WalkStage);
+constexpr int WK_QUEUE = 224;        // screened pixels queued per warp before they are evaluated densely
+constexpr size_t WK_SMEM_WARP = WK_RING * sizeof(float4) + WK_QUEUE * sizeof(uint4);
+
+__device__ __forceinline__ uint2 ldg_pinned(const uint8_t* p) {
+  uint2 v;
+  asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+
+// Dense evaluation of a warp's queue of screened pixels (called every ~15 rows: kept out of line, the row loop should stay small).
+__device__ __noinline__ void walk_drain(uint4* queue, int& qn, double& wmax, double thr8, int fr, const CornerWorkView& wv, int lane) {
+  const size_t lb_off = (size_t)fr * wv.cand_cap;
+  __syncwarp();
+  // pass 1: exact scores (kept in registers: WK_QUEUE / 32 entries per lane), candidate count
+  constexpr int PER = WK_QUEUE / 32;
+  double u[PER];
+  unsigned pos[PER], cm[PER];
+  int ncand = 0;
+#pragma unroll
+  for (int k = 0; k < PER; k++) {
+    const int e = k * 32 + lane;
+    bool c = false;
+    u[k] = 0.0;
+    pos[k] = 0;
+    if (e < qn) {
+      const uint4 q = queue[e];
+      pos[k] = q.x & 0x7FFFFFFFu;
+      if (!(q.x >> 31)) {
+        u[k] = exact_u(__float2int_rn(__uint_as_float(q.y)), __float2int_rn(__uint_as_float(q.z)), __float2int_rn(__uint_as_float(q.w)));
+        wmax = fmax(wmax, u[k]);
+        c = u[k] >= thr8;
+      } else {
+        c = true;  // border pixel: queued only while 0 >= thr8
+      }
+    }
+    cm[k] = __ballot_sync(0xffffffffu, c);
+    ncand += __popc(cm[k]);
+  }
+  if (ncand > 0) {
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(wv.ncand + fr, (unsigned)ncand);
+    base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      if (cm[k] & (1u << lane)) {
+        const unsigned slot = base + __popc(cm[k] & ((1u << lane) - 1u));
+        const unsigned x = pos[k] & 0xFFFFu, y = pos[k] >> 16;
+        atomicOr(wv.bitmap + (size_t)fr * wv.words_per_frame + (size_t)y * wv.wpr + (x >> 5), 1u << (x & 31));
+        if (slot < (unsigned)wv.cand_cap) {
+          wv.tmp_idx[lb_off + slot] = pos[k];
+          wv.tmp_key[lb_off + slot] = (unsigned long long)__double_as_longlong(0.125 * u[k]);
+        }
+      }
+      base += __popc(cm[k]);
+    }
+  }
+  qn = 0;
+  __syncwarp();
+}
 
 __global__ void __launch_bounds__(WK_WARPS * 32, WK_MINB) score_walk_kernel(const uint8_t* __restrict__ img, int w, int h, int pitch,
                                                                       size_t fstride, int frame0, CornerWorkView wv, double quality,
@@ -435,83 +488,54 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_MINB) score_walk_kernel(cons
   const uint8_t* im = img + (size_t)(frame0 + fr) * fstride;
   unsigned char* wbase = score_raw + (size_t)warp * WK_SMEM_WARP;
   float4* ring = reinterpret_cast<float4*>(wbase) + lane;  // [row % 5][k] at ring[(row5 * 6 + k) * 32]
-  WalkStage& stg = *reinterpret_cast<WalkStage*>(wbase + WK_RING * sizeof(float4));
-  // candidate staging: list slots are reserved with ONE global atomic per ~128 candidates, and its result is only needed
-  // when the buffer is written out - one flush later - so the warp never waits for the atomic's round trip
-  int st_cur = 0, st_n = 0, pend_n = 0;
-  unsigned pend_base = 0;  // lane 0: start of the reserved range of the pending buffer
-  const size_t lb_off = (size_t)fr * wv.cand_cap;
-  auto write_out = [&](int buf, int cnt, unsigned base0) {  // staged entries -> their reserved list slots
-    const unsigned base = __shfl_sync(0xffffffffu, base0, 0);
-    for (int e = lane; e < cnt; e += 32) {
-      const unsigned slot = base + (unsigned)e;
-      if (slot < (unsigned)wv.cand_cap) {
-        wv.tmp_idx[lb_off + slot] = stg.idx[buf][e];
-        wv.tmp_key[lb_off + slot] = stg.key[buf][e];
-      }
-    }
-  };
-  auto flush = [&]() {  // write the pending buffer out, reserve slots for the current one, swap
-    __syncwarp();
-    if (pend_n > 0) write_out(st_cur ^ 1, pend_n, pend_base);
-    pend_n = st_n;
-    if (st_n > 0 && lane == 0) pend_base = atomicAdd(wv.ncand + fr, (unsigned)st_n);
-    st_cur ^= 1;
-    st_n = 0;
-    __syncwarp();
-  };
+  // Screened pixels (FP32 estimate within its error of the provisional threshold: a few percent) are not evaluated where
+  // they are found - one lane with a hit would drag the whole warp through the FP64 expression - but queued with their
+  // exact (integer-valued) sums and evaluated DENSELY, 32 at a time; survivors get their list slots with one global atomic
+  // per drain and mark the candidate bitmap (zeroed before the launch) with a fire-and-forget atomicOr.
+  uint4* queue = reinterpret_cast<uint4*>(wbase + WK_RING * sizeof(float4));  // (y << 16 | x | border << 31, a, b, c as float bits)
+  int qn = 0;
+  double wmax = 0.0;      // this warp's exact maximum so far (lane-local until published)
+  double lb = 0.0;        // lower bound of the frame maximum the threshold was derived from
+  double thr8 = 0.0;      // provisional 8 * thr
+  float boundf = -EST_MARGIN;
+  bool border_on = true;  // 0 >= thr8: border pixels (score exactly 0, :240, :253-254) are candidates
+  auto drain = [&]() { walk_drain(queue, qn, wmax, thr8, fr, wv, lane); };
   unsigned long long* maxbits = wv.maxbits + fr;
   const int wm1 = w - 1;
-  // a lane whose 14 tap columns x0-3 .. x0+10 are not all inside the image clamps them one by one (image borders only)
-  const bool edge_lane = x0 < 3 || x0 + 10 > wm1;
-  const bool own_inside = x0 + 7 <= wm1;  // the 64-bit load stays inside the row's w bytes
+  // Warp-uniform: does any of the strip's tap columns xs-3 .. xs+258 fall outside the image?  Only such strips run the
+  // per-byte clamp (the reference clamps its gradient taps into the image, :242-249).
+  const bool edge_strip = xs == 0 || xs + WK_STRIP + 2 > wm1;
+  // per-lane column masks (bit t = column x0 + t)
+  unsigned in_img = 0, interior_cols = 0;
+#pragma unroll
+  for (int t = 0; t < 8; t++) {
+    if (x0 + t < w) in_img |= 1u << t;
+    if (x0 + t >= 2 && x0 + t < w - 2) interior_cols |= 1u << t;
+  }
 
-  // raw taps of one row: the lane's 8 bytes + the 4 bytes before the strip (lane 0) / after it (lane 31)
+  // Raw taps of one row: the 8 bytes before the lane's columns, its own 8, the 8 after (three 64-bit loads; the
+  // neighbours' lines are in L1 already).  Addresses stay inside the frame batch: a row's over-read ends in the next row.
   struct Raw {
-    uint32_t lo, hi, ext;
+    uint2 l, m, r;
   };
+  const int xl = (x0 >= 8) ? x0 - 8 : x0, xr = (x0 + 16 <= pitch) ? x0 + 8 : x0;  // rows are pitch bytes: stay inside them
   auto load_row = [&](int t) {
-    Raw r;
-    t = t < 0 ? 0 : (t > h - 1 ? h - 1 : t);  // clamped tap rows (:242-249)
+    Raw q;
+    t = t < 0 ? 0 : (t > h - 1 ? h - 1 : t);  // clamped tap rows
     const uint8_t* row = im + (size_t)t * pitch;
-    if (own_inside) {
-      const uint2 v = __ldg(reinterpret_cast<const uint2*>(row + x0));
-      r.lo = v.x;
-      r.hi = v.y;
-    } else {  // the lane straddles or lies beyond the right border: clamped byte loads
-      r.lo = r.hi = 0;
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        r.lo |= (uint32_t)__ldg(row + min(x0 + k, wm1)) << (8 * k);
-        r.hi |= (uint32_t)__ldg(row + min(x0 + 4 + k, wm1)) << (8 * k);
-      }
-    }
-    r.ext = 0;
-    if (lane == 0) {  // bytes x0-4 .. x0-1 (clamped at the left border)
-      if (x0 >= 4) r.ext = __ldg(reinterpret_cast<const uint32_t*>(row + x0 - 4));
-      else r.ext = 0x01010101u * (uint32_t)__ldg(row);
-    } else if (lane == 31) {  // bytes x0+8 .. x0+11 (clamped at the right border)
-      if (x0 + 11 <= wm1) {
-        r.ext = __ldg(reinterpret_cast<const uint32_t*>(row + x0 + 8));
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; k++) r.ext |= (uint32_t)__ldg(row + min(x0 + 8 + k, wm1)) << (8 * k);
-      }
-    }
-    return r;
+    // volatile asm: the loads are issued HERE, three rows before their conversion (the compiler would sink them to their use)
+    q.m = ldg_pinned(row + (x0 + 8 <= pitch ? x0 : 0));
+    q.l = ldg_pinned(row + (x0 + 8 <= pitch ? xl : 0));
+    q.r = ldg_pinned(row + (x0 + 8 <= pitch ? xr : 0));
+    return q;
   };
   // 14 integer-valued floats (2^23 + byte) of tap columns x0-3 .. x0+10
-  auto convert = [&](const Raw& r, float* F) {
-    uint32_t left = __shfl_up_sync(0xffffffffu, r.hi, 1), right = __shfl_down_sync(0xffffffffu, r.lo, 1);
-    if (lane == 0) left = r.ext;
-    if (lane == 31) right = r.ext;
-    uint32_t lo = r.lo, hi = r.hi;
-    if (edge_lane) {  // clamp every tap column into [0, w-1]: replicate the border byte
-      if (x0 < 3) {  // left border: columns < 0 take column 0 (x0 == 0 here: strips start at multiples of 256)
-        left = 0x01010101u * (lo & 0xffu);
-      }
-      if (x0 + 10 > wm1) {  // right border: columns > w-1 take column w-1
-        const int last = wm1 - x0;  // index of the last valid own byte (may be < 0 or >= 8)
+  auto convert = [&](const Raw& q, float* F) {
+    uint32_t left = q.l.y, lo = q.m.x, hi = q.m.y, right = q.r.x;
+    if (edge_strip) {  // clamp every tap column into [0, w-1]: replicate the border byte
+      if (x0 < 3) left = 0x01010101u * (lo & 0xffu);  // x0 == 0: columns < 0 take column 0
+      if (x0 + 10 > wm1) {                             // columns > w-1 take column w-1
+        const int last = wm1 - x0;                     // position of the last valid byte (own bytes 0..7, right 8..11)
         uint32_t b;
         if (last < 0) b = 0;  // whole lane beyond the image: its values are never used
         else if (last < 4) b = (lo >> (8 * last)) & 0xffu;
@@ -538,8 +562,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_MINB) score_walk_kernel(cons
     F[13] = bytef(right, 2);
   };
 
-  float Fm[14], Fc[14], Fp[14];  // tap rows T-2, T-1, T as floats
-  float V[24];                   // vertical running sums: xx[0..7], xy[0..7], yy[0..7]
+  float V[24];  // vertical running sums: xx[0..7], xy[0..7], yy[0..7]
 #pragma unroll
   for (int k = 0; k < 24; k++) V[k] = 0.f;
   {
@@ -548,27 +571,14 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_MINB) score_walk_kernel(cons
     for (int k = 0; k < 30; k++) ring[k * 32] = z;
   }
   __syncwarp();
-  double wmax = 0.0;      // this warp's exact maximum so far (lane-local until published)
-  double lb = 0.0;        // lower bound of the frame maximum the threshold was derived from
-  double thr8 = 0.0;      // provisional 8 * thr
-  float boundf = -EST_MARGIN;
   unsigned long long gmax_bits = *(volatile unsigned long long*)maxbits;
   const int T0 = y_begin - 3;  // first tap row
-  Raw r0 = load_row(T0), r1 = load_row(T0 + 1), r2 = load_row(T0 + 2);
-  convert(r0, Fm);
-  convert(r1, Fc);
-  r0 = load_row(T0 + 3);
-  r1 = load_row(T0 + 4);
-  // iteration i: tap row T = T0 + 2 + i arrives, gradient row G = T - 1 = y_begin - 2 + i, and once five rows of horizontal
-  // sums are in (i >= 4) the output row y = G - 2 = y_begin + i - 4 is complete
   const int n_iter = (y_end - y_begin) + 4;
-  for (int i = 0; i < n_iter; i++) {
-    convert(r2, Fp);
-    r2 = r0;
-    r0 = r1;
-    r1 = load_row(T0 + 5 + i);
-    const int G = T0 + 1 + i;   // gradient / h row
-    const int y = G - 2;        // output row once five h rows are in
+
+  // One row: tap rows G-1 (Fm), G (Fc), G+1 (Fp) are in registers; i counts rows from the segment's first gradient row
+  // G = y_begin - 2; once five rows of horizontal sums are in (i >= 4) the output row y = G - 2 is complete.
+  auto row_step = [&](const float* Fm, const float* Fc, const float* Fp, int i) {
+    const int y = y_begin + i - 4;
     // running lower bound of the frame maximum -> provisional threshold (re-read every 8 rows; the load is issued four
     // rows before its value is used)
     if ((i & 7) == 4) gmax_bits = *(volatile unsigned long long*)maxbits;
@@ -579,6 +589,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_MINB) score_walk_kernel(cons
         lb = nl;
         thr8 = 8.0 * ((0.125 * lb) * quality);
         boundf = __double2float_rd(thr8) - EST_MARGIN;
+        border_on = 0.0 >= thr8;
       }
     }
     // gradients of row G at columns x0-2 .. x0+9, horizontal 5-sums of their products at x0 .. x0+7
@@ -630,88 +641,47 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_MINB) score_walk_kernel(cons
         V[16 + t] += hy[t] - of[16 + t];
       }
     }
-#pragma unroll
-    for (int c = 0; c < 14; c++) {
-      Fm[c] = Fc[c];
-      Fc[c] = Fp[c];
-    }
-    if (i < 4 || y >= y_end) continue;  // warm-up rows (warp-uniform)
-    // estimates, screen, exact scores of the screened pixels
-    const bool row_interior = y >= 2 && y < h - 2;
-    unsigned flags = 0, border = 0;
+    if (i < 4) return;  // warm-up rows (warp-uniform)
+    // FP32 estimates against the screen
+    unsigned pass = 0;
 #pragma unroll
     for (int t = 0; t < 8; t++) {
-      const int x = x0 + t;
       const float u = est_u(V[t], V[16 + t], V[8 + t]);
-      const bool interior = row_interior && x >= 2 && x < w - 2;
-      if (interior) {
-        if (u >= boundf) flags |= 1u << t;
-      } else if (x < w && 0.0 >= thr8) {
-        border |= 1u << t;  // border score is exactly 0 (:240, :253-254)
-      }
+      if (u >= boundf) pass |= 1u << t;
     }
-    double ue[8];
-    unsigned cand = border;
-    if (__any_sync(0xffffffffu, flags != 0)) {
+    const bool row_interior = y >= 2 && y < h - 2;
+    const unsigned flags = row_interior ? (pass & interior_cols) : 0u;
+    const unsigned border = border_on ? (in_img & ~(row_interior ? interior_cols : 0u)) : 0u;
+    const unsigned want = flags | border;
+    if (__any_sync(0xffffffffu, want != 0)) {
+      auto push = [&](unsigned m) {
+        const int cnt = __popc(m);
+        int inc = cnt;
 #pragma unroll
-      for (int t = 0; t < 8; t++) {
-        ue[t] = 0.0;
-        if (flags & (1u << t)) {
-          const double u = exact_u(__float2int_rn(V[t]), __float2int_rn(V[16 + t]), __float2int_rn(V[8 + t]));
-          ue[t] = u;
-          wmax = fmax(wmax, u);
-          if (u >= thr8) cand |= 1u << t;
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += v;
         }
-      }
-    } else {
-#pragma unroll
-      for (int t = 0; t < 8; t++) ue[t] = 0.0;
-    }
-    // candidate bitmap: 4 lanes make one 32-pixel word; every word of the strip's row is written (zeros too)
-    {
-      unsigned wbits = cand;
-      wbits |= __shfl_down_sync(0xffffffffu, wbits, 1) << 8;
-      wbits |= __shfl_down_sync(0xffffffffu, wbits, 2) << 16;
-      if ((lane & 3) == 0 && x0 < w) wv.bitmap[(size_t)fr * wv.words_per_frame + (size_t)y * wv.wpr + (x0 >> 5)] = wbits;
-    }
-    // list append through the staging buffers
-    if (__any_sync(0xffffffffu, cand != 0)) {
-      const int cnt = __popc(cand);
-      int inc = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += v;
-      }
-      const int total = __shfl_sync(0xffffffffu, inc, 31);
-      if (st_n + total > WK_STAGE) flush();
-      if (total > WK_STAGE) {  // a row with more candidates than a buffer holds (flat / weak frames): straight to the list
-        unsigned base = 0;
-        if (lane == 31) base = atomicAdd(wv.ncand + fr, (unsigned)total);
-        base = __shfl_sync(0xffffffffu, base, 31) + (unsigned)(inc - cnt);
+        const int total = __shfl_sync(0xffffffffu, inc, 31);
+        if (qn + total > WK_QUEUE) drain();
+        int e = qn + inc - cnt;
 #pragma unroll
         for (int t = 0; t < 8; t++)
-          if (cand & (1u << t)) {
-            if (base < (unsigned)wv.cand_cap) {
-              wv.tmp_idx[lb_off + base] = ((unsigned)y << 16) | (unsigned)(x0 + t);
-              wv.tmp_key[lb_off + base] = (unsigned long long)__double_as_longlong(0.125 * ue[t]);
-            }
-            base++;
-          }
-      } else {
-        int e = st_n + inc - cnt;
-#pragma unroll
-        for (int t = 0; t < 8; t++)
-          if (cand & (1u << t)) {
-            stg.idx[st_cur][e] = ((unsigned)y << 16) | (unsigned)(x0 + t);
-            stg.key[st_cur][e] = (unsigned long long)__double_as_longlong(0.125 * ue[t]);
+          if (m & (1u << t)) {
+            const unsigned bd = (border >> t) & 1u;
+            queue[e] = make_uint4(((unsigned)y << 16) | (unsigned)(x0 + t) | (bd << 31), __float_as_uint(V[t]), __float_as_uint(V[16 + t]),
+                                  __float_as_uint(V[8 + t]));
             e++;
           }
-        st_n += total;
-      }
+        qn += total;
+      };
+      // more screened pixels in one row than the queue holds (flat / weak frames): two halves
+      const int parts = __reduce_add_sync(0xffffffffu, __popc(want)) <= WK_QUEUE ? 1 : 2;
+#pragma unroll 1
+      for (int part = 0; part < parts; part++) push(parts == 1 ? want : (part == 0 ? want & 0x0Fu : want & 0xF0u));
     }
     // publish a new maximum as soon as it is known (other warps' thresholds follow it)
-    if ((i & 7) == 7 || y == y_end - 1) {
+    if ((i & 7) == 7) {
       double m = wmax;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -721,9 +691,40 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_MINB) score_walk_kernel(cons
         if (mb > *(volatile unsigned long long*)maxbits) atomicMax(maxbits, mb);  // u >= 0: bit order == value order
       }
     }
+  };
+
+  // two raw rows are in flight ahead of the row being converted; the three float rows shift by register moves (an
+  // unrolled-by-three rotation tripled the code and cost more in instruction fetch than the 28 moves)
+  float Fm[14], Fc[14], Fp[14];
+  Raw r0 = load_row(T0), r1 = load_row(T0 + 1), r2 = load_row(T0 + 2);
+  convert(r0, Fm);
+  convert(r1, Fc);
+  r0 = load_row(T0 + 3);
+  r1 = load_row(T0 + 4);
+#pragma unroll 1
+  for (int i = 0; i < n_iter; i++) {
+    convert(r2, Fp);
+    r2 = r0;
+    r0 = r1;
+    r1 = load_row(T0 + 5 + i);
+    row_step(Fm, Fc, Fp, i);
+#pragma unroll
+    for (int c = 0; c < 14; c++) {
+      Fm[c] = Fc[c];
+      Fc[c] = Fp[c];
+    }
   }
-  flush();  // reserve the last buffer ...
-  flush();  // ... and write it out
+  drain();
+  // the maximum of the last rows and the last drain
+  {
+    double m = wmax;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) {
+      const unsigned long long mb = (unsigned long long)__double_as_longlong(m);
+      if (mb > *(volatile unsigned long long*)maxbits) atomicMax(maxbits, mb);
+    }
+  }
 }
 
 // Frames whose PROVISIONAL list overflowed the capacity are redone against the final threshold (their exact list may
@@ -902,6 +903,7 @@ int sfm_corner_candidates_batch(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int fir
       static const int walk_id = sfm_next_cfg_id();
       const size_t wsm = (size_t)WK_WARPS * WK_SMEM_WARP;
       SFM_SMEM_OPTIN(ctx, walk_id, score_walk_kernel, wsm);
+      SFM_CUDA(ctx, cudaMemsetAsync(wv.bitmap, 0, sizeof(unsigned) * wv.words_per_frame * count, ctx->stream));
       SFM_LAUNCH(ctx, score_walk_kernel, dim3(sfm_cdiv(f->w, WK_WARPS * WK_STRIP), sfm_cdiv(f->h, seg_rows), count), WK_WARPS * 32, wsm,
                  f->lvl[0], f->w, f->h, f->pitch[0], f->fstride[0], first, wv, quality, seg_rows);
     }
