@@ -57,9 +57,9 @@ def temple_K():
 
 
 def shard_range(n_items, world, rank):
-    base, extra = divmod(n_items, world)
-    start = rank * base + min(rank, extra)
-    return start, start + base + (1 if rank < extra else 0)
+    """The scheduler's block partition (sfmgpu_sched_shard of the C ABI, through sfmgpu/sched.py)."""
+    from sfmgpu import sched
+    return sched.shard_range(n_items, world, rank)
 
 
 def workload_cfg(wl, n_gpus, nframes):
@@ -860,6 +860,19 @@ def main():
                 find_e[name] = (time.perf_counter() - t0) / 3 * 1e3
                 find_e[name.replace("_ms", "_inliers")] = int(kk.value)
             shim.shim_set_device_solver(0)
+            # the loop-closure block (:1841-1852) through the shim on a TempleRing-sized pair, as the reference writes it
+            # (track_one_public per corner: one launch + sync each, 2 x 1200 per loop closure) and with the batched call
+            from sfmgpu import synth
+            f0, f1 = synth.frame(SEED0, 0, 640, 480), synth.frame(SEED0, 1, 640, 480)
+            lli, llj, nn = np.zeros((1200, 2)), np.zeros((1200, 2)), C.c_int(0)
+            find_e["loop_closure_block"] = {"image": "640x480", "max_corners": 1200}
+            for name, batched in (("per_point_ms", 0), ("batched_ms", 1)):
+                shimlib.ck(shim, shim.shim_pair_frontend(f0, f1, 640, 480, 1200, 0.01, 8, 3, 5, 10, 1.0, batched, lli, llj, C.byref(nn)))
+                t0 = time.perf_counter()
+                kept = shimlib.ck(shim, shim.shim_pair_frontend(f0, f1, 640, 480, 1200, 0.01, 8, 3, 5, 10, 1.0, batched, lli, llj, C.byref(nn)))
+                find_e["loop_closure_block"][name] = (time.perf_counter() - t0) * 1e3
+                find_e["loop_closure_block"]["corners"] = int(nn.value)
+                find_e["loop_closure_block"]["kept"] = int(kept)
         except Exception as ex:  # the shim is optional for the bench line
             find_e = {"error": str(ex)[:200]}
 

@@ -1,6 +1,6 @@
 #!/bin/bash
-# Round profile set on the C2 shape: ncu launch list + one --set full capture per hot kernel (gpurun_out/, scratch).
-mkdir -p gpurun_out
-bash scripts/gpu_launches.sh 999 r1_launches > /dev/null
-NCU_COUNT=1 bash scripts/gpu_prof.sh 999 klt_quad_kernel r1_klt_quad radix_sort_frame r1_radix nms_kernel r1_nms pyr_down r1_pyr ransac_count r1_ransac
-NCU_COUNT=2 bash scripts/gpu_prof.sh 999 score_tile_kernel r1_score 'klt_lane_kernel' r1_klt_border
+# Round-2 evidence: launch lists (C2 full, C3 400 frames) and ncu --set full captures of the hot kernels on the C2 shape.
+mkdir -p gpurun_out; : > gpurun_out/summary.txt
+bash scripts/gpu_launches.sh 1000 r2_launches_c2 c2
+bash scripts/gpu_launches.sh 400 r2_launches_c3 c3
+WL=c2 bash scripts/gpu_prof.sh 1000 score_walk r2_score_walk ransac_count r2_ransac_count eight_point r2_eight_point radix_sort r2_radix nms_kernel r2_nms klt_quad r2_klt_quad klt_lane r2_klt_border pyr_down r2_pyr pose_kernel r2_pose

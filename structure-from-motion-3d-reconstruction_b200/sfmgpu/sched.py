@@ -1,41 +1,40 @@
-"""Multi-GPU frame-pair / sequence scheduler: one process per GPU, torch.distributed for the plumbing.
+"""Multi-GPU frame-pair / sequence scheduler - the torch.distributed face, used by bench.py and the
+gloo tests.  The C++ drop-in uses the same sharding through the C ABI (include/sfmgpu.h: sfmgpu_sched_*, csrc/sched.cu,
+NCCL send / recv); `shard_range` below IS that C function, so both faces agree by construction.
 
 The front end shards with NO data-path collective:
-  * pair mode     — the stateless two-view unit (cpp/src/templering_sfm.cpp:1836-1857): pairs (t, t+1) are independent;
-                    rank g owns a contiguous block of pairs plus one halo frame;
-  * sequence mode — whole sequences per rank (a KLTTracker chain cannot be split across frames, :370-371); several
-                    sequences per GPU advance in lock step (run_sequences -> sfmgpu_multitracker);
-  * segment mode  — contiguous segments of one sequence per rank, each restarting the tracker (segment_shard).
+  * pair mode     - the stateless two-view unit (cpp/src/templering_sfm.cpp:1836-1857): pairs (t, t+1) are independent;
+                    rank g owns a contiguous block of pairs plus one halo frame (`pair_shard`);
+  * sequence mode - whole sequences per rank (a KLTTracker chain cannot be split across frames, :370-371): `shard_range`
+                    over the sequences; several sequences per GPU advance in lock step (run_sequences -> sfmgpu_multitracker);
+  * segment mode  - contiguous frame segments of one sequence per rank, each restarting the tracker: `shard_range` over
+                    the frames.  That equals the reference run on each segment separately (track ids restart per
+                    segment), NOT the unsegmented run.
 The only communication is the gather of results (tracks, survivor counts, inlier sets) to rank 0: an all_gather of
 per-rank sizes followed by one padded gather (NCCL has no gatherv).  Works on NCCL (GPU tensors) and gloo (CPU tests).
 """
+import ctypes as C
+
 import numpy as np
 import torch
 import torch.distributed as dist
 
 
 def shard_range(n_items, world, rank):
-    """Contiguous block [start, end) of n_items for `rank`; sizes differ by at most one, lower ranks get the extra."""
-    base, extra = divmod(n_items, world)
-    start = rank * base + min(rank, extra)
-    return start, start + base + (1 if rank < extra else 0)
+    """Contiguous block [start, end) of n_items for `rank`; sizes differ by at most one, lower ranks get the extra.
+    Calls sfmgpu_sched_shard (a pure function of the C ABI: no GPU needed)."""
+    import sfmgpu
+    lib = sfmgpu.load_library()
+    a, b = C.c_int(0), C.c_int(0)
+    if lib.sfmgpu_sched_shard(int(n_items), int(world), int(rank), C.byref(a), C.byref(b)) != 0:
+        raise ValueError(f"shard_range({n_items}, {world}, {rank})")
+    return a.value, b.value
 
 
 def pair_shard(n_frames, world, rank):
     """Pairs [p0, p1) of a sequence of n_frames and the frames [p0, p1] (inclusive halo) the rank must hold."""
     p0, p1 = shard_range(max(n_frames - 1, 0), world, rank)
     return p0, p1, (p0, p1 + 1 if p1 > p0 else p0)
-
-
-def sequence_shard(n_sequences, world, rank):
-    return shard_range(n_sequences, world, rank)
-
-
-def segment_shard(n_frames, world, rank):
-    """Segment mode: frames [f0, f1) of ONE long sequence for a tracker that starts with reset() on f0.
-    Equals the reference run on each segment separately (track ids restart per segment), NOT the unsegmented run: a
-    KLTTracker chain cannot be cut without changing its state (cpp/src/templering_sfm.cpp:364-371)."""
-    return shard_range(n_frames, world, rank)
 
 
 def _dev(t):

@@ -25,7 +25,7 @@ def test_shard_ranges_cover_everything():
             assert max(sizes) - min(sizes) <= 1
     p0, p1, fr = sched.pair_shard(1000, 8, 3)
     assert fr == (p0, p1 + 1) and (p1 - p0) in (124, 125)
-    segs = [sched.segment_shard(2000, 8, r) for r in range(8)]
+    segs = [sched.shard_range(2000, 8, r) for r in range(8)]
     assert segs[0] == (0, 250) and segs[-1] == (1750, 2000) and all(segs[i][1] == segs[i + 1][0] for i in range(7))
 
 
