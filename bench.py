@@ -773,6 +773,7 @@ def main():
                     help="c3 (default): 4K x 2000 frames, 8000 corners, pair-sharded; c2: 1080p x 1000 frames, 2000 corners; "
                          "c5: 64 independent 1080p sequences in tracker mode (attached to the default line as 'c5')")
     ap.add_argument("--no-c5", action="store_true", help="skip the C5 side measurement of the default line")
+    ap.add_argument("--no-shim", action="store_true", help="skip the C++ shim timings (find_E_ransac, loop-closure block): profiling runs")
     ap.add_argument("--frames", type=int, default=0, help="frames of the sequence (default: the workload's own length)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (cpu_baseline, parity_in_bench)")
     ap.add_argument("--no-c2", action="store_true", help="skip the C2 side measurement of the default line")
@@ -840,7 +841,7 @@ def main():
 
     # ---- the reference's own two-view entry point through the C++ shim (TempleRing-sized call, sfm.cpp:1739) ---------------------
     find_e = None
-    if rank == 0:
+    if rank == 0 and not args.no_shim:
         try:
             import ctypes as C
             sys.path.insert(0, os.path.join(ROOT, "tests"))

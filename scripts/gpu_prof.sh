@@ -2,7 +2,7 @@
 # ncu --set full captures of named kernels on a short bench run.  usage: gpu_prof.sh <frames> <regex> <outname> [<regex> <outname> ...]
 mkdir -p gpurun_out
 FR=$1; shift
-SMALL="python bench.py --workload ${WL:-c2} --steps 1 --warmup 1 --frames $FR --no-cpu-baseline --no-c2"
+SMALL="python bench.py --workload ${WL:-c2} --steps 1 --warmup 1 --frames $FR --no-cpu-baseline --no-c2 --no-c5 --no-shim"
 while [ $# -ge 2 ]; do
   RX=$1; OUT=$2; shift 2
   $SMALL > gpurun_out/plain_$OUT.log 2>&1 &&

@@ -62,10 +62,11 @@ __device__ __forceinline__ bool is_inlier(double n2, double den, double thr, dou
 // and  e >= thr  is certain when (|num_f| - dn)^2 > thr_hi (den_f + dd), with thr_lo / thr_hi = thr (1 -/+ 2e-6) rounded
 // outwards and divided / multiplied by 1 + 2^-20 for the FP32 roundings of the bound arithmetic itself (< 7u).  NaNs,
 // infinities and overflowing magnitudes fail both tests and take the FP64 path.
-struct RsHyp {
+struct __align__(16) RsHyp {  // 48 bytes: read with three 128-bit shared-memory loads
   float e[9];
   float cn;   // 32u * Esum (rounded up, floored at 1e-30: subnormal hypotheses)
   float qd;   // sqrt(64u) * Emax (rounded up)
+  float pad;
 };
 
 // blockIdx.z = correspondence set ("pair") of a batch: points at xi/xj + pair * pt_stride, npts[pair] of them (npts == nullptr:
@@ -77,7 +78,9 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_count_kernel(const double2*
                                                                  float thr_hi_f, int* __restrict__ counts) {
   __shared__ double sE[RS_HCHUNK * 9];
   __shared__ RsHyp sH[RS_HCHUNK];
-  __shared__ int sC[RS_THREADS / 32][RS_HCHUNK];  // per-warp counts of the chunk: plain stores, summed once per chunk
+  // per-warp counts of the chunk, four hypotheses per word (a warp counts at most 2 x 32 per hypothesis: one byte each):
+  // one warp reduction and one plain store per FOUR hypotheses, summed once per chunk
+  __shared__ unsigned sC[RS_THREADS / 32][RS_HCHUNK / 4];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pair = blockIdx.z;
   const int n = npts ? npts[pair] : n_single;
@@ -143,8 +146,17 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_count_kernel(const double2*
       sH[tid].qd = fmaxf(__double2float_ru(emax * (0.0019531250 * 1.000001)), 1e-18f);  // sqrt(64u) = 2^-9
     }
     __syncthreads();
-    for (int h = 0; h < nh; h++) {
-      const RsHyp& hy = sH[h];
+    for (int h4 = 0; h4 < nh; h4 += 4) {  // (entries past nh hold stale hypotheses: computed, never read back)
+      unsigned cpack = 0;
+#pragma unroll
+      for (int hk = 0; hk < 4; hk++) {
+      const int h = h4 + hk;
+      const float4 q0 = reinterpret_cast<const float4*>(&sH[h])[0], q1 = reinterpret_cast<const float4*>(&sH[h])[1],
+                   q2 = reinterpret_cast<const float4*>(&sH[h])[2];
+      RsHyp hy;
+      hy.e[0] = q0.x; hy.e[1] = q0.y; hy.e[2] = q0.z; hy.e[3] = q0.w;
+      hy.e[4] = q1.x; hy.e[5] = q1.y; hy.e[6] = q1.z; hy.e[7] = q1.w;
+      hy.e[8] = q2.x; hy.cn = q2.y; hy.qd = q2.z;
       // the thread's points two at a time: FFMA2 / FMUL2 / FADD2 (sm_100a packed FP32, one issue slot for two points'
       // worth of work; a scalar coefficient is a broadcast operand).  Every half is the correctly rounded FP32 operation
       // the bound derivation assumes.
@@ -184,14 +196,16 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_count_kernel(const double2*
             c += is_inlier(n2, den, thr, thr_lo, thr_hi) ? 1 : 0;
           }
       }
-      c = __reduce_add_sync(0xffffffffu, c);
-      if (lane == 0) sC[warp][h] = c;
+      cpack += (unsigned)c << (8 * hk);
+      }
+      cpack = __reduce_add_sync(0xffffffffu, cpack);
+      if (lane == 0) sC[warp][h4 >> 2] = cpack;
     }
     __syncthreads();
     if (tid < nh) {
       int t = 0;
 #pragma unroll
-      for (int wq = 0; wq < RS_THREADS / 32; wq++) t += sC[wq][tid];
+      for (int wq = 0; wq < RS_THREADS / 32; wq++) t += (int)((sC[wq][tid >> 2] >> (8 * (tid & 3))) & 0xffu);
       if (t) atomicAdd(&counts[hc + tid], t);
     }
   }

@@ -31,42 +31,43 @@ struct NcclApi {
   std::string err;
 };
 
+// Bound once per process (C++11 function-local static: thread-safe - ranks may be threads of one process).
 NcclApi* nccl_api() {
-  static NcclApi api;
-  static bool tried = false;
-  if (tried) return &api;
-  tried = true;
-  const char* names[] = {getenv("SFMGPU_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
-  for (const char* n : names) {
-    if (!n || !*n) continue;
-    api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
-    if (api.lib) break;
-  }
-  if (!api.lib) {
-    api.err = "NCCL library not found (libnccl.so.2; set SFMGPU_NCCL_LIB)";
-    return &api;
-  }
-  bool ok = true;
-  auto sym = [&](const char* name) {
-    void* p = dlsym(api.lib, name);
-    if (!p) {
-      ok = false;
-      api.err = std::string("NCCL symbol missing: ") + name;
+  static NcclApi api = [] {
+    NcclApi a;
+    const char* names[] = {getenv("SFMGPU_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      if (!n || !*n) continue;
+      a.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (a.lib) break;
     }
-    return p;
-  };
-  api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
-  api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
-  api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
-  api.Send = (decltype(api.Send))sym("ncclSend");
-  api.Recv = (decltype(api.Recv))sym("ncclRecv");
-  api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
-  api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
-  api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
-  if (!ok) {
-    dlclose(api.lib);
-    api.lib = nullptr;
-  }
+    if (!a.lib) {
+      a.err = "NCCL library not found (libnccl.so.2; set SFMGPU_NCCL_LIB)";
+      return a;
+    }
+    bool ok = true;
+    auto sym = [&](const char* name) {
+      void* p = dlsym(a.lib, name);
+      if (!p) {
+        ok = false;
+        a.err = std::string("NCCL symbol missing: ") + name;
+      }
+      return p;
+    };
+    a.GetUniqueId = (decltype(a.GetUniqueId))sym("ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))sym("ncclCommInitRank");
+    a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy");
+    a.Send = (decltype(a.Send))sym("ncclSend");
+    a.Recv = (decltype(a.Recv))sym("ncclRecv");
+    a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart");
+    a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd");
+    a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
+    if (!ok) {
+      dlclose(a.lib);
+      a.lib = nullptr;
+    }
+    return a;
+  }();
   return &api;
 }
 
