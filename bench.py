@@ -779,7 +779,7 @@ def main():
     ap.add_argument("--no-c2", action="store_true", help="skip the C2 side measurement of the default line")
     ap.add_argument("--pipe", type=int, default=-1, help="pairs per sub-chunk of the stage pipeline (-1: library default, 0: off)")
     ap.add_argument("--klt-mode", type=int, default=0, help="sfmgpu_klt_set_mode value (A/B timing of kernel variants)")
-    ap.add_argument("--chunk", type=int, default=0, help="frames per chunk of the streaming e2e call (0: a tenth of the rank's frames)")
+    ap.add_argument("--chunk", type=int, default=0, help="frames per chunk of the streaming e2e call (0: library default, about 100 frames)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     wl = WORKLOADS["c3" if args.workload == "c5" else args.workload]

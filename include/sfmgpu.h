@@ -152,8 +152,8 @@ int sfmgpu_pair_frontend(sfmgpu_ctx* ctx, sfmgpu_frames* f, int first_frame, int
 int sfmgpu_pipeline_set(sfmgpu_ctx* ctx, int pairs_per_chunk);
 /* Streaming variant for frames that live in HOST memory (pinned for full speed; nframes images of w*h bytes, stride
  * w).  Frames [0, nframes) of `f` are overwritten; pairs (k, k+1), k < nframes-1.  The upload of chunk c+1 overlaps
- * pyramid + corners + KLT of chunk c and the download of chunk c-1 (separate streams); chunk_frames <= 0 picks a
- * sixth of the sequence.  li/lj are [nframes-1][max_corners] (x,y) pairs, n_kept/n_corners [nframes-1]; any of the
+ * pyramid + corners + KLT of chunk c and the download of chunk c-1 (separate streams); chunk_frames <= 0 picks
+ * about 100 frames (at least 8, at most 20 chunks).  li/lj are [nframes-1][max_corners] (x,y) pairs, n_kept/n_corners [nframes-1]; any of the
  * four may be NULL.  Returns after everything has landed in host memory. */
 int sfmgpu_pair_frontend_host(sfmgpu_ctx* ctx, sfmgpu_frames* f, const uint8_t* host_pix, int nframes,
                               const sfmgpu_lkcfg* cfg, sfmgpu_pairs* out, int chunk_frames, double* li_xy, double* lj_xy,

@@ -377,7 +377,8 @@ constexpr int RX_TILE = 4096;  // words per tile (THREADS * ITEMS)
 
 template <int THREADS>
 struct RadixSmem {
-  __align__(16) unsigned long long tile[2][RX_TILE];  // cp.async double buffer
+  __align__(16) unsigned long long tile[2][RX_TILE];  // double buffer filled by the TMA engine (cp.async.bulk), one mbarrier each
+  __align__(8) unsigned long long bar[2];
   unsigned hist[RX_PASSES][256];
   unsigned goff[256];
   unsigned wc[THREADS / 32][256];
@@ -397,8 +398,35 @@ __device__ __forceinline__ unsigned long long rx_key_of(const CornerWorkView& wv
   return wv.tmp_key[(size_t)fr * wv.cand_cap + (low & RX_SLOT)];
 }
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+// ---- bulk asynchronous copies (the 1-D form of TMA, sm_90+ / sm_100a: UBLKCP in SASS) -----------------------------------------
+// One thread hands a whole tile (up to 32 KB) to the copy engine and the bytes are counted on an mbarrier; the other 511 /
+// 1023 threads issue nothing (the cp.async version cost every thread 4-8 copy instructions + a commit per tile).
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem, const void* gmem, unsigned bytes, unsigned long long* bar) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar), d = (unsigned)__cvta_generic_to_shared(smem);
+  // generic-proxy accesses made so far (this block's global stores of the previous pass, shared-memory reads of the
+  // buffer's previous tile) are ordered before the async-proxy copy
+  asm volatile("fence.proxy.async;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(gmem), "r"(bytes),
+               "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(b),
+      "r"(parity)
+      : "memory");
 }
 
 template <int THREADS, int ITEMS>
@@ -413,7 +441,13 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) radix_sort_frame_kern
   unsigned long long* B = wv.pk_b + cb;
   if (tid == 0) wv.sorted_in_b[fr] = 0;
   for (int i = tid; i < RX_PASSES * 256; i += THREADS) (&sm.hist[0][0])[i] = 0;
-  if (tid == 0) sm.nkeep = 0;
+  if (tid == 0) {
+    sm.nkeep = 0;
+    mbar_init(&sm.bar[0], 1);
+    mbar_init(&sm.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  unsigned bar_parity = 0;  // bit b: parity the next completion of buffer b's barrier will have
   __syncthreads();
   unsigned n;
   if (wv.exact_list[fr]) {
@@ -476,7 +510,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) radix_sort_frame_kern
         }
       }
     }
-    __threadfence();  // the first pass reads A back through cp.async (L2)
+    __threadfence();  // the first pass reads A back through the copy engine (L2)
     __syncthreads();
     n = sm.nkeep;
     if (tid == 0) wv.nfinal[fr] = n;
@@ -511,22 +545,18 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) radix_sort_frame_kern
       for (int k = 0; k < warp; k++) base += sm.wsum[k];
       sm.goff[tid] += base;
     }
-    // tiles stream through a cp.async double buffer: tile t+1 is in flight while tile t is ranked and scattered
+    // tiles stream through a double buffer filled by bulk copies: tile t+1 is in flight while tile t is ranked and scattered
     auto fetch = [&](int buf, unsigned t0) {
       const unsigned words = n - t0 < (unsigned)TILE ? n - t0 : (unsigned)TILE, chunks = (words + 1) / 2;  // 16-byte chunks
-      for (unsigned c = tid; c < chunks; c += THREADS) cp_async16(&sm.tile[buf][2 * c], src + t0 + 2 * c);
-      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (tid == 0) bulk_load(&sm.tile[buf][0], src + t0, chunks * 16u, &sm.bar[buf]);
     };
     fetch(0, 0);
     int it = 0;
     for (unsigned t0 = 0; t0 < n; t0 += TILE, it++) {
-      if (t0 + TILE < n) {
-        fetch((it + 1) & 1, t0 + TILE);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-      } else {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-      }
-      __syncthreads();  // tile landed for every thread / goff ready / previous tile's scatter has read wc
+      if (t0 + TILE < n) fetch((it + 1) & 1, t0 + TILE);
+      mbar_wait(&sm.bar[it & 1], (bar_parity >> (it & 1)) & 1u);  // the tile's bytes have landed
+      bar_parity ^= 1u << (it & 1);
+      __syncthreads();  // goff ready / previous tile's scatter has read wc
 #pragma unroll
       for (int k = 0; k < WARPS; k += THREADS / 256) {
         const int row = k + (tid >> 8);
@@ -582,7 +612,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) radix_sort_frame_kern
       for (int r = 0; r < ITEMS; r++)
         if (base + r * 32 + lane < n) dst[sm.wc[warp][d[r]] + old[r]] = v[r];
     }
-    __threadfence();  // the next pass reads these words back through cp.async (L2)
+    __threadfence();  // the next pass reads these words back through the copy engine (L2)
     __syncthreads();
     unsigned long long* t = src;
     src = dst;

@@ -538,9 +538,16 @@ int sfmgpu_pair_frontend_host(sfmgpu_ctx* ctx, sfmgpu_frames* f, const uint8_t* 
   SFM_CUDA(ctx, cudaMemsetAsync(out->totals, 0, 64, ctx->stream));
   if (nframes == 0) return 0;
   SFM_TRY(pipe_streams(ctx));
-  // default: a tenth of the sequence (measured on C2, 1000 frames: chunks of 84-125 frames 43.0 ms end to end, 167: 44.1,
-  // 250: 46.3, 50: 47.8 - smaller chunks shorten the pipeline fill, too small ones under-fill the per-frame kernels)
-  int chunk = chunk_frames > 0 ? chunk_frames : (nframes + 9) / 10;
+  // default: about 100 frames, at least 8 chunks for short sequences, at most 20 for long ones.  Smaller chunks shorten the
+  // pipeline fill (the first upload and the last chunk's compute are not overlapped), too small ones under-fill the
+  // one-block-per-frame kernels.  Measured end to end: C2 (1000 x 1080p) chunks of 84-125 frames 43.0 ms, 167: 44.1, 250: 46.3,
+  // 50: 47.8; C3 with the RANSAC stage (2000 x 4K) 50: 372 ms, 100: 358, 150: 385, 200: 390.
+  int chunk = chunk_frames;
+  if (chunk <= 0) {
+    const int by8 = (nframes + 7) / 8, by20 = (nframes + 19) / 20;
+    chunk = by8 < 96 ? by8 : 96;
+    if (chunk < by20) chunk = by20;
+  }
   if (chunk < 2) chunk = 2;
   if (chunk > 1024) chunk = 1024;
   const int nchunks = (nframes + chunk - 1) / chunk;
