@@ -361,6 +361,12 @@ __global__ void __launch_bounds__(32 * LWARPS, MINB) klt_lane_kernel(KltLaunch k
 // does not shift with the tap index and all 68 products per pixel must be accumulated directly: ~12 k instructions per
 // build, no faster than the FP64 masked walk of klt_lane_kernel<..., true> - 15.05 vs 14.96 ms for the stage.)
 //
+// (Also tried, round 2: the build on packed FP32 - FFMA2 with (dx, dy) register pairs advances the xx and yy families, the two
+// orders of the mixed family and (xe, ye) together: 216 FFMA2 per grid row instead of 414 FFMA, 521 instead of 805
+// instructions per row, bit-identical matrices - and SLOWER: 15.7 vs 14.8 ms on C2, 24.4 vs 22.8 ms on 400 4K frames; with
+// the row loops unrolled by two 19.0 / 30.0 ms.  An FFMA2 holds the FMA pipe for ~2.4 cycles, so a build that is bound by the
+// FMA pipe gains nothing from the saved issue slots and pays for the register-pair moves.)
+//
 // Lanes of a warp advance independently (level, iteration): a lane iterates while its matrices are valid and waits when
 // it needs new ones; when every unfinished lane waits, all of them stage their tiles and build together.
 constexpr int QM = 50;                         // doubles per lane: XX, YY, XY, XE, YE x 10 upper-triangle entries

@@ -17,6 +17,8 @@
 // (no dense contraction).
 #include <math.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -55,18 +57,26 @@ __device__ __forceinline__ bool is_inlier(double n2, double den, double thr, dou
 // u = 2^-24, P = max(|x|,|y|,1), P' = max(|x'|,|y'|,1), Pm = max(P,P'), Esum = sum |E_ij|, Emax = the largest absolute
 // row / column sum of E that enters ex, ey, ez, tx, ty:
 //   |v_f - v| <= 6u Emax Pm               for v in {ex, ey, ez, tx, ty}   (inputs rounded to FP32, two FMAs: <= 4.1u S)
-//   |num_f - num| <= 32u Esum P' Pm       (three such terms scaled by |x'|, |y'|, 1 plus two FMA roundings: <= 21u ...)
-//   |den_f - den| <= 64u (Emax Pm)^2 + 8u den_f   (v^2 error <= dv(2|v| + dv), |v| <= Emax Pm; four FMA roundings)
+//   |num_f - num| <= dn = 32u Esum P' Pm  (three such terms scaled by |x'|, |y'|, 1 plus two FMA roundings: <= 21u ...)
+//   |den_f - den| <= dd = 64u (Emax Pm)^2 + 8u den_f   (v^2 error <= dv(2|v| + dv), |v| <= Emax Pm; four FMA roundings)
 // The FP64 reference's own value differs from the exact one by < 1e-13 relative to the same magnitudes, which the slack
-// between 21u and 32u (resp. 48u and 64u) covers.  Then  e < thr  is certain when (|num_f| + dn)^2 < thr_lo (den_f - dd)
-// and  e >= thr  is certain when (|num_f| - dn)^2 > thr_hi (den_f + dd), with thr_lo / thr_hi = thr (1 -/+ 2e-6) rounded
-// outwards and divided / multiplied by 1 + 2^-20 for the FP32 roundings of the bound arithmetic itself (< 7u).  NaNs,
-// infinities and overflowing magnitudes fail both tests and take the FP64 path.
+// between 21u and 32u (resp. 48u and 64u) covers.  With N = |num_f|, D = den_f and eps = 2e-6:
+//   e < thr   is certain when (N + dn)^2 < thr (1 - eps) (D - dd),   e >= thr   when max(N - dn, 0)^2 > thr (1 + eps) (D + dd).
+// Both follow from ONE residual test (expand the squares; (N - dn)^2 >= N^2 - 2 N dn):
+//   r = N^2 - thr D,     |r| > B,     B >= dn (2N + dn) + thr (1 + eps) 64u (Emax Pm)^2 + (eps + 8u (1 + eps)) thr D,
+// the sign of r then being the answer.  The kernel evaluates r_f = fma(N, N, -td), td = fl(thr_f D), s_f = fma(N, N, td):
+// |r_f - r| <= 3.1u s, thr D <= (1 + 2.1u) s, so with z >= Pm^2 >= P' Pm per point and, per hypothesis, c1 = 2 cn,
+// c2 >= cn^2 (cn >= 32u Esum), cq >= thr (1 + eps) 64u Emax^2, kappa = eps + 16u (>= eps + 11.2u, the rest is slack for
+// the <= 4 FP32 roundings of the bound's own arithmetic, as is the 1e-6 every constant is scaled up by):
+//   B_f = fma(z, fma(c1, N, fma(c2, z, cq)), kappa s_f).
+// NaNs, infinities and overflowing magnitudes make the comparison false and take the FP64 path; thresholds outside
+// (1e-18, 1e18) disable the screen (every pair takes the FP64 path).  tests/test_ransac_bound.py emulates this arithmetic
+// on the CPU against 80-bit values.
 struct __align__(16) RsHyp {  // 48 bytes: read with three 128-bit shared-memory loads
   float e[9];
-  float cn;   // 32u * Esum (rounded up, floored at 1e-30: subnormal hypotheses)
-  float qd;   // sqrt(64u) * Emax (rounded up)
-  float pad;
+  float c1;  // 2 cn, cn = 32u * Esum (rounded up, floored at 1e-30: subnormal hypotheses)
+  float c2;  // cn^2 (rounded up)
+  float cq;  // thr (1 + eps) * 64u * Emax^2 (rounded up)
 };
 
 // blockIdx.z = correspondence set ("pair") of a batch: points at xi/xj + pair * pt_stride, npts[pair] of them (npts == nullptr:
@@ -74,8 +84,8 @@ struct __align__(16) RsHyp {  // 48 bytes: read with three 128-bit shared-memory
 __global__ void __launch_bounds__(RS_THREADS) ransac_count_kernel(const double2* __restrict__ xi, const double2* __restrict__ xj,
                                                                  size_t pt_stride, const int* __restrict__ npts, int n_single,
                                                                  const double* __restrict__ E, int H, int h_per_block,
-                                                                 double thr, double thr_lo, double thr_hi, float thr_lo_f,
-                                                                 float thr_hi_f, int* __restrict__ counts) {
+                                                                 double thr, double thr_lo, double thr_hi, float thr_f,
+                                                                 float kappa_f, int* __restrict__ counts) {
   __shared__ double sE[RS_HCHUNK * 9];
   __shared__ RsHyp sH[RS_HCHUNK];
   // per-warp counts of the chunk, four hypotheses per word (a warp counts at most 2 x 32 per hypothesis: one byte each):
@@ -91,13 +101,14 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_count_kernel(const double2*
   counts += (size_t)pair * H;
   const int p0 = (blockIdx.x * RS_THREADS + tid) * RS_PTS;
   double x[RS_PTS], y[RS_PTS], xp[RS_PTS], yp[RS_PTS];
-  float xf[RS_PTS], yf[RS_PTS], xpf[RS_PTS], ypf[RS_PTS], pp[RS_PTS], pm[RS_PTS];
-  bool valid[RS_PTS];
+  float xf[RS_PTS], yf[RS_PTS], xpf[RS_PTS], ypf[RS_PTS], zf[RS_PTS];
+  unsigned vmask = 0;  // bit k: point k of this thread exists
 #pragma unroll
   for (int k = 0; k < RS_PTS; k++) {
-    valid[k] = p0 + k < n;
-    const double2 a = valid[k] ? xi[p0 + k] : make_double2(0, 0);
-    const double2 b = valid[k] ? xj[p0 + k] : make_double2(0, 0);
+    const bool valid = p0 + k < n;
+    vmask |= valid ? (1u << k) : 0u;
+    const double2 a = valid ? xi[p0 + k] : make_double2(0, 0);
+    const double2 b = valid ? xj[p0 + k] : make_double2(0, 0);
     x[k] = a.x;
     y[k] = a.y;
     xp[k] = b.x;
@@ -106,23 +117,22 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_count_kernel(const double2*
     yf[k] = (float)a.y;
     xpf[k] = (float)b.x;
     ypf[k] = (float)b.y;
-    const double P = fmax(fmax(fabs(a.x), fabs(a.y)), 1.0), Pp = fmax(fmax(fabs(b.x), fabs(b.y)), 1.0), Pm = fmax(P, Pp);
-    pm[k] = __double2float_ru(Pm);                 // NaN / inf propagate and end in the FP64 path
-    pp[k] = __double2float_ru(Pp * Pm * 1.000001);
+    const double Pm = fmax(fmax(fmax(fabs(a.x), fabs(a.y)), fmax(fabs(b.x), fabs(b.y))), 1.0);
+    zf[k] = __double2float_ru(Pm * Pm * 1.000002);  // NaN / inf propagate and end in the FP64 path
   }
   static_assert(RS_PTS % 2 == 0, "the FP32 screen packs the thread's points two by two into float2");
   constexpr int NP = RS_PTS / 2;
-  float2 X[NP], Y[NP], XP[NP], YP[NP], PP[NP], PM[NP];
+  float2 X[NP], Y[NP], XP[NP], YP[NP], Z[NP];
 #pragma unroll
   for (int g = 0; g < NP; g++) {
     X[g] = make_float2(xf[2 * g], xf[2 * g + 1]);
     Y[g] = make_float2(yf[2 * g], yf[2 * g + 1]);
     XP[g] = make_float2(xpf[2 * g], xpf[2 * g + 1]);
     YP[g] = make_float2(ypf[2 * g], ypf[2 * g + 1]);
-    PP[g] = make_float2(pp[2 * g], pp[2 * g + 1]);
-    PM[g] = make_float2(pm[2 * g], pm[2 * g + 1]);
+    Z[g] = make_float2(zf[2 * g], zf[2 * g + 1]);
   }
-  const float U8 = 4.76837158203125e-7f;  // 8u
+  // only the last block of a set has threads without points: the common case counts without masking
+  const bool tail = (int)((blockIdx.x + 1) * RS_THREADS * RS_PTS) > n;
   const int h_begin = blockIdx.y * h_per_block;
   const int h_end = min(H, h_begin + h_per_block);
   for (int hc = h_begin; hc < h_end; hc += RS_HCHUNK) {
@@ -142,65 +152,74 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_count_kernel(const double2*
       const double r0 = a[0] + a[1] + a[2], r1 = a[3] + a[4] + a[5], r2 = a[6] + a[7] + a[8];
       const double c0 = a[0] + a[3] + a[6], c1 = a[1] + a[4] + a[7];
       const double emax = fmax(fmax(fmax(r0, r1), fmax(r2, c0)), c1), esum = r0 + r1 + r2;
-      sH[tid].cn = fmaxf(__double2float_ru(esum * (32.0 * 5.9604644775390625e-8 * 1.000001)), 1e-30f);
-      sH[tid].qd = fmaxf(__double2float_ru(emax * (0.0019531250 * 1.000001)), 1e-18f);  // sqrt(64u) = 2^-9
+      const float cn = fmaxf(__double2float_ru(esum * (32.0 * 5.9604644775390625e-8 * 1.000001)), 1e-30f);
+      sH[tid].c1 = cn + cn;
+      sH[tid].c2 = __double2float_ru((double)cn * (double)cn * 1.000001);
+      sH[tid].cq = __double2float_ru(thr * (1.0 + 2e-6) * (64.0 * 5.9604644775390625e-8 * 1.000001) * emax * emax);
     }
     __syncthreads();
-    for (int h4 = 0; h4 < nh; h4 += 4) {  // (entries past nh hold stale hypotheses: computed, never read back)
-      unsigned cpack = 0;
+    auto chunk = [&](auto tail_tag) {
+      constexpr bool TAIL = decltype(tail_tag)::value;
+      for (int h4 = 0; h4 < nh; h4 += 4) {  // (entries past nh hold stale hypotheses: computed, never read back)
+        unsigned cpack = 0;
 #pragma unroll
-      for (int hk = 0; hk < 4; hk++) {
-      const int h = h4 + hk;
-      const float4 q0 = reinterpret_cast<const float4*>(&sH[h])[0], q1 = reinterpret_cast<const float4*>(&sH[h])[1],
-                   q2 = reinterpret_cast<const float4*>(&sH[h])[2];
-      RsHyp hy;
-      hy.e[0] = q0.x; hy.e[1] = q0.y; hy.e[2] = q0.z; hy.e[3] = q0.w;
-      hy.e[4] = q1.x; hy.e[5] = q1.y; hy.e[6] = q1.z; hy.e[7] = q1.w;
-      hy.e[8] = q2.x; hy.cn = q2.y; hy.qd = q2.z;
-      // the thread's points two at a time: FFMA2 / FMUL2 / FADD2 (sm_100a packed FP32, one issue slot for two points'
-      // worth of work; a scalar coefficient is a broadcast operand).  Every half is the correctly rounded FP32 operation
-      // the bound derivation assumes.
-      int c = 0;
-      unsigned undecided = 0;
+        for (int hk = 0; hk < 4; hk++) {
+          const int h = h4 + hk;
+          const float4 q0 = reinterpret_cast<const float4*>(&sH[h])[0], q1 = reinterpret_cast<const float4*>(&sH[h])[1],
+                       q2 = reinterpret_cast<const float4*>(&sH[h])[2];
+          RsHyp hy;
+          hy.e[0] = q0.x; hy.e[1] = q0.y; hy.e[2] = q0.z; hy.e[3] = q0.w;
+          hy.e[4] = q1.x; hy.e[5] = q1.y; hy.e[6] = q1.z; hy.e[7] = q1.w;
+          hy.e[8] = q2.x; hy.c1 = q2.y; hy.c2 = q2.z; hy.cq = q2.w;
+          // the thread's points two at a time: FFMA2 / FMUL2 / FADD2 (sm_100a packed FP32, one issue slot for two points'
+          // worth of work; a scalar coefficient is a broadcast operand).  Every half is the correctly rounded FP32 operation
+          // the bound derivation assumes.
+          int c = 0;
+          unsigned undecided = 0;
 #pragma unroll
-      for (int g = 0; g < NP; g++) {
-        const float2 ex = __ffma2_rn(B2(hy.e[0]), X[g], __ffma2_rn(B2(hy.e[1]), Y[g], B2(hy.e[2])));
-        const float2 ey = __ffma2_rn(B2(hy.e[3]), X[g], __ffma2_rn(B2(hy.e[4]), Y[g], B2(hy.e[5])));
-        const float2 ez = __ffma2_rn(B2(hy.e[6]), X[g], __ffma2_rn(B2(hy.e[7]), Y[g], B2(hy.e[8])));
-        const float2 tx = __ffma2_rn(B2(hy.e[0]), XP[g], __ffma2_rn(B2(hy.e[3]), YP[g], B2(hy.e[6])));
-        const float2 ty = __ffma2_rn(B2(hy.e[1]), XP[g], __ffma2_rn(B2(hy.e[4]), YP[g], B2(hy.e[7])));
-        const float2 nv = __ffma2_rn(XP[g], ex, __ffma2_rn(YP[g], ey, ez));
-        const float2 num = make_float2(fabsf(nv.x), fabsf(nv.y));
-        const float2 den = __ffma2_rn(ty, ty, __ffma2_rn(tx, tx, __ffma2_rn(ey, ey, __ffma2_rn(ex, ex, B2(1e-12f)))));
-        const float2 dn = __fmul2_rn(B2(hy.cn), PP[g]);
-        const float2 q = __fmul2_rn(B2(hy.qd), PM[g]);
-        const float2 dd = __ffma2_rn(q, q, __fmul2_rn(B2(U8), den));
-        const float2 a = __fadd2_rn(num, dn);
-        const float2 bm = __fadd2_rn(num, make_float2(-dn.x, -dn.y));
-        const float2 b = make_float2(fmaxf(bm.x, 0.f), fmaxf(bm.y, 0.f));
-        const float2 a2 = __fmul2_rn(a, a), b2 = __fmul2_rn(b, b);
-        const float2 lo = __fmul2_rn(B2(thr_lo_f), __fadd2_rn(den, make_float2(-dd.x, -dd.y)));
-        const float2 hi = __fmul2_rn(B2(thr_hi_f), __fadd2_rn(den, dd));
-        const bool in0 = a2.x < lo.x, in1 = a2.y < lo.y;
-        const bool out0 = (b2.x > hi.x) && (a.x < 1.0e18f), out1 = (b2.y > hi.y) && (a.y < 1.0e18f);
-        c += ((in0 && valid[2 * g]) ? 1 : 0) + ((in1 && valid[2 * g + 1]) ? 1 : 0);
-        undecided |= ((!in0 && !out0 && valid[2 * g]) ? (1u << (2 * g)) : 0u) | ((!in1 && !out1 && valid[2 * g + 1]) ? (2u << (2 * g)) : 0u);
-      }
-      if (__any_sync(0xffffffffu, undecided != 0)) {  // rare: the reference's FP64 arithmetic decides
-        const double* e = sE + h * 9;
-#pragma unroll
-        for (int k = 0; k < RS_PTS; k++)
-          if (undecided & (1u << k)) {
-            double n2, den;
-            sampson_parts(e, x[k], y[k], xp[k], yp[k], n2, den);
-            c += is_inlier(n2, den, thr, thr_lo, thr_hi) ? 1 : 0;
+          for (int g = 0; g < NP; g++) {
+            const float2 ex = __ffma2_rn(B2(hy.e[0]), X[g], __ffma2_rn(B2(hy.e[1]), Y[g], B2(hy.e[2])));
+            const float2 ey = __ffma2_rn(B2(hy.e[3]), X[g], __ffma2_rn(B2(hy.e[4]), Y[g], B2(hy.e[5])));
+            const float2 ez = __ffma2_rn(B2(hy.e[6]), X[g], __ffma2_rn(B2(hy.e[7]), Y[g], B2(hy.e[8])));
+            const float2 tx = __ffma2_rn(B2(hy.e[0]), XP[g], __ffma2_rn(B2(hy.e[3]), YP[g], B2(hy.e[6])));
+            const float2 ty = __ffma2_rn(B2(hy.e[1]), XP[g], __ffma2_rn(B2(hy.e[4]), YP[g], B2(hy.e[7])));
+            const float2 nv = __ffma2_rn(XP[g], ex, __ffma2_rn(YP[g], ey, ez));
+            const float2 den = __ffma2_rn(ty, ty, __ffma2_rn(tx, tx, __ffma2_rn(ey, ey, __ffma2_rn(ex, ex, B2(1e-12f)))));
+            const float2 td = __fmul2_rn(B2(thr_f), den);
+            const float2 r = __ffma2_rn(nv, nv, make_float2(-td.x, -td.y));
+            const float2 sm = __ffma2_rn(nv, nv, td);
+            const float2 i1 = __ffma2_rn(B2(hy.c2), Z[g], B2(hy.cq));
+            const float2 i2 = __ffma2_rn(B2(hy.c1), make_float2(fabsf(nv.x), fabsf(nv.y)), i1);
+            const float2 bb = __ffma2_rn(Z[g], i2, __fmul2_rn(B2(kappa_f), sm));
+            const bool dec0 = fabsf(r.x) > bb.x, dec1 = fabsf(r.y) > bb.y;  // false for NaN / inf: the FP64 path decides
+            const bool in0 = dec0 && r.x < 0.f, in1 = dec1 && r.y < 0.f;
+            if (TAIL) {
+              c += ((in0 && (vmask >> (2 * g)) & 1u) ? 1 : 0) + ((in1 && (vmask >> (2 * g + 1)) & 1u) ? 1 : 0);
+              undecided |= ((!dec0 ? 1u : 0u) | (!dec1 ? 2u : 0u)) << (2 * g);
+            } else {
+              c += (in0 ? 1 : 0) + (in1 ? 1 : 0);
+              undecided |= ((!dec0 ? 1u : 0u) | (!dec1 ? 2u : 0u)) << (2 * g);
+            }
           }
+          if (TAIL) undecided &= vmask;
+          if (__any_sync(0xffffffffu, undecided != 0)) {  // rare: the reference's FP64 arithmetic decides
+            const double* e = sE + h * 9;
+#pragma unroll
+            for (int k = 0; k < RS_PTS; k++)
+              if (undecided & (1u << k)) {
+                double n2, den;
+                sampson_parts(e, x[k], y[k], xp[k], yp[k], n2, den);
+                c += is_inlier(n2, den, thr, thr_lo, thr_hi) ? 1 : 0;
+              }
+          }
+          cpack += (unsigned)c << (8 * hk);
+        }
+        cpack = __reduce_add_sync(0xffffffffu, cpack);
+        if (lane == 0) sC[warp][h4 >> 2] = cpack;
       }
-      cpack += (unsigned)c << (8 * hk);
-      }
-      cpack = __reduce_add_sync(0xffffffffu, cpack);
-      if (lane == 0) sC[warp][h4 >> 2] = cpack;
-    }
+    };
+    if (tail) chunk(std::true_type{});
+    else chunk(std::false_type{});
     __syncthreads();
     if (tid < nh) {
       int t = 0;
@@ -309,22 +328,16 @@ int sfm_ransac_score_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* 
     const unsigned gy = sfm_cdiv(H, hpb);
     // thr_lo / thr_hi bracket thr by 2^-50 relative (see is_inlier)
     const double eps = 8.8817841970012523e-16;  // 2^-50
-    // FP32 screen thresholds: thr (1 -/+ 2e-6), rounded outwards, with the 1 + 2^-20 of the bound arithmetic folded in.
-    // A threshold the screen cannot represent (<= 0, non-finite, outside the FP32 range) disables it: every pair is
-    // then undecided and takes the FP64 path.
-    const double kk = 1.0 + 9.5367431640625e-7;
-    float tlo = (float)(thr * (1.0 - 2e-6) / kk), thi = (float)(thr * (1.0 + 2e-6) * kk);
-    tlo = nextafterf(tlo, -INFINITY);
-    thi = nextafterf(thi, INFINITY);
-    if (!(thr > 1e-30 && thr < 1e30)) {
-      tlo = -INFINITY;  // "a*a < -inf" never holds
-      thi = INFINITY;   // "b*b > inf" never holds
-    }
+    // FP32 screen (see RsHyp): thr as float, kappa = (eps + 16u) with slack.  A threshold the screen cannot handle
+    // (<= 0, non-finite, outside (1e-18, 1e18)) disables it: td = NaN leaves every pair undecided, i.e. to the FP64 path.
+    float thr_f = (float)thr;
+    const float kappa_f = (float)((2e-6 + 16.0 * 5.9604644775390625e-8) * 1.00001);
+    if (!(thr > 1e-18 && thr < 1e18)) thr_f = NAN;
     for (int z0 = 0; z0 < npairs; z0 += 65535) {  // grid.z limit
       const int nz = npairs - z0 < 65535 ? npairs - z0 : 65535;
       SFM_LAUNCH(ctx, ransac_count_kernel, dim3(gx, gy, nz), RS_THREADS, 0, xi + (size_t)z0 * pt_stride, xj + (size_t)z0 * pt_stride,
                  pt_stride, npts ? npts + z0 : nullptr, n, E + (size_t)z0 * H * 9, H, (int)hpb, thr, thr * (1.0 - eps),
-                 thr * (1.0 + eps), tlo, thi, counts + (size_t)z0 * H);
+                 thr * (1.0 + eps), thr_f, kappa_f, counts + (size_t)z0 * H);
     }
   }
   SFM_LAUNCH(ctx, ransac_argmax_kernel, npairs, 1024, 0, (const int*)counts, H, best);
