@@ -64,7 +64,10 @@ struct sfmgpu_ctx {
   DevBuf sel_work;   // corner-select work area
   DevBuf misc;       // small scalars
   DevBuf rs_xi, rs_xj, rs_E, rs_counts, rs_inl, rs_best, rs_idx8;
+  DevBuf sv_list;    // screening solver: [0] count, [64...] hypotheses left to the Jacobi emulation (repeated index)
   int rs_n = 0, rs_H = 0;
+  bool rs_screened = false;  // rs_E holds screening hypotheses of the octets in rs_idx8: the winner is re-solved when scored
+  int solver_mode = 1;       // device 8-point solver: 1 screening solver for the counts + Jacobi emulation for the winner, 0 Jacobi emulation for every hypothesis
   bool profile = false;
   struct StageEv { int stage; cudaEvent_t a, b; };
   std::vector<StageEv> stage_evs;
@@ -213,8 +216,10 @@ int sfm_candidates_single(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int frame, do
 int sfm_sort_perm(sfmgpu_ctx* ctx, const double* keys, int n, int32_t* perm);
 // solver.cu / ransac.cu: batched over correspondence sets
 int sfm_eight_point_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, const int* npts, int n_single,
-                            int npairs, const int* idx8, int H, double* Eout);
+                            int npairs, const int* idx8, int H, double* Eout, int screen);
+int sfm_eight_point_winners(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, const int* npts, int n_single,
+                            int npairs, const int* idx8, int H, const int* best, double* E);
 int sfm_pose_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, int npairs, const int* status,
                      const int* best, const int* inl, const double* bestE, double* R, double* t);
 int sfm_ransac_score_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, const int* npts, int n_max,
-                             int npairs, const double* E, int H, double thr, int* counts, int* best, int* inl);
+                             int npairs, double* E, int H, double thr, int* counts, int* best, int* inl, const int* refine_idx8);

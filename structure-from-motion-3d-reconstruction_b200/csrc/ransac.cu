@@ -266,8 +266,8 @@ __global__ void __launch_bounds__(1024) ransac_argmax_kernel(const int* __restri
 // Inlier indices of the winner, ascending (:669-672), by one block with an ordered ballot compaction.
 __global__ void __launch_bounds__(1024) ransac_mask_kernel(const double2* __restrict__ xi, const double2* __restrict__ xj,
                                                           size_t pt_stride, const int* __restrict__ npts, int n_single,
-                                                          const double* __restrict__ E, int H, const int* __restrict__ best, double thr,
-                                                          int* __restrict__ inl) {
+                                                          const double* __restrict__ E, int H, int* __restrict__ best, double thr,
+                                                          int* __restrict__ inl, int recount) {
   __shared__ int swarp[32];
   __shared__ int sbase;
   const int pair = blockIdx.x;  // one block per correspondence set
@@ -307,6 +307,8 @@ __global__ void __launch_bounds__(1024) ransac_mask_kernel(const double2* __rest
     if (tid == 0) sbase = base + total;
     __syncthreads();
   }
+  // the winner was re-solved after the counting pass (screening solver): its count is that of the hypothesis listed here
+  if (recount && tid == 0) best[1] = sbase;
 }
 
 }  // namespace
@@ -314,8 +316,11 @@ __global__ void __launch_bounds__(1024) ransac_mask_kernel(const double2* __rest
 // Scoring loop (:667-676) for `npairs` correspondence sets in one launch set: counts [npairs][H], best [npairs][2] =
 // (winner or -1, its count), inl [npairs][pt_stride] the winner's inlier indices ascending.  n_max bounds the points of a
 // set (grid size); npts (device, may be null: n_max points in every set) holds the actual numbers.
+// refine_idx8 != nullptr: E holds SCREENING hypotheses (solver.cu, eight_point_qr_kernel) of the octets refine_idx8
+// [npairs][H][8]: they decide the winner; the winner is then solved again by the Jacobi emulation (written over its slot
+// of E) and its inlier list and count (best[1]) are those of that hypothesis.
 int sfm_ransac_score_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, const int* npts, int n_max,
-                             int npairs, const double* E, int H, double thr, int* counts, int* best, int* inl) {
+                             int npairs, double* E, int H, double thr, int* counts, int* best, int* inl, const int* refine_idx8) {
   const int n = n_max;
   if (npairs <= 0) return 0;
   SFM_CUDA(ctx, cudaMemsetAsync(counts, 0, (size_t)npairs * (H > 0 ? H : 1) * sizeof(int), ctx->stream));
@@ -341,8 +346,11 @@ int sfm_ransac_score_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* 
     }
   }
   SFM_LAUNCH(ctx, ransac_argmax_kernel, npairs, 1024, 0, (const int*)counts, H, best);
-  if (H > 0 && n > 0)
-    SFM_LAUNCH(ctx, ransac_mask_kernel, npairs, 1024, 0, xi, xj, pt_stride, npts, n, E, H, (const int*)best, thr, inl);
+  if (H > 0 && n > 0) {
+    if (refine_idx8) SFM_TRY(sfm_eight_point_winners(ctx, xi, xj, pt_stride, npts, n, npairs, refine_idx8, H, (const int*)best, E));
+    SFM_LAUNCH(ctx, ransac_mask_kernel, npairs, 1024, 0, xi, xj, pt_stride, npts, n, (const double*)E, H, best, thr, inl,
+               refine_idx8 ? 1 : 0);
+  }
   return 0;
 }
 
@@ -350,8 +358,8 @@ namespace {
 
 int score_resident(sfmgpu_ctx* ctx, double thr) {
   return sfm_ransac_score_batched(ctx, (const double2*)ctx->rs_xi.p, (const double2*)ctx->rs_xj.p, 0, nullptr, ctx->rs_n, 1,
-                                  (const double*)ctx->rs_E.p, ctx->rs_H, thr, (int*)ctx->rs_counts.p, (int*)ctx->rs_best.p,
-                                  (int*)ctx->rs_inl.p);
+                                  (double*)ctx->rs_E.p, ctx->rs_H, thr, (int*)ctx->rs_counts.p, (int*)ctx->rs_best.p,
+                                  (int*)ctx->rs_inl.p, ctx->rs_screened ? (const int*)ctx->rs_idx8.p : nullptr);
 }
 
 }  // namespace
@@ -375,6 +383,7 @@ int sfmgpu_ransac_upload(sfmgpu_ctx* ctx, const double* xi_xy, const double* xj_
   if (H > 0) SFM_CUDA(ctx, cudaMemcpyAsync(ctx->rs_E.p, E, (size_t)H * 72, cudaMemcpyHostToDevice, ctx->stream));
   ctx->rs_n = n;
   ctx->rs_H = H;
+  ctx->rs_screened = false;
   return 0;
 }
 

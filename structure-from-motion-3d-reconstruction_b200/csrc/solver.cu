@@ -220,6 +220,23 @@ __device__ __forceinline__ void svd3_dev(const double* E0, double* U, double* s,
   U[2] = u2x; U[5] = u2y; U[8] = u2z;
 }
 
+// enforce_rank2 (:595-607) of the 3x3 matrix E0 (row-major): E = U diag(s0, s1, 0) V^T
+__device__ __forceinline__ void rank2_project(const double* E0, double* __restrict__ E) {
+  double U[9], sv[3], V[9];
+  svd3_dev(E0, U, sv, V);
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      // (U S)(r,k) = U(r,k) s_k ; row-by-column products in the reference's order (k = 0, 1, 2 with a zero third term)
+      double acc = 0;
+      acc += (U[3 * r] * sv[0]) * V[3 * c + 0];
+      acc += (U[3 * r + 1] * sv[1]) * V[3 * c + 1];
+      acc += 0.0 * V[3 * c + 2];
+      E[3 * r + c] = acc;
+    }
+}
+
 // eight_point_E (:609-627) for one index octet; sA = this thread's shared-memory column (stride TPB doubles).
 template <int TPB>
 __device__ void eight_point_solve(const double2* __restrict__ xi, const double2* __restrict__ xj, const int* __restrict__ idx8, int n,
@@ -308,20 +325,7 @@ __device__ void eight_point_solve(const double2* __restrict__ xi, const double2*
   double E0[9];
 #pragma unroll
   for (int i = 0; i < 9; i++) E0[i] = sA[i * TPB];
-  // enforce_rank2 (:595-607): E = U diag(s0, s1, 0) V^T
-  double U[9], sv[3], V[9];
-  svd3_dev(E0, U, sv, V);
-#pragma unroll
-  for (int r = 0; r < 3; r++)
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      // (U S)(r,k) = U(r,k) s_k ; row-by-column products in the reference's order (k = 0, 1, 2 with a zero third term)
-      double acc = 0;
-      acc += (U[3 * r] * sv[0]) * V[3 * c + 0];
-      acc += (U[3 * r + 1] * sv[1]) * V[3 * c + 1];
-      acc += 0.0 * V[3 * c + 2];
-      E[3 * r + c] = acc;
-    }
+  rank2_project(E0, E);
 }
 
 // Hypothesis h of pair blockIdx.y: octet idx8[pair][h][8], points xi/xj[pair * stride ...], n = npts[pair] (npts == nullptr:
@@ -336,6 +340,130 @@ __global__ void __launch_bounds__(SV_TPB, SV_MINB) eight_point_kernel(const doub
   const size_t ho = (size_t)pair * H + hyp;
   eight_point_solve<SV_TPB>(xi + (size_t)pair * pt_stride, xj + (size_t)pair * pt_stride, idx8 + ho * 8, n, sv_smem + threadIdx.x,
                             Eout + ho * 9);
+}
+
+// ---- direct null vector: the SCREENING solver of the batched RANSAC stage -----------------------------------------------------
+// eight_point_E asks for the unit vector e minimising ||A e|| (A: 8 x 9, one row per correspondence) and gets it as the
+// eigenvector of the smallest eigenvalue of A^T A from a Jacobi iteration (<= 120 rotations, absolute 1e-12 stop).  For
+// eight points A has an exact null vector, and that is what the iteration converges to.  This kernel computes the same
+// vector directly: Householder QR of A^T (9 x 8), column by column (left-looking: the finished reflectors are applied to
+// one new column at a time, so only the reflectors - 44 doubles - and one column are live), and e = Q e_9 = H_1 ... H_8 e_9,
+// the unit vector orthogonal to every row of A.  ~1,000 FMAs in registers instead of ~50,000 instructions of
+// shared-memory Jacobi.  Orthogonal transformations throughout: e is accurate to ~eps * cond(A), the Jacobi result to
+// ~eps * cond(A)^2 + 1e-12, so the two agree to the JACOBI result's own error (measured on the test scenes: median 1e-10,
+// 99 % below 5e-6 relative, against 1e-13 / 1e-8 for the emulation above), up to the sign of e, which neither the Sampson
+// error nor the pose tail sees.  Octets with a repeated index (sampling is with replacement, ~1 % of the hypotheses) have
+// a two-dimensional null space: every implementation returns an arbitrary member of it.
+// Used for COUNTING only: the winner of every correspondence set is re-solved by the Jacobi emulation (eight_point_winner_
+// kernel) before its inlier list, count and pose are produced, so what leaves the stage is the emulation's hypothesis.
+// FMAs are used on purpose here (nothing of the reference's operation order is being reproduced).
+constexpr int QR_TPB = 128;
+
+__device__ __forceinline__ void qr_null_vector(const double2* __restrict__ xi, const double2* __restrict__ xj, const int* __restrict__ idx8,
+                                               int n, double* __restrict__ e) {
+  double v[8][9];  // reflector k lives in v[k][k..8]
+  double beta[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    int i = idx8[j];
+    i = i < 0 ? 0 : (i >= n ? n - 1 : i);
+    const double2 a = xi[i], b = xj[i];
+    double col[9] = {b.x * a.x, b.x * a.y, b.x, b.y * a.x, b.y * a.y, b.y, a.x, a.y, 1.0};
+#pragma unroll
+    for (int k = 0; k < j; k++) {
+      double s = 0.0;
+#pragma unroll
+      for (int c = k; c < 9; c++) s = __fma_rn(v[k][c], col[c], s);
+      s *= -beta[k];
+#pragma unroll
+      for (int c = k; c < 9; c++) col[c] = __fma_rn(s, v[k][c], col[c]);
+    }
+    double sig = 0.0;
+#pragma unroll
+    for (int c = j; c < 9; c++) sig = __fma_rn(col[c], col[c], sig);
+    const double nrm = sqrt(sig);
+    const double vj = col[j] + copysign(nrm, col[j]);
+    const double den = nrm * fabs(vj);  // = v^T v / 2
+    beta[j] = den > 0.0 ? 1.0 / den : 0.0;  // a zero column needs no reflection
+    v[j][j] = vj;
+#pragma unroll
+    for (int c = j + 1; c < 9; c++) v[j][c] = col[c];
+  }
+  double q[9] = {0, 0, 0, 0, 0, 0, 0, 0, 1.0};
+#pragma unroll
+  for (int k = 7; k >= 0; k--) {
+    double s = 0.0;
+#pragma unroll
+    for (int c = k; c < 9; c++) s = __fma_rn(v[k][c], q[c], s);
+    s *= -beta[k];
+#pragma unroll
+    for (int c = k; c < 9; c++) q[c] = __fma_rn(s, v[k][c], q[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < 9; c++) e[c] = q[c];
+}
+
+__global__ void __launch_bounds__(QR_TPB, 4) eight_point_qr_kernel(const double2* __restrict__ xi, const double2* __restrict__ xj,
+                                                                   size_t pt_stride, const int* __restrict__ npts, int n_single,
+                                                                   const int* __restrict__ idx8, int H, double* __restrict__ Eout,
+                                                                   int* __restrict__ rep_count, int* __restrict__ rep_list) {
+  const int pair = blockIdx.y, hyp = blockIdx.x * QR_TPB + threadIdx.x;
+  const int n = npts ? npts[pair] : n_single;
+  if (hyp >= H || n < 8) return;
+  const size_t ho = (size_t)pair * H + hyp;
+  const int* oct = idx8 + ho * 8;
+  // a repeated index: two-dimensional null space, which member comes back is a property of the Jacobi iteration - those
+  // octets (about 28 / n of them) are left to the emulation (eight_point_list_kernel)
+  int id[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int i = oct[j];
+    id[j] = i < 0 ? 0 : (i >= n ? n - 1 : i);
+  }
+  bool rep = false;
+#pragma unroll
+  for (int a = 0; a < 8; a++)
+#pragma unroll
+    for (int b = a + 1; b < 8; b++) rep |= id[a] == id[b];
+  if (rep) {
+    rep_list[atomicAdd(rep_count, 1)] = (int)ho;
+    return;
+  }
+  double e[9];
+  qr_null_vector(xi + (size_t)pair * pt_stride, xj + (size_t)pair * pt_stride, oct, n, e);
+  rank2_project(e, Eout + ho * 9);
+}
+
+// The Jacobi emulation for the hypotheses on a device-side list (flat indices pair * H + hyp), resident grid.
+__global__ void __launch_bounds__(SV_TPB, SV_MINB) eight_point_list_kernel(const double2* __restrict__ xi, const double2* __restrict__ xj,
+                                                                    size_t pt_stride, const int* __restrict__ npts, int n_single,
+                                                                    const int* __restrict__ idx8, int H, const int* __restrict__ rep_count,
+                                                                    const int* __restrict__ rep_list, double* __restrict__ Eout) {
+  extern __shared__ double sv_smem[];
+  const int total = *rep_count;
+  for (int k = blockIdx.x * SV_TPB + threadIdx.x; k < total; k += gridDim.x * SV_TPB) {
+    const size_t ho = (size_t)rep_list[k];
+    const int pair = (int)(ho / (size_t)H);
+    const int n = npts ? npts[pair] : n_single;
+    eight_point_solve<SV_TPB>(xi + (size_t)pair * pt_stride, xj + (size_t)pair * pt_stride, idx8 + ho * 8, n, sv_smem + threadIdx.x,
+                              Eout + ho * 9);
+  }
+}
+
+// The winner of every correspondence set (best[2 * pair] = hypothesis index or -1) solved again by the Jacobi emulation,
+// in place of the screening hypothesis: one thread per set.
+__global__ void __launch_bounds__(SV_TPB, SV_MINB) eight_point_winner_kernel(const double2* __restrict__ xi, const double2* __restrict__ xj,
+                                                                      size_t pt_stride, const int* __restrict__ npts, int n_single,
+                                                                      const int* __restrict__ idx8, int H, const int* __restrict__ best,
+                                                                      int npairs, double* __restrict__ E) {
+  extern __shared__ double sv_smem[];
+  const int pair = blockIdx.x * SV_TPB + threadIdx.x;
+  if (pair >= npairs) return;
+  const int n = npts ? npts[pair] : n_single, bh = best[2 * pair];
+  if (bh < 0 || bh >= H || n < 8) return;
+  const size_t ho = (size_t)pair * H + bh;
+  eight_point_solve<SV_TPB>(xi + (size_t)pair * pt_stride, xj + (size_t)pair * pt_stride, idx8 + ho * 8, n, sv_smem + threadIdx.x,
+                            E + ho * 9);
 }
 
 // Batched triangulate_dlt (:1477-1516), one thread per track.  Same formulas and order as the host
@@ -484,14 +612,42 @@ int sfm_pose_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size
 }
 
 // Hypotheses for `npairs` correspondence sets in one launch: xi/xj + pair * pt_stride, npts[pair] points (npts may be null:
-// n_single for all), idx8 [npairs][H][8], Eout [npairs][H][9].
+// n_single for all), idx8 [npairs][H][8], Eout [npairs][H][9].  screen != 0: the direct null-vector solver (counting only,
+// see eight_point_qr_kernel; the caller re-solves the winners with sfm_eight_point_winners).
 int sfm_eight_point_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, const int* npts, int n_single,
-                            int npairs, const int* idx8, int H, double* Eout) {
+                            int npairs, const int* idx8, int H, double* Eout, int screen) {
   if (npairs <= 0 || H <= 0) return 0;
+  if (screen) {
+    if ((long long)npairs * H > 0x7fffffffll) return sfm_fail(ctx, SFMGPU_E_ARG, "eight_point: %d x %d hypotheses in one launch", npairs, H);
+    SFM_TRY(sfm_reserve(ctx, ctx->sv_list, ((size_t)npairs * H + 64) * sizeof(int)));
+    int* rep_count = (int*)ctx->sv_list.p;
+    int* rep_list = rep_count + 64;
+    SFM_CUDA(ctx, cudaMemsetAsync(rep_count, 0, sizeof(int), ctx->stream));
+    SFM_LAUNCH(ctx, eight_point_qr_kernel, dim3(sfm_cdiv(H, QR_TPB), npairs), QR_TPB, 0, xi, xj, pt_stride, npts, n_single, idx8, H, Eout,
+               rep_count, rep_list);
+    static const int list_cfg = sfm_next_cfg_id();
+    const size_t lsmem = (size_t)SV_TRI * SV_TPB * sizeof(double);
+    SFM_SMEM_OPTIN(ctx, list_cfg, eight_point_list_kernel, lsmem);
+    const long long want = ((long long)npairs * H + SV_TPB - 1) / SV_TPB, cap = (long long)ctx->n_sm * SV_MINB;
+    SFM_LAUNCH(ctx, eight_point_list_kernel, (unsigned)(want < cap ? want : cap), SV_TPB, lsmem, xi, xj, pt_stride, npts, n_single, idx8, H,
+               (const int*)rep_count, (const int*)rep_list, Eout);
+    return 0;
+  }
   static const int cfg_id = sfm_next_cfg_id();
   const size_t smem = (size_t)SV_TRI * SV_TPB * sizeof(double);
   SFM_SMEM_OPTIN(ctx, cfg_id, eight_point_kernel, smem);
   SFM_LAUNCH(ctx, eight_point_kernel, dim3(sfm_cdiv(H, SV_TPB), npairs), SV_TPB, smem, xi, xj, pt_stride, npts, n_single, idx8, H, Eout);
+  return 0;
+}
+
+// E[pair][best[2 * pair]] := the Jacobi emulation's hypothesis for that octet (no-op for sets without a winner).
+int sfm_eight_point_winners(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, const int* npts, int n_single,
+                            int npairs, const int* idx8, int H, const int* best, double* E) {
+  if (npairs <= 0 || H <= 0) return 0;
+  static const int cfg_id = sfm_next_cfg_id();
+  const size_t smem = (size_t)SV_TRI * SV_TPB * sizeof(double);
+  SFM_SMEM_OPTIN(ctx, cfg_id, eight_point_winner_kernel, smem);
+  SFM_LAUNCH(ctx, eight_point_winner_kernel, sfm_cdiv(npairs, SV_TPB), SV_TPB, smem, xi, xj, pt_stride, npts, n_single, idx8, H, best, npairs, E);
   return 0;
 }
 
@@ -531,24 +687,70 @@ extern "C" int sfmgpu_triangulate_dlt(sfmgpu_ctx* ctx, const double* K, const do
   return 0;
 }
 
+static int hypotheses_resident(sfmgpu_ctx* ctx, const double* xi_xy, const double* xj_xy, int n, const int32_t* idx8, int H, int screen) {
+  SFM_TRY(sfmgpu_ransac_upload(ctx, xi_xy, xj_xy, n, nullptr, 0));  // points resident, room for 0 hypotheses
+  SFM_TRY(sfm_reserve(ctx, ctx->rs_E, (size_t)(H + 1) * 72));
+  SFM_TRY(sfm_reserve(ctx, ctx->rs_counts, (size_t)(H + 1) * 4));
+  SFM_TRY(sfm_reserve(ctx, ctx->rs_idx8, (size_t)(H + 1) * 32));
+  ctx->rs_H = H;
+  ctx->rs_screened = false;
+  if (H == 0) return 0;
+  SFM_CUDA(ctx, cudaMemcpyAsync(ctx->rs_idx8.p, idx8, (size_t)H * 32, cudaMemcpyHostToDevice, ctx->stream));
+  SFM_TRY(sfm_eight_point_batched(ctx, (const double2*)ctx->rs_xi.p, (const double2*)ctx->rs_xj.p, 0, nullptr, n, 1,
+                                  (const int*)ctx->rs_idx8.p, H, (double*)ctx->rs_E.p, screen));
+  ctx->rs_screened = screen != 0;
+  return 0;
+}
+
 extern "C" int sfmgpu_ransac_hypotheses(sfmgpu_ctx* ctx, const double* xi_xy, const double* xj_xy, int n, const int32_t* idx8, int H,
                                         double* E_out) {
   SFM_ENTER(ctx);
   if (!ctx || n < 0 || H < 0) return sfm_fail(ctx, SFMGPU_E_ARG, "ransac_hypotheses: bad sizes");
   if (n < 1 && H > 0) return sfm_fail(ctx, SFMGPU_E_ARG, "ransac_hypotheses: no correspondences");
   if ((n > 0 && (!xi_xy || !xj_xy)) || (H > 0 && !idx8)) return sfm_fail(ctx, SFMGPU_E_ARG, "ransac_hypotheses: null pointer");
-  SFM_TRY(sfmgpu_ransac_upload(ctx, xi_xy, xj_xy, n, nullptr, 0));  // points resident, room for 0 hypotheses
-  SFM_TRY(sfm_reserve(ctx, ctx->rs_E, (size_t)(H + 1) * 72));
-  SFM_TRY(sfm_reserve(ctx, ctx->rs_counts, (size_t)(H + 1) * 4));
-  SFM_TRY(sfm_reserve(ctx, ctx->rs_idx8, (size_t)(H + 1) * 32));
-  ctx->rs_H = H;
-  if (H == 0) return 0;
-  SFM_CUDA(ctx, cudaMemcpyAsync(ctx->rs_idx8.p, idx8, (size_t)H * 32, cudaMemcpyHostToDevice, ctx->stream));
-  SFM_TRY(sfm_eight_point_batched(ctx, (const double2*)ctx->rs_xi.p, (const double2*)ctx->rs_xj.p, 0, nullptr, n, 1,
-                                  (const int*)ctx->rs_idx8.p, H, (double*)ctx->rs_E.p));
-  if (E_out) {
+  // the caller wants the hypotheses themselves: the Jacobi emulation for every octet; resident only (E_out == NULL: they
+  // are there to be scored): the context's solver mode, the winner is re-solved when scored
+  SFM_TRY(hypotheses_resident(ctx, xi_xy, xj_xy, n, idx8, H, (!E_out && ctx->solver_mode == 1) ? 1 : 0));
+  if (E_out && H > 0) {
     SFM_CUDA(ctx, cudaMemcpyAsync(E_out, ctx->rs_E.p, (size_t)H * 72, cudaMemcpyDeviceToHost, ctx->stream));
     SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
+  return 0;
+}
+
+extern "C" int sfmgpu_ransac_solve_score(sfmgpu_ctx* ctx, const double* xi_xy, const double* xj_xy, int n, const int32_t* idx8, int H,
+                                         double thr, int* best_h, int* best_n, double* best_E, int32_t* best_inl) {
+  SFM_ENTER(ctx);
+  if (!ctx || n < 0 || H < 0) return sfm_fail(ctx, SFMGPU_E_ARG, "ransac_solve_score: bad sizes");
+  if (n < 1 && H > 0) return sfm_fail(ctx, SFMGPU_E_ARG, "ransac_solve_score: no correspondences");
+  if ((n > 0 && (!xi_xy || !xj_xy)) || (H > 0 && !idx8)) return sfm_fail(ctx, SFMGPU_E_ARG, "ransac_solve_score: null pointer");
+  SFM_TRY(hypotheses_resident(ctx, xi_xy, xj_xy, n, idx8, H, ctx->solver_mode == 1 ? 1 : 0));
+  int bh = -1, bn = 0;
+  SFM_TRY(sfmgpu_ransac_score_resident(ctx, thr, &bh, &bn));
+  if (ctx->rs_screened) {  // the count of the re-solved winner
+    int hb[2];
+    SFM_CUDA(ctx, cudaMemcpyAsync(hb, ctx->rs_best.p, sizeof hb, cudaMemcpyDeviceToHost, ctx->stream));
+    SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    bh = hb[0];
+    bn = hb[1];
+  }
+  if (best_h) *best_h = bh;
+  if (best_n) *best_n = bn;
+  if (best_E) {
+    if (bh >= 0) {
+      SFM_CUDA(ctx, cudaMemcpyAsync(best_E, (const double*)ctx->rs_E.p + 9 * (size_t)bh, 72, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+      for (int i = 0; i < 9; i++) best_E[i] = 0.0;
+    }
+  }
+  if (best_inl && bh >= 0 && bn > 0)
+    SFM_CUDA(ctx, cudaMemcpyAsync(best_inl, ctx->rs_inl.p, (size_t)bn * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int sfmgpu_solver_set_mode(sfmgpu_ctx* ctx, int mode) {
+  if (!ctx || (mode != 0 && mode != 1)) return sfm_fail(ctx, SFMGPU_E_ARG, "solver_set_mode: mode must be 0 or 1");
+  ctx->solver_mode = mode;
   return 0;
 }

@@ -212,6 +212,7 @@ int sfm_two_view_stage(sfmgpu_ctx* ctx, sfmgpu_pairs* p, int pair_off, int npair
     SFM_TRY(raw_stream(ctx, tv->raw, tv->raw_n, (long long)H * 8, (double)cap / 4294967296.0));
   }
   const int mp = rc.min_points > 0 ? rc.min_points : 0;
+  const int screen = (!E_host && H > 0 && ctx->solver_mode == 1) ? 1 : 0;  // see solver.cu: eight_point_qr_kernel
   const double* k = tv->Kinv;
   for (int c0 = 0; c0 < npairs; c0 += chunk) {
     const int pc = npairs - c0 < chunk ? npairs - c0 : chunk, po = pair_off + c0;
@@ -226,11 +227,11 @@ int sfm_two_view_stage(sfmgpu_ctx* ctx, sfmgpu_pairs* p, int pair_off, int npair
         SFM_LAUNCH(ctx, tv_sample_kernel, pc, 1024, 0, (const unsigned*)tv->raw.p, tv->raw_n, (const int*)(tv->neff + po), 0, H * 8,
                    (int*)tv->idx8.p, tv->flags);
         SFM_TRY(sfm_eight_point_batched(ctx, tv->xi + so, tv->xj + so, (size_t)cap, tv->neff + po, 0, pc, (const int*)tv->idx8.p, H,
-                                        (double*)tv->E.p));
+                                        (double*)tv->E.p, screen));
       }
     }
-    SFM_TRY(sfm_ransac_score_batched(ctx, tv->xi + so, tv->xj + so, (size_t)cap, tv->neff + po, cap, pc, (const double*)tv->E.p, H, rc.thr,
-                                     (int*)tv->counts.p, tv->best + 2 * po, tv->inl + so));
+    SFM_TRY(sfm_ransac_score_batched(ctx, tv->xi + so, tv->xj + so, (size_t)cap, tv->neff + po, cap, pc, (double*)tv->E.p, H, rc.thr,
+                                     (int*)tv->counts.p, tv->best + 2 * po, tv->inl + so, screen ? (const int*)tv->idx8.p : nullptr));
     SFM_LAUNCH(ctx, tv_finalize_kernel, sfm_cdiv(pc, 128), 128, 0, (const int*)(p->nkept + po), (const int*)(tv->neff + po),
                (const int*)(tv->best + 2 * po), (const double*)tv->E.p, Hs, pc, mp, rc.min_inliers, tv->status + po, tv->bestE + 9 * (size_t)po);
     SFM_TRY(sfm_pose_batched(ctx, tv->xi + so, tv->xj + so, (size_t)cap, pc, tv->status + po, tv->best + 2 * po, tv->inl + so,

@@ -161,12 +161,15 @@ static std::optional<RelPose> find_E_ransac(const Mat33& K, const std::vector<Ve
     check(ctx, sfmgpu_ransac_score(ctx, la.xi_ptr(), la.xj_ptr(), n, E.data(), H, thr, nullptr, &best_h, inl.data(), &best_n),
           "ransac_score");
   } else {
-    // opt-in (SFMGPU_DEVICE_SOLVER=1 or set_device_solver(true)): the same octets, hypotheses solved on the device
-    // (equal to the host solver's to ~1e-9, not bit for bit), scored as above
+    // opt-in (SFMGPU_DEVICE_SOLVER=1 or set_device_solver(true)): the same octets, hypotheses solved on the device.  The
+    // counts come from the screening solver, the winner is solved again by the Jacobi emulation (equal to the host
+    // solver's hypothesis to ~1e-9, not bit for bit): its E, count and inlier list come back
     static_assert(sizeof(int) == sizeof(std::int32_t), "int32 octets");
-    check(ctx, sfmgpu_ransac_hypotheses(ctx, la.xi_ptr(), la.xj_ptr(), n, idx.data(), H, E.data()), "ransac_hypotheses");
-    check(ctx, sfmgpu_ransac_score_resident(ctx, thr, &best_h, &best_n), "ransac_score_resident");
-    check(ctx, sfmgpu_ransac_download(ctx, nullptr, inl.data(), n), "ransac_download");
+    double bestE[9];
+    check(ctx, sfmgpu_ransac_solve_score(ctx, la.xi_ptr(), la.xj_ptr(), n, idx.data(), H, thr, &best_h, &best_n, bestE, inl.data()),
+          "ransac_solve_score");
+    if (best_h >= 0)
+      for (int i = 0; i < 9; i++) E[9 * (size_t)best_h + i] = bestE[i];
   }
   if (best_n < min_inliers) return std::nullopt;
   RelPose rp;

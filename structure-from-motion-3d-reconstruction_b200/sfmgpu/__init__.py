@@ -34,7 +34,7 @@ SYMBOLS = [
     "sfmgpu_multitracker_prefetch", "sfmgpu_multitracker_step_pipelined",
     "sfmgpu_multitracker_totals",
     "sfmgpu_ransac_score", "sfmgpu_ransac_upload", "sfmgpu_ransac_score_resident", "sfmgpu_ransac_download",
-    "sfmgpu_ransac_hypotheses", "sfmgpu_global_desc32", "sfmgpu_desc_search", "sfmgpu_triangulate_dlt",
+    "sfmgpu_ransac_hypotheses", "sfmgpu_ransac_solve_score", "sfmgpu_solver_set_mode", "sfmgpu_global_desc32", "sfmgpu_desc_search", "sfmgpu_triangulate_dlt",
     "sfmgpu_stage_times_n", "sfmgpu_pairs_set_ransac", "sfmgpu_pairs_ransac_host_outputs", "sfmgpu_pairs_ransac",
     "sfmgpu_pairs_ransac_download", "sfmgpu_pairs_ransac_download_all", "sfmgpu_pairs_ransac_device_ptrs", "sfmgpu_ransac_sample",
     "sfmgpu_pairs_set_matches",
@@ -141,6 +141,8 @@ def load_library():
         "sfmgpu_global_desc32": (_i, [_vp, _vp, _i, _i, _vp]),
         "sfmgpu_desc_search": (_i, [_vp, _vp, _i, _vp, _vp, C.POINTER(_i), C.POINTER(C.c_float)]),
         "sfmgpu_ransac_hypotheses": (_i, [_vp, _f64p, _f64p, _i, _i32p, _i, _vp]),
+        "sfmgpu_ransac_solve_score": (_i, [_vp, _f64p, _f64p, _i, _i32p, _i, _d, C.POINTER(_i), C.POINTER(_i), _vp, _vp]),
+        "sfmgpu_solver_set_mode": (_i, [_vp, _i]),
         "sfmgpu_stage_times_n": (_i, [_vp, C.POINTER(C.c_float), _i]),
         "sfmgpu_pairs_set_ransac": (_i, [_vp, _vp, _vp, C.POINTER(RansacCfg)]),
         "sfmgpu_pairs_ransac_host_outputs": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -214,6 +216,11 @@ class Context:
     def select_set_mode(self, mode):
         """0 radix sort + exact fallback on consumed score ties (default), 1 introsort emulation for every frame."""
         self._ck(self.lib.sfmgpu_select_set_mode(self.h, mode))
+
+    def solver_set_mode(self, mode):
+        """Device 8-point solver: 1 (default) screening solver for the counts + Jacobi emulation for the winner, 0 the
+        Jacobi emulation for every hypothesis."""
+        self._ck(self.lib.sfmgpu_solver_set_mode(self.h, mode))
 
     def timer_start(self):
         self._ck(self.lib.sfmgpu_timer_start(self.h))
@@ -299,6 +306,20 @@ class Context:
         E = np.zeros((max(H, 1), 9)) if fetch else None
         self._ck(self.lib.sfmgpu_ransac_hypotheses(self.h, xi, xj, len(xi), idx8 if H else np.zeros((1, 8), np.int32), H, _ptr(E)))
         return E[:H] if fetch else None
+
+    def ransac_solve_score(self, xi, xj, idx8, thr):
+        """Solver + scoring loop of find_E_ransac for the octets idx8: (winner, count, winner's E, ascending inlier list);
+        hypotheses and counts stay resident (ransac_download)."""
+        xi = np.ascontiguousarray(xi, np.float64).reshape(-1, 2)
+        xj = np.ascontiguousarray(xj, np.float64).reshape(-1, 2)
+        idx8 = np.ascontiguousarray(idx8, np.int32).reshape(-1, 8)
+        H, n = len(idx8), len(xi)
+        bh, bn = _i(-1), _i(0)
+        E = np.zeros(9)
+        inl = np.full(max(n, 1), -1, np.int32)
+        self._ck(self.lib.sfmgpu_ransac_solve_score(self.h, xi, xj, n, idx8 if H else np.zeros((1, 8), np.int32), H, thr, C.byref(bh),
+                                                    C.byref(bn), _ptr(E), _ptr(inl)))
+        return bh.value, bn.value, E, inl[:bn.value].copy()
 
     def ransac_download(self, H, n):
         counts = np.zeros(max(H, 1), np.int32)

@@ -87,15 +87,22 @@ def test_pairs_ransac_with_reference_hypotheses(ctx, checker, iters, thr, min_in
     assert seen >= ({0, 2} if min_pts == 120 else {1, 2})  # skipped, no pose and pose all occur across the configurations
 
 
-@pytest.mark.parametrize("iters,thr,min_inl,min_pts", [(400, 1e-3, 60, 120), (1000, 2e-3, 80, 120)])
-def test_pairs_ransac_device_solver(ctx, checker, iters, thr, min_inl, min_pts):
+@pytest.mark.parametrize("solver_mode", [1, 0])
+@pytest.mark.parametrize("iters,thr,min_inl,min_pts", [(400, 1e-3, 60, 120), (1000, 2e-3, 80, 120), (4000, 2e-3, 80, 120)])
+def test_pairs_ransac_device_solver(ctx, checker, iters, thr, min_inl, min_pts, solver_mode):
     """Everything on the device (sampler, 8-point solver, scoring, pose): same status, winner count and inlier list as
-    find_E_ransac on these scenes; R, t within 1e-6 (the device solver's hypotheses agree to ~1e-9, not bit for bit)."""
+    find_E_ransac on these scenes; R, t within 1e-6 (the device solver's hypotheses agree to ~1e-9, not bit for bit).
+    solver_mode 1 (default): counts from the screening solver, winner re-solved by the Jacobi emulation; 0: the
+    emulation for every hypothesis."""
     K = TEMPLE_K
     scenes = _scenes()
+    ctx.solver_set_mode(solver_mode)
     pairs = ctx.pairs(len(scenes), 2500)
     pairs.set_matches([s[0] for s in scenes], [s[1] for s in scenes])
-    pairs.ransac(K, iters, thr, min_inl, min_pts)
+    try:
+        pairs.ransac(K, iters, thr, min_inl, min_pts)
+    finally:
+        ctx.solver_set_mode(1)
     want = _reference_results(checker, K, scenes, iters, thr, min_inl, min_pts)
     st_all, bn_all = np.zeros(len(scenes), np.int32), np.zeros(len(scenes), np.int32)
     inl_all = np.zeros((len(scenes), 2500), np.int32)
@@ -135,6 +142,55 @@ def test_device_solver_hypotheses_close_to_reference(ctx, checker):
     wc, wbh, winl = checker.ransac_score(xi, xj, Eref, 1e-3)
     assert bh == wbh and np.array_equal(inl[:bn], winl)
     assert (counts != wc).mean() < 0.02
+
+
+@pytest.mark.parametrize("n,seed,frac,sigma,thr", [(2200, 11, 0.3, 0.3, 1e-3), (1000, 5, 0.5, 1.0, 2e-3), (3000, 9, 0.1, 0.1, 1e-4),
+                                                  (640, 6, 0.1, 0.3, 1e-5), (2500, 4, 0.5, 0.3, 2e-3)])
+def test_screening_solver_counts(ctx, checker, n, seed, frac, sigma, thr):
+    """Solver mode 1: the counts of the screening solver (unit null vector of the design matrix by Householder QR) against
+    the reference solver's counts for the same octets.  Octets of eight distinct points: equal counts except where a
+    point's error sits within the reference iteration's own error of the threshold (< 0.5 % of the hypotheses, by
+    at most a few points); octets with a repeated index have a two-dimensional null space and are left to the Jacobi
+    emulation in both modes (which member comes back is a property of the iteration: the emulation reproduces it for
+    ~80 % of them).  Winner, its count and inlier list as find_E_ransac's."""
+    pi, pj = two_view_scene(n, seed=seed, outlier_frac=frac, sigma=sigma)
+    xi, xj = checker.norm_points(TEMPLE_K, pi), checker.norm_points(TEMPLE_K, pj)
+    H = 3000
+    Eref, idx = checker.ransac_hypotheses(xi, xj, H)
+    wc, wbh, winl = checker.ransac_score(xi, xj, Eref, thr)
+    distinct = np.array([len(set(r)) == 8 for r in idx])
+    res, rep_counts = {}, {}
+    for mode in (1, 0):
+        ctx.solver_set_mode(mode)
+        try:
+            bh, bn, E, inl = ctx.ransac_solve_score(xi, xj, idx, thr)
+        finally:
+            ctx.solver_set_mode(1)
+        counts, _ = ctx.ransac_download(H, n)
+        diff = counts != wc
+        res[mode] = (diff[distinct].mean(), np.abs(counts - wc)[distinct].max(), diff[~distinct].mean())
+        rep_counts[mode] = counts[~distinct].copy()
+        assert bh == wbh and bn == len(winl) and np.array_equal(inl, winl), mode
+        d = min(np.abs(E - Eref[wbh]).max(), np.abs(E + Eref[wbh]).max())
+        assert d < 1e-7, (mode, d)  # the winner's hypothesis is the emulation's in both modes
+        assert diff[distinct].mean() < 0.005 and np.abs(counts - wc)[distinct].max() <= 4, (mode, res[mode])
+    assert np.array_equal(rep_counts[0], rep_counts[1])
+    print(f"counts != reference (distinct octets / max |diff| / repeated-index octets): screening {res[1]}, emulation {res[0]}")
+
+
+def test_solve_score_edge_cases(ctx, checker):
+    """No hypothesis (H = 0), eight points, a threshold nothing passes: winner -1, zero matrix, empty list (as :667-677)."""
+    pi, pj = two_view_scene(8, seed=5, outlier_frac=0.0)
+    xi, xj = checker.norm_points(TEMPLE_K, pi), checker.norm_points(TEMPLE_K, pj)
+    bh, bn, E, inl = ctx.ransac_solve_score(xi, xj, np.zeros((0, 8), np.int32), 1e-3)
+    assert bh == -1 and bn == 0 and not E.any() and len(inl) == 0
+    _, idx = checker.ransac_hypotheses(xi, xj, 50)
+    bh, bn, E, inl = ctx.ransac_solve_score(xi, xj, idx, -1.0)
+    assert bh == -1 and bn == 0 and not E.any() and len(inl) == 0
+    bh, bn, E, inl = ctx.ransac_solve_score(xi, xj, idx, 1e-3)
+    Eref, _ = checker.ransac_hypotheses(xi, xj, 50)
+    wc, wbh, winl = checker.ransac_score(xi, xj, Eref, 1e-3)
+    assert bh == wbh and np.array_equal(inl, winl)
 
 
 @pytest.mark.parametrize("streaming", [False, True])
