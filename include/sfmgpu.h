@@ -119,8 +119,11 @@ int sfmgpu_corners(sfmgpu_ctx* ctx, sfmgpu_frames* f, int frame, int max_corners
  * perm[i] = original index of the element that std::sort leaves at position i. */
 int sfmgpu_sort_perm_desc(sfmgpu_ctx* ctx, const double* keys, int n, int32_t* perm);
 /* How every later corner selection of this context orders its candidates (results are bit-identical either way):
- * 0 = radix sort by score, and the exact introsort emulation only for frames where two candidates with identical
- * scores fall inside the consumed prefix (default); 1 = introsort emulation for every frame (tests, A/B timing). */
+ * 0 = bucket selection (candidates grouped by score bucket, blocked ones dropped unsorted, the survivors sorted and
+ * selected bucket group by bucket group), and the exact introsort emulation only for frames where two candidates with
+ * identical scores are both still selectable (default); 1 = introsort emulation for every frame; 2 = full radix sort by
+ * score + selection over the sorted list; 12..34 = bucket selection with that many order-code bits (tests: short codes
+ * exercise the equal-code path). */
 int sfmgpu_select_set_mode(sfmgpu_ctx* ctx, int mode);
 
 /* ---- KLT: track_one / lk_step / sample_bilinear (:183-198, :396-460) ------------------------------- */

@@ -59,7 +59,7 @@ struct sfmgpu_ctx {
   DevBuf flush;
   DevBuf klt_in, klt_p1, klt_pb, klt_nit, klt_keep, klt_defer;
   int klt_mode = 0;  // 0 auto, 1 warp-per-feature, 2 lane-per-feature (tests / profiling)
-  int select_mode = 0;  // 0 radix sort + tie fallback, 1 introsort emulation only (tests / profiling)
+  int select_mode = 0;  // 0 bucket selection + tie fallback, 1 introsort emulation only, 2 full radix sort + selection, 12..34 bucket selection with that many code bits (tests / profiling)
   DevBuf cs_work;    // corner-score work area for single-frame calls
   DevBuf sel_work;   // corner-select work area
   DevBuf misc;       // small scalars
@@ -209,8 +209,8 @@ int sfm_corners_batch(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first, int co
                       int min_dist, int cand_cap, void* work, size_t work_bytes, double2* out_xy, int* out_n);
 int sfm_corners_score_stage(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first, int count, double quality, int min_dist, int cand_cap,
                             void* work, size_t work_bytes);
-int sfm_corners_select_stage(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int count, int max_corners, double quality, int min_dist, int cand_cap, void* work,
-                             size_t work_bytes, double2* out_xy, int* out_n);
+int sfm_corners_select_stage(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first, int count, int max_corners, double quality, int min_dist,
+                             int cand_cap, void* work, size_t work_bytes, double2* out_xy, int* out_n);
 int sfm_candidates_single(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int frame, double quality, int32_t* xy,
                           double* score, int cap, int* n_out, double* max_score);
 int sfm_sort_perm(sfmgpu_ctx* ctx, const double* keys, int n, int32_t* perm);

@@ -882,6 +882,472 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(CornerWorkView wv, int
   }
 }
 
+// ---- bucket selection (default path) ------------------------------------------------------------------------------------------
+// The greedy loop only ever accepts candidates that no accepted corner blocks, and a candidate that is blocked once stays
+// blocked.  With ~50 candidates per accepted corner almost every candidate is blocked by the time its turn comes, so the
+// list is NOT sorted as a whole: one block per frame
+//   (1) sweeps the unordered list once: entries that reach the final threshold become words (order code << 30 | y << 15 | x,
+//       order code = up to 34 leading bits of the score's distance below the frame maximum: ascending word = descending
+//       score) and are counted per MSD bucket (top 11 bits of the code);
+//   (2) scatters the words into bucket order (one pass, unordered inside a bucket);
+//   (3) walks the buckets from the best score down in gathers of <= 4096 words: a word whose pixel is already blocked is
+//       dropped at once (order-independent, exact); the SURVIVORS of the gather - all of them early on, a few per cent
+//       later - are sorted in shared memory (bitonic, 64-bit words) and go through the greedy rounds (conflict bit rows,
+//       as nms_kernel); accepted corners mark their discs; the walk stops when max_corners are accepted.
+// Buckets the selection never reaches are never sorted, blocked candidates are never sorted, and nothing is gathered
+// through a slot index: the word carries the pixel.
+// Equal order codes among the survivors of a gather (rare with 34 bits): the members' exact scores are recomputed from
+// the image (same expression as the score kernels) and the run is ordered by them; IDENTICAL scores are flagged and
+// handled by the observable-tie rule: if two members of a tie are still unblocked when the rounds reach
+// them, or a run is longer than 64, or a single bucket's survivors do not fit, the frame gets status 3 and is redone by
+// the exact emulation (select_kernel mode 3).
+constexpr int BK_THREADS = 256, BK_WARPS = BK_THREADS / 32;
+constexpr int BK_NB_BITS = 11, BK_NB = 1 << BK_NB_BITS;
+constexpr int BK_CODE_BITS = 34;
+constexpr int BK_T = 4096;                      // survivors held per gather
+constexpr int BK_EPT = 8, BK_PIECE = BK_THREADS * BK_EPT;
+constexpr int BK_ALIVE = BK_THREADS;            // survivors resolved per greedy round, one per thread
+constexpr int BK_MAXRUN = 64;
+constexpr unsigned BK_YX = 0x3FFFFFFFu;
+
+struct BucketSmem {
+  __align__(16) unsigned long long sv[BK_T];
+  unsigned cur[BK_NB];
+  __align__(16) unsigned pxy[BK_ALIVE];
+  unsigned accm[BK_ALIVE / 32], deadm[BK_ALIVE / 32];
+  unsigned short accl[BK_ALIVE];
+  unsigned char tf[BK_T];  // bit 0: identical score as the predecessor, bit 1: member of a group of >= 3
+  int wcnt[BK_WARPS];
+  unsigned nkeep;
+  int accepted, cut, tiehit, eqrun;
+};
+
+__device__ __forceinline__ int bk_block_scan(BucketSmem& sm, int c, int& total) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int inc = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) sm.wcnt[warp] = inc;
+  __syncthreads();
+  int pre = 0, tot = 0;
+#pragma unroll
+  for (int k = 0; k < BK_WARPS; k++) {
+    const int v = sm.wcnt[k];
+    if (k < warp) pre += v;
+    tot += v;
+  }
+  __syncthreads();  // wcnt is reused by the next scan
+  total = tot;
+  return inc - c + pre;
+}
+
+// shi_tomasi's score of one pixel (:252-270) from the image: integer window sums, then the single FP64 expression the score
+// kernels evaluate (corner_score.cu: exact_u) - bit-identical to the list's value.
+__device__ double bk_exact_score(const uint8_t* __restrict__ im, int pitch, int w, int h, int x, int y) {
+  if (x < 2 || y < 2 || x >= w - 2 || y >= h - 2) return 0.0;
+  int a = 0, b = 0, c = 0;
+  for (int yy = y - 2; yy <= y + 2; yy++) {
+    const uint8_t* r0 = im + (size_t)yy * pitch;
+    const uint8_t* rm = im + (size_t)max(yy - 1, 0) * pitch;
+    const uint8_t* rp = im + (size_t)min(yy + 1, h - 1) * pitch;
+    for (int xx = x - 2; xx <= x + 2; xx++) {
+      const int gx = (int)r0[min(xx + 1, w - 1)] - (int)r0[max(xx - 1, 0)];
+      const int gy = (int)rp[xx] - (int)rm[xx];
+      a += gx * gx;
+      b += gy * gy;
+      c += gx * gy;
+    }
+  }
+  const double dd = (double)(a - b), c2 = (double)(2 * c);
+  const double D = dd * dd + c2 * c2;
+  return 0.125 * ((double)(a + b) - sqrt(D));
+}
+
+__global__ void __launch_bounds__(BK_THREADS, 4) bucket_select_kernel(CornerWorkView wv, const uint8_t* __restrict__ img, int pitch,
+                                                                      size_t fstride, int first, int w, int h, int max_corners,
+                                                                      int min_dist, double quality, int code_bits,
+                                                                      double2* __restrict__ out_xy, int* __restrict__ out_n) {
+  extern __shared__ __align__(16) unsigned char bk_raw[];
+  BucketSmem& sm = *reinterpret_cast<BucketSmem*>(bk_raw);
+  const int fr = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t cb = (size_t)fr * wv.cand_cap;
+  unsigned long long* A = wv.pk_a + cb;
+  unsigned long long* B = wv.pk_b + cb;
+  const bool exact = wv.exact_list[fr] != 0;
+  const unsigned nlist = exact ? wv.nfinal[fr] : wv.ncand[fr];
+  if (nlist > (unsigned)wv.cand_cap) {  // capacity exceeded: report, never truncate silently
+    if (tid == 0) {
+      wv.status[fr] = 1;
+      if (out_n) out_n[fr] = -1;
+    }
+    return;
+  }
+  for (int i = tid; i < BK_NB; i += BK_THREADS) sm.cur[i] = 0;
+  if (tid == 0) {
+    sm.nkeep = 0;
+    sm.accepted = 0;
+    sm.tiehit = 0;
+  }
+  __syncthreads();
+
+  // (1) list -> words + bucket counts.  The frame maximum is final: entries of a provisional list below the final threshold
+  // are dropped here (s >= thr, :282).
+  const double maxv = 0.125 * __longlong_as_double(wv.maxbits[fr]);
+  const double thr = maxv * quality;
+  const unsigned long long maxkey = (unsigned long long)__double_as_longlong(maxv);
+  const unsigned long long thrkey = thr > 0.0 ? (unsigned long long)__double_as_longlong(thr) : 0ull;
+  const unsigned long long range = maxkey > thrkey ? maxkey - thrkey : 0ull;
+  const int bits = 64 - __clzll((long long)range);
+  const int shift = bits > code_bits ? bits - code_bits : 0;
+  const int used_bits = bits < code_bits ? bits : code_bits;
+  const int bshift = used_bits > BK_NB_BITS ? used_bits - BK_NB_BITS : 0;
+  {
+    const unsigned long long* lkey = wv.tmp_key + cb;
+    const unsigned* lidx = wv.tmp_idx + cb;
+    for (unsigned i0 = 0; i0 < nlist; i0 += BK_THREADS * 4) {  // block-uniform trip count
+      unsigned long long k[4];
+      unsigned yx[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const unsigned e = i0 + q * BK_THREADS + tid;
+        k[q] = e < nlist ? __ldcg(lkey + e) : 0ull;
+        yx[q] = e < nlist ? __ldcg(lidx + e) : 0u;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const unsigned e = i0 + q * BK_THREADS + tid;
+        const bool keep = e < nlist && __longlong_as_double((long long)k[q]) >= thr;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (m) {
+          unsigned base = 0;
+          if (lane == 0) base = atomicAdd(&sm.nkeep, (unsigned)__popc(m));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (keep) {
+            const unsigned long long code = (maxkey - k[q]) >> shift;
+            A[base + __popc(m & ((1u << lane) - 1u))] = (code << 30) | (unsigned long long)(((yx[q] >> 16) << 15) | (yx[q] & 0x7FFFu));
+            atomicAdd(&sm.cur[(unsigned)(code >> bshift)], 1u);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const unsigned n = sm.nkeep;
+  if (tid == 0) wv.nfinal[fr] = n;
+  const int cap_out = max_corners < 1 ? 1 : max_corners;  // the cap is tested after the push (:298-299)
+  if (n == 0) {
+    if (tid == 0) {
+      wv.status[fr] = 0;
+      if (out_n) out_n[fr] = 0;
+    }
+    return;
+  }
+  // bucket starts
+  {
+    constexpr int PER = BK_NB / BK_THREADS;
+    unsigned c[PER];
+    int s = 0;
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+      c[j] = sm.cur[tid * PER + j];
+      s += (int)c[j];
+    }
+    int tot;
+    unsigned run = (unsigned)bk_block_scan(sm, s, tot);
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+      sm.cur[tid * PER + j] = run;
+      run += c[j];
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+  // (2) scatter into bucket order; cur[b] ends up as the END of bucket b
+  for (unsigned i0 = 0; i0 < n; i0 += BK_THREADS * 4) {
+    unsigned long long v[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const unsigned i = i0 + q * BK_THREADS + tid;
+      v[q] = i < n ? __ldcg(A + i) : ~0ull;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const bool in = i0 + q * BK_THREADS + tid < n;
+      const unsigned b = in ? (unsigned)((v[q] >> 30) >> bshift) : 0xFFFFFFFFu;
+      const unsigned pm = __match_any_sync(0xffffffffu, b);
+      const int leader = __ffs(pm) - 1;
+      unsigned old = 0;
+      if (in && lane == leader) old = atomicAdd(&sm.cur[b], (unsigned)__popc(pm));
+      old = __shfl_sync(0xffffffffu, old, leader);
+      if (in) B[old + __popc(pm & ((1u << lane) - 1u))] = v[q];
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+
+  // (3) the walk
+  unsigned* blocked = wv.wordoff + (size_t)fr * wv.words_per_frame;  // free until a fallback frame needs raster ranks
+  const uint8_t* im = img + (size_t)(first + fr) * fstride;
+  double2* out = out_xy + (size_t)fr * cap_out;
+  const int d = min_dist, d2 = min_dist * min_dist, rows = 2 * d - 1;
+  const bool suppress = wv.cell > 0;
+  unsigned pos = 0;  // words [0, pos) are done (block-uniform)
+  int bi = 0;        // first bucket that is not done
+  while (pos < n && sm.accepted < cap_out && !sm.tiehit) {
+    // as many whole buckets as certainly fit; a bucket that does not fit by itself is filtered anyway and must fit afterwards
+    unsigned tgt = pos;
+    while (bi < BK_NB && sm.cur[bi] - pos <= (unsigned)BK_T) tgt = sm.cur[bi++];
+    if (tgt == pos) tgt = sm.cur[bi++];
+    int nsv = 0;
+    bool overflow = false;
+    for (unsigned p0 = pos; p0 < tgt; p0 += BK_PIECE) {
+      unsigned long long v[BK_EPT];
+      unsigned bw[BK_EPT];
+#pragma unroll
+      for (int e = 0; e < BK_EPT; e++) {
+        const unsigned i = p0 + tid * BK_EPT + e;
+        v[e] = i < tgt ? __ldcg(B + i) : ~0ull;
+      }
+#pragma unroll
+      for (int e = 0; e < BK_EPT; e++) {
+        const unsigned x = (unsigned)v[e] & 0x7FFFu, y = ((unsigned)v[e] >> 15) & 0x7FFFu;
+        bw[e] = (suppress && p0 + tid * BK_EPT + e < tgt) ? __ldcg(blocked + (size_t)y * wv.wpr + (x >> 5)) : 0u;
+      }
+      unsigned am = 0;
+#pragma unroll
+      for (int e = 0; e < BK_EPT; e++)
+        if (p0 + tid * BK_EPT + e < tgt && !((bw[e] >> ((unsigned)v[e] & 31u)) & 1u)) am |= 1u << e;
+      int tot;
+      int r = nsv + bk_block_scan(sm, __popc(am), tot);
+      if (nsv + tot > BK_T) {  // block-uniform
+        overflow = true;
+        break;
+      }
+#pragma unroll
+      for (int e = 0; e < BK_EPT; e++)
+        if (am & (1u << e)) sm.sv[r++] = v[e];
+      nsv += tot;
+    }
+    pos = tgt;
+    if (overflow) {
+      if (tid == 0) sm.tiehit = 1;
+      __syncthreads();
+      break;
+    }
+    if (nsv == 0) {
+      __syncthreads();
+      continue;
+    }
+    // sort the survivors (ascending word = descending score); pad to a power of two
+    int N2 = 32;
+    while (N2 < nsv) N2 <<= 1;
+    for (int i = nsv + tid; i < N2; i += BK_THREADS) sm.sv[i] = ~0ull;
+    for (int i = tid; i < nsv; i += BK_THREADS) sm.tf[i] = 0;
+    if (tid == 0) sm.eqrun = 0;
+    __syncthreads();
+    for (int k = 2; k <= N2; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = tid; t < (N2 >> 1); t += BK_THREADS) {
+          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), p = i | j;  // the pair (i, i + j) of this step
+          const unsigned long long a = sm.sv[i], b = sm.sv[p];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) {
+            sm.sv[i] = b;
+            sm.sv[p] = a;
+          }
+        }
+        __syncthreads();
+      }
+    // equal order codes among the survivors: order by the exact score, flag identical scores (rare)
+    for (int i = tid; i + 1 < nsv; i += BK_THREADS)
+      if ((sm.sv[i] >> 30) == (sm.sv[i + 1] >> 30)) sm.eqrun = 1;
+    __syncthreads();
+    if (sm.eqrun) {
+      for (int i = tid; i + 1 < nsv; i += BK_THREADS) {
+        const unsigned long long code = sm.sv[i] >> 30;
+        if ((sm.sv[i + 1] >> 30) != code || (i > 0 && (sm.sv[i - 1] >> 30) == code)) continue;  // not the start of a run
+        int j = i + 2;
+        while (j < nsv && j - i < BK_MAXRUN && (sm.sv[j] >> 30) == code) j++;
+        if (j < nsv && (sm.sv[j] >> 30) == code) {  // pathological pile-up: let the exact path decide
+          sm.tiehit = 1;
+          continue;
+        }
+        // insertion sort of [i, j) by the exact score, descending (scores recomputed on every comparison: the runs are pairs)
+        for (int p = i + 1; p < j; p++) {
+          const unsigned long long e = sm.sv[p];
+          const double se = bk_exact_score(im, pitch, w, h, (int)((unsigned)e & 0x7FFFu), (int)(((unsigned)e >> 15) & 0x7FFFu));
+          int q = p;
+          while (q > i) {
+            const unsigned long long f = sm.sv[q - 1];
+            const double sf = bk_exact_score(im, pitch, w, h, (int)((unsigned)f & 0x7FFFu), (int)(((unsigned)f >> 15) & 0x7FFFu));
+            if (!(sf < se)) break;
+            sm.sv[q] = f;
+            q--;
+          }
+          sm.sv[q] = e;
+        }
+        double sprev = 0.0;
+        for (int p = i; p < j; p++) {
+          const unsigned long long e = sm.sv[p];
+          const double s = bk_exact_score(im, pitch, w, h, (int)((unsigned)e & 0x7FFFu), (int)(((unsigned)e >> 15) & 0x7FFFu));
+          if (p > i && s == sprev) {
+            sm.tf[p] |= 1;
+            if (p > i + 1 && (sm.tf[p - 1] & 1)) {
+              sm.tf[p - 2] |= 2;
+              sm.tf[p - 1] |= 2;
+              sm.tf[p] |= 2;
+            }
+          }
+          sprev = s;
+        }
+      }
+      __syncthreads();
+    }
+    // greedy rounds over the sorted survivors
+    int t0 = 0;
+    while (t0 < nsv) {
+      const int acc0 = sm.accepted;
+      if (acc0 >= cap_out) break;
+      const int cnt = min(BK_PIECE, nsv - t0);
+      unsigned yx[BK_EPT], bw[BK_EPT];
+      unsigned tie = 0, big = 0;
+#pragma unroll
+      for (int e = 0; e < BK_EPT; e++) {
+        const int t = tid * BK_EPT + e;
+        yx[e] = t < cnt ? (unsigned)sm.sv[t0 + t] & BK_YX : 0u;
+        const unsigned f = t < cnt ? sm.tf[t0 + t] : 0u;
+        tie |= (f & 1u) << e;
+        big |= ((f >> 1) & 1u) << e;
+      }
+#pragma unroll
+      for (int e = 0; e < BK_EPT; e++) {
+        const int t = tid * BK_EPT + e;
+        const unsigned x = yx[e] & 0x7FFFu, y = yx[e] >> 15;
+        bw[e] = (suppress && t < cnt) ? __ldcg(blocked + (size_t)y * wv.wpr + (x >> 5)) : 0u;
+      }
+      unsigned am = 0;
+#pragma unroll
+      for (int e = 0; e < BK_EPT; e++)
+        if (tid * BK_EPT + e < cnt && !((bw[e] >> (yx[e] & 31u)) & 1u)) am |= 1u << e;
+      {
+        // std::sort's order inside a group of identical scores is only observable if at least two of its members are still
+        // unblocked.  Conservative test on the survivors of the bitmap check (predecessors outside the warp /
+        // chunk count as unblocked).
+        const unsigned up = __shfl_up_sync(0xffffffffu, am, 1);
+        const unsigned prev_alive = (am << 1) | (lane > 0 ? (up >> (BK_EPT - 1)) & 1u : 1u);
+        if (am & (big | (tie & prev_alive))) sm.tiehit = 1;
+      }
+      int na;
+      const int exc = bk_block_scan(sm, __popc(am), na);
+      if (sm.tiehit) break;  // block-uniform: written before the scan's barriers, not again before the next ones
+      if (tid == 0) sm.cut = cnt;
+      __syncthreads();
+      {
+        int r = exc;
+#pragma unroll
+        for (int e = 0; e < BK_EPT; e++)
+          if (am & (1u << e)) {
+            if (r < BK_ALIVE) sm.pxy[r] = yx[e];
+            if (r == BK_ALIVE) sm.cut = tid * BK_EPT + e;  // first candidate that does not fit: it starts the next round
+            r++;
+          }
+      }
+      if (tid < BK_ALIVE / 32) sm.accm[tid] = sm.deadm[tid] = 0;
+      na = na < BK_ALIVE ? na : BK_ALIVE;
+      __syncthreads();
+      const int used = sm.cut;
+      // conflicts inside the round: thread i collects the higher-priority survivors closer than min_dist as a bit row, then
+      // rounds of pure bit logic: dead if the row meets an accepted survivor, accepted once every member of it is dead
+      const unsigned me = sm.pxy[tid];
+      const int mx = (int)(me & 0x7FFFu), my = (int)(me >> 15);
+      unsigned C[BK_ALIVE / 32];
+#pragma unroll
+      for (int wd = 0; wd < BK_ALIVE / 32; wd++) {
+        C[wd] = 0;
+        if (suppress && wd <= warp && wd * 32 < na) {
+          unsigned bitsw = 0;
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            const uint4 o = *reinterpret_cast<const uint4*>(&sm.pxy[wd * 32 + q * 4]);
+            const unsigned ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+              const int dx = (int)(ov[kk] & 0x7FFFu) - mx, dy = (int)(ov[kk] >> 15) - my;
+              if (dx * dx + dy * dy < d2) bitsw |= 1u << (q * 4 + kk);
+            }
+          }
+          if (wd == warp) bitsw &= (1u << lane) - 1u;  // strictly higher priority only
+          C[wd] = bitsw;
+        }
+      }
+      int state = tid < na ? ST_UNDEC : ST_DEAD;
+      if (!suppress && tid < na) state = ST_ACC;
+      while (true) {
+        if (state == ST_UNDEC) {
+          unsigned hit = 0, und = 0;
+#pragma unroll
+          for (int wd = 0; wd < BK_ALIVE / 32; wd++) {
+            const unsigned a = sm.accm[wd], dd = sm.deadm[wd];
+            hit |= C[wd] & a;
+            und |= C[wd] & ~(a | dd);
+          }
+          state = hit ? ST_DEAD : (und ? ST_UNDEC : ST_ACC);
+        }
+        __syncthreads();  // everybody has read the masks of the previous round
+        const unsigned ba = __ballot_sync(0xffffffffu, state == ST_ACC), bd = __ballot_sync(0xffffffffu, state == ST_DEAD);
+        if (lane == 0) {
+          sm.accm[warp] = ba;
+          sm.deadm[warp] = bd;
+        }
+        if (__syncthreads_or(state == ST_UNDEC) == 0) break;
+      }
+      // append accepted survivors in priority order, stop at the cap; mark their discs
+      const bool acc = state == ST_ACC;
+      int nacc;
+      const int rank = bk_block_scan(sm, acc ? 1 : 0, nacc);
+      if (acc && acc0 + rank < cap_out) {
+        out[acc0 + rank] = make_double2((double)mx, (double)my);
+        sm.accl[rank] = (unsigned short)tid;
+      }
+      __syncthreads();
+      const int nnew = min(nacc, cap_out - acc0);
+      if (suppress && acc0 + nnew < cap_out) {  // nothing is looked up once the cap is reached
+        for (int i = tid; i < nnew * rows; i += BK_THREADS) {
+          const int c = i / rows, dy = i - c * rows - (d - 1);
+          const unsigned sp = sm.pxy[sm.accl[c]];
+          const int px = (int)(sp & 0x7FFFu), py = (int)(sp >> 15) + dy;
+          if (py < 0 || py >= h) continue;
+          const int r2 = d2 - 1 - dy * dy;  // dx^2 <= r2  <=>  dx^2 + dy^2 < d^2
+          int r = (int)sqrtf((float)r2);
+          while (r * r > r2) r--;
+          while ((r + 1) * (r + 1) <= r2) r++;
+          const int xa = max(px - r, 0), xb = min(px + r, w - 1);
+          unsigned* rowp = blocked + (size_t)py * wv.wpr;
+          for (int wd = xa >> 5; wd <= (xb >> 5); wd++) {
+            const int lo = max(xa - wd * 32, 0), hi = min(xb - wd * 32, 31);
+            atomicOr(rowp + wd, (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo));
+          }
+        }
+        __threadfence_block();
+      }
+      __syncthreads();
+      if (tid == 0) sm.accepted = acc0 + nnew;
+      t0 += used;
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    // an observable tie, an unresolved pile-up of equal order codes or a bucket whose survivors do not fit: the frame is
+    // redone by select_kernel mode 3
+    wv.status[fr] = sm.tiehit ? 3 : 0;
+    if (out_n) out_n[fr] = sm.accepted;
+  }
+}
+
 // mode 0: full shi_tomasi selection; mode 1: sort only (sfmgpu_sort_perm_desc).
 // mode 3: redo exactly the frames nms_kernel marked with status 3 (a consumed score tie) through the emulation.
 __global__ void __launch_bounds__(SEL_THREADS, 4) select_kernel(CornerWorkView wv, int w, int max_corners, int min_dist, int mode,
@@ -1067,6 +1533,8 @@ int select_smem_config(sfmgpu_ctx* ctx) {
   SFM_SMEM_OPTIN(ctx, cfg_id[0], select_kernel, sizeof(SelSmem));
   SFM_SMEM_OPTIN(ctx, cfg_id[1], (radix_sort_frame_kernel<512, 8>), sizeof(RadixSmem<512>));
   SFM_SMEM_OPTIN(ctx, cfg_id[2], (radix_sort_frame_kernel<1024, 4>), sizeof(RadixSmem<1024>));
+  static const int bk_id = sfm_next_cfg_id();
+  SFM_SMEM_OPTIN(ctx, bk_id, bucket_select_kernel, sizeof(BucketSmem));
   return 0;
 }
 
@@ -1094,8 +1562,8 @@ int sfm_corners_score_stage(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first, 
   return sfm_corner_candidates_batch(ctx, f, first, count, quality, wv);
 }
 
-int sfm_corners_select_stage(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int count, int max_corners, double quality, int min_dist, int cand_cap, void* work,
-                             size_t work_bytes, double2* out_xy, int* out_n) {
+int sfm_corners_select_stage(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first, int count, int max_corners, double quality, int min_dist,
+                             int cand_cap, void* work, size_t work_bytes, double2* out_xy, int* out_n) {
   CornerWorkView wv;
   SFM_TRY(corners_args(ctx, f, count, min_dist, cand_cap, work, work_bytes, wv));
   SFM_TRY(select_smem_config(ctx));
@@ -1107,13 +1575,19 @@ int sfm_corners_select_stage(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int count,
     SFM_LAUNCH(ctx, select_kernel, count, SEL_THREADS, sizeof(SelSmem), wv, f->w, max_corners, min_dist, 0, out_xy, out_n);
     return 0;
   }
-  SFM_CUDA(ctx, cudaMemsetAsync(wv.tiepos, 0xFF, sizeof(unsigned) * count, ctx->stream));
-  SFM_CUDA(ctx, cudaMemsetAsync(wv.wordoff, 0, sizeof(unsigned) * wv.words_per_frame * count, ctx->stream));  // nms_kernel's blocked-pixel map
-  if (count >= 2 * ctx->n_sm)
-    SFM_LAUNCH(ctx, (radix_sort_frame_kernel<512, 8>), count, 512, sizeof(RadixSmem<512>), wv, quality);
-  else  // few frames: the widest block per frame
-    SFM_LAUNCH(ctx, (radix_sort_frame_kernel<1024, 4>), count, 1024, sizeof(RadixSmem<1024>), wv, quality);
-  SFM_LAUNCH(ctx, nms_kernel, count, NMS_THREADS, 0, wv, f->w, f->h, max_corners, min_dist, out_xy, out_n);
+  SFM_CUDA(ctx, cudaMemsetAsync(wv.wordoff, 0, sizeof(unsigned) * wv.words_per_frame * count, ctx->stream));  // the blocked-pixel map
+  if (ctx->select_mode == 2) {  // the full radix sort + selection over the sorted list (A/B timing)
+    SFM_CUDA(ctx, cudaMemsetAsync(wv.tiepos, 0xFF, sizeof(unsigned) * count, ctx->stream));
+    if (count >= 2 * ctx->n_sm)
+      SFM_LAUNCH(ctx, (radix_sort_frame_kernel<512, 8>), count, 512, sizeof(RadixSmem<512>), wv, quality);
+    else  // few frames: the widest block per frame
+      SFM_LAUNCH(ctx, (radix_sort_frame_kernel<1024, 4>), count, 1024, sizeof(RadixSmem<1024>), wv, quality);
+    SFM_LAUNCH(ctx, nms_kernel, count, NMS_THREADS, 0, wv, f->w, f->h, max_corners, min_dist, out_xy, out_n);
+  } else {
+    const int code_bits = ctx->select_mode >= 12 ? ctx->select_mode : BK_CODE_BITS;  // tests: short codes make equal codes common
+    SFM_LAUNCH(ctx, bucket_select_kernel, count, BK_THREADS, sizeof(BucketSmem), wv, f->lvl[0], f->pitch[0], f->fstride[0], first, f->w, f->h,
+               max_corners, min_dist, quality, code_bits, out_xy, out_n);
+  }
   // frames where a score tie was consumed (status 3): raster order, then the exact emulation.  Blocks of all other
   // frames return at once.
   SFM_TRY(sfm_corner_raster_order(ctx, count, wv, quality, 1));
@@ -1124,7 +1598,7 @@ int sfm_corners_select_stage(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int count,
 int sfm_corners_batch(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first, int count, int max_corners, double quality,
                       int min_dist, int cand_cap, void* work, size_t work_bytes, double2* out_xy, int* out_n) {
   SFM_TRY(sfm_corners_score_stage(ctx, f, first, count, quality, min_dist, cand_cap, work, work_bytes));
-  return sfm_corners_select_stage(ctx, f, count, max_corners, quality, min_dist, cand_cap, work, work_bytes, out_xy, out_n);
+  return sfm_corners_select_stage(ctx, f, first, count, max_corners, quality, min_dist, cand_cap, work, work_bytes, out_xy, out_n);
 }
 
 size_t sfm_corner_work_bytes_md(int w, int h, int nframes, int cand_cap, int min_dist) {
@@ -1135,7 +1609,8 @@ size_t sfm_corner_work_bytes_md(int w, int h, int nframes, int cand_cap, int min
 extern "C" int sfmgpu_select_set_mode(sfmgpu_ctx* ctx, int mode) {
   SFM_ENTER(ctx);
   if (!ctx) return SFMGPU_E_ARG;
-  if (mode != 0 && mode != 1) return sfm_fail(ctx, SFMGPU_E_ARG, "select_set_mode: mode %d not in {0,1}", mode);
+  if (mode != 0 && mode != 1 && mode != 2 && !(mode >= 12 && mode <= BK_CODE_BITS))
+    return sfm_fail(ctx, SFMGPU_E_ARG, "select_set_mode: mode %d not in {0, 1, 2, 12..%d}", mode, BK_CODE_BITS);
   ctx->select_mode = mode;
   return 0;
 }

@@ -247,7 +247,7 @@ static int stage_score(sfmgpu_ctx* ctx, const ChunkArgs& c) {
 
 static int stage_select(sfmgpu_ctx* ctx, const ChunkArgs& c) {
   const size_t so = (size_t)c.pair_off * c.out->cap;
-  return sfm_corners_select_stage(ctx, c.f, c.npairs, c.cfg->max_tracks, c.cfg->quality, c.md, c.cand_cap, c.work->p, c.work->cap, c.out->xy0 + so,
+  return sfm_corners_select_stage(ctx, c.f, c.first_frame, c.npairs, c.cfg->max_tracks, c.cfg->quality, c.md, c.cand_cap, c.work->p, c.work->cap, c.out->xy0 + so,
                                   c.out->ncorn + c.pair_off);
 }
 

@@ -571,6 +571,10 @@ __device__ __forceinline__ void quad_eval(const double* m, double fx, double fy,
   b1 = s[4];
 }
 
+#ifdef KLT_ROUND_STATS
+__device__ unsigned long long klt_round_hist[2][33];  // [0]: build rounds by lanes building, [1]: iteration rounds by lanes iterating
+#endif
+
 template <int MINB, int LSTAGE, typename T>
 __global__ void __launch_bounds__(32, MINB) klt_quad_kernel(KltLaunch k, int* __restrict__ defer_count, int* __restrict__ defer_list) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -641,6 +645,12 @@ __global__ void __launch_bounds__(32, MINB) klt_quad_kernel(KltLaunch k, int* __
       }
       const int key = dir * SFM_MAXL + l;
       const bool hit = act && FX == tFX && FY == tFY && key == tkey;
+#ifdef KLT_ROUND_STATS
+      {
+        const unsigned hm = __ballot_sync(FULL, hit);
+        if (hm && lane == 0) atomicAdd(&klt_round_hist[1][__popc(hm)], 1ull);
+      }
+#endif
       if (__any_sync(FULL, hit)) {
         if (hit) {
           double a00, a01, a11, b0, b1;
@@ -663,6 +673,9 @@ __global__ void __launch_bounds__(32, MINB) klt_quad_kernel(KltLaunch k, int* __
       // nobody can iterate: every lane that still has work needs matrices for its position
       unsigned need = __ballot_sync(FULL, act);
       if (!need) continue;  // only level hand-overs are pending
+#ifdef KLT_ROUND_STATS
+      if (lane == 0) atomicAdd(&klt_round_hist[0][__popc(need)], 1ull);
+#endif
       __syncwarp();
       while (need) {
         int ss[LSTAGE], sx0[LSTAGE];
@@ -768,3 +781,9 @@ int sfm_klt_lane_masked_launch(sfmgpu_ctx* ctx, const KltLaunch& k, const int* i
                                int* defer_list) {
   return lane_launch<1, 8, 4, true>(ctx, k, in_list, in_count, defer_count, defer_list);
 }
+
+#ifdef KLT_ROUND_STATS
+extern "C" int sfmgpu_debug_klt_round_hist(unsigned long long* out66) {
+  return (int)cudaMemcpyFromSymbol(out66, klt_round_hist, sizeof(unsigned long long) * 66);
+}
+#endif
