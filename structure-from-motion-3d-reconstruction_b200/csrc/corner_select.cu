@@ -918,8 +918,8 @@ struct BucketSmem {
   unsigned short accl[BK_ALIVE];
   unsigned char tf[BK_T];  // bit 0: identical score as the predecessor, bit 1: member of a group of >= 3
   int wcnt[BK_WARPS];
-  unsigned nkeep;
-  int accepted, cut, tiehit, eqrun;
+  unsigned nkeep, tgt;
+  int accepted, cut, tiehit, eqrun, bi;
 };
 
 __device__ __forceinline__ int bk_block_scan(BucketSmem& sm, int c, int& total) {
@@ -974,7 +974,6 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_select_kernel(CornerWork
   BucketSmem& sm = *reinterpret_cast<BucketSmem*>(bk_raw);
   const int fr = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t cb = (size_t)fr * wv.cand_cap;
-  unsigned long long* A = wv.pk_a + cb;
   unsigned long long* B = wv.pk_b + cb;
   const bool exact = wv.exact_list[fr] != 0;
   const unsigned nlist = exact ? wv.nfinal[fr] : wv.ncand[fr];
@@ -1004,35 +1003,35 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_select_kernel(CornerWork
   const int shift = bits > code_bits ? bits - code_bits : 0;
   const int used_bits = bits < code_bits ? bits : code_bits;
   const int bshift = used_bits > BK_NB_BITS ? used_bits - BK_NB_BITS : 0;
+  const unsigned long long* lkey = wv.tmp_key + cb;
+  const unsigned* lidx = wv.tmp_idx + cb;
+  // sweep 1: bucket counts (keys only); the loads of the next round are in flight while this one is counted
   {
-    const unsigned long long* lkey = wv.tmp_key + cb;
-    const unsigned* lidx = wv.tmp_idx + cb;
+    unsigned long long k[4], kn[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const unsigned e = q * BK_THREADS + tid;
+      kn[q] = e < nlist ? __ldcg(lkey + e) : 0ull;
+    }
+    unsigned cnt = 0;
     for (unsigned i0 = 0; i0 < nlist; i0 += BK_THREADS * 4) {  // block-uniform trip count
-      unsigned long long k[4];
-      unsigned yx[4];
 #pragma unroll
       for (int q = 0; q < 4; q++) {
-        const unsigned e = i0 + q * BK_THREADS + tid;
-        k[q] = e < nlist ? __ldcg(lkey + e) : 0ull;
-        yx[q] = e < nlist ? __ldcg(lidx + e) : 0u;
+        k[q] = kn[q];
+        const unsigned e = i0 + BK_THREADS * 4 + q * BK_THREADS + tid;
+        kn[q] = e < nlist ? __ldcg(lkey + e) : 0ull;
       }
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         const unsigned e = i0 + q * BK_THREADS + tid;
-        const bool keep = e < nlist && __longlong_as_double((long long)k[q]) >= thr;
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (m) {
-          unsigned base = 0;
-          if (lane == 0) base = atomicAdd(&sm.nkeep, (unsigned)__popc(m));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (keep) {
-            const unsigned long long code = (maxkey - k[q]) >> shift;
-            A[base + __popc(m & ((1u << lane) - 1u))] = (code << 30) | (unsigned long long)(((yx[q] >> 16) << 15) | (yx[q] & 0x7FFFu));
-            atomicAdd(&sm.cur[(unsigned)(code >> bshift)], 1u);
-          }
+        if (e < nlist && __longlong_as_double((long long)k[q]) >= thr) {
+          atomicAdd(&sm.cur[(unsigned)(((maxkey - k[q]) >> shift) >> bshift)], 1u);
+          cnt++;
         }
       }
     }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0 && cnt) atomicAdd(&sm.nkeep, cnt);
   }
   __syncthreads();
   const unsigned n = sm.nkeep;
@@ -1063,26 +1062,40 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_select_kernel(CornerWork
       run += c[j];
     }
   }
-  __threadfence_block();
   __syncthreads();
-  // (2) scatter into bucket order; cur[b] ends up as the END of bucket b
-  for (unsigned i0 = 0; i0 < n; i0 += BK_THREADS * 4) {
-    unsigned long long v[4];
+  // sweep 2: words into bucket order (unordered inside a bucket); cur[b] ends up as the END of bucket b
+  {
+    unsigned long long k[4], kn[4];
+    unsigned yx[4], yxn[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-      const unsigned i = i0 + q * BK_THREADS + tid;
-      v[q] = i < n ? __ldcg(A + i) : ~0ull;
+      const unsigned e = q * BK_THREADS + tid;
+      kn[q] = e < nlist ? __ldcg(lkey + e) : 0ull;
+      yxn[q] = e < nlist ? __ldcg(lidx + e) : 0u;
     }
+    for (unsigned i0 = 0; i0 < nlist; i0 += BK_THREADS * 4) {
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const bool in = i0 + q * BK_THREADS + tid < n;
-      const unsigned b = in ? (unsigned)((v[q] >> 30) >> bshift) : 0xFFFFFFFFu;
-      const unsigned pm = __match_any_sync(0xffffffffu, b);
-      const int leader = __ffs(pm) - 1;
-      unsigned old = 0;
-      if (in && lane == leader) old = atomicAdd(&sm.cur[b], (unsigned)__popc(pm));
-      old = __shfl_sync(0xffffffffu, old, leader);
-      if (in) B[old + __popc(pm & ((1u << lane) - 1u))] = v[q];
+      for (int q = 0; q < 4; q++) {
+        k[q] = kn[q];
+        yx[q] = yxn[q];
+        const unsigned e = i0 + BK_THREADS * 4 + q * BK_THREADS + tid;
+        kn[q] = e < nlist ? __ldcg(lkey + e) : 0ull;
+        yxn[q] = e < nlist ? __ldcg(lidx + e) : 0u;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const unsigned e = i0 + q * BK_THREADS + tid;
+        const bool in = e < nlist && __longlong_as_double((long long)k[q]) >= thr;
+        const unsigned long long code = (maxkey - k[q]) >> shift;
+        const unsigned b = in ? (unsigned)(code >> bshift) : 0xFFFFFFFFu;
+        const unsigned pm = __match_any_sync(0xffffffffu, b);
+        const int leader = __ffs(pm) - 1;
+        unsigned old = 0;
+        if (in && lane == leader) old = atomicAdd(&sm.cur[b], (unsigned)__popc(pm));
+        old = __shfl_sync(0xffffffffu, old, leader);
+        if (in)
+          B[old + __popc(pm & ((1u << lane) - 1u))] = (code << 30) | (unsigned long long)(((yx[q] >> 16) << 15) | (yx[q] & 0x7FFFu));
+      }
     }
   }
   __threadfence_block();
@@ -1098,9 +1111,24 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_select_kernel(CornerWork
   int bi = 0;        // first bucket that is not done
   while (pos < n && sm.accepted < cap_out && !sm.tiehit) {
     // as many whole buckets as certainly fit; a bucket that does not fit by itself is filtered anyway and must fit afterwards
-    unsigned tgt = pos;
-    while (bi < BK_NB && sm.cur[bi] - pos <= (unsigned)BK_T) tgt = sm.cur[bi++];
-    if (tgt == pos) tgt = sm.cur[bi++];
+    if (warp == 0) {  // 32 buckets per step
+      int b2 = bi;
+      while (b2 < BK_NB) {
+        const bool fits = b2 + lane < BK_NB && sm.cur[b2 + lane] - pos <= (unsigned)BK_T;
+        const int run = __ffs(~__ballot_sync(0xffffffffu, fits)) - 1;  // leading buckets that fit (32: all of them)
+        b2 += run < 0 ? 32 : run;
+        if (run >= 0 && run < 32) break;
+      }
+      if (b2 > BK_NB) b2 = BK_NB;
+      if (b2 == bi) b2++;  // the next bucket does not fit by itself
+      if (lane == 0) {
+        sm.bi = b2;
+        sm.tgt = sm.cur[b2 - 1];
+      }
+    }
+    __syncthreads();
+    bi = sm.bi;
+    const unsigned tgt = sm.tgt;
     int nsv = 0;
     bool overflow = false;
     for (unsigned p0 = pos; p0 < tgt; p0 += BK_PIECE) {
@@ -1207,11 +1235,13 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_select_kernel(CornerWork
       __syncthreads();
     }
     // greedy rounds over the sorted survivors
-    int t0 = 0;
+    // A round resolves at most BK_ALIVE unblocked survivors: where most survivors are still unblocked (the first gathers)
+    // a short chunk holds that many, and whatever a round does not consume is tested again by the next one
+    int t0 = 0, want = 2 * BK_ALIVE;
     while (t0 < nsv) {
       const int acc0 = sm.accepted;
       if (acc0 >= cap_out) break;
-      const int cnt = min(BK_PIECE, nsv - t0);
+      const int cnt = min(want, nsv - t0);
       unsigned yx[BK_EPT], bw[BK_EPT];
       unsigned tie = 0, big = 0;
 #pragma unroll
@@ -1336,6 +1366,8 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_select_kernel(CornerWork
       __syncthreads();
       if (tid == 0) sm.accepted = acc0 + nnew;
       t0 += used;
+      want = used < cnt ? 2 * used : 2 * want;  // the chunk was cut (enough unblocked survivors) / was used up
+      want = want < 2 * BK_ALIVE ? 2 * BK_ALIVE : (want > BK_PIECE ? BK_PIECE : want);
       __syncthreads();
     }
   }
