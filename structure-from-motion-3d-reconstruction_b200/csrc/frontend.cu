@@ -541,7 +541,10 @@ int sfmgpu_pair_frontend_host(sfmgpu_ctx* ctx, sfmgpu_frames* f, const uint8_t* 
   // default: about 100 frames, at least 8 chunks for short sequences, at most 20 for long ones.  Smaller chunks shorten the
   // pipeline fill (the first upload and the last chunk's compute are not overlapped), too small ones under-fill the
   // one-block-per-frame kernels.  Measured end to end: C2 (1000 x 1080p) chunks of 84-125 frames 43.0 ms, 167: 44.1, 250: 46.3,
-  // 50: 47.8; C3 with the RANSAC stage (2000 x 4K) 50: 372 ms, 100: 358, 150: 385, 200: 390.
+  // 50: 47.8; C3 with the RANSAC stage (2000 x 4K) 50: 372 ms, 100: 358, 150: 385, 200: 390.  (Tried and dropped: halving the
+  // last chunks - 50, 25, 13, 12 frames, or 50 + 25 + 25 - so that less compute is left behind the last upload: 325 / 322 ms
+  // against 321 ms on C3; the one-block-per-frame kernels of a 12-frame chunk still take their full latency and the short
+  // uploads ran at 37 instead of 54 GB/s.)
   int chunk = chunk_frames;
   if (chunk <= 0) {
     const int by8 = (nframes + 7) / 8, by20 = (nframes + 19) / 20;
