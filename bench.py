@@ -824,7 +824,7 @@ def main():
     xi, xj = c4_points(RS_N)
     idx8 = ctx.ransac_sample(RS_N, RS_H * 8).reshape(RS_H, 8)
     solver = {}
-    for mode in (1, 0):  # 1: screening solver (what the batched stage counts with), 0: Jacobi emulation for every octet
+    for mode in (3, 0):  # 3: screening solver (what the batched stage counts with), 0: Jacobi emulation for every octet
         ctx.solver_set_mode(mode)
         ctx.ransac_hypotheses(xi, xj, idx8, fetch=False)
         ctx.sync()
@@ -832,7 +832,7 @@ def main():
         ctx.ransac_hypotheses(xi, xj, idx8, fetch=False)
         solver[mode] = ctx.timer_stop()
     ctx.solver_set_mode(1)
-    solver_ms, screen_ms = solver[0], solver[1]  # the scoring rate below is measured on the emulation's hypotheses
+    solver_ms, screen_ms = solver[0], solver[3]  # the scoring rate below is measured on the emulation's hypotheses
     for _ in range(3):
         ctx.ransac_score_resident(1e-3, fetch=False)
     ctx.sync()

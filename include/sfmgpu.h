@@ -312,13 +312,15 @@ int sfmgpu_ransac_download(sfmgpu_ctx* ctx, int32_t* counts, int32_t* best_inl, 
  * only) the context's solver mode applies, see sfmgpu_ransac_solve_score. */
 int sfmgpu_ransac_hypotheses(sfmgpu_ctx* ctx, const double* xi_xy, const double* xj_xy, int n, const int32_t* idx8, int H,
                              double* E_out);
-/* Solver + scoring loop of find_E_ransac (:657-677) in one call: hypotheses of the octets idx8[H][8], counts, winner
+/* Solver + scoring loop of find_E_ransac (:657-677) in one call: hypotheses of the octets idx8[H][8] (NULL: the reference's
+ * seeded sampling for n correspondences, std::mt19937(12345) + uniform_int_distribution, on the device), counts, winner
  * (largest count, lowest index), its hypothesis best_E[9] (zero matrix when no hypothesis has an inlier, as the reference's
  * Mat33{}) and ascending inlier list best_inl (room for n).  In solver mode 1 (default) the COUNTS come from a screening
  * solver - the unit null vector of the 8 x 9 design matrix by Householder QR, i.e. the vector the reference's Jacobi
  * iteration converges to, ~50x cheaper - and the winner is solved again by the Jacobi emulation of
  * sfmgpu_ransac_hypotheses before its inlier list and count are taken: best_E, best_n and best_inl are the emulation's.
- * Mode 0 runs the emulation for every octet.  The batched RANSAC stage (sfmgpu_pairs_set_ransac) follows the same mode. */
+ * Mode 0 runs the emulation for every octet (mode 2: the same through the warp-per-hypothesis kernel that re-solves the
+ * winners - bit-identical, for tests; mode 3: screening for every launch, for tests).  The batched RANSAC stage (sfmgpu_pairs_set_ransac) follows the same mode. */
 int sfmgpu_ransac_solve_score(sfmgpu_ctx* ctx, const double* xi_xy, const double* xj_xy, int n, const int32_t* idx8, int H,
                               double thr, int* best_h, int* best_n, double* best_E, int32_t* best_inl);
 int sfmgpu_solver_set_mode(sfmgpu_ctx* ctx, int mode);

@@ -64,10 +64,12 @@ struct sfmgpu_ctx {
   DevBuf sel_work;   // corner-select work area
   DevBuf misc;       // small scalars
   DevBuf rs_xi, rs_xj, rs_E, rs_counts, rs_inl, rs_best, rs_idx8;
+  DevBuf rs_raw;     // std::mt19937(12345) outputs for single-call sampling (two_view.cu: raw_stream)
+  int rs_raw_n = 0;
   DevBuf sv_list;    // screening solver: [0] count, [64...] hypotheses left to the Jacobi emulation (repeated index)
   int rs_n = 0, rs_H = 0;
   bool rs_screened = false;  // rs_E holds screening hypotheses of the octets in rs_idx8: the winner is re-solved when scored
-  int solver_mode = 1;       // device 8-point solver: 1 screening solver for the counts + Jacobi emulation for the winner, 0 Jacobi emulation for every hypothesis
+  int solver_mode = 1;       // device 8-point solver: 1 screening solver for the counts of launches beyond one wave + Jacobi emulation for the winner, 0 Jacobi emulation for every hypothesis, 2 the same by the warp kernel, 3 screening always (2, 3: tests)
   bool profile = false;
   struct StageEv { int stage; cudaEvent_t a, b; };
   std::vector<StageEv> stage_evs;
@@ -217,6 +219,8 @@ int sfm_sort_perm(sfmgpu_ctx* ctx, const double* keys, int n, int32_t* perm);
 // solver.cu / ransac.cu: batched over correspondence sets
 int sfm_eight_point_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, const int* npts, int n_single,
                             int npairs, const int* idx8, int H, double* Eout, int screen);
+bool sfm_solver_screens(const sfmgpu_ctx* ctx, int npairs, int H);
+int sfm_sample_octets(sfmgpu_ctx* ctx, int n, int H, int* d_idx8, int* d_flag);
 int sfm_eight_point_winners(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, const int* npts, int n_single,
                             int npairs, const int* idx8, int H, const int* best, double* E);
 int sfm_pose_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, int npairs, const int* status,

@@ -95,7 +95,7 @@ void sfmgpu_destroy(sfmgpu_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->flush,  &ctx->klt_in, &ctx->klt_p1, &ctx->klt_pb,    &ctx->klt_nit, &ctx->klt_keep, &ctx->klt_defer, &ctx->cs_work,
                     &ctx->sel_work, &ctx->misc,   &ctx->rs_xi,  &ctx->rs_xj,     &ctx->rs_E,    &ctx->rs_counts, &ctx->rs_inl,
-                    &ctx->rs_best, &ctx->rs_idx8, &ctx->sv_list};
+                    &ctx->rs_best, &ctx->rs_idx8, &ctx->sv_list, &ctx->rs_raw};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);

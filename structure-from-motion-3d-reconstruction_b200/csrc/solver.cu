@@ -11,6 +11,8 @@
 // the reference's; measured agreement of the hypotheses is ~1e-12 relative (up to the eigenvector's sign, which the
 // Sampson error ignores) and the tests require the same winner and inlier set on their scenes.  The reference path
 // of the drop-in (bit-identical hypotheses from the host, scored on the device) remains the default.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace {
@@ -342,6 +344,169 @@ __global__ void __launch_bounds__(SV_TPB, SV_MINB) eight_point_kernel(const doub
                             Eout + ho * 9);
 }
 
+// ---- the same emulation, one WARP per hypothesis (latency: the winner of a pair, the few repeated-index octets of a single call) ----
+// Bit-identical to eight_point_solve: every matrix entry sees the same operations on the same operands, only spread over
+// lanes.  Per rotation: the 36 off-diagonal entries are searched by 32 lanes (two entries for lanes 0..12) and reduced with
+// the sequential scan's rule (largest magnitude, first in raster order; NaN never wins); every lane evaluates the rotation;
+// lanes 0..8 update their row's two entries, lane 9 the pivot block, lane 10 records the rotation.  ~550 cycles per
+// rotation instead of ~1,500 for the single thread.
+constexpr int WJ_WARPS = 4;  // hypotheses per block
+struct WarpJacobi {
+  double a[SV_TRI];
+  double rows[8][9];
+  double rc[SV_ROT9], rs[SV_ROT9];
+  double vec[9];
+  unsigned char rpq[SV_ROT9];
+};
+
+__device__ void eight_point_solve_warp(const double2* __restrict__ xi, const double2* __restrict__ xj, const int* __restrict__ idx8, int n,
+                                       WarpJacobi& w, double* __restrict__ E, int lane) {
+  const unsigned FULL = 0xffffffffu;
+  if (lane < 8) {
+    int i = idx8[lane];
+    i = i < 0 ? 0 : (i >= n ? n - 1 : i);
+    const double2 a = xi[i], b = xj[i];
+    const double row[9] = {b.x * a.x, b.x * a.y, b.x, b.y * a.x, b.y * a.y, b.y, a.x, a.y, 1.0};
+#pragma unroll
+    for (int c = 0; c < 9; c++) w.rows[lane][c] = row[c];
+  }
+  __syncwarp();
+  // this lane's packed entries e0 = lane, e1 = lane + 32 (< 45) and their (row, column)
+  int ei[2], ej[2];
+#pragma unroll
+  for (int t = 0; t < 2; t++) {
+    const int e = lane + 32 * t;
+    int i = 0, base = 0;
+    while (i < 8 && e >= base + (9 - i)) {
+      base += 9 - i;
+      i++;
+    }
+    ei[t] = i;
+    ej[t] = i + (e - base);
+  }
+#pragma unroll
+  for (int t = 0; t < 2; t++) {
+    const int e = lane + 32 * t;
+    if (e < SV_TRI) {
+      double g = 0.0;
+      for (int r = 0; r < 8; r++) g += w.rows[r][ei[t]] * w.rows[r][ej[t]];
+      w.a[e] = g;
+    }
+  }
+  __syncwarp();
+  int nrot = 0;
+  for (; nrot < SV_ROT9; nrot++) {
+    double best = -1.0;
+    int bcode = 1, be = 1 << 20;
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+      const int e = lane + 32 * t;
+      if (e < SV_TRI && ei[t] != ej[t]) {
+        double v = fabs(w.a[e]);
+        v = v == v ? v : -1.0;
+        if (v > best) {  // e0 < e1: the earlier entry keeps a tie
+          best = v;
+          bcode = ei[t] * 16 + ej[t];
+          be = e;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(FULL, best, o);
+      const int oc = __shfl_xor_sync(FULL, bcode, o), oe = __shfl_xor_sync(FULL, be, o);
+      if (ov > best || (ov == best && oe < be)) {
+        best = ov;
+        bcode = oc;
+        be = oe;
+      }
+    }
+    if (!(best > 0.0) || best < 1e-12) break;  // big starts at 0 and only a strictly larger entry replaces it
+    const int p = bcode >> 4, q = bcode & 15;
+    const int ipp = tri_idx(p, p), iqq = tri_idx(q, q), ipq = tri_idx(p, q);
+    const double app = w.a[ipp], aqq = w.a[iqq], apq = w.a[ipq];
+    double c, s;
+    half_angle(2.0 * apq, aqq - app, c, s);
+    double u = 0.0, v = 0.0;
+    int ikp = 0, ikq = 0;
+    const bool rowlane = lane < 9 && lane != p && lane != q;
+    if (rowlane) {
+      const int k = lane;
+      ikp = k < p ? tri_idx(k, p) : tri_idx(p, k);
+      ikq = k < q ? tri_idx(k, q) : tri_idx(q, k);
+      u = w.a[ikp];
+      v = w.a[ikq];
+    }
+    __syncwarp();
+    if (rowlane) {
+      w.a[ikp] = c * u - s * v;
+      w.a[ikq] = s * u + c * v;
+    } else if (lane == 9) {
+      // the pivot block sees both updates (rows first, then columns)
+      const double tpp = c * app - s * apq, tpq = c * apq - s * aqq, tqp = s * app + c * apq, tqq = s * apq + c * aqq;
+      w.a[ipp] = c * tpp - s * tpq;
+      w.a[iqq] = s * tqp + c * tqq;
+      w.a[ipq] = 0.0;
+    } else if (lane == 10) {
+      w.rc[nrot] = c;
+      w.rs[nrot] = s;
+      w.rpq[nrot] = (unsigned char)bcode;
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    int m = 0;
+    double bestd = w.a[0];
+    for (int i = 1; i < 9; i++) {
+      const double d = w.a[tri_idx(i, i)];
+      if (d < bestd) {
+        bestd = d;
+        m = i;
+      }
+    }
+    for (int i = 0; i < 9; i++) w.vec[i] = i == m ? 1.0 : 0.0;
+    for (int r = nrot - 1; r >= 0; r--) {
+      const int p = w.rpq[r] >> 4, q = w.rpq[r] & 15;
+      const double c = w.rc[r], s = w.rs[r];
+      const double u = w.vec[p], v = w.vec[q];
+      w.vec[p] = c * u + s * v;
+      w.vec[q] = c * v - s * u;
+    }
+    double E0[9];
+    for (int i = 0; i < 9; i++) E0[i] = w.vec[i];
+    rank2_project(E0, E);
+  }
+  __syncwarp();
+}
+
+// Items: best == nullptr: list[0 .. min(*list_count, max_items)); best != nullptr: the winners of npairs sets.
+__global__ void __launch_bounds__(WJ_WARPS * 32) eight_point_warp_kernel(const double2* __restrict__ xi, const double2* __restrict__ xj,
+                                                                        size_t pt_stride, const int* __restrict__ npts, int n_single,
+                                                                        const int* __restrict__ idx8, int H, const int* __restrict__ list_count,
+                                                                        const int* __restrict__ list, int max_items,
+                                                                        const int* __restrict__ best, int npairs, double* __restrict__ E) {
+  __shared__ WarpJacobi wj[WJ_WARPS];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int total = best ? npairs : *list_count;
+  if (!best && total > max_items) total = max_items;
+  for (int k = blockIdx.x * WJ_WARPS + wid; k < total; k += gridDim.x * WJ_WARPS) {
+    size_t ho;
+    int pair;
+    if (best) {
+      pair = k;
+      const int bh = best[2 * pair];
+      if (bh < 0 || bh >= H) continue;
+      ho = (size_t)pair * H + bh;
+    } else {
+      ho = (size_t)list[k];
+      pair = (int)(ho / (size_t)H);
+    }
+    const int n = npts ? npts[pair] : n_single;
+    if (n < 8) continue;
+    eight_point_solve_warp(xi + (size_t)pair * pt_stride, xj + (size_t)pair * pt_stride, idx8 + ho * 8, n, wj[wid], E + ho * 9, lane);
+  }
+}
+
 // ---- direct null vector: the SCREENING solver of the batched RANSAC stage -----------------------------------------------------
 // eight_point_E asks for the unit vector e minimising ||A e|| (A: 8 x 9, one row per correspondence) and gets it as the
 // eigenvector of the smallest eigenvalue of A^T A from a Jacobi iteration (<= 120 rotations, absolute 1e-12 stop).  For
@@ -438,10 +603,10 @@ __global__ void __launch_bounds__(QR_TPB, 4) eight_point_qr_kernel(const double2
 __global__ void __launch_bounds__(SV_TPB, SV_MINB) eight_point_list_kernel(const double2* __restrict__ xi, const double2* __restrict__ xj,
                                                                     size_t pt_stride, const int* __restrict__ npts, int n_single,
                                                                     const int* __restrict__ idx8, int H, const int* __restrict__ rep_count,
-                                                                    const int* __restrict__ rep_list, double* __restrict__ Eout) {
+                                                                    const int* __restrict__ rep_list, int skip, double* __restrict__ Eout) {
   extern __shared__ double sv_smem[];
   const int total = *rep_count;
-  for (int k = blockIdx.x * SV_TPB + threadIdx.x; k < total; k += gridDim.x * SV_TPB) {
+  for (int k = skip + blockIdx.x * SV_TPB + threadIdx.x; k < total; k += gridDim.x * SV_TPB) {
     const size_t ho = (size_t)rep_list[k];
     const int pair = (int)(ho / (size_t)H);
     const int n = npts ? npts[pair] : n_single;
@@ -450,20 +615,10 @@ __global__ void __launch_bounds__(SV_TPB, SV_MINB) eight_point_list_kernel(const
   }
 }
 
-// The winner of every correspondence set (best[2 * pair] = hypothesis index or -1) solved again by the Jacobi emulation,
-// in place of the screening hypothesis: one thread per set.
-__global__ void __launch_bounds__(SV_TPB, SV_MINB) eight_point_winner_kernel(const double2* __restrict__ xi, const double2* __restrict__ xj,
-                                                                      size_t pt_stride, const int* __restrict__ npts, int n_single,
-                                                                      const int* __restrict__ idx8, int H, const int* __restrict__ best,
-                                                                      int npairs, double* __restrict__ E) {
-  extern __shared__ double sv_smem[];
-  const int pair = blockIdx.x * SV_TPB + threadIdx.x;
-  if (pair >= npairs) return;
-  const int n = npts ? npts[pair] : n_single, bh = best[2 * pair];
-  if (bh < 0 || bh >= H || n < 8) return;
-  const size_t ho = (size_t)pair * H + bh;
-  eight_point_solve<SV_TPB>(xi + (size_t)pair * pt_stride, xj + (size_t)pair * pt_stride, idx8 + ho * 8, n, sv_smem + threadIdx.x,
-                            E + ho * 9);
+__global__ void iota_list_kernel(int* count, int* list, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *count = total;
+  if (i < total) list[i] = i;
 }
 
 // Batched triangulate_dlt (:1477-1516), one thread per track.  Same formulas and order as the host
@@ -611,12 +766,22 @@ int sfm_pose_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size
   return 0;
 }
 
+// Whether a launch of npairs x H hypotheses is counted with the screening solver (solver mode 1).  Up to one wave of the
+// emulation kernel (n_sm x 4 blocks x 128 hypotheses: 75,776 on B200) the emulation for EVERY octet is the faster choice: its
+// time is one thread's latency (~150 us) either way, and the screening path adds the list and winner launches behind it
+// (measured, 2,500 hypotheses x 2,200 points: 0.31 ms against 0.42 ms for the whole solve + score call).
+bool sfm_solver_screens(const sfmgpu_ctx* ctx, int npairs, int H) {
+  if (ctx->solver_mode == 3) return true;  // tests: always
+  return ctx->solver_mode == 1 && (long long)npairs * H > (long long)ctx->n_sm * SV_MINB * SV_TPB;
+}
+
 // Hypotheses for `npairs` correspondence sets in one launch: xi/xj + pair * pt_stride, npts[pair] points (npts may be null:
 // n_single for all), idx8 [npairs][H][8], Eout [npairs][H][9].  screen != 0: the direct null-vector solver (counting only,
 // see eight_point_qr_kernel; the caller re-solves the winners with sfm_eight_point_winners).
 int sfm_eight_point_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, const int* npts, int n_single,
                             int npairs, const int* idx8, int H, double* Eout, int screen) {
   if (npairs <= 0 || H <= 0) return 0;
+  screen = screen && sfm_solver_screens(ctx, npairs, H);
   if (screen) {
     if ((long long)npairs * H > 0x7fffffffll) return sfm_fail(ctx, SFMGPU_E_ARG, "eight_point: %d x %d hypotheses in one launch", npairs, H);
     SFM_TRY(sfm_reserve(ctx, ctx->sv_list, ((size_t)npairs * H + 64) * sizeof(int)));
@@ -629,8 +794,24 @@ int sfm_eight_point_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* x
     const size_t lsmem = (size_t)SV_TRI * SV_TPB * sizeof(double);
     SFM_SMEM_OPTIN(ctx, list_cfg, eight_point_list_kernel, lsmem);
     const long long want = ((long long)npairs * H + SV_TPB - 1) / SV_TPB, cap = (long long)ctx->n_sm * SV_MINB;
+    // a single correspondence set has a few dozen such octets: the first 512 go to the warp-per-hypothesis kernel (latency)
+    const int warp_items = npairs == 1 ? 512 : 0;
+    if (warp_items)
+      SFM_LAUNCH(ctx, eight_point_warp_kernel, warp_items / WJ_WARPS, WJ_WARPS * 32, 0, xi, xj, pt_stride, npts, n_single, idx8, H,
+                 (const int*)rep_count, (const int*)rep_list, warp_items, (const int*)nullptr, 0, Eout);
     SFM_LAUNCH(ctx, eight_point_list_kernel, (unsigned)(want < cap ? want : cap), SV_TPB, lsmem, xi, xj, pt_stride, npts, n_single, idx8, H,
-               (const int*)rep_count, (const int*)rep_list, Eout);
+               (const int*)rep_count, (const int*)rep_list, warp_items, Eout);
+    return 0;
+  }
+  if (screen == 0 && ctx->solver_mode == 2) {  // tests: every octet through the warp-per-hypothesis emulation
+    if ((long long)npairs * H > 0x7fffffffll) return sfm_fail(ctx, SFMGPU_E_ARG, "eight_point: %d x %d hypotheses in one launch", npairs, H);
+    SFM_TRY(sfm_reserve(ctx, ctx->sv_list, ((size_t)npairs * H + 64) * sizeof(int)));
+    int* rep_count = (int*)ctx->sv_list.p;
+    int* rep_list = rep_count + 64;
+    const int total = npairs * H;
+    SFM_LAUNCH(ctx, iota_list_kernel, sfm_cdiv(total, 256), 256, 0, rep_count, rep_list, total);
+    SFM_LAUNCH(ctx, eight_point_warp_kernel, (unsigned)(ctx->n_sm * 8), WJ_WARPS * 32, 0, xi, xj, pt_stride, npts, n_single, idx8, H,
+               (const int*)rep_count, (const int*)rep_list, total, (const int*)nullptr, 0, Eout);
     return 0;
   }
   static const int cfg_id = sfm_next_cfg_id();
@@ -644,10 +825,8 @@ int sfm_eight_point_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* x
 int sfm_eight_point_winners(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, const int* npts, int n_single,
                             int npairs, const int* idx8, int H, const int* best, double* E) {
   if (npairs <= 0 || H <= 0) return 0;
-  static const int cfg_id = sfm_next_cfg_id();
-  const size_t smem = (size_t)SV_TRI * SV_TPB * sizeof(double);
-  SFM_SMEM_OPTIN(ctx, cfg_id, eight_point_winner_kernel, smem);
-  SFM_LAUNCH(ctx, eight_point_winner_kernel, sfm_cdiv(npairs, SV_TPB), SV_TPB, smem, xi, xj, pt_stride, npts, n_single, idx8, H, best, npairs, E);
+  SFM_LAUNCH(ctx, eight_point_warp_kernel, sfm_cdiv(npairs, WJ_WARPS), WJ_WARPS * 32, 0, xi, xj, pt_stride, npts, n_single, idx8, H,
+             (const int*)nullptr, (const int*)nullptr, 0, best, npairs, E);
   return 0;
 }
 
@@ -687,19 +866,53 @@ extern "C" int sfmgpu_triangulate_dlt(sfmgpu_ctx* ctx, const double* K, const do
   return 0;
 }
 
-static int hypotheses_resident(sfmgpu_ctx* ctx, const double* xi_xy, const double* xj_xy, int n, const int32_t* idx8, int H, int screen) {
+// staged: the caller synchronises the stream before it returns, so the points may go through the context's pinned staging
+// area (one memcpy + truly asynchronous copies instead of two staged pageable copies)
+static int hypotheses_resident(sfmgpu_ctx* ctx, const double* xi_xy, const double* xj_xy, int n, const int32_t* idx8, int H, int screen,
+                               bool staged = false) {
+  if (staged && n > 0) {
+    const size_t pb = (size_t)n * 16;
+    SFM_TRY(sfm_pinned(ctx, 2 * pb + 256));
+    memcpy(ctx->pinned, xi_xy, pb);
+    memcpy((char*)ctx->pinned + pb, xj_xy, pb);
+    xi_xy = (const double*)ctx->pinned;
+    xj_xy = (const double*)((char*)ctx->pinned + pb);
+  }
   SFM_TRY(sfmgpu_ransac_upload(ctx, xi_xy, xj_xy, n, nullptr, 0));  // points resident, room for 0 hypotheses
   SFM_TRY(sfm_reserve(ctx, ctx->rs_E, (size_t)(H + 1) * 72));
   SFM_TRY(sfm_reserve(ctx, ctx->rs_counts, (size_t)(H + 1) * 4));
-  SFM_TRY(sfm_reserve(ctx, ctx->rs_idx8, (size_t)(H + 1) * 32));
+  SFM_TRY(sfm_reserve(ctx, ctx->rs_idx8, (size_t)(H + 1) * 32 + 64));
   ctx->rs_H = H;
   ctx->rs_screened = false;
   if (H == 0) return 0;
-  SFM_CUDA(ctx, cudaMemcpyAsync(ctx->rs_idx8.p, idx8, (size_t)H * 32, cudaMemcpyHostToDevice, ctx->stream));
+  if (idx8) {
+    SFM_CUDA(ctx, cudaMemcpyAsync(ctx->rs_idx8.p, idx8, (size_t)H * 32, cudaMemcpyHostToDevice, ctx->stream));
+  } else {  // the reference's seeded sampling on the device; the flag word sits behind the octets
+    SFM_TRY(sfm_sample_octets(ctx, n, H, (int*)ctx->rs_idx8.p, (int*)ctx->rs_idx8.p + (size_t)H * 8 + 8));
+  }
   SFM_TRY(sfm_eight_point_batched(ctx, (const double2*)ctx->rs_xi.p, (const double2*)ctx->rs_xj.p, 0, nullptr, n, 1,
                                   (const int*)ctx->rs_idx8.p, H, (double*)ctx->rs_E.p, screen));
-  ctx->rs_screened = screen != 0;
+  ctx->rs_screened = screen != 0 && sfm_solver_screens(ctx, 1, H);
   return 0;
+}
+
+// (winner, count, sampler flag, -, E of the winner or the zero matrix) in one block: one read-back instead of two round trips
+struct SolveScoreResult {
+  int bh, bn, flag, pad;
+  double E[9];
+};
+
+__global__ void solve_score_pack_kernel(const int* __restrict__ best, const int* __restrict__ flag, const double* __restrict__ E,
+                                        SolveScoreResult* __restrict__ out) {
+  const int i = threadIdx.x;
+  const int bh = best[0];
+  if (i == 0) {
+    out->bh = bh;
+    out->bn = best[1];
+    out->flag = flag ? *flag : 0;
+    out->pad = 0;
+  }
+  if (i < 9) out->E[i] = bh >= 0 ? E[9 * (size_t)bh + i] : 0.0;
 }
 
 extern "C" int sfmgpu_ransac_hypotheses(sfmgpu_ctx* ctx, const double* xi_xy, const double* xj_xy, int n, const int32_t* idx8, int H,
@@ -710,7 +923,7 @@ extern "C" int sfmgpu_ransac_hypotheses(sfmgpu_ctx* ctx, const double* xi_xy, co
   if ((n > 0 && (!xi_xy || !xj_xy)) || (H > 0 && !idx8)) return sfm_fail(ctx, SFMGPU_E_ARG, "ransac_hypotheses: null pointer");
   // the caller wants the hypotheses themselves: the Jacobi emulation for every octet; resident only (E_out == NULL: they
   // are there to be scored): the context's solver mode, the winner is re-solved when scored
-  SFM_TRY(hypotheses_resident(ctx, xi_xy, xj_xy, n, idx8, H, (!E_out && ctx->solver_mode == 1) ? 1 : 0));
+  SFM_TRY(hypotheses_resident(ctx, xi_xy, xj_xy, n, idx8, H, E_out ? 0 : 1));
   if (E_out && H > 0) {
     SFM_CUDA(ctx, cudaMemcpyAsync(E_out, ctx->rs_E.p, (size_t)H * 72, cudaMemcpyDeviceToHost, ctx->stream));
     SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -723,34 +936,33 @@ extern "C" int sfmgpu_ransac_solve_score(sfmgpu_ctx* ctx, const double* xi_xy, c
   SFM_ENTER(ctx);
   if (!ctx || n < 0 || H < 0) return sfm_fail(ctx, SFMGPU_E_ARG, "ransac_solve_score: bad sizes");
   if (n < 1 && H > 0) return sfm_fail(ctx, SFMGPU_E_ARG, "ransac_solve_score: no correspondences");
-  if ((n > 0 && (!xi_xy || !xj_xy)) || (H > 0 && !idx8)) return sfm_fail(ctx, SFMGPU_E_ARG, "ransac_solve_score: null pointer");
-  SFM_TRY(hypotheses_resident(ctx, xi_xy, xj_xy, n, idx8, H, ctx->solver_mode == 1 ? 1 : 0));
-  int bh = -1, bn = 0;
-  SFM_TRY(sfmgpu_ransac_score_resident(ctx, thr, &bh, &bn));
-  if (ctx->rs_screened) {  // the count of the re-solved winner
-    int hb[2];
-    SFM_CUDA(ctx, cudaMemcpyAsync(hb, ctx->rs_best.p, sizeof hb, cudaMemcpyDeviceToHost, ctx->stream));
-    SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    bh = hb[0];
-    bn = hb[1];
-  }
+  if (n > 0 && (!xi_xy || !xj_xy)) return sfm_fail(ctx, SFMGPU_E_ARG, "ransac_solve_score: null pointer");
+  if (!idx8 && H > 0 && n < 1) return sfm_fail(ctx, SFMGPU_E_ARG, "ransac_solve_score: no correspondences to sample from");
+  const size_t pb = (size_t)n * 16, res_off = (2 * pb + 255) & ~(size_t)255;
+  SFM_TRY(sfm_pinned(ctx, res_off + sizeof(SolveScoreResult) + (size_t)n * 4 + 256));  // staging of the points + the results
+  SFM_TRY(hypotheses_resident(ctx, xi_xy, xj_xy, n, idx8, H, 1, true));
+  SFM_TRY(sfmgpu_ransac_score_resident(ctx, thr, nullptr, nullptr));
+  // winner, count (of the re-solved winner when the counts were screened), its E, the sampler's flag: one block, one sync
+  SFM_TRY(sfm_reserve(ctx, ctx->misc, 256));
+  SolveScoreResult* d_res = (SolveScoreResult*)ctx->misc.p;
+  SolveScoreResult* h_res = (SolveScoreResult*)((char*)ctx->pinned + res_off);
+  int* h_inl = (int*)(h_res + 1);
+  SFM_LAUNCH(ctx, solve_score_pack_kernel, 1, 32, 0, (const int*)ctx->rs_best.p,
+             (!idx8 && H > 0) ? (const int*)ctx->rs_idx8.p + (size_t)H * 8 + 8 : (const int*)nullptr, (const double*)ctx->rs_E.p, d_res);
+  SFM_CUDA(ctx, cudaMemcpyAsync(h_res, d_res, sizeof(SolveScoreResult), cudaMemcpyDeviceToHost, ctx->stream));
+  if (best_inl && n > 0) SFM_CUDA(ctx, cudaMemcpyAsync(h_inl, ctx->rs_inl.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h_res->flag) return sfm_fail(ctx, SFMGPU_E_CAPACITY, "ransac_solve_score: the random stream was too short (internal)");
+  const int bh = h_res->bh, bn = h_res->bn;
   if (best_h) *best_h = bh;
   if (best_n) *best_n = bn;
-  if (best_E) {
-    if (bh >= 0) {
-      SFM_CUDA(ctx, cudaMemcpyAsync(best_E, (const double*)ctx->rs_E.p + 9 * (size_t)bh, 72, cudaMemcpyDeviceToHost, ctx->stream));
-    } else {
-      for (int i = 0; i < 9; i++) best_E[i] = 0.0;
-    }
-  }
-  if (best_inl && bh >= 0 && bn > 0)
-    SFM_CUDA(ctx, cudaMemcpyAsync(best_inl, ctx->rs_inl.p, (size_t)bn * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (best_E) memcpy(best_E, h_res->E, sizeof h_res->E);
+  if (best_inl && bh >= 0 && bn > 0) memcpy(best_inl, h_inl, (size_t)bn * 4);
   return 0;
 }
 
 extern "C" int sfmgpu_solver_set_mode(sfmgpu_ctx* ctx, int mode) {
-  if (!ctx || (mode != 0 && mode != 1)) return sfm_fail(ctx, SFMGPU_E_ARG, "solver_set_mode: mode must be 0 or 1");
+  if (!ctx || mode < 0 || mode > 3) return sfm_fail(ctx, SFMGPU_E_ARG, "solver_set_mode: mode must be 0 ... 3");
   ctx->solver_mode = mode;
   return 0;
 }

@@ -212,7 +212,7 @@ int sfm_two_view_stage(sfmgpu_ctx* ctx, sfmgpu_pairs* p, int pair_off, int npair
     SFM_TRY(raw_stream(ctx, tv->raw, tv->raw_n, (long long)H * 8, (double)cap / 4294967296.0));
   }
   const int mp = rc.min_points > 0 ? rc.min_points : 0;
-  const int screen = (!E_host && H > 0 && ctx->solver_mode == 1) ? 1 : 0;  // see solver.cu: eight_point_qr_kernel
+  const int screen = (!E_host && H > 0 && sfm_solver_screens(ctx, chunk, H)) ? 1 : 0;  // see solver.cu: eight_point_qr_kernel
   const double* k = tv->Kinv;
   for (int c0 = 0; c0 < npairs; c0 += chunk) {
     const int pc = npairs - c0 < chunk ? npairs - c0 : chunk, po = pair_off + c0;
@@ -241,6 +241,18 @@ int sfm_two_view_stage(sfmgpu_ctx* ctx, sfmgpu_pairs* p, int pair_off, int npair
 }
 
 bool sfm_two_view_enabled(const sfmgpu_pairs* p) { return p->tv && p->tv->enabled; }
+
+// H index octets of find_E_ransac's seeded sampling (:657-665) for ONE set of n correspondences into d_idx8 [H][8], from the
+// context's resident mt19937(12345) stream; *d_flag (device, 4 bytes, zeroed here) becomes non-zero if the stream was too
+// short (it is sized with a margin: cannot happen, the caller checks).
+int sfm_sample_octets(sfmgpu_ctx* ctx, int n, int H, int* d_idx8, int* d_flag) {
+  if (H <= 0) return 0;
+  const double rej = (double)(4294967296ull % (unsigned long long)n) / 4294967296.0;
+  SFM_TRY(raw_stream(ctx, ctx->rs_raw, ctx->rs_raw_n, (long long)H * 8, rej));
+  SFM_CUDA(ctx, cudaMemsetAsync(d_flag, 0, 4, ctx->stream));
+  SFM_LAUNCH(ctx, tv_sample_kernel, 1, 1024, 0, (const unsigned*)ctx->rs_raw.p, ctx->rs_raw_n, (const int*)nullptr, n, H * 8, d_idx8, d_flag);
+  return 0;
+}
 
 // D2H of the stage's per-pair results for pairs [pair_off, pair_off + npairs) into the registered host outputs, on `s`.
 int sfm_two_view_download(sfmgpu_ctx* ctx, sfmgpu_pairs* p, int pair_off, int npairs, cudaStream_t s) {

@@ -130,12 +130,16 @@ static std::optional<RelPose> find_E_ransac(const Mat33& K, const std::vector<Ve
   const int n = (int)pi.size();
   TwoViewLA la(K);
   la.normalise(pi, pj);
-  // the reference's seeded sampling (:657-665), one continuing stream, re-seeded on every call
-  std::mt19937 rng(12345);
-  std::uniform_int_distribution<int> uni(0, n - 1);
   const int H = iters > 0 ? iters : 0;
-  std::vector<int> idx((size_t)8 * H);
-  for (size_t k = 0; k < idx.size(); k++) idx[k] = uni(rng);
+  // the reference's seeded sampling (:657-665), one continuing stream, re-seeded on every call (host solver; the device
+  // solver path samples on the device: the same octets, sfmgpu_ransac_solve_score with idx8 == NULL)
+  std::vector<int> idx;
+  if (!device_solver()) {
+    std::mt19937 rng(12345);
+    std::uniform_int_distribution<int> uni(0, n - 1);
+    idx.resize((size_t)8 * H);
+    for (size_t k = 0; k < idx.size(); k++) idx[k] = uni(rng);
+  }
   std::vector<double> E(9 * (size_t)H);
   sfmgpu_ctx* ctx = context();
   std::vector<int> inl((size_t)n);
@@ -166,7 +170,7 @@ static std::optional<RelPose> find_E_ransac(const Mat33& K, const std::vector<Ve
     // solver's hypothesis to ~1e-9, not bit for bit): its E, count and inlier list come back
     static_assert(sizeof(int) == sizeof(std::int32_t), "int32 octets");
     double bestE[9];
-    check(ctx, sfmgpu_ransac_solve_score(ctx, la.xi_ptr(), la.xj_ptr(), n, idx.data(), H, thr, &best_h, &best_n, bestE, inl.data()),
+    check(ctx, sfmgpu_ransac_solve_score(ctx, la.xi_ptr(), la.xj_ptr(), n, nullptr, H, thr, &best_h, &best_n, bestE, inl.data()),
           "ransac_solve_score");
     if (best_h >= 0)
       for (int i = 0; i < 9; i++) E[9 * (size_t)best_h + i] = bestE[i];

@@ -141,7 +141,7 @@ def load_library():
         "sfmgpu_global_desc32": (_i, [_vp, _vp, _i, _i, _vp]),
         "sfmgpu_desc_search": (_i, [_vp, _vp, _i, _vp, _vp, C.POINTER(_i), C.POINTER(C.c_float)]),
         "sfmgpu_ransac_hypotheses": (_i, [_vp, _f64p, _f64p, _i, _i32p, _i, _vp]),
-        "sfmgpu_ransac_solve_score": (_i, [_vp, _f64p, _f64p, _i, _i32p, _i, _d, C.POINTER(_i), C.POINTER(_i), _vp, _vp]),
+        "sfmgpu_ransac_solve_score": (_i, [_vp, _f64p, _f64p, _i, _vp, _i, _d, C.POINTER(_i), C.POINTER(_i), _vp, _vp]),
         "sfmgpu_solver_set_mode": (_i, [_vp, _i]),
         "sfmgpu_stage_times_n": (_i, [_vp, C.POINTER(C.c_float), _i]),
         "sfmgpu_pairs_set_ransac": (_i, [_vp, _vp, _vp, C.POINTER(RansacCfg)]),
@@ -218,8 +218,9 @@ class Context:
         self._ck(self.lib.sfmgpu_select_set_mode(self.h, mode))
 
     def solver_set_mode(self, mode):
-        """Device 8-point solver: 1 (default) screening solver for the counts + Jacobi emulation for the winner, 0 the
-        Jacobi emulation for every hypothesis."""
+        """Device 8-point solver: 1 (default) screening solver for the counts of launches beyond one wave + Jacobi emulation
+        for the winner, 0 the Jacobi emulation for every hypothesis, 2 the same through the warp-per-hypothesis kernel,
+        3 screening for every launch (2, 3: tests)."""
         self._ck(self.lib.sfmgpu_solver_set_mode(self.h, mode))
 
     def timer_start(self):
@@ -307,18 +308,24 @@ class Context:
         self._ck(self.lib.sfmgpu_ransac_hypotheses(self.h, xi, xj, len(xi), idx8 if H else np.zeros((1, 8), np.int32), H, _ptr(E)))
         return E[:H] if fetch else None
 
-    def ransac_solve_score(self, xi, xj, idx8, thr):
-        """Solver + scoring loop of find_E_ransac for the octets idx8: (winner, count, winner's E, ascending inlier list);
-        hypotheses and counts stay resident (ransac_download)."""
+    def ransac_solve_score(self, xi, xj, idx8, thr, iters=None):
+        """Solver + scoring loop of find_E_ransac for the octets idx8 (None: `iters` octets from the reference's seeded
+        sampling, drawn on the device): (winner, count, winner's E, ascending inlier list); hypotheses and counts stay
+        resident (ransac_download)."""
         xi = np.ascontiguousarray(xi, np.float64).reshape(-1, 2)
         xj = np.ascontiguousarray(xj, np.float64).reshape(-1, 2)
-        idx8 = np.ascontiguousarray(idx8, np.int32).reshape(-1, 8)
-        H, n = len(idx8), len(xi)
+        n = len(xi)
+        if idx8 is None:
+            H = int(iters)
+        else:
+            idx8 = np.ascontiguousarray(idx8, np.int32).reshape(-1, 8)
+            H = len(idx8)
+            if H == 0:
+                idx8 = np.zeros((1, 8), np.int32)
         bh, bn = _i(-1), _i(0)
         E = np.zeros(9)
         inl = np.full(max(n, 1), -1, np.int32)
-        self._ck(self.lib.sfmgpu_ransac_solve_score(self.h, xi, xj, n, idx8 if H else np.zeros((1, 8), np.int32), H, thr, C.byref(bh),
-                                                    C.byref(bn), _ptr(E), _ptr(inl)))
+        self._ck(self.lib.sfmgpu_ransac_solve_score(self.h, xi, xj, n, _ptr(idx8), H, thr, C.byref(bh), C.byref(bn), _ptr(E), _ptr(inl)))
         return bh.value, bn.value, E, inl[:bn.value].copy()
 
     def ransac_download(self, H, n):

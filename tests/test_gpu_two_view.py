@@ -87,13 +87,13 @@ def test_pairs_ransac_with_reference_hypotheses(ctx, checker, iters, thr, min_in
     assert seen >= ({0, 2} if min_pts == 120 else {1, 2})  # skipped, no pose and pose all occur across the configurations
 
 
-@pytest.mark.parametrize("solver_mode", [1, 0])
+@pytest.mark.parametrize("solver_mode", [3, 1, 0])
 @pytest.mark.parametrize("iters,thr,min_inl,min_pts", [(400, 1e-3, 60, 120), (1000, 2e-3, 80, 120), (4000, 2e-3, 80, 120)])
 def test_pairs_ransac_device_solver(ctx, checker, iters, thr, min_inl, min_pts, solver_mode):
     """Everything on the device (sampler, 8-point solver, scoring, pose): same status, winner count and inlier list as
     find_E_ransac on these scenes; R, t within 1e-6 (the device solver's hypotheses agree to ~1e-9, not bit for bit).
-    solver_mode 1 (default): counts from the screening solver, winner re-solved by the Jacobi emulation; 0: the
-    emulation for every hypothesis."""
+    solver_mode 3: counts from the screening solver, winner re-solved by the Jacobi emulation (what mode 1, the default,
+    does for launches of more than 75,776 hypotheses); 0: the emulation for every hypothesis."""
     K = TEMPLE_K
     scenes = _scenes()
     ctx.solver_set_mode(solver_mode)
@@ -147,7 +147,7 @@ def test_device_solver_hypotheses_close_to_reference(ctx, checker):
 @pytest.mark.parametrize("n,seed,frac,sigma,thr", [(2200, 11, 0.3, 0.3, 1e-3), (1000, 5, 0.5, 1.0, 2e-3), (3000, 9, 0.1, 0.1, 1e-4),
                                                   (640, 6, 0.1, 0.3, 1e-5), (2500, 4, 0.5, 0.3, 2e-3)])
 def test_screening_solver_counts(ctx, checker, n, seed, frac, sigma, thr):
-    """Solver mode 1: the counts of the screening solver (unit null vector of the design matrix by Householder QR) against
+    """Solver mode 3 (= mode 1 for launches beyond one wave): the counts of the screening solver (unit null vector of the design matrix by Householder QR) against
     the reference solver's counts for the same octets.  Octets of eight distinct points: equal counts except where a
     point's error sits within the reference iteration's own error of the threshold (< 0.5 % of the hypotheses, by
     at most a few points); octets with a repeated index have a two-dimensional null space and are left to the Jacobi
@@ -160,7 +160,7 @@ def test_screening_solver_counts(ctx, checker, n, seed, frac, sigma, thr):
     wc, wbh, winl = checker.ransac_score(xi, xj, Eref, thr)
     distinct = np.array([len(set(r)) == 8 for r in idx])
     res, rep_counts = {}, {}
-    for mode in (1, 0):
+    for mode in (3, 0):
         ctx.solver_set_mode(mode)
         try:
             bh, bn, E, inl = ctx.ransac_solve_score(xi, xj, idx, thr)
@@ -174,8 +174,25 @@ def test_screening_solver_counts(ctx, checker, n, seed, frac, sigma, thr):
         d = min(np.abs(E - Eref[wbh]).max(), np.abs(E + Eref[wbh]).max())
         assert d < 1e-7, (mode, d)  # the winner's hypothesis is the emulation's in both modes
         assert diff[distinct].mean() < 0.005 and np.abs(counts - wc)[distinct].max() <= 4, (mode, res[mode])
-    assert np.array_equal(rep_counts[0], rep_counts[1])
-    print(f"counts != reference (distinct octets / max |diff| / repeated-index octets): screening {res[1]}, emulation {res[0]}")
+    assert np.array_equal(rep_counts[0], rep_counts[3])
+    print(f"counts != reference (distinct octets / max |diff| / repeated-index octets): screening {res[3]}, emulation {res[0]}")
+
+
+@pytest.mark.parametrize("n,seed", [(2200, 11), (8, 5), (40, 3)])
+def test_warp_emulation_bit_identical(ctx, checker, n, seed):
+    """The warp-per-hypothesis form of the Jacobi emulation (winners, repeated-index octets of single calls) returns the
+    thread-per-hypothesis kernel's hypotheses bit for bit - octets with repeated indices included (n = 8: all of them)."""
+    pi, pj = two_view_scene(n, seed=seed, outlier_frac=0.2)
+    xi, xj = checker.norm_points(TEMPLE_K, pi), checker.norm_points(TEMPLE_K, pj)
+    _, idx = checker.ransac_hypotheses(xi, xj, 1500)
+    got = {}
+    for mode in (0, 2):
+        ctx.solver_set_mode(mode)
+        try:
+            got[mode] = ctx.ransac_hypotheses(xi, xj, idx)
+        finally:
+            ctx.solver_set_mode(1)
+    assert np.array_equal(got[0].view(np.uint64), got[2].view(np.uint64))
 
 
 def test_solve_score_edge_cases(ctx, checker):
@@ -191,6 +208,24 @@ def test_solve_score_edge_cases(ctx, checker):
     Eref, _ = checker.ransac_hypotheses(xi, xj, 50)
     wc, wbh, winl = checker.ransac_score(xi, xj, Eref, 1e-3)
     assert bh == wbh and np.array_equal(inl, winl)
+    # octets sampled on the device (idx8 == NULL): the same call
+    bh2, bn2, E2, inl2 = ctx.ransac_solve_score(xi, xj, None, 1e-3, iters=50)
+    assert bh2 == bh and bn2 == bn and np.array_equal(E2, E) and np.array_equal(inl2, inl)
+
+
+@pytest.mark.parametrize("n,H", [(2200, 2500), (150, 4000), (9, 300)])
+def test_solve_score_device_sampling(ctx, checker, n, H):
+    """sfmgpu_ransac_solve_score with idx8 == NULL samples the reference's octets itself (:657-665): same winner, count,
+    hypothesis and inlier list as with the reference's octets passed in."""
+    pi, pj = two_view_scene(n, seed=n, outlier_frac=0.3)
+    xi, xj = checker.norm_points(TEMPLE_K, pi), checker.norm_points(TEMPLE_K, pj)
+    _, idx = checker.ransac_hypotheses(xi, xj, H)
+    a = ctx.ransac_solve_score(xi, xj, idx, 1e-3)
+    b = ctx.ransac_solve_score(xi, xj, None, 1e-3, iters=H)
+    assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    Eref, _ = checker.ransac_hypotheses(xi, xj, H)
+    wc, wbh, winl = checker.ransac_score(xi, xj, Eref, 1e-3)
+    assert b[0] == wbh and np.array_equal(b[3], winl)
 
 
 @pytest.mark.parametrize("streaming", [False, True])
