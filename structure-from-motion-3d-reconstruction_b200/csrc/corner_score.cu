@@ -460,8 +460,6 @@ __device__ __noinline__ void walk_drain(uint4* queue, int& qn, double& wmax, dou
     for (int k = 0; k < PER; k++) {
       if (cm[k] & (1u << lane)) {
         const unsigned slot = base + __popc(cm[k] & ((1u << lane) - 1u));
-        const unsigned x = pos[k] & 0xFFFFu, y = pos[k] >> 16;
-        atomicOr(wv.bitmap + (size_t)fr * wv.words_per_frame + (size_t)y * wv.wpr + (x >> 5), 1u << (x & 31));
         if (slot < (unsigned)wv.cand_cap) {
           wv.tmp_idx[lb_off + slot] = pos[k];
           wv.tmp_key[lb_off + slot] = (unsigned long long)__double_as_longlong(0.125 * u[k]);
@@ -491,7 +489,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_MINB) score_walk_kernel(cons
   // Screened pixels (FP32 estimate within its error of the provisional threshold: a few percent) are not evaluated where
   // they are found - one lane with a hit would drag the whole warp through the FP64 expression - but queued with their
   // exact (integer-valued) sums and evaluated DENSELY, 32 at a time; survivors get their list slots with one global atomic
-  // per drain and mark the candidate bitmap (zeroed before the launch) with a fire-and-forget atomicOr.
+  // per drain.  (The candidate bitmap is not written here: only the raster-order paths need it and build it from the list.)
   uint4* queue = reinterpret_cast<uint4*>(wbase + WK_RING * sizeof(float4));  // (y << 16 | x | border << 31, a, b, c as float bits)
   int qn = 0;
   double wmax = 0.0;      // this warp's exact maximum so far (lane-local until published)
@@ -750,10 +748,21 @@ __global__ void rescue_mark_kernel(CornerWorkView wv, int count) {
   wv.rescue_list[atomicAdd(wv.rescue_count, 1)] = fr;
 }
 
-// Provisional list -> final list, for the paths that do not run the radix sort (which does the same in its first sweep):
-// keeps the entries that reach the final threshold (dense sort words (order code << 32 | slot) in pk_a, count in nfinal)
-// and clears the candidate-bitmap bit of every other entry (the raster ranks need the exact bitmap).
-// flagged_only: only frames the selection flagged (status 3), and only the bitmap is cleaned (their sort words exist).
+// The raster-order paths (exact emulation of a flagged frame, candidate-list API, select mode 1) need the candidate bitmap.
+// Frames with an exact list got it from the tile kernel; for a provisional list (walk-down pass, which writes no bitmap) it
+// is built here from the list entries that reach the FINAL threshold: cleared by bitmap_clear_kernel, set below.
+// flagged_only: only frames the selection flagged (status 3).
+__global__ void __launch_bounds__(256) bitmap_clear_kernel(CornerWorkView wv, int flagged_only) {
+  const int fr = blockIdx.y;
+  if (wv.exact_list[fr]) return;
+  if (flagged_only && wv.status[fr] != 3) return;
+  unsigned* bm = wv.bitmap + (size_t)fr * wv.words_per_frame;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < wv.words_per_frame; i += (size_t)gridDim.x * blockDim.x) bm[i] = 0u;
+}
+
+// Provisional list -> final list: sets the candidate-bitmap bit of every entry that reaches the final threshold and, for the
+// paths that do not run the selection's own sweep (flagged_only == 0), produces the final count and the sort words of
+// the radix path (order code << 32 | slot in pk_a, count in nfinal).
 __global__ void __launch_bounds__(256) candidate_finalize_kernel(CornerWorkView wv, double quality, int flagged_only) {
   const int fr = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
   if (wv.exact_list[fr]) return;
@@ -774,9 +783,9 @@ __global__ void __launch_bounds__(256) candidate_finalize_kernel(CornerWorkView 
     if (e < nprov) {
       k = wv.tmp_key[cb + e];
       keep = __longlong_as_double((long long)k) >= thr;  // s >= thr (:282)
-      if (!keep) {
+      if (keep) {
         const unsigned yx = wv.tmp_idx[cb + e], x = yx & 0xFFFFu, y = yx >> 16;
-        atomicAnd(wv.bitmap + wb + (size_t)y * wv.wpr + (x >> 5), ~(1u << (x & 31)));
+        atomicOr(wv.bitmap + wb + (size_t)y * wv.wpr + (x >> 5), 1u << (x & 31));
       }
     }
     const unsigned m = __ballot_sync(0xffffffffu, keep && !flagged_only);
@@ -865,6 +874,7 @@ size_t sfm_corner_work_bytes(int w, int h, int nframes, int cand_cap) {
 int sfm_corner_raster_order(sfmgpu_ctx* ctx, int count, const CornerWorkView& wv, double quality, int only_flagged) {
   // provisional lists (fused score pass): drop the surplus bits from the candidate bitmap; without the radix sort
   // (only_flagged == 0) also produce the final count and sort words
+  SFM_LAUNCH(ctx, bitmap_clear_kernel, dim3(32, count), 256, 0, wv, only_flagged);
   SFM_LAUNCH(ctx, candidate_finalize_kernel, dim3(32, count), 256, 0, wv, quality, only_flagged);
   SFM_LAUNCH(ctx, bitmap_scan_kernel, count, 1024, 0, wv, only_flagged);
   SFM_LAUNCH(ctx, order_kernel, dim3(16, count), 256, 0, wv, quality, only_flagged);
@@ -903,7 +913,6 @@ int sfm_corner_candidates_batch(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int fir
       static const int walk_id = sfm_next_cfg_id();
       const size_t wsm = (size_t)WK_WARPS * WK_SMEM_WARP;
       SFM_SMEM_OPTIN(ctx, walk_id, score_walk_kernel, wsm);
-      SFM_CUDA(ctx, cudaMemsetAsync(wv.bitmap, 0, sizeof(unsigned) * wv.words_per_frame * count, ctx->stream));
       SFM_LAUNCH(ctx, score_walk_kernel, dim3(sfm_cdiv(f->w, WK_WARPS * WK_STRIP), sfm_cdiv(f->h, seg_rows), count), WK_WARPS * 32, wsm,
                  f->lvl[0], f->w, f->h, f->pitch[0], f->fstride[0], first, wv, quality, seg_rows);
     }
