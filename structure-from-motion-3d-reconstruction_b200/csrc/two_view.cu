@@ -40,7 +40,9 @@ struct TwoViewState {
 
 namespace {
 
-constexpr int TV_CHUNK = 256;  // pairs per launch set: bounds the scratch (256 x 4000 hypotheses: 74 MB of E)
+constexpr int TV_CHUNK = 1024;  // pairs per launch set: bounds the scratch (1024 x 4000 hypotheses: 295 MB of E, 131 MB of octets).
+                                // The small kernels of a set (sampler, repeated-index and winner solves, argmax, mask, pose) are
+                                // latency-bound, ~0.6 ms per set: 256 pairs per set cost C3 (1999 pairs) 8 x that, C2 4 x
 
 __global__ void __launch_bounds__(256) tv_normalize_kernel(const double2* __restrict__ li, const double2* __restrict__ lj,
                                                           const int* __restrict__ nkept, int cap, int min_points, double k0, double k1,
