@@ -538,7 +538,7 @@ int sfmgpu_pair_frontend_host(sfmgpu_ctx* ctx, sfmgpu_frames* f, const uint8_t* 
   SFM_CUDA(ctx, cudaMemsetAsync(out->totals, 0, 64, ctx->stream));
   if (nframes == 0) return 0;
   SFM_TRY(pipe_streams(ctx));
-  // default: about 100 frames, at least 8 chunks for short sequences, at most 20 for long ones.  Smaller chunks shorten the
+  // default: about 100 frames (50 for large frames), at least 8 chunks for short sequences, at most 20 (40) for long ones.  Smaller chunks shorten the
   // pipeline fill (the first upload and the last chunk's compute are not overlapped), too small ones under-fill the
   // one-block-per-frame kernels.  Measured end to end: C2 (1000 x 1080p) chunks of 84-125 frames 43.0 ms, 167: 44.1, 250: 46.3,
   // 50: 47.8; C3 with the RANSAC stage (2000 x 4K) 50: 372 ms, 100: 358, 150: 385, 200: 390.  (Tried and dropped: halving the
@@ -547,9 +547,14 @@ int sfmgpu_pair_frontend_host(sfmgpu_ctx* ctx, sfmgpu_frames* f, const uint8_t* 
   // uploads ran at 37 instead of 54 GB/s.)
   int chunk = chunk_frames;
   if (chunk <= 0) {
-    const int by8 = (nframes + 7) / 8, by20 = (nframes + 19) / 20;
-    chunk = by8 < 96 ? by8 : 96;
-    if (chunk < by20) chunk = by20;
+    // what is left behind the last upload is the compute of the last chunk, which grows with the frame size: about 100 frames
+    // up to 4 Mpixel, about 50 above (C3 with the uploads back to back on the copy stream: 100 frames 315 ms, 64: 314, 50: 309,
+    // 40: 311; C2: 100-125 frames 47.8 ms, 50: 52.6, 32: 64.1)
+    const bool big = (size_t)f->w * f->h > 4000000u;
+    const int base = big ? 48 : 96, most = big ? 40 : 20;
+    const int by8 = (nframes + 7) / 8, bym = (nframes + most - 1) / most;
+    chunk = by8 < base ? by8 : base;
+    if (chunk < bym) chunk = bym;
   }
   if (chunk < 2) chunk = 2;
   if (chunk > 1024) chunk = 1024;
@@ -572,16 +577,17 @@ int sfmgpu_pair_frontend_host(sfmgpu_ctx* ctx, sfmgpu_frames* f, const uint8_t* 
                                     f->w, (size_t)f->h * (b - a), cudaMemcpyDefault, ctx->copy_stream));
     cudaEvent_t up = p.next();
     if (!up) return sfm_fail(ctx, SFMGPU_E_CUDA, "pair_frontend_host: cudaEventCreate failed");
-    {
-      StageScope sc(ctx, ctx->copy_stream);  // the pyramid of a chunk is built right behind its upload
-      SFM_TRY(sfmgpu_pyramid_build(ctx, f, a, b - a));
-      SFM_CUDA(ctx, cudaEventRecord(up, ctx->stream));
-    }
+    // The copy stream carries NOTHING but the uploads, back to back: the call is bound by them.  The chunk's pyramid is built
+    // on the score stream behind the upload's event (on the copy stream it sat between two uploads and, waiting for SMs
+    // behind the running KLT / RANSAC kernels, kept the copy engine idle ~0.35 ms per chunk).
+    SFM_CUDA(ctx, cudaEventRecord(up, ctx->copy_stream));
+    SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, up, 0));
+    SFM_TRY(sfmgpu_pyramid_build(ctx, f, a, b - a));
     // pairs whose second frame arrived with this chunk
     const int P0 = a > 0 ? a - 1 : 0, P1 = b - 1;
     if (P1 <= P0) continue;
     cudaEvent_t done = nullptr;
-    SFM_TRY(pipe_chunk(p, f, P0, P0, P1 - P0, cfg, out, up, &done));
+    SFM_TRY(pipe_chunk(p, f, P0, P0, P1 - P0, cfg, out, nullptr, &done));
     SFM_CUDA(ctx, cudaStreamWaitEvent(ctx->back_stream, done, 0));
     const size_t np_ = (size_t)(P1 - P0), o = (size_t)P0;
     if (li_xy)
