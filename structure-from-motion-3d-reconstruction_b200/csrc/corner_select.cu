@@ -918,11 +918,13 @@ constexpr int BK_ALIVE = BK_THREADS;            // survivors resolved per greedy
 constexpr int BK_MAXRUN = 64;
 constexpr unsigned BK_YX = 0x3FFFFFFFu;
 static_assert((BK_T & (BK_T - 1)) == 0 && BK_T >= BK_PIECE, "the bitonic sort pads a gather to a power of two inside sv[]");
-static_assert(BK_NB % BK_THREADS == 0, "bucket starts: BK_NB / BK_THREADS counters per thread");
+static_assert(BK_NB % BK_THREADS == 0 || BK_NB < BK_THREADS, "bucket starts: BK_NB / BK_THREADS counters per thread");
 // Measured (select stage, ms per 999 1080p frames / per 399 4K frames): buckets 2048: 3.39 / 6.71, 1024: 3.08 / 6.41 (T = 4096),
 // 512: 2.65 / 6.09, 256: 2.52 / 5.81; T = 2048 with 256 buckets 2.42 / 6.09, T = 1024: 2.71 / 6.74.  Fewer buckets: the scatter
 // writes coalesce better and the walk has fewer steps; a bucket is then often larger than a gather, which only matters if its
-// UNBLOCKED words exceed it (the dense buckets lie near the threshold, where almost everything is blocked).
+// UNBLOCKED words exceed it (the dense buckets lie near the threshold, where almost everything is blocked).  Below 256 buckets that
+// starts to happen on 4K frames (128 buckets: 2.36 / 5.61 with T = 4096 but 31 ms with T = 2048; 64 buckets: 31 ms; 32: 51 ms -
+// the overflowing frames go through the exact emulation), so 256 keeps a factor of two of margin.
 
 struct BucketSmem {
   __align__(16) unsigned long long sv[BK_T];
@@ -1060,19 +1062,19 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_select_kernel(CornerWork
   }
   // bucket starts
   {
-    constexpr int PER = BK_NB / BK_THREADS;
+    constexpr int PER = BK_NB >= BK_THREADS ? BK_NB / BK_THREADS : 1;
     unsigned c[PER];
     int s = 0;
 #pragma unroll
     for (int j = 0; j < PER; j++) {
-      c[j] = sm.cur[tid * PER + j];
+      c[j] = tid * PER + j < BK_NB ? sm.cur[tid * PER + j] : 0u;
       s += (int)c[j];
     }
     int tot;
     unsigned run = (unsigned)bk_block_scan(sm, s, tot);
 #pragma unroll
     for (int j = 0; j < PER; j++) {
-      sm.cur[tid * PER + j] = run;
+      if (tid * PER + j < BK_NB) sm.cur[tid * PER + j] = run;
       run += c[j];
     }
   }
