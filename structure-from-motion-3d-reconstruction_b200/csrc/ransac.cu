@@ -171,6 +171,8 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_count_kernel(const double2*
           hy.e[0] = q0.x; hy.e[1] = q0.y; hy.e[2] = q0.z; hy.e[3] = q0.w;
           hy.e[4] = q1.x; hy.e[5] = q1.y; hy.e[6] = q1.z; hy.e[7] = q1.w;
           hy.e[8] = q2.x; hy.c1 = q2.y; hy.c2 = q2.z; hy.cq = q2.w;
+          // (Tried and dropped: the denominator chain and the residual pair as scalar FFMAs - an FFMA2 holds the FP32 pipe ~2.4
+          // cycles against 2 x 1 for two FFMAs, and issue slots are free at 62 % - 838 vs 834 G hyp*pts/s on C4: noise.)
           // the thread's points two at a time: FFMA2 / FMUL2 / FADD2 (sm_100a packed FP32, one issue slot for two points'
           // worth of work; a scalar coefficient is a broadcast operand).  Every half is the correctly rounded FP32 operation
           // the bound derivation assumes.
