@@ -23,12 +23,21 @@
 
 namespace {
 
-constexpr int RS_THREADS = 256;
+#ifndef RS_THREADS_V
+#define RS_THREADS_V 256
+#endif
+constexpr int RS_THREADS = RS_THREADS_V;
 #ifndef RS_PTS_V
 #define RS_PTS_V 2
 #endif
 constexpr int RS_PTS = RS_PTS_V;  // points per thread, packed two by two (FFMA2)
-constexpr int RS_HCHUNK = 64;    // hypotheses staged per block iteration
+#ifndef RS_HCHUNK_V
+#define RS_HCHUNK_V 64
+#endif
+constexpr int RS_HCHUNK = RS_HCHUNK_V;    // hypotheses staged per block iteration
+// (Measured, threads x chunk: RANSAC stage per 999 C2 pairs / per 399 C3 pairs / C4 rate: 256 x 64: 9.93 ms / 14.53 ms / 834 G;
+//  128 x 128: 9.69 / 14.02 / 806; 128 x 64: 9.72 / 14.11 / 810; 256 x 128: 9.84 / 14.34 / 848; 256 x 32: 10.12 / 14.82 / 839;
+//  512 x 64: 10.89 / 15.48 / 816 - within 4 % of each other.)
 
 __device__ __forceinline__ float2 B2(float s) { return make_float2(s, s); }  // scalar broadcast operand of a packed instruction
 
