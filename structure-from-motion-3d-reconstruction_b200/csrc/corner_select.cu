@@ -888,7 +888,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(CornerWorkView wv, int
 // list is NOT sorted as a whole: one block per frame
 //   (1) sweeps the unordered list once: entries that reach the final threshold become words (order code << 30 | y << 15 | x,
 //       order code = up to 34 leading bits of the score's distance below the frame maximum: ascending word = descending
-//       score) and are counted per MSD bucket (top 8 bits of the code);
+//       score) and are counted per MSD bucket (top 7 bits of the code);
 //   (2) scatters the words into bucket order (one pass, unordered inside a bucket);
 //   (3) walks the buckets from the best score down in gathers of <= 4096 words: a word whose pixel is already blocked is
 //       dropped at once (order-independent, exact); the SURVIVORS of the gather - all of them early on, a few per cent
@@ -901,11 +901,11 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_kernel(CornerWorkView wv, int
 // Equal order codes among the survivors of a gather (rare with 34 bits): the members' exact scores are recomputed from
 // the image (same expression as the score kernels) and the run is ordered by them; IDENTICAL scores are flagged and
 // handled by the observable-tie rule: if two members of a tie are still unblocked when the rounds reach
-// them, or a run is longer than 64, or a single bucket's survivors do not fit, the frame gets status 3 and is redone by
-// the exact emulation (select_kernel mode 3).
+// them, or a run is longer than 64, or a single SUB-bucket's survivors (2^-15 of the score range) do not fit, the frame gets
+// status 3 and is redone by the exact emulation (select_kernel mode 3).
 constexpr int BK_THREADS = 256, BK_WARPS = BK_THREADS / 32;
 #ifndef BK_NB_BITS_V
-#define BK_NB_BITS_V 8
+#define BK_NB_BITS_V 7
 #endif
 constexpr int BK_NB_BITS = BK_NB_BITS_V, BK_NB = 1 << BK_NB_BITS;
 constexpr int BK_CODE_BITS = 34;
@@ -919,12 +919,13 @@ constexpr int BK_MAXRUN = 64;
 constexpr unsigned BK_YX = 0x3FFFFFFFu;
 static_assert((BK_T & (BK_T - 1)) == 0 && BK_T >= BK_PIECE, "the bitonic sort pads a gather to a power of two inside sv[]");
 static_assert(BK_NB % BK_THREADS == 0 || BK_NB < BK_THREADS, "bucket starts: BK_NB / BK_THREADS counters per thread");
-// Measured (select stage, ms per 999 1080p frames / per 399 4K frames): buckets 2048: 3.39 / 6.71, 1024: 3.08 / 6.41 (T = 4096),
-// 512: 2.65 / 6.09, 256: 2.52 / 5.81; T = 2048 with 256 buckets 2.42 / 6.09, T = 1024: 2.71 / 6.74.  Fewer buckets: the scatter
-// writes coalesce better and the walk has fewer steps; a bucket is then often larger than a gather, which only matters if its
-// UNBLOCKED words exceed it (the dense buckets lie near the threshold, where almost everything is blocked).  Below 256 buckets that
-// starts to happen on 4K frames (128 buckets: 2.36 / 5.61 with T = 4096 but 31 ms with T = 2048; 64 buckets: 31 ms; 32: 51 ms -
-// the overflowing frames go through the exact emulation), so 256 keeps a factor of two of margin.
+// Measured (select stage, ms per 999 1080p frames / per 399 4K frames, T = 4096): buckets 2048: 3.39 / 6.71, 1024: 3.08 / 6.41,
+// 512: 2.65 / 6.09, 256: 2.57 / 5.75, 128: 2.37 / 5.53, 64: 2.26 / 5.34, 32: 2.21 / 39, 16: 2.55 / 40 (T = 2048: 64 buckets
+// 2.19 / 5.43).  Fewer buckets: the scatter's writes coalesce better and the walk has fewer steps; a bucket is then often larger
+// than a gather, which is fine while its UNBLOCKED words fit (the dense buckets lie near the threshold, where almost everything
+// is blocked); a bucket whose unblocked words do not fit is walked in runs of its 256 sub-buckets, re-read once per run - cheap
+// for the occasional bucket, quadratic when most buckets need it (32 buckets on 4K frames).  128 buckets keep a factor of four
+// of bucket size between the default and that regime.
 
 struct BucketSmem {
   __align__(16) unsigned long long sv[BK_T];
@@ -934,8 +935,9 @@ struct BucketSmem {
   unsigned short accl[BK_ALIVE];
   unsigned char tf[BK_T];  // bit 0: identical score as the predecessor, bit 1: member of a group of >= 3
   int wcnt[BK_WARPS];
+  unsigned subh[256];  // unblocked words per sub-bucket (next 8 code bits) of a bucket whose unblocked words exceed a gather
   unsigned nkeep, tgt;
-  int accepted, cut, tiehit, eqrun, bi;
+  int accepted, cut, tiehit, eqrun, bi, sub_lo, sub_hi;
 };
 
 __device__ __forceinline__ int bk_block_scan(BucketSmem& sm, int c, int& total) {
@@ -1125,26 +1127,49 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_select_kernel(CornerWork
   const bool suppress = wv.cell > 0;
   unsigned pos = 0;  // words [0, pos) are done (block-uniform)
   int bi = 0;        // first bucket that is not done
+  // A bucket whose UNBLOCKED words exceed a gather is walked in runs of its sub-buckets (the next 8 bits of the order code):
+  // sub_next >= 0 while that is going on; [pos, tgt) is then that bucket, re-read once per run.
+  const int sbits = bshift < 8 ? bshift : 8, sshift = bshift - sbits;
+  const unsigned smask = (1u << sbits) - 1u;
+  int sub_next = -1;
+  unsigned tgt = 0;
   while (pos < n && sm.accepted < cap_out && !sm.tiehit) {
-    // as many whole buckets as certainly fit; a bucket that does not fit by itself is filtered anyway and must fit afterwards
-    if (warp == 0) {  // 32 buckets per step
-      int b2 = bi;
-      while (b2 < BK_NB) {
-        const bool fits = b2 + lane < BK_NB && sm.cur[b2 + lane] - pos <= (unsigned)BK_T;
-        const int run = __ffs(~__ballot_sync(0xffffffffu, fits)) - 1;  // leading buckets that fit (32: all of them)
-        b2 += run < 0 ? 32 : run;
-        if (run >= 0 && run < 32) break;
+    unsigned s_lo = 0, s_hi = smask;
+    if (sub_next < 0) {
+      // as many whole buckets as certainly fit; a bucket that does not fit by itself is filtered anyway (see below)
+      if (warp == 0) {  // 32 buckets per step
+        int b2 = bi;
+        while (b2 < BK_NB) {
+          const bool fits = b2 + lane < BK_NB && sm.cur[b2 + lane] - pos <= (unsigned)BK_T;
+          const int run = __ffs(~__ballot_sync(0xffffffffu, fits)) - 1;  // leading buckets that fit (32: all of them)
+          b2 += run < 0 ? 32 : run;
+          if (run >= 0 && run < 32) break;
+        }
+        if (b2 > BK_NB) b2 = BK_NB;
+        if (b2 == bi) b2++;  // the next bucket does not fit by itself
+        if (lane == 0) {
+          sm.bi = b2;
+          sm.tgt = sm.cur[b2 - 1];
+        }
       }
-      if (b2 > BK_NB) b2 = BK_NB;
-      if (b2 == bi) b2++;  // the next bucket does not fit by itself
-      if (lane == 0) {
-        sm.bi = b2;
-        sm.tgt = sm.cur[b2 - 1];
+      __syncthreads();
+      bi = sm.bi;
+      tgt = sm.tgt;
+    } else {
+      // the next run of sub-buckets whose (earlier counted, since then only shrunk) unblocked words fit
+      if (tid == 0) {
+        int hi = sub_next;
+        unsigned sum = sm.subh[hi];
+        while (hi + 1 <= (int)smask && sum + sm.subh[hi + 1] <= (unsigned)BK_T) sum += sm.subh[++hi];
+        sm.sub_lo = sub_next;
+        sm.sub_hi = hi;
+        if (sm.subh[sub_next] > (unsigned)BK_T) sm.tiehit = 1;  // > BK_T unblocked words within 2^-16 of the score range
       }
+      __syncthreads();
+      if (sm.tiehit) break;
+      s_lo = (unsigned)sm.sub_lo;
+      s_hi = (unsigned)sm.sub_hi;
     }
-    __syncthreads();
-    bi = sm.bi;
-    const unsigned tgt = sm.tgt;
     int nsv = 0;
     bool overflow = false;
     for (unsigned p0 = pos; p0 < tgt; p0 += BK_PIECE) {
@@ -1162,8 +1187,10 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_select_kernel(CornerWork
       }
       unsigned am = 0;
 #pragma unroll
-      for (int e = 0; e < BK_EPT; e++)
-        if (p0 + tid * BK_EPT + e < tgt && !((bw[e] >> ((unsigned)v[e] & 31u)) & 1u)) am |= 1u << e;
+      for (int e = 0; e < BK_EPT; e++) {
+        const unsigned sub = (unsigned)(v[e] >> (30 + sshift)) & smask;
+        if (p0 + tid * BK_EPT + e < tgt && !((bw[e] >> ((unsigned)v[e] & 31u)) & 1u) && sub >= s_lo && sub <= s_hi) am |= 1u << e;
+      }
       int tot;
       int r = nsv + bk_block_scan(sm, __popc(am), tot);
       if (nsv + tot > BK_T) {  // block-uniform
@@ -1175,11 +1202,38 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_select_kernel(CornerWork
         if (am & (1u << e)) sm.sv[r++] = v[e];
       nsv += tot;
     }
-    pos = tgt;
     if (overflow) {
-      if (tid == 0) sm.tiehit = 1;
+      // only a single bucket can overflow (several are gathered only if all their words fit): count its unblocked words per
+      // sub-bucket and walk it in runs of sub-buckets.  No sub-bits left, or already in that mode (the counts bound every
+      // run): the exact emulation takes the frame.
+      if (sub_next >= 0 || sbits == 0) {
+        if (tid == 0) sm.tiehit = 1;
+        __syncthreads();
+        break;
+      }
+      for (int i = tid; i < 256; i += BK_THREADS) sm.subh[i] = 0;
       __syncthreads();
-      break;
+      for (unsigned p0 = pos; p0 < tgt; p0 += BK_THREADS) {
+        const unsigned i = p0 + tid;
+        if (i < tgt) {
+          const unsigned long long v = __ldcg(B + i);
+          const unsigned x = (unsigned)v & 0x7FFFu, y = ((unsigned)v >> 15) & 0x7FFFu;
+          const unsigned bwd = suppress ? __ldcg(blocked + (size_t)y * wv.wpr + (x >> 5)) : 0u;
+          if (!((bwd >> (x & 31u)) & 1u)) atomicAdd(&sm.subh[(unsigned)(v >> (30 + sshift)) & smask], 1u);
+        }
+      }
+      __syncthreads();
+      sub_next = 0;
+      continue;
+    }
+    if (sub_next >= 0) {
+      sub_next = (int)s_hi + 1;
+      if (sub_next > (int)smask) {  // the bucket is done
+        sub_next = -1;
+        pos = tgt;
+      }
+    } else {
+      pos = tgt;
     }
     if (nsv == 0) {
       __syncthreads();
