@@ -986,7 +986,7 @@ __device__ double bk_exact_score(const uint8_t* __restrict__ im, int pitch, int 
 
 __global__ void __launch_bounds__(BK_THREADS, 4) bucket_select_kernel(CornerWorkView wv, const uint8_t* __restrict__ img, int pitch,
                                                                       size_t fstride, int first, int w, int h, int max_corners,
-                                                                      int min_dist, double quality, int code_bits,
+                                                                      int min_dist, double quality, int code_bits, int gather_cap,
                                                                       double2* __restrict__ out_xy, int* __restrict__ out_n) {
   extern __shared__ __align__(16) unsigned char bk_raw[];
   BucketSmem& sm = *reinterpret_cast<BucketSmem*>(bk_raw);
@@ -1140,7 +1140,7 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_select_kernel(CornerWork
       if (warp == 0) {  // 32 buckets per step
         int b2 = bi;
         while (b2 < BK_NB) {
-          const bool fits = b2 + lane < BK_NB && sm.cur[b2 + lane] - pos <= (unsigned)BK_T;
+          const bool fits = b2 + lane < BK_NB && sm.cur[b2 + lane] - pos <= (unsigned)gather_cap;
           const int run = __ffs(~__ballot_sync(0xffffffffu, fits)) - 1;  // leading buckets that fit (32: all of them)
           b2 += run < 0 ? 32 : run;
           if (run >= 0 && run < 32) break;
@@ -1160,10 +1160,10 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_select_kernel(CornerWork
       if (tid == 0) {
         int hi = sub_next;
         unsigned sum = sm.subh[hi];
-        while (hi + 1 <= (int)smask && sum + sm.subh[hi + 1] <= (unsigned)BK_T) sum += sm.subh[++hi];
+        while (hi + 1 <= (int)smask && sum + sm.subh[hi + 1] <= (unsigned)gather_cap) sum += sm.subh[++hi];
         sm.sub_lo = sub_next;
         sm.sub_hi = hi;
-        if (sm.subh[sub_next] > (unsigned)BK_T) sm.tiehit = 1;  // > BK_T unblocked words within 2^-16 of the score range
+        if (sm.subh[sub_next] > (unsigned)gather_cap) sm.tiehit = 1;  // more unblocked words than a gather within 2^-15 of the score range
       }
       __syncthreads();
       if (sm.tiehit) break;
@@ -1193,7 +1193,7 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_select_kernel(CornerWork
       }
       int tot;
       int r = nsv + bk_block_scan(sm, __popc(am), tot);
-      if (nsv + tot > BK_T) {  // block-uniform
+      if (nsv + tot > gather_cap) {  // block-uniform
         overflow = true;
         break;
       }
@@ -1687,9 +1687,11 @@ int sfm_corners_select_stage(sfmgpu_ctx* ctx, const sfmgpu_frames* f, int first,
       SFM_LAUNCH(ctx, (radix_sort_frame_kernel<1024, 4>), count, 1024, sizeof(RadixSmem<1024>), wv, quality);
     SFM_LAUNCH(ctx, nms_kernel, count, NMS_THREADS, 0, wv, f->w, f->h, max_corners, min_dist, out_xy, out_n);
   } else {
-    const int code_bits = ctx->select_mode >= 12 ? ctx->select_mode : BK_CODE_BITS;  // tests: short codes make equal codes common
+    // tests: short codes make equal codes common (modes 12..34); small gathers make the sub-bucket walk common (modes 1000 + g)
+    const int code_bits = (ctx->select_mode >= 12 && ctx->select_mode <= BK_CODE_BITS) ? ctx->select_mode : BK_CODE_BITS;
+    const int gather_cap = ctx->select_mode >= 1000 ? ctx->select_mode - 1000 : BK_T;
     SFM_LAUNCH(ctx, bucket_select_kernel, count, BK_THREADS, sizeof(BucketSmem), wv, f->lvl[0], f->pitch[0], f->fstride[0], first, f->w, f->h,
-               max_corners, min_dist, quality, code_bits, out_xy, out_n);
+               max_corners, min_dist, quality, code_bits, gather_cap, out_xy, out_n);
   }
   // frames where a score tie was consumed (status 3): raster order, then the exact emulation.  Blocks of all other
   // frames return at once.
@@ -1712,8 +1714,8 @@ size_t sfm_corner_work_bytes_md(int w, int h, int nframes, int cand_cap, int min
 extern "C" int sfmgpu_select_set_mode(sfmgpu_ctx* ctx, int mode) {
   SFM_ENTER(ctx);
   if (!ctx) return SFMGPU_E_ARG;
-  if (mode != 0 && mode != 1 && mode != 2 && !(mode >= 12 && mode <= BK_CODE_BITS))
-    return sfm_fail(ctx, SFMGPU_E_ARG, "select_set_mode: mode %d not in {0, 1, 2, 12..%d}", mode, BK_CODE_BITS);
+  if (mode != 0 && mode != 1 && mode != 2 && !(mode >= 12 && mode <= BK_CODE_BITS) && !(mode >= 1000 + 64 && mode <= 1000 + BK_T))
+    return sfm_fail(ctx, SFMGPU_E_ARG, "select_set_mode: mode %d not in {0, 1, 2, 12..%d, %d..%d}", mode, BK_CODE_BITS, 1000 + 64, 1000 + BK_T);
   ctx->select_mode = mode;
   return 0;
 }

@@ -100,11 +100,12 @@ def test_device_std_sort_permutation(ctx, port, n, distinct):
 @pytest.mark.parametrize("name", list(_images()))
 @pytest.mark.parametrize("mc,q,d", [(2200, 0.01, 8), (50, 0.2, 3), (0, 0.01, 8), (300, 0.0, 1), (100, 0.01, 0), (4000, 0.001, 2),
                                     (500, 0.01, 25)])
-@pytest.mark.parametrize("select_mode", [0, 1, 2, 14, 20])
+@pytest.mark.parametrize("select_mode", [0, 1, 2, 14, 20, 1064, 1300])
 def test_corners_bit_exact(ctx, checker, name, mc, q, d, select_mode):
     """select_mode 0: bucket selection + exact introsort fallback on observable score ties; 1: introsort emulation; 2: full
     radix sort + selection; 14 / 20: bucket selection with 14- / 20-bit order codes (equal codes everywhere: the exact-score
-    path orders them; with 14 bits a bucket is a few codes wide)."""
+    path orders them; with 14 bits a bucket is a few codes wide); 1064 / 1300: gathers of 64 / 300 words (every bucket is
+    oversized: walked in runs of its sub-buckets, or handed to the exact emulation where a sub-bucket alone is too large)."""
     img = _images()[name]
     f = _frames(ctx, [img], 1)
     ctx.select_set_mode(select_mode)
@@ -577,7 +578,7 @@ def test_pair_frontend_batch_with_score_ties(ctx, checker):
     f = _frames(ctx, imgs)
     cfg = sfmgpu.lkcfg(max_tracks=900)
     pairs = ctx.pairs(6, 900)
-    for mode in (0, 1, 2, 16):
+    for mode in (0, 1, 2, 16, 1100):
         ctx.select_set_mode(mode)
         try:
             pairs.run(f, 0, 6, cfg)
