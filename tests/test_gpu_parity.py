@@ -651,6 +651,23 @@ def test_c3_shape_4k_pair(ctx, checker):
     assert np.array_equal(kept_all[sel], keep) and _klt_close(p1[sel], w1) and _klt_close(pb[sel], wb)
 
 
+@pytest.mark.parametrize("select_mode", [0, 1300, 3048, 20, 2])
+def test_c3_shape_4k_corners_select_modes(ctx, checker, select_mode):
+    """One 3840x2160 frame, 8000 corners (~400 k candidates): the bucket selection with its default geometry, with gathers
+    of 300 / 2048 words (every bucket oversized: the sub-bucket walk at scale, or the exact emulation), with 20-bit order
+    codes (equal codes by the exact score recomputed from the image) and the full radix sort: bit-exact corners."""
+    w, h, nmax = 3840, 2160, 8000
+    f0 = synth.frame(SEED, 3, w, h)
+    f = _frames(ctx, [f0], 1)
+    ctx.select_set_mode(select_mode)
+    try:
+        got = f.corners(0, nmax, 0.01, 8)
+    finally:
+        ctx.select_set_mode(0)
+    want = checker.shi_tomasi(f0, nmax, 0.01, 8)
+    assert got.shape == want.shape and np.array_equal(got, want), (select_mode, len(got), len(want))
+
+
 def test_errors_are_loud(ctx):
     f = ctx.frames(64, 48, 2, 3)
     with pytest.raises(sfmgpu.SfmGpuError):
