@@ -23,21 +23,16 @@
 
 namespace {
 
-#ifndef RS_THREADS_V
-#define RS_THREADS_V 256
-#endif
-constexpr int RS_THREADS = RS_THREADS_V;
+// block size x hypotheses staged per block iteration: one instantiation for single correspondence sets (C4 shape), one for the
+// batched stage (a few thousand points per pair: 128-thread blocks waste less of a pair's last block)
+constexpr int RS_THREADS_1 = 256, RS_HCHUNK_1 = 128, RS_THREADS_B = 128, RS_HCHUNK_B = 128;
 #ifndef RS_PTS_V
 #define RS_PTS_V 2
 #endif
 constexpr int RS_PTS = RS_PTS_V;  // points per thread, packed two by two (FFMA2)
-#ifndef RS_HCHUNK_V
-#define RS_HCHUNK_V 64
-#endif
-constexpr int RS_HCHUNK = RS_HCHUNK_V;    // hypotheses staged per block iteration
 // (Measured, threads x chunk: RANSAC stage per 999 C2 pairs / per 399 C3 pairs / C4 rate: 256 x 64: 9.93 ms / 14.53 ms / 834 G;
 //  128 x 128: 9.69 / 14.02 / 806; 128 x 64: 9.72 / 14.11 / 810; 256 x 128: 9.84 / 14.34 / 848; 256 x 32: 10.12 / 14.82 / 839;
-//  512 x 64: 10.89 / 15.48 / 816 - within 4 % of each other.)
+//  512 x 64: 10.89 / 15.48 / 816 - within 4 % of each other: 128 x 128 for the batched stage, 256 x 128 for single sets.)
 
 __device__ __forceinline__ float2 B2(float s) { return make_float2(s, s); }  // scalar broadcast operand of a packed instruction
 
@@ -90,6 +85,7 @@ struct __align__(16) RsHyp {  // 48 bytes: read with three 128-bit shared-memory
 
 // blockIdx.z = correspondence set ("pair") of a batch: points at xi/xj + pair * pt_stride, npts[pair] of them (npts == nullptr:
 // n_single), hypotheses E + pair * H * 9, counts + pair * H.  Sets with fewer than 8 points are not scored (:648).
+template <int RS_THREADS, int RS_HCHUNK>
 __global__ void __launch_bounds__(RS_THREADS) ransac_count_kernel(const double2* __restrict__ xi, const double2* __restrict__ xj,
                                                                  size_t pt_stride, const int* __restrict__ npts, int n_single,
                                                                  const double* __restrict__ E, int H, int h_per_block,
@@ -336,11 +332,13 @@ int sfm_ransac_score_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* 
   if (npairs <= 0) return 0;
   SFM_CUDA(ctx, cudaMemsetAsync(counts, 0, (size_t)npairs * (H > 0 ? H : 1) * sizeof(int), ctx->stream));
   if (H > 0 && n > 0) {
-    const unsigned gx = sfm_cdiv(n, RS_THREADS * RS_PTS);
+    const bool batched = npairs > 1;
+    const int threads = batched ? RS_THREADS_B : RS_THREADS_1, hchunk = batched ? RS_HCHUNK_B : RS_HCHUNK_1;
+    const unsigned gx = sfm_cdiv(n, threads * RS_PTS);
     // enough blocks to fill the machine several times over, whole chunks of hypotheses per block
     long long want_y = ((long long)ctx->n_sm * 8 + (long long)gx * npairs - 1) / ((long long)gx * npairs);
     long long hpb = (H + want_y - 1) / want_y;
-    hpb = ((hpb + RS_HCHUNK - 1) / RS_HCHUNK) * RS_HCHUNK;
+    hpb = ((hpb + hchunk - 1) / hchunk) * hchunk;
     const unsigned gy = sfm_cdiv(H, hpb);
     // thr_lo / thr_hi bracket thr by 2^-50 relative (see is_inlier)
     const double eps = 8.8817841970012523e-16;  // 2^-50
@@ -351,9 +349,14 @@ int sfm_ransac_score_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* 
     if (!(thr > 1e-18 && thr < 1e18)) thr_f = NAN;
     for (int z0 = 0; z0 < npairs; z0 += 65535) {  // grid.z limit
       const int nz = npairs - z0 < 65535 ? npairs - z0 : 65535;
-      SFM_LAUNCH(ctx, ransac_count_kernel, dim3(gx, gy, nz), RS_THREADS, 0, xi + (size_t)z0 * pt_stride, xj + (size_t)z0 * pt_stride,
-                 pt_stride, npts ? npts + z0 : nullptr, n, E + (size_t)z0 * H * 9, H, (int)hpb, thr, thr * (1.0 - eps),
-                 thr * (1.0 + eps), thr_f, kappa_f, counts + (size_t)z0 * H);
+      if (batched)
+        SFM_LAUNCH(ctx, (ransac_count_kernel<RS_THREADS_B, RS_HCHUNK_B>), dim3(gx, gy, nz), RS_THREADS_B, 0, xi + (size_t)z0 * pt_stride,
+                   xj + (size_t)z0 * pt_stride, pt_stride, npts ? npts + z0 : nullptr, n, E + (size_t)z0 * H * 9, H, (int)hpb, thr,
+                   thr * (1.0 - eps), thr * (1.0 + eps), thr_f, kappa_f, counts + (size_t)z0 * H);
+      else
+        SFM_LAUNCH(ctx, (ransac_count_kernel<RS_THREADS_1, RS_HCHUNK_1>), dim3(gx, gy, nz), RS_THREADS_1, 0, xi + (size_t)z0 * pt_stride,
+                   xj + (size_t)z0 * pt_stride, pt_stride, npts ? npts + z0 : nullptr, n, E + (size_t)z0 * H * 9, H, (int)hpb, thr,
+                   thr * (1.0 - eps), thr * (1.0 + eps), thr_f, kappa_f, counts + (size_t)z0 * H);
     }
   }
   SFM_LAUNCH(ctx, ransac_argmax_kernel, npairs, 1024, 0, (const int*)counts, H, best);
