@@ -26,12 +26,14 @@
 #include <array>
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
 #include <memory>
 #include <optional>
 #include <random>
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/sfmgpu.h"
@@ -124,10 +126,83 @@ struct Pool {
 struct DevicePyr {
   std::shared_ptr<Pool> pool;
   int slot = -1;
+  unsigned long long serial = 0;  // unique per build_pyr call (slots are reused, serials are not)
+  unsigned long long imgkey = 0;  // content key of the level-0 image (image_key)
   ~DevicePyr() {
     if (pool && slot >= 0) pool->used[slot] = 0;
   }
 };
+
+// Content key of an image: size + a multiplicative hash over its 8-byte words (~0.05 ms per 640x480 image).
+inline unsigned long long image_key(const GrayImage& im) {
+  unsigned long long h = 0x9E3779B97F4A7C15ull ^ ((unsigned long long)(unsigned)im.w << 32) ^ (unsigned)im.h;
+  const size_t n = im.pix.size(), nw = n / 8;
+  const unsigned char* p = im.pix.data();
+  for (size_t i = 0; i < nw; i++) {
+    unsigned long long w;
+    std::memcpy(&w, p + 8 * i, 8);
+    h = (h ^ w) * 0xFF51AFD7ED558CCDull;
+    h ^= h >> 29;
+  }
+  for (size_t i = nw * 8; i < n; i++) h = (h ^ p[i]) * 0x100000001B3ull;
+  return h ? h : 1;
+}
+
+// ---- speculation behind track_one_public --------------------------------------------------------------------------------------
+// The reference's loop-closure block (:1841-1852) detects corners on an image, builds two pyramids and then calls
+// track_one_public twice per corner (forward, then backward from the result): 2 x 1200 launches + synchronisations, ~60 ms.
+// The shim remembers the corners shi_tomasi last returned per image; the first track_one_public(a, b, p) whose point is one
+// of the corners of a's image tracks ALL of them forward and backward in one batch (the kernel a single call runs, so
+// every value is bit-identical to what the single calls would return) and answers this and the following calls - the
+// forward ones by (a, b, corner), the backward ones by (b, a, forward result) - from that table.  Anything else (other
+// points, other parameters) takes the single-call path.  SFMGPU_SPECULATE=0 turns it off.
+struct CornerMemo {
+  unsigned long long imgkey = 0;
+  std::vector<Vec2> corners;
+};
+inline CornerMemo* corner_memos() {
+  static CornerMemo m[2];
+  return m;
+}
+inline void remember_corners(const GrayImage& im, const std::vector<Vec2>& c) {
+  CornerMemo* m = corner_memos();
+  m[1] = std::move(m[0]);
+  m[0].imgkey = image_key(im);
+  m[0].corners = c;
+}
+struct TrackKey {
+  unsigned long long a, b, x, y;
+  bool operator==(const TrackKey& o) const { return a == o.a && b == o.b && x == o.x && y == o.y; }
+};
+struct TrackKeyHash {
+  size_t operator()(const TrackKey& k) const {
+    unsigned long long h = k.a * 0x9E3779B97F4A7C15ull ^ k.b * 0xC2B2AE3D27D4EB4Full ^ k.x * 0xFF51AFD7ED558CCDull ^ (k.y + (k.y << 31));
+    return (size_t)(h ^ (h >> 32));
+  }
+};
+struct TrackMemo {
+  unsigned long long a = 0, b = 0;  // pyramid serials of the speculated pair
+  int radius = 0, iters = 0;
+  std::unordered_map<TrackKey, Vec2, TrackKeyHash> table;
+};
+inline TrackMemo& track_memo() {
+  static TrackMemo m;
+  return m;
+}
+inline bool& speculate_flag() {
+  static bool on = [] {
+    const char* e = std::getenv("SFMGPU_SPECULATE");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+inline bool speculate() { return speculate_flag(); }
+inline void set_speculate(bool on) { speculate_flag() = on; }
+inline unsigned long long dbits(double v) {
+  unsigned long long u;
+  std::memcpy(&u, &v, 8);
+  return u;
+}
 inline std::shared_ptr<DevicePyr> acquire_slot(int w, int h, int levels) {
   static std::vector<std::shared_ptr<Pool>> pools;
   constexpr int SLOTS = 8;
@@ -169,6 +244,9 @@ static Pyramid build_pyr(const GrayImage& im, int levels) {
   sfmgpu_ctx* ctx = context();
   Pyramid p;
   p.dev = acquire_slot(im.w, im.h, levels);
+  static unsigned long long next_serial = 1;
+  p.dev->serial = next_serial++;
+  p.dev->imgkey = speculate() ? image_key(im) : 0;
   sfmgpu_frames* f = p.dev->pool->frames;
   check(ctx, sfmgpu_frames_upload(ctx, f, p.dev->slot, 1, im.pix.data()), "frames_upload");
   check(ctx, sfmgpu_pyramid_build(ctx, f, p.dev->slot, 1), "pyramid_build");
@@ -196,6 +274,7 @@ static std::vector<Vec2> shi_tomasi(const GrayImage& im, int max_corners, double
   check(ctx, sfmgpu_corners(ctx, f, slot->slot, max_corners, quality, min_dist, xy.data(), &n), "corners");
   std::vector<Vec2> out((size_t)n);
   for (int i = 0; i < n; i++) out[i] = Vec2{xy[2 * i], xy[2 * i + 1]};
+  if (speculate()) remember_corners(im, out);
   return out;
 }
 
@@ -292,8 +371,54 @@ class KLTTracker {
 
   const std::vector<Track>& tracks() const { return tracks_; }
 
-  // Single-direction, single-point track (:396-398).  One launch per call: prefer track_pairs() in loops.
+  // Single-direction, single-point track (:396-398).  A loop over the corners of a's image (:1845-1849) is answered from
+  // ONE batched forward + backward track of all of them (see "speculation" above); any other call is one launch.
   Vec2 track_one_public(const Pyramid& a, const Pyramid& b, Vec2 p0) const {
+    using namespace sfmgpu_shim;
+    if (speculate() && a.dev && b.dev && a.dev->pool == b.dev->pool) {
+      TrackMemo& tm = track_memo();
+      const bool same_cfg = tm.radius == cfg_.win_radius && tm.iters == cfg_.iters;
+      if (same_cfg && ((tm.a == a.dev->serial && tm.b == b.dev->serial) || (tm.a == b.dev->serial && tm.b == a.dev->serial))) {
+        auto it = tm.table.find(TrackKey{a.dev->serial, b.dev->serial, dbits(p0.x), dbits(p0.y)});
+        if (it != tm.table.end()) return it->second;
+      }
+      for (int m = 0; m < 2; m++) {
+        const CornerMemo& cm = corner_memos()[m];
+        if (cm.imgkey == 0 || cm.imgkey != a.dev->imgkey || cm.corners.size() < 2) continue;
+        bool member = false;
+        for (const Vec2& c : cm.corners)
+          if (dbits(c.x) == dbits(p0.x) && dbits(c.y) == dbits(p0.y)) {
+            member = true;
+            break;
+          }
+        if (!member) continue;
+        // all corners of a's image, forward and backward, through the kernel a single call runs (warp per feature)
+        std::vector<Vec2> p1, pb;
+        sfmgpu_ctx* ctx = context();
+        check(ctx, sfmgpu_klt_set_mode(ctx, 1), "klt_set_mode");
+        try {
+          track_pairs(a, b, cm.corners, cfg_.win_radius, cfg_.iters, p1, &pb);
+        } catch (...) {
+          sfmgpu_klt_set_mode(ctx, 0);
+          throw;
+        }
+        check(ctx, sfmgpu_klt_set_mode(ctx, 0), "klt_set_mode");
+        tm.a = a.dev->serial;
+        tm.b = b.dev->serial;
+        tm.radius = cfg_.win_radius;
+        tm.iters = cfg_.iters;
+        tm.table.clear();
+        tm.table.reserve(2 * cm.corners.size());
+        Vec2 answer = p0;
+        for (size_t k = 0; k < cm.corners.size(); k++) {
+          const Vec2& c = cm.corners[k];
+          tm.table[TrackKey{tm.a, tm.b, dbits(c.x), dbits(c.y)}] = p1[k];
+          tm.table[TrackKey{tm.b, tm.a, dbits(p1[k].x), dbits(p1[k].y)}] = pb[k];
+          if (dbits(c.x) == dbits(p0.x) && dbits(c.y) == dbits(p0.y)) answer = p1[k];
+        }
+        return answer;
+      }
+    }
     std::vector<Vec2> in{p0}, out;
     track_pairs(a, b, in, cfg_.win_radius, cfg_.iters, out, nullptr);
     return out[0];

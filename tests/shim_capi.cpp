@@ -218,6 +218,7 @@ int shim_host_triangulate(const double* K, const double* poses, const int* ia, c
 
 // opt-in device solver for find_E_ransac
 void shim_set_device_solver(int on) { sfmgpu_shim::set_device_solver(on != 0); }
+void shim_set_speculate(int on) { sfmgpu_shim::set_speculate(on != 0); }
 
 // ---- host-only pieces (no GPU needed): checked on the CPU against the compiled reference ----------------------
 int shim_host_norm_points(const double* K, const double* p, int n, double* out) {

@@ -34,6 +34,8 @@ def load():
     lib.shim_host_triangulate.argtypes = [_f8, _f8, _i4, _i4, _f8, _f8, _i, _f8]
     lib.shim_set_device_solver.argtypes = [_i]
     lib.shim_set_device_solver.restype = None
+    lib.shim_set_speculate.argtypes = [_i]
+    lib.shim_set_speculate.restype = None
     lib.shim_host_norm_points.argtypes = [_f8, _f8, _i, _f8]
     lib.shim_host_hypotheses.argtypes = [_f8, _f8, _i, _i, _f8]
     lib.shim_host_recover_pose.argtypes = [_f8, _f8, _f8, _i4, _i, _f8, _f8]

@@ -42,6 +42,27 @@ def test_loop_closure_block(shim, checker, batched):
     assert np.abs(lj[:k] - wj).max() <= KLT_TOL
 
 
+def test_track_one_public_speculation_is_bit_identical(shim):
+    """The per-point loop of :1845-1849 through the shim: answered from ONE speculative batch (default) it returns exactly
+    what 2 x n single launches return, for two different pairs in a row (the table is rebuilt per pair) and a repeated one."""
+    res = {}
+    for spec in (1, 0):
+        shim.shim_set_speculate(spec)
+        try:
+            out = []
+            for (a, b) in [(2, 3), (7, 8), (2, 3)]:
+                f0, f1 = synth.frame(SEED, a, W, H), synth.frame(SEED, b, W, H)
+                li, lj, nc = np.zeros((300, 2)), np.zeros((300, 2)), C.c_int(0)
+                k = shimlib.ck(shim, shim.shim_pair_frontend(f0, f1, W, H, 300, 0.01, 8, 3, 5, 10, 1.0, 0, li, lj, C.byref(nc)))
+                out.append((k, nc.value, li[:k].copy(), lj[:k].copy()))
+            res[spec] = out
+        finally:
+            shim.shim_set_speculate(1)
+    for x, y in zip(res[1], res[0]):
+        assert x[0] == y[0] and x[1] == y[1] and np.array_equal(x[2], y[2])
+        assert np.array_equal(x[3].view(np.uint64), y[3].view(np.uint64))
+
+
 def test_tracker_class(shim, checker):
     kw = dict(max_tracks=150, min_tracks=120, quality=0.01, min_distance=8, levels=3, radius=5, iters=10, fb=1.0)
     want = checker.tracker(**kw)
