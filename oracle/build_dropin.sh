@@ -1,9 +1,11 @@
 #!/bin/bash
-# oracle/build_dropin.sh — TEST INFRASTRUCTURE.  Builds two executables into oracle/_ref/ (git-ignored):
+# oracle/build_dropin.sh — TEST INFRASTRUCTURE.  Builds three executables into oracle/_ref/ (git-ignored):
 #   templering_sfm_ref : the reference's own CLI, unmodified (cpp/src/templering_sfm.cpp as it lies)
 #   templering_sfm_gpu : the same main() with the front-end definitions guarded out and host/sfmgpu_shim.hpp
 #                        included instead — exactly the patch of INTEGRATION.md §2, applied to a scratch copy under
 #                        /tmp (nothing of the reference is copied into the repository).
+#   ate_keyframes      : the reference's own trajectory-evaluation tool (cpp/tools/ate_keyframes.cpp, unmodified): scores
+#                        both runs against the ground truth of the synthetic ring dataset (tests/ring_dataset.py).
 # Used by tests/test_gpu_dropin.py to compare the whole pipeline's outputs with and without the GPU front end.
 set -e
 REF_DIR=${REF_DIR:-/root/reference}
@@ -27,5 +29,6 @@ CXXF="-std=c++20 -O3 -DNDEBUG -w -I$REF_DIR/cpp/include"
 g++ $CXXF "$SRC" -o "$HERE/_ref/templering_sfm_ref"
 g++ $CXXF -pthread -ffp-contract=off -DUSE_SFMGPU -I"$PKG/host" "$TMP/templering_sfm_dropin.cpp" -o "$HERE/_ref/templering_sfm_gpu" \
     -L"$PKG" -lsfmgpu -Wl,-rpath,'$ORIGIN/../../structure-from-motion-3d-reconstruction_b200'
+g++ $CXXF "$REF_DIR/cpp/tools/ate_keyframes.cpp" -o "$HERE/_ref/ate_keyframes"
 rm -rf "$TMP"
-echo "built $HERE/_ref/templering_sfm_ref and templering_sfm_gpu"
+echo "built $HERE/_ref/templering_sfm_ref, templering_sfm_gpu and ate_keyframes"
