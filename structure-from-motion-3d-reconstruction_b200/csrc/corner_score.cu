@@ -17,8 +17,8 @@
 // integer-valued floats without a single rounding.  Bytes become floats with one PRMT (0x4B000000 | b = 2^23 + b);
 // the offset cancels in the gradient differences.
 //
-// Which pixels see the FP64 expression: every pixel gets the FP32 ESTIMATE u~ = T - sqrt.approx(D) (error < 0.5:
-// T <= 1.63e6 has ulp 0.125, D carries two roundings, sqrt.approx 2^-23 relative).  A pixel can only matter if
+// Which pixels see the FP64 expression: every pixel gets the FP32 ESTIMATE u~ = T - sqrt.approx(D) (error < 0.72: root <=
+// T <= 3.25e6, D carries two roundings, sqrt.approx 2^-23 relative; tests/test_score_estimate_cpu.py).  A pixel can only matter if
 // u~ >= bound - 2 (bound = the tile's / frame's running maximum in the max pass, 8*thr in the candidate pass); those
 // few are queued and evaluated DENSELY with the exact FP64 expression afterwards, which alone decides.
 //
@@ -43,7 +43,7 @@ constexpr int TAP_H = TH + 6, TAP_S = 76;   // tap rows; 19-word row stride: con
 constexpr int HS_ROWS = TH + 4, HS_S = 65;  // horizontal sums: 64 rows, padded
 constexpr int RUN = 16;                     // phase 1: outputs per thread (64 rows x 4 runs)
 constexpr int VRUN = 15;                    // phase 2: outputs per thread (64 columns x 4 row groups)
-constexpr float EST_MARGIN = 2.0f;          // >= 4x the error bound of the FP32 estimate
+constexpr float EST_MARGIN = 2.0f;          // > 2.7x the error bound of the FP32 estimate (0.72; observed worst case 0.58)
 
 struct ScoreSmem {
   float hxx[HS_ROWS * HS_S], hxy[HS_ROWS * HS_S], hyy[HS_ROWS * HS_S];
@@ -260,7 +260,7 @@ __device__ __forceinline__ void score_tile(ScoreSmem& sm, const uint8_t* __restr
     bound = fmaxf(bound, bm) - EST_MARGIN;  // a pixel below this cannot be the frame maximum
     if (MODE == 2) {
       // provisional threshold from a lower bound of the frame maximum: the running maximum (an exact score) or this
-      // tile's best estimate minus the margin (estimate error < margin / 4)
+      // tile's best estimate minus the margin (estimate error < 0.72 < margin)
       const double lb = fmax(runmax, fmax(0.0, (double)bm - (double)EST_MARGIN));
       thr8 = 8.0 * ((0.125 * lb) * quality);
       bound = fminf(bound, __double2float_rd(thr8) - EST_MARGIN);
