@@ -1,8 +1,8 @@
 """Synthetic TempleRing stand-in with real 3-D structure (TEST INFRASTRUCTURE).
 
 The Middlebury TempleRing images are not shipped with the reference, and the value-noise frames of
-`sfmgpu.synth` are 2-D translations of one texture: a planar, zero-parallax scene on which the reference's map initialises
-but its camera centres come out as NaN.  This module ray-casts a small textured scene (a sphere in front of a wall, both
+`sfmgpu.synth` are 2-D translations of one texture: a planar, zero-parallax scene with no ground-truth trajectory to score
+against.  This module ray-casts a small textured scene (a sphere in front of a wall, both
 carrying a smooth analytic 3-D texture) from cameras on a ring around it, Middlebury temple intrinsics, and writes the
 directory layout the reference's CLI reads (`templeRing/templeR_par.txt`, `templeR_ang.txt`, `templeRing_pgm/*.pgm`,
 /root/reference/cpp/src/templering_sfm.cpp:120-152, :1678-1712) with the TRUE poses in the par file, so that the
@@ -10,7 +10,8 @@ reference's own `ate_keyframes` tool can score a run against ground truth.
 
 The angular step per frame is tiny on purpose: the reference's `lk_step` evaluates the error at the SAME location in both
 images (sfm.cpp:439-442), which multiplies small flows by ~31.5 (SURVEY.md §8c KAT 4); a true flow of ~0.05 px per frame
-keeps the tracked flow at a few pixels, where the tracker, the essential-matrix stage and BA all stay finite.
+keeps the tracked flow near the 18 px the reference's keyframe rule asks for (sfm.cpp:1576, :1703).  The tests run it with
+bundle adjustment off: the reference's map points depend on heap contents (tests/test_gpu_dropin.py explains).
 """
 import os
 
