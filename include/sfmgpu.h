@@ -208,6 +208,15 @@ int sfmgpu_pairs_set_ransac(sfmgpu_ctx* ctx, sfmgpu_pairs* p, const double* K, c
  * [npairs][max_corners] (first best_n valid), R [npairs][9], t [npairs][3]; any may be NULL; pinned memory for overlap. */
 int sfmgpu_pairs_ransac_host_outputs(sfmgpu_ctx* ctx, sfmgpu_pairs* p, int32_t* status, int32_t* best_n, int32_t* inliers,
                                      double* R, double* t);
+/* Early stop of the stage (default on; exact).  The scoring loop keeps the FIRST hypothesis with the largest count (:673,
+ * strict >) and a count cannot exceed the number of correspondences, so once a hypothesis explains ALL points of a pair
+ * nothing after it can win: the stage scores the first 128 hypotheses of every pair and takes the pairs that already hold
+ * a full count out of the remaining launches - same winner, inlier list, count and pose.  With the reference's thresholds
+ * (1e-3 / 2e-3 on the Sampson error in normalised coordinates) that is the common case.  Applies to the device solver's
+ * own hypotheses (not E_host) and iters > 256.  on = 0: every hypothesis of every pair is solved and scored.
+ * sfmgpu_pairs_ransac_early: pairs stopped early since the last call of it (reads and resets; synchronises). */
+int sfmgpu_ransac_set_early_stop(sfmgpu_ctx* ctx, int on);
+int sfmgpu_pairs_ransac_early(sfmgpu_ctx* ctx, sfmgpu_pairs* p, long long* pairs_stopped);
 /* Run the stage now on the pairs of the last batch.  E_host: NULL (device solver) or [npairs][iters][9] hypotheses. */
 int sfmgpu_pairs_ransac(sfmgpu_ctx* ctx, sfmgpu_pairs* p, const double* K, const sfmgpu_ransac_cfg* rc, const double* E_host);
 /* One pair: status, winner (-1: none), its count, inlier indices ascending (into the pair's survivor list; cap entries of

@@ -70,6 +70,7 @@ struct sfmgpu_ctx {
   int rs_n = 0, rs_H = 0;
   bool rs_screened = false;  // rs_E holds screening hypotheses of the octets in rs_idx8: the winner is re-solved when scored
   int solver_mode = 1;       // device 8-point solver: 1 screening solver for the counts of launches beyond one wave + Jacobi emulation for the winner, 0 Jacobi emulation for every hypothesis, 2 the same by the warp kernel, 3 screening always (2, 3: tests)
+  int rs_early = 1;          // batched RANSAC stage: stop scoring a pair once a hypothesis explains all of its points (two_view.cu)
   bool profile = false;
   struct StageEv { int stage; cudaEvent_t a, b; };
   std::vector<StageEv> stage_evs;
@@ -219,6 +220,8 @@ int sfm_sort_perm(sfmgpu_ctx* ctx, const double* keys, int n, int32_t* perm);
 // solver.cu / ransac.cu: batched over correspondence sets
 int sfm_eight_point_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, const int* npts, int n_single,
                             int npairs, const int* idx8, int H, double* Eout, int screen);
+int sfm_eight_point_range(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, const int* npts, int n_single,
+                          int npairs, const int* idx8, int H, int h0, int h1, double* Eout, int screen);
 bool sfm_solver_screens(const sfmgpu_ctx* ctx, int npairs, int H);
 int sfm_sample_octets(sfmgpu_ctx* ctx, int n, int H, int* d_idx8, int* d_flag);
 int sfm_eight_point_winners(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, const int* npts, int n_single,
@@ -227,3 +230,7 @@ int sfm_pose_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size
                      const int* best, const int* inl, const double* bestE, double* R, double* t);
 int sfm_ransac_score_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, const int* npts, int n_max,
                              int npairs, double* E, int H, double thr, int* counts, int* best, int* inl, const int* refine_idx8);
+int sfm_ransac_count_range(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, const int* npts, int n_max,
+                           int npairs, const double* E, int H, int h0, int h1, double thr, int* counts);
+int sfm_ransac_finish(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, const int* npts, int n_max, int npairs,
+                      double* E, int H, double thr, const int* counts, int* best, int* inl, const int* refine_idx8);

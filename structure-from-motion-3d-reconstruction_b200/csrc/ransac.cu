@@ -88,9 +88,9 @@ struct __align__(16) RsHyp {  // 48 bytes: read with three 128-bit shared-memory
 template <int RS_THREADS, int RS_HCHUNK>
 __global__ void __launch_bounds__(RS_THREADS) ransac_count_kernel(const double2* __restrict__ xi, const double2* __restrict__ xj,
                                                                  size_t pt_stride, const int* __restrict__ npts, int n_single,
-                                                                 const double* __restrict__ E, int H, int h_per_block,
-                                                                 double thr, double thr_lo, double thr_hi, float thr_f,
-                                                                 float kappa_f, int* __restrict__ counts) {
+                                                                 const double* __restrict__ E, int H, int h0, int h1,
+                                                                 int h_per_block, double thr, double thr_lo, double thr_hi,
+                                                                 float thr_f, float kappa_f, int* __restrict__ counts) {
   __shared__ double sE[RS_HCHUNK * 9];
   __shared__ RsHyp sH[RS_HCHUNK];
   // per-warp counts of the chunk, four hypotheses per word (a warp counts at most 2 x 32 per hypothesis: one byte each):
@@ -138,8 +138,8 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_count_kernel(const double2*
   }
   // only the last block of a set has threads without points: the common case counts without masking
   const bool tail = (int)((blockIdx.x + 1) * RS_THREADS * RS_PTS) > n;
-  const int h_begin = blockIdx.y * h_per_block;
-  const int h_end = min(H, h_begin + h_per_block);
+  const int h_begin = h0 + blockIdx.y * h_per_block;  // hypotheses [h0, h1) of the set; E / counts keep their [H] layout
+  const int h_end = min(h1, h_begin + h_per_block);
   for (int hc = h_begin; hc < h_end; hc += RS_HCHUNK) {
     const int nh = min(RS_HCHUNK, h_end - hc);
     __syncthreads();
@@ -328,38 +328,55 @@ __global__ void __launch_bounds__(1024) ransac_mask_kernel(const double2* __rest
 // of E) and its inlier list and count (best[1]) are those of that hypothesis.
 int sfm_ransac_score_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, const int* npts, int n_max,
                              int npairs, double* E, int H, double thr, int* counts, int* best, int* inl, const int* refine_idx8) {
-  const int n = n_max;
   if (npairs <= 0) return 0;
   SFM_CUDA(ctx, cudaMemsetAsync(counts, 0, (size_t)npairs * (H > 0 ? H : 1) * sizeof(int), ctx->stream));
-  if (H > 0 && n > 0) {
-    const bool batched = npairs > 1;
-    const int threads = batched ? RS_THREADS_B : RS_THREADS_1, hchunk = batched ? RS_HCHUNK_B : RS_HCHUNK_1;
-    const unsigned gx = sfm_cdiv(n, threads * RS_PTS);
-    // enough blocks to fill the machine several times over, whole chunks of hypotheses per block
-    long long want_y = ((long long)ctx->n_sm * 8 + (long long)gx * npairs - 1) / ((long long)gx * npairs);
-    long long hpb = (H + want_y - 1) / want_y;
-    hpb = ((hpb + hchunk - 1) / hchunk) * hchunk;
-    const unsigned gy = sfm_cdiv(H, hpb);
-    // thr_lo / thr_hi bracket thr by 2^-50 relative (see is_inlier)
-    const double eps = 8.8817841970012523e-16;  // 2^-50
-    // FP32 screen (see RsHyp): thr as float, kappa = (eps + 16u) with slack.  A threshold the screen cannot handle
-    // (<= 0, non-finite, outside (1e-18, 1e18)) disables it: td = NaN leaves every pair undecided, i.e. to the FP64 path.
-    float thr_f = (float)thr;
-    const float kappa_f = (float)((2e-6 + 16.0 * 5.9604644775390625e-8) * 1.00001);
-    if (!(thr > 1e-18 && thr < 1e18)) thr_f = NAN;
-    for (int z0 = 0; z0 < npairs; z0 += 65535) {  // grid.z limit
-      const int nz = npairs - z0 < 65535 ? npairs - z0 : 65535;
-      if (batched)
-        SFM_LAUNCH(ctx, (ransac_count_kernel<RS_THREADS_B, RS_HCHUNK_B>), dim3(gx, gy, nz), RS_THREADS_B, 0, xi + (size_t)z0 * pt_stride,
-                   xj + (size_t)z0 * pt_stride, pt_stride, npts ? npts + z0 : nullptr, n, E + (size_t)z0 * H * 9, H, (int)hpb, thr,
-                   thr * (1.0 - eps), thr * (1.0 + eps), thr_f, kappa_f, counts + (size_t)z0 * H);
-      else
-        SFM_LAUNCH(ctx, (ransac_count_kernel<RS_THREADS_1, RS_HCHUNK_1>), dim3(gx, gy, nz), RS_THREADS_1, 0, xi + (size_t)z0 * pt_stride,
-                   xj + (size_t)z0 * pt_stride, pt_stride, npts ? npts + z0 : nullptr, n, E + (size_t)z0 * H * 9, H, (int)hpb, thr,
-                   thr * (1.0 - eps), thr * (1.0 + eps), thr_f, kappa_f, counts + (size_t)z0 * H);
-    }
+  SFM_TRY(sfm_ransac_count_range(ctx, xi, xj, pt_stride, npts, n_max, npairs, E, H, 0, H, thr, counts));
+  return sfm_ransac_finish(ctx, xi, xj, pt_stride, npts, n_max, npairs, E, H, thr, counts, best, inl, refine_idx8);
+}
+
+// Counts of the hypotheses [h0, h1) of every set, ADDED to counts [npairs][H] (the caller zeroes them); sets with
+// npts[pair] < 8 are skipped.
+int sfm_ransac_count_range(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, const int* npts, int n_max,
+                           int npairs, const double* E, int H, int h0, int h1, double thr, int* counts) {
+  const int n = n_max, Hr = h1 - h0;
+  if (npairs <= 0 || H <= 0 || n <= 0 || Hr <= 0) return 0;
+  if (h0 < 0 || h1 > H) return sfm_fail(ctx, SFMGPU_E_ARG, "ransac: hypothesis range [%d, %d) outside [0, %d)", h0, h1, H);
+  const bool batched = npairs > 1;
+  const int threads = batched ? RS_THREADS_B : RS_THREADS_1, hchunk = batched ? RS_HCHUNK_B : RS_HCHUNK_1;
+  const unsigned gx = sfm_cdiv(n, threads * RS_PTS);
+  // enough blocks to fill the machine several times over, whole chunks of hypotheses per block
+  long long want_y = ((long long)ctx->n_sm * 8 + (long long)gx * npairs - 1) / ((long long)gx * npairs);
+  long long hpb = (Hr + want_y - 1) / want_y;
+  hpb = ((hpb + hchunk - 1) / hchunk) * hchunk;
+  const unsigned gy = sfm_cdiv(Hr, hpb);
+  // thr_lo / thr_hi bracket thr by 2^-50 relative (see is_inlier)
+  const double eps = 8.8817841970012523e-16;  // 2^-50
+  // FP32 screen (see RsHyp): thr as float, kappa = (eps + 16u) with slack.  A threshold the screen cannot handle
+  // (<= 0, non-finite, outside (1e-18, 1e18)) disables it: td = NaN leaves every pair undecided, i.e. to the FP64 path.
+  float thr_f = (float)thr;
+  const float kappa_f = (float)((2e-6 + 16.0 * 5.9604644775390625e-8) * 1.00001);
+  if (!(thr > 1e-18 && thr < 1e18)) thr_f = NAN;
+  for (int z0 = 0; z0 < npairs; z0 += 65535) {  // grid.z limit
+    const int nz = npairs - z0 < 65535 ? npairs - z0 : 65535;
+    if (batched)
+      SFM_LAUNCH(ctx, (ransac_count_kernel<RS_THREADS_B, RS_HCHUNK_B>), dim3(gx, gy, nz), RS_THREADS_B, 0, xi + (size_t)z0 * pt_stride,
+                 xj + (size_t)z0 * pt_stride, pt_stride, npts ? npts + z0 : nullptr, n, E + (size_t)z0 * H * 9, H, h0, h1, (int)hpb, thr,
+                 thr * (1.0 - eps), thr * (1.0 + eps), thr_f, kappa_f, counts + (size_t)z0 * H);
+    else
+      SFM_LAUNCH(ctx, (ransac_count_kernel<RS_THREADS_1, RS_HCHUNK_1>), dim3(gx, gy, nz), RS_THREADS_1, 0, xi + (size_t)z0 * pt_stride,
+                 xj + (size_t)z0 * pt_stride, pt_stride, npts ? npts + z0 : nullptr, n, E + (size_t)z0 * H * 9, H, h0, h1, (int)hpb, thr,
+                 thr * (1.0 - eps), thr * (1.0 + eps), thr_f, kappa_f, counts + (size_t)z0 * H);
   }
-  SFM_LAUNCH(ctx, ransac_argmax_kernel, npairs, 1024, 0, (const int*)counts, H, best);
+  return 0;
+}
+
+// Winner of every set from counts [npairs][H] (largest count, lowest index), the screening winner re-solved (refine_idx8),
+// its inlier list.
+int sfm_ransac_finish(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, const int* npts, int n_max, int npairs,
+                      double* E, int H, double thr, const int* counts, int* best, int* inl, const int* refine_idx8) {
+  const int n = n_max;
+  if (npairs <= 0) return 0;
+  SFM_LAUNCH(ctx, ransac_argmax_kernel, npairs, 1024, 0, counts, H, best);
   if (H > 0 && n > 0) {
     if (refine_idx8) SFM_TRY(sfm_eight_point_winners(ctx, xi, xj, pt_stride, npts, n, npairs, refine_idx8, H, (const int*)best, E));
     SFM_LAUNCH(ctx, ransac_mask_kernel, npairs, 1024, 0, xi, xj, pt_stride, npts, n, (const double*)E, H, best, thr, inl,

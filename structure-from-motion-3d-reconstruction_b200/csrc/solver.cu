@@ -334,11 +334,12 @@ __device__ void eight_point_solve(const double2* __restrict__ xi, const double2*
 // n_single); pairs with fewer than 8 points produce nothing.
 __global__ void __launch_bounds__(SV_TPB, SV_MINB) eight_point_kernel(const double2* __restrict__ xi, const double2* __restrict__ xj,
                                                                size_t pt_stride, const int* __restrict__ npts, int n_single,
-                                                               const int* __restrict__ idx8, int H, double* __restrict__ Eout) {
+                                                               const int* __restrict__ idx8, int H, int h0, int h1,
+                                                               double* __restrict__ Eout) {
   extern __shared__ double sv_smem[];
-  const int pair = blockIdx.y, hyp = blockIdx.x * SV_TPB + threadIdx.x;
+  const int pair = blockIdx.y, hyp = h0 + blockIdx.x * SV_TPB + threadIdx.x;  // hypotheses [h0, h1) of every pair
   const int n = npts ? npts[pair] : n_single;
-  if (hyp >= H || n < 8) return;
+  if (hyp >= h1 || n < 8) return;
   const size_t ho = (size_t)pair * H + hyp;
   eight_point_solve<SV_TPB>(xi + (size_t)pair * pt_stride, xj + (size_t)pair * pt_stride, idx8 + ho * 8, n, sv_smem + threadIdx.x,
                             Eout + ho * 9);
@@ -570,11 +571,12 @@ __device__ __forceinline__ void qr_null_vector(const double2* __restrict__ xi, c
 
 __global__ void __launch_bounds__(QR_TPB, 4) eight_point_qr_kernel(const double2* __restrict__ xi, const double2* __restrict__ xj,
                                                                    size_t pt_stride, const int* __restrict__ npts, int n_single,
-                                                                   const int* __restrict__ idx8, int H, double* __restrict__ Eout,
-                                                                   int* __restrict__ rep_count, int* __restrict__ rep_list) {
-  const int pair = blockIdx.y, hyp = blockIdx.x * QR_TPB + threadIdx.x;
+                                                                   const int* __restrict__ idx8, int H, int h0, int h1,
+                                                                   double* __restrict__ Eout, int* __restrict__ rep_count,
+                                                                   int* __restrict__ rep_list) {
+  const int pair = blockIdx.y, hyp = h0 + blockIdx.x * QR_TPB + threadIdx.x;  // hypotheses [h0, h1) of every pair
   const int n = npts ? npts[pair] : n_single;
-  if (hyp >= H || n < 8) return;
+  if (hyp >= h1 || n < 8) return;
   const size_t ho = (size_t)pair * H + hyp;
   const int* oct = idx8 + ho * 8;
   // a repeated index: two-dimensional null space, which member comes back is a property of the Jacobi iteration - those
@@ -781,19 +783,29 @@ bool sfm_solver_screens(const sfmgpu_ctx* ctx, int npairs, int H) {
 int sfm_eight_point_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, const int* npts, int n_single,
                             int npairs, const int* idx8, int H, double* Eout, int screen) {
   if (npairs <= 0 || H <= 0) return 0;
-  screen = screen && sfm_solver_screens(ctx, npairs, H);
+  return sfm_eight_point_range(ctx, xi, xj, pt_stride, npts, n_single, npairs, idx8, H, 0, H, Eout, screen && sfm_solver_screens(ctx, npairs, H));
+}
+
+// The same for the hypotheses [h0, h1) of every set (idx8 / Eout keep their [npairs][H] layout); `screen` is taken as given
+// (the caller decides once per launch set, so that the parts of a set are solved the same way).  Solver mode 2 (tests)
+// supports the full range only.
+int sfm_eight_point_range(sfmgpu_ctx* ctx, const double2* xi, const double2* xj, size_t pt_stride, const int* npts, int n_single,
+                          int npairs, const int* idx8, int H, int h0, int h1, double* Eout, int screen) {
+  if (npairs <= 0 || H <= 0 || h1 <= h0) return 0;
+  if (h0 < 0 || h1 > H) return sfm_fail(ctx, SFMGPU_E_ARG, "eight_point: hypothesis range [%d, %d) outside [0, %d)", h0, h1, H);
+  const int Hr = h1 - h0;
   if (screen) {
     if ((long long)npairs * H > 0x7fffffffll) return sfm_fail(ctx, SFMGPU_E_ARG, "eight_point: %d x %d hypotheses in one launch", npairs, H);
     SFM_TRY(sfm_reserve(ctx, ctx->sv_list, ((size_t)npairs * H + 64) * sizeof(int)));
     int* rep_count = (int*)ctx->sv_list.p;
     int* rep_list = rep_count + 64;
     SFM_CUDA(ctx, cudaMemsetAsync(rep_count, 0, sizeof(int), ctx->stream));
-    SFM_LAUNCH(ctx, eight_point_qr_kernel, dim3(sfm_cdiv(H, QR_TPB), npairs), QR_TPB, 0, xi, xj, pt_stride, npts, n_single, idx8, H, Eout,
-               rep_count, rep_list);
+    SFM_LAUNCH(ctx, eight_point_qr_kernel, dim3(sfm_cdiv(Hr, QR_TPB), npairs), QR_TPB, 0, xi, xj, pt_stride, npts, n_single, idx8, H, h0, h1,
+               Eout, rep_count, rep_list);
     static const int list_cfg = sfm_next_cfg_id();
     const size_t lsmem = (size_t)SV_TRI * SV_TPB * sizeof(double);
     SFM_SMEM_OPTIN(ctx, list_cfg, eight_point_list_kernel, lsmem);
-    const long long want = ((long long)npairs * H + SV_TPB - 1) / SV_TPB, cap = (long long)ctx->n_sm * SV_MINB;
+    const long long want = ((long long)npairs * Hr + SV_TPB - 1) / SV_TPB, cap = (long long)ctx->n_sm * SV_MINB;
     // a single correspondence set has a few dozen such octets: the first 512 go to the warp-per-hypothesis kernel (latency)
     const int warp_items = npairs == 1 ? 512 : 0;
     if (warp_items)
@@ -804,6 +816,7 @@ int sfm_eight_point_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* x
     return 0;
   }
   if (screen == 0 && ctx->solver_mode == 2) {  // tests: every octet through the warp-per-hypothesis emulation
+    if (h0 != 0 || h1 != H) return sfm_fail(ctx, SFMGPU_E_ARG, "eight_point: solver mode 2 solves whole sets only");
     if ((long long)npairs * H > 0x7fffffffll) return sfm_fail(ctx, SFMGPU_E_ARG, "eight_point: %d x %d hypotheses in one launch", npairs, H);
     SFM_TRY(sfm_reserve(ctx, ctx->sv_list, ((size_t)npairs * H + 64) * sizeof(int)));
     int* rep_count = (int*)ctx->sv_list.p;
@@ -817,7 +830,7 @@ int sfm_eight_point_batched(sfmgpu_ctx* ctx, const double2* xi, const double2* x
   static const int cfg_id = sfm_next_cfg_id();
   const size_t smem = (size_t)SV_TRI * SV_TPB * sizeof(double);
   SFM_SMEM_OPTIN(ctx, cfg_id, eight_point_kernel, smem);
-  SFM_LAUNCH(ctx, eight_point_kernel, dim3(sfm_cdiv(H, SV_TPB), npairs), SV_TPB, smem, xi, xj, pt_stride, npts, n_single, idx8, H, Eout);
+  SFM_LAUNCH(ctx, eight_point_kernel, dim3(sfm_cdiv(Hr, SV_TPB), npairs), SV_TPB, smem, xi, xj, pt_stride, npts, n_single, idx8, H, h0, h1, Eout);
   return 0;
 }
 

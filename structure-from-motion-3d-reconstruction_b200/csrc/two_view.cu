@@ -31,6 +31,7 @@ struct TwoViewState {
   double *bestE = nullptr, *R = nullptr, *t = nullptr;     // [max_pairs][9], [9], [3]
   int* flags = nullptr;                  // [1] != 0: the raw stream was too short for some pair (cannot happen, checked)
   DevBuf idx8, E, counts;                // chunk scratch: [chunk][H][8], [chunk][H][9], [chunk][H]
+  DevBuf neff2;                          // chunk scratch [chunk]: neff, or 0 for pairs whose scoring stopped early
   DevBuf raw;                            // mt19937(12345) outputs
   int raw_n = 0;
   // host outputs of the streaming front end (any may be null)
@@ -109,6 +110,28 @@ __global__ void __launch_bounds__(1024) tv_sample_kernel(const unsigned* __restr
     if (base >= want) return;
   }
   if (tid == 0 && base < want) atomicOr(flags, 1);
+}
+
+// Early stop (exact).  The scoring loop keeps the FIRST hypothesis with the largest count (:673, strict >) and a count cannot
+// exceed the number of points, so once some hypothesis h explains ALL n points of a pair no later hypothesis can replace the
+// winner: the winner is the lowest such h, and nothing after it has to be solved or scored.  With the reference's thresholds
+// (2e-3 / 1e-3 on the Sampson error in normalised coordinates: tens of pixels) that is the common case.  The stage therefore
+// scores the first TV_EARLY_H hypotheses of every pair, and this kernel takes the pairs that already hold a full count out
+// of the rest of the launch set (n2 = 0: the solver and count kernels skip sets with fewer than 8 points); their remaining
+// counts stay 0, so the arg-max finds the same winner, and the inlier list, count and pose come from it as before.
+constexpr int TV_EARLY_H = 128;  // = one hypothesis chunk of the batched count kernel
+
+__global__ void __launch_bounds__(128) tv_early_kernel(const int* __restrict__ counts, int H, int h1, const int* __restrict__ neff,
+                                                      int* __restrict__ neff2, int* __restrict__ n_early) {
+  const int pair = blockIdx.x, n = neff[pair];
+  bool full = false;
+  if (n >= 8)
+    for (int h = threadIdx.x; h < h1; h += blockDim.x) full |= counts[(size_t)pair * H + h] == n;
+  const int any = __syncthreads_or(full ? 1 : 0);
+  if (threadIdx.x == 0) {
+    neff2[pair] = any ? 0 : n;
+    if (any) atomicAdd(n_early, 1);
+  }
 }
 
 // status (0 skipped by min_points, 1 no pose: n < 8 or best < min_inliers, 2 pose wanted) and the winner's hypothesis
@@ -191,7 +214,7 @@ void sfm_two_view_free(sfmgpu_ctx* ctx, sfmgpu_pairs* p) {
   (void)ctx;
   TwoViewState* tv = p->tv;
   if (!tv) return;
-  void* ptrs[] = {tv->xi, tv->xj, tv->inl, tv->neff, tv->status, tv->best, tv->bestE, tv->R, tv->t, tv->flags, tv->idx8.p, tv->E.p, tv->counts.p, tv->raw.p};
+  void* ptrs[] = {tv->xi, tv->xj, tv->inl, tv->neff, tv->status, tv->best, tv->bestE, tv->R, tv->t, tv->flags, tv->idx8.p, tv->E.p, tv->counts.p, tv->neff2.p, tv->raw.p};
   for (void* q : ptrs)
     if (q) cudaFree(q);
   delete tv;
@@ -215,6 +238,9 @@ int sfm_two_view_stage(sfmgpu_ctx* ctx, sfmgpu_pairs* p, int pair_off, int npair
   }
   const int mp = rc.min_points > 0 ? rc.min_points : 0;
   const int screen = (!E_host && H > 0 && sfm_solver_screens(ctx, chunk, H)) ? 1 : 0;  // see solver.cu: eight_point_qr_kernel
+  // early stop: the device solver's own hypotheses, more than one probe's worth of them, not the whole-set test solver
+  const bool early = ctx->rs_early && !E_host && H > 2 * TV_EARLY_H && ctx->solver_mode != 2;
+  if (early) SFM_TRY(sfm_reserve(ctx, tv->neff2, (size_t)chunk * sizeof(int)));
   const double* k = tv->Kinv;
   for (int c0 = 0; c0 < npairs; c0 += chunk) {
     const int pc = npairs - c0 < chunk ? npairs - c0 : chunk, po = pair_off + c0;
@@ -228,12 +254,30 @@ int sfm_two_view_stage(sfmgpu_ctx* ctx, sfmgpu_pairs* p, int pair_off, int npair
       } else {
         SFM_LAUNCH(ctx, tv_sample_kernel, pc, 1024, 0, (const unsigned*)tv->raw.p, tv->raw_n, (const int*)(tv->neff + po), 0, H * 8,
                    (int*)tv->idx8.p, tv->flags);
-        SFM_TRY(sfm_eight_point_batched(ctx, tv->xi + so, tv->xj + so, (size_t)cap, tv->neff + po, 0, pc, (const int*)tv->idx8.p, H,
-                                        (double*)tv->E.p, screen));
+        if (!early)
+          SFM_TRY(sfm_eight_point_batched(ctx, tv->xi + so, tv->xj + so, (size_t)cap, tv->neff + po, 0, pc, (const int*)tv->idx8.p, H,
+                                          (double*)tv->E.p, screen));
       }
     }
-    SFM_TRY(sfm_ransac_score_batched(ctx, tv->xi + so, tv->xj + so, (size_t)cap, tv->neff + po, cap, pc, (double*)tv->E.p, H, rc.thr,
-                                     (int*)tv->counts.p, tv->best + 2 * po, tv->inl + so, screen ? (const int*)tv->idx8.p : nullptr));
+    if (early) {
+      // (the octets above are sampled for all H hypotheses: cheap, and the winner's octet is needed either way)
+      const int scr = screen && sfm_solver_screens(ctx, pc, H);  // one decision for both parts of the set
+      const double2 *cxi = tv->xi + so, *cxj = tv->xj + so;
+      int* n2 = (int*)tv->neff2.p;
+      SFM_CUDA(ctx, cudaMemsetAsync(tv->counts.p, 0, (size_t)pc * H * sizeof(int), ctx->stream));
+      SFM_TRY(sfm_eight_point_range(ctx, cxi, cxj, (size_t)cap, tv->neff + po, 0, pc, (const int*)tv->idx8.p, H, 0, TV_EARLY_H, (double*)tv->E.p, scr));
+      SFM_TRY(sfm_ransac_count_range(ctx, cxi, cxj, (size_t)cap, tv->neff + po, cap, pc, (const double*)tv->E.p, H, 0, TV_EARLY_H, rc.thr,
+                                     (int*)tv->counts.p));
+      SFM_LAUNCH(ctx, tv_early_kernel, pc, 128, 0, (const int*)tv->counts.p, H, TV_EARLY_H, (const int*)(tv->neff + po), n2, tv->flags + 1);
+      SFM_TRY(sfm_eight_point_range(ctx, cxi, cxj, (size_t)cap, (const int*)n2, 0, pc, (const int*)tv->idx8.p, H, TV_EARLY_H, H, (double*)tv->E.p, scr));
+      SFM_TRY(sfm_ransac_count_range(ctx, cxi, cxj, (size_t)cap, (const int*)n2, cap, pc, (const double*)tv->E.p, H, TV_EARLY_H, H, rc.thr,
+                                     (int*)tv->counts.p));
+      SFM_TRY(sfm_ransac_finish(ctx, cxi, cxj, (size_t)cap, tv->neff + po, cap, pc, (double*)tv->E.p, H, rc.thr, (const int*)tv->counts.p,
+                                tv->best + 2 * po, tv->inl + so, screen ? (const int*)tv->idx8.p : nullptr));
+    } else {
+      SFM_TRY(sfm_ransac_score_batched(ctx, tv->xi + so, tv->xj + so, (size_t)cap, tv->neff + po, cap, pc, (double*)tv->E.p, H, rc.thr,
+                                       (int*)tv->counts.p, tv->best + 2 * po, tv->inl + so, screen ? (const int*)tv->idx8.p : nullptr));
+    }
     SFM_LAUNCH(ctx, tv_finalize_kernel, sfm_cdiv(pc, 128), 128, 0, (const int*)(p->nkept + po), (const int*)(tv->neff + po),
                (const int*)(tv->best + 2 * po), (const double*)tv->E.p, Hs, pc, mp, rc.min_inliers, tv->status + po, tv->bestE + 9 * (size_t)po);
     SFM_TRY(sfm_pose_batched(ctx, tv->xi + so, tv->xj + so, (size_t)cap, pc, tv->status + po, tv->best + 2 * po, tv->inl + so,
@@ -287,6 +331,25 @@ int sfmgpu_pairs_set_ransac(sfmgpu_ctx* ctx, sfmgpu_pairs* p, const double* K, c
   p->tv->rc = *rc;
   for (int i = 0; i < 9; i++) p->tv->Kinv[i] = Ki[i];
   p->tv->enabled = true;
+  return 0;
+}
+
+int sfmgpu_ransac_set_early_stop(sfmgpu_ctx* ctx, int on) {
+  if (!ctx) return SFMGPU_E_ARG;
+  ctx->rs_early = on ? 1 : 0;
+  return 0;
+}
+
+int sfmgpu_pairs_ransac_early(sfmgpu_ctx* ctx, sfmgpu_pairs* p, long long* pairs_stopped) {
+  SFM_ENTER(ctx);
+  if (!ctx || !p || !pairs_stopped) return sfm_fail(ctx, SFMGPU_E_ARG, "pairs_ransac_early: null pointer");
+  *pairs_stopped = 0;
+  if (!p->tv) return 0;
+  int v = 0;
+  SFM_CUDA(ctx, cudaMemcpyAsync(&v, p->tv->flags + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  SFM_CUDA(ctx, cudaMemsetAsync(p->tv->flags + 1, 0, 4, ctx->stream));
+  SFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *pairs_stopped = v;
   return 0;
 }
 

@@ -37,7 +37,7 @@ SYMBOLS = [
     "sfmgpu_ransac_hypotheses", "sfmgpu_ransac_solve_score", "sfmgpu_solver_set_mode", "sfmgpu_global_desc32", "sfmgpu_desc_search", "sfmgpu_triangulate_dlt",
     "sfmgpu_stage_times_n", "sfmgpu_pairs_set_ransac", "sfmgpu_pairs_ransac_host_outputs", "sfmgpu_pairs_ransac",
     "sfmgpu_pairs_ransac_download", "sfmgpu_pairs_ransac_download_all", "sfmgpu_pairs_ransac_device_ptrs", "sfmgpu_ransac_sample",
-    "sfmgpu_pairs_set_matches",
+    "sfmgpu_pairs_set_matches", "sfmgpu_ransac_set_early_stop", "sfmgpu_pairs_ransac_early",
     "sfmgpu_sched_shard", "sfmgpu_sched_unique_id", "sfmgpu_sched_create", "sfmgpu_sched_destroy", "sfmgpu_sched_pair_shard",
     "sfmgpu_sched_gather_pairs", "sfmgpu_frames_device_ptr", "sfmgpu_multitracker_reset",
 ]
@@ -143,6 +143,8 @@ def load_library():
         "sfmgpu_ransac_hypotheses": (_i, [_vp, _f64p, _f64p, _i, _i32p, _i, _vp]),
         "sfmgpu_ransac_solve_score": (_i, [_vp, _f64p, _f64p, _i, _vp, _i, _d, C.POINTER(_i), C.POINTER(_i), _vp, _vp]),
         "sfmgpu_solver_set_mode": (_i, [_vp, _i]),
+        "sfmgpu_ransac_set_early_stop": (_i, [_vp, _i]),
+        "sfmgpu_pairs_ransac_early": (_i, [_vp, _vp, C.POINTER(_ll)]),
         "sfmgpu_stage_times_n": (_i, [_vp, C.POINTER(C.c_float), _i]),
         "sfmgpu_pairs_set_ransac": (_i, [_vp, _vp, _vp, C.POINTER(RansacCfg)]),
         "sfmgpu_pairs_ransac_host_outputs": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -222,6 +224,10 @@ class Context:
         for the winner, 0 the Jacobi emulation for every hypothesis, 2 the same through the warp-per-hypothesis kernel,
         3 screening for every launch (2, 3: tests)."""
         self._ck(self.lib.sfmgpu_solver_set_mode(self.h, mode))
+
+    def ransac_set_early_stop(self, on):
+        """Batched RANSAC stage: stop solving / scoring a pair once a hypothesis explains all of its points (default on, exact)."""
+        self._ck(self.lib.sfmgpu_ransac_set_early_stop(self.h, 1 if on else 0))
 
     def timer_start(self):
         self._ck(self.lib.sfmgpu_timer_start(self.h))
@@ -551,6 +557,12 @@ class Pairs:
         if E_host is not None:
             E_host = np.ascontiguousarray(E_host, np.float64)
         self.ctx._ck(self.ctx.lib.sfmgpu_pairs_ransac(self.ctx.h, self.h_, K, C.byref(rc), _ptr(E_host)))
+
+    def ransac_early(self):
+        """Pairs whose scoring stopped early (a hypothesis explained all points) since the last call; resets the counter."""
+        v = _ll(0)
+        self.ctx._ck(self.ctx.lib.sfmgpu_pairs_ransac_early(self.ctx.h, self.h_, C.byref(v)))
+        return int(v.value)
 
     def ransac_download(self, pair):
         """(status, best_h, inlier indices, E [3,3], R [3,3], t [3]) of one pair."""

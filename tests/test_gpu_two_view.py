@@ -279,3 +279,65 @@ def test_pair_frontend_with_ransac_stage(ctx, checker, streaming):
     for p in range(5):
         if st[p] == 2:
             assert np.array_equal(inl[p, :bn[p]], inl2[p, :bn2[p]])
+
+
+@pytest.mark.parametrize("solver_mode", [1, 3, 0])
+@pytest.mark.parametrize("iters,thr,min_pts", [(4000, 2e-3, 120), (300, 2e-3, 120), (4000, 1e-6, 9), (4000, 6e-7, 9)])
+def test_pairs_ransac_early_stop_is_exact(ctx, checker, iters, thr, min_pts, solver_mode):
+    """The early stop of the batched stage (a pair leaves the launch set once one of its first 128 hypotheses explains all
+    of its points: nothing later can win, :673) against the same stage with every hypothesis solved and scored: status,
+    winner, count, inlier list, E, R, t bit-identical on a batch that mixes outlier-free sets with contaminated, tiny and
+    skipped ones.  thr 2e-3 (the reference's): hypothesis 0 explains every outlier-free set; 1e-6: the first full hypothesis
+    sits at 0 ... 51; 6e-7: at 1, 103 (stopped), 155, 224, 355 (beyond the probe: scored to the end, the full count
+    still wins) or nowhere.  At the reference's threshold also against find_E_ransac."""
+    K = TEMPLE_K
+    min_inl = 80
+    scenes = _scenes()
+    for n, seed in ((500, 21), (2500, 22), (130, 23), (1200, 24), (60, 25), (300, 26)):  # no outliers, 0.3 px noise
+        pi, pj = two_view_scene(n, seed=seed, outlier_frac=0.0)
+        scenes.insert(len(scenes) // 2, (pi, pj))
+    P = len(scenes)
+    res = {}
+    ctx.solver_set_mode(solver_mode)
+    try:
+        for early in (1, 0):
+            ctx.ransac_set_early_stop(early)
+            pairs = ctx.pairs(P, 2500)
+            pairs.set_matches([s[0] for s in scenes], [s[1] for s in scenes])
+            pairs.ransac_early()
+            pairs.ransac(K, iters, thr, min_inl, min_pts)
+            stopped = pairs.ransac_early()
+            st, bn = np.zeros(P, np.int32), np.zeros(P, np.int32)
+            inl, R, t = np.zeros((P, 2500), np.int32), np.zeros((P, 9)), np.zeros((P, 3))
+            pairs.ransac_download_all(st, bn, inl, R, t)
+            one = [pairs.ransac_download(k) for k in range(P)]
+            res[early] = (stopped, st, bn, inl, R, t, one)
+    finally:
+        ctx.ransac_set_early_stop(1)
+        ctx.solver_set_mode(1)
+    s1, st1, bn1, inl1, R1, t1, one1 = res[1]
+    s0, st0, bn0, inl0, R0, t0, one0 = res[0]
+    assert s0 == 0
+    assert np.array_equal(st1, st0) and np.array_equal(bn1, bn0)
+    okp = st1 == 2  # R, t of pairs without a pose are not written (the two runs use different pairs objects)
+    assert okp.sum() >= 6 and np.array_equal(R1[okp], R0[okp]) and np.array_equal(t1[okp], t0[okp])
+    full = 0
+    for k in range(P):
+        a, b = one1[k], one0[k]
+        assert a[0] == b[0], k
+        if st1[k] == 2:
+            assert a[1] == b[1] and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3]), k
+            assert np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5]), k
+            assert np.array_equal(inl1[k, :bn1[k]], inl0[k, :bn0[k]]), k
+            full += int(bn1[k] == len(scenes[k][0]) and a[1] < 128)
+    print(f"iters {iters} thr {thr} mode {solver_mode}: {s1} of {P} pairs stopped early, {full} valid poses with a full count in the probe")
+    assert full >= 1 and 1 <= s1 <= P, (full, s1)
+    if solver_mode == 0:  # exact counts of the emulation's hypotheses decide both the stop and the final count
+        assert full <= s1, (full, s1)
+    if thr == 2e-3:
+        assert full >= 4
+        want = _reference_results(checker, K, scenes, iters, thr, min_inl, min_pts)
+        for k, (wst, wr) in enumerate(want):
+            assert st1[k] == wst, k
+            if wst == 2:
+                assert bn1[k] == len(wr[2]) and np.array_equal(inl1[k, :bn1[k]], wr[2]), k
