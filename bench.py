@@ -15,7 +15,10 @@ attached to the line as "c2".
 metric  : KLT feature-tracks/s (1 feature-track = fwd + bwd track_one + fb test of one corner) for the
           whole unit incl. its RANSAC stage; the RANSAC half of BASELINE.json's metric (hyp x pts / s, config C4) is
           reported under "ransac".
-value   : frames resident in HBM, CUDA events on the library's stream, max over ranks.
+value   : frames resident in HBM, CUDA events on the library's stream, max over ranks.  The library's default path: the
+          RANSAC stage stops solving / scoring a pair - exactly - once one of its first 128 hypotheses explains all of its
+          points; "ransac_early_stop" reports the fraction of pairs stopped and the same step with the stop
+          off (every hypothesis of every pair solved and scored, as the reference does) as "full_scoring".
 e2e     : the same step through the C ABI with HOST (pinned) frames: H2D of the frames and D2H of tracks, inlier sets and
           poses inside the timed region (N > 1: plus the NCCL gather to rank 0, which then reads everything back).
 parity_in_bench : the reference (oracle/_ref) runs the same unit on sample pairs of the same frames on the host; corner
